@@ -1,0 +1,37 @@
+"""neuronx_distributed_b200 — a Blackwell-native tensor/pipeline-parallel training and inference
+library with the capabilities and public API of aws-neuron/neuronx-distributed.
+
+Top-level exports mirror reference ``src/neuronx_distributed/__init__.py:1-19``.
+"""
+from . import utils  # noqa: F401
+from . import ops  # noqa: F401
+from . import parallel_layers  # noqa: F401
+from .trainer.trainer import (  # noqa: F401
+    initialize_parallel_model,
+    initialize_parallel_optimizer,
+    neuronx_distributed_config,
+)
+
+__version__ = "0.1.0"
+
+
+def __getattr__(name):
+    # heavier sub-systems are imported lazily so `import neuronx_distributed_b200` stays cheap
+    import importlib
+
+    lazy = {
+        "pipeline": ".pipeline", "kernels": ".kernels", "trace": ".inference", "inference": ".inference",
+        "modules": ".modules", "models": ".models", "optimizer": ".optimizer", "trainer": ".trainer",
+        "quantization": ".quantization", "operators": ".operators", "lightning": ".lightning",
+    }
+    if name in lazy:
+        return importlib.import_module(lazy[name], __name__)
+    ckpt = {"save_checkpoint", "load_checkpoint", "has_checkpoint", "finalize_checkpoint", "CheckpointIOState"}
+    if name in ckpt:
+        mod = importlib.import_module(".trainer.checkpoint", __name__)
+        return getattr(mod, name)
+    inf = {"ModelBuilder", "NxDModel", "BaseNxDModel", "shard_checkpoint", "NxDParallelState"}
+    if name in inf:
+        mod = importlib.import_module(".inference", __name__)
+        return getattr(mod, name)
+    raise AttributeError(name)

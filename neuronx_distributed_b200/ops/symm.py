@@ -1,0 +1,112 @@
+"""Symmetric (peer-mapped) device memory for in-kernel NVLink communication.
+
+Native part: ``csrc/symm.cpp`` — ``cudaMalloc`` + CUDA-IPC handle exchange; every rank ends up
+with a table of device pointers to all peers' buffers plus a flags region, which the fused
+GEMM+collective kernels (``csrc/gemm_sm100.cu``) and the ZeRO-1 reduce-scatter kernel dereference
+directly (P2P ld/st over NVSwitch).  Handles travel over the gloo control group.
+
+A :class:`SymmWorkspace` is created lazily per (process group, purpose) and reused; kernels use
+monotonically increasing epochs with double-buffered payload so no extra barrier is needed
+between consecutive calls (see DESIGN.md §symmetric memory protocol).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _ext
+
+_WORKSPACES: Dict[Tuple[int, str], "SymmWorkspace"] = {}
+
+
+def reset() -> None:
+    for ws in list(_WORKSPACES.values()):
+        ws.close()
+    _WORKSPACES.clear()
+
+
+def available() -> bool:
+    e = _ext.ext()
+    return e is not None and hasattr(e, "symm_alloc") and torch.cuda.is_available()
+
+
+@dataclass
+class SymmWorkspace:
+    """``nbytes`` of payload + ``nflags`` 32-bit flags on every rank of ``group``; ``ptrs``/``flag_ptrs``
+    are device-resident tables (int64) of all ranks' base addresses, indexed by group rank."""
+
+    group: object
+    rank: int
+    world: int
+    nbytes: int
+    nflags: int
+    handle: int = 0                       # native handle id
+    ptrs: Optional[torch.Tensor] = None   # [world] int64 on device
+    flag_ptrs: Optional[torch.Tensor] = None
+    local_ptr: int = 0
+    local_flag_ptr: int = 0
+    epoch: Dict[str, int] = field(default_factory=dict)
+
+    def next_epoch(self, key: str) -> int:
+        self.epoch[key] = self.epoch.get(key, 0) + 1
+        return self.epoch[key]
+
+    def local_tensor(self, offset: int, shape, dtype) -> torch.Tensor:
+        """A torch view over this rank's payload (for debugging / eager reads)."""
+        return _ext.ext().symm_view(self.handle, int(offset), list(shape), dtype)
+
+    def close(self) -> None:
+        if self.handle:
+            try:
+                _ext.ext().symm_free(self.handle)
+            except Exception:
+                pass
+            self.handle = 0
+
+
+def _control_group_for(group):
+    """gloo group with the same membership as ``group`` for handle exchange."""
+    from ..parallel_layers import parallel_state as ps
+
+    ranks = dist.get_process_group_ranks(group)
+    key = ("symm_ctl", tuple(ranks))
+    cache = getattr(_control_group_for, "_cache", {})
+    _control_group_for._cache = cache
+    if key not in cache:
+        # every rank of the WORLD must participate in new_group; callers guarantee collective use
+        cache[key] = None
+    return ranks
+
+
+def get_workspace(group, purpose: str, nbytes: int, nflags: int = 4096) -> SymmWorkspace:
+    """Collective over ``group``: allocate (or fetch) a symmetric workspace of at least ``nbytes``."""
+    key = (id(group), purpose)
+    ws = _WORKSPACES.get(key)
+    if ws is not None and ws.nbytes >= nbytes and ws.nflags >= nflags:
+        return ws
+    if ws is not None:
+        ws.close()
+    e = _ext.ext()
+    assert e is not None, "symmetric memory needs the CUDA extension"
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nbytes = (int(nbytes) + (1 << 21) - 1) & ~((1 << 21) - 1)
+    handle, ipc_payload, ipc_flags = e.symm_alloc(nbytes, int(nflags))
+    gathered: List[Optional[tuple]] = [None] * world
+    dist.all_gather_object(gathered, (os.getpid(), ipc_payload, ipc_flags), group=group)
+    ptrs, flag_ptrs = e.symm_open(handle, rank, [g[1] for g in gathered], [g[2] for g in gathered])
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ws = SymmWorkspace(
+        group=group, rank=rank, world=world, nbytes=nbytes, nflags=nflags, handle=handle,
+        ptrs=torch.tensor(ptrs, dtype=torch.int64, device=dev),
+        flag_ptrs=torch.tensor(flag_ptrs, dtype=torch.int64, device=dev),
+        local_ptr=ptrs[rank], local_flag_ptr=flag_ptrs[rank],
+    )
+    # nobody may touch a peer buffer before every rank has mapped everything
+    torch.cuda.synchronize()
+    dist.barrier(group=group)
+    _WORKSPACES[key] = ws
+    return ws

@@ -1,0 +1,169 @@
+"""Collective wrappers used by the cold paths and the ``nccl`` (library) backend.
+
+Same surface as reference ``parallel_layers/comm.py:124-220`` (``all_reduce`` accepting a tensor
+*bucket*, ``all_gather``/``reduce_scatter`` along an arbitrary dim).  On CUDA these are NCCL
+calls issued through ``torch.distributed``; in CPU mode they run on gloo, which lacks
+reduce-scatter, so that one is emulated (all-reduce + local slice — simpler and deterministic
+compared with the reference's reduce-to-root + scatter :82-121).
+
+The hot tensor-parallel paths do NOT go through this file on B200: they use the fused
+GEMM+collective kernels in ``ops/tp_fused.py``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Union
+
+import torch
+import torch.distributed as dist
+
+from . import parallel_state as ps
+
+_REDUCE_OPS = {
+    "sum": dist.ReduceOp.SUM,
+    "max": dist.ReduceOp.MAX,
+    "min": dist.ReduceOp.MIN,
+    "avg": dist.ReduceOp.SUM,  # divided afterwards: gloo has no AVG
+    "product": dist.ReduceOp.PRODUCT,
+}
+
+
+def _tp(group):
+    return group if group is not None else ps.get_tensor_model_parallel_group()
+
+
+def _is_gloo(group) -> bool:
+    try:
+        return dist.get_backend(group) == "gloo"
+    except Exception:
+        return False
+
+
+def group_size(group=None) -> int:
+    return dist.get_world_size(_tp(group))
+
+
+def group_rank(group=None) -> int:
+    return dist.get_rank(_tp(group))
+
+
+def all_reduce(
+    tensors: Union[torch.Tensor, Sequence[torch.Tensor]],
+    op: str = "sum",
+    group=None,
+    async_op: bool = False,
+):
+    """In-place all-reduce of a tensor or a bucket (list) of tensors.
+
+    A bucket is flattened into one buffer so a single collective is launched
+    (reference comm.py:200-220 coalesces likewise)."""
+    group = _tp(group)
+    rop = _REDUCE_OPS[op]
+    n = dist.get_world_size(group)
+    if isinstance(tensors, torch.Tensor):
+        if n == 1:
+            return None if async_op else tensors
+        work = dist.all_reduce(tensors, op=rop, group=group, async_op=async_op)
+        if op == "avg":
+            assert not async_op
+            tensors.div_(n)
+        return work if async_op else tensors
+    tensors = list(tensors)
+    if not tensors or n == 1:
+        return tensors
+    assert not async_op, "bucketed all_reduce is synchronous"
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=rop, group=group)
+    if op == "avg":
+        flat.div_(n)
+    off = 0
+    for t in tensors:
+        t.copy_(flat[off : off + t.numel()].view_as(t))
+        off += t.numel()
+    return tensors
+
+
+def all_gather(x: torch.Tensor, dim: int = 0, group=None) -> torch.Tensor:
+    """Concatenate every rank's ``x`` along ``dim``."""
+    group = _tp(group)
+    n = dist.get_world_size(group)
+    if n == 1:
+        return x
+    if x.dim() == 0:
+        x = x.view(1)
+    dim = dim % x.dim()
+    xc = x.contiguous()
+    out = torch.empty((n,) + tuple(xc.shape), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out.view(-1, *xc.shape[1:]), xc, group=group)
+    if dim == 0:
+        return out.view(n * xc.shape[0], *xc.shape[1:])
+    # [n, d0, ..., dk, ...] -> move n in front of dk and merge
+    out = out.movedim(0, dim)  # [..., n, dk, ...]
+    shape = list(xc.shape)
+    shape[dim] = n * shape[dim]
+    return out.reshape(shape)
+
+
+def reduce_scatter(x: torch.Tensor, dim: int = 0, group=None, op: str = "sum") -> torch.Tensor:
+    """Sum ``x`` over the group and return this rank's 1/n slice along ``dim``."""
+    group = _tp(group)
+    n = dist.get_world_size(group)
+    if n == 1:
+        return x
+    dim = dim % x.dim()
+    assert x.shape[dim] % n == 0, f"dim {dim} of {tuple(x.shape)} not divisible by group size {n}"
+    r = dist.get_rank(group)
+    if _is_gloo(group):
+        full = x.contiguous().clone()
+        dist.all_reduce(full, op=_REDUCE_OPS[op], group=group)
+        out = full.chunk(n, dim=dim)[r].contiguous()
+    else:
+        xin = x if dim == 0 else x.movedim(dim, 0)
+        xin = xin.contiguous()
+        out = torch.empty((xin.shape[0] // n,) + tuple(xin.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.reduce_scatter_tensor(out, xin, op=_REDUCE_OPS[op], group=group)
+        if dim != 0:
+            out = out.movedim(0, dim).contiguous()
+    if op == "avg":
+        out = out / n
+    return out
+
+
+def all_to_all(x: torch.Tensor, split_dim: int, concat_dim: int, group=None) -> torch.Tensor:
+    """Split ``x`` into n pieces along ``split_dim``, exchange, concatenate along ``concat_dim``
+    (semantics of ``xm.all_to_all`` used at reference mappings.py:160-172)."""
+    group = group if group is not None else ps.get_expert_model_parallel_group()
+    n = dist.get_world_size(group)
+    if n == 1:
+        return x
+    pieces = [p.contiguous() for p in x.chunk(n, dim=split_dim)]
+    outs = [torch.empty_like(pieces[0]) for _ in range(n)]
+    if _is_gloo(group):
+        # gloo all_to_all support is uneven across versions → use all_gather of the stacked pieces
+        stacked = torch.stack(pieces)  # [n, ...]
+        gathered = [torch.empty_like(stacked) for _ in range(n)]
+        dist.all_gather(gathered, stacked, group=group)
+        r = dist.get_rank(group)
+        outs = [gathered[src][r] for src in range(n)]
+    else:
+        dist.all_to_all(outs, pieces, group=group)
+    return torch.cat(outs, dim=concat_dim)
+
+
+def broadcast(x: torch.Tensor, src: int, group=None) -> torch.Tensor:
+    group = _tp(group)
+    if dist.get_world_size(group) > 1:
+        dist.broadcast(x, src=src, group=group)
+    return x
+
+
+def barrier(group=None) -> None:
+    if dist.is_initialized():
+        dist.barrier(group=group)
+
+
+def send(x: torch.Tensor, dst: int, group=None):
+    return dist.send(x.contiguous(), dst=dst, group=group)
+
+
+def recv(x: torch.Tensor, src: int, group=None):
+    return dist.recv(x, src=src, group=group)

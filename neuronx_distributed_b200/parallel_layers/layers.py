@@ -1,0 +1,810 @@
+"""Tensor-parallel layers.
+
+Capability parity with reference ``parallel_layers/layers.py`` (``ParallelEmbedding`` :186,
+``LinearWithAsyncCommunication`` :434, ``ColumnParallelLinear`` :561, ``RowParallelLinear``
+:815, conv layers :1309/:1432, ``SPMDRank`` :1543) and ``layers_utils.py:16-140``.
+
+B200 design notes
+-----------------
+* A TP linear is ONE autograd node (:class:`_TPLinear`) covering gather → GEMM → reduce in
+  both directions, so the forward and backward each map to a single fused GEMM+collective
+  kernel (``ops/tp_fused.py``: AG→GEMM, GEMM→RS, GEMM→AR over NVLink peer memory) instead of
+  an autograd chain of separate collective and matmul nodes.  The same node falls back to
+  NCCL/gloo collectives + ``torch.matmul`` for CPU mode, unsupported shapes/dtypes, and the
+  ``nccl`` baseline backend.
+* Weight init is TP-degree independent: build the full fp32 master weight from the default
+  RNG, cast, keep this rank's (strided) slice.
+* Row-parallel reductions honour ``reduce_dtype`` (fp32 default, as the reference) on the
+  library path; the fused path accumulates in fp32 and moves bf16 on the wire (documented in
+  DESIGN.md).
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Any, Callable, Dict, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+from torch.nn import init
+from torch.nn.parameter import Parameter
+
+from ..utils import cpu_mode, get_device
+from ..utils.logger import get_logger
+from . import comm, mappings
+from . import parallel_state as ps
+from .random import get_rng_tracker
+from .utils import (
+    EmbeddingUtility,
+    create_local_weight,
+    divide,
+    set_tensor_model_parallel_attributes,
+)
+
+logger = get_logger()
+
+_SP_ATTR = "sequence_parallel_enabled"
+
+
+def _tag_sequence_parallel(param: torch.Tensor, enabled: bool) -> None:
+    setattr(param, _SP_ATTR, enabled)
+
+
+def get_padding_length(size: int, multiple: int) -> int:
+    return (-size) % multiple
+
+
+# --------------------------------------------------------------------------------------
+# parameter initialisation
+# --------------------------------------------------------------------------------------
+def _initialize_parameter_from_master(
+    param: torch.Tensor,
+    partition_dim: int,
+    num_partitions: int,
+    init_method: Callable[[torch.Tensor], Any],
+    return_master_param: bool = False,
+    param_dtype: torch.dtype = torch.float32,
+    stride: int = 1,
+    rank: Optional[int] = None,
+) -> Optional[torch.Tensor]:
+    """Initialise the *full* fp32 weight (identical on all ranks) and copy this rank's slice
+    into ``param`` — results do not depend on the TP degree (reference layers.py:111-164)."""
+    set_tensor_model_parallel_attributes(param, True, partition_dim, stride, num_partitions)
+    if ps.get_aot_mode() or param.device.type == "meta":
+        return None
+    shape = list(param.shape)
+    shape[partition_dim] *= num_partitions
+    master = torch.empty(shape, dtype=torch.float32)
+    init_method(master)
+    master = master.to(param_dtype)
+    with torch.no_grad():
+        local = create_local_weight(
+            master, partition_dim, param.shape[partition_dim], stride, rank=rank, world_size=num_partitions
+        )
+        param.copy_(local.to(param.device))
+    return master if return_master_param else None
+
+
+def _initialize_parameter_sharded(
+    param: torch.Tensor, partition_dim: int, num_partitions: int, init_method, stride: int = 1
+) -> None:
+    """Initialise only the local shard under the TP-forked RNG stream (cheaper; results depend
+    on TP degree) — reference ``_initialize_affine_weight_neuron`` layers.py:60-84."""
+    set_tensor_model_parallel_attributes(param, True, partition_dim, stride, num_partitions)
+    if param.device.type == "meta":
+        return
+    with get_rng_tracker().fork():
+        init_method(param)
+
+
+class BaseParallelLayer(nn.Module):
+    """Brings up a single-rank parallel state if the user never initialised one
+    (reference layers.py:167-183)."""
+
+    def __init__(self, device: Optional[torch.device] = None):
+        super().__init__()
+        if not ps.model_parallel_is_initialized():
+            warnings.warn("parallel state is not initialized; falling back to a single-rank world")
+            ps.initialize_fallback_parallel_state()
+
+
+def _group_info(group) -> Tuple[Any, int, int]:
+    group = group if group is not None else ps.get_tensor_model_parallel_group()
+    return group, dist.get_world_size(group), dist.get_rank(group)
+
+
+# --------------------------------------------------------------------------------------
+# SPMDRank
+# --------------------------------------------------------------------------------------
+class SPMDRank(nn.Module):
+    """Holds this rank's index as a *weight* so one captured program can be replayed on all
+    ranks with only the weights differing (reference layers.py:1543-1603)."""
+
+    def __init__(self, world_size: int, tensor_model_parallel_size: Optional[int] = None):
+        super().__init__()
+        self.world_size = world_size
+        tp = tensor_model_parallel_size or world_size
+        self.rank = Parameter(torch.zeros(1, dtype=torch.int32), requires_grad=False)
+        set_tensor_model_parallel_attributes(self.rank, True, 0, 1, num_partitions=tp)
+        try:
+            self.rank.data.fill_(ps.get_tensor_model_parallel_rank())
+        except AssertionError:
+            pass
+
+    def get_rank(self) -> torch.Tensor:
+        return self.rank
+
+    def forward(self) -> torch.Tensor:
+        return self.rank
+
+    def preshard_hook(self, model_state_dict: Dict[str, Any], prefix: str) -> None:
+        # full tensor is arange(world) so that sharding dim 0 hands every rank its id
+        key = prefix if prefix.endswith("rank") else prefix + "rank"
+        model_state_dict[key] = torch.arange(0, self.world_size, dtype=torch.int32)
+
+
+# --------------------------------------------------------------------------------------
+# Embedding
+# --------------------------------------------------------------------------------------
+class ParallelEmbedding(BaseParallelLayer):
+    """Embedding sharded along the vocabulary (default) or the embedding dim.
+
+    Vocab sharding: ids outside ``[start, end)`` are looked up as row 0 and zeroed, then the
+    partial embeddings are summed across TP — by all-reduce, or by reduce-scatter straight into
+    the sequence-parallel ``[S/tp, B, H]`` layout (reference layers.py:334-378)."""
+
+    def __init__(
+        self,
+        num_embeddings: int,
+        embedding_dim: int,
+        padding_idx: Optional[int] = None,
+        max_norm: Optional[float] = None,
+        norm_type: float = 2.0,
+        scale_grad_by_freq: bool = False,
+        sparse: bool = False,
+        init_method: Callable[[Any], Any] = init.normal_,
+        device: Optional[torch.device] = None,
+        dtype: torch.dtype = torch.float32,
+        shard_across_embedding: bool = False,
+        pad: bool = False,
+        sequence_parallel_enabled: bool = False,
+        tensor_model_parallel_group=None,
+        use_spmd_rank: bool = False,
+        sequence_dimension: Optional[int] = None,
+        tile_cc: bool = False,
+        rank_ordering: Optional[Sequence[int]] = None,
+        collect_output: bool = True,
+    ):
+        super().__init__(device=device)
+        self.num_embeddings, self.embedding_dim = num_embeddings, embedding_dim
+        self.padding_idx, self.max_norm, self.norm_type = padding_idx, max_norm, norm_type
+        self.scale_grad_by_freq, self.sparse = scale_grad_by_freq, sparse
+        self.tensor_model_parallel_group, self.tensor_model_parallel_size, tp_rank = _group_info(
+            tensor_model_parallel_group
+        )
+        self.shard_across_embedding = shard_across_embedding
+        self.pad, self.pad_size = pad, 0
+        self.sequence_parallel_enabled = sequence_parallel_enabled
+        self.sequence_dim = sequence_dimension
+        self.rank_ordering = rank_ordering
+        self.collect_output = collect_output
+        self.dtype, self.init_method, self.stride = dtype, init_method, 1
+        self.rank_util = SPMDRank(self.tensor_model_parallel_size) if use_spmd_rank else None
+        tp = self.tensor_model_parallel_size
+        if shard_across_embedding:
+            if pad:
+                self.pad_size = get_padding_length(embedding_dim, tp)
+                self.embedding_dim += self.pad_size
+            self.num_embeddings_per_partition = num_embeddings
+            self.embedding_dim_per_partition = divide(self.embedding_dim, tp)
+            self.weight_partition_dim = 1
+            shape = (num_embeddings, self.embedding_dim_per_partition)
+        else:
+            if pad:
+                self.pad_size = get_padding_length(num_embeddings, tp)
+                self.num_embeddings += self.pad_size
+            self.start_index, self.end_index = EmbeddingUtility.range_from_global_vocab_size(
+                self.num_embeddings, tp_rank, tp
+            )
+            self.num_embeddings_per_partition = self.end_index - self.start_index
+            self.embedding_dim_per_partition = embedding_dim
+            self.weight_partition_dim = 0
+            shape = (self.num_embeddings_per_partition, embedding_dim)
+        device = device if device is not None else torch.device("cpu")
+        self.weight = Parameter(torch.empty(*shape, device=device, dtype=dtype))
+        _initialize_parameter_from_master(
+            self.weight, self.weight_partition_dim, tp, init_method, param_dtype=dtype, rank=tp_rank
+        )
+        if rank_ordering is not None:
+            self.weight.rank_ordering = list(rank_ordering)
+
+    def _embed(self, ids: torch.Tensor) -> torch.Tensor:
+        return F.embedding(
+            ids.long(), self.weight, self.padding_idx, self.max_norm, self.norm_type, self.scale_grad_by_freq, self.sparse
+        )
+
+    def forward(self, input_: torch.Tensor) -> torch.Tensor:
+        if self.pad and self.training:
+            raise RuntimeError("`pad=True` is only supported for inference. Set model.eval()")
+        if self.shard_across_embedding:
+            out = self._embed(input_)
+            if self.collect_output:
+                out = mappings.gather_from_tensor_model_parallel_region(out, self.tensor_model_parallel_group)
+            if self.pad and self.pad_size > 0 and self.collect_output:
+                out = out.narrow(-1, 0, self.embedding_dim - self.pad_size)
+            return out
+        tp = self.tensor_model_parallel_size
+        if tp > 1:
+            if self.rank_util is not None:
+                start = self.num_embeddings_per_partition * self.rank_util.get_rank().to(input_.device).long()
+                end = start + self.num_embeddings_per_partition
+            else:
+                start, end = self.start_index, self.end_index
+            mask = (input_ >= start) & (input_ < end)
+            ids = (input_ - start) * mask
+        else:
+            mask, ids = None, input_
+        out = self._embed(ids)
+        if mask is not None:
+            out = out * mask.unsqueeze(-1).to(out.dtype)
+        if not self.collect_output:
+            return out
+        if self.sequence_parallel_enabled:
+            if self.sequence_dim is not None:
+                return mappings.reduce_scatter_to_sequence_parallel_region(
+                    out, self.sequence_dim, self.tensor_model_parallel_group
+                )
+            # default layout contract: [B, S] ids → [S/tp, B, H]
+            return mappings.reduce_scatter_to_sequence_parallel_region(
+                out.transpose(0, 1).contiguous(), 0, self.tensor_model_parallel_group
+            )
+        return mappings.reduce_from_tensor_model_parallel_region(out, self.tensor_model_parallel_group)
+
+    def preshard_hook(self, model_state_dict: Dict[str, Any], prefix: str) -> None:
+        """Pad a full (unsharded) checkpoint weight so it divides by tp (reference :404-431)."""
+        if not self.pad or self.pad_size == 0:
+            return
+        w = model_state_dict[prefix]
+        if self.shard_across_embedding:
+            if self.embedding_dim != w.shape[1] + self.pad_size:
+                raise RuntimeError(f"State dict {prefix} has unexpected shape {tuple(w.shape)}")
+            model_state_dict[prefix] = F.pad(w, (0, self.pad_size))
+        else:
+            if self.num_embeddings != w.shape[0] + self.pad_size:
+                raise RuntimeError(f"State dict {prefix} has unexpected shape {tuple(w.shape)}")
+            model_state_dict[prefix] = F.pad(w, (0, 0, 0, self.pad_size))
+
+
+# --------------------------------------------------------------------------------------
+# The single autograd node behind Column/Row linear layers
+# --------------------------------------------------------------------------------------
+def _flat2d(x: torch.Tensor) -> torch.Tensor:
+    return x.reshape(-1, x.shape[-1])
+
+
+class _TPLinear(torch.autograd.Function):
+    """``y = collective_out( collective_in(x) @ W^T )`` with its transposed backward.
+
+    modes (``in_mode`` → ``out_mode``):
+      * ``"gather"`` → ``"none"``   : Column + SP. fwd AG(seq)→GEMM ; bwd GEMM→RS(seq) + wgrad on re-gathered x
+      * ``"copy"``   → ``"none"``   : Column, no SP. fwd GEMM ; bwd GEMM→AR (overlapped with wgrad)
+      * ``"none"``   → ``"none"``   : plain linear on already-parallel data
+      * ``"none"``   → ``"scatter"``: Row + SP. fwd GEMM→RS(seq) ; bwd AG(seq)→GEMM
+      * ``"none"``   → ``"reduce"`` : Row, no SP. fwd GEMM→AR ; bwd GEMM
+    Semantics follow reference layers.py:434-532 and layers_utils.py:16-140 (input is saved
+    *sharded* and re-gathered in backward; dgrad collective overlaps wgrad).
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, in_mode, out_mode, seq_dim, group, reduce_dtype, save_for_backward):
+        from .. import ops
+
+        ctx.in_mode, ctx.out_mode, ctx.seq_dim, ctx.group = in_mode, out_mode, seq_dim, group
+        ctx.reduce_dtype = reduce_dtype
+        ctx.has_bias = bias is not None
+        ctx.x_requires_grad = x.requires_grad
+        n = dist.get_world_size(group)
+        if save_for_backward:
+            ctx.save_for_backward(x, weight)
+        fused = ops.tp_fused.dispatch(x, weight, in_mode, out_mode, seq_dim, group)
+        if fused is not None:
+            ctx.fused = True
+            y = fused.forward(x, weight)
+        else:
+            ctx.fused = False
+            total = comm.all_gather(x, dim=seq_dim, group=group) if (in_mode == "gather" and n > 1) else x
+            y = torch.matmul(total, weight.t())
+            if n > 1 and out_mode in ("scatter", "reduce"):
+                od = y.dtype
+                yr = y.to(reduce_dtype) if reduce_dtype is not None else y
+                if out_mode == "scatter":
+                    yr = comm.reduce_scatter(yr, dim=seq_dim, group=group)
+                else:
+                    comm.all_reduce(yr, group=group)
+                y = yr.to(od)
+        if bias is not None:
+            y = y + bias
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from .. import ops
+
+        x, weight = ctx.saved_tensors
+        group, seq_dim = ctx.group, ctx.seq_dim
+        n = dist.get_world_size(group)
+        in_mode, out_mode = ctx.in_mode, ctx.out_mode
+        gbias = None
+        gy = gy.contiguous()
+        if ctx.fused:
+            fused = ops.tp_fused.dispatch(x, weight, in_mode, out_mode, seq_dim, group)
+            gx, gw, gbias = fused.backward(x, weight, gy, ctx.has_bias, ctx.x_requires_grad, weight.requires_grad)
+            return gx, gw, gbias, None, None, None, None, None, None
+
+        # ---- grad wrt the GEMM output (undo the output collective) -----------------
+        if out_mode == "scatter" and n > 1:
+            g_out = comm.all_gather(gy, dim=seq_dim, group=group)
+        else:
+            g_out = gy  # "reduce": identity backward; "none"
+        if ctx.has_bias:
+            # bias is added after the collective → its grad uses the *local* gy
+            gbias = _flat2d(gy).sum(0)
+        # ---- dgrad --------------------------------------------------------------------
+        gx = None
+        work = None
+        if ctx.x_requires_grad:
+            gx = torch.matmul(g_out, weight)
+            if n > 1 and in_mode == "copy":
+                work = comm.all_reduce(gx, group=group, async_op=True)  # overlaps wgrad
+            elif n > 1 and in_mode == "gather":
+                od = gx.dtype
+                rd = ctx.reduce_dtype
+                gx = comm.reduce_scatter(gx.to(rd) if rd is not None else gx, dim=seq_dim, group=group).to(od)
+        # ---- wgrad ----------------------------------------------------------------------
+        gw = None
+        if weight.requires_grad:
+            total = comm.all_gather(x, dim=seq_dim, group=group) if (in_mode == "gather" and n > 1) else x
+            gw = torch.matmul(_flat2d(g_out).t(), _flat2d(total))
+        if work is not None:
+            work.wait()
+        return gx, gw, gbias, None, None, None, None, None, None
+
+
+def tp_linear(
+    x: torch.Tensor,
+    weight: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    in_mode: str,
+    out_mode: str,
+    seq_dim: int = 0,
+    group=None,
+    reduce_dtype: Optional[torch.dtype] = None,
+    save_for_backward: bool = True,
+    autocast: bool = False,
+) -> torch.Tensor:
+    group = group if group is not None else ps.get_tensor_model_parallel_group()
+    if autocast or torch.is_autocast_enabled():
+        dt = torch.get_autocast_dtype("cuda" if x.is_cuda else "cpu") if torch.is_autocast_enabled() else x.dtype
+        x = x.to(dt)
+        weight = weight.to(dt)
+        bias = bias.to(dt) if bias is not None else None
+        with torch.autocast(device_type="cuda" if x.is_cuda else "cpu", enabled=False):
+            return _TPLinear.apply(x, weight, bias, in_mode, out_mode, seq_dim, group, reduce_dtype, save_for_backward)
+    return _TPLinear.apply(x, weight, bias, in_mode, out_mode, seq_dim, group, reduce_dtype, save_for_backward)
+
+
+class LinearWithAsyncCommunication:
+    """Name-compatible façade (reference layers.py:434): ``apply`` maps the reference's flag
+    combination onto :class:`_TPLinear` modes."""
+
+    @staticmethod
+    def apply(
+        input,  # noqa: A002
+        weight,
+        bias,
+        async_grad_allreduce: bool,
+        sequence_parallel_enabled: bool,
+        sequence_dimension: Optional[int] = 0,
+        save_for_backward: bool = True,
+        process_group=None,
+        reduce_dtype: torch.dtype = torch.float32,
+    ):
+        if sequence_parallel_enabled:
+            assert not async_grad_allreduce
+            in_mode = "gather"
+        else:
+            in_mode = "copy" if async_grad_allreduce else "none"
+        return tp_linear(
+            input, weight, bias, in_mode, "none", sequence_dimension or 0, process_group, reduce_dtype, save_for_backward
+        )
+
+
+def linear_with_async_allreduce(
+    input: torch.Tensor,  # noqa: A002
+    weight: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    async_grad_allreduce: bool,
+    sequence_parallel_enabled: bool,
+    sequence_dimension: Optional[int] = 0,
+    autocast: bool = False,
+    save_for_backward: bool = True,
+    process_group=None,
+    reduce_dtype: torch.dtype = torch.float32,
+) -> torch.Tensor:
+    if sequence_parallel_enabled:
+        in_mode = "gather"
+    else:
+        in_mode = "copy" if async_grad_allreduce else "none"
+    return tp_linear(
+        input, weight, bias, in_mode, "none", sequence_dimension or 0, process_group, reduce_dtype,
+        save_for_backward, autocast,
+    )
+
+
+# --------------------------------------------------------------------------------------
+# Column / Row parallel linear
+# --------------------------------------------------------------------------------------
+class ColumnParallelLinear(BaseParallelLayer):
+    """``Y = X A^T + b`` with ``A`` split along its output dim: ``A = [A_1; …; A_p]``.
+
+    Arguments mirror reference layers.py:587-607.  ``stride`` >1 interleaves fused matrices
+    (gate/up, q/k/v) so each rank's shard holds matching slices of each."""
+
+    def __init__(
+        self,
+        input_size: int,
+        output_size: int,
+        bias: bool = True,
+        gather_output: bool = True,
+        dtype: torch.dtype = torch.float32,
+        device: Optional[torch.device] = None,
+        stride: int = 1,
+        init_method: Optional[Callable[..., Any]] = None,
+        sequence_parallel_enabled: bool = False,
+        sequence_dimension: Optional[int] = None,
+        keep_master_weight: bool = False,
+        skip_bias_add: bool = False,
+        pad: bool = False,
+        pad_alignment_size_per_rank: int = 1,
+        keep_padded_output: bool = False,
+        tensor_model_parallel_group=None,
+        reduce_dtype: torch.dtype = torch.float32,
+        rank_ordering: Optional[Sequence[int]] = None,
+    ):
+        super().__init__(device=device)
+        self.input_size, self.output_size = input_size, output_size
+        self.gather_output, self.stride = gather_output, stride
+        self.tensor_parallel_group, tp, self._tp_rank = _group_info(tensor_model_parallel_group)
+        self.tensor_model_parallel_size = tp
+        self.pad, self.pad_size, self.keep_padded_output = pad, 0, keep_padded_output
+        self.pad_alignment_size_per_rank = pad_alignment_size_per_rank
+        if pad:
+            self.pad_size = get_padding_length(output_size, tp * pad_alignment_size_per_rank)
+            self.output_size = output_size + self.pad_size
+        self.output_size_per_partition = divide(self.output_size, tp)
+        self.dtype = dtype
+        self.device = device if device is not None else torch.device("cpu")
+        self.keep_master_weight, self.skip_bias_add = keep_master_weight, skip_bias_add
+        self.sequence_parallel_enabled = sequence_parallel_enabled
+        self.sequence_dimension = 0 if sequence_dimension is None else sequence_dimension
+        self.reduce_dtype, self.rank_ordering = reduce_dtype, rank_ordering
+        self.arg_init_method = init_method
+        self.async_tensor_model_parallel_allreduce = not sequence_parallel_enabled and tp > 1
+        self.weight_partition_dim = 0
+        self.master_weight: Optional[torch.Tensor] = None
+        self.weight = Parameter(
+            torch.empty(self.output_size_per_partition, input_size, dtype=dtype, device=self.device)
+        )
+        self.bias_shape = (self.output_size_per_partition,) if not gather_output else (self.output_size,)
+        if bias:
+            # bias is sharded like the weight unless the output is gathered (then it is
+            # replicated and added after the gather) — reference :700-722
+            self.bias = Parameter(torch.zeros(*self.bias_shape, dtype=dtype, device=self.device))
+            if not gather_output:
+                set_tensor_model_parallel_attributes(self.bias, True, 0, stride, num_partitions=tp)
+            else:
+                set_tensor_model_parallel_attributes(self.bias, False, 0, 1, num_partitions=1)
+        else:
+            self.register_parameter("bias", None)
+        self.initialize_weight_and_bias()
+
+    def _init_weight(self, w: torch.Tensor) -> None:
+        if self.arg_init_method is None:
+            init.kaiming_uniform_(w, a=math.sqrt(5))
+        else:
+            self.arg_init_method(w)
+
+    def initialize_weight_and_bias(self) -> None:
+        tp = self.tensor_model_parallel_size
+        master = _initialize_parameter_from_master(
+            self.weight, 0, tp, self._init_weight, return_master_param=self.keep_master_weight,
+            param_dtype=self.dtype, stride=self.stride, rank=self._tp_rank,
+        )
+        if self.rank_ordering is not None:
+            self.weight.rank_ordering = list(self.rank_ordering)
+        if self.keep_master_weight:
+            self.master_weight = master
+        if self.bias is not None and self.arg_init_method is None and self.weight.device.type != "meta":
+            bound = 1 / math.sqrt(self.input_size) if self.input_size > 0 else 0
+            with torch.no_grad():
+                full = torch.empty(self.output_size, dtype=torch.float32)
+                init.uniform_(full, -bound, bound)
+                if self.gather_output:
+                    self.bias.copy_(full.to(self.dtype))
+                else:
+                    self.bias.copy_(create_local_weight(
+                        full.to(self.dtype), 0, self.output_size_per_partition, self.stride,
+                        rank=self._tp_rank, world_size=tp))
+
+    def forward(self, input: torch.Tensor, slice_indices: Optional[torch.Tensor] = None, *_: Any):  # noqa: A002
+        if self.pad and self.training:
+            raise RuntimeError("`pad=True` is only supported for inference. Set model.eval()")
+        tp = self.tensor_model_parallel_size
+        weight = self.weight if slice_indices is None else self.weight.index_select(0, slice_indices)
+        if self.sequence_parallel_enabled:
+            in_mode = "gather"
+        else:
+            in_mode = "copy" if tp > 1 else "none"
+        out = tp_linear(
+            input, weight, None, in_mode, "none", self.sequence_dimension, self.tensor_parallel_group, self.reduce_dtype
+        )
+        if self.gather_output:
+            out = mappings.gather_from_tensor_model_parallel_region(out, self.tensor_parallel_group)
+            if self.pad and self.pad_size > 0 and not self.keep_padded_output:
+                out = out.narrow(-1, 0, self.output_size - self.pad_size)
+        if self.skip_bias_add:
+            return out, self.bias
+        if self.bias is not None:
+            b = self.bias
+            if self.gather_output and self.pad and self.pad_size > 0 and not self.keep_padded_output:
+                b = b.narrow(0, 0, self.output_size - self.pad_size)
+            out = out + b
+        return out
+
+    def preshard_hook(self, model_state_dict: Dict[str, Any], prefix: str) -> None:
+        """Zero-pad a full checkpoint weight/bias along the output dim (reference :770-783)."""
+        if not self.pad or self.pad_size == 0:
+            return
+        w = model_state_dict[prefix]
+        if w.shape[0] + self.pad_size != self.output_size:
+            raise RuntimeError(f"State dict {prefix} has unexpected shape {tuple(w.shape)}")
+        model_state_dict[prefix] = F.pad(w, (0, 0, 0, self.pad_size))
+        bkey = prefix.replace("weight", "bias")
+        if self.bias is not None and bkey in model_state_dict:
+            model_state_dict[bkey] = F.pad(model_state_dict[bkey], (0, self.pad_size))
+
+
+class RowParallelLinear(BaseParallelLayer):
+    """``Y = X A^T + b`` with ``A`` split along its input dim; partial products are summed
+    across TP — all-reduce, or reduce-scatter along the sequence dim under SP (reference
+    layers.py:815-1063)."""
+
+    def __init__(
+        self,
+        input_size: int,
+        output_size: int,
+        bias: bool = True,
+        input_is_parallel: bool = False,
+        dtype: torch.dtype = torch.float32,
+        device: Optional[torch.device] = None,
+        stride: int = 1,
+        init_method: Optional[Callable[..., Any]] = None,
+        sequence_parallel_enabled: bool = False,
+        sequence_dimension: Optional[int] = None,
+        keep_master_weight: bool = False,
+        skip_bias_add: bool = False,
+        pad: bool = False,
+        reduce_output: bool = True,
+        reduce_dtype: torch.dtype = torch.float32,
+        tensor_model_parallel_group=None,
+        tile_cc: bool = False,
+        rank_ordering: Optional[Sequence[int]] = None,
+    ):
+        super().__init__(device=device)
+        self.input_size, self.output_size = input_size, output_size
+        self.input_is_parallel, self.stride = input_is_parallel, stride
+        self.tensor_parallel_group, tp, self._tp_rank = _group_info(tensor_model_parallel_group)
+        self.tensor_model_parallel_size = tp
+        self.pad, self.pad_size = pad, 0
+        if pad:
+            self.pad_size = get_padding_length(input_size, tp)
+            self.input_size = input_size + self.pad_size
+        self.input_size_per_partition = divide(self.input_size, tp)
+        self.dtype = dtype
+        self.device = device if device is not None else torch.device("cpu")
+        self.keep_master_weight, self.skip_bias_add = keep_master_weight, skip_bias_add
+        self.sequence_parallel_enabled = sequence_parallel_enabled
+        self.sequence_dimension = 0 if sequence_dimension is None else sequence_dimension
+        self.reduce_output, self.reduce_dtype = reduce_output, reduce_dtype
+        self.rank_ordering = rank_ordering
+        self.arg_init_method = init_method
+        if sequence_parallel_enabled and not input_is_parallel:
+            raise RuntimeError("To enable `sequence_parallel_enabled`, `input_is_parallel` must be `True`")
+        self.weight_partition_dim = 1
+        self.master_weight: Optional[torch.Tensor] = None
+        self.weight = Parameter(
+            torch.empty(output_size, self.input_size_per_partition, dtype=dtype, device=self.device)
+        )
+        if bias:
+            self.bias = Parameter(torch.zeros(output_size, dtype=dtype, device=self.device))
+            _tag_sequence_parallel(self.bias, sequence_parallel_enabled)
+        else:
+            self.register_parameter("bias", None)
+        self.initialize_weight_and_bias()
+
+    def _init_weight(self, w: torch.Tensor) -> None:
+        if self.arg_init_method is None:
+            init.kaiming_uniform_(w, a=math.sqrt(5))
+        else:
+            self.arg_init_method(w)
+
+    def initialize_weight_and_bias(self) -> None:
+        master = _initialize_parameter_from_master(
+            self.weight, 1, self.tensor_model_parallel_size, self._init_weight,
+            return_master_param=self.keep_master_weight, param_dtype=self.dtype, stride=self.stride,
+            rank=self._tp_rank,
+        )
+        if self.rank_ordering is not None:
+            self.weight.rank_ordering = list(self.rank_ordering)
+        if self.keep_master_weight:
+            self.master_weight = master
+        if self.bias is not None and self.arg_init_method is None and self.weight.device.type != "meta":
+            bound = 1 / math.sqrt(self.input_size) if self.input_size > 0 else 0
+            with torch.no_grad():
+                init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, input_: torch.Tensor):
+        if self.pad and self.training:
+            raise RuntimeError("`pad=True` is only supported for inference. Set model.eval()")
+        tp = self.tensor_model_parallel_size
+        if self.input_is_parallel:
+            x = input_
+        else:
+            if self.pad and self.pad_size > 0:
+                input_ = F.pad(input_, (0, self.pad_size))
+            x = mappings.scatter_to_tensor_model_parallel_region(input_, self.tensor_parallel_group)
+        if not self.reduce_output or tp == 1:
+            out_mode = "none"
+        else:
+            out_mode = "scatter" if self.sequence_parallel_enabled else "reduce"
+        out = tp_linear(
+            x, self.weight, None, "none", out_mode, self.sequence_dimension, self.tensor_parallel_group,
+            self.reduce_dtype,
+        )
+        if self.skip_bias_add:
+            return out, self.bias
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+    def preshard_hook(self, model_state_dict: Dict[str, Any], prefix: str) -> None:
+        if not self.pad or self.pad_size == 0:
+            return
+        w = model_state_dict[prefix]
+        if w.shape[1] + self.pad_size != self.input_size:
+            raise RuntimeError(f"State dict {prefix} has unexpected shape {tuple(w.shape)}")
+        model_state_dict[prefix] = F.pad(w, (0, self.pad_size))
+
+
+# --------------------------------------------------------------------------------------
+# Conv2d
+# --------------------------------------------------------------------------------------
+def _pair(v) -> Tuple[int, int]:
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+class _ConvWithAsyncAllReduce(torch.autograd.Function):
+    """conv2d whose input-grad all-reduce overlaps the weight-grad computation
+    (reference layers.py:1066-1150)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups, allreduce_dgrad, group):
+        ctx.save_for_backward(x, weight)
+        ctx.conf = (stride, padding, dilation, groups)
+        ctx.has_bias, ctx.allreduce_dgrad, ctx.group = bias is not None, allreduce_dgrad, group
+        return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        stride, padding, dilation, groups = ctx.conf
+        gx = gw = gb = None
+        work = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.nn.grad.conv2d_input(x.shape, weight, gy, stride, padding, dilation, groups)
+            if ctx.allreduce_dgrad and dist.get_world_size(ctx.group) > 1:
+                work = comm.all_reduce(gx, group=ctx.group, async_op=True)
+        if ctx.needs_input_grad[1]:
+            gw = torch.nn.grad.conv2d_weight(x, weight.shape, gy, stride, padding, dilation, groups)
+        if ctx.has_bias:
+            gb = gy.sum((0, 2, 3))
+        if work is not None:
+            work.wait()
+        return gx, gw, gb, None, None, None, None, None, None
+
+
+class BaseParallelConv(BaseParallelLayer):
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
+                 padding_mode, partition_dim, dtype, device, init_method, keep_master_weight, group):
+        super().__init__(device=device)
+        if groups != 1:
+            raise NotImplementedError("grouped convolution is not supported by the parallel conv layers")
+        if padding_mode != "zeros":
+            raise NotImplementedError("only zero padding is supported")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride = _pair(kernel_size), _pair(stride)
+        self.padding, self.dilation, self.groups = _pair(padding), _pair(dilation), groups
+        self.tensor_parallel_group, self.tensor_model_parallel_size, self._tp_rank = _group_info(group)
+        self.partition_dim, self.dtype = partition_dim, dtype
+        self.arg_init_method, self.keep_master_weight = init_method, keep_master_weight
+        self.device = device if device is not None else torch.device("cpu")
+        tp = self.tensor_model_parallel_size
+        oc = divide(out_channels, tp) if partition_dim == 0 else out_channels
+        ic = divide(in_channels, tp) if partition_dim == 1 else in_channels
+        self.weight = Parameter(torch.empty(oc, ic, *self.kernel_size, dtype=dtype, device=self.device))
+        self.master_weight = _initialize_parameter_from_master(
+            self.weight, partition_dim, tp, self._init_weight, keep_master_weight, dtype, 1, self._tp_rank)
+        if bias:
+            self.bias = Parameter(torch.zeros(oc if partition_dim == 0 else out_channels, dtype=dtype, device=self.device))
+            fan_in = in_channels * self.kernel_size[0] * self.kernel_size[1]
+            bound = 1 / math.sqrt(fan_in)
+            with torch.no_grad():
+                full = torch.empty(out_channels, dtype=torch.float32)
+                init.uniform_(full, -bound, bound)
+                if partition_dim == 0:
+                    self.bias.copy_(create_local_weight(full.to(dtype), 0, oc, 1, rank=self._tp_rank, world_size=tp))
+                    set_tensor_model_parallel_attributes(self.bias, True, 0, 1, num_partitions=tp)
+                else:
+                    self.bias.copy_(full.to(dtype))
+        else:
+            self.register_parameter("bias", None)
+
+    def _init_weight(self, w):
+        if self.arg_init_method is None:
+            init.kaiming_uniform_(w, a=math.sqrt(5))
+        else:
+            self.arg_init_method(w)
+
+
+class OutputChannelParallelConv2d(BaseParallelConv):
+    """Conv2d sharded along output channels; optional all-gather on the channel dim
+    (reference layers.py:1309-1430)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, padding_mode="zeros", gather_output=True, dtype=torch.float32, device=None,
+                 init_method=None, keep_master_weight=False, tensor_model_parallel_group=None):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
+                         padding_mode, 0, dtype, device, init_method, keep_master_weight, tensor_model_parallel_group)
+        self.gather_output = gather_output
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        tp = self.tensor_model_parallel_size
+        out = _ConvWithAsyncAllReduce.apply(x, self.weight, self.bias, self.stride, self.padding, self.dilation,
+                                            self.groups, tp > 1, self.tensor_parallel_group)
+        if self.gather_output:
+            out = mappings.gather_from_tensor_model_parallel_region_with_dim(out, 1, self.tensor_parallel_group)
+        return out
+
+
+class InputChannelParallelConv2d(BaseParallelConv):
+    """Conv2d sharded along input channels; partial outputs all-reduced
+    (reference layers.py:1432-1540)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, padding_mode="zeros", input_is_parallel=False, dtype=torch.float32, device=None,
+                 init_method=None, keep_master_weight=False, tensor_model_parallel_group=None):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
+                         padding_mode, 1, dtype, device, init_method, keep_master_weight, tensor_model_parallel_group)
+        self.input_is_parallel = input_is_parallel
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not self.input_is_parallel:
+            x = mappings.scatter_input_channels_to_tensor_model_parallel_region(x, self.tensor_parallel_group)
+        out = _ConvWithAsyncAllReduce.apply(x, self.weight, None, self.stride, self.padding, self.dilation,
+                                            self.groups, False, self.tensor_parallel_group)
+        out = mappings.reduce_from_tensor_model_parallel_region(out, self.tensor_parallel_group)
+        if self.bias is not None:
+            out = out + self.bias.view(1, -1, 1, 1)
+        return out

@@ -1,0 +1,62 @@
+"""Optimizer wrapper (reference ``trainer/optimizer.py:10-147``).
+
+``step()`` = CP grad average → SP-param grad all-reduce → (non-ZeRO) DP bucket all-reduce
+(+ EP second pass) → clip → inner step.  ``grad_norm`` exposes the last global norm."""
+from __future__ import annotations
+
+from typing import Any, List, Optional
+
+import torch
+
+from ..optimizer.zero_redundancy_optimizer import NeuronEPZero1Optimizer, Zero1Optimizer
+from ..parallel_layers import grads
+from ..parallel_layers import parallel_state as ps
+
+
+class NxDOptimizer(torch.optim.Optimizer):
+    def __init__(self, optimizer: torch.optim.Optimizer, nxd_config: dict):
+        self.optimizer = optimizer
+        self.nxd_config = nxd_config
+        self._grad_norm: Optional[torch.Tensor] = None
+        self.param_groups = optimizer.param_groups
+        self.defaults = getattr(optimizer, "defaults", {})
+        self.state = getattr(optimizer, "state", {})
+        self._is_zero = isinstance(optimizer, (Zero1Optimizer, NeuronEPZero1Optimizer))
+
+    @property
+    def grad_norm(self) -> Optional[torch.Tensor]:
+        return self._grad_norm
+
+    @property
+    def params(self) -> List[torch.nn.Parameter]:
+        return [p for g in self.param_groups for p in g["params"]]
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        self.optimizer.zero_grad(set_to_none=set_to_none)
+
+    def state_dict(self) -> Any:
+        return self.optimizer.state_dict()
+
+    def load_state_dict(self, sd: Any) -> None:
+        self.optimizer.load_state_dict(sd)
+
+    def step(self, closure=None):
+        cfg = self.nxd_config["optimizer_config"]
+        grads.allreduce_context_parallel_gradients(self.optimizer)
+        if self.nxd_config.get("sequence_parallel", False):
+            grads.allreduce_sequence_parallel_gradients(self.optimizer)
+        if self._is_zero:
+            out = self.optimizer.step(closure=closure)
+            self._grad_norm = self.optimizer.grad_norm
+            return out
+        pp_handles_dp = self.nxd_config.get("pipeline_parallel_size", 1) > 1 and \
+            not (self.nxd_config.get("pipeline_config") or {}).get("use_optimizer_wrapper", True)
+        if not pp_handles_dp and ps.get_data_parallel_size() > 1:
+            allg = [p.grad for p in self.params if p.grad is not None]
+            grads.bucket_allreduce_gradients(allg)
+            if ps.get_expert_model_parallel_size() > 1:
+                non_ep = [p.grad for p in self.params if p.grad is not None and not getattr(p, "expert_model_parallel", False)]
+                grads.bucket_allreduce_gradients(non_ep, reduce_over_ep_group=True)
+        if cfg["grad_clipping"]:
+            self._grad_norm = grads.clip_grad_norm(self.params, cfg["max_grad_norm"])
+        return self.optimizer.step(closure=closure)

@@ -1,0 +1,62 @@
+"""Rank-aware logging (behaviour of reference ``utils/logger.py:16-112``).
+
+* level from ``NXD_LOG_LEVEL`` (off, fatal, error, warning, info, debug, trace)
+* ``NXD_LOG_HIDE_TIME=1`` drops the timestamp
+* ``rank0_only=True`` loggers are silent on every rank but 0
+"""
+from __future__ import annotations
+
+import logging
+import os
+import sys
+
+_LEVELS = {
+    "off": logging.CRITICAL + 10,
+    "fatal": logging.CRITICAL,
+    "error": logging.ERROR,
+    "warning": logging.WARNING,
+    "info": logging.INFO,
+    "debug": logging.DEBUG,
+    "trace": 5,
+}
+logging.addLevelName(5, "TRACE")
+
+
+class _RankZeroFilter(logging.Filter):
+    def filter(self, record: logging.LogRecord) -> bool:  # noqa: A003
+        try:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                return dist.get_rank() == 0
+        except Exception:
+            pass
+        return int(os.environ.get("RANK", "0")) == 0
+
+
+_CACHE: dict[tuple[str, bool], logging.Logger] = {}
+
+
+def get_log_level() -> int:
+    return _LEVELS.get(os.environ.get("NXD_LOG_LEVEL", "info").lower(), logging.INFO)
+
+
+def get_logger(name: str = "nxd_b200", rank0_only: bool = True) -> logging.Logger:
+    key = (name, rank0_only)
+    if key in _CACHE:
+        return _CACHE[key]
+    logger = logging.getLogger(f"{name}{'.r0' if rank0_only else '.all'}")
+    logger.setLevel(get_log_level())
+    logger.propagate = False
+    if not logger.handlers:
+        handler = logging.StreamHandler(sys.stdout)
+        if os.environ.get("NXD_LOG_HIDE_TIME", "0") == "1":
+            fmt = "[%(levelname).1s %(filename)s:%(lineno)d] %(message)s"
+        else:
+            fmt = "[%(asctime)s %(levelname).1s %(filename)s:%(lineno)d] %(message)s"
+        handler.setFormatter(logging.Formatter(fmt))
+        logger.addHandler(handler)
+    if rank0_only:
+        logger.addFilter(_RankZeroFilter())
+    _CACHE[key] = logger
+    return logger
