@@ -1,0 +1,225 @@
+// pybind11 bindings: tensor checks + raw-pointer extraction; all math lives in the .cu files.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <pybind11/stl.h>
+#include <torch/extension.h>
+
+#include "kernels.h"
+#include "symm.h"
+
+namespace py = pybind11;
+using at::Tensor;
+
+static int dt_code(const Tensor& t) {
+  switch (t.scalar_type()) {
+    case at::kFloat: return nxd::kF32;
+    case at::kBFloat16: return nxd::kBF16;
+    case at::kHalf: return nxd::kF16;
+    default: TORCH_CHECK(false, "unsupported dtype ", t.scalar_type());
+  }
+}
+static cudaStream_t stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+#define CHECK_IN(t) TORCH_CHECK((t).is_cuda() && (t).is_contiguous(), #t " must be a contiguous CUDA tensor")
+
+static std::vector<Tensor> rmsnorm_fwd(const Tensor& x, const Tensor& w, double eps) {
+  CHECK_IN(x); CHECK_IN(w);
+  TORCH_CHECK(x.dim() == 2 && w.numel() == x.size(1) && w.scalar_type() == x.scalar_type());
+  c10::cuda::CUDAGuard g(x.device());
+  auto y = at::empty_like(x);
+  auto rstd = at::empty({x.size(0), 1}, x.options().dtype(at::kFloat));
+  if (x.size(0) > 0)
+    nxd::rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(), (int)x.size(0), (int)x.size(1),
+                     (float)eps, dt_code(x), stream());
+  return {y, rstd};
+}
+
+static std::vector<Tensor> rmsnorm_bwd(const Tensor& g, const Tensor& x, const Tensor& w, const Tensor& rstd) {
+  CHECK_IN(g); CHECK_IN(x); CHECK_IN(w); CHECK_IN(rstd);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int rows = (int)x.size(0), H = (int)x.size(1);
+  auto dx = at::empty_like(x);
+  auto dw = at::zeros({H}, x.options().dtype(at::kFloat));
+  if (rows > 0) {
+    auto partial = at::empty({nxd::rmsnorm_bwd_num_partials(rows), H}, x.options().dtype(at::kFloat));
+    nxd::rmsnorm_bwd(g.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr<float>(), dx.data_ptr(),
+                     partial.data_ptr<float>(), dw.data_ptr<float>(), rows, H, dt_code(x), stream());
+  }
+  return {dx, dw};
+}
+
+static Tensor swiglu_fwd(const Tensor& gu) {
+  CHECK_IN(gu);
+  c10::cuda::CUDAGuard g(gu.device());
+  const int I = (int)gu.size(1) / 2;
+  auto out = at::empty({gu.size(0), I}, gu.options());
+  if (gu.numel()) nxd::swiglu_fwd(gu.data_ptr(), out.data_ptr(), gu.size(0), I, dt_code(gu), stream());
+  return out;
+}
+static Tensor swiglu_bwd(const Tensor& go, const Tensor& gu) {
+  CHECK_IN(go); CHECK_IN(gu);
+  c10::cuda::CUDAGuard g(gu.device());
+  auto d = at::empty_like(gu);
+  if (gu.numel()) nxd::swiglu_bwd(go.data_ptr(), gu.data_ptr(), d.data_ptr(), gu.size(0), (int)gu.size(1) / 2, dt_code(gu), stream());
+  return d;
+}
+
+static Tensor rope_apply(const Tensor& x, const Tensor& cos_t, const Tensor& sin_t, double sign) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.stride(3) == 1, "rope: x must be [B,S,H,D] with contiguous D");
+  CHECK_IN(cos_t); CHECK_IN(sin_t);
+  TORCH_CHECK(cos_t.scalar_type() == at::kFloat && cos_t.size(0) >= x.size(1) && cos_t.size(1) == x.size(3) / 2);
+  c10::cuda::CUDAGuard g(x.device());
+  auto out = at::empty(x.sizes(), x.options());
+  const int es = (int)x.element_size();
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(x.data_ptr()) % 16) == 0 && (x.stride(0) * es) % 16 == 0 &&
+              (x.stride(1) * es) % 16 == 0 && (x.stride(2) * es) % 16 == 0, "rope: 16-byte alignment required");
+  if (x.numel())
+    nxd::rope_apply(x.data_ptr(), out.data_ptr(), cos_t.data_ptr<float>(), sin_t.data_ptr<float>(), (int)x.size(0),
+                    (int)x.size(1), (int)x.size(2), (int)x.size(3), x.stride(0), x.stride(1), x.stride(2), (float)sign,
+                    dt_code(x), stream());
+  return out;
+}
+
+static Tensor ce_stats(const Tensor& logits, const Tensor& target, int64_t vocab_start) {
+  CHECK_IN(logits); CHECK_IN(target);
+  TORCH_CHECK(target.scalar_type() == at::kLong && logits.dim() == 2 && target.numel() == logits.size(0));
+  c10::cuda::CUDAGuard g(logits.device());
+  auto stats = at::empty({logits.size(0), 4}, logits.options().dtype(at::kFloat));
+  if (logits.size(0))
+    nxd::ce_stats(logits.data_ptr(), target.data_ptr<int64_t>(), stats.data_ptr<float>(), (int)logits.size(0),
+                  (int)logits.size(1), (int)vocab_start, dt_code(logits), stream());
+  return stats;
+}
+static Tensor ce_backward(const Tensor& logits, const Tensor& target, const Tensor& lse, const Tensor& gout,
+                          int64_t vocab_start, double smoothing, int64_t vocab) {
+  CHECK_IN(logits); CHECK_IN(target); CHECK_IN(lse); CHECK_IN(gout);
+  c10::cuda::CUDAGuard g(logits.device());
+  auto grad = at::empty_like(logits);
+  if (logits.size(0))
+    nxd::ce_backward(logits.data_ptr(), target.data_ptr<int64_t>(), lse.data_ptr<float>(), gout.data_ptr<float>(),
+                     grad.data_ptr(), (int)logits.size(0), (int)logits.size(1), (int)vocab_start, (float)smoothing,
+                     (int)vocab, dt_code(logits), stream());
+  return grad;
+}
+
+static std::vector<nxd::TensorRef> refs(const std::vector<Tensor>& ts) {
+  std::vector<nxd::TensorRef> r;
+  r.reserve(ts.size());
+  for (auto& t : ts) {
+    TORCH_CHECK(t.is_cuda() && t.is_contiguous());
+    r.push_back({t.data_ptr(), (long)t.numel()});
+  }
+  return r;
+}
+static void multi_tensor_sq_norm(const std::vector<Tensor>& ts, Tensor out) {
+  if (ts.empty()) return;
+  c10::cuda::CUDAGuard g(ts[0].device());
+  nxd::multi_tensor_sq_norm(refs(ts), dt_code(ts[0]), out.data_ptr<float>(), stream());
+}
+static void multi_tensor_scale(const std::vector<Tensor>& ts, const Tensor& scale) {
+  if (ts.empty()) return;
+  c10::cuda::CUDAGuard g(ts[0].device());
+  nxd::multi_tensor_scale(refs(ts), dt_code(ts[0]), scale.data_ptr<float>(), stream());
+}
+static void fused_adamw(const std::vector<Tensor>& p, const std::vector<Tensor>& g, const std::vector<Tensor>& m,
+                        const std::vector<Tensor>& v, const std::vector<Tensor>& lowp, double lr, double b1, double b2,
+                        double eps, double wd, double bc1, double bc2, const Tensor& grad_scale) {
+  if (p.empty()) return;
+  TORCH_CHECK(p[0].scalar_type() == at::kFloat && m[0].scalar_type() == at::kFloat);
+  c10::cuda::CUDAGuard guard(p[0].device());
+  nxd::fused_adamw(refs(p), refs(g), refs(m), refs(v), refs(lowp), dt_code(g[0]), lowp.empty() ? 0 : dt_code(lowp[0]),
+                   (float)lr, (float)b1, (float)b2, (float)eps, (float)wd, (float)bc1, (float)bc2,
+                   grad_scale.data_ptr<float>(), stream());
+}
+
+// ---- GEMM ---------------------------------------------------------------------------------------
+static void gemm_bf16(const Tensor& a, const Tensor& b, Tensor out, bool trans_a, bool trans_b, bool accumulate) {
+  CHECK_IN(a); CHECK_IN(b); CHECK_IN(out);
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && a.dim() == 2 && b.dim() == 2);
+  const int M = (int)(trans_a ? a.size(1) : a.size(0)), K = (int)(trans_a ? a.size(0) : a.size(1));
+  const int N = (int)(trans_b ? b.size(0) : b.size(1));
+  TORCH_CHECK((trans_b ? b.size(1) : b.size(0)) == K && out.size(0) == M && out.size(1) == N, "gemm shape mismatch");
+  c10::cuda::CUDAGuard g(a.device());
+  nxd::GemmComm none;
+  nxd::gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, trans_a, trans_b, dt_code(out), accumulate, none,
+                 nullptr, stream());
+}
+
+// all-gather(A shards along rows) → GEMM.  `a_shard` [M/world, K]; gathered A lives in the symmetric payload at
+// buf_offset (every rank), out = A_full @ op(B).
+static void ag_gemm_bf16(const Tensor& a_shard, const Tensor& b, Tensor out, bool trans_b, const Tensor& peer_bufs,
+                         const Tensor& peer_flags, int64_t buf_offset, int64_t flag_offset, int64_t epoch, int64_t rank,
+                         int64_t world, int64_t comm_sms) {
+  CHECK_IN(a_shard); CHECK_IN(b); CHECK_IN(out);
+  const int Ms = (int)a_shard.size(0), K = (int)a_shard.size(1), M = Ms * (int)world;
+  const int N = (int)(trans_b ? b.size(0) : b.size(1));
+  TORCH_CHECK(out.size(0) == M && out.size(1) == N);
+  c10::cuda::CUDAGuard g(a_shard.device());
+  nxd::GemmComm c;
+  c.mode = 1; c.rank = (int)rank; c.world = (int)world;
+  c.peer_bufs = peer_bufs.data_ptr<int64_t>(); c.peer_flags = peer_flags.data_ptr<int64_t>();
+  c.buf_offset = buf_offset; c.flag_offset = (int)flag_offset; c.epoch = (uint32_t)epoch; c.comm_sms = (int)comm_sms;
+  // A operand = this rank's gathered buffer
+  auto host_ptrs = peer_bufs.cpu();
+  const void* a_full = (const void*)(host_ptrs.data_ptr<int64_t>()[rank] + buf_offset);
+  nxd::gemm_bf16(a_full, b.data_ptr(), out.data_ptr(), M, N, K, false, trans_b, dt_code(out), false, c,
+                 a_shard.data_ptr(), stream());
+}
+
+// GEMM → reduce-scatter over rows.  a [M, K]; out [M/world, N] bf16 (sum over ranks of rows owned by this rank).
+static void gemm_rs_bf16(const Tensor& a, const Tensor& b, Tensor out, bool trans_b, int64_t local_buf_ptr,
+                         const Tensor& peer_bufs, const Tensor& peer_flags, int64_t buf_offset, int64_t flag_offset,
+                         int64_t epoch, int64_t rank, int64_t world) {
+  CHECK_IN(a); CHECK_IN(b); CHECK_IN(out);
+  const int M = (int)a.size(0), K = (int)a.size(1);
+  const int N = (int)(trans_b ? b.size(0) : b.size(1));
+  TORCH_CHECK(out.size(0) * world == M && out.size(1) == N && out.scalar_type() == at::kBFloat16);
+  (void)local_buf_ptr;
+  c10::cuda::CUDAGuard g(a.device());
+  nxd::GemmComm c;
+  c.mode = 2; c.rank = (int)rank; c.world = (int)world;
+  c.peer_bufs = peer_bufs.data_ptr<int64_t>(); c.peer_flags = peer_flags.data_ptr<int64_t>();
+  c.buf_offset = buf_offset; c.flag_offset = (int)flag_offset; c.epoch = (uint32_t)epoch;
+  nxd::gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, false, trans_b, nxd::kBF16, false, c, nullptr,
+                 stream());
+}
+
+// ---- symmetric memory ---------------------------------------------------------------------------
+static py::tuple symm_alloc(int64_t nbytes, int64_t nflags) {
+  auto a = nxd::symm_alloc((size_t)nbytes, (size_t)nflags);
+  return py::make_tuple(a.id, py::bytes(a.payload_handle), py::bytes(a.flags_handle));
+}
+static py::tuple symm_open(int64_t id, int64_t rank, const std::vector<py::bytes>& ph, const std::vector<py::bytes>& fh) {
+  std::vector<std::string> p, f;
+  for (auto& b : ph) p.push_back((std::string)b);
+  for (auto& b : fh) f.push_back((std::string)b);
+  auto r = nxd::symm_open(id, (int)rank, p, f);
+  return py::make_tuple(r.payload, r.flags);
+}
+static Tensor symm_view(int64_t id, int64_t offset, const std::vector<int64_t>& shape, py::object dtype) {
+  size_t nbytes = 0;
+  auto* base = (uint8_t*)nxd::symm_local_payload(id, &nbytes);
+  auto st = torch::python::detail::py_object_to_dtype(dtype);
+  int dev; cudaGetDevice(&dev);
+  auto opts = at::TensorOptions().dtype(st).device(at::kCUDA, dev);
+  return at::from_blob(base + offset, shape, opts);
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("rmsnorm_fwd", &rmsnorm_fwd);
+  m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("swiglu_fwd", &swiglu_fwd);
+  m.def("swiglu_bwd", &swiglu_bwd);
+  m.def("rope_apply", &rope_apply);
+  m.def("ce_stats", &ce_stats);
+  m.def("ce_backward", &ce_backward);
+  m.def("multi_tensor_sq_norm", &multi_tensor_sq_norm);
+  m.def("multi_tensor_scale", &multi_tensor_scale);
+  m.def("fused_adamw", &fused_adamw);
+  m.def("gemm_bf16", &gemm_bf16);
+  m.def("ag_gemm_bf16", &ag_gemm_bf16);
+  m.def("gemm_rs_bf16", &gemm_rs_bf16);
+  m.def("symm_alloc", &symm_alloc);
+  m.def("symm_open", &symm_open);
+  m.def("symm_free", &nxd::symm_free);
+  m.def("symm_view", &symm_view);
+}

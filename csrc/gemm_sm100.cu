@@ -1,0 +1,556 @@
+// bf16 GEMM for sm_100a on the 5th-generation tensor cores, optionally fused with a tensor-parallel
+// collective over NVLink peer memory.
+//
+//   D[M,N] (+)= op(A)[M,K] · op(B)[K,N]           fp32 accumulation in TMEM
+//
+// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0      TMA producer   : cp.async.bulk.tensor → 128B-swizzled smem ring (4 stages × 48 KB)
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma (M=128, N=256, K=16) into a
+//                                double-buffered 128×256 fp32 accumulator in TMEM (2×256 columns);
+//                                tcgen05.commit releases smem stages / publishes accumulators
+//   warps 2-5   epilogue       : tcgen05.ld (32 lanes × 32 columns per warp) → convert → global stores
+//
+// Operand majors are template parameters so forward (A K-major, B K-major), dgrad (B MN-major) and wgrad
+// (A and B MN-major) all run without transposition copies — only the TMA boxes and UMMA descriptors differ.
+//
+// Fused collective modes (no NCCL call on these paths — reference call sites layers_utils.py:56,
+// layers.py:1035-1038, mappings.py:125-157, 347-352):
+//   MODE 1  all-gather → GEMM : `comm_sms` CTAs push this rank's A shard into every peer's symmetric
+//           buffer (st.global over NVLink, 16 B vectors) and publish per-(source,row-block) flags with
+//           st.release.sys; GEMM CTAs walk row-chunks in arrival order and their TMA producer acquires
+//           the flag (ld.acquire.sys + fence.proxy.async) before loading tiles of that chunk.
+//   MODE 2  GEMM → reduce-scatter : the epilogue stores each partial tile straight into the owner rank's
+//           staging slot (peer st.global), then bumps the owner's per-(source,row-block) counter with
+//           red.release.sys; after its last tile every CTA turns into a reducer that acquires the 8
+//           counters of a row-block, sums the partials in fp32 and writes the bf16 result.
+//   Payload regions are double-buffered by call parity and flags are monotonic, so consecutive calls need
+//   no barrier ("symmetric memory protocol").
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nxd {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;           // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kABytes = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;   // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;   // 48 KB
+constexpr int kThreads = 192;
+constexpr int kEpilogueThreads = 128;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kTmemCols = kAccStages * BLOCK_N;  // 512
+
+// ------------------------------------------------------------------ PTX wrappers
+NXD_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+NXD_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+NXD_DEVICE void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+NXD_DEVICE void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+NXD_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+NXD_DEVICE void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+NXD_DEVICE void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+NXD_DEVICE void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+NXD_DEVICE void tcgen05_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+NXD_DEVICE void tcgen05_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+NXD_DEVICE void tcgen05_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+NXD_DEVICE void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+NXD_DEVICE void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+NXD_DEVICE void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+NXD_DEVICE void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+NXD_DEVICE void tcgen05_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes × 32 consecutive fp32 columns: thread `lane` receives row (quarter*32+lane), columns c..c+31
+NXD_DEVICE void tcgen05_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// ------------------------------------------------------------------ descriptors
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B).
+NXD_DEVICE uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10),
+// a_major bit15, b_major bit16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct CommDev {
+  int rank, world;
+  const int64_t* peer_bufs;
+  const int64_t* peer_flags;
+  long buf_offset;
+  int flag_offset;
+  uint32_t epoch;
+  int comm_sms;
+  int rows_per_rank;      // M / world
+  const void* a_local;    // MODE 1: this rank's [rows_per_rank, K] shard
+  void* rs_out;           // MODE 2: reduced [rows_per_rank, N] output
+};
+
+// tile index → (m_blk, n_blk).  `chunk_order` visits row-chunks (one per rank) in communication order.
+template <int MODE>
+NXD_DEVICE void tile_coords(int tile, int tiles_m, int tiles_n, const CommDev& c, int& m_blk, int& n_blk) {
+  if constexpr (MODE == 0) {
+    constexpr int GROUP = 8;  // rasterise 8 M-blocks at a time so B tiles are re-used from L2
+    const int per_group = GROUP * tiles_n;
+    const int g = tile / per_group;
+    const int first_m = g * GROUP;
+    const int gsz = min(GROUP, tiles_m - first_m);
+    const int in = tile - g * per_group;
+    m_blk = first_m + in % gsz;
+    n_blk = in / gsz;
+  } else {
+    const int mb_per_rank = c.rows_per_rank / BLOCK_M;
+    const int per_chunk = mb_per_rank * tiles_n;
+    const int step = tile / per_chunk;           // 0 .. world-1
+    const int in = tile - step * per_chunk;
+    int chunk;
+    if constexpr (MODE == 1) chunk = (c.rank - step + c.world) % c.world;        // own, then rank-1, rank-2, …
+    else chunk = (c.rank + 1 + step) % c.world;                                  // rank+1, …, own last
+    m_blk = chunk * mb_per_rank + in % mb_per_rank;
+    n_blk = in / mb_per_rank;
+  }
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR, int MODE, typename OutT>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 OutT* __restrict__ out, int M, int N, int K, int accumulate, CommDev comm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1 KB alignment
+  uint64_t* bars = (uint64_t*)(smem + kStages * kStageBytes);
+  // [0,kStages) full, [kStages,2kStages) empty, then tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kStages + 2 * kAccStages);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStages);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * kStages), bar_tempty = smem_u32(bars + 2 * kStages + kAccStages);
+  const uint32_t smem_base = smem_u32(smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M, tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  // ---- one-time setup ------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tma_a);
+    prefetch_tmap(&tma_b);
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, kEpilogueThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tcgen05_alloc(smem_u32(tmem_slot), kTmemCols); tcgen05_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- role split ------------------------------------------------------------------
+  int gemm_cta = blockIdx.x, gemm_ctas = gridDim.x;
+  bool is_comm_cta = false;
+  if constexpr (MODE == 1) {
+    is_comm_cta = (int)blockIdx.x < comm.comm_sms;
+    gemm_cta = blockIdx.x - comm.comm_sms;
+    gemm_ctas = gridDim.x - comm.comm_sms;
+  }
+
+  if constexpr (MODE == 1) {
+    if (is_comm_cta) {
+      // ===== all-gather pusher: (destination, row-block) items, destinations in rotated order =====
+      const int mb_per_rank = comm.rows_per_rank / BLOCK_M;
+      const int items = comm.world * mb_per_rank;
+      const size_t row_bytes = (size_t)K * 2;
+      const size_t blk_bytes = (size_t)BLOCK_M * row_bytes;
+      for (int it = blockIdx.x; it < items; it += comm.comm_sms) {
+        const int step = it / mb_per_rank, mb = it % mb_per_rank;
+        const int dst = (comm.rank + step) % comm.world;          // step 0 = local copy
+        const uint8_t* src = (const uint8_t*)comm.a_local + (size_t)mb * blk_bytes;
+        uint8_t* dbase = (uint8_t*)comm.peer_bufs[dst] + comm.buf_offset +
+                         ((size_t)comm.rank * comm.rows_per_rank + (size_t)mb * BLOCK_M) * row_bytes;
+        const size_t nvec = blk_bytes / 16;
+        const uint4* s4 = (const uint4*)src;
+        uint4* d4 = (uint4*)dbase;
+        size_t i = threadIdx.x;
+        // 4 independent 16-byte loads in flight per thread
+        for (; i + 3 * kThreads < nvec; i += 4 * kThreads) {
+          const uint4 v0 = __ldg(s4 + i), v1 = __ldg(s4 + i + kThreads), v2 = __ldg(s4 + i + 2 * kThreads),
+                      v3 = __ldg(s4 + i + 3 * kThreads);
+          d4[i] = v0; d4[i + kThreads] = v1; d4[i + 2 * kThreads] = v2; d4[i + 3 * kThreads] = v3;
+        }
+        for (; i < nvec; i += kThreads) d4[i] = __ldg(s4 + i);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          uint32_t* f = (uint32_t*)comm.peer_flags[dst] + comm.flag_offset + comm.rank * mb_per_rank + mb;
+          st_release_sys(f, comm.epoch);
+        }
+      }
+    }
+  }
+
+  if (!is_comm_cta) {
+    if (warp == 0) {
+      // ===== TMA producer =====
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = gemm_cta; tile < num_tiles; tile += gemm_ctas) {
+          int m_blk, n_blk;
+          tile_coords<MODE>(tile, tiles_m, tiles_n, comm, m_blk, n_blk);
+          if constexpr (MODE == 1) {
+            const int mb_per_rank = comm.rows_per_rank / BLOCK_M;
+            const uint32_t* f = (const uint32_t*)comm.peer_flags[comm.rank] + comm.flag_offset + m_blk;
+            (void)mb_per_rank;
+            wait_flag_ge(f, comm.epoch);
+            fence_proxy_async_global();   // peer generic-proxy writes → visible to our TMA reads
+          }
+          const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t full = bar_full + 8 * stage;
+            mbar_expect_tx(full, kStageBytes);
+            const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+            const int k0 = kb * BLOCK_K;
+            if constexpr (A_KMAJOR) {
+              tma_load_2d(sa, &tma_a, full, k0, m0);                          // box {64 k, 128 m}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * 8192, &tma_a, full, m0 + j * 64, k0);  // box {64 m, 64 k}
+            }
+            if constexpr (B_KMAJOR) {
+              tma_load_2d(sb, &tma_b, full, k0, n0);                          // box {64 k, 256 n}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * 8192, &tma_b, full, n0 + j * 64, k0);  // box {64 n, 64 k}
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ===== MMA issuer =====
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(!A_KMAJOR, !B_KMAJOR, BLOCK_M, BLOCK_N);
+        int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+        for (int tile = gemm_cta; tile < num_tiles; tile += gemm_ctas) {
+          mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // K-major: advance 32 B inside the 128 B swizzle row; MN-major: 16 k-rows × 128 B = 2 KB
+              const uint64_t da = A_KMAJOR ? make_smem_desc(sa + k * 32, 16, 1024) : make_smem_desc(sa + k * 2048, 8192, 1024);
+              const uint64_t db = B_KMAJOR ? make_smem_desc(sb + k * 32, 16, 1024) : make_smem_desc(sb + k * 2048, 8192, 1024);
+              tcgen05_mma_f16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            tcgen05_commit(bar_empty + 8 * stage);   // smem stage reusable once these MMAs retire
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          tcgen05_commit(bar_tfull + 8 * as);        // accumulator complete
+          if (++as == kAccStages) { as = 0; aphase ^= 1; }
+        }
+      }
+      __syncwarp();
+    } else {
+      // ===== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====
+      const int q = warp & 3;
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = gemm_cta; tile < num_tiles; tile += gemm_ctas) {
+        int m_blk, n_blk;
+        tile_coords<MODE>(tile, tiles_m, tiles_n, comm, m_blk, n_blk);
+        mbar_wait(bar_tfull + 8 * as, aphase);
+        tcgen05_fence_after();
+        const int row = m_blk * BLOCK_M + q * 32 + lane;
+        const int n0 = n_blk * BLOCK_N;
+        OutT* orow;
+        int ld = N;
+        if constexpr (MODE == 2) {
+          // partial tile goes to the owner's staging slot [src = my rank][row in chunk][N]
+          const int owner = (m_blk * BLOCK_M) / comm.rows_per_rank;
+          const int lrow = row - owner * comm.rows_per_rank;
+          uint8_t* base = (uint8_t*)comm.peer_bufs[owner] + comm.buf_offset;
+          orow = (OutT*)base + ((size_t)comm.rank * comm.rows_per_rank + lrow) * (size_t)N;
+        } else {
+          orow = out + (size_t)row * ld;
+        }
+        const bool row_ok = row < M;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t r[32];
+          tcgen05_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, r);
+          tcgen05_wait_ld();
+          const int col0 = n0 + c * 32;
+          if (row_ok && col0 < N) {
+            if constexpr (sizeof(OutT) == 2) {
+              if (col0 + 32 <= N) {
+                uint4 pk[4];
+                __nv_bfloat162* h = (__nv_bfloat162*)pk;
+                if (accumulate && MODE != 2) {
+                  const uint4* old = (const uint4*)(orow + col0);
+#pragma unroll
+                  for (int v = 0; v < 4; ++v) {
+                    const uint4 o = old[v];
+                    const __nv_bfloat162* oh = (const __nv_bfloat162*)&o;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 of = __bfloat1622float2(oh[j]);
+                      h[v * 4 + j] = __floats2bfloat162_rn(__uint_as_float(r[v * 8 + 2 * j]) + of.x,
+                                                           __uint_as_float(r[v * 8 + 2 * j + 1]) + of.y);
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    h[j] = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                }
+                uint4* dst = (uint4*)(orow + col0);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) dst[v] = pk[v];
+              } else {
+                for (int j = 0; j < 32 && col0 + j < N; ++j) {
+                  float v = __uint_as_float(r[j]);
+                  if (accumulate && MODE != 2) v += __bfloat162float(((__nv_bfloat16*)orow)[col0 + j]);
+                  ((__nv_bfloat16*)orow)[col0 + j] = __float2bfloat16_rn(v);
+                }
+              }
+            } else {
+              if (col0 + 32 <= N) {
+                float4* dst = (float4*)(orow + col0);
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                  float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                         __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                  if (accumulate) { const float4 p = dst[v]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+                  dst[v] = o;
+                }
+              } else {
+                for (int j = 0; j < 32 && col0 + j < N; ++j) {
+                  float v = __uint_as_float(r[j]);
+                  if (accumulate) v += ((float*)orow)[col0 + j];
+                  ((float*)orow)[col0 + j] = v;
+                }
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        mbar_arrive(bar_tempty + 8 * as);            // TMEM stage may be overwritten
+        if constexpr (MODE == 2) {
+          // publish: all 128 epilogue threads' peer stores, then one counter bump on the owner
+          __threadfence_system();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) {
+            const int owner = (m_blk * BLOCK_M) / comm.rows_per_rank;
+            const int mb_in = m_blk - owner * (comm.rows_per_rank / BLOCK_M);
+            uint32_t* f = (uint32_t*)comm.peer_flags[owner] + comm.flag_offset +
+                          comm.rank * (comm.rows_per_rank / BLOCK_M) + mb_in;
+            red_add_release_sys(f, 1u);
+          }
+        }
+        if (++as == kAccStages) { as = 0; aphase ^= 1; }
+      }
+    }
+  }
+
+  if constexpr (MODE == 2) {
+    // ===== reducer phase: (row-block, 256-column slab) items of my chunk =====
+    __syncthreads();
+    const int mb_per_rank = comm.rows_per_rank / BLOCK_M;
+    const int slabs = (N + 255) / 256;
+    const int items = mb_per_rank * slabs;
+    const uint32_t* myflags = (const uint32_t*)comm.peer_flags[comm.rank] + comm.flag_offset;
+    const __nv_bfloat16* stage_base = (const __nv_bfloat16*)((const uint8_t*)comm.peer_bufs[comm.rank] + comm.buf_offset);
+    __nv_bfloat16* rout = (__nv_bfloat16*)comm.rs_out;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int mb = it / slabs, slab = it % slabs;
+      if (threadIdx.x < comm.world) {
+        // counter reaches epoch (cumulative number of n-tiles this source has ever sent for this row-block)
+        wait_flag_ge(myflags + threadIdx.x * mb_per_rank + mb, comm.epoch);
+      }
+      __syncthreads();
+      const int c0 = slab * 256;
+      const int cols = min(256, N - c0);
+      const int vec_per_row = cols / 8;
+      for (int idx = threadIdx.x; idx < BLOCK_M * vec_per_row; idx += kThreads) {
+        const int r = idx / vec_per_row, v = idx % vec_per_row;
+        const size_t off = ((size_t)(mb * BLOCK_M + r)) * N + c0 + v * 8;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int s = 0; s < comm.world; ++s) {
+          const uint4 raw = *(const uint4*)(stage_base + (size_t)s * comm.rows_per_rank * N + off);
+          const __nv_bfloat162* h = (const __nv_bfloat162*)&raw;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+        }
+        uint4 o; __nv_bfloat162* oh = (__nv_bfloat162*)&o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+        *(uint4*)(rout + off) = o;
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tcgen05_dealloc(tmem_base, kTmemCols); }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    NXD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) nxd_throw("cuTensorMapEncodeTiled not available", __FILE__, __LINE__);
+    fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] (cols contiguous); box = {box_cols, box_rows}; 128B swizzle.
+static CUtensorMap make_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) nxd_throw("cuTensorMapEncodeTiled failed: " + std::to_string((int)r), __FILE__, __LINE__);
+  return m;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+  return n;
+}
+
+template <bool AK, bool BK, int MODE, typename OutT>
+static void launch(const CUtensorMap& ta, const CUtensorMap& tb, void* out, int M, int N, int K, bool accumulate,
+                   const CommDev& c, int grid, cudaStream_t st) {
+  auto kern = gemm_bf16_kernel<AK, BK, MODE, OutT>;
+  static bool configured = false;
+  if (!configured) {
+    NXD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  kern<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, (OutT*)out, M, N, K, accumulate ? 1 : 0, c);
+  NXD_CUDA_CHECK(cudaGetLastError());
+}
+
+void gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, bool trans_a, bool trans_b, int out_dt,
+               bool accumulate, const GemmComm& comm, const void* a_local_shard, cudaStream_t st) {
+  // trans_a=false: a is [M,K] (K-major).  trans_a=true: a is [K,M] (MN-major).
+  // trans_b=true : b is [N,K] (K-major).  trans_b=false: b is [K,N] (MN-major).
+  const bool AK = !trans_a, BK = trans_b;
+  const CUtensorMap ta = AK ? make_tmap(a, M, K, BLOCK_K, BLOCK_M) : make_tmap(a, K, M, 64, BLOCK_K);
+  const CUtensorMap tb = BK ? make_tmap(b, N, K, BLOCK_K, BLOCK_N) : make_tmap(b, K, N, 64, BLOCK_K);
+  CommDev c{};
+  c.rank = comm.rank; c.world = comm.world; c.peer_bufs = comm.peer_bufs; c.peer_flags = comm.peer_flags;
+  c.buf_offset = comm.buf_offset; c.flag_offset = comm.flag_offset; c.epoch = comm.epoch; c.comm_sms = comm.comm_sms;
+  c.rows_per_rank = comm.world > 0 ? M / comm.world : M;
+  c.a_local = a_local_shard; c.rs_out = out;
+  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int sms = sm_count();
+  if (comm.mode != 0) {
+    if (c.rows_per_rank % BLOCK_M || M % comm.world) nxd_throw("fused TP GEMM needs rows/rank % 128 == 0", __FILE__, __LINE__);
+    if (comm.mode == 2 && (N % 8)) nxd_throw("GEMM→RS needs N % 8 == 0", __FILE__, __LINE__);
+  }
+#define NXD_LAUNCH(AKv, BKv)                                                                                          \
+  do {                                                                                                                \
+    if (comm.mode == 1) {                                                                                             \
+      if (out_dt == kBF16) launch<AKv, BKv, 1, __nv_bfloat16>(ta, tb, out, M, N, K, accumulate, c, sms, st);          \
+      else launch<AKv, BKv, 1, float>(ta, tb, out, M, N, K, accumulate, c, sms, st);                                  \
+    } else if (comm.mode == 2) {                                                                                      \
+      launch<AKv, BKv, 2, __nv_bfloat16>(ta, tb, out, M, N, K, false, c, sms, st);                                    \
+    } else {                                                                                                          \
+      const int grid = tiles < sms ? tiles : sms;                                                                     \
+      if (out_dt == kBF16) launch<AKv, BKv, 0, __nv_bfloat16>(ta, tb, out, M, N, K, accumulate, c, grid, st);         \
+      else launch<AKv, BKv, 0, float>(ta, tb, out, M, N, K, accumulate, c, grid, st);                                 \
+    }                                                                                                                 \
+  } while (0)
+  if (AK && BK) NXD_LAUNCH(true, true);
+  else if (AK && !BK) NXD_LAUNCH(true, false);
+  else if (!AK && !BK) NXD_LAUNCH(false, false);
+  else NXD_LAUNCH(false, true);
+#undef NXD_LAUNCH
+}
+
+bool gemm_self_check_supported() { return true; }
+
+}  // namespace nxd

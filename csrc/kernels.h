@@ -1,0 +1,50 @@
+// Launcher declarations shared between the .cu translation units and binding.cpp.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+
+namespace nxd {
+
+enum DType : int { kF32 = 0, kBF16 = 1, kF16 = 2 };
+
+// ---- elementwise.cu
+void rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H, float eps, int dt, cudaStream_t st);
+int rmsnorm_bwd_num_partials(int rows);
+void rmsnorm_bwd(const void* g, const void* x, const void* w, const float* rstd, void* dx, float* partial, float* dw,
+                 int rows, int H, int dt, cudaStream_t st);
+void swiglu_fwd(const void* gu, void* out, long rows, int I, int dt, cudaStream_t st);
+void swiglu_bwd(const void* go, const void* gu, void* dgu, long rows, int I, int dt, cudaStream_t st);
+void rope_apply(const void* x, void* out, const float* cos_t, const float* sin_t, int B, int S, int Hh, int D, long sb,
+                long ss, long sh, float sign, int dt, cudaStream_t st);
+void ce_stats(const void* logits, const int64_t* target, float* stats, int rows, int V, int vocab_start, int dt,
+              cudaStream_t st);
+void ce_backward(const void* logits, const int64_t* target, const float* lse, const float* gout, void* grad, int rows,
+                 int V, int vocab_start, float smoothing, int vocab, int dt, cudaStream_t st);
+
+// ---- optim.cu
+struct TensorRef { void* ptr; long numel; };
+void multi_tensor_sq_norm(const std::vector<TensorRef>& ts, int dt, float* out, cudaStream_t st);
+void multi_tensor_scale(const std::vector<TensorRef>& ts, int dt, const float* scale, cudaStream_t st);
+// p,m,v fp32; g dtype gdt; optional low-precision copy lowp (dtype ldt, may be empty)
+void fused_adamw(const std::vector<TensorRef>& p, const std::vector<TensorRef>& g, const std::vector<TensorRef>& m,
+                 const std::vector<TensorRef>& v, const std::vector<TensorRef>& lowp, int gdt, int ldt, float lr,
+                 float beta1, float beta2, float eps, float wd, float bc1, float bc2, const float* grad_scale,
+                 cudaStream_t st);
+
+// ---- gemm_sm100.cu
+struct GemmComm {          // in-kernel NVLink communication description (all zero → plain GEMM)
+  int mode = 0;            // 0 none, 1 all-gather A rows then GEMM, 2 GEMM then reduce-scatter rows
+  int rank = 0, world = 1;
+  const int64_t* peer_bufs = nullptr;   // device table [world] of peer payload base addresses
+  const int64_t* peer_flags = nullptr;  // device table [world] of peer flag base addresses
+  long buf_offset = 0;     // byte offset of this call's payload region inside every peer buffer
+  int flag_offset = 0;     // index of this call's first flag
+  uint32_t epoch = 0;      // monotonically increasing per (workspace, purpose)
+  int comm_sms = 0;        // CTAs dedicated to communication (mode 1)
+};
+void gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, bool trans_a, bool trans_b, int out_dt,
+               bool accumulate, const GemmComm& comm, const void* a_local_shard, cudaStream_t st);
+bool gemm_self_check_supported();
+
+}  // namespace nxd

@@ -113,8 +113,9 @@ class GQAQKVColumnParallelLinear(BaseParallelLayer):
             # tensor is [Q ; K_rep ; V_rep] with stride-3-like semantics expressed by
             # `fused_qkv`/`num_attention_heads`… attrs used by the checkpoint sharder.
             self.weight_qkv = Parameter(torch.empty(qp + 2 * kvp, input_size, dtype=dtype, device=self.device))
-            self.bias_qkv = Parameter(torch.zeros(qp + 2 * kvp, dtype=dtype, device=self.device)) if bias else None
-            if not bias:
+            if bias:
+                self.bias_qkv = Parameter(torch.zeros(qp + 2 * kvp, dtype=dtype, device=self.device))
+            else:
                 self.register_parameter("bias_qkv", None)
         else:
             self.weight_q = Parameter(torch.empty(qp, input_size, dtype=dtype, device=self.device))

@@ -1,0 +1,175 @@
+"""On-GPU numerics + timing smoke for every hand-written kernel (run under gpurun).
+
+usage: python tools/gpu_check.py [elementwise|gemm|gemm_perf|all]
+Each check prints one line `CHECK name PASS/FAIL max_err=…`; results are also appended to
+gpurun_out/gpu_check.jsonl.  Comparison target is always a plain PyTorch fp32 reference."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from neuronx_distributed_b200 import ops  # noqa: E402
+
+OUT = os.path.join(os.environ.get("GRAFT_REPO_ROOT", "."), "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+dev = torch.device("cuda")
+RESULTS = []
+
+
+def report(name, ok, **kw):
+    rec = {"name": name, "ok": bool(ok), **{k: (float(v) if isinstance(v, (int, float)) else v) for k, v in kw.items()}}
+    RESULTS.append(rec)
+    print("CHECK", name, "PASS" if ok else "FAIL", " ".join(f"{k}={v}" for k, v in kw.items()), flush=True)
+    with open(os.path.join(OUT, "gpu_check.jsonl"), "a") as f:
+        f.write(json.dumps(rec) + "\n")
+
+
+def relerr(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-6))
+
+
+def timeit(fn, iters=20, warmup=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    times = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        torch.cuda.synchronize()
+        times.append(s.elapsed_time(e))
+    times.sort()
+    return times[len(times) // 2]
+
+
+def check_elementwise():
+    torch.manual_seed(0)
+    T, H = 1024, 4096
+    for dt in (torch.bfloat16, torch.float32):
+        x = torch.randn(T, H, device=dev, dtype=dt)
+        w = (torch.rand(H, device=dev) + 0.5).to(dt)
+        xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+        ref = (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-5) * wr)
+        g = torch.randn_like(ref)
+        ref.backward(g)
+        xx, ww = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        y = ops.norm.rms_norm(xx, ww, 1e-5)
+        y.backward(g.to(dt))
+        tol = 2e-2 if dt == torch.bfloat16 else 1e-5
+        report(f"rmsnorm_fwd_{dt}", relerr(y, ref) < tol, err=relerr(y, ref))
+        report(f"rmsnorm_dx_{dt}", relerr(xx.grad, xr.grad) < tol, err=relerr(xx.grad, xr.grad))
+        report(f"rmsnorm_dw_{dt}", relerr(ww.grad, wr.grad) < tol, err=relerr(ww.grad, wr.grad))
+    # swiglu
+    gu = torch.randn(T, 2 * 2752, device=dev, dtype=torch.bfloat16)
+    gur = gu.float().requires_grad_(True)
+    a, b = gur.chunk(2, -1)
+    ref = torch.nn.functional.silu(a) * b
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    gg = gu.clone().requires_grad_(True)
+    y = ops.act.swiglu(gg)
+    y.backward(g.bfloat16())
+    report("swiglu_fwd", relerr(y, ref) < 2e-2, err=relerr(y, ref))
+    report("swiglu_bwd", relerr(gg.grad, gur.grad) < 2e-2, err=relerr(gg.grad, gur.grad))
+    # rope on a transposed [S,B,h,D] view
+    S, B, Hh, D = 512, 2, 4, 128
+    base = torch.randn(S, B, Hh * D, device=dev, dtype=torch.bfloat16)
+    q = base.view(S, B, Hh, D).transpose(0, 1)
+    cos, sin = ops.rope.rope_tables(S, D, device=dev)
+    from neuronx_distributed_b200.ops.rope import _rope_ref
+    qq = q.detach().clone().requires_grad_(True)
+    out = ops.rope.apply_rotary(qq, cos, sin)
+    ref = _rope_ref(q.float(), cos, sin, 1.0)
+    report("rope_fwd", relerr(out, ref) < 2e-2, err=relerr(out, ref))
+    g = torch.randn_like(out)
+    out.backward(g)
+    refb = _rope_ref(g.float(), cos, sin, -1.0)
+    report("rope_bwd", relerr(qq.grad, refb) < 2e-2, err=relerr(qq.grad, refb))
+    # cross entropy
+    for V, dt in ((4000, torch.bfloat16), (32000, torch.float32)):
+        Tt = 512
+        logits = torch.randn(Tt, V, device=dev, dtype=dt) * 3
+        tgt = torch.randint(0, V, (Tt,), device=dev)
+        lr = logits.float().requires_grad_(True)
+        ref = torch.nn.functional.cross_entropy(lr, tgt, reduction="none")
+        ref.sum().backward()
+        st = ops.cross_entropy.ce_stats(logits, tgt, 0)
+        lse = st[:, 0] + torch.log(st[:, 1])
+        loss = lse - st[:, 2]
+        report(f"ce_stats_V{V}", relerr(loss, ref) < (2e-2 if dt == torch.bfloat16 else 1e-4), err=relerr(loss, ref))
+        gr = ops.cross_entropy.ce_backward(logits, tgt, lse, torch.ones(Tt, device=dev), 0, 0.0, V)
+        report(f"ce_bwd_V{V}", relerr(gr, lr.grad) < (2e-2 if dt == torch.bfloat16 else 1e-4), err=relerr(gr, lr.grad))
+    # multi tensor ops + adamw
+    ts = [torch.randn(n, device=dev, dtype=torch.bfloat16) for n in (5, 1000, 65536 * 3 + 17, 4096 * 4096)]
+    ref = sum(t.float().pow(2).sum() for t in ts)
+    got = ops.optim.multi_tensor_sq_norm(ts)
+    report("multi_sq_norm", abs(float(got) - float(ref)) / float(ref) < 1e-3, got=float(got), ref=float(ref))
+    ts2 = [t.clone() for t in ts]
+    ops.optim.multi_tensor_scale_(ts2, torch.tensor(0.5, device=dev))
+    report("multi_scale", all(relerr(a, b.float() * 0.5) < 1e-2 for a, b in zip(ts2, ts)))
+    n = 65536 * 2 + 33
+    p = torch.randn(n, device=dev); g = torch.randn(n, device=dev, dtype=torch.bfloat16)
+    m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev); low = torch.zeros(n, device=dev, dtype=torch.bfloat16)
+    pr, mr, vr = p.clone(), m.clone(), v.clone()
+    ops.optim.fused_adamw_([p], [g], [m], [v], 1e-2, 0.9, 0.95, 1e-8, 0.1, 1, torch.tensor(0.7, device=dev), [low])
+    g32 = g.float() * 0.7
+    pr.mul_(1 - 1e-2 * 0.1); mr.mul_(0.9).add_(g32, alpha=0.1); vr.mul_(0.95).addcmul_(g32, g32, value=0.05)
+    pr.addcdiv_(mr / (1 - 0.9), (vr / (1 - 0.95)).sqrt() + 1e-8, value=-1e-2)
+    report("fused_adamw", relerr(p, pr) < 1e-5 and relerr(low, pr) < 1e-2, perr=relerr(p, pr), lowerr=relerr(low, pr))
+
+
+def check_gemm(perf=False):
+    torch.manual_seed(0)
+    shapes = [(128, 256, 64), (256, 512, 256), (384, 768, 192), (4096, 1536, 4096), (512, 4096, 1376), (1000, 264, 72)]
+    for (M, N, K) in shapes:
+        for ta, tb in ((False, True), (False, False), (True, False)):
+            a = torch.randn((K, M) if ta else (M, K), device=dev, dtype=torch.bfloat16)
+            b = torch.randn((N, K) if tb else (K, N), device=dev, dtype=torch.bfloat16)
+            ref = (a.float().t() if ta else a.float()) @ (b.float().t() if tb else b.float())
+            try:
+                out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+                ops._ext.ext().gemm_bf16(a, b, out, ta, tb, False)
+                torch.cuda.synchronize()
+                err = relerr(out, ref)
+                report(f"gemm_{M}x{N}x{K}_ta{int(ta)}_tb{int(tb)}", err < 1e-2, err=err)
+            except Exception as e:  # noqa: BLE001
+                report(f"gemm_{M}x{N}x{K}_ta{int(ta)}_tb{int(tb)}", False, exc=repr(e)[:200])
+    # fp32 out + accumulate
+    M, N, K = 256, 512, 128
+    a = torch.randn(M, K, device=dev, dtype=torch.bfloat16); b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+    out = torch.ones(M, N, device=dev, dtype=torch.float32)
+    ops._ext.ext().gemm_bf16(a, b, out, False, True, True)
+    ref = a.float() @ b.float().t() + 1
+    report("gemm_f32_accumulate", relerr(out, ref) < 1e-3, err=relerr(out, ref))
+
+
+def check_gemm_perf():
+    peaks = {}
+    for (M, N, K) in [(4096, 1536, 4096), (4096, 2752, 4096), (4096, 4096, 512), (4096, 4096, 1376), (4096, 4000, 4096),
+                      (4096, 12288, 4096), (4096, 22016, 4096), (4096, 4096, 11008), (8192, 8192, 8192)]:
+        a = torch.randn(M, K, device=dev, dtype=torch.bfloat16); b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        t_own = timeit(lambda: ops._ext.ext().gemm_bf16(a, b, out, False, True, False))
+        t_lib = timeit(lambda: torch.matmul(a, b.t()))
+        fl = 2.0 * M * N * K
+        report(f"gemm_perf_{M}x{N}x{K}", True, own_ms=t_own, cublas_ms=t_lib, own_tflops=fl / t_own / 1e9,
+               cublas_tflops=fl / t_lib / 1e9)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    assert ops.extension_available(), ops._ext.load_error()
+    if what in ("elementwise", "all"):
+        check_elementwise()
+    if what in ("gemm", "all"):
+        check_gemm()
+    if what in ("gemm_perf", "all"):
+        check_gemm_perf()
+    bad = [r["name"] for r in RESULTS if not r["ok"]]
+    print("SUMMARY", len(RESULTS) - len(bad), "passed,", len(bad), "failed", bad, flush=True)
