@@ -146,9 +146,9 @@ static void gemm_bf16(const Tensor& a, const Tensor& b, Tensor out, bool trans_a
 
 // all-gather(A shards along rows) → GEMM.  `a_shard` [M/world, K]; gathered A lives in the symmetric payload at
 // buf_offset (every rank), out = A_full @ op(B).
-static void ag_gemm_bf16(const Tensor& a_shard, const Tensor& b, Tensor out, bool trans_b, const Tensor& peer_bufs,
-                         const Tensor& peer_flags, int64_t buf_offset, int64_t flag_offset, int64_t epoch, int64_t rank,
-                         int64_t world, int64_t comm_sms) {
+static void ag_gemm_bf16(const Tensor& a_shard, const Tensor& b, Tensor out, bool trans_b, int64_t local_buf_ptr,
+                         const Tensor& peer_bufs, const Tensor& peer_flags, int64_t buf_offset, int64_t flag_offset,
+                         int64_t epoch, int64_t rank, int64_t world, int64_t comm_sms) {
   CHECK_IN(a_shard); CHECK_IN(b); CHECK_IN(out);
   const int Ms = (int)a_shard.size(0), K = (int)a_shard.size(1), M = Ms * (int)world;
   const int N = (int)(trans_b ? b.size(0) : b.size(1));
@@ -159,8 +159,7 @@ static void ag_gemm_bf16(const Tensor& a_shard, const Tensor& b, Tensor out, boo
   c.peer_bufs = peer_bufs.data_ptr<int64_t>(); c.peer_flags = peer_flags.data_ptr<int64_t>();
   c.buf_offset = buf_offset; c.flag_offset = (int)flag_offset; c.epoch = (uint32_t)epoch; c.comm_sms = (int)comm_sms;
   // A operand = this rank's gathered buffer
-  auto host_ptrs = peer_bufs.cpu();
-  const void* a_full = (const void*)(host_ptrs.data_ptr<int64_t>()[rank] + buf_offset);
+  const void* a_full = (const void*)(local_buf_ptr + buf_offset);
   nxd::gemm_bf16(a_full, b.data_ptr(), out.data_ptr(), M, N, K, false, trans_b, dt_code(out), false, c,
                  a_shard.data_ptr(), stream());
 }
@@ -168,7 +167,7 @@ static void ag_gemm_bf16(const Tensor& a_shard, const Tensor& b, Tensor out, boo
 // GEMM → reduce-scatter over rows.  a [M, K]; out [M/world, N] bf16 (sum over ranks of rows owned by this rank).
 static void gemm_rs_bf16(const Tensor& a, const Tensor& b, Tensor out, bool trans_b, int64_t local_buf_ptr,
                          const Tensor& peer_bufs, const Tensor& peer_flags, int64_t buf_offset, int64_t flag_offset,
-                         int64_t epoch, int64_t rank, int64_t world) {
+                         const std::vector<int64_t>& targets, int64_t rank, int64_t world) {
   CHECK_IN(a); CHECK_IN(b); CHECK_IN(out);
   const int M = (int)a.size(0), K = (int)a.size(1);
   const int N = (int)(trans_b ? b.size(0) : b.size(1));
@@ -178,7 +177,10 @@ static void gemm_rs_bf16(const Tensor& a, const Tensor& b, Tensor out, bool tran
   nxd::GemmComm c;
   c.mode = 2; c.rank = (int)rank; c.world = (int)world;
   c.peer_bufs = peer_bufs.data_ptr<int64_t>(); c.peer_flags = peer_flags.data_ptr<int64_t>();
-  c.buf_offset = buf_offset; c.flag_offset = (int)flag_offset; c.epoch = (uint32_t)epoch;
+  c.buf_offset = buf_offset; c.flag_offset = (int)flag_offset; c.epoch = 0;
+  uint32_t tg[64] = {0};
+  for (size_t i = 0; i < targets.size() && i < 64; ++i) tg[i] = (uint32_t)targets[i];
+  c.rs_targets = tg;
   nxd::gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, false, trans_b, nxd::kBF16, false, c, nullptr,
                  stream());
 }

@@ -45,6 +45,7 @@ constexpr int kThreads = 192;
 constexpr int kEpilogueThreads = 128;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = kAccStages * BLOCK_N;  // 512
+constexpr int kMaxRowBlocks = 64;   // flag index = source_rank * kMaxRowBlocks + row_block (shape independent)
 
 // ------------------------------------------------------------------ PTX wrappers
 NXD_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -145,6 +146,7 @@ struct CommDev {
   uint32_t epoch;
   int comm_sms;
   int rows_per_rank;      // M / world
+  uint32_t rs_targets[kMaxRowBlocks];   // MODE 2: cumulative n-tile count expected per row-block counter
   const void* a_local;    // MODE 1: this rank's [rows_per_rank, K] shard
   void* rs_out;           // MODE 2: reduced [rows_per_rank, N] output
 };
@@ -242,7 +244,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
-          uint32_t* f = (uint32_t*)comm.peer_flags[dst] + comm.flag_offset + comm.rank * mb_per_rank + mb;
+          uint32_t* f = (uint32_t*)comm.peer_flags[dst] + comm.flag_offset + comm.rank * kMaxRowBlocks + mb;
           st_release_sys(f, comm.epoch);
         }
       }
@@ -259,8 +261,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           tile_coords<MODE>(tile, tiles_m, tiles_n, comm, m_blk, n_blk);
           if constexpr (MODE == 1) {
             const int mb_per_rank = comm.rows_per_rank / BLOCK_M;
-            const uint32_t* f = (const uint32_t*)comm.peer_flags[comm.rank] + comm.flag_offset + m_blk;
-            (void)mb_per_rank;
+            const uint32_t* f = (const uint32_t*)comm.peer_flags[comm.rank] + comm.flag_offset +
+                                (m_blk / mb_per_rank) * kMaxRowBlocks + (m_blk % mb_per_rank);
             wait_flag_ge(f, comm.epoch);
             fence_proxy_async_global();   // peer generic-proxy writes → visible to our TMA reads
           }
@@ -407,8 +409,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (threadIdx.x == 64) {
             const int owner = (m_blk * BLOCK_M) / comm.rows_per_rank;
             const int mb_in = m_blk - owner * (comm.rows_per_rank / BLOCK_M);
-            uint32_t* f = (uint32_t*)comm.peer_flags[owner] + comm.flag_offset +
-                          comm.rank * (comm.rows_per_rank / BLOCK_M) + mb_in;
+            uint32_t* f = (uint32_t*)comm.peer_flags[owner] + comm.flag_offset + comm.rank * kMaxRowBlocks + mb_in;
             red_add_release_sys(f, 1u);
           }
         }
@@ -430,7 +431,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int mb = it / slabs, slab = it % slabs;
       if (threadIdx.x < comm.world) {
         // counter reaches epoch (cumulative number of n-tiles this source has ever sent for this row-block)
-        wait_flag_ge(myflags + threadIdx.x * mb_per_rank + mb, comm.epoch);
+        wait_flag_ge(myflags + threadIdx.x * kMaxRowBlocks + mb, comm.rs_targets[mb]);
       }
       __syncthreads();
       const int c0 = slab * 256;
@@ -525,6 +526,8 @@ void gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, boo
   c.buf_offset = comm.buf_offset; c.flag_offset = comm.flag_offset; c.epoch = comm.epoch; c.comm_sms = comm.comm_sms;
   c.rows_per_rank = comm.world > 0 ? M / comm.world : M;
   c.a_local = a_local_shard; c.rs_out = out;
+  for (int i = 0; i < kMaxRowBlocks; ++i) c.rs_targets[i] = comm.rs_targets ? comm.rs_targets[i] : 0u;
+  if (comm.mode != 0 && c.rows_per_rank / BLOCK_M > kMaxRowBlocks) nxd_throw("too many row blocks per rank", __FILE__, __LINE__);
   const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int sms = sm_count();
   if (comm.mode != 0) {

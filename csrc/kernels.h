@@ -42,6 +42,7 @@ struct GemmComm {          // in-kernel NVLink communication description (all ze
   int flag_offset = 0;     // index of this call's first flag
   uint32_t epoch = 0;      // monotonically increasing per (workspace, purpose)
   int comm_sms = 0;        // CTAs dedicated to communication (mode 1)
+  const uint32_t* rs_targets = nullptr;  // host array [64]: cumulative per-row-block tile counts (mode 2)
 };
 void gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, bool trans_a, bool trans_b, int out_dt,
                bool accumulate, const GemmComm& comm, const void* a_local_shard, cudaStream_t st);

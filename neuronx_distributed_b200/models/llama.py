@@ -48,6 +48,7 @@ class LlamaConfig:
     pad_token_id: Optional[int] = None
     # context parallel: each CP rank holds a contiguous S/cp slice; positions are offset
     context_parallel: bool = False
+    device: Optional[torch.device] = None       # construct parameters directly here (e.g. cuda)
 
     def __post_init__(self):
         if self.num_key_value_heads is None:
@@ -88,11 +89,11 @@ class LlamaMLP(nn.Module):
         # stride=2 interleaves [gate; up] so each rank's shard is [gate_r ; up_r]
         self.gate_up_proj = ColumnParallelLinear(
             cfg.hidden_size, 2 * cfg.intermediate_size, bias=False, gather_output=False, stride=2,
-            init_method=init, sequence_parallel_enabled=sp, sequence_dimension=0, dtype=cfg.dtype,
+            init_method=init, sequence_parallel_enabled=sp, sequence_dimension=0, dtype=cfg.dtype, device=cfg.device,
         )
         self.down_proj = RowParallelLinear(
             cfg.intermediate_size, cfg.hidden_size, bias=False, input_is_parallel=True, init_method=init,
-            sequence_parallel_enabled=sp, sequence_dimension=0, dtype=cfg.dtype,
+            sequence_parallel_enabled=sp, sequence_dimension=0, dtype=cfg.dtype, device=cfg.device,
         )
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -118,11 +119,11 @@ class LlamaAttention(nn.Module):
             [cfg.num_attention_heads * self.head_dim, cfg.num_key_value_heads * self.head_dim],
             bias=False, gather_output=False, init_method=init, sequence_parallel_enabled=sp,
             kv_size_multiplier=kv_mult, fuse_qkv=cfg.fuse_qkv, dtype=cfg.dtype, sequence_dimension=0,
-            head_dim=self.head_dim,
+            head_dim=self.head_dim, device=cfg.device,
         )
         self.o_proj = RowParallelLinear(
             cfg.num_attention_heads * self.head_dim, cfg.hidden_size, bias=False, input_is_parallel=True,
-            init_method=init, sequence_parallel_enabled=sp, sequence_dimension=0, dtype=cfg.dtype,
+            init_method=init, sequence_parallel_enabled=sp, sequence_dimension=0, dtype=cfg.dtype, device=cfg.device,
         )
 
     def forward(self, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
@@ -149,10 +150,10 @@ class LlamaDecoderLayer(nn.Module):
     def __init__(self, cfg: LlamaConfig):
         super().__init__()
         sp = cfg.sequence_parallel_enabled
-        self.input_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, sequence_parallel_enabled=sp, dtype=cfg.dtype)
+        self.input_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, sequence_parallel_enabled=sp, dtype=cfg.dtype, device=cfg.device)
         self.self_attn = LlamaAttention(cfg)
         self.post_attention_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, sequence_parallel_enabled=sp,
-                                                dtype=cfg.dtype)
+                                                dtype=cfg.dtype, device=cfg.device)
         self.mlp = LlamaMLP(cfg)
 
     def forward(self, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
@@ -167,11 +168,11 @@ class LlamaModel(nn.Module):
         self.cfg = cfg
         self.embed_tokens = ParallelEmbedding(
             cfg.vocab_size, cfg.hidden_size, init_method=_normal_init(cfg.initializer_range), dtype=cfg.dtype,
-            sequence_parallel_enabled=cfg.sequence_parallel_enabled,
+            sequence_parallel_enabled=cfg.sequence_parallel_enabled, device=cfg.device,
         )
         self.layers = nn.ModuleList([LlamaDecoderLayer(cfg) for _ in range(cfg.num_hidden_layers)])
         self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, sequence_parallel_enabled=cfg.sequence_parallel_enabled,
-                            dtype=cfg.dtype)
+                            dtype=cfg.dtype, device=cfg.device)
         self._rope_cache: Optional[Tuple[int, int, torch.device, torch.Tensor, torch.Tensor]] = None
 
     def rope(self, seq_len: int, device, offset: int = 0):
@@ -210,7 +211,7 @@ class LlamaForCausalLM(nn.Module):
         self.lm_head = ColumnParallelLinear(
             cfg.hidden_size, cfg.vocab_size, bias=False, gather_output=False,
             init_method=_normal_init(cfg.initializer_range), sequence_parallel_enabled=cfg.sequence_parallel_enabled,
-            sequence_dimension=0, dtype=cfg.dtype,
+            sequence_dimension=0, dtype=cfg.dtype, device=cfg.device,
         )
         if cfg.tie_word_embeddings:
             self.lm_head.weight = self.model.embed_tokens.weight

@@ -133,7 +133,7 @@ class GQAQKVColumnParallelLinear(BaseParallelLayer):
 
     # ------------------------------------------------------------------ init
     def _init_full(self, rows: int) -> torch.Tensor:
-        w = torch.empty(rows, self.input_size, dtype=torch.float32)
+        w = torch.empty(rows, self.input_size, dtype=torch.float32, device=self.device)
         if self.arg_init_method is None:
             init.kaiming_uniform_(w, a=math.sqrt(5))
         else:

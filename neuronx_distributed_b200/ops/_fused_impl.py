@@ -1,0 +1,188 @@
+"""Fused tensor-parallel linear paths on the sm_100a GEMM+collective kernels (``csrc/gemm_sm100.cu``).
+
+Column + sequence-parallel  (``in_mode="gather"``):
+    fwd   y      = AG(x) @ Wᵀ                  → ``ag_gemm``   (MODE 1, B K-major)
+    bwd   dx     = RS(g @ W)                   → ``gemm_rs``   (MODE 2, B MN-major)
+          dW     = gᵀ @ AG(x)                  → plain tcgen05 GEMM on the gathered x saved by the forward
+Row + sequence-parallel     (``out_mode="scatter"``):
+    fwd   y      = RS(x @ Wᵀ)                  → ``gemm_rs``   (MODE 2, B K-major)
+    bwd   dx     = AG(g) @ W                   → ``ag_gemm``   (MODE 1, B MN-major)
+          dW     = AG(g)ᵀ @ x                  → plain GEMM reading AG(g) straight from the symmetric buffer
+
+Design choice vs the reference: the gathered activation is kept (one D2D copy out of the symmetric
+buffer) instead of being re-all-gathered in backward (reference layers_utils.py:82-87) — HBM is
+plentiful on B200 and NVLink is the scarce resource on these paths.  Wire dtype is bf16 with fp32
+accumulation at the owner (the reference reduces fp32 on the wire, layers.py:1031-1045); see DESIGN.md.
+
+Protocol state (epochs, cumulative counters) lives in :class:`TPWorkspace`, one per process group.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _ext, gemm, symm
+
+BLOCK_M = 128
+MAX_ROW_BLOCKS = 64
+_FLAGS_AG = 0
+_FLAGS_RS = 2048
+_NFLAGS = 4096
+_COMM_SMS = int(os.environ.get("NXD_AG_COMM_SMS", "16"))
+
+
+class TPWorkspace:
+    """Symmetric buffers + protocol counters for one TP group."""
+
+    def __init__(self, group):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.ag_bytes = 0
+        self.rs_bytes = 0
+        self.ws: Optional[symm.SymmWorkspace] = None
+        self.ag_epoch = 0
+        self.rs_calls = 0
+        self.rs_counts = [0] * MAX_ROW_BLOCKS
+
+    def _ensure(self, ag_bytes: int, rs_bytes: int) -> None:
+        if self.ws is not None and ag_bytes <= self.ag_bytes and rs_bytes <= self.rs_bytes:
+            return
+        # (re)allocate collectively; all ranks see the same shapes so they arrive here together
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.ag_bytes = max(self.ag_bytes, _round(ag_bytes), _round(int(os.environ.get("NXD_SYMM_MIN_MB", "32")) << 20))
+        self.rs_bytes = max(self.rs_bytes, _round(rs_bytes), _round(int(os.environ.get("NXD_SYMM_MIN_MB", "32")) << 20))
+        self.ws = symm.get_workspace(self.group, "tp", 2 * self.ag_bytes + 2 * self.rs_bytes, _NFLAGS)
+        self.ag_epoch, self.rs_calls, self.rs_counts = 0, 0, [0] * MAX_ROW_BLOCKS
+
+    # ------------------------------------------------------------------ all-gather → GEMM
+    def ag_gemm(self, a_shard: torch.Tensor, b: torch.Tensor, trans_b: bool, out_dtype=torch.bfloat16
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Returns ``(out [M, N], gathered_A view [M, K] in the symmetric buffer)``."""
+        ms, K = a_shard.shape
+        M = ms * self.world
+        N = b.shape[0] if trans_b else b.shape[1]
+        self._ensure(M * K * 2, 0)
+        self.ag_epoch += 1
+        off = (self.ag_epoch & 1) * self.ag_bytes
+        out = torch.empty(M, N, dtype=out_dtype, device=a_shard.device)
+        _ext.count_launch()
+        _ext.ext().ag_gemm_bf16(a_shard, b, out, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs, off,
+                                _FLAGS_AG, self.ag_epoch, self.rank, self.world, _COMM_SMS)
+        gathered = self.ws.local_tensor(off, (M, K), torch.bfloat16)
+        return out, gathered
+
+    # ------------------------------------------------------------------ GEMM → reduce-scatter
+    def gemm_rs(self, a: torch.Tensor, b: torch.Tensor, trans_b: bool) -> torch.Tensor:
+        M, K = a.shape
+        N = b.shape[0] if trans_b else b.shape[1]
+        ms = M // self.world
+        self._ensure(0, M * N * 2)
+        self.rs_calls += 1
+        off = 2 * self.ag_bytes + (self.rs_calls & 1) * self.rs_bytes
+        tiles_n = (N + 255) // 256
+        for mb in range(ms // BLOCK_M):
+            self.rs_counts[mb] = (self.rs_counts[mb] + tiles_n) & 0xFFFFFFFF
+        out = torch.empty(ms, N, dtype=torch.bfloat16, device=a.device)
+        _ext.count_launch()
+        _ext.ext().gemm_rs_bf16(a, b, out, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs, off, _FLAGS_RS,
+                                list(self.rs_counts), self.rank, self.world)
+        return out
+
+
+def _round(n: int) -> int:
+    return (int(n) + (1 << 21) - 1) & ~((1 << 21) - 1)
+
+
+_WORKSPACES: Dict[int, TPWorkspace] = {}
+
+
+def workspace(group) -> TPWorkspace:
+    ws = _WORKSPACES.get(id(group))
+    if ws is None:
+        ws = _WORKSPACES[id(group)] = TPWorkspace(group)
+    return ws
+
+
+def reset() -> None:
+    _WORKSPACES.clear()
+
+
+def _flat(x: torch.Tensor) -> torch.Tensor:
+    return x.reshape(-1, x.shape[-1])
+
+
+class _ColumnSP:
+    """in_mode="gather", out_mode="none"."""
+
+    def __init__(self, ws: TPWorkspace):
+        self.ws = ws
+        self.saved_gathered: Optional[torch.Tensor] = None
+
+    def forward(self, x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        x2 = _flat(x).contiguous()
+        out, gathered = self.ws.ag_gemm(x2, weight, True)
+        self.gathered = gathered.clone()   # keep AG(x) for wgrad (one D2D copy; no re-gather in backward)
+        return out.view(x.shape[0] * self.ws.world, *x.shape[1:-1], weight.shape[0])
+
+    def backward(self, x, weight, gy, has_bias, need_gx, need_gw, gathered):
+        g2 = _flat(gy).contiguous()
+        gbias = g2.float().sum(0).to(gy.dtype) if has_bias else None
+        gx = gw = None
+        if need_gx:
+            gx2 = self.ws.gemm_rs(g2, weight, False)                     # RS(g @ W)
+            gx = gx2.view(x.shape)
+        if need_gw:
+            gw = gemm.matmul(g2, gathered, trans_a=True, trans_b=False)  # gᵀ @ AG(x)
+        return gx, gw, gbias
+
+
+class _RowSP:
+    """in_mode="none", out_mode="scatter"."""
+
+    def __init__(self, ws: TPWorkspace):
+        self.ws = ws
+
+    def forward(self, x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        x2 = _flat(x).contiguous()
+        out = self.ws.gemm_rs(x2, weight, True)
+        return out.view(x.shape[0] // self.ws.world, *x.shape[1:-1], weight.shape[0])
+
+    def backward(self, x, weight, gy, has_bias, need_gx, need_gw, gathered=None):
+        g2 = _flat(gy).contiguous()
+        gbias = g2.float().sum(0).to(gy.dtype) if has_bias else None
+        gx2, g_full = self.ws.ag_gemm(g2, weight, False)                 # AG(g) @ W
+        gx = gx2.view(x.shape) if need_gx else None
+        gw = gemm.matmul(g_full, _flat(x), trans_a=True, trans_b=False) if need_gw else None   # AG(g)ᵀ @ x
+        return gx, gw, gbias
+
+
+def select(x: torch.Tensor, weight: torch.Tensor, in_mode: str, out_mode: str, seq_dim: int, group):
+    """Return a fused implementation for this call or ``None``."""
+    if os.environ.get("NXD_DISABLE_FUSED_TP", "0") == "1":
+        return None
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and seq_dim == 0):
+        return None
+    e = _ext.ext()
+    if e is None or not hasattr(e, "ag_gemm_bf16") or not symm.available():
+        return None
+    world = dist.get_world_size(group)
+    if world == 1 or world > 8 or not weight.is_contiguous():
+        return None
+    rows = x.numel() // x.shape[-1]
+    K, N = weight.shape[1], weight.shape[0]
+    if K % 8 or N % 8:
+        return None
+    if in_mode == "gather" and out_mode == "none":
+        if rows % BLOCK_M or rows // BLOCK_M > MAX_ROW_BLOCKS:
+            return None
+        return _ColumnSP(workspace(group))
+    if in_mode == "none" and out_mode == "scatter":
+        if rows % (world * BLOCK_M) or rows // (world * BLOCK_M) > MAX_ROW_BLOCKS:
+            return None
+        return _RowSP(workspace(group))
+    return None

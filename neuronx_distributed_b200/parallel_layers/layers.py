@@ -76,7 +76,10 @@ def _initialize_parameter_from_master(
         return None
     shape = list(param.shape)
     shape[partition_dim] *= num_partitions
-    master = torch.empty(shape, dtype=torch.float32)
+    # the full weight is drawn from the *default* generator of the parameter's device: identical on
+    # every TP rank (same seed), on the GPU when the layer was constructed with device=cuda (fast path
+    # for multi-billion-parameter models), on the CPU otherwise.
+    master = torch.empty(shape, dtype=torch.float32, device=param.device)
     init_method(master)
     master = master.to(param_dtype)
     with torch.no_grad():
@@ -306,14 +309,21 @@ class _TPLinear(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.x_requires_grad = x.requires_grad
         n = dist.get_world_size(group)
-        if save_for_backward:
-            ctx.save_for_backward(x, weight)
         fused = ops.tp_fused.dispatch(x, weight, in_mode, out_mode, seq_dim, group)
         if fused is not None:
             ctx.fused = True
             y = fused.forward(x, weight)
+            gathered = getattr(fused, "gathered", None)
+            ctx.has_gathered = gathered is not None
+            if save_for_backward:
+                if gathered is not None:
+                    ctx.save_for_backward(x, weight, gathered)
+                else:
+                    ctx.save_for_backward(x, weight)
         else:
             ctx.fused = False
+            if save_for_backward:
+                ctx.save_for_backward(x, weight)
             total = comm.all_gather(x, dim=seq_dim, group=group) if (in_mode == "gather" and n > 1) else x
             y = torch.matmul(total, weight.t())
             if n > 1 and out_mode in ("scatter", "reduce"):
@@ -332,16 +342,21 @@ class _TPLinear(torch.autograd.Function):
     def backward(ctx, gy):
         from .. import ops
 
-        x, weight = ctx.saved_tensors
         group, seq_dim = ctx.group, ctx.seq_dim
         n = dist.get_world_size(group)
         in_mode, out_mode = ctx.in_mode, ctx.out_mode
         gbias = None
         gy = gy.contiguous()
         if ctx.fused:
+            if ctx.has_gathered:
+                x, weight, gathered = ctx.saved_tensors
+            else:
+                (x, weight), gathered = ctx.saved_tensors, None
             fused = ops.tp_fused.dispatch(x, weight, in_mode, out_mode, seq_dim, group)
-            gx, gw, gbias = fused.backward(x, weight, gy, ctx.has_bias, ctx.x_requires_grad, weight.requires_grad)
+            gx, gw, gbias = fused.backward(x, weight, gy, ctx.has_bias, ctx.x_requires_grad, weight.requires_grad,
+                                           gathered)
             return gx, gw, gbias, None, None, None, None, None, None
+        x, weight = ctx.saved_tensors
 
         # ---- grad wrt the GEMM output (undo the output collective) -----------------
         if out_mode == "scatter" and n > 1:

@@ -29,6 +29,7 @@ def report(name, ok, **kw):
 
 def relerr(a, b):
     a, b = a.float(), b.float()
+    a, b = a.detach(), b.detach()
     return float((a - b).abs().max() / (b.abs().max() + 1e-6))
 
 
@@ -54,11 +55,11 @@ def check_elementwise():
     for dt in (torch.bfloat16, torch.float32):
         x = torch.randn(T, H, device=dev, dtype=dt)
         w = (torch.rand(H, device=dev) + 0.5).to(dt)
-        xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+        xr, wr = x.detach().float().clone().requires_grad_(True), w.detach().float().clone().requires_grad_(True)
         ref = (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-5) * wr)
         g = torch.randn_like(ref)
         ref.backward(g)
-        xx, ww = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        xx, ww = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
         y = ops.norm.rms_norm(xx, ww, 1e-5)
         y.backward(g.to(dt))
         tol = 2e-2 if dt == torch.bfloat16 else 1e-5
