@@ -24,7 +24,7 @@ def _eligible(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int) -> bool:
         return False
     if not (a.is_cuda and b.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16):
         return False
-    if not (a.is_contiguous() and b.is_contiguous()):
+    if not (a.is_contiguous() and b.is_contiguous()) or a.data_ptr() % 16 or b.data_ptr() % 16:
         return False
     if not _ext.use_cuda(a, b) or not hasattr(_ext.ext(), "gemm_bf16"):
         return False
@@ -46,6 +46,10 @@ def matmul(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: boo
         _ext.count_launch()
         _ext.ext().gemm_bf16(a, b, out, bool(trans_a), bool(trans_b), bool(accumulate))
         return out
+    if a.is_cuda and a.dtype == torch.bfloat16 and not os.environ.get("NXD_DISABLE_TCGEN05_GEMM") \
+            and (not a.is_contiguous() or not b.is_contiguous()):
+        # make operands dense once and retry the tensor-core kernel
+        return matmul(a.contiguous(), b.contiguous(), trans_a, trans_b, out, accumulate, out_dtype)
     aa = a.t() if trans_a else a
     bb = b.t() if trans_b else b
     res = torch.matmul(aa, bb)

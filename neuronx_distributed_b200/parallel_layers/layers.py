@@ -325,7 +325,7 @@ class _TPLinear(torch.autograd.Function):
             if save_for_backward:
                 ctx.save_for_backward(x, weight)
             total = comm.all_gather(x, dim=seq_dim, group=group) if (in_mode == "gather" and n > 1) else x
-            y = torch.matmul(total, weight.t())
+            y = ops.gemm.linear_nt(total, weight)          # tcgen05 kernel on CUDA bf16, torch.matmul otherwise
             if n > 1 and out_mode in ("scatter", "reduce"):
                 od = y.dtype
                 yr = y.to(reduce_dtype) if reduce_dtype is not None else y
@@ -370,7 +370,7 @@ class _TPLinear(torch.autograd.Function):
         gx = None
         work = None
         if ctx.x_requires_grad:
-            gx = torch.matmul(g_out, weight)
+            gx = ops.gemm.matmul(_flat2d(g_out), weight, False, False).view(*g_out.shape[:-1], weight.shape[1])
             if n > 1 and in_mode == "copy":
                 work = comm.all_reduce(gx, group=group, async_op=True)  # overlaps wgrad
             elif n > 1 and in_mode == "gather":
@@ -381,7 +381,7 @@ class _TPLinear(torch.autograd.Function):
         gw = None
         if weight.requires_grad:
             total = comm.all_gather(x, dim=seq_dim, group=group) if (in_mode == "gather" and n > 1) else x
-            gw = torch.matmul(_flat2d(g_out).t(), _flat2d(total))
+            gw = ops.gemm.matmul(_flat2d(g_out), _flat2d(total), True, False)
         if work is not None:
             work.wait()
         return gx, gw, gbias, None, None, None, None, None, None

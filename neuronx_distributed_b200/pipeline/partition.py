@@ -1,0 +1,161 @@
+"""Model → pipeline stages.
+
+Role parity with reference ``pipeline/trace.py:31-219`` + ``pipeline/partition.py:18-303``: trace
+with ``torch.fx`` keeping transformer layers and TP layers as leaves, cut after the requested layer
+calls, split into ``submod_i`` stage modules, analyse stage IO (values live across each boundary,
+including *pass-along* values that skip stages, are forwarded hop by hop), and detect parameters
+shared by several stages (tied embeddings).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Sequence, Set, Tuple, Type
+
+import torch
+import torch.fx as fx
+from torch import nn
+from torch.fx.passes.split_module import split_module
+
+
+def create_partitions(num_layers: int, num_stages: int) -> List[int]:
+    """Even split of ``num_layers`` transformer layers into ``num_stages`` stages, remainder to the
+    *later* stages; returns the layer indices after which to cut (reference partition.py:268-303)."""
+    if num_stages > num_layers:
+        raise ValueError(f"cannot split {num_layers} layers into {num_stages} stages")
+    base, rem = divmod(num_layers, num_stages)
+    sizes = [base + (1 if s >= num_stages - rem else 0) for s in range(num_stages)]
+    cuts, acc = [], 0
+    for s in sizes[:-1]:
+        acc += s
+        cuts.append(acc - 1)
+    return cuts
+
+
+def stage_to_pipeline_parallel_rank(stage: int, pp_size: int) -> int:
+    return stage % pp_size
+
+
+class _LeafTracer(fx.Tracer):
+    def __init__(self, leaf_types: Tuple[type, ...], autowrap_functions=(), autowrap_modules=()):
+        super().__init__(autowrap_functions=tuple(autowrap_functions), autowrap_modules=tuple(autowrap_modules),
+                         param_shapes_constant=True)
+        self.leaf_types = leaf_types
+
+    def is_leaf_module(self, m: nn.Module, qualname: str) -> bool:
+        return isinstance(m, self.leaf_types) or super().is_leaf_module(m, qualname)
+
+
+def trace_model(model: nn.Module, input_names: Optional[Sequence[str]], leaf_module_cls: Sequence[type],
+                autowrap_functions=(), autowrap_modules=(), tracer_cls=None) -> fx.GraphModule:
+    import inspect
+
+    from ..parallel_layers import PARALLEL_FUNCTIONS, PARALLEL_MODULES
+
+    leaf = tuple(leaf_module_cls) + tuple(PARALLEL_MODULES)
+    sig = inspect.signature(model.forward)
+    concrete = {}
+    if input_names is not None:
+        for name, p in sig.parameters.items():
+            if name not in input_names and p.default is not inspect.Parameter.empty:
+                concrete[name] = p.default
+    tracer = (tracer_cls or _LeafTracer)(leaf, tuple(autowrap_functions) + tuple(PARALLEL_FUNCTIONS), autowrap_modules)
+    graph = tracer.trace(model, concrete_args=concrete or None)
+    return fx.GraphModule(model, graph)
+
+
+@dataclass
+class StageIO:
+    inputs_from_model: List[str] = field(default_factory=list)      # placeholder names consumed directly
+    inputs_from_prev: List[str] = field(default_factory=list)       # values received from stage-1 (ordered)
+    outputs_to_next: List[str] = field(default_factory=list)        # values sent to stage+1 (ordered)
+    call_args: List[str] = field(default_factory=list)              # argument names of the stage module, in order
+    produces: List[Tuple[str, Optional[int]]] = field(default_factory=list)  # (name, index into the stage result or None)
+
+
+def partition_traced_model(traced: fx.GraphModule, cut_after: Sequence[str], num_stages: int):
+    """Split ``traced`` after each call_module node whose target is in ``cut_after``."""
+    cut_set = set(cut_after)
+    stage_of: Dict[fx.Node, int] = {}
+    cur = 0
+    for node in traced.graph.nodes:
+        stage_of[node] = cur
+        if node.op == "call_module" and node.target in cut_set:
+            cur += 1
+    assert cur + 1 == num_stages, f"cuts produce {cur + 1} stages, expected {num_stages}"
+    split = split_module(traced, traced, lambda n: stage_of[n])
+    return split
+
+
+def analyze_pipeline_module(split: fx.GraphModule) -> Tuple[List[StageIO], List[str]]:
+    """Per-stage IO of a ``split_module`` result.  Returns (stage_ios, names of the final outputs)."""
+    placeholders: Set[str] = set()
+    produced_by: Dict[str, int] = {}
+    stage_nodes: List[fx.Node] = []
+    final_outputs: List[str] = []
+    out_spec = None
+    for node in split.graph.nodes:
+        if node.op == "placeholder":
+            placeholders.add(node.name)
+        elif node.op == "call_module":
+            stage_nodes.append(node)
+        elif node.op == "output":
+            out_spec = node.args[0]
+    n = len(stage_nodes)
+    ios = [StageIO() for _ in range(n)]
+    # names: a stage result used via getitem has per-item names
+    alias: Dict[str, Tuple[int, Optional[int]]] = {}
+    for s, node in enumerate(stage_nodes):
+        alias[node.name] = (s, None)
+    for node in split.graph.nodes:
+        if node.op == "call_function" and getattr(node.target, "__name__", "") == "getitem":
+            src = node.args[0]
+            if isinstance(src, fx.Node) and src.name in alias:
+                alias[node.name] = (alias[src.name][0], node.args[1])
+    for name, (s, _) in alias.items():
+        produced_by[name] = s
+    consumers: Dict[str, Set[int]] = {}
+    for s, node in enumerate(stage_nodes):
+        for a in list(node.args) + list(node.kwargs.values()):
+            if isinstance(a, fx.Node):
+                ios[s].call_args.append(a.name)
+                if a.name in placeholders:
+                    ios[s].inputs_from_model.append(a.name)
+                else:
+                    consumers.setdefault(a.name, set()).add(s)
+    def _names(x):
+        if isinstance(x, fx.Node):
+            return [x.name]
+        if isinstance(x, (tuple, list)):
+            return [n for y in x for n in _names(y)]
+        if isinstance(x, dict):
+            return [n for y in x.values() for n in _names(y)]
+        return []
+    final_outputs = _names(out_spec)
+    for name in final_outputs:
+        if name in produced_by:
+            consumers.setdefault(name, set()).add(n)  # virtual consumer after the last stage
+    # a value produced at stage p and consumed at stage c > p crosses every boundary p..c-1
+    for name, cons in consumers.items():
+        p = produced_by.get(name)
+        if p is None:
+            continue
+        last = max(cons)
+        for b in range(p, min(last, n - 1)):
+            if name not in ios[b].outputs_to_next:
+                ios[b].outputs_to_next.append(name)
+            if name not in ios[b + 1].inputs_from_prev:
+                ios[b + 1].inputs_from_prev.append(name)
+    for name, (s, idx) in alias.items():
+        ios[s].produces.append((name, idx))
+    return ios, final_outputs
+
+
+def analyze_shared_weights_across_stages(split: fx.GraphModule, stage_modules: List[nn.Module]) -> List[List[Tuple[int, str]]]:
+    """Groups of (stage, local parameter name) that are the same Parameter object in several stages."""
+    seen: Dict[int, List[Tuple[int, str]]] = {}
+    for s, m in enumerate(stage_modules):
+        for name, p in m.named_parameters(remove_duplicate=False):
+            seen.setdefault(id(p), [])
+            if not any(st == s for st, _ in seen[id(p)]):
+                seen[id(p)].append((s, name))
+    return [v for v in seen.values() if len(v) > 1]

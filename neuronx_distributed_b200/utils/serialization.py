@@ -1,0 +1,62 @@
+"""Flatten arbitrary python containers into (tensor list, skeleton) and back — role of reference
+``utils/serialization.py:36-254`` (``SerializationManager``, ``TensorMeta``, ``find_loss_from_output_and_spec``).
+Built on ``torch.utils._pytree`` instead of a hand-written recursive walker."""
+from __future__ import annotations
+
+from typing import Any, List, Tuple
+
+import torch
+from torch.utils import _pytree as pytree
+
+
+class TensorStub:
+    """Placeholder left in the skeleton where a tensor was."""
+
+    def __init__(self, index: int):
+        self.index = index
+
+    def __repr__(self) -> str:
+        return f"TensorStub({self.index})"
+
+
+class SerializationManager:
+    def serialize(self, obj: Any) -> Tuple[Any, List[torch.Tensor]]:
+        leaves, spec = pytree.tree_flatten(obj)
+        tensors: List[torch.Tensor] = []
+        stubs = []
+        for leaf in leaves:
+            if isinstance(leaf, torch.Tensor):
+                stubs.append(TensorStub(len(tensors)))
+                tensors.append(leaf)
+            else:
+                stubs.append(leaf)
+        return (stubs, spec), tensors
+
+    def deserialize(self, skeleton: Any, tensors: List[torch.Tensor]) -> Any:
+        stubs, spec = skeleton
+        leaves = [tensors[s.index] if isinstance(s, TensorStub) else s for s in stubs]
+        return pytree.tree_unflatten(leaves, spec)
+
+
+def find_loss_from_output_and_spec(output: Any, spec: Any) -> torch.Tensor:
+    """Pick the loss out of a model output using a spec of the same structure whose leaves are
+    booleans (exactly one True), e.g. ``(True, False)`` or ``{"loss": True}``; ``True`` alone means
+    the output itself (reference :212-254)."""
+    if spec is True or spec is None:
+        if isinstance(output, torch.Tensor):
+            return output
+        if hasattr(output, "loss"):
+            return output.loss
+        if isinstance(output, (tuple, list)):
+            return output[0]
+        raise ValueError("cannot infer loss from output")
+    if isinstance(spec, dict):
+        for k, v in spec.items():
+            if v is not False and v is not None:
+                sub = output[k] if isinstance(output, dict) else getattr(output, k)
+                return find_loss_from_output_and_spec(sub, v)
+    if isinstance(spec, (tuple, list)):
+        for i, v in enumerate(spec):
+            if v is not False and v is not None:
+                return find_loss_from_output_and_spec(output[i], v)
+    raise ValueError(f"no loss selected by spec {spec!r}")

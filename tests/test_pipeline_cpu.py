@@ -1,0 +1,150 @@
+"""Pipeline engine: schedule invariants (pure data) + 1F1B / interleaved runs on gloo vs non-pipelined."""
+import pytest
+import torch
+from torch import nn
+
+from dist_utils import run_distributed
+from neuronx_distributed_b200.pipeline import scheduler as S
+from neuronx_distributed_b200.pipeline.partition import create_partitions
+
+
+def _simulate(schedules):
+    """Execute all stages' task lists with rendezvous p2p semantics; returns per-stage compute orders."""
+    progs = [[t for step in sch.steps() for t in step] for sch in schedules]
+    n = len(progs)
+    pc = [0] * n
+    done_f, done_b = [set() for _ in range(n)], [set() for _ in range(n)]
+    chan = {}  # (src, dst, kind, mb, chunk) -> posted
+    guard = 0
+    while any(pc[s] < len(progs[s]) for s in range(n)):
+        guard += 1
+        assert guard < 100000, "deadlock in schedule simulation"
+        moved = False
+        for s in range(n):
+            if pc[s] >= len(progs[s]):
+                continue
+            t = progs[s][pc[s]]
+            if isinstance(t, S.ReduceGradsTask):
+                pc[s] += 1; moved = True; continue
+            key = (t.mb, t.model_chunk)
+            if isinstance(t, S.ForwardStepTask):
+                done_f[s].add(key); pc[s] += 1; moved = True
+            elif isinstance(t, S.BackwardStepTask):
+                assert key in done_f[s]
+                done_b[s].add(key); pc[s] += 1; moved = True
+            elif isinstance(t, S.ForwardPostprocessTask):
+                chan[("f", s, key)] = True; pc[s] += 1; moved = True       # buffered send
+            elif isinstance(t, S.BackwardPostprocessTask):
+                chan[("b", s, key)] = True; pc[s] += 1; moved = True
+            elif isinstance(t, S.ForwardPreprocessTask):
+                first = s == 0 and t.model_chunk == 0
+                src = (s - 1) % n
+                src_key = (t.mb, t.model_chunk if s > 0 else t.model_chunk - 1)
+                if first or chan.pop(("f", src, src_key), None):
+                    pc[s] += 1; moved = True
+            elif isinstance(t, S.BackwardPreprocessTask):
+                src = (s + 1) % n
+                src_key = (t.mb, t.model_chunk if s < n - 1 else t.model_chunk + 1)
+                if chan.pop(("b", src, src_key), None):
+                    pc[s] += 1; moved = True
+        assert moved, f"deadlock: pcs={pc}"
+    return done_f, done_b
+
+
+@pytest.mark.parametrize("pp,mb", [(2, 1), (2, 4), (4, 4), (4, 8), (8, 32), (16, 32)])
+def test_1f1b_schedule_completes(pp, mb):
+    schs = [S.Train1F1BSchedule(mb, pp, r) for r in range(pp)]
+    f, b = _simulate(schs)
+    for r in range(pp):
+        assert f[r] == {(m, 0) for m in range(mb)} == b[r]
+        order = schs[r].compute_order()
+        # never more than (pp - r) forwards in flight
+        inflight = mx = 0
+        for is_f, *_ in order:
+            inflight += 1 if is_f else -1
+            mx = max(mx, inflight)
+        assert mx <= min(pp - r, mb)
+        assert list(schs[r].steps())[-1] == [S.ReduceGradsTask()]
+
+
+@pytest.mark.parametrize("pp,mb,chunks", [(2, 2, 2), (2, 4, 2), (4, 8, 2), (4, 4, 3), (4, 16, 4)])
+def test_interleaved_schedule_completes(pp, mb, chunks):
+    schs = [S.TrainInterleavedSchedule(mb, chunks, pp, r) for r in range(pp)]
+    f, b = _simulate(schs)
+    want = {(m, c) for m in range(mb) for c in range(chunks)}
+    for r in range(pp):
+        assert f[r] == want == b[r]
+
+
+def test_interleaved_requires_divisible_microbatches():
+    with pytest.raises(ValueError):
+        S.TrainInterleavedSchedule(3, 2, 2, 0)
+
+
+def test_create_partitions():
+    assert create_partitions(8, 4) == [1, 3, 5]
+    assert create_partitions(10, 4) == [1, 3, 6]      # remainder goes to later stages: sizes 2,2,3,3
+    with pytest.raises(ValueError):
+        create_partitions(2, 4)
+
+
+class Block(nn.Module):
+    def __init__(self, h):
+        super().__init__()
+        self.fc1, self.fc2 = nn.Linear(h, 2 * h), nn.Linear(2 * h, h)
+
+    def forward(self, x):
+        return x + self.fc2(torch.tanh(self.fc1(x)))
+
+
+class Toy(nn.Module):
+    def __init__(self, v=32, h=16, layers=4, tie=False):
+        super().__init__()
+        self.emb = nn.Embedding(v, h)
+        self.layers = nn.ModuleList([Block(h) for _ in range(layers)])
+        self.head = nn.Linear(h, v, bias=False)
+        if tie:
+            self.head.weight = self.emb.weight
+
+    def forward(self, input_ids, labels):
+        x = self.emb(input_ids)
+        for l in self.layers:
+            x = l(x)
+        logits = self.head(x)
+        return torch.nn.functional.cross_entropy(logits.view(-1, logits.shape[-1]), labels.view(-1))
+
+
+def _pp_worker(rank, world, pp, vpp, tie, out_path):
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.pipeline import NxDPPModel
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=1, pipeline_model_parallel_size=pp)
+    torch.manual_seed(0)
+    ref = Toy(tie=tie)
+    torch.manual_seed(0)
+    model = Toy(tie=tie)
+    ids = torch.randint(0, 32, (8, 6), generator=torch.Generator().manual_seed(1))
+    ref_loss = ref(ids, ids)
+    ref_loss.backward()
+    ppm = NxDPPModel(model, transformer_layer_cls=Block, num_microbatches=4, virtual_pipeline_size=vpp,
+                     output_loss_value_spec=True, input_names=["input_ids", "labels"],
+                     broadcast_and_average_loss=True)
+    loss = ppm.run_train(input_ids=ids, labels=ids)
+    torch.testing.assert_close(loss.float(), ref_loss.detach().float(), rtol=1e-4, atol=1e-5)
+    refp = dict(ref.named_parameters(remove_duplicate=False))
+    n = 0
+    for name, p in ppm.local_named_parameters():
+        assert name in refp, name
+        if p.grad is not None:
+            torch.testing.assert_close(p.grad, refp[name].grad, rtol=1e-3, atol=1e-5)
+            n += 1
+    assert n > 0
+    sd = ppm.local_state_dict()
+    assert all(k in dict(ref.state_dict()) for k in sd)
+    ev = ppm.run_eval(input_ids=ids, labels=ids)
+    assert ev is not None
+
+
+@pytest.mark.parametrize("pp,vpp,tie", [(2, 1, False), (2, 2, False), (2, 1, True)])
+def test_pipeline_matches_single_process(tmp_path, pp, vpp, tie):
+    run_distributed(_pp_worker, pp, pp, vpp, tie, str(tmp_path / "o.pt"), timeout=90)
