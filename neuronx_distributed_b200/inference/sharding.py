@@ -1,0 +1,61 @@
+"""Shard a full (unsharded) state dict for a given TP rank from the parameters' parallel attributes.
+
+Role parity with reference ``trace/trace.py:628-825`` (``get_sharded_checkpoint`` →
+``preprocess_checkpoint`` (preshard hooks) → ``shard_children``) and
+``parallel_layers/checkpointing.py:48-67``.  Rules: a parameter tagged ``tensor_model_parallel`` is cut
+along ``partition_dim`` into ``num_partitions * partition_stride`` chunks and rank r takes chunks
+``r, r+P, …`` (``create_local_weight``); fused QKV parameters are sharded per (q, k, v) section;
+``rank_ordering`` permutes which logical shard a rank receives; everything else is replicated.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import torch
+from torch import nn
+
+from ..parallel_layers.utils import create_local_weight
+
+
+def _run_preshard_hooks(model: nn.Module, sd: Dict[str, Any]) -> None:
+    for name, module in model.named_modules():
+        hook = getattr(module, "preshard_hook", None)
+        if hook is None:
+            continue
+        prefix = (name + "." if name else "")
+        for pname, _ in list(module.named_parameters(recurse=False)) or [("weight", None)]:
+            key = prefix + pname
+            try:
+                hook(sd, key)
+            except KeyError:
+                pass
+            break
+
+
+def shard_tensor(full: torch.Tensor, param: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    if not getattr(param, "tensor_model_parallel", False):
+        return full
+    dim = param.partition_dim
+    stride = getattr(param, "partition_stride", 1)
+    nparts = getattr(param, "num_partitions", world)
+    order = getattr(param, "rank_ordering", None)
+    r = order[rank] if order else rank
+    if getattr(param, "fused_qkv", False) and full.shape[dim] != param.shape[dim] * nparts:
+        raise ValueError("fused qkv tensor has unexpected size; run preshard hooks first")
+    if full.shape[dim] == param.shape[dim]:
+        return full  # already local (e.g. SPMDRank handled by hook)
+    per = full.shape[dim] // nparts
+    return create_local_weight(full, dim, per, stride, rank=r, world_size=nparts).clone()
+
+
+def shard_state_dict_for_rank(model: nn.Module, full_sd: Dict[str, Any], rank: int, world: int,
+                              run_hooks: bool = True) -> Dict[str, Any]:
+    sd = dict(full_sd)
+    if run_hooks:
+        _run_preshard_hooks(model, sd)
+    out: Dict[str, Any] = {}
+    params = dict(model.named_parameters(remove_duplicate=False))
+    for k, v in sd.items():
+        p = params.get(k)
+        out[k] = shard_tensor(v, p, rank, world) if (p is not None and isinstance(v, torch.Tensor)) else v
+    return out

@@ -1,0 +1,394 @@
+"""``save_checkpoint`` / ``load_checkpoint`` with the reference's on-disk layout
+(reference ``trainer/checkpoint.py:54-972``):
+
+    <dir>/<tag>/checkpoint                                  (marker: save started)
+    <dir>/<tag>/model/dp_rank_00_tp_rank_XX_pp_rank_XX.pt    (+ ``_ep_rank_XX`` when EP>1)
+    <dir>/<tag>/optim/dp_rank_XX_tp_rank_XX_pp_rank_XX.pt    (per dp-rank only for ZeRO-1)
+    <dir>/<tag>/scheduler.pt, user_content.pt
+    <dir>/<tag>/done                                         (marker: save complete)
+
+``use_xser=True`` stores every tensor in its own file ``<file>.tensors/tensor_<i>.pt`` next to a
+reference file whose tensors are :class:`TensorReference` stubs plus ``<file>.info.pt`` with
+``{tid: {dtype, shape}}`` — tensor files are spread over DP peers by greedy bin-packing so replicas
+share the write bandwidth, and on load one rank per replica group reads each tensor and broadcasts it.
+Other features: ``num_kept_ckpts`` rotation with clean-up of interrupted saves, ``async_save`` on a
+1-thread executor with an atexit flush, ``avoid_saving_lower_precision_weights``, newest-complete-tag
+auto-resume.
+"""
+from __future__ import annotations
+
+import atexit
+import os
+import threading
+from concurrent.futures import Future, ThreadPoolExecutor
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..parallel_layers import parallel_state as ps
+from ..utils.logger import get_logger
+from .checkpoint_storage import BaseCheckpointStorage, create_checkpoint_storage
+
+logger = get_logger()
+
+
+class TensorReference:
+    """Stub left in an xser reference file in place of a tensor (pickle-compatible role of
+    ``torch_xla.utils.serialization.TensorReference``)."""
+
+    def __init__(self, tid: int):
+        self.tid = tid
+
+    def __repr__(self) -> str:
+        return f"TensorReference({self.tid})"
+
+
+def _get_path(prefix: str, tp: bool = True, pp: bool = True, dp: bool = False, ep: bool = False) -> str:
+    """``prefix/dp_rank_XX[_ep_rank_XX]_tp_rank_XX_pp_rank_XX`` (reference :54-63)."""
+    dp_rank = (ps.get_expert_data_parallel_rank() if ep else ps.get_data_parallel_rank()) if dp else 0
+    name = f"dp_rank_{dp_rank:02d}"
+    if ep:
+        name += f"_ep_rank_{ps.get_expert_model_parallel_rank():02d}"
+    name += f"_tp_rank_{ps.get_tensor_model_parallel_rank() if tp else 0:02d}"
+    name += f"_pp_rank_{ps.get_pipeline_model_parallel_rank() if pp else 0:02d}"
+    return os.path.join(prefix, name)
+
+
+def _determine_remove_tags(storage: BaseCheckpointStorage, num_kept: Optional[int]) -> List[str]:
+    """Tags to delete: everything incomplete that is older than the newest complete tag (interrupted
+    saves / deletes) plus complete tags beyond ``num_kept`` (reference :66-98)."""
+    if num_kept is None or num_kept < 0:
+        return []
+    tags = storage.list_checkpoint_tags()
+    done = [t for t in tags if storage.is_checkpoint_tag_completed(t)]
+    remove = []
+    if done:
+        newest_done = tags.index(done[-1])
+        remove += [t for t in tags[:newest_done] if t not in done]
+    if len(done) > num_kept:
+        remove += done[: len(done) - num_kept]
+    return remove
+
+
+class CheckpointIOState:
+    """Serialises checkpoint IO; optionally runs it on a background thread (reference :110-325)."""
+
+    def __init__(self, async_save: bool = False):
+        self.async_save = async_save
+        self.executor = ThreadPoolExecutor(max_workers=1) if async_save else None
+        self.save_future: Optional[Future] = None
+        self.remove_future: Optional[Future] = None
+        self.items: List[Tuple[Any, str]] = []
+        self.storage: Optional[BaseCheckpointStorage] = None
+        self.tag: Optional[str] = None
+        self.lock = threading.Lock()
+
+    # -- lifecycle -----------------------------------------------------------------------
+    def begin(self, storage: BaseCheckpointStorage, tag: str) -> None:
+        self.wait_all()                       # at most one save in flight
+        self.storage, self.tag, self.items = storage, tag, []
+        if _rank() == 0:
+            storage.create_dir(tag)
+            storage.save_text("1", os.path.join(tag, "checkpoint"))
+        _barrier()
+
+    def add_save_task(self, obj: Any, filename: str) -> None:
+        self.items.append((obj, filename))
+
+    def end(self, num_kept: Optional[int]) -> None:
+        storage, tag, items = self.storage, self.tag, self.items
+        assert storage is not None and tag is not None
+
+        def write_all():
+            for obj, filename in items:
+                storage.save_object(obj, filename)
+
+        if self.async_save:
+            # tensors were already copied to host by the caller; hand the writes to the thread
+            def job():
+                write_all()
+                return True
+
+            self.save_future = self.executor.submit(job)
+            self._finish_async(storage, tag, num_kept)
+        else:
+            write_all()
+            _barrier()
+            if _rank() == 0:
+                storage.save_text("1", os.path.join(tag, "done"))
+                for t in _determine_remove_tags(storage, num_kept):
+                    storage.remove_dir(t)
+            _barrier()
+        self.items = []
+
+    def _finish_async(self, storage, tag, num_kept) -> None:
+        prev = self.save_future
+
+        def finalize():
+            prev.result()
+            return True
+
+        # the "done" marker needs *all* ranks' writes → it is written at the next synchronisation point
+        self._pending_done = (storage, tag, num_kept)
+
+    def wait_save(self) -> None:
+        if self.save_future is not None:
+            self.save_future.result()
+            self.save_future = None
+        pend = getattr(self, "_pending_done", None)
+        if pend is not None:
+            storage, tag, num_kept = pend
+            self._pending_done = None
+            _barrier()
+            if _rank() == 0:
+                storage.save_text("1", os.path.join(tag, "done"))
+                for t in _determine_remove_tags(storage, num_kept):
+                    storage.remove_dir(t)
+            _barrier()
+
+    def wait_all(self) -> None:
+        self.wait_save()
+
+    def finalize_shutdown(self) -> None:
+        try:
+            if self.save_future is not None:
+                self.save_future.result()
+                self.save_future = None
+            pend = getattr(self, "_pending_done", None)
+            if pend is not None and _rank() == 0:
+                storage, tag, _ = pend
+                storage.save_text("1", os.path.join(tag, "done"))
+                self._pending_done = None
+        finally:
+            if self.executor is not None:
+                self.executor.shutdown(wait=True)
+
+
+g_iostate: Optional[CheckpointIOState] = None
+
+
+def _rank() -> int:
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
+def _barrier() -> None:
+    if dist.is_initialized() and os.environ.get("NXD_SKIP_RENDEZVOUS", "0") != "1":
+        dist.barrier()
+
+
+def _to_cpu(obj: Any) -> Any:
+    if isinstance(obj, torch.Tensor):
+        return obj.detach().to("cpu", copy=True) if obj.device.type != "cpu" else obj.detach().clone()
+    if isinstance(obj, dict):
+        return {k: _to_cpu(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to_cpu(v) for v in obj)
+    return obj
+
+
+# ---------------------------------------------------------------------------- xser format
+def _flatten_tensors(obj: Any, out: List[torch.Tensor]) -> Any:
+    if isinstance(obj, torch.Tensor):
+        out.append(obj)
+        return TensorReference(len(out) - 1)
+    if isinstance(obj, dict):
+        return {k: _flatten_tensors(v, out) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_flatten_tensors(v, out) for v in obj)
+    return obj
+
+
+def _unflatten_tensors(obj: Any, tensors: Dict[int, torch.Tensor]) -> Any:
+    if isinstance(obj, TensorReference):
+        return tensors[obj.tid]
+    if isinstance(obj, dict):
+        return {k: _unflatten_tensors(v, tensors) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_unflatten_tensors(v, tensors) for v in obj)
+    return obj
+
+
+def _assign_tensors_to_bins(tensors: List[torch.Tensor], bin_count: int) -> List[List[int]]:
+    """Greedy largest-first bin packing of tensor indices by byte size (reference :443-474)."""
+    order = sorted(range(len(tensors)), key=lambda i: -tensors[i].numel() * tensors[i].element_size())
+    bins: List[List[int]] = [[] for _ in range(bin_count)]
+    load = [0] * bin_count
+    for i in order:
+        b = load.index(min(load))
+        bins[b].append(i)
+        load[b] += tensors[i].numel() * tensors[i].element_size()
+    return bins
+
+
+def _xser_tasks(state: Any, path: str, writers: int, writer_rank: int, iostate: CheckpointIOState) -> None:
+    tensors: List[torch.Tensor] = []
+    ref = _flatten_tensors(state, tensors)
+    bins = _assign_tensors_to_bins(tensors, max(1, writers))
+    for tid in bins[writer_rank % max(1, writers)]:
+        iostate.add_save_task(_to_cpu(tensors[tid]), os.path.join(path + ".tensors", f"tensor_{tid}.pt"))
+    if writer_rank == 0:
+        iostate.add_save_task(ref, path)
+        info = {i: {"dtype": t.dtype, "shape": tuple(t.shape),
+                    "expert_model_parallel": bool(getattr(t, "expert_model_parallel", False))} for i, t in enumerate(tensors)}
+        iostate.add_save_task(info, path + ".info.pt")
+
+
+def _xser_load(storage: BaseCheckpointStorage, path: str, group, readers: int, reader_rank: int) -> Any:
+    """One reader per replica group loads each tensor file and broadcasts it (reference :347-432)."""
+    ref = storage.load_object(path, map_location="cpu")
+    info = storage.load_object(path + ".info.pt", map_location="cpu")
+    tensors: Dict[int, torch.Tensor] = {}
+    from ..utils import get_device
+
+    dev = get_device()
+    for tid in sorted(info):
+        meta = info[tid]
+        if readers <= 1:
+            tensors[tid] = storage.load_object(os.path.join(path + ".tensors", f"tensor_{tid}.pt"), map_location="cpu")
+            continue
+        owner = tid % readers
+        if reader_rank == owner:
+            t = storage.load_object(os.path.join(path + ".tensors", f"tensor_{tid}.pt"), map_location="cpu").to(dev)
+        else:
+            t = torch.empty(meta["shape"], dtype=meta["dtype"], device=dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, owner), group=group)
+        tensors[tid] = t
+    return _unflatten_tensors(ref, tensors)
+
+
+# ---------------------------------------------------------------------------- public API
+def has_checkpoint(checkpoint_dir_str: str) -> bool:
+    return len(create_checkpoint_storage(checkpoint_dir_str).list_completed_checkpoint_tags()) > 0
+
+
+def _zero1_states_have_master_weights(sd: Any) -> bool:
+    return isinstance(sd, dict) and "sharded_master_weights" in sd
+
+
+def save_checkpoint(
+    checkpoint_dir_str: str,
+    tag: str,
+    model: Any = None,
+    optimizer: Any = None,
+    scheduler: Any = None,
+    user_content: Any = None,
+    num_workers: int = 8,
+    use_xser: bool = False,
+    num_kept_ckpts: Optional[int] = None,
+    async_save: bool = False,
+    zero1_optimizer: bool = False,
+    use_zero1_dcp: bool = False,
+    avoid_saving_lower_precision_weights: bool = False,
+) -> None:
+    global g_iostate
+    assert dist.is_initialized(), "Only support distributed training mode."
+    storage = create_checkpoint_storage(checkpoint_dir_str)
+    if g_iostate is None or g_iostate.async_save != async_save:
+        if g_iostate is not None:
+            g_iostate.wait_all()
+        g_iostate = CheckpointIOState(async_save)
+        atexit.register(g_iostate.finalize_shutdown)
+    io = g_iostate
+    io.begin(storage, tag)
+    ep = ps.get_expert_model_parallel_size() > 1
+    dp_rank, dp_size = ps.get_data_parallel_rank(), ps.get_data_parallel_size()
+
+    opt_has_master = False
+    if optimizer is not None:
+        sd = optimizer.state_dict() if hasattr(optimizer, "state_dict") else optimizer
+        from ..optimizer.zero_redundancy_optimizer import NeuronEPZero1Optimizer, Zero1Optimizer
+
+        inner = getattr(optimizer, "optimizer", optimizer)
+        zero1 = zero1_optimizer or isinstance(inner, (Zero1Optimizer, NeuronEPZero1Optimizer))
+        opt_has_master = _zero1_states_have_master_weights(sd)
+        path = _get_path(os.path.join(tag, "optim"), dp=zero1, ep=False)
+        if use_zero1_dcp and zero1:
+            from ..optimizer import zero_dcp_utils
+
+            zero_dcp_utils.save_optim_state_dict(os.path.join(storage.dirname(), tag, "optim"), sd, inner)
+        elif use_xser:
+            writers, wrank = (1, 0) if zero1 else (dp_size, dp_rank)
+            _xser_tasks(sd, path, writers, wrank, io)
+        elif zero1 or dp_rank == 0:
+            io.add_save_task(_to_cpu(sd), path + ".pt")
+
+    if model is not None:
+        skip_weights = avoid_saving_lower_precision_weights and opt_has_master
+        if skip_weights:
+            logger.info("model weights are not saved: optimizer checkpoint holds the fp32 master weights")
+        else:
+            sd = model.state_dict() if hasattr(model, "state_dict") else model
+            path = _get_path(os.path.join(tag, "model"), dp=False, ep=ep)
+            if use_xser:
+                _xser_tasks(sd, path, dp_size, dp_rank, io)
+            elif dp_rank == 0 or ep:
+                io.add_save_task(_to_cpu(sd), path + ".pt")
+
+    if _rank() == 0:
+        if scheduler is not None:
+            io.add_save_task(scheduler.state_dict() if hasattr(scheduler, "state_dict") else scheduler,
+                             os.path.join(tag, "scheduler.pt"))
+        if user_content is not None:
+            io.add_save_task(user_content, os.path.join(tag, "user_content.pt"))
+    io.end(num_kept_ckpts)
+
+
+def load_checkpoint(
+    path: str,
+    tag: Optional[str] = None,
+    model: Optional[torch.nn.Module] = None,
+    optimizer: Optional[torch.optim.Optimizer] = None,
+    scheduler: Any = None,
+    num_workers: int = 8,
+    strict: bool = True,
+    use_zero1_dcp: bool = False,
+) -> Any:
+    assert dist.is_initialized(), "Only support distributed training mode."
+    global g_iostate
+    if g_iostate is not None:
+        g_iostate.wait_all()
+    storage = create_checkpoint_storage(path)
+    if tag is None:
+        tags = storage.list_completed_checkpoint_tags()
+        if not tags:
+            raise RuntimeError(f"no completed checkpoint under {path}")
+        tag = tags[-1]
+    ep = ps.get_expert_model_parallel_size() > 1
+    model_dir, optim_dir = os.path.join(tag, "model"), os.path.join(tag, "optim")
+    use_xser = storage.is_checkpoint_xser(model_dir) or storage.is_checkpoint_xser(optim_dir)
+    dp_group, dp_size, dp_rank = ps.get_data_parallel_group(), ps.get_data_parallel_size(), ps.get_data_parallel_rank()
+
+    if model is not None and storage.dir_exists(model_dir):
+        p = _get_path(model_dir, dp=False, ep=ep)
+        sd = _xser_load(storage, p, dp_group, dp_size, dp_rank) if use_xser else storage.load_object(p + ".pt", "cpu")
+        model.load_state_dict(sd, strict=strict)
+    if optimizer is not None:
+        from ..optimizer.zero_redundancy_optimizer import NeuronEPZero1Optimizer, Zero1Optimizer
+
+        inner = getattr(optimizer, "optimizer", optimizer)
+        zero1 = isinstance(inner, (Zero1Optimizer, NeuronEPZero1Optimizer))
+        p = _get_path(optim_dir, dp=zero1, ep=False)
+        if use_zero1_dcp and zero1:
+            from ..optimizer import zero_dcp_utils
+
+            sd = zero_dcp_utils.load_optim_state_dict(os.path.join(storage.dirname(), optim_dir), inner)
+        elif use_xser:
+            sd = _xser_load(storage, p, dp_group, 1 if zero1 else dp_size, 0 if zero1 else dp_rank)
+        else:
+            sd = storage.load_object(p + ".pt", "cpu")
+        optimizer.load_state_dict(sd)
+        if model is not None and not storage.dir_exists(model_dir) and zero1:
+            pass  # weights were restored from the fp32 master shards by the optimizer's load_state_dict
+    if scheduler is not None and storage.file_exists(os.path.join(tag, "scheduler.pt")):
+        scheduler.load_state_dict(storage.load_object(os.path.join(tag, "scheduler.pt"), "cpu"))
+    user_content = None
+    if storage.file_exists(os.path.join(tag, "user_content.pt")):
+        user_content = storage.load_object(os.path.join(tag, "user_content.pt"), "cpu")
+    _barrier()
+    return user_content
+
+
+def finalize_checkpoint() -> None:
+    if g_iostate is not None:
+        g_iostate.wait_all()

@@ -1,0 +1,237 @@
+"""Checkpoint storage back-ends (reference ``trainer/checkpoint_storage.py:46-612``).
+
+``BaseCheckpointStorage`` is the small file-system API the checkpoint logic is written against;
+``FilesysCheckpointStorage`` implements it for local/NFS/Lustre paths, ``S3CheckpointStorage`` for
+``s3://`` URIs (boto3 is optional in this image — the class raises a clear error at construction if it
+is missing).  Throttling errors are retried with decreasing jitter."""
+from __future__ import annotations
+
+import io
+import os
+import random
+import shutil
+import time
+from abc import ABC, abstractmethod
+from typing import Any, Callable, List, Optional
+
+import torch
+
+
+class BaseCheckpointStorage(ABC):
+    def __init__(self, dirname: str):
+        self._dirname = dirname
+
+    def dirname(self) -> str:
+        return self._dirname
+
+    # -- primitive ops ------------------------------------------------------------------
+    @abstractmethod
+    def dir_exists(self, dirname: str) -> bool: ...
+    @abstractmethod
+    def file_exists(self, filename: str) -> bool: ...
+    @abstractmethod
+    def is_checkpoint_xser(self, dirname: str) -> bool: ...
+    @abstractmethod
+    def list_dirs(self, dirname: str) -> List[str]: ...
+    @abstractmethod
+    def create_dir(self, dirname: str, exist_ok: bool = True) -> None: ...
+    @abstractmethod
+    def create_shared_dir(self, dirname: str, exist_ok: bool = True, process_group=None) -> None: ...
+    @abstractmethod
+    def remove_dir(self, dirname: str) -> None: ...
+    @abstractmethod
+    def remove_file(self, filename: str) -> None: ...
+    @abstractmethod
+    def save_text(self, text: str, filename: str) -> None: ...
+    @abstractmethod
+    def save_object(self, obj: Any, filename: str) -> None: ...
+    @abstractmethod
+    def load_object(self, filename: str, map_location=None) -> Any: ...
+
+    # -- derived ops -------------------------------------------------------------------
+    def is_checkpoint_tag_completed(self, tag: str) -> bool:
+        return self.file_exists(os.path.join(tag, "done"))
+
+    def list_checkpoint_tags(self) -> List[str]:
+        """All tags (sub-directories containing a ``checkpoint`` marker), oldest first."""
+        tags = [d for d in self.list_dirs(".") if self.file_exists(os.path.join(d, "checkpoint"))]
+        return self._sort_tags(tags)
+
+    def list_completed_checkpoint_tags(self) -> List[str]:
+        return [t for t in self.list_checkpoint_tags() if self.is_checkpoint_tag_completed(t)]
+
+    def find_files(self, dirname: str, pattern: str) -> List[str]:
+        return []
+
+    def _sort_tags(self, tags: List[str]) -> List[str]:
+        return sorted(tags, key=lambda t: self._tag_time(t))
+
+    def _tag_time(self, tag: str) -> float:
+        return 0.0
+
+
+class FilesysCheckpointStorage(BaseCheckpointStorage):
+    def _p(self, name: str) -> str:
+        return os.path.join(self._dirname, name)
+
+    def dir_exists(self, dirname: str) -> bool:
+        return os.path.isdir(self._p(dirname))
+
+    def file_exists(self, filename: str) -> bool:
+        return os.path.isfile(self._p(filename))
+
+    def is_checkpoint_xser(self, dirname: str) -> bool:
+        d = self._p(dirname)
+        if not os.path.isdir(d):
+            return False
+        return any(x.endswith(".tensors") for x in os.listdir(d))
+
+    def list_dirs(self, dirname: str) -> List[str]:
+        d = self._p(dirname)
+        if not os.path.isdir(d):
+            return []
+        return [x for x in os.listdir(d) if os.path.isdir(os.path.join(d, x))]
+
+    def find_files(self, dirname: str, pattern: str) -> List[str]:
+        import fnmatch
+
+        out = []
+        for root, _dirs, files in os.walk(self._p(dirname)):
+            for f in files:
+                if fnmatch.fnmatch(f, pattern):
+                    out.append(os.path.relpath(os.path.join(root, f), self._dirname))
+        return out
+
+    def create_dir(self, dirname: str, exist_ok: bool = True) -> None:
+        os.makedirs(self._p(dirname), exist_ok=exist_ok)
+
+    def create_shared_dir(self, dirname: str, exist_ok: bool = True, process_group=None) -> None:
+        import torch.distributed as dist
+
+        rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        if rank == 0:
+            self.create_dir(dirname, exist_ok)
+        if dist.is_initialized():
+            dist.barrier(group=process_group)
+
+    def remove_dir(self, dirname: str) -> None:
+        shutil.rmtree(self._p(dirname), ignore_errors=True)
+
+    def remove_file(self, filename: str) -> None:
+        try:
+            os.remove(self._p(filename))
+        except FileNotFoundError:
+            pass
+
+    def save_text(self, text: str, filename: str) -> None:
+        path = self._p(filename)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = path + ".tmp"
+        with open(tmp, "w") as f:
+            f.write(text)
+        os.replace(tmp, path)
+
+    def save_object(self, obj: Any, filename: str) -> None:
+        path = self._p(filename)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = path + ".tmp"
+        torch.save(obj, tmp)
+        os.replace(tmp, path)   # atomic publish: a reader never sees a half-written file
+
+    def load_object(self, filename: str, map_location=None) -> Any:
+        return torch.load(self._p(filename), map_location=map_location, weights_only=False)
+
+    def _tag_time(self, tag: str) -> float:
+        try:
+            return os.path.getmtime(self._p(os.path.join(tag, "checkpoint")))
+        except OSError:
+            return 0.0
+
+
+class S3CheckpointStorage(BaseCheckpointStorage):
+    """``s3://bucket/prefix`` storage (reference :236-605).  Requires boto3."""
+
+    MAX_RETRY = 10
+
+    def __init__(self, dirname: str):
+        super().__init__(dirname)
+        try:
+            import boto3  # type: ignore
+        except ImportError as e:  # pragma: no cover - boto3 is not in the offline image
+            raise RuntimeError("S3CheckpointStorage needs boto3, which is not installed in this environment") from e
+        assert dirname.startswith("s3://")
+        rest = dirname[len("s3://"):]
+        self.bucket, _, self.prefix = rest.partition("/")
+        self.s3 = boto3.client("s3")
+
+    def _key(self, name: str) -> str:
+        return os.path.normpath(os.path.join(self.prefix, name)).lstrip("./")
+
+    def _retry(self, fn: Callable, *a, **k):  # pragma: no cover - needs network
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        for attempt in range(self.MAX_RETRY):
+            try:
+                return fn(*a, **k)
+            except Exception as e:  # noqa: BLE001
+                msg = str(e)
+                if not any(t in msg for t in ("SlowDown", "Timeout", "RequestTimeout", "Throttl")) or attempt == self.MAX_RETRY - 1:
+                    raise
+                # jitter window shrinks with every attempt; scaled by job size so ranks spread out
+                time.sleep(random.uniform(0, max(1.0, world / 64.0) * (self.MAX_RETRY - attempt)))
+
+    def dir_exists(self, dirname: str) -> bool:  # pragma: no cover
+        r = self._retry(self.s3.list_objects_v2, Bucket=self.bucket, Prefix=self._key(dirname).rstrip("/") + "/", MaxKeys=1)
+        return r.get("KeyCount", 0) > 0
+
+    def file_exists(self, filename: str) -> bool:  # pragma: no cover
+        try:
+            self._retry(self.s3.head_object, Bucket=self.bucket, Key=self._key(filename))
+            return True
+        except Exception:  # noqa: BLE001
+            return False
+
+    def is_checkpoint_xser(self, dirname: str) -> bool:  # pragma: no cover
+        r = self._retry(self.s3.list_objects_v2, Bucket=self.bucket, Prefix=self._key(dirname).rstrip("/") + "/")
+        return any(".tensors/" in o["Key"] for o in r.get("Contents", []))
+
+    def list_dirs(self, dirname: str) -> List[str]:  # pragma: no cover
+        pfx = self._key(dirname).rstrip("/") + "/" if dirname not in (".", "") else (self.prefix.rstrip("/") + "/" if self.prefix else "")
+        r = self._retry(self.s3.list_objects_v2, Bucket=self.bucket, Prefix=pfx, Delimiter="/")
+        return [c["Prefix"][len(pfx):].rstrip("/") for c in r.get("CommonPrefixes", [])]
+
+    def create_dir(self, dirname: str, exist_ok: bool = True) -> None:
+        pass  # S3 has no directories
+
+    def create_shared_dir(self, dirname: str, exist_ok: bool = True, process_group=None) -> None:
+        pass
+
+    def remove_dir(self, dirname: str) -> None:  # pragma: no cover
+        pfx = self._key(dirname).rstrip("/") + "/"
+        while True:
+            r = self._retry(self.s3.list_objects_v2, Bucket=self.bucket, Prefix=pfx)
+            objs = [{"Key": o["Key"]} for o in r.get("Contents", [])]
+            if not objs:
+                break
+            self._retry(self.s3.delete_objects, Bucket=self.bucket, Delete={"Objects": objs})
+
+    def remove_file(self, filename: str) -> None:  # pragma: no cover
+        self._retry(self.s3.delete_object, Bucket=self.bucket, Key=self._key(filename))
+
+    def save_text(self, text: str, filename: str) -> None:  # pragma: no cover
+        self._retry(self.s3.put_object, Bucket=self.bucket, Key=self._key(filename), Body=text.encode())
+
+    def save_object(self, obj: Any, filename: str) -> None:  # pragma: no cover
+        buf = io.BytesIO()
+        torch.save(obj, buf)
+        buf.seek(0)
+        self._retry(self.s3.upload_fileobj, buf, self.bucket, self._key(filename))
+
+    def load_object(self, filename: str, map_location=None) -> Any:  # pragma: no cover
+        buf = io.BytesIO()
+        self._retry(self.s3.download_fileobj, self.bucket, self._key(filename), buf)
+        buf.seek(0)
+        return torch.load(buf, map_location=map_location, weights_only=False)
+
+
+def create_checkpoint_storage(dirname: str) -> BaseCheckpointStorage:
+    return S3CheckpointStorage(dirname) if dirname.startswith("s3://") else FilesysCheckpointStorage(dirname)
