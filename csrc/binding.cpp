@@ -144,6 +144,16 @@ static void gemm_bf16(const Tensor& a, const Tensor& b, Tensor out, bool trans_a
                  nullptr, stream());
 }
 
+static void gemm_bf16_2cta(const Tensor& a, const Tensor& b, Tensor out, bool trans_a, bool trans_b, bool accumulate) {
+  CHECK_IN(a); CHECK_IN(b); CHECK_IN(out);
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && a.dim() == 2 && b.dim() == 2);
+  const int M = (int)(trans_a ? a.size(1) : a.size(0)), K = (int)(trans_a ? a.size(0) : a.size(1));
+  const int N = (int)(trans_b ? b.size(0) : b.size(1));
+  TORCH_CHECK((trans_b ? b.size(1) : b.size(0)) == K && out.size(0) == M && out.size(1) == N, "gemm shape mismatch");
+  c10::cuda::CUDAGuard g(a.device());
+  nxd::gemm_bf16_2cta(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, trans_a, trans_b, dt_code(out), accumulate, stream());
+}
+
 // all-gather(A shards along rows) → GEMM.  `a_shard` [M/world, K]; gathered A lives in the symmetric payload at
 // buf_offset (every rank), out = A_full @ op(B).
 static void ag_gemm_bf16(const Tensor& a_shard, const Tensor& b, Tensor out, bool trans_b, int64_t local_buf_ptr,
@@ -218,6 +228,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("multi_tensor_scale", &multi_tensor_scale);
   m.def("fused_adamw", &fused_adamw);
   m.def("gemm_bf16", &gemm_bf16);
+  m.def("gemm_bf16_2cta", &gemm_bf16_2cta);
   m.def("ag_gemm_bf16", &ag_gemm_bf16);
   m.def("gemm_rs_bf16", &gemm_rs_bf16);
   m.def("symm_alloc", &symm_alloc);

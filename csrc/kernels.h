@@ -47,5 +47,8 @@ struct GemmComm {          // in-kernel NVLink communication description (all ze
 void gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, bool trans_a, bool trans_b, int out_dt,
                bool accumulate, const GemmComm& comm, const void* a_local_shard, cudaStream_t st);
 bool gemm_self_check_supported();
+// CTA-pair (cta_group::2) variant, plain GEMM only
+void gemm_bf16_2cta(const void* a, const void* b, void* out, int M, int N, int K, bool trans_a, bool trans_b, int out_dt,
+                    bool accumulate, cudaStream_t st);
 
 }  // namespace nxd

@@ -112,6 +112,12 @@ def reset() -> None:
     _WORKSPACES.clear()
 
 
+def _wgrad(go2d, x2d, weight):
+    from ..parallel_layers.layers import wgrad
+
+    return wgrad(go2d, x2d, weight)
+
+
 def _flat(x: torch.Tensor) -> torch.Tensor:
     return x.reshape(-1, x.shape[-1])
 
@@ -137,7 +143,7 @@ class _ColumnSP:
             gx2 = self.ws.gemm_rs(g2, weight, False)                     # RS(g @ W)
             gx = gx2.view(x.shape)
         if need_gw:
-            gw = gemm.matmul(g2, gathered, trans_a=True, trans_b=False)  # gᵀ @ AG(x)
+            gw = _wgrad(g2, gathered, weight)                            # gᵀ @ AG(x)
         return gx, gw, gbias
 
 
@@ -157,7 +163,7 @@ class _RowSP:
         gbias = g2.float().sum(0).to(gy.dtype) if has_bias else None
         gx2, g_full = self.ws.ag_gemm(g2, weight, False)                 # AG(g) @ W
         gx = gx2.view(x.shape) if need_gx else None
-        gw = gemm.matmul(g_full, _flat(x), trans_a=True, trans_b=False) if need_gw else None   # AG(g)ᵀ @ x
+        gw = _wgrad(g_full, _flat(x), weight) if need_gw else None       # AG(g)ᵀ @ x
         return gx, gw, gbias
 
 

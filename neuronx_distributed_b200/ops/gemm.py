@@ -17,6 +17,11 @@ import torch
 from . import _ext
 
 _MIN_DIM = 64
+_USE_2CTA = os.environ.get("NXD_GEMM_2CTA", "0") == "1"   # CTA-pair kernel (cta_group::2)
+
+
+def fused_wgrad_enabled() -> bool:
+    return os.environ.get("NXD_DISABLE_FUSED_WGRAD", "0") != "1" and os.environ.get("NXD_DISABLE_TCGEN05_GEMM", "0") != "1"
 
 
 def _eligible(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int) -> bool:
@@ -44,7 +49,10 @@ def matmul(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: boo
             out = torch.empty(M, N, dtype=out_dtype, device=a.device)
             accumulate = False
         _ext.count_launch()
-        _ext.ext().gemm_bf16(a, b, out, bool(trans_a), bool(trans_b), bool(accumulate))
+        if _USE_2CTA and M >= 256 and hasattr(_ext.ext(), "gemm_bf16_2cta"):
+            _ext.ext().gemm_bf16_2cta(a, b, out, bool(trans_a), bool(trans_b), bool(accumulate))
+        else:
+            _ext.ext().gemm_bf16(a, b, out, bool(trans_a), bool(trans_b), bool(accumulate))
         return out
     if a.is_cuda and a.dtype == torch.bfloat16 and not os.environ.get("NXD_DISABLE_TCGEN05_GEMM") \
             and (not a.is_contiguous() or not b.is_contiguous()):

@@ -170,17 +170,30 @@ class Zero1Optimizer(torch.optim.Optimizer):
         def hook(param):
             if param.grad is None:
                 return
-            param.main_grad.add_(param.grad.to(param.main_grad.dtype))
+            if getattr(param, "main_grad_fresh", False):   # first contribution since zero_grad: overwrite
+                param.main_grad.copy_(param.grad)
+                param.main_grad_fresh = False
+            else:
+                param.main_grad.add_(param.grad)
             param.grad = None
 
         self._hooks.append(p.register_post_accumulate_grad_hook(hook))
 
     # ------------------------------------------------------------------ grads
     def zero_grad(self, set_to_none: bool = True) -> None:
+        """No memset of the (multi-GB) flat gradient buffer: parameters are marked *fresh* and the first
+        gradient contribution of the step overwrites instead of accumulating."""
         for fg in self.flat_groups:
-            fg.grad_flat.zero_()
             for s in fg.slots:
                 s.param.grad = None
+                s.param.main_grad_fresh = True
+
+    def _zero_untouched(self) -> None:
+        for fg in self.flat_groups:
+            for s in fg.slots:
+                if getattr(s.param, "main_grad_fresh", False):   # received no gradient this step
+                    s.param.main_grad.zero_()
+                    s.param.main_grad_fresh = False
 
     def _reduce_scatter_grads(self) -> None:
         """grad_flat (summed over microbatches) → this rank's averaged shard."""
@@ -266,6 +279,7 @@ class Zero1Optimizer(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure: Optional[Callable] = None, **kwargs):
         loss = closure() if closure is not None else None
+        self._zero_untouched()
         self._reduce_scatter_grads()
         coeff = None
         if self.grad_clipping:
@@ -386,6 +400,7 @@ class NeuronEPZero1Optimizer(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None, **kw):
         for o in self._opts:
+            o._zero_untouched()
             o._reduce_scatter_grads()
         coeff = None
         if self.grad_clipping:

@@ -287,6 +287,22 @@ def _flat2d(x: torch.Tensor) -> torch.Tensor:
     return x.reshape(-1, x.shape[-1])
 
 
+def wgrad(go2d: torch.Tensor, x2d: torch.Tensor, weight: torch.Tensor):
+    """``dW = goᵀ @ x``.  If the optimizer gave the weight an fp32 ``main_grad`` buffer (ZeRO-1 with fp32 gradient
+    accumulation) the GEMM epilogue accumulates straight into it — no bf16 gradient tensor, no cast, no separate
+    add kernel — and ``None`` is returned to autograd (Megatron-style gradient-accumulation fusion)."""
+    from .. import ops
+
+    mg = getattr(weight, "main_grad", None)
+    if (mg is not None and go2d.is_cuda and go2d.dtype == torch.bfloat16 and mg.dtype == torch.float32
+            and mg.is_contiguous() and mg.shape == weight.shape and ops.gemm.fused_wgrad_enabled()):
+        fresh = getattr(weight, "main_grad_fresh", False)
+        ops.gemm.matmul(go2d, x2d, True, False, out=mg, accumulate=not fresh)
+        weight.main_grad_fresh = False
+        return None
+    return ops.gemm.matmul(go2d, x2d, True, False)
+
+
 class _TPLinear(torch.autograd.Function):
     """``y = collective_out( collective_in(x) @ W^T )`` with its transposed backward.
 
@@ -381,7 +397,7 @@ class _TPLinear(torch.autograd.Function):
         gw = None
         if weight.requires_grad:
             total = comm.all_gather(x, dim=seq_dim, group=group) if (in_mode == "gather" and n > 1) else x
-            gw = ops.gemm.matmul(_flat2d(g_out), _flat2d(total), True, False)
+            gw = wgrad(_flat2d(g_out), _flat2d(total), weight)
         if work is not None:
             work.wait()
         return gx, gw, gbias, None, None, None, None, None, None

@@ -150,6 +150,35 @@ def check_gemm(perf=False):
     report("gemm_f32_accumulate", relerr(out, ref) < 1e-3, err=relerr(out, ref))
 
 
+def check_gemm_2cta():
+    torch.manual_seed(0)
+    e = ops._ext.ext()
+    for (M, N, K) in [(256, 256, 64), (512, 512, 256), (4096, 1536, 4096), (1000, 264, 72), (384, 768, 192)]:
+        for ta, tb in ((False, True), (False, False), (True, False)):
+            a = torch.randn((K, M) if ta else (M, K), device=dev, dtype=torch.bfloat16)
+            b = torch.randn((N, K) if tb else (K, N), device=dev, dtype=torch.bfloat16)
+            ref = (a.float().t() if ta else a.float()) @ (b.float().t() if tb else b.float())
+            out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            e.gemm_bf16_2cta(a, b, out, ta, tb, False)
+            torch.cuda.synchronize()
+            err = relerr(out, ref)
+            report(f"gemm2cta_{M}x{N}x{K}_ta{int(ta)}_tb{int(tb)}", err < 1e-2, err=err)
+    M, N, K = 512, 512, 128
+    a = torch.randn(M, K, device=dev, dtype=torch.bfloat16); b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+    out = torch.ones(M, N, device=dev, dtype=torch.float32)
+    e.gemm_bf16_2cta(a, b, out, False, True, True)
+    report("gemm2cta_f32_accumulate", relerr(out, a.float() @ b.float().t() + 1) < 1e-3)
+    for (M, N, K) in [(4096, 1536, 4096), (4096, 4096, 1376), (4096, 12288, 4096), (4096, 22016, 4096), (4096, 4096, 11008),
+                      (8192, 8192, 8192)]:
+        a = torch.randn(M, K, device=dev, dtype=torch.bfloat16); b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        t2 = timeit(lambda: e.gemm_bf16_2cta(a, b, out, False, True, False))
+        t1 = timeit(lambda: e.gemm_bf16(a, b, out, False, True, False))
+        tl = timeit(lambda: torch.matmul(a, b.t()))
+        fl = 2.0 * M * N * K
+        report(f"gemm2cta_perf_{M}x{N}x{K}", True, cta2_tflops=fl / t2 / 1e9, cta1_tflops=fl / t1 / 1e9, cublas_tflops=fl / tl / 1e9)
+
+
 def check_gemm_perf():
     peaks = {}
     for (M, N, K) in [(4096, 1536, 4096), (4096, 2752, 4096), (4096, 4096, 512), (4096, 4096, 1376), (4096, 4000, 4096),
@@ -170,6 +199,8 @@ if __name__ == "__main__":
         check_elementwise()
     if what in ("gemm", "all"):
         check_gemm()
+    if what in ("gemm2",):
+        check_gemm_2cta()
     if what in ("gemm_perf", "all"):
         check_gemm_perf()
     bad = [r["name"] for r in RESULTS if not r["ok"]]
