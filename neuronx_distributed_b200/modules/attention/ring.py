@@ -1,0 +1,100 @@
+"""Context-parallel ring attention.
+
+Role of the reference's NKI ring kernels (``kernels/ring_attention_kernel.py:44-167``, K3/K4): each CP rank holds a
+contiguous ``S/cp`` slice of Q, K, V; K/V blocks travel around the CP ring and every rank merges the partial
+attention of each visiting block into its output with a log-sum-exp update.  With contiguous slices and a causal
+mask, a block that originated on a *later* rank is skipped, the local block is causal, earlier blocks are dense
+(same — load-imbalanced — split as the reference: no zig-zag).
+
+B200 design: the ring transfer is an NCCL p2p exchange issued *before* the block's attention so it overlaps the
+compute; the exchange is itself an autograd node (its backward moves dK/dV the opposite way round the ring), so
+backward is the exact transpose of forward without a hand-written second pass.  Per-block attention is the
+flash kernel (returns LSE) on CUDA and an fp32 reference on CPU.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ...parallel_layers import parallel_state as ps
+
+
+def block_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool, scale: float
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """q [B,Sq,H,D], k/v [B,Sk,Hkv,D] → (out [B,Sq,H,D], lse [B,H,Sq] fp32)."""
+    hq, hkv = q.shape[2], k.shape[2]
+    qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+    if hq != hkv:
+        kt, vt = kt.repeat_interleave(hq // hkv, 1), vt.repeat_interleave(hq // hkv, 1)
+    if q.is_cuda and q.dtype in (torch.bfloat16, torch.float16):
+        out, lse = torch.ops.aten._scaled_dot_product_flash_attention(qt, kt, vt, 0.0, causal, False, scale=scale)[:2]
+        return out.transpose(1, 2), lse.float()
+    s = torch.matmul(qt.float(), kt.float().transpose(-1, -2)) * scale
+    if causal:
+        sq, sk = s.shape[-2], s.shape[-1]
+        mask = torch.ones(sq, sk, dtype=torch.bool, device=s.device).tril(diagonal=sk - sq)
+        s = s.masked_fill(~mask, float("-inf"))
+    lse = torch.logsumexp(s, dim=-1)
+    p = torch.exp(s - lse.unsqueeze(-1))
+    out = torch.matmul(p, vt.float()).to(q.dtype)
+    return out.transpose(1, 2), lse
+
+
+class _RingShift(torch.autograd.Function):
+    """send ``x`` to the next rank of the ring, receive the previous rank's; backward shifts the other way."""
+
+    @staticmethod
+    def forward(ctx, x, group, nxt, prv):
+        ctx.group, ctx.nxt, ctx.prv = group, nxt, prv
+        return _exchange(x, group, nxt, prv)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _exchange(g.contiguous(), ctx.group, ctx.prv, ctx.nxt), None, None, None
+
+
+def _exchange(x: torch.Tensor, group, send_to: int, recv_from: int) -> torch.Tensor:
+    buf = torch.empty_like(x)
+    ops = [dist.P2POp(dist.isend, x.contiguous(), send_to, group), dist.P2POp(dist.irecv, buf, recv_from, group)]
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    return buf
+
+
+def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True,
+                   scale: Optional[float] = None, group=None) -> torch.Tensor:
+    """q/k/v: this rank's ``[B, S/cp, H, D]`` slices → attention output for the local queries."""
+    group = group if group is not None else ps.get_context_model_parallel_group()
+    cp = dist.get_world_size(group)
+    scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
+    if cp == 1:
+        return block_attention(q, k, v, causal, scale)[0]
+    r = dist.get_rank(group)
+    ranks = dist.get_process_group_ranks(group)
+    nxt, prv = ranks[(r + 1) % cp], ranks[(r - 1) % cp]
+    out: Optional[torch.Tensor] = None
+    lse: Optional[torch.Tensor] = None
+    kv = torch.stack([k, v])  # travel together: one message per hop
+    for step in range(cp):
+        src = (r - step) % cp                       # origin rank of the block currently held
+        nxt_kv = _RingShift.apply(kv, group, nxt, prv) if step < cp - 1 else None   # start next hop early
+        if not causal or src <= r:
+            o_b, lse_b = block_attention(q, kv[0], kv[1], causal and src == r, scale)
+            if out is None:
+                out, lse = o_b.float(), lse_b
+            else:
+                new_lse = torch.logaddexp(lse, lse_b)
+                w_old = torch.exp(lse - new_lse).transpose(1, 2).unsqueeze(-1)     # [B,S,H,1]
+                w_new = torch.exp(lse_b - new_lse).transpose(1, 2).unsqueeze(-1)
+                out = out * w_old + o_b.float() * w_new
+                lse = new_lse
+        if nxt_kv is None:
+            last_kv = kv
+        kv = nxt_kv
+    # tie the last visiting block into the graph with zero weight: a rank that skipped it (causal) must still run
+    # every ring-shift backward, otherwise its neighbours would wait forever for the matching exchange
+    out = out + 0.0 * last_kv.float().sum()
+    return out.to(q.dtype)

@@ -1,0 +1,35 @@
+"""Distributed argmax over a dimension sharded across TP (reference ``operators/argmax.py:55-152``).
+
+local (max, argmax) → ONE all-gather of the packed ``[..., 2]`` (value, global index) pairs over the group →
+final argmax of the ``tp`` candidates.  Ties resolve to the smallest global index, like ``torch.argmax`` on
+the gathered tensor.  The reference's multi-stage "cascaded max" NKI kernel (K10) is a single fused
+``torch.max`` pass per shard on CUDA — a [B, V/tp] row reduction is a one-kernel HBM-bound op."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from ..parallel_layers import comm
+from ..parallel_layers import parallel_state as ps
+
+
+def argmax(tensor: torch.Tensor, dim: int, gather_dim: Optional[int] = None, keepdim: bool = False,
+           process_group=None, rank_id: Optional[torch.Tensor] = None) -> torch.Tensor:
+    group = process_group if process_group is not None else ps.get_tensor_model_parallel_group()
+    n = dist.get_world_size(group)
+    dim = dim % tensor.dim()
+    val, idx = torch.max(tensor, dim=dim, keepdim=True)
+    if n == 1:
+        return idx if keepdim else idx.squeeze(dim)
+    r = dist.get_rank(group) if rank_id is None else rank_id.reshape(-1)[0].to(idx.device)
+    gidx = idx + r * tensor.shape[dim]
+    packed = torch.stack([val.float(), gidx.float()], dim=-1)           # one collective for both
+    allp = comm.all_gather(packed.unsqueeze(0), dim=0, group=group)     # [n, ..., 1, ..., 2]
+    vals, gids = allp[..., 0], allp[..., 1].long()
+    # max value; among equal values the lowest global index
+    best = vals.max(dim=0, keepdim=True).values
+    cand = torch.where(vals == best, gids, torch.full_like(gids, torch.iinfo(torch.long).max))
+    out = cand.min(dim=0).values
+    return out if keepdim else out.squeeze(dim)

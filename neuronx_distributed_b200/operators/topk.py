@@ -1,0 +1,28 @@
+"""Distributed top-k over a dimension sharded across TP (reference ``operators/topk.py:31-148``):
+local top-k → all-gather of (values, global indices) → top-k of the ``k·tp`` candidates."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..parallel_layers import comm
+from ..parallel_layers import parallel_state as ps
+
+
+def topk(tensor: torch.Tensor, k: int, dim: int, gather_dim: Optional[int] = None, process_group=None,
+         rank_id: Optional[torch.Tensor] = None, stages: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    group = process_group if process_group is not None else ps.get_tensor_model_parallel_group()
+    n = dist.get_world_size(group)
+    dim = dim % tensor.dim()
+    kk = min(k, tensor.shape[dim])
+    vals, idx = torch.topk(tensor, kk, dim=dim)
+    if n == 1:
+        return vals, idx
+    r = dist.get_rank(group) if rank_id is None else rank_id.reshape(-1)[0].to(idx.device)
+    gidx = idx + r * tensor.shape[dim]
+    allv = comm.all_gather(vals, dim=dim, group=group)
+    alli = comm.all_gather(gidx, dim=dim, group=group)
+    fv, pos = torch.topk(allv, k, dim=dim)
+    return fv, torch.gather(alli, dim, pos)

@@ -1,0 +1,50 @@
+"""On-device token sampling (reference ``utils/sampling.py:6-77``): greedy, top-k / top-p / temperature
+multinomial, all on the GPU with no host sync; with vocab-parallel logits the top-k candidates come from
+:func:`operators.topk` (one all-gather of k·tp pairs)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ..operators import argmax as dist_argmax
+from ..operators import topk as dist_topk
+
+
+class Sampler:
+    def __init__(self, top_k: int = 1, top_p: float = 1.0, temperature: float = 1.0, do_sample: bool = False,
+                 dynamic: bool = False, deterministic: bool = False, on_device: bool = True, vocab_parallel: bool = False):
+        self.top_k, self.top_p, self.temperature = top_k, top_p, temperature
+        self.do_sample, self.dynamic, self.deterministic = do_sample, dynamic, deterministic
+        self.vocab_parallel = vocab_parallel
+
+    def sample(self, logits: torch.Tensor, rank_id: Optional[torch.Tensor] = None,
+               generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """``logits`` [B, V] (or [B, V/tp] when ``vocab_parallel``) → token ids [B]."""
+        if self.top_k == 1 or not self.do_sample:
+            if self.vocab_parallel:
+                return dist_argmax(logits, dim=-1, rank_id=rank_id)
+            return torch.argmax(logits, dim=-1)
+        k = self.top_k if self.top_k > 0 else logits.shape[-1]
+        if self.vocab_parallel:
+            vals, idx = dist_topk(logits, k, dim=-1, rank_id=rank_id)
+        else:
+            vals, idx = torch.topk(logits, min(k, logits.shape[-1]), dim=-1)
+        vals = vals.float() / max(self.temperature, 1e-6)
+        probs = torch.softmax(vals, dim=-1)
+        if self.top_p < 1.0:
+            cum = probs.cumsum(-1)
+            keep = (cum - probs) < self.top_p          # always keeps the first candidate
+            probs = probs * keep
+            probs = probs / probs.sum(-1, keepdim=True)
+        if self.deterministic:
+            choice = probs.argmax(-1, keepdim=True)
+        else:
+            choice = torch.multinomial(probs, 1, generator=generator)
+        return idx.gather(-1, choice).squeeze(-1)
+
+
+def create_sampler(neuron_config=None, **kw) -> Sampler:
+    if neuron_config is not None:
+        kw = {**{k: getattr(neuron_config, k) for k in ("top_k", "top_p", "temperature", "do_sample") if hasattr(neuron_config, k)}, **kw}
+    return Sampler(**kw)

@@ -148,3 +148,27 @@ def _pp_worker(rank, world, pp, vpp, tie, out_path):
 @pytest.mark.parametrize("pp,vpp,tie", [(2, 1, False), (2, 2, False), (2, 1, True)])
 def test_pipeline_matches_single_process(tmp_path, pp, vpp, tie):
     run_distributed(_pp_worker, pp, pp, vpp, tie, str(tmp_path / "o.pt"), timeout=90)
+
+
+def _ring_worker(rank, world):
+    from neuronx_distributed_b200.modules.attention.ring import block_attention, ring_attention
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    ps.initialize_model_parallel(1, 1, context_parallel_size=world)
+    torch.manual_seed(0)
+    B, S, H, D = 2, 16, 4, 8
+    q, k, v = [torch.randn(B, S, H, D) for _ in range(3)]
+    qr, kr, vr = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    ref, _ = block_attention(qr, kr, vr, True, D ** -0.5)
+    ref.sum().backward()
+    sl = slice(rank * S // world, (rank + 1) * S // world)
+    ql, kl, vl = [t[:, sl].clone().requires_grad_(True) for t in (q, k, v)]
+    o = ring_attention(ql, kl, vl, True)
+    torch.testing.assert_close(o, ref[:, sl].detach(), rtol=1e-4, atol=1e-5)
+    o.sum().backward()
+    for a, b in ((ql, qr), (kl, kr), (vl, vr)):
+        torch.testing.assert_close(a.grad, b.grad[:, sl], rtol=1e-4, atol=1e-5)
+
+
+def test_ring_attention_context_parallel():
+    run_distributed(_ring_worker, 4, timeout=90)
