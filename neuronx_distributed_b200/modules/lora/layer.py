@@ -1,0 +1,103 @@
+"""LoRA adapter layers (reference ``modules/lora/layer.py``): ``y = base(x) + scaling · B(A(dropout(x)))``."""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .config import LoraConfig
+
+
+class LoraLayer(nn.Module):
+    """Common state: base layer, low-rank pair, scaling, merge bookkeeping."""
+
+    def __init__(self, base_layer: nn.Module, config: LoraConfig):
+        super().__init__()
+        self.base_layer = base_layer
+        self.lora_config = config
+        self.r, self.scaling = config.lora_rank, config.scaling
+        self.dropout = nn.Dropout(config.lora_dropout) if config.lora_dropout > 0 else nn.Identity()
+        self.merged = False
+        for p in base_layer.parameters():
+            p.requires_grad_(False)
+
+    def init_lora_parameters(self, a: torch.Tensor, b: torch.Tensor) -> None:
+        if self.lora_config.init_lora_weights == "gaussian":
+            nn.init.normal_(a, std=1.0 / self.r)
+        else:
+            nn.init.kaiming_uniform_(a, a=math.sqrt(5))
+        nn.init.zeros_(b)
+
+    def delta_weight(self) -> torch.Tensor:
+        raise NotImplementedError
+
+    def merge(self) -> None:
+        if not self.merged:
+            self.base_layer.weight.data += self.delta_weight().to(self.base_layer.weight.dtype)
+            self.merged = True
+
+    def unmerge(self) -> None:
+        if self.merged:
+            self.base_layer.weight.data -= self.delta_weight().to(self.base_layer.weight.dtype)
+            self.merged = False
+
+
+class LoraLinear(LoraLayer):
+    def __init__(self, base_layer: nn.Linear, config: LoraConfig):
+        super().__init__(base_layer, config)
+        dt, dev = base_layer.weight.dtype, base_layer.weight.device
+        self.lora_A = nn.Linear(base_layer.in_features, self.r, bias=False, dtype=dt, device=dev)
+        self.lora_B = nn.Linear(self.r, base_layer.out_features, bias=False, dtype=dt, device=dev)
+        self.init_lora_parameters(self.lora_A.weight, self.lora_B.weight)
+
+    def delta_weight(self) -> torch.Tensor:
+        return (self.lora_B.weight @ self.lora_A.weight) * self.scaling
+
+    def forward(self, x: torch.Tensor, *a, **k):
+        y = self.base_layer(x, *a, **k)
+        if self.merged:
+            return y
+        return y + self.lora_B(self.lora_A(self.dropout(x))) * self.scaling
+
+
+class LoraEmbedding(LoraLayer):
+    def __init__(self, base_layer: nn.Embedding, config: LoraConfig):
+        super().__init__(base_layer, config)
+        dt, dev = base_layer.weight.dtype, base_layer.weight.device
+        self.lora_embedding_A = nn.Parameter(torch.empty(self.r, base_layer.num_embeddings, dtype=dt, device=dev))
+        self.lora_embedding_B = nn.Parameter(torch.empty(base_layer.embedding_dim, self.r, dtype=dt, device=dev))
+        nn.init.zeros_(self.lora_embedding_A)
+        nn.init.normal_(self.lora_embedding_B)
+
+    def delta_weight(self) -> torch.Tensor:
+        return (self.lora_embedding_B @ self.lora_embedding_A).t() * self.scaling
+
+    def forward(self, ids: torch.Tensor):
+        y = self.base_layer(ids)
+        if self.merged:
+            return y
+        after_a = F.embedding(ids, self.lora_embedding_A.t())
+        return y + (after_a @ self.lora_embedding_B.t()) * self.scaling
+
+
+class LoraConv2d(LoraLayer):
+    def __init__(self, base_layer: nn.Conv2d, config: LoraConfig):
+        super().__init__(base_layer, config)
+        dt, dev = base_layer.weight.dtype, base_layer.weight.device
+        self.lora_A = nn.Conv2d(base_layer.in_channels, self.r, base_layer.kernel_size, base_layer.stride,
+                                base_layer.padding, bias=False, dtype=dt, device=dev)
+        self.lora_B = nn.Conv2d(self.r, base_layer.out_channels, 1, 1, bias=False, dtype=dt, device=dev)
+        self.init_lora_parameters(self.lora_A.weight, self.lora_B.weight)
+
+    def delta_weight(self) -> torch.Tensor:
+        a, b = self.lora_A.weight, self.lora_B.weight
+        return (b.flatten(1) @ a.flatten(1)).view(self.base_layer.weight.shape) * self.scaling
+
+    def forward(self, x: torch.Tensor):
+        y = self.base_layer(x)
+        if self.merged:
+            return y
+        return y + self.lora_B(self.lora_A(self.dropout(x))) * self.scaling
