@@ -112,6 +112,24 @@ class BaseParallelLayer(nn.Module):
             warnings.warn("parallel state is not initialized; falling back to a single-rank world")
             ps.initialize_fallback_parallel_state()
 
+    def __deepcopy__(self, memo):
+        """Process groups are shared by reference (they cannot be pickled/copied) and the parallel attributes on
+        parameters survive the copy (``Parameter.__deepcopy__`` drops custom attributes)."""
+        import copy
+
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if isinstance(v, dist.ProcessGroup):
+                new.__dict__[k] = v
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        for (_, p_old), (_, p_new) in zip(self.named_parameters(recurse=False), new.named_parameters(recurse=False)):
+            for ak, av in p_old.__dict__.items():
+                if not hasattr(p_new, ak):
+                    setattr(p_new, ak, av)
+        return new
+
 
 def _group_info(group) -> Tuple[Any, int, int]:
     group = group if group is not None else ps.get_tensor_model_parallel_group()
