@@ -17,7 +17,7 @@ import torch
 from . import _ext
 
 _MIN_DIM = 64
-_USE_2CTA = os.environ.get("NXD_GEMM_2CTA", "0") == "1"   # CTA-pair kernel (cta_group::2)
+_USE_2CTA = os.environ.get("NXD_GEMM_2CTA", "1") == "1"   # CTA-pair kernel (cta_group::2)
 
 
 def fused_wgrad_enabled() -> bool:
