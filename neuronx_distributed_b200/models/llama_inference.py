@@ -1,0 +1,132 @@
+"""Llama inference model: context encoding (prefill) + token generation (decode) over a persistent KV cache, with
+on-device sampling — role of reference ``examples/inference`` (``NeuronBaseModel`` / ``ModelWrapper`` /
+``KVCacheManager`` / ``hf_adapter``), re-using the training model's parameter names so the same checkpoints load.
+No sequence parallelism at inference: Row-parallel outputs are all-reduced."""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .. import ops
+from ..inference.kv_cache import KVCacheManager
+from ..operators import argmax as dist_argmax
+from ..parallel_layers import parallel_state as ps
+from ..utils.sampling import Sampler
+from .llama import LlamaConfig, LlamaForCausalLM
+
+
+class LlamaForInference(nn.Module):
+    def __init__(self, cfg: LlamaConfig, batch_size: int = 1, max_seq_len: int = 2048, on_device_sampling: bool = True,
+                 sampler: Optional[Sampler] = None):
+        super().__init__()
+        cfg.sequence_parallel_enabled = False
+        cfg.activation_checkpointing = "none"
+        self.cfg = cfg
+        self.lm = LlamaForCausalLM(cfg)
+        self.batch_size, self.max_seq_len = batch_size, max_seq_len
+        attn0 = self.lm.model.layers[0].self_attn
+        self.kv = KVCacheManager(cfg.num_hidden_layers, batch_size, max_seq_len, attn0.num_kv_heads_local, cfg.head_dim,
+                                 dtype=cfg.dtype, device=cfg.device)
+        self.sampler = sampler or Sampler(top_k=1, vocab_parallel=True)
+        self.on_device_sampling = on_device_sampling
+        cos, sin = ops.rope.rope_tables(max_seq_len, cfg.head_dim, cfg.rope_theta, cfg.device, 0, cfg.rope_scaling_factor)
+        self.register_buffer("rope_cos", cos, persistent=False)
+        self.register_buffer("rope_sin", sin, persistent=False)
+
+    def load_state_dict(self, sd, strict: bool = True):
+        return self.lm.load_state_dict(sd, strict=strict)
+
+    def state_dict(self, *a, **k):
+        return self.lm.state_dict(*a, **k)
+
+    # ------------------------------------------------------------------ shared pieces
+    def _attn_block(self, layer_idx: int, layer, x: torch.Tensor, positions: Optional[torch.Tensor], prefill: bool,
+                    kv_len: Optional[int]) -> torch.Tensor:
+        att = layer.self_attn
+        h = layer.input_layernorm(x)
+        q, k, v = att.qkv_proj(h)                          # [S, B, h*D]
+        S, B = q.shape[0], q.shape[1]
+        D = att.head_dim
+        q = q.reshape(S, B, att.num_heads_local, D).transpose(0, 1)
+        k = k.reshape(S, B, att.num_kv_heads_local, D).transpose(0, 1)
+        v = v.reshape(S, B, att.num_kv_heads_local, D).transpose(0, 1).contiguous()
+        if prefill:
+            cos, sin = self.rope_cos[:S], self.rope_sin[:S]
+            q, k = ops.rope.apply_rotary(q, cos, sin), ops.rope.apply_rotary(k, cos, sin)
+            self.kv.write_prefill(layer_idx, k, v)
+            o = ops.attention.flash_attention(q, k, v, causal=True)
+        else:
+            # one new token per sequence at its own position
+            cos = self.rope_cos[positions].unsqueeze(1)     # [B, 1, D/2] → per-batch tables
+            sin = self.rope_sin[positions].unsqueeze(1)
+            q, k = _rope_per_batch(q, cos, sin), _rope_per_batch(k, cos, sin)
+            self.kv.write_decode(layer_idx, k, v, positions)
+            kc, vc = self.kv.get(layer_idx, kv_len)
+            o = _decode_attention(q, kc, vc, positions)
+        o = o.transpose(0, 1).reshape(S, B, att.num_heads_local * D)
+        return x + att.o_proj(o)
+
+    def _body(self, input_ids: torch.Tensor, positions: Optional[torch.Tensor], prefill: bool, kv_len: Optional[int]):
+        x = self.lm.model.embed_tokens(input_ids).transpose(0, 1).contiguous()     # [S, B, H]
+        for i, layer in enumerate(self.lm.model.layers):
+            x = self._attn_block(i, layer, x, positions, prefill, kv_len)
+            x = x + layer.mlp(layer.post_attention_layernorm(x))
+        return self.lm.model.norm(x)
+
+    # ------------------------------------------------------------------ entry points
+    @torch.no_grad()
+    def context_encoding(self, input_ids: torch.Tensor, last_token_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``input_ids`` [B, S_bucket] (right-padded) → next token ids [B] (or vocab-parallel logits)."""
+        h = self._body(input_ids, None, True, None)                              # [S, B, H]
+        B = input_ids.shape[0]
+        if last_token_index is None:
+            last = h[-1]
+        else:
+            last = h[last_token_index, torch.arange(B, device=h.device)]
+        logits = self.lm.lm_head(last.unsqueeze(0))[0].float()                   # [B, V/tp]
+        return self.sampler.sample(logits) if self.on_device_sampling else logits
+
+    @torch.no_grad()
+    def token_generation(self, input_ids: torch.Tensor, positions: torch.Tensor, kv_len: Optional[int] = None) -> torch.Tensor:
+        """``input_ids`` [B, 1], ``positions`` [B] → next token ids [B]."""
+        h = self._body(input_ids, positions, False, kv_len)
+        logits = self.lm.lm_head(h)[0].float()
+        return self.sampler.sample(logits) if self.on_device_sampling else logits
+
+    @torch.no_grad()
+    def generate(self, prompt_ids: torch.Tensor, max_new_tokens: int, prompt_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, S = prompt_ids.shape
+        lens = prompt_lens if prompt_lens is not None else torch.full((B,), S, device=prompt_ids.device, dtype=torch.long)
+        tok = self.context_encoding(prompt_ids, lens - 1)
+        out = [tok]
+        pos = lens.clone()
+        for _ in range(max_new_tokens - 1):
+            tok = self.token_generation(tok.view(B, 1), pos)
+            out.append(tok)
+            pos = pos + 1
+        return torch.stack(out, dim=1)
+
+
+def _rope_per_batch(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    """x [B,1,H,D]; cos/sin [B,1,D/2] — tiny decode-time rotation (elementwise, graph-capturable)."""
+    d2 = x.shape[-1] // 2
+    xf = x.float()
+    x1, x2 = xf[..., :d2], xf[..., d2:]
+    c, s = cos.unsqueeze(2), sin.unsqueeze(2)
+    return torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1).to(x.dtype)
+
+
+def _decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
+    """q [B,1,H,D] vs cache k/v [B,L,Hkv,D]; keys beyond each sequence's position are masked."""
+    B, _, H, D = q.shape
+    Hkv, L = k.shape[2], k.shape[1]
+    qt = q.transpose(1, 2)                                   # [B,H,1,D]
+    kt, vt = k.transpose(1, 2), v.transpose(1, 2)
+    if H != Hkv:
+        kt, vt = kt.repeat_interleave(H // Hkv, 1), vt.repeat_interleave(H // Hkv, 1)
+    mask = (torch.arange(L, device=q.device)[None, :] <= positions[:, None])[:, None, None, :]
+    o = torch.nn.functional.scaled_dot_product_attention(qt, kt, vt, attn_mask=mask)
+    return o.transpose(1, 2)

@@ -1,0 +1,80 @@
+import os
+
+import torch
+
+from dist_utils import run_distributed
+
+
+def _infer(rank, world, tmp):
+    from neuronx_distributed_b200.inference.model_builder import ModelBuilder, shard_checkpoint
+    from neuronx_distributed_b200.models.llama import LlamaConfig
+    from neuronx_distributed_b200.models.llama_inference import LlamaForInference
+    from neuronx_distributed_b200.operators import argmax
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.parallel_layers.utils import gather_full_weight
+    from neuronx_distributed_b200.utils.safetensors_utils import load_state_dict_safetensors
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    cfg = LlamaConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, dtype=torch.float32, max_position_embeddings=32)
+    torch.manual_seed(0)
+    m = LlamaForInference(cfg, batch_size=2, max_seq_len=32).eval()
+    ids = torch.randint(0, 64, (2, 8), generator=torch.Generator().manual_seed(1))
+    gen = m.generate(ids, 5)
+    assert gen.shape == (2, 5)
+    # greedy generation with the KV cache == greedy re-running the full model on the growing sequence
+    seq, ref = ids.clone(), []
+    with torch.no_grad():
+        for _ in range(5):
+            _, logits = m.lm(seq)                       # [S, B, V/tp]
+            nxt = argmax(logits[-1].float(), dim=-1)
+            ref.append(nxt)
+            seq = torch.cat([seq, nxt.view(2, 1)], 1)
+    assert torch.equal(gen, torch.stack(ref, 1)), (gen, torch.stack(ref, 1))
+    # bucketed runtime: prefill + decode programs routed by input shape
+    mb = ModelBuilder(tp_degree=world, use_cuda_graphs=False)
+    mb.add("context_encoding_model", m, [(ids, torch.tensor([7, 7]))], step_fn=lambda mod, i, l: mod.context_encoding(i, l))
+    mb.add("token_generation_model", m, [(ids[:, :1], torch.tensor([8, 8]))], step_fn=lambda mod, i, p: mod.token_generation(i, p))
+    nxd = mb.trace()
+    m.kv.reset()
+    t0 = nxd(ids, torch.tensor([7, 7]))
+    t1 = nxd(t0.view(2, 1), torch.tensor([8, 8]))
+    assert torch.equal(torch.stack([t0, t1], 1), gen[:, :2])
+    if world == 2:
+        import torch.distributed as dist
+
+        sd = m.lm.state_dict()
+        params = dict(m.lm.named_parameters())
+        full = {}
+        for k, v in sd.items():
+            p = params[k]
+            if getattr(p, "tensor_model_parallel", False):
+                parts = [torch.empty_like(v) for _ in range(world)]
+                dist.all_gather(parts, v.contiguous())
+                full[k] = torch.cat(parts, 0) if getattr(p, "fused_qkv", False) else \
+                    gather_full_weight(parts, p.partition_dim, p.partition_stride)
+            else:
+                full[k] = v
+        shards = shard_checkpoint(full, m.lm, world, serialize_path=tmp if rank == 0 else None)
+        for k in sd:
+            torch.testing.assert_close(shards[rank][k], sd[k])
+        dist.barrier()
+        assert os.path.isfile(os.path.join(tmp, "tp0_sharded_checkpoint.safetensors"))
+        back = load_state_dict_safetensors(os.path.join(tmp, f"tp{rank}_sharded_checkpoint.safetensors"))
+        torch.testing.assert_close(back["lm_head.weight"], sd["lm_head.weight"])
+
+
+def test_llama_inference_kv_cache_and_buckets_tp1(tmp_path):
+    run_distributed(_infer, 1, str(tmp_path), timeout=120)
+
+
+def test_llama_inference_tp2_and_shard_checkpoint(tmp_path):
+    run_distributed(_infer, 2, str(tmp_path), timeout=120)
+
+
+def test_benchmark_report():
+    from neuronx_distributed_b200.inference.benchmark import Benchmark, generate_report
+
+    b = Benchmark(lambda: sum(range(1000)), num_runs=5)
+    rep = generate_report(b.run(), 128, 2)
+    assert set(rep) >= {"latency_ms_p50", "latency_ms_p99", "latency_ms_avg", "throughput"} and rep["throughput"] > 0
