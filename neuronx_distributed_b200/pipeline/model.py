@@ -152,6 +152,19 @@ class NxDPPModel(nn.Module):
         self.traced_model = traced
         split = part.partition_traced_model(traced, self.pipeline_cuts, self.num_stages)
         ios, final_outputs = part.analyze_pipeline_module(split)
+        # parameters/buffers touched directly by the root forward (not through a leaf module) are re-homed onto the
+        # stage that uses them so they are owned, moved and optimised with that stage
+        import operator
+
+        for s_idx, io in enumerate(ios):
+            sub = getattr(split, f"submod_{s_idx}")
+            for arg_name, target in io.attr_args.items():
+                val = operator.attrgetter(target)(split)
+                holder = "_pp_attr_" + arg_name
+                if isinstance(val, nn.Parameter):
+                    sub.register_parameter(holder, val)
+                else:
+                    sub.register_buffer(holder, val)
         self.final_output_names = final_outputs
         self._output_spec = self._capture_output_spec(split)
         self.model_input_names = [n.name for n in split.graph.nodes if n.op == "placeholder"]
@@ -456,7 +469,8 @@ class NxDPPModel(nn.Module):
                 labels = mb.get("labels")
                 named = {"hidden": self.manual_pp_loss_fn(out, labels)}
         else:
-            args = [leaves[a] if a in leaves else mb.get(a) for a in st.io.call_args]
+            args = [leaves[a] if a in leaves else
+                    (getattr(st.module, "_pp_attr_" + a) if a in st.io.attr_args else mb.get(a)) for a in st.io.call_args]
             out = st.module(*args)
             named = {n: (out if idx is None else out[idx]) for n, idx in st.io.produces}
         # forward everything the next stage needs: own products + pass-along values

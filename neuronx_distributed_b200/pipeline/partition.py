@@ -51,7 +51,10 @@ def trace_model(model: nn.Module, input_names: Optional[Sequence[str]], leaf_mod
 
     from ..parallel_layers import PARALLEL_FUNCTIONS, PARALLEL_MODULES
 
-    leaf = tuple(leaf_module_cls) + tuple(PARALLEL_MODULES)
+    from ..modules.rms_norm import RMSNorm
+    from ..parallel_layers.layer_norm import LayerNorm
+
+    leaf = tuple(leaf_module_cls) + tuple(PARALLEL_MODULES) + (RMSNorm, LayerNorm)
     sig = inspect.signature(model.forward)
     concrete = {}
     if input_names is not None:
@@ -70,6 +73,7 @@ class StageIO:
     outputs_to_next: List[str] = field(default_factory=list)        # values sent to stage+1 (ordered)
     call_args: List[str] = field(default_factory=list)              # argument names of the stage module, in order
     produces: List[Tuple[str, Optional[int]]] = field(default_factory=list)  # (name, index into the stage result or None)
+    attr_args: Dict[str, str] = field(default_factory=dict)         # call arg name → qualified attribute (get_attr) on the root
 
 
 def partition_traced_model(traced: fx.GraphModule, cut_after: Sequence[str], num_stages: int):
@@ -93,9 +97,12 @@ def analyze_pipeline_module(split: fx.GraphModule) -> Tuple[List[StageIO], List[
     stage_nodes: List[fx.Node] = []
     final_outputs: List[str] = []
     out_spec = None
+    attrs: Dict[str, str] = {}
     for node in split.graph.nodes:
         if node.op == "placeholder":
             placeholders.add(node.name)
+        elif node.op == "get_attr":
+            attrs[node.name] = node.target   # parameters used outside leaf modules stay on the root (split_module)
         elif node.op == "call_module":
             stage_nodes.append(node)
         elif node.op == "output":
@@ -120,6 +127,8 @@ def analyze_pipeline_module(split: fx.GraphModule) -> Tuple[List[StageIO], List[
                 ios[s].call_args.append(a.name)
                 if a.name in placeholders:
                     ios[s].inputs_from_model.append(a.name)
+                elif a.name in attrs:
+                    ios[s].attr_args[a.name] = attrs[a.name]
                 else:
                     consumers.setdefault(a.name, set()).add(s)
     def _names(x):
