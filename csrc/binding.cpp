@@ -195,6 +195,33 @@ static void gemm_rs_bf16(const Tensor& a, const Tensor& b, Tensor out, bool tran
                  stream());
 }
 
+// CTA-pair fused TP kernels.  mode 1: a = shard [M/world,K] → out [M,N];  mode 2: a = [M,K] → out [M/world,N]
+static void tp_gemm_2cta(int64_t mode, const Tensor& a, const Tensor& b, Tensor out, Tensor partial, bool trans_b,
+                         int64_t local_buf_ptr, const Tensor& peer_bufs, const Tensor& peer_flags, int64_t buf_offset,
+                         int64_t flag_offset, int64_t epoch, int64_t rank, int64_t world, int64_t comm_ctas,
+                         Tensor counters, int64_t gemm_done_target) {
+  CHECK_IN(a); CHECK_IN(b); CHECK_IN(out);
+  c10::cuda::CUDAGuard g(a.device());
+  const int K = (int)a.size(1);
+  const int N = (int)(trans_b ? b.size(0) : b.size(1));
+  auto* ctr = (uint32_t*)counters.data_ptr();           // [0] = gemm_done, [64..] = tile_done per 128-row block
+  if (mode == 1) {
+    const int M = (int)a.size(0) * (int)world;
+    TORCH_CHECK(out.size(0) == M && out.size(1) == N);
+    nxd::gemm_bf16_2cta_tp(1, (const void*)(local_buf_ptr + buf_offset), b.data_ptr(), out.data_ptr(), nullptr, a.data_ptr(),
+                           M, N, K, trans_b, (int)rank, (int)world, peer_bufs.data_ptr<int64_t>(),
+                           peer_flags.data_ptr<int64_t>(), buf_offset, (int)flag_offset, (uint32_t)epoch, (int)comm_ctas,
+                           ctr + 64, ctr, 0u, stream());
+  } else {
+    const int M = (int)a.size(0);
+    TORCH_CHECK(out.size(0) * world == M && out.size(1) == N && partial.size(0) == M && partial.size(1) == N);
+    nxd::gemm_bf16_2cta_tp(2, a.data_ptr(), b.data_ptr(), partial.data_ptr(), out.data_ptr(), nullptr, M, N, K, trans_b,
+                           (int)rank, (int)world, peer_bufs.data_ptr<int64_t>(), peer_flags.data_ptr<int64_t>(), buf_offset,
+                           (int)flag_offset, (uint32_t)epoch, (int)comm_ctas, ctr + 64, ctr, (uint32_t)gemm_done_target,
+                           stream());
+  }
+}
+
 // ---- symmetric memory ---------------------------------------------------------------------------
 static py::tuple symm_alloc(int64_t nbytes, int64_t nflags) {
   auto a = nxd::symm_alloc((size_t)nbytes, (size_t)nflags);
@@ -231,6 +258,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16_2cta", &gemm_bf16_2cta);
   m.def("ag_gemm_bf16", &ag_gemm_bf16);
   m.def("gemm_rs_bf16", &gemm_rs_bf16);
+  m.def("tp_gemm_2cta", &tp_gemm_2cta);
   m.def("symm_alloc", &symm_alloc);
   m.def("symm_open", &symm_open);
   m.def("symm_free", &nxd::symm_free);

@@ -234,6 +234,300 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
   if (warp == 1) { __syncwarp(); tcgen05_dealloc_2cta(tmem_base, kTmemCols); }
 }
 
+
+// =====================================================================================================
+// Tensor-parallel fused variants on the CTA-pair kernel (no NCCL call on these paths).
+//   MODE 1  all-gather → GEMM   : the first `comm_ctas` CTAs push this rank's A shard to every peer's symmetric buffer
+//                                 (coalesced 16 B × 192-thread stores over NVLink) and publish per-(source,128-row block)
+//                                 flags (st.release.sys = epoch); GEMM pairs walk the row chunks in arrival order, each
+//                                 CTA's TMA producer acquiring the flag of its own 128 rows first.
+//   MODE 2  GEMM → reduce-scatter: GEMM pairs write bf16 partial tiles to a LOCAL buffer (L2-merged stores) and bump a
+//                                 local per-row-block counter; comm CTAs wait for a row block to be complete and push it to
+//                                 the owner's staging slot as full 512 B rows (NVLink-friendly bursts, decoupled from the
+//                                 MMA epilogue), then publish the owner's flag; finally every CTA becomes a reducer that
+//                                 sums the world partials of its rank's rows in fp32.
+// =====================================================================================================
+struct TpComm {
+  int mode, rank, world;
+  const int64_t* peer_bufs;
+  const int64_t* peer_flags;
+  long buf_offset;
+  int flag_offset;
+  uint32_t epoch;
+  int comm_ctas;
+  int rows_per_rank;
+  const void* a_local;
+  void* rs_out;
+  uint32_t* tile_done;
+  uint32_t* gemm_done;
+  uint32_t gemm_done_target;
+};
+constexpr int kMaxRowBlocks = 64;
+
+NXD_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+NXD_DEVICE void red_add_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int MODE>
+NXD_DEVICE void tp_tile_coords(int tile, int tiles_n, const TpComm& c, int& m_blk, int& n_blk) {
+  const int mb_per_rank = c.rows_per_rank / TILE_M;           // 256-row blocks per rank
+  const int per_chunk = mb_per_rank * tiles_n;
+  const int step = tile / per_chunk;
+  const int in = tile - step * per_chunk;
+  const int chunk = MODE == 1 ? (c.rank - step + c.world) % c.world : (c.rank + 1 + step) % c.world;
+  m_blk = chunk * mb_per_rank + in % mb_per_rank;
+  n_blk = in / mb_per_rank;
+}
+
+// copy `bytes` (multiple of 16) with all threads of the CTA, 4 independent 16-byte transfers in flight per thread
+NXD_DEVICE void cta_copy16(uint8_t* dst, const uint8_t* src, size_t bytes) {
+  const size_t nvec = bytes / 16;
+  const uint4* s4 = (const uint4*)src;
+  uint4* d4 = (uint4*)dst;
+  size_t i = threadIdx.x;
+  for (; i + 3 * kThreads < nvec; i += 4 * kThreads) {
+    const uint4 v0 = s4[i], v1 = s4[i + kThreads], v2 = s4[i + 2 * kThreads], v3 = s4[i + 3 * kThreads];
+    d4[i] = v0; d4[i + kThreads] = v1; d4[i + 2 * kThreads] = v2; d4[i + 3 * kThreads] = v3;
+  }
+  for (; i < nvec; i += kThreads) d4[i] = s4[i];
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                         __nv_bfloat16* __restrict__ out, int M, int N, int K, TpComm comm) {
+  using OutT = __nv_bfloat16;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + kStages * kStageBytes);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kStages + 2 * kAcc);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStages);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * kStages), bar_tempty = smem_u32(bars + 2 * kStages + kAcc);
+  const uint32_t smem_base = smem_u32(smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int tiles_m = (M + TILE_M - 1) / TILE_M, tiles_n = (N + TILE_N - 1) / TILE_N;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+  const bool is_comm = (int)blockIdx.x < comm.comm_ctas;
+  const int pair = ((int)blockIdx.x - comm.comm_ctas) >> 1, num_pairs = ((int)gridDim.x - comm.comm_ctas) >> 1;
+  const int blk128_per_rank = comm.rows_per_rank / CTA_M;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tma_a);
+    prefetch_tmap(&tma_b);
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 2); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < kAcc; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 2 * 128); }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 1) { tcgen05_alloc_2cta(smem_u32(tmem_slot), kTmemCols); tcgen05_relinquish_2cta(); }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (is_comm) {
+    if constexpr (MODE == 1) {
+      // ---- all-gather pusher: (destination step, 128-row block) items; step 0 = local copy --------------------
+      const int items = comm.world * blk128_per_rank;
+      const size_t blk_bytes = (size_t)CTA_M * K * 2;
+      for (int it = blockIdx.x; it < items; it += comm.comm_ctas) {
+        const int step = it / blk128_per_rank, mb = it % blk128_per_rank;
+        const int dst = (comm.rank + step) % comm.world;
+        const uint8_t* src = (const uint8_t*)comm.a_local + (size_t)mb * blk_bytes;
+        uint8_t* d = (uint8_t*)comm.peer_bufs[dst] + comm.buf_offset +
+                     ((size_t)comm.rank * blk128_per_rank + mb) * blk_bytes;
+        cta_copy16(d, src, blk_bytes);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0)
+          st_release_sys((uint32_t*)comm.peer_flags[dst] + comm.flag_offset + comm.rank * kMaxRowBlocks + mb, comm.epoch);
+      }
+    } else {
+      // ---- reduce-scatter pusher: ship finished row blocks of remote chunks to their owners -------------------
+      const int items = (comm.world - 1) * blk128_per_rank;
+      const size_t blk_bytes = (size_t)CTA_M * N * 2;
+      for (int it = blockIdx.x; it < items; it += comm.comm_ctas) {
+        const int step = it / blk128_per_rank, mb = it % blk128_per_rank;
+        const int owner = (comm.rank + 1 + step) % comm.world;
+        const int gblk = owner * blk128_per_rank + mb;                 // global 128-row block of the partial
+        if (threadIdx.x == 0) {
+          while (ld_acquire_gpu(comm.tile_done + gblk) < (uint32_t)tiles_n) __nanosleep(128);
+          comm.tile_done[gblk] = 0;                                    // single consumer: re-arm for the next call
+        }
+        __syncthreads();
+        const uint8_t* src = (const uint8_t*)out + (size_t)gblk * blk_bytes;
+        uint8_t* d = (uint8_t*)comm.peer_bufs[owner] + comm.buf_offset +
+                     ((size_t)comm.rank * blk128_per_rank + mb) * blk_bytes;
+        cta_copy16(d, src, blk_bytes);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0)
+          st_release_sys((uint32_t*)comm.peer_flags[owner] + comm.flag_offset + comm.rank * kMaxRowBlocks + mb, comm.epoch);
+      }
+    }
+  } else if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int m_blk, n_blk;
+        tp_tile_coords<MODE>(tile, tiles_n, comm, m_blk, n_blk);
+        const int m0 = m_blk * TILE_M + (int)cta * CTA_M;
+        const int n0 = n_blk * TILE_N + (int)cta * HALF_N;
+        if constexpr (MODE == 1) {
+          const int gblk = m0 / CTA_M;
+          const uint32_t* f = (const uint32_t*)comm.peer_flags[comm.rank] + comm.flag_offset +
+                              (gblk / blk128_per_rank) * kMaxRowBlocks + (gblk % blk128_per_rank);
+          wait_flag_ge(f, comm.epoch);
+          fence_proxy_async_global();
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t full = bar_full + 8 * stage;
+          if (leader) mbar_expect_tx(full, 2 * kStageBytes);
+          else mbar_arrive_cluster(mapa_shared(full, 0));
+          const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+          const int k0 = kb * BK;
+          if constexpr (A_KMAJOR) {
+            tma_load_2d_2cta(sa, &tma_a, full, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CTA_M / 64; ++j) tma_load_2d_2cta(sa + j * 8192, &tma_a, full, m0 + j * 64, k0);
+          }
+          if constexpr (B_KMAJOR) {
+            tma_load_2d_2cta(sb, &tma_b, full, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < HALF_N / 64; ++j) tma_load_2d_2cta(sb + j * 8192, &tma_b, full, n0 + j * 64, k0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(!A_KMAJOR, !B_KMAJOR, TILE_M, TILE_N);
+      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * TILE_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t da = A_KMAJOR ? make_smem_desc(sa + k * 32, 16, 1024) : make_smem_desc(sa + k * 2048, 8192, 1024);
+            const uint64_t db = B_KMAJOR ? make_smem_desc(sb + k * 32, 16, 1024) : make_smem_desc(sb + k * 2048, 8192, 1024);
+            tcgen05_mma_f16_2cta(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tcgen05_commit_2cta(bar_empty + 8 * stage, 0b11);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit_2cta(bar_tfull + 8 * as, 0b11);
+        if (++as == kAcc) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const uint32_t tempty_leader = mapa_shared(bar_tempty, 0);
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int m_blk, n_blk;
+      tp_tile_coords<MODE>(tile, tiles_n, comm, m_blk, n_blk);
+      mbar_wait(bar_tfull + 8 * as, aphase);
+      tcgen05_fence_after();
+      const int row = m_blk * TILE_M + (int)cta * CTA_M + q * 32 + lane;
+      const int n0 = n_blk * TILE_N;
+      OutT* orow = out + (size_t)row * N;
+      const bool row_ok = row < M;
+#pragma unroll 1
+      for (int c = 0; c < TILE_N / 32; ++c) {
+        uint32_t r[32];
+        tcgen05_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * TILE_N + c * 32, r);
+        tcgen05_wait_ld();
+        const int col0 = n0 + c * 32;
+        if (row_ok && col0 < N) store_chunk<OutT>(orow, col0, N, r, 0);
+      }
+      tcgen05_fence_before();
+      mbar_arrive_cluster(tempty_leader + 8 * as);
+      if constexpr (MODE == 2) {
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) red_add_release_gpu(comm.tile_done + (m_blk * TILE_M + (int)cta * CTA_M) / CTA_M, 1u);
+      }
+      if (++as == kAcc) { as = 0; aphase ^= 1; }
+    }
+    if constexpr (MODE == 2) {
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) red_add_release_gpu(comm.gemm_done, 1u);
+    }
+  }
+
+  if constexpr (MODE == 2) {
+    // ---- reducer: (own 128-row block, 256-column slab) items, all CTAs -------------------------------------------
+    __syncthreads();
+    const int slabs = (N + 255) / 256;
+    const int items = blk128_per_rank * slabs;
+    const uint32_t* myflags = (const uint32_t*)comm.peer_flags[comm.rank] + comm.flag_offset;
+    const __nv_bfloat16* staging = (const __nv_bfloat16*)((const uint8_t*)comm.peer_bufs[comm.rank] + comm.buf_offset);
+    const __nv_bfloat16* own = out + (size_t)comm.rank * comm.rows_per_rank * N;
+    __nv_bfloat16* rout = (__nv_bfloat16*)comm.rs_out;
+    bool own_ready = false;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int mb = it / slabs, slab = it % slabs;
+      if ((int)threadIdx.x < comm.world && (int)threadIdx.x != comm.rank)
+        wait_flag_ge(myflags + threadIdx.x * kMaxRowBlocks + mb, comm.epoch);
+      if (!own_ready && threadIdx.x == 0)
+        while ((int32_t)(ld_acquire_gpu(comm.gemm_done) - comm.gemm_done_target) < 0) __nanosleep(128);
+      own_ready = true;
+      __syncthreads();
+      const int c0 = slab * 256;
+      const int cols = min(256, N - c0);
+      const int vec_per_row = cols / 8;
+      for (int idx = threadIdx.x; idx < CTA_M * vec_per_row; idx += kThreads) {
+        const int r = idx / vec_per_row, v = idx % vec_per_row;
+        const size_t off = ((size_t)(mb * CTA_M + r)) * N + c0 + v * 8;
+        float acc[8];
+        {
+          const uint4 raw = *(const uint4*)(own + off);
+          const __nv_bfloat162* h = (const __nv_bfloat162*)&raw;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); acc[2 * j] = f.x; acc[2 * j + 1] = f.y; }
+        }
+        for (int s = 0; s < comm.world; ++s) {
+          if (s == comm.rank) continue;
+          const uint4 raw = *(const uint4*)(staging + (size_t)s * comm.rows_per_rank * N + off);
+          const __nv_bfloat162* h = (const __nv_bfloat162*)&raw;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+        }
+        uint4 o; __nv_bfloat162* oh = (__nv_bfloat162*)&o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+        *(uint4*)(rout + off) = o;
+      }
+      __syncthreads();
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) { __syncwarp(); tcgen05_dealloc_2cta(tmem_base, kTmemCols); }
+}
+
 }  // namespace g2
 
 // ------------------------------------------------------------------ host side
@@ -271,6 +565,43 @@ void gemm_bf16_2cta(const void* a, const void* b, void* out, int M, int N, int K
   else if (!AK && !BK_) NXD_L2(false, false);
   else NXD_L2(false, true);
 #undef NXD_L2
+}
+
+
+template <bool AK, bool BK_, int MODE>
+static void launch_tp(const CUtensorMap& ta, const CUtensorMap& tb, void* out, int M, int N, int K, const g2::TpComm& c,
+                      int grid, cudaStream_t st) {
+  auto kern = g2::gemm_bf16_2cta_tp_kernel<AK, BK_, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    NXD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::kSmem));
+    configured = true;
+  }
+  kern<<<grid, g2::kThreads, g2::kSmem, st>>>(ta, tb, (__nv_bfloat16*)out, M, N, K, c);
+  NXD_CUDA_CHECK(cudaGetLastError());
+}
+
+// mode 1: `a` = this rank's gathered buffer [M,K] inside the symmetric payload, `a_local` = shard; out = [M,N].
+// mode 2: `a` = [M,K]; `partial` = local [M,N] scratch; `rs_out` = [M/world, N].
+void gemm_bf16_2cta_tp(int mode, const void* a, const void* b, void* out_or_partial, void* rs_out, const void* a_local,
+                       int M, int N, int K, bool trans_b, int rank, int world, const int64_t* peer_bufs,
+                       const int64_t* peer_flags, long buf_offset, int flag_offset, uint32_t epoch, int comm_ctas,
+                       uint32_t* tile_done, uint32_t* gemm_done, uint32_t gemm_done_target, cudaStream_t st) {
+  const bool BK_ = trans_b;
+  const CUtensorMap ta = make_tmap_bf16(a, M, K, g2::BK, g2::CTA_M);
+  const CUtensorMap tb = BK_ ? make_tmap_bf16(b, N, K, g2::BK, g2::HALF_N) : make_tmap_bf16(b, K, N, 64, g2::BK);
+  g2::TpComm c{};
+  c.mode = mode; c.rank = rank; c.world = world; c.peer_bufs = peer_bufs; c.peer_flags = peer_flags;
+  c.buf_offset = buf_offset; c.flag_offset = flag_offset; c.epoch = epoch; c.comm_ctas = comm_ctas;
+  c.rows_per_rank = M / world; c.a_local = a_local; c.rs_out = rs_out; c.tile_done = tile_done; c.gemm_done = gemm_done;
+  c.gemm_done_target = gemm_done_target;
+  if (M % world || c.rows_per_rank % g2::TILE_M || c.rows_per_rank / g2::CTA_M > g2::kMaxRowBlocks)
+    nxd_throw("fused TP GEMM (CTA-pair) needs rows/rank to be a multiple of 256 and <= 8192", __FILE__, __LINE__);
+  const int grid = (device_sm_count() / 2) * 2;
+  if (mode == 1) { if (BK_) launch_tp<true, true, 1>(ta, tb, out_or_partial, M, N, K, c, grid, st);
+                   else launch_tp<true, false, 1>(ta, tb, out_or_partial, M, N, K, c, grid, st); }
+  else { if (BK_) launch_tp<true, true, 2>(ta, tb, out_or_partial, M, N, K, c, grid, st);
+         else launch_tp<true, false, 2>(ta, tb, out_or_partial, M, N, K, c, grid, st); }
 }
 
 }  // namespace nxd

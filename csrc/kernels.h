@@ -51,4 +51,9 @@ bool gemm_self_check_supported();
 void gemm_bf16_2cta(const void* a, const void* b, void* out, int M, int N, int K, bool trans_a, bool trans_b, int out_dt,
                     bool accumulate, cudaStream_t st);
 
+void gemm_bf16_2cta_tp(int mode, const void* a, const void* b, void* out_or_partial, void* rs_out, const void* a_local,
+                       int M, int N, int K, bool trans_b, int rank, int world, const int64_t* peer_bufs,
+                       const int64_t* peer_flags, long buf_offset, int flag_offset, uint32_t epoch, int comm_ctas,
+                       uint32_t* tile_done, uint32_t* gemm_done, uint32_t gemm_done_target, cudaStream_t st);
+
 }  // namespace nxd

@@ -30,8 +30,13 @@ BLOCK_M = 128
 MAX_ROW_BLOCKS = 64
 _FLAGS_AG = 0
 _FLAGS_RS = 2048
+_FLAGS_RS2 = 3072
 _NFLAGS = 4096
 _COMM_SMS = int(os.environ.get("NXD_AG_COMM_SMS", "16"))
+_COMM_CTAS_AG = int(os.environ.get("NXD_TP_COMM_CTAS_AG", "16"))     # CTA-pair kernels: must be even
+_COMM_CTAS_RS = int(os.environ.get("NXD_TP_COMM_CTAS_RS", "24"))
+_USE_2CTA_TP = os.environ.get("NXD_TP_2CTA", "1") == "1"
+TILE_M2 = 256
 
 
 class TPWorkspace:
@@ -47,6 +52,11 @@ class TPWorkspace:
         self.ag_epoch = 0
         self.rs_calls = 0
         self.rs_counts = [0] * MAX_ROW_BLOCKS
+        self.rs2_calls = 0
+        self.gemm_done_total = 0
+        self.counters: Optional[torch.Tensor] = None     # [0] gemm_done, [64:] per-128-row-block tile counters
+        self.partial: Optional[torch.Tensor] = None
+        self.sm_pairs = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count // 2
 
     def _ensure(self, ag_bytes: int, rs_bytes: int) -> None:
         if self.ws is not None and ag_bytes <= self.ag_bytes and rs_bytes <= self.rs_bytes:
@@ -58,6 +68,8 @@ class TPWorkspace:
         self.rs_bytes = max(self.rs_bytes, _round(rs_bytes), _round(int(os.environ.get("NXD_SYMM_MIN_MB", "32")) << 20))
         self.ws = symm.get_workspace(self.group, "tp", 2 * self.ag_bytes + 2 * self.rs_bytes, _NFLAGS)
         self.ag_epoch, self.rs_calls, self.rs_counts = 0, 0, [0] * MAX_ROW_BLOCKS
+        self.rs2_calls, self.gemm_done_total = 0, 0
+        self.counters = torch.zeros(64 + 1024, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
 
     # ------------------------------------------------------------------ all-gather → GEMM
     def ag_gemm(self, a_shard: torch.Tensor, b: torch.Tensor, trans_b: bool, out_dtype=torch.bfloat16
@@ -71,8 +83,12 @@ class TPWorkspace:
         off = (self.ag_epoch & 1) * self.ag_bytes
         out = torch.empty(M, N, dtype=out_dtype, device=a_shard.device)
         _ext.count_launch()
-        _ext.ext().ag_gemm_bf16(a_shard, b, out, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs, off,
-                                _FLAGS_AG, self.ag_epoch, self.rank, self.world, _COMM_SMS)
+        if _USE_2CTA_TP and ms % TILE_M2 == 0 and out_dtype == torch.bfloat16 and hasattr(_ext.ext(), "tp_gemm_2cta"):
+            _ext.ext().tp_gemm_2cta(1, a_shard, b, out, out, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs,
+                                    off, _FLAGS_AG, self.ag_epoch, self.rank, self.world, _COMM_CTAS_AG, self.counters, 0)
+        else:
+            _ext.ext().ag_gemm_bf16(a_shard, b, out, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs, off,
+                                    _FLAGS_AG, self.ag_epoch, self.rank, self.world, _COMM_SMS)
         gathered = self.ws.local_tensor(off, (M, K), torch.bfloat16)
         return out, gathered
 
@@ -82,6 +98,19 @@ class TPWorkspace:
         N = b.shape[0] if trans_b else b.shape[1]
         ms = M // self.world
         self._ensure(0, M * N * 2)
+        if _USE_2CTA_TP and ms % TILE_M2 == 0 and hasattr(_ext.ext(), "tp_gemm_2cta"):
+            self.rs2_calls += 1
+            off = 2 * self.ag_bytes + (self.rs2_calls & 1) * self.rs_bytes
+            if self.partial is None or self.partial.numel() < M * N:
+                self.partial = torch.empty(M * N, dtype=torch.bfloat16, device=a.device)
+            partial = self.partial[: M * N].view(M, N)
+            self.gemm_done_total = (self.gemm_done_total + 2 * self.sm_pairs - _COMM_CTAS_RS) & 0xFFFFFFFF
+            out = torch.empty(ms, N, dtype=torch.bfloat16, device=a.device)
+            _ext.count_launch()
+            _ext.ext().tp_gemm_2cta(2, a, b, out, partial, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs, off,
+                                    _FLAGS_RS2, self.rs2_calls, self.rank, self.world, _COMM_CTAS_RS, self.counters,
+                                    self.gemm_done_total)
+            return out
         self.rs_calls += 1
         off = 2 * self.ag_bytes + (self.rs_calls & 1) * self.rs_bytes
         tiles_n = (N + 255) // 256
