@@ -24,12 +24,29 @@ from typing import Any, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-_PREFIXES = ("torch_xla", "torch_neuronx", "neuronxcc", "libneuronxla", "tenacity", "nkilib", "torchdistx")
+_PREFIXES = ("torch_xla", "torch_neuronx", "neuronxcc", "libneuronxla", "tenacity", "nkilib", "torchdistx", "nki", "neuronx_cc", "torch_neuron")
 # modules of installed packages that newer releases removed (transformers 5 dropped the fx tracer the reference imports)
 _EXACT = ("transformers.utils.fx", "boto3", "botocore", "awscrt", "s3transfer")
 
 
-class _Dummy:
+class _DummyMeta(type):
+    """Class-level attribute access also yields placeholders (``structure.Packer``, ``hlo_pb2.HloModuleProto`` …)."""
+
+    def __getattr__(cls, name):
+        if name.startswith("__") and name.endswith("__"):
+            raise AttributeError(name)
+        return _DummyMeta(name, (_Dummy,), {})
+
+    def __getitem__(cls, item):
+        return cls
+
+    def __or__(cls, other):
+        return cls
+
+    __ror__ = __or__
+
+
+class _Dummy(metaclass=_DummyMeta):
     """Callable / subscriptable / inheritable placeholder."""
 
     def __init__(self, *a, **k):
@@ -64,7 +81,7 @@ class _StubModule(types.ModuleType):
     def __getattr__(self, name):
         if name.startswith("__") and name.endswith("__"):
             raise AttributeError(name)
-        val = type(name, (_Dummy,), {})
+        val = _DummyMeta(name, (_Dummy,), {})
         setattr(self, name, val)
         return val
 
@@ -137,7 +154,11 @@ def _xm_all_gather(value, dim=0, groups=None, output=None, pin_layout=True):
     v = value.contiguous()
     parts = [torch.empty_like(v) for _ in range(n)]
     dist.all_gather(parts, v, group=pg)
-    return torch.cat(parts, dim=dim)
+    res = torch.cat(parts, dim=dim)
+    if output is not None:                      # torch_xla writes into `output` when given
+        output.copy_(res)
+        return output
+    return res
 
 
 def _xm_reduce_scatter(reduce_type, input, scale, scatter_dim, shard_count, groups=None, output=None, pin_layout=True):
@@ -151,13 +172,25 @@ def _xm_reduce_scatter(reduce_type, input, scale, scatter_dim, shard_count, grou
             o = t
         else:
             xin = t.movedim(scatter_dim, 0).contiguous() if scatter_dim != 0 else t.contiguous()
-            o = torch.empty((xin.shape[0] // n,) + tuple(xin.shape[1:]), dtype=t.dtype, device=t.device)
-            dist.reduce_scatter_tensor(o, xin, group=pg)
+            if dist.get_backend(pg) == "gloo":          # CPU plumbing check only
+                full = xin.clone()
+                dist.all_reduce(full, group=pg)
+                o = full.chunk(n, 0)[dist.get_rank(pg)].contiguous()
+            else:
+                o = torch.empty((xin.shape[0] // n,) + tuple(xin.shape[1:]), dtype=t.dtype, device=t.device)
+                dist.reduce_scatter_tensor(o, xin, group=pg)
             if scatter_dim != 0:
                 o = o.movedim(0, scatter_dim).contiguous()
         if scale != 1.0:
             o = o * scale
         outs.append(o)
+    if output is not None:                      # in-place form used by the reference's mappings
+        if single:
+            output.copy_(outs[0])
+            return output
+        for dst, src in zip(output, outs):
+            dst.copy_(src)
+        return output
     return outs[0] if single else outs
 
 
@@ -173,6 +206,8 @@ def _xm_all_to_all(value, split_dimension, concat_dimension, split_count, groups
 
 
 def _device(*a, **k):
+    if not torch.cuda.is_available():       # CPU plumbing check only
+        return torch.device("cpu")
     return torch.device("cuda", torch.cuda.current_device())
 
 
@@ -190,6 +225,7 @@ class ZeroRedundancyOptimizer(torch.optim.Optimizer):
         self.optimizer_dtype = optimizer_dtype if optimizer_dtype not in (None, torch.double) else torch.float32
         self.grad_clipping, self.max_norm = grad_clipping, (max_norm if max_norm is not None else 1.0)
         self.sharding_groups, self.grad_norm_groups = sharding_groups, grad_norm_groups
+        self._sharding_groups, self._grad_norm_groups = sharding_groups, grad_norm_groups
         self.use_grad_acc_hook, self.higher_cc_precision = use_grad_acc_hook, higher_cc_precision
         self.pg = _pg_for(sharding_groups)
         self.local_world_size = dist.get_world_size(self.pg)
@@ -211,6 +247,9 @@ class ZeroRedundancyOptimizer(torch.optim.Optimizer):
 
     def _shard(self, t):
         return self._pad(t).chunk(self.local_world_size, 0)[self.local_rank].clone()
+
+    def _shard_parameters(self):
+        return None
 
     def init_zero(self):
         base_groups = []
@@ -306,14 +345,14 @@ def _populate(module: types.ModuleType) -> None:
         module.xrt_world_size = lambda *a, **k: dist.get_world_size() if dist.is_initialized() else 1
         module.is_master_ordinal = lambda *a, **k: (not dist.is_initialized()) or dist.get_rank() == 0
         module.add_step_closure = lambda fn, args=(), **k: fn(*args)
-        module.wait_device_ops = lambda *a, **k: torch.cuda.synchronize()
-        module.get_local_ordinal = lambda *a, **k: torch.cuda.current_device()
+        module.wait_device_ops = lambda *a, **k: torch.cuda.synchronize() if torch.cuda.is_available() else None
+        module.get_local_ordinal = lambda *a, **k: int(__import__('os').environ.get('LOCAL_RANK', '0'))
         module.set_rng_state = lambda seed, *a, **k: torch.cuda.manual_seed(seed)
         module.get_rng_state = lambda *a, **k: torch.cuda.initial_seed()
     elif name == "torch_xla.runtime":
         module.world_size = lambda: dist.get_world_size() if dist.is_initialized() else 1
         module.global_ordinal = lambda: dist.get_rank() if dist.is_initialized() else 0
-        module.local_ordinal = lambda: torch.cuda.current_device()
+        module.local_ordinal = lambda: int(__import__('os').environ.get('LOCAL_RANK', '0'))
     elif name == "torch_xla.distributed.zero_redundancy_optimizer":
         module.ZeroRedundancyOptimizer = ZeroRedundancyOptimizer
     elif name == "torch_xla.utils.checkpoint":
@@ -323,10 +362,28 @@ def _populate(module: types.ModuleType) -> None:
     elif name in ("torch_neuronx.utils", "torch_neuronx.utils.utils"):
         module.get_platform_target = lambda *a, **k: "trn1"
         module.SUPPORTED_TYPES = ["trn1", "trn2", "inf2"]
+    elif name == "torch_xla.core.xla_env_vars":
+        import os as _os
+
+        module.HOST_WORLD_SIZE = "XRT_HOST_WORLD_SIZE"
+        _os.environ.setdefault("XRT_HOST_WORLD_SIZE", "1")          # single node
+        module.WORLD_SIZE, module.ORDINAL, module.LOCAL_ORDINAL = "WORLD_SIZE", "RANK", "LOCAL_RANK"
     elif name == "torch_xla":
         module._XLAC = _StubModule("torch_xla._XLAC")
     elif name == "tenacity":
         module.retry = lambda *a, **k: (lambda f: f)
+
+
+class _XlaDeviceRewrite(torch.overrides.TorchFunctionMode):
+    """`device="xla"` literals in the reference (e.g. parallel_state.py:655 collective warm-up) → the real device."""
+
+    def __torch_function__(self, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        d = kwargs.get("device", None)
+        if d is not None and (d == "xla" or (isinstance(d, torch.device) and d.type == "xla")):
+            kwargs = dict(kwargs)
+            kwargs["device"] = _device()
+        return func(*args, **kwargs)
 
 
 _INSTALLED = False
@@ -340,10 +397,32 @@ def install() -> None:
     # the reference builds its device groups with backend-specific pg_options; NCCL takes none
     _orig_new_group = dist.new_group
 
+    _MESHES = {}
+
     def new_group(ranks=None, timeout=None, backend=None, pg_options=None, **kw):
         if backend in ("xla",):
             backend = None
-        return _orig_new_group(ranks=ranks, backend=backend) if timeout is None else _orig_new_group(ranks=ranks, timeout=timeout, backend=backend)
+        pg = _orig_new_group(ranks=ranks, backend=backend) if timeout is None else _orig_new_group(ranks=ranks, timeout=timeout, backend=backend)
+        mesh = None
+        if isinstance(pg_options, dict):
+            mesh = pg_options.get("xla_pg_options", {}).get("mesh")
+        if mesh is not None and pg is not None and not isinstance(pg, int):
+            _MESHES[pg.group_name] = mesh           # torch_xla's "xla" backend exposes the replica mesh as pg._mesh
+        return pg
 
     dist.new_group = new_group
+
+    def _mesh_of(self):
+        m = _MESHES.get(self.group_name)
+        if m is None:
+            m = [dist.get_process_group_ranks(self)] if self is not dist.group.WORLD else [list(range(dist.get_world_size()))]
+        return m
+
+    dist.ProcessGroup._mesh = property(_mesh_of)
+    # `torch.classes.neuron.SPMDModel` appears in annotations evaluated at import time (reference trace/spmd.py:19)
+    try:
+        setattr(torch.classes, "neuron", _Dummy())
+    except Exception:
+        pass
+    _XlaDeviceRewrite().__enter__()
     _INSTALLED = True
