@@ -284,15 +284,21 @@ NXD_DEVICE void tp_tile_coords(int tile, int tiles_n, const TpComm& c, int& m_bl
   n_blk = in / mb_per_rank;
 }
 
-// copy `bytes` (multiple of 16) with all threads of the CTA, 4 independent 16-byte transfers in flight per thread
+// copy `bytes` (multiple of 16) with all threads of the CTA.  16 independent 16-byte loads are in flight per thread
+// (48 KB per CTA) before the first store issues: NVLink/L2 latency is ~1-2 us, so bytes-in-flight is what sets the
+// per-CTA copy bandwidth.
 NXD_DEVICE void cta_copy16(uint8_t* dst, const uint8_t* src, size_t bytes) {
+  constexpr int U = 16;
   const size_t nvec = bytes / 16;
   const uint4* s4 = (const uint4*)src;
   uint4* d4 = (uint4*)dst;
   size_t i = threadIdx.x;
-  for (; i + 3 * kThreads < nvec; i += 4 * kThreads) {
-    const uint4 v0 = s4[i], v1 = s4[i + kThreads], v2 = s4[i + 2 * kThreads], v3 = s4[i + 3 * kThreads];
-    d4[i] = v0; d4[i + kThreads] = v1; d4[i + 2 * kThreads] = v2; d4[i + 3 * kThreads] = v3;
+  for (; i + (U - 1) * kThreads < nvec; i += U * kThreads) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = s4[i + u * kThreads];
+#pragma unroll
+    for (int u = 0; u < U; ++u) d4[i + u * kThreads] = v[u];
   }
   for (; i < nvec; i += kThreads) d4[i] = s4[i];
 }
@@ -300,7 +306,8 @@ NXD_DEVICE void cta_copy16(uint8_t* dst, const uint8_t* src, size_t bytes) {
 template <bool A_KMAJOR, bool B_KMAJOR, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                         __nv_bfloat16* __restrict__ out, int M, int N, int K, TpComm comm) {
+                         const __grid_constant__ CUtensorMap tma_a_local, __nv_bfloat16* __restrict__ out, int M, int N,
+                         int K, TpComm comm) {
   using OutT = __nv_bfloat16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -323,6 +330,7 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tma_a);
     prefetch_tmap(&tma_b);
+    prefetch_tmap(&tma_a_local);
     for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 2); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < kAcc; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 2 * 128); }
     fence_barrier_init();
@@ -336,11 +344,12 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
 
   if (is_comm) {
     if constexpr (MODE == 1) {
-      // ---- all-gather pusher: (destination step, 128-row block) items; step 0 = local copy --------------------
-      const int items = comm.world * blk128_per_rank;
+      // ---- all-gather pusher: (destination step, 128-row block) items.  The local chunk is NOT copied: GEMM tiles of
+      //      the own chunk read the shard in place through `tma_a_local` and start immediately. -------------------
+      const int items = (comm.world - 1) * blk128_per_rank;
       const size_t blk_bytes = (size_t)CTA_M * K * 2;
       for (int it = blockIdx.x; it < items; it += comm.comm_ctas) {
-        const int step = it / blk128_per_rank, mb = it % blk128_per_rank;
+        const int step = it / blk128_per_rank + 1, mb = it % blk128_per_rank;
         const int dst = (comm.rank + step) % comm.world;
         const uint8_t* src = (const uint8_t*)comm.a_local + (size_t)mb * blk_bytes;
         uint8_t* d = (uint8_t*)comm.peer_bufs[dst] + comm.buf_offset +
@@ -382,12 +391,20 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         tp_tile_coords<MODE>(tile, tiles_n, comm, m_blk, n_blk);
         const int m0 = m_blk * TILE_M + (int)cta * CTA_M;
         const int n0 = n_blk * TILE_N + (int)cta * HALF_N;
+        const CUtensorMap* amap = &tma_a;
+        int a_row = m0;
         if constexpr (MODE == 1) {
           const int gblk = m0 / CTA_M;
-          const uint32_t* f = (const uint32_t*)comm.peer_flags[comm.rank] + comm.flag_offset +
-                              (gblk / blk128_per_rank) * kMaxRowBlocks + (gblk % blk128_per_rank);
-          wait_flag_ge(f, comm.epoch);
-          fence_proxy_async_global();
+          const int src_rank = gblk / blk128_per_rank;
+          if (src_rank == comm.rank) {
+            amap = &tma_a_local;                       // own shard, in place
+            a_row = m0 - src_rank * comm.rows_per_rank;
+          } else {
+            const uint32_t* f = (const uint32_t*)comm.peer_flags[comm.rank] + comm.flag_offset +
+                                src_rank * kMaxRowBlocks + (gblk % blk128_per_rank);
+            wait_flag_ge(f, comm.epoch);
+            fence_proxy_async_global();
+          }
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -397,10 +414,10 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
           const int k0 = kb * BK;
           if constexpr (A_KMAJOR) {
-            tma_load_2d_2cta(sa, &tma_a, full, k0, m0);
+            tma_load_2d_2cta(sa, amap, full, k0, a_row);
           } else {
 #pragma unroll
-            for (int j = 0; j < CTA_M / 64; ++j) tma_load_2d_2cta(sa + j * 8192, &tma_a, full, m0 + j * 64, k0);
+            for (int j = 0; j < CTA_M / 64; ++j) tma_load_2d_2cta(sa + j * 8192, amap, full, a_row + j * 64, k0);
           }
           if constexpr (B_KMAJOR) {
             tma_load_2d_2cta(sb, &tma_b, full, k0, n0);
@@ -569,15 +586,15 @@ void gemm_bf16_2cta(const void* a, const void* b, void* out, int M, int N, int K
 
 
 template <bool AK, bool BK_, int MODE>
-static void launch_tp(const CUtensorMap& ta, const CUtensorMap& tb, void* out, int M, int N, int K, const g2::TpComm& c,
-                      int grid, cudaStream_t st) {
+static void launch_tp(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, void* out, int M, int N, int K,
+                      const g2::TpComm& c, int grid, cudaStream_t st) {
   auto kern = g2::gemm_bf16_2cta_tp_kernel<AK, BK_, MODE>;
   static bool configured = false;
   if (!configured) {
     NXD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::kSmem));
     configured = true;
   }
-  kern<<<grid, g2::kThreads, g2::kSmem, st>>>(ta, tb, (__nv_bfloat16*)out, M, N, K, c);
+  kern<<<grid, g2::kThreads, g2::kSmem, st>>>(ta, tb, tal, (__nv_bfloat16*)out, M, N, K, c);
   NXD_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -598,10 +615,11 @@ void gemm_bf16_2cta_tp(int mode, const void* a, const void* b, void* out_or_part
   if (M % world || c.rows_per_rank % g2::TILE_M || c.rows_per_rank / g2::CTA_M > g2::kMaxRowBlocks)
     nxd_throw("fused TP GEMM (CTA-pair) needs rows/rank to be a multiple of 256 and <= 8192", __FILE__, __LINE__);
   const int grid = (device_sm_count() / 2) * 2;
-  if (mode == 1) { if (BK_) launch_tp<true, true, 1>(ta, tb, out_or_partial, M, N, K, c, grid, st);
-                   else launch_tp<true, false, 1>(ta, tb, out_or_partial, M, N, K, c, grid, st); }
-  else { if (BK_) launch_tp<true, true, 2>(ta, tb, out_or_partial, M, N, K, c, grid, st);
-         else launch_tp<true, false, 2>(ta, tb, out_or_partial, M, N, K, c, grid, st); }
+  const CUtensorMap tal = (mode == 1) ? make_tmap_bf16(a_local, c.rows_per_rank, K, g2::BK, g2::CTA_M) : ta;
+  if (mode == 1) { if (BK_) launch_tp<true, true, 1>(ta, tb, tal, out_or_partial, M, N, K, c, grid, st);
+                   else launch_tp<true, false, 1>(ta, tb, tal, out_or_partial, M, N, K, c, grid, st); }
+  else { if (BK_) launch_tp<true, true, 2>(ta, tb, tal, out_or_partial, M, N, K, c, grid, st);
+         else launch_tp<true, false, 2>(ta, tb, tal, out_or_partial, M, N, K, c, grid, st); }
 }
 
 }  // namespace nxd

@@ -33,8 +33,8 @@ _FLAGS_RS = 2048
 _FLAGS_RS2 = 3072
 _NFLAGS = 4096
 _COMM_SMS = int(os.environ.get("NXD_AG_COMM_SMS", "16"))
-_COMM_CTAS_AG = int(os.environ.get("NXD_TP_COMM_CTAS_AG", "16"))     # CTA-pair kernels: must be even
-_COMM_CTAS_RS = int(os.environ.get("NXD_TP_COMM_CTAS_RS", "24"))
+_COMM_CTAS_AG = int(os.environ.get("NXD_TP_COMM_CTAS_AG", "12"))     # CTA-pair kernels: must be even
+_COMM_CTAS_RS = int(os.environ.get("NXD_TP_COMM_CTAS_RS", "12"))
 _USE_2CTA_TP = os.environ.get("NXD_TP_2CTA", "1") == "1"
 TILE_M2 = 256
 
@@ -86,6 +86,10 @@ class TPWorkspace:
         if _USE_2CTA_TP and ms % TILE_M2 == 0 and out_dtype == torch.bfloat16 and hasattr(_ext.ext(), "tp_gemm_2cta"):
             _ext.ext().tp_gemm_2cta(1, a_shard, b, out, out, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs,
                                     off, _FLAGS_AG, self.ag_epoch, self.rank, self.world, _COMM_CTAS_AG, self.counters, 0)
+            # the kernel reads the own shard in place (no local copy); complete the gathered view for wgrad consumers
+            gathered = self.ws.local_tensor(off, (M, K), torch.bfloat16)
+            gathered[self.rank * ms:(self.rank + 1) * ms].copy_(a_shard)
+            return out, gathered
         else:
             _ext.ext().ag_gemm_bf16(a_shard, b, out, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs, off,
                                     _FLAGS_AG, self.ag_epoch, self.rank, self.world, _COMM_SMS)
