@@ -514,27 +514,55 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       const int c0 = slab * 256;
       const int cols = min(256, N - c0);
       const int vec_per_row = cols / 8;
-      for (int idx = threadIdx.x; idx < CTA_M * vec_per_row; idx += kThreads) {
-        const int r = idx / vec_per_row, v = idx % vec_per_row;
-        const size_t off = ((size_t)(mb * CTA_M + r)) * N + c0 + v * 8;
-        float acc[8];
-        {
-          const uint4 raw = *(const uint4*)(own + off);
+      // 4 vectors per thread per iteration and two sources at a time → 8 independent 16-byte loads in flight
+      constexpr int V = 4;
+      const int total_vec = CTA_M * vec_per_row;
+      const size_t src_stride = (size_t)comm.rows_per_rank * N;
+      for (int base = threadIdx.x; base < total_vec; base += V * kThreads) {
+        size_t off[V];
+        bool ok[V];
+        float acc[V][8];
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          const int idx = base + u * kThreads;
+          ok[u] = idx < total_vec;
+          const int r = ok[u] ? idx / vec_per_row : 0, v = ok[u] ? idx % vec_per_row : 0;
+          off[u] = ((size_t)(mb * CTA_M + r)) * N + c0 + v * 8;
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          const uint4 raw = ok[u] ? *(const uint4*)(own + off[u]) : make_uint4(0, 0, 0, 0);
           const __nv_bfloat162* h = (const __nv_bfloat162*)&raw;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); acc[2 * j] = f.x; acc[2 * j + 1] = f.y; }
+          for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); acc[u][2 * j] = f.x; acc[u][2 * j + 1] = f.y; }
         }
-        for (int s = 0; s < comm.world; ++s) {
-          if (s == comm.rank) continue;
-          const uint4 raw = *(const uint4*)(staging + (size_t)s * comm.rows_per_rank * N + off);
-          const __nv_bfloat162* h = (const __nv_bfloat162*)&raw;
+        for (int s0 = 0; s0 < comm.world; s0 += 2) {
+          uint4 raw[2][V];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+          for (int d = 0; d < 2; ++d) {
+            const int sidx = s0 + d;
+            const bool use = sidx < comm.world && sidx != comm.rank;
+#pragma unroll
+            for (int u = 0; u < V; ++u)
+              raw[d][u] = (use && ok[u]) ? *(const uint4*)(staging + (size_t)sidx * src_stride + off[u]) : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int d = 0; d < 2; ++d)
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+              const __nv_bfloat162* h = (const __nv_bfloat162*)&raw[d][u];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); acc[u][2 * j] += f.x; acc[u][2 * j + 1] += f.y; }
+            }
         }
-        uint4 o; __nv_bfloat162* oh = (__nv_bfloat162*)&o;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
-        *(uint4*)(rout + off) = o;
+        for (int u = 0; u < V; ++u) {
+          if (!ok[u]) continue;
+          uint4 o; __nv_bfloat162* oh = (__nv_bfloat162*)&o;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(acc[u][2 * j], acc[u][2 * j + 1]);
+          *(uint4*)(rout + off[u]) = o;
+        }
       }
       __syncthreads();
     }

@@ -34,7 +34,7 @@ _FLAGS_RS2 = 3072
 _NFLAGS = 4096
 _COMM_SMS = int(os.environ.get("NXD_AG_COMM_SMS", "16"))
 _COMM_CTAS_AG = int(os.environ.get("NXD_TP_COMM_CTAS_AG", "12"))     # CTA-pair kernels: must be even
-_COMM_CTAS_RS = int(os.environ.get("NXD_TP_COMM_CTAS_RS", "12"))
+_COMM_CTAS_RS = int(os.environ.get("NXD_TP_COMM_CTAS_RS", "16"))
 _USE_2CTA_TP = os.environ.get("NXD_TP_2CTA", "1") == "1"
 TILE_M2 = 256
 
