@@ -222,6 +222,24 @@ static void tp_gemm_2cta(int64_t mode, const Tensor& a, const Tensor& b, Tensor 
   }
 }
 
+// ---- ZeRO-1 collectives over peer memory
+static void zero1_reduce_scatter(const Tensor& peer_bufs, int64_t grad_off_bytes, const Tensor& peer_flags, int64_t flag_off,
+                                 int64_t epoch, int64_t rank, int64_t world, int64_t shard_numel, double scale, Tensor out,
+                                 Tensor done_ctr, bool grads_fp32) {
+  c10::cuda::CUDAGuard g(out.device());
+  nxd::zero1_reduce_scatter(peer_bufs.data_ptr<int64_t>(), grad_off_bytes, peer_flags.data_ptr<int64_t>(), (int)flag_off,
+                            (uint32_t)epoch, (int)rank, (int)world, shard_numel, (float)scale, out.data_ptr<float>(),
+                            (uint32_t*)done_ctr.data_ptr(), grads_fp32 ? nxd::kF32 : nxd::kBF16, stream());
+}
+static void zero1_all_gather(const Tensor& master, const Tensor& peer_bufs, int64_t param_off_bytes, const Tensor& peer_flags,
+                             int64_t flag_off, int64_t epoch, int64_t rank, int64_t world, int64_t shard_numel,
+                             Tensor done_ctr, bool params_bf16) {
+  c10::cuda::CUDAGuard g(master.device());
+  nxd::zero1_all_gather(master.data_ptr<float>(), peer_bufs.data_ptr<int64_t>(), param_off_bytes,
+                        peer_flags.data_ptr<int64_t>(), (int)flag_off, (uint32_t)epoch, (int)rank, (int)world, shard_numel,
+                        (uint32_t*)done_ctr.data_ptr(), params_bf16 ? nxd::kBF16 : nxd::kF32, stream());
+}
+
 // ---- symmetric memory ---------------------------------------------------------------------------
 static py::tuple symm_alloc(int64_t nbytes, int64_t nflags) {
   auto a = nxd::symm_alloc((size_t)nbytes, (size_t)nflags);
@@ -259,6 +277,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ag_gemm_bf16", &ag_gemm_bf16);
   m.def("gemm_rs_bf16", &gemm_rs_bf16);
   m.def("tp_gemm_2cta", &tp_gemm_2cta);
+  m.def("zero1_reduce_scatter", &zero1_reduce_scatter);
+  m.def("zero1_all_gather", &zero1_all_gather);
   m.def("symm_alloc", &symm_alloc);
   m.def("symm_open", &symm_open);
   m.def("symm_free", &nxd::symm_free);

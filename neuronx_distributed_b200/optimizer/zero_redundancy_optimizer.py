@@ -55,7 +55,7 @@ class _FlatGroup:
     """Flat storage for one optimizer param-group (single model dtype)."""
 
     def __init__(self, params: List[torch.nn.Parameter], group_idx: int, world: int, rank: int,
-                 grad_dtype: torch.dtype, master_dtype: torch.dtype, use_master: bool):
+                 grad_dtype: torch.dtype, master_dtype: torch.dtype, use_master: bool, arena=None):
         self.world, self.rank = world, rank
         self.slots: List[_ParamSlot] = []
         off = 0
@@ -68,8 +68,14 @@ class _FlatGroup:
         self.total = per * world
         p0 = params[0]
         self.model_dtype, self.device = p0.dtype, p0.device
-        self.param_flat = torch.zeros(self.total, dtype=self.model_dtype, device=self.device)
-        self.grad_flat = torch.zeros(self.total, dtype=grad_dtype, device=self.device)
+        self.group_idx, self.arena = group_idx, arena
+        if arena is not None:   # peer-visible buffers for the NVLink reduce-scatter / all-gather kernels
+            self.param_flat, self.param_off = arena.alloc(self.total, self.model_dtype)
+            self.grad_flat, self.grad_off = arena.alloc(self.total, grad_dtype)
+            self.rs_out = torch.zeros(per, dtype=torch.float32, device=self.device)
+        else:
+            self.param_flat = torch.zeros(self.total, dtype=self.model_dtype, device=self.device)
+            self.grad_flat = torch.zeros(self.total, dtype=grad_dtype, device=self.device)
         for s in self.slots:
             view = self.param_flat[s.offset : s.offset + s.numel].view_as(s.param)
             view.copy_(s.param.data)
@@ -147,13 +153,25 @@ class Zero1Optimizer(torch.optim.Optimizer):
     def _build(self) -> None:
         self.flat_groups: List[_FlatGroup] = []
         base_groups = []
+        arena = None
+        first = next(p for g in self.param_groups for p in g["params"])
+        if first.is_cuda and ops.zero1_comm.available(self.pg):
+            total = 0
+            for group in self.param_groups:
+                ps_ = [p for p in group["params"] if p.requires_grad]
+                n = sum((p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN for p in ps_)
+                per = ((n + self.world - 1) // self.world + _ALIGN - 1) // _ALIGN * _ALIGN
+                gbytes = 4 if (self.use_grad_acc_hook or ps_[0].dtype == torch.float32) else ps_[0].element_size()
+                total += per * self.world * (ps_[0].element_size() + gbytes) + 1024
+            arena = ops.zero1_comm.Zero1Symm(self.pg, total)
+        self.arena = arena
         for gi, group in enumerate(self.param_groups):
             params = [p for p in group["params"] if p.requires_grad]
             assert params, "empty param group"
             assert len({p.dtype for p in params}) == 1, "one dtype per param group"
             grad_dtype = torch.float32 if (self.use_grad_acc_hook or params[0].dtype == torch.float32) else params[0].dtype
             fg = _FlatGroup(params, gi, self.world, self.rank, grad_dtype, self.optimizer_dtype,
-                            self.use_master_weights and params[0].dtype != self.optimizer_dtype)
+                            self.use_master_weights and params[0].dtype != self.optimizer_dtype, arena)
             self.flat_groups.append(fg)
             shard_param = torch.nn.Parameter(fg.master_shard, requires_grad=True)
             if fg.use_master:
@@ -202,10 +220,9 @@ class Zero1Optimizer(torch.optim.Optimizer):
             if self.world == 1:
                 fg.grad_shard = fg.grad_flat[lo:hi]
                 continue
-            fused = ops.zero1_comm.reduce_scatter_scaled(fg.grad_flat, self.pg, 1.0 / self.grad_scale_divisor) \
-                if hasattr(ops, "zero1_comm") else None
-            if fused is not None:
-                fg.grad_shard = fused
+            if fg.arena is not None:
+                fg.grad_shard = fg.arena.reduce_scatter(fg.grad_off, fg.grad_flat.dtype, fg.shard_numel,
+                                                        1.0 / self.grad_scale_divisor, fg.rs_out, fg.group_idx)
                 continue
             gf = fg.grad_flat
             if self.higher_cc_precision and gf.dtype != torch.float32:
@@ -233,9 +250,8 @@ class Zero1Optimizer(torch.optim.Optimizer):
             return
         for fg in self.flat_groups:
             lo, hi = fg.shard_range
-            fused = ops.zero1_comm.all_gather_params(fg.param_flat, fg.shard_numel, self.pg) \
-                if hasattr(ops, "zero1_comm") else None
-            if fused is not None:
+            if fg.arena is not None and fg.master_shard.dtype == torch.float32:
+                fg.arena.all_gather(fg.master_shard, fg.param_off, fg.model_dtype, fg.shard_numel, fg.group_idx)
                 continue
             if dist.get_backend(self.pg) == "gloo":
                 parts = [torch.empty(fg.shard_numel, dtype=fg.model_dtype, device=fg.device) for _ in range(self.world)]

@@ -41,3 +41,47 @@ def _fused_vs_nccl(rank, world):
 def test_fused_tp_matches_nccl():
     n = min(torch.cuda.device_count(), 8)
     run_distributed(_fused_vs_nccl, 2 if n < 4 else n if n in (2, 4, 8) else 2, use_cuda=True, timeout=240)
+
+
+def _zero1_fused(rank, world):
+    """DP=2 ZeRO-1: NVLink pull reduce-scatter + push all-gather kernels vs the NCCL path."""
+    import neuronx_distributed_b200 as nxd
+    from neuronx_distributed_b200 import ops
+    from neuronx_distributed_b200.models.llama import LlamaConfig, LlamaForCausalLM
+    from neuronx_distributed_b200.ops import zero1_comm
+    from neuronx_distributed_b200.utils.adamw_fp32_optim_params import AdamW_FP32OptimParams
+
+    dev = torch.device("cuda", rank)
+    losses = {}
+    for fused in (False, True):
+        zero1_comm._ENABLED = fused
+        from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+        if ps.model_parallel_is_initialized():
+            ps.destroy_model_parallel()
+        cfg = nxd.neuronx_distributed_config(tensor_parallel_size=1, optimizer_config={"zero_one_enabled": True, "grad_clipping": True, "max_grad_norm": 1.0})
+        mcfg = LlamaConfig(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                           dtype=torch.bfloat16, device=dev, max_position_embeddings=128)
+        torch.manual_seed(0); torch.cuda.manual_seed(0)
+        model = nxd.initialize_parallel_model(cfg, lambda: LlamaForCausalLM(mcfg))
+        opt = nxd.initialize_parallel_optimizer(cfg, AdamW_FP32OptimParams, model.parameters(), lr=1e-2)
+        assert (opt.optimizer.arena is not None) == fused
+        out = []
+        for step in range(4):
+            ids = torch.randint(0, 512, (2, 128), generator=torch.Generator().manual_seed(10 * step + rank)).to(dev)
+            opt.zero_grad()
+            loss = model.run_train(input_ids=ids, labels=ids)
+            opt.step()
+            out.append(float(loss))
+        # parameters must be identical on both DP ranks after the all-gather
+        flat = opt.optimizer.flat_groups[0].param_flat.float()
+        other = flat.clone()
+        import torch.distributed as dist
+        dist.all_reduce(other)
+        assert torch.allclose(other, flat * world, rtol=0, atol=0)
+        losses[fused] = out
+    for a, b in zip(losses[True], losses[False]):
+        assert abs(a - b) < 5e-2, losses
+
+
+def test_zero1_fused_comm_matches_nccl():
+    run_distributed(_zero1_fused, 2, use_cuda=True, timeout=240)
