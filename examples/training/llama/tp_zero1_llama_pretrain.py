@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""Llama pre-training with TP (+SP) + ZeRO-1 — the B200 counterpart of the reference's
+``examples/training/llama/tp_zero1_llama_hf_pretrain/tp_zero1_llama_hf_pretrain.py`` (flags keep its names where they apply).
+
+  torchrun --nproc-per-node 8 examples/training/llama/tp_zero1_llama_pretrain.py --model 7b --tensor_parallel_size 8 \
+      --seq_len 4096 --batch_size 1 --grad_accum_usteps 8 --max_steps 100 --output_dir out --use_sequence_parallel 1
+"""
+import argparse
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "examples", "training"))
+
+import neuronx_distributed_b200 as nxd  # noqa: E402
+from neuronx_distributed_b200.models.llama import (LlamaConfig, LlamaForCausalLM, llama2_7b_config, llama2_13b_config,  # noqa: E402
+                                                   llama2_70b_config)
+from neuronx_distributed_b200.parallel_layers import parallel_state as ps  # noqa: E402
+from neuronx_distributed_b200.utils.adamw_fp32_optim_params import AdamW_FP32OptimParams  # noqa: E402
+from training_utils import (Throughput, TrainingMetrics, init_distributed, linear_warmup_cosine, memmap_batches,  # noqa: E402
+                            synthetic_batches)
+
+
+def get_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--model", default="7b", choices=["tiny", "7b", "13b", "70b"])
+    p.add_argument("--num_layers", type=int, default=-1)
+    p.add_argument("--tensor_parallel_size", type=int, default=8)
+    p.add_argument("--context_parallel_size", type=int, default=1)
+    p.add_argument("--use_sequence_parallel", type=int, default=1)
+    p.add_argument("--use_zero_1", type=int, default=1)
+    p.add_argument("--use_mix_precision", type=int, default=1)
+    p.add_argument("--selective_checkpoint_enabled", action="store_true")
+    p.add_argument("--seq_len", type=int, default=4096)
+    p.add_argument("--batch_size", type=int, default=1)
+    p.add_argument("--grad_accum_usteps", type=int, default=8)
+    p.add_argument("--max_steps", type=int, default=20)
+    p.add_argument("--warmup_steps", type=int, default=5)
+    p.add_argument("--lr", type=float, default=3e-4)
+    p.add_argument("--weight_decay", type=float, default=0.1)
+    p.add_argument("--beta1", type=float, default=0.9)
+    p.add_argument("--beta2", type=float, default=0.95)
+    p.add_argument("--data_path", default=None, help="flat uint16 token file; synthetic tokens if omitted")
+    p.add_argument("--output_dir", default="./output")
+    p.add_argument("--metrics_file", default="results.json")
+    p.add_argument("--checkpoint_freq", type=int, default=0)
+    p.add_argument("--checkpoint_dir", default=None)
+    p.add_argument("--loading_step", default="latest_if_exists")
+    p.add_argument("--num_kept_checkpoint", type=int, default=2)
+    p.add_argument("--save_load_xser", type=int, default=1)
+    p.add_argument("--async_checkpoint_saving", type=int, default=0)
+    p.add_argument("--logging_interval", type=int, default=1)
+    p.add_argument("--seed", type=int, default=1234)
+    return p.parse_args()
+
+
+def main():
+    a = get_args()
+    dev = init_distributed()
+    sp = bool(a.use_sequence_parallel) and a.tensor_parallel_size > 1
+    cfg = nxd.neuronx_distributed_config(
+        tensor_parallel_size=a.tensor_parallel_size, context_parallel_size=a.context_parallel_size, sequence_parallel=sp,
+        optimizer_config={"zero_one_enabled": bool(a.use_zero_1), "grad_clipping": True, "max_grad_norm": 1.0},
+        mixed_precision_config=None if a.use_mix_precision else {"use_master_weights": False, "use_fp32_grad_acc": False,
+                                                                 "use_master_weights_in_ckpt": False},
+        activation_checkpoint_config="full" if a.selective_checkpoint_enabled else None,
+    )
+    dtype = torch.bfloat16 if dev.type == "cuda" else torch.float32
+    kw = dict(sequence_parallel_enabled=sp, dtype=dtype, device=dev, max_position_embeddings=a.seq_len,
+              context_parallel=a.context_parallel_size > 1)
+    mcfg = {"7b": llama2_7b_config, "13b": llama2_13b_config, "70b": llama2_70b_config}.get(a.model, lambda **k: LlamaConfig(
+        vocab_size=4096, hidden_size=512, intermediate_size=1408, num_hidden_layers=4, num_attention_heads=8, **k))(**kw)
+    if a.num_layers > 0:
+        mcfg.num_hidden_layers = a.num_layers
+
+    def model_fn():
+        torch.manual_seed(a.seed)
+        if dev.type == "cuda":
+            torch.cuda.manual_seed(a.seed)
+        return LlamaForCausalLM(mcfg)
+
+    model = nxd.initialize_parallel_model(cfg, model_fn)
+    opt = nxd.initialize_parallel_optimizer(cfg, AdamW_FP32OptimParams, model.parameters(), lr=a.lr, betas=(a.beta1, a.beta2),
+                                            weight_decay=a.weight_decay)
+    sched = linear_warmup_cosine(opt.optimizer if hasattr(opt, "optimizer") else opt, a.warmup_steps, a.max_steps)
+    dp, dpr = ps.get_data_parallel_size(), ps.get_data_parallel_rank()
+    data = (memmap_batches(a.data_path, a.batch_size, a.seq_len, dpr, dp, dev) if a.data_path
+            else synthetic_batches(mcfg.vocab_size, a.batch_size, a.seq_len, a.seed + dpr, dev))
+    step = 0
+    ckpt_dir = a.checkpoint_dir or os.path.join(a.output_dir, "checkpoints")
+    if a.loading_step == "latest_if_exists" and a.checkpoint_freq > 0 and nxd.has_checkpoint(ckpt_dir):
+        uc = nxd.load_checkpoint(ckpt_dir, tag=None, model=model, optimizer=opt, scheduler=sched)
+        step = (uc or {}).get("total_steps", 0)
+    os.makedirs(a.output_dir, exist_ok=True)
+    metrics = TrainingMetrics(os.path.join(a.output_dir, a.metrics_file))
+    metrics.store_parameters(vars(a))
+    thr = Throughput(a.batch_size, dp, a.grad_accum_usteps, logging_interval=a.logging_interval)
+    tps = []
+    while step < a.max_steps:
+        opt.zero_grad()
+        total = 0.0
+        for _ in range(a.grad_accum_usteps):
+            batch = next(data)
+            if a.context_parallel_size > 1:
+                from neuronx_distributed_b200.utils.batch_utils import get_batch_on_this_context_parallel_rank
+
+                batch = get_batch_on_this_context_parallel_rank(batch)
+            loss = model.run_train(**batch)
+            total = total + loss.detach() / a.grad_accum_usteps
+        opt.step()
+        sched.step()
+        step += 1
+        if step % a.logging_interval == 0:
+            if dp > 1:
+                dist.all_reduce(total, group=ps.get_data_parallel_group())
+                total = total / dp
+            tp = thr.get_throughput()
+            tps.append(tp)
+            if dist.get_rank() == 0:
+                gn = float(opt.grad_norm) if opt.grad_norm is not None else float("nan")
+                print(f"step {step} loss {float(total):.4f} grad_norm {gn:.3f} lr {sched.get_last_lr()[0]:.2e} "
+                      f"throughput {tp:.2f} seq/s ({tp * a.seq_len:.0f} tok/s)", flush=True)
+        if a.checkpoint_freq > 0 and step % a.checkpoint_freq == 0:
+            nxd.save_checkpoint(ckpt_dir, f"step_{step}", model=model, optimizer=opt, scheduler=sched,
+                                user_content={"total_steps": step}, use_xser=bool(a.save_load_xser),
+                                num_kept_ckpts=a.num_kept_checkpoint, async_save=bool(a.async_checkpoint_saving))
+    nxd.finalize_checkpoint()
+    steady = tps[min(10, len(tps) // 2):] or tps
+    metrics.store_metrics({"final_loss": float(total), "average_throughput_seq_s": sum(steady) / max(1, len(steady)),
+                           "peak_throughput_seq_s": thr.peak, "steps": step})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

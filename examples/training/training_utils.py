@@ -1,0 +1,105 @@
+"""Shared helpers for the training examples (role of reference ``examples/training/llama/training_utils.py:268-376``):
+moving-average throughput, a JSON metrics file, synthetic / memory-mapped token datasets, distributed bring-up."""
+from __future__ import annotations
+
+import json
+import os
+import time
+from typing import Dict, Iterator, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def init_distributed():
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    if torch.cuda.is_available() and os.environ.get("NXD_CPU_MODE", "0") != "1":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        return torch.device("cuda", local)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    return torch.device("cpu")
+
+
+class Throughput:
+    """seq/s = window·(batch·dp·grad_accum·log_interval)/window_time, moving average over ``moving_avg_window`` steps."""
+
+    def __init__(self, batch_size: int, world_size_dp: int, grad_accum_usteps: int, moving_avg_window_size: int = 10,
+                 logging_interval: int = 1):
+        self.seqs_per_iteration = batch_size * world_size_dp * grad_accum_usteps * logging_interval
+        self.moving_avg_window_size = moving_avg_window_size
+        self.window = []
+        self.window_time = 0.0
+        self.start = time.time()
+        self.peak = 0.0
+
+    def get_throughput(self) -> float:
+        now = time.time()
+        dt, self.start = now - self.start, now
+        self.window.append(dt)
+        self.window_time += dt
+        if len(self.window) > self.moving_avg_window_size:
+            self.window_time -= self.window.pop(0)
+        tp = len(self.window) * self.seqs_per_iteration / max(self.window_time, 1e-9)
+        self.peak = max(self.peak, tp)
+        return tp
+
+
+class TrainingMetrics:
+    def __init__(self, path: str):
+        self.path = path
+        self.data: Dict[str, Dict] = {}
+
+    def store_parameters(self, params: Dict) -> None:
+        self.data.setdefault("parameters", {}).update(params)
+        self._flush()
+
+    def store_metrics(self, metrics: Dict) -> None:
+        self.data.setdefault("metrics", {}).update(metrics)
+        self._flush()
+
+    def _flush(self) -> None:
+        if (dist.get_rank() if dist.is_initialized() else 0) == 0:
+            with open(self.path, "w") as f:
+                json.dump(self.data, f, indent=1, default=str)
+
+
+def synthetic_batches(vocab: int, batch: int, seq: int, seed: int, device) -> Iterator[Dict[str, torch.Tensor]]:
+    g = torch.Generator().manual_seed(seed)
+    pin = torch.cuda.is_available()
+    while True:
+        ids = torch.randint(0, vocab, (batch, seq), generator=g)
+        if pin:
+            ids = ids.pin_memory()
+        ids = ids.to(device, non_blocking=True)
+        yield {"input_ids": ids, "labels": ids}
+
+
+def memmap_batches(path: str, batch: int, seq: int, dp_rank: int, dp_size: int, device, dtype=np.uint16) -> Iterator[Dict[str, torch.Tensor]]:
+    """Flat token file → [batch, seq] windows, strided over data-parallel ranks."""
+    data = np.memmap(path, dtype=dtype, mode="r")
+    n = (len(data) - 1) // seq
+    i = dp_rank
+    while True:
+        rows = []
+        for _ in range(batch):
+            rows.append(torch.from_numpy(data[(i % n) * seq:(i % n) * seq + seq].astype(np.int64)))
+            i += dp_size
+        ids = torch.stack(rows).to(device, non_blocking=True)
+        yield {"input_ids": ids, "labels": ids}
+
+
+def linear_warmup_cosine(optimizer, warmup: int, total: int, min_ratio: float = 0.1):
+    import math
+
+    def f(step):
+        if step < warmup:
+            return (step + 1) / max(1, warmup)
+        p = min(1.0, (step - warmup) / max(1, total - warmup))
+        return min_ratio + (1 - min_ratio) * 0.5 * (1 + math.cos(math.pi * p))
+
+    return torch.optim.lr_scheduler.LambdaLR(optimizer, f)
