@@ -122,13 +122,34 @@ static void multi_tensor_scale(const std::vector<Tensor>& ts, const Tensor& scal
 }
 static void fused_adamw(const std::vector<Tensor>& p, const std::vector<Tensor>& g, const std::vector<Tensor>& m,
                         const std::vector<Tensor>& v, const std::vector<Tensor>& lowp, double lr, double b1, double b2,
-                        double eps, double wd, double bc1, double bc2, const Tensor& grad_scale) {
+                        double eps, double wd, double bc1, double bc2, const Tensor& grad_scale, bool hf_form) {
   if (p.empty()) return;
   TORCH_CHECK(p[0].scalar_type() == at::kFloat && m[0].scalar_type() == at::kFloat);
   c10::cuda::CUDAGuard guard(p[0].device());
   nxd::fused_adamw(refs(p), refs(g), refs(m), refs(v), refs(lowp), dt_code(g[0]), lowp.empty() ? 0 : dt_code(lowp[0]),
                    (float)lr, (float)b1, (float)b2, (float)eps, (float)wd, (float)bc1, (float)bc2,
-                   grad_scale.data_ptr<float>(), stream());
+                   grad_scale.data_ptr<float>(), hf_form ? 1 : 0, stream());
+}
+
+// ---- attention ----------------------------------------------------------------------------------
+static void check_qkv(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.dim() == 4 && t.size(3) == 128 && t.stride(3) == 1,
+              name, ": expected a bf16 CUDA [B,S,H,128] view with contiguous head_dim");
+}
+// returns (out [B,S,H,D] view — memory laid out [S,B,H,D] when sbhd_out —, lse [B,H,S] fp32)
+static std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, bool causal, double scale,
+                                          bool sbhd_out) {
+  check_qkv(q, "q"); check_qkv(k, "k"); check_qkv(v, "v");
+  const int B = q.size(0), S = q.size(1), H = q.size(2), Skv = k.size(1), Hkv = k.size(2);
+  TORCH_CHECK(k.size(0) == B && v.size(0) == B && v.size(1) == Skv && v.size(2) == Hkv && H % Hkv == 0);
+  c10::cuda::CUDAGuard guard(q.device());
+  Tensor out = sbhd_out ? at::empty({S, B, H, 128}, q.options()).transpose(0, 1) : at::empty({B, S, H, 128}, q.options());
+  Tensor lse = at::empty({B, H, S}, q.options().dtype(at::kFloat));
+  const long qs[3] = {q.stride(0), q.stride(1), q.stride(2)}, ks[3] = {k.stride(0), k.stride(1), k.stride(2)};
+  const long vs[3] = {v.stride(0), v.stride(1), v.stride(2)}, os[3] = {out.stride(0), out.stride(1), out.stride(2)};
+  nxd::flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), B, S, Skv, H, Hkv,
+                      qs, ks, vs, os, (float)scale, causal, stream());
+  return {out, lse};
 }
 
 // ---- GEMM ---------------------------------------------------------------------------------------
@@ -274,6 +295,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("fused_adamw", &fused_adamw);
   m.def("gemm_bf16", &gemm_bf16);
   m.def("gemm_bf16_2cta", &gemm_bf16_2cta);
+  m.def("flash_attn_fwd", &flash_attn_fwd);
   m.def("ag_gemm_bf16", &ag_gemm_bf16);
   m.def("gemm_rs_bf16", &gemm_rs_bf16);
   m.def("tp_gemm_2cta", &tp_gemm_2cta);

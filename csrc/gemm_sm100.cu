@@ -415,6 +415,20 @@ static int sm_count() {
 CUtensorMap make_tmap_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
   return make_tmap(ptr, rows, cols, box_cols, box_rows);
 }
+// same, rows `row_stride_elems` apart (strided views: fused-QKV slices, [S,B,H,D] activations)
+CUtensorMap make_tmap_bf16_strided(const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                                   uint32_t box_cols, uint32_t box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) nxd_throw("cuTensorMapEncodeTiled (strided) failed: " + std::to_string((int)r), __FILE__, __LINE__);
+  return m;
+}
 int device_sm_count() { return sm_count(); }
 
 template <bool AK, bool BK, int MODE, typename OutT>

@@ -30,7 +30,7 @@ void multi_tensor_scale(const std::vector<TensorRef>& ts, int dt, const float* s
 void fused_adamw(const std::vector<TensorRef>& p, const std::vector<TensorRef>& g, const std::vector<TensorRef>& m,
                  const std::vector<TensorRef>& v, const std::vector<TensorRef>& lowp, int gdt, int ldt, float lr,
                  float beta1, float beta2, float eps, float wd, float bc1, float bc2, const float* grad_scale,
-                 cudaStream_t st);
+                 int hf_form, cudaStream_t st);
 
 // ---- gemm_sm100.cu
 struct GemmComm {          // in-kernel NVLink communication description (all zero → plain GEMM)
@@ -63,5 +63,10 @@ void zero1_reduce_scatter(const int64_t* peer_bufs, long grad_off_bytes, const i
 void zero1_all_gather(const float* master, const int64_t* peer_bufs, long param_off_bytes, const int64_t* peer_flags,
                       int flag_off, uint32_t epoch, int rank, int world, long shard_numel, uint32_t* done_ctr, int param_dt,
                       cudaStream_t st);
+
+// ---- attention (attention_sm100.cu): q [B,S_q,H,128], k/v [B,S_kv,Hkv,128] bf16 views; strides = (b, s, h) in elements
+void flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int S_q, int S_kv, int H,
+                    int Hkv, const long* qs, const long* ks, const long* vs, const long* os, float scale, bool causal,
+                    cudaStream_t st);
 
 }  // namespace nxd

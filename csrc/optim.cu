@@ -67,9 +67,14 @@ __global__ void __launch_bounds__(256) scale_kernel(ChunkTable<1> tab, const flo
 }
 
 template <typename G, typename L, bool HAS_LOW>
-__global__ void __launch_bounds__(256) adamw_kernel(ChunkTable<5> tab, float lr, float beta1, float beta2, float eps,
-                                                    float wd, float inv_bc1, float inv_bc2,
+__global__ void __launch_bounds__(256) adamw_kernel(ChunkTable<5> tab, float step_size, float beta1, float beta2,
+                                                    float eps, float decay_pre, float decay_post, float vscale,
                                                     const float* __restrict__ grad_scale) {
+  // One update rule covers both AdamW forms:
+  //   p = (p * decay_pre - step_size * m / (sqrt(v * vscale) + eps)) * decay_post
+  // torch form : step_size = lr/bc1, vscale = 1/bc2, decay_pre = 1 - lr*wd, decay_post = 1
+  // HF form    : step_size = lr*sqrt(bc2)/bc1, vscale = 1, decay_pre = 1, decay_post = 1 - lr*wd
+  //              (reference utils/adamw_fp32_optim_params.py:130-155: eps added before bias correction, decay applied last)
   const int t = tab.block_tensor[blockIdx.x];
   const long base = (long)tab.block_chunk[blockIdx.x] * kChunk;
   const long n = min(tab.numel[t] - base, kChunk);
@@ -79,7 +84,6 @@ __global__ void __launch_bounds__(256) adamw_kernel(ChunkTable<5> tab, float lr,
   float* v = (float*)tab.ptr[3][t] + base;
   L* low = HAS_LOW ? (L*)tab.ptr[4][t] + base : nullptr;
   const float gs = grad_scale ? *grad_scale : 1.f;
-  const float decay = 1.f - lr * wd;
   // 4 elements / thread / iteration: fp32 state moves as 16-byte packets
   const bool aligned = ((uintptr_t)p % 16 == 0) && ((uintptr_t)m % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
                        ((uintptr_t)g % (4 * sizeof(G)) == 0) && (!HAS_LOW || (uintptr_t)low % (4 * sizeof(L)) == 0);
@@ -106,8 +110,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(ChunkTable<5> tab, float lr,
         const float gr = gg[j] * gs;
         ma[j] = beta1 * ma[j] + (1.f - beta1) * gr;
         va[j] = beta2 * va[j] + (1.f - beta2) * gr * gr;
-        const float denom = sqrtf(va[j] * inv_bc2) + eps;
-        pa[j] = pa[j] * decay - lr * (ma[j] * inv_bc1) / denom;
+        const float denom = sqrtf(va[j] * vscale) + eps;
+        pa[j] = (pa[j] * decay_pre - step_size * ma[j] / denom) * decay_post;
       }
       *reinterpret_cast<float4*>(p + q * 4) = pp;
       *reinterpret_cast<float4*>(m + q * 4) = mm;
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(ChunkTable<5> tab, float lr,
     const float gr = to_f32<G>(g[i]) * gs;
     const float mi = beta1 * m[i] + (1.f - beta1) * gr;
     const float vi = beta2 * v[i] + (1.f - beta2) * gr * gr;
-    const float pi = p[i] * decay - lr * (mi * inv_bc1) / (sqrtf(vi * inv_bc2) + eps);
+    const float pi = (p[i] * decay_pre - step_size * mi / (sqrtf(vi * vscale) + eps)) * decay_post;
     m[i] = mi; v[i] = vi; p[i] = pi;
     if constexpr (HAS_LOW) low[i] = from_f32<L>(pi);
   }
@@ -197,12 +201,15 @@ void multi_tensor_scale(const std::vector<TensorRef>& ts, int dt, const float* s
 void fused_adamw(const std::vector<TensorRef>& p, const std::vector<TensorRef>& g, const std::vector<TensorRef>& m,
                  const std::vector<TensorRef>& v, const std::vector<TensorRef>& lowp, int gdt, int ldt, float lr,
                  float beta1, float beta2, float eps, float wd, float bc1, float bc2, const float* grad_scale,
-                 cudaStream_t st) {
+                 int hf_form, cudaStream_t st) {
   const std::vector<TensorRef> lists[5] = {p, g, m, v, lowp};
   const bool has_low = !lowp.empty();
-  const float ib1 = 1.f / bc1, ib2 = 1.f / bc2;
+  const float step_size = hf_form ? lr * sqrtf(bc2) / bc1 : lr / bc1;
+  const float vscale = hf_form ? 1.f : 1.f / bc2;
+  const float decay_pre = hf_form ? 1.f : 1.f - lr * wd;
+  const float decay_post = hf_form ? 1.f - lr * wd : 1.f;
   run_tables<5>(lists, [&](const ChunkTable<5>& tab, int nb) {
-#define LAUNCH(G, L, HL) adamw_kernel<G, L, HL><<<nb, 256, 0, st>>>(tab, lr, beta1, beta2, eps, wd, ib1, ib2, grad_scale)
+#define LAUNCH(G, L, HL) adamw_kernel<G, L, HL><<<nb, 256, 0, st>>>(tab, step_size, beta1, beta2, eps, decay_pre, decay_post, vscale, grad_scale)
     if (gdt == kF32) {
       if (!has_low) LAUNCH(float, float, false);
       else if (ldt == kBF16) LAUNCH(float, __nv_bfloat16, true);

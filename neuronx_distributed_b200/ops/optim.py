@@ -69,14 +69,20 @@ def fused_adamw_(
     step: int,
     grad_scale: Optional[torch.Tensor] = None,   # device scalar multiplied into grads (clip coeff)
     model_params: Optional[List[torch.Tensor]] = None,  # optional low-precision copies to refresh
+    hf_form: bool = True,
+    correct_bias: bool = True,
 ) -> None:
     """One launch: AdamW update on fp32 state for all tensors; optionally also writes the bf16
     model copy (``model_params``) — semantic match for reference
-    ``utils/adamw_fp32_optim_params.py:91-155`` (decoupled weight decay, bias correction)."""
+    ``utils/adamw_fp32_optim_params.py:91-155``.
+
+    ``hf_form=True`` (default) reproduces that file's update bit-for-bit in structure: ``denom = sqrt(v) + eps``,
+    ``step = lr·sqrt(bc2)/bc1`` and the decoupled decay applied *after* the Adam step; ``hf_form=False`` is
+    ``torch.optim.AdamW`` (decay first, eps after bias correction)."""
     if not params:
         return
-    bc1 = 1.0 - beta1 ** step
-    bc2 = 1.0 - beta2 ** step
+    bc1 = 1.0 - beta1 ** step if correct_bias else 1.0
+    bc2 = 1.0 - beta2 ** step if correct_bias else 1.0
     if _all_cuda(params) and _ext.use_cuda(*params):
         dev = params[0].device
         gs = grad_scale if grad_scale is not None else torch.ones((), dtype=torch.float32, device=dev)
@@ -92,17 +98,21 @@ def fused_adamw_(
                 [params[i] for i in idxs], [grads[i] for i in idxs], [exp_avgs[i] for i in idxs],
                 [exp_avg_sqs[i] for i in idxs],
                 [model_params[i] for i in idxs] if model_params is not None else [],
-                float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), float(bc1), float(bc2), gs,
+                float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), float(bc1), float(bc2), gs, bool(hf_form),
             )
         return
     for i, (p, g, m, v) in enumerate(zip(params, grads, exp_avgs, exp_avg_sqs)):
         g32 = g.float()
         if grad_scale is not None:
             g32 = g32 * grad_scale.to(g32.device)
-        p.mul_(1.0 - lr * weight_decay)
         m.mul_(beta1).add_(g32, alpha=1.0 - beta1)
         v.mul_(beta2).addcmul_(g32, g32, value=1.0 - beta2)
-        denom = (v / bc2).sqrt_().add_(eps)
-        p.addcdiv_(m / bc1, denom, value=-lr)
+        if hf_form:
+            p.addcdiv_(m, v.sqrt().add_(eps), value=-lr * (bc2 ** 0.5) / bc1)
+            if weight_decay > 0.0:
+                p.mul_(1.0 - lr * weight_decay)
+        else:
+            p.mul_(1.0 - lr * weight_decay)
+            p.addcdiv_(m / bc1, (v / bc2).sqrt_().add_(eps), value=-lr)
         if model_params is not None:
             model_params[i].copy_(p)

@@ -61,7 +61,8 @@ class AdamW_FP32OptimParams(Optimizer):
                 ops.optim.fused_adamw_(
                     [ps_[i] for i in idx], [gs[i] for i in idx], [ms[i] for i in idx], [vs[i] for i in idx],
                     group["lr"], b1, b2, group["eps"], group["weight_decay"],
-                    step if group["correct_bias"] else 10**9, self.grad_scale,
+                    step, self.grad_scale,
                     [lowp[i] for i in idx] if want_low else None,
+                    hf_form=True, correct_bias=group["correct_bias"],
                 )
         return loss

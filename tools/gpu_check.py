@@ -118,11 +118,23 @@ def check_elementwise():
     p = torch.randn(n, device=dev); g = torch.randn(n, device=dev, dtype=torch.bfloat16)
     m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev); low = torch.zeros(n, device=dev, dtype=torch.bfloat16)
     pr, mr, vr = p.clone(), m.clone(), v.clone()
-    ops.optim.fused_adamw_([p], [g], [m], [v], 1e-2, 0.9, 0.95, 1e-8, 0.1, 1, torch.tensor(0.7, device=dev), [low])
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    ops.optim.fused_adamw_([p], [g], [m], [v], 1e-2, 0.9, 0.95, 1e-8, 0.1, 1, torch.tensor(0.7, device=dev), [low],
+                           hf_form=False)
     g32 = g.float() * 0.7
     pr.mul_(1 - 1e-2 * 0.1); mr.mul_(0.9).add_(g32, alpha=0.1); vr.mul_(0.95).addcmul_(g32, g32, value=0.05)
     pr.addcdiv_(mr / (1 - 0.9), (vr / (1 - 0.95)).sqrt() + 1e-8, value=-1e-2)
     report("fused_adamw", relerr(p, pr) < 1e-5 and relerr(low, pr) < 1e-2, perr=relerr(p, pr), lowerr=relerr(low, pr))
+    # HF form (the reference optimizer's update): eps before bias correction, decay last; 3 steps
+    ph = p2.clone()
+    for step in (1, 2, 3):
+        ops.optim.fused_adamw_([p2], [g], [m2], [v2], 1e-2, 0.9, 0.95, 1e-3, 0.1, step, None, None, hf_form=True)
+    mh = torch.zeros_like(ph); vh = torch.zeros_like(ph); gf = g.float()
+    for step in (1, 2, 3):
+        mh.mul_(0.9).add_(gf, alpha=0.1); vh.mul_(0.95).addcmul_(gf, gf, value=0.05)
+        ph.addcdiv_(mh, vh.sqrt() + 1e-3, value=-1e-2 * (1 - 0.95 ** step) ** 0.5 / (1 - 0.9 ** step))
+        ph.add_(ph, alpha=-1e-2 * 0.1)
+    report("fused_adamw_hf", relerr(p2, ph) < 1e-5, perr=relerr(p2, ph))
 
 
 def check_gemm(perf=False):
