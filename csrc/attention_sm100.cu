@@ -273,12 +273,355 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
   if (warp == 1) tcgen05_dealloc(tmem_base, 256);
 }
 
+
+// ====================================================================================================================
+// Backward.  One CTA per (128-row KV tile, kv head, batch); it keeps K/V resident in smem and dK/dV resident in TMEM and
+// walks the 64-row query tiles (× the GQA group) that can see this KV tile.  Everything is computed transposed so that the
+// softmax threads own a *kv* row and P/dS land directly in the operand layouts the next GEMMs need:
+//   Sᵀ  = K·Qᵀ        (A = K  K-major, B = Q  K-major)            → TMEM [128 kv × 64 q]
+//   dPᵀ = V·dOᵀ       (A = V  K-major, B = dO K-major)            → TMEM [128 kv × 64 q]
+//   Pᵀ = exp2(Sᵀ·c − lse₂[q]) ;  dSᵀ = Pᵀ ∘ (dPᵀ·scale − δ[q]·scale)   (thread = kv row; lse₂/δ broadcast from smem)
+//   dV += Pᵀ·dO       (A = Pᵀ from TMEM (in place over Sᵀ), B = dO MN-major)
+//   dK += dSᵀ·Q       (A = dSᵀ smem K-major,               B = Q  MN-major)
+//   dQᵀ = Kᵀ·dSᵀ      (A = K MN-major, B = dSᵀ MN-major)          → TMEM [128 d × 64 q], drained by a second warpgroup
+//                      into smem and added to the fp32 dQ accumulator with one bulk async reduce (no per-element atomics).
+// warp 0 TMA, warp 1 MMA issue, warps 2-5 softmax/dS (+ dK/dV epilogue), warps 6-9 dQ drain.
+constexpr int BQ = 64;
+constexpr int kThreadsBwd = 320;
+constexpr int kQStages = 3;
+constexpr uint32_t kQTile = BQ * HD * 2;                        // 16 KB
+constexpr uint32_t kOffK = 0, kOffV = kTile, kOffQ = 2 * kTile, kOffdO = kOffQ + kQStages * kQTile,
+                   kOffdS = kOffdO + kQStages * kQTile, kOffdQ = kOffdS + 2 * kQTile, kOffStats = kOffdQ + 16384,
+                   kOffBars = kOffStats + kQStages * 512;
+constexpr uint32_t kSmemBwd = kOffBars + 256 + 1024;
+
+struct BwdParams {
+  int S_q, S_kv, H, Hkv, B, S_pad;
+  Coord q, k, v, g;
+  long dk_sb, dk_ss, dk_sh, dv_sb, dv_ss, dv_sh;
+  float scale, scale_log2;
+  int causal;
+  const float* stats;          // [2][B*H*S_pad (+pad)] : lse·log2e , δ·scale
+  long stats_stride;
+  float* dq_acc;               // [B, H, S_pad, 128] fp32
+};
+
+NXD_DEVICE void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+NXD_DEVICE void bulk_reduce_add_f32(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+               ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+NXD_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+NXD_DEVICE void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+NXD_DEVICE void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+NXD_DEVICE void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+NXD_DEVICE void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__global__ void __launch_bounds__(kThreadsBwd, 1)
+fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+              const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tg,
+              __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = base + kOffK, sV = base + kOffV, sQ = base + kOffQ, sdO = base + kOffdO, sdS = base + kOffdS,
+                 sdQ = base + kOffdQ, sStats = base + kOffStats, bars = base + kOffBars;
+  // barriers: kv | qf[3] | qe[3] | s[2] | p[2] | dq[2] | dqr[2] | acc | tmem slot
+  const uint32_t bar_kv = bars, bar_qf = bars + 8, bar_qe = bars + 32, bar_s = bars + 56, bar_p = bars + 72,
+                 bar_dq = bars + 88, bar_dqr = bars + 104, bar_acc = bars + 120, tmem_slot = bars + 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int group = p.H / p.Hkv;
+  const int nq = (p.S_q + BQ - 1) / BQ;
+  const int t0 = p.causal ? (n * BN) / BQ : 0;
+  const int per_head = nq - t0;
+  const int n_iter = per_head * group;
+  const int kv0 = n * BN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_kv, 1);
+    for (int i = 0; i < kQStages; ++i) { mbar_init(bar_qf + 8 * i, 1); mbar_init(bar_qe + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_s + 8 * i, 1); mbar_init(bar_p + 8 * i, 128); mbar_init(bar_dq + 8 * i, 1); mbar_init(bar_dqr + 8 * i, 128);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tcgen05_alloc(tmem_slot, 512);
+    tcgen05_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tmem_dK = tmem_base, tmem_dV = tmem_base + 128, tmem_ST = tmem_base + 256, tmem_dP = tmem_base + 384;
+
+  if (warp == 0) {
+    if (lane == 0 && n_iter > 0) {
+      prefetch_tmap(&tq); prefetch_tmap(&tk); prefetch_tmap(&tv); prefetch_tmap(&tg);
+      const int kc = b * p.k.col_b + kvh * p.k.col_h, kr = b * p.k.row_b + kvh * p.k.row_h + kv0;
+      const int vc = b * p.v.col_b + kvh * p.v.col_h, vr = b * p.v.row_b + kvh * p.v.row_h + kv0;
+      mbar_expect_tx(bar_kv, 2 * kTile);
+      tma_load_2d(sK, &tk, bar_kv, kc, kr);
+      tma_load_2d(sK + kHalf, &tk, bar_kv, kc + 64, kr);
+      tma_load_2d(sV, &tv, bar_kv, vc, vr);
+      tma_load_2d(sV + kHalf, &tv, bar_kv, vc + 64, vr);
+      for (int it = 0; it < n_iter; ++it) {
+        const int qs = it % kQStages;
+        const uint32_t ph = (uint32_t)((it / kQStages) & 1);
+        const int head = kvh * group + it / per_head, t = t0 + it % per_head;
+        mbar_wait(bar_qe + 8 * qs, ph ^ 1);
+        const uint32_t full = bar_qf + 8 * qs;
+        mbar_expect_tx(full, 2 * kQTile + 512);
+        const int qc = b * p.q.col_b + head * p.q.col_h, qr = b * p.q.row_b + head * p.q.row_h + t * BQ;
+        const int gc = b * p.g.col_b + head * p.g.col_h, gr = b * p.g.row_b + head * p.g.row_h + t * BQ;
+        tma_load_2d(sQ + qs * kQTile, &tq, full, qc, qr);
+        tma_load_2d(sQ + qs * kQTile + kQTile / 2, &tq, full, qc + 64, qr);
+        tma_load_2d(sdO + qs * kQTile, &tg, full, gc, gr);
+        tma_load_2d(sdO + qs * kQTile + kQTile / 2, &tg, full, gc + 64, gr);
+        const float* st = p.stats + ((long)b * p.H + head) * p.S_pad + t * BQ;
+        bulk_load_1d(sStats + qs * 512, st, 256, full);
+        bulk_load_1d(sStats + qs * 512 + 256, st + p.stats_stride, 256, full);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && n_iter > 0) {
+      constexpr uint32_t idesc_s = make_idesc(false, false, 128, BQ);      // Sᵀ, dPᵀ
+      constexpr uint32_t idesc_acc = make_idesc(false, true, 128, HD);     // dK, dV
+      constexpr uint32_t idesc_dq = make_idesc(true, true, 128, BQ);       // dQᵀ
+      mbar_wait(bar_kv, 0);
+      auto issue_s = [&](int it) {
+        const int qs = it % kQStages, st = it & 1;
+        mbar_wait(bar_qf + 8 * qs, (uint32_t)((it / kQStages) & 1));
+        if (it >= 2) mbar_wait(bar_dqr + 8 * st, (uint32_t)(((it - 2) >> 1) & 1));   // dQᵀ_{it-2} drained from this region
+        tcgen05_fence_after();
+        const uint32_t q_s = sQ + qs * kQTile, g_s = sdO + qs * kQTile;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            tcgen05_mma_f16(tmem_ST + st * BQ, make_smem_desc(sK + kb * kHalf + kk * 32, 16, 1024),
+                            make_smem_desc(q_s + kb * (kQTile / 2) + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            tcgen05_mma_f16(tmem_dP + st * BQ, make_smem_desc(sV + kb * kHalf + kk * 32, 16, 1024),
+                            make_smem_desc(g_s + kb * (kQTile / 2) + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
+        tcgen05_commit(bar_s + 8 * st);
+      };
+      issue_s(0);
+      for (int it = 0; it < n_iter; ++it) {
+        if (it + 1 < n_iter) issue_s(it + 1);
+        const int qs = it % kQStages, st = it & 1;
+        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        mbar_wait(bar_p + 8 * st, ph);
+        tcgen05_fence_after();
+        const uint32_t q_s = sQ + qs * kQTile, g_s = sdO + qs * kQTile, ds_s = sdS + st * kQTile;
+#pragma unroll
+        for (int kk = 0; kk < BQ / 16; ++kk)
+          tcgen05_mma_f16(tmem_dK, make_smem_desc(ds_s + kk * 32, 16, 1024), make_smem_desc(q_s + kk * 2048, kQTile / 2, 1024),
+                          idesc_acc, (it | kk) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < BQ / 16; ++kk)
+          tcgen05_mma_ts(tmem_dV, tmem_ST + st * BQ + kk * 8, make_smem_desc(g_s + kk * 2048, kQTile / 2, 1024), idesc_acc,
+                         (it | kk) ? 1u : 0u);
+        tcgen05_commit(bar_qe + 8 * qs);
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk)
+          tcgen05_mma_f16(tmem_dP + st * BQ, make_smem_desc(sK + kk * 2048, kHalf, 1024),
+                          make_smem_desc(ds_s + kk * 2048, kHalf, 1024), idesc_dq, kk ? 1u : 0u);
+        tcgen05_commit(bar_dq + 8 * st);
+      }
+      tcgen05_commit(bar_acc);
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // ===== softmax / dS warps: thread = kv row =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int kv = kv0 + row;
+    const float sl2 = p.scale_log2, sc = p.scale;
+    for (int it = 0; it < n_iter; ++it) {
+      const int qs = it % kQStages, st = it & 1;
+      const int t = t0 + it % per_head;
+      const int q0 = t * BQ;
+      mbar_wait(bar_qf + 8 * qs, (uint32_t)((it / kQStages) & 1));     // stats (TMA-written) visible to this thread
+      mbar_wait(bar_s + 8 * st, (uint32_t)((it >> 1) & 1));
+      tcgen05_fence_after();
+      const bool masked = (p.causal && q0 < kv0 + BN - 1) || (q0 + BQ > p.S_q) || (kv0 + BN > p.S_kv);
+      const uint32_t stats_s = sStats + qs * 512;
+      const uint32_t ds_row = sdS + st * kQTile + row * 128;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t s[32], dp[32];
+        tcgen05_ld_32x32(tmem_ST + st * BQ + lane_base + h * 32, s);
+        tcgen05_ld_32x32(tmem_dP + st * BQ + lane_base + h * 32, dp);
+        tcgen05_wait_ld();
+        uint32_t pk[16], dk_[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 l2, dl;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(l2.x), "=f"(l2.y), "=f"(l2.z), "=f"(l2.w)
+                       : "r"(stats_s + (h * 32 + i) * 4));
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(dl.x), "=f"(dl.y), "=f"(dl.z), "=f"(dl.w)
+                       : "r"(stats_s + 256 + (h * 32 + i) * 4));
+          const float l2a[4] = {l2.x, l2.y, l2.z, l2.w}, dla[4] = {dl.x, dl.y, dl.z, dl.w};
+          float pv[4], dsv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float pe = ex2(fmaf(__uint_as_float(s[i + e]), sl2, -l2a[e]));
+            float de = pe * fmaf(__uint_as_float(dp[i + e]), sc, -dla[e]);
+            if (masked) {
+              const int q = q0 + h * 32 + i + e;
+              if (!(kv < p.S_kv && q < p.S_q && (!p.causal || kv <= q))) { pe = 0.f; de = 0.f; }   // also kills NaN padding
+            }
+            pv[e] = pe;
+            dsv[e] = de;
+          }
+          pk[i >> 1] = pack_bf16(pv[0], pv[1]);      pk[(i >> 1) + 1] = pack_bf16(pv[2], pv[3]);
+          dk_[i >> 1] = pack_bf16(dsv[0], dsv[1]);   dk_[(i >> 1) + 1] = pack_bf16(dsv[2], dsv[3]);
+        }
+        tcgen05_st_32x16(tmem_ST + st * BQ + lane_base + h * 16, pk);
+        // dSᵀ row → smem, 128B-swizzled: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t chunk = (uint32_t)(h * 4 + c) ^ (uint32_t)(row & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ds_row + chunk * 16), "r"(dk_[c * 4]), "r"(dk_[c * 4 + 1]),
+                       "r"(dk_[c * 4 + 2]), "r"(dk_[c * 4 + 3]) : "memory");
+        }
+      }
+      tcgen05_wait_st();
+      fence_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(bar_p + 8 * st);
+    }
+    // ---- epilogue: dK, dV
+    if (n_iter > 0) {
+      mbar_wait(bar_acc, 0);
+      tcgen05_fence_after();
+    }
+    const bool row_ok = kv < p.S_kv;
+    __nv_bfloat16* dk_row = dk + (long)b * p.dk_sb + (long)kv * p.dk_ss + (long)kvh * p.dk_sh;
+    __nv_bfloat16* dv_row = dv + (long)b * p.dv_sb + (long)kv * p.dv_ss + (long)kvh * p.dv_sh;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* orow = which ? dv_row : dk_row;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        if (n_iter > 0) {
+          tcgen05_ld_32x32((which ? tmem_dV : tmem_dK) + lane_base + c * 32, r);
+          tcgen05_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0;
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(r[v4 * 8 + 0]), __uint_as_float(r[v4 * 8 + 1]));
+            o.y = pack_bf16(__uint_as_float(r[v4 * 8 + 2]), __uint_as_float(r[v4 * 8 + 3]));
+            o.z = pack_bf16(__uint_as_float(r[v4 * 8 + 4]), __uint_as_float(r[v4 * 8 + 5]));
+            o.w = pack_bf16(__uint_as_float(r[v4 * 8 + 6]), __uint_as_float(r[v4 * 8 + 7]));
+            *reinterpret_cast<uint4*>(orow + c * 32 + v4 * 8) = o;
+          }
+        }
+      }
+    }
+  } else {
+    // ===== dQ drain warps: thread = head-dim index d (TMEM lane), columns = q =====
+    const int quarter = warp & 3;
+    const int d = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int tid = threadIdx.x - 192;
+    for (int it = 0; it < n_iter; ++it) {
+      const int st = it & 1;
+      const int head = kvh * group + it / per_head, t = t0 + it % per_head;
+      mbar_wait(bar_dq + 8 * st, (uint32_t)((it >> 1) & 1));
+      tcgen05_fence_after();
+      float* gdst = p.dq_acc + (((long)b * p.H + head) * p.S_pad + (long)t * BQ) * HD;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[32];
+        tcgen05_ld_32x32(tmem_dP + st * BQ + lane_base + h * 32, r);
+        tcgen05_wait_ld();
+        if (h == 1) {
+          tcgen05_fence_before();
+          mbar_arrive(bar_dqr + 8 * st);
+        }
+        if (tid == 0) bulk_wait_read0();        // previous bulk reduce has finished reading the staging tile
+        named_bar(1, 128);
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(sdQ + c * 512 + d * 4), "r"(r[c]) : "memory");
+        fence_async_smem();
+        named_bar(1, 128);
+        if (tid == 0) {
+          bulk_reduce_add_f32(gdst + (long)h * 32 * HD, sdQ, 16384);
+          bulk_commit();
+        }
+      }
+    }
+    if (tid == 0) bulk_wait0();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tcgen05_dealloc(tmem_base, 512);
+}
+
+// δ·scale and lse·log2e per (b, h, s): one warp per row of 128 elements.
+__global__ void fa_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ go,
+                                   const float* __restrict__ lse, float* __restrict__ stats, long stats_stride, int B, int S,
+                                   int H, int S_pad, long o_sb, long o_ss, long o_sh, long g_sb, long g_ss, long g_sh,
+                                   float scale) {
+  const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long)B * H * S) return;
+  const int s = (int)(w % S), h = (int)((w / S) % H), b = (int)(w / ((long)S * H));
+  const uint2 ov = *reinterpret_cast<const uint2*>(o + b * o_sb + s * o_ss + h * o_sh + lane * 4);
+  const uint2 gv = *reinterpret_cast<const uint2*>(go + b * g_sb + s * g_ss + h * g_sh + lane * 4);
+  const __nv_bfloat16* oe = reinterpret_cast<const __nv_bfloat16*>(&ov);
+  const __nv_bfloat16* ge = reinterpret_cast<const __nv_bfloat16*>(&gv);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc += __bfloat162float(oe[i]) * __bfloat162float(ge[i]);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const long idx = ((long)b * H + h) * S_pad + s;
+    stats[idx] = lse[((long)b * H + h) * S + s] * 1.4426950408889634f;
+    stats[stats_stride + idx] = acc * scale;
+  }
+}
+
+// fp32 dQ accumulator [B,H,S_pad,128] → bf16 dq with arbitrary (b, s, h) strides; 8 elements per thread.
+__global__ void fa_bwd_dq_out_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int S, int H,
+                                     int S_pad, long sb, long ss, long sh) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;        // over B*H*S*16
+  if (i >= (long)B * H * S * 16) return;
+  const int c = (int)(i & 15);
+  const long r = i >> 4;
+  const int s = (int)(r % S), h = (int)((r / S) % H), b = (int)(r / ((long)S * H));
+  const float4* src = reinterpret_cast<const float4*>(acc + (((long)b * H + h) * S_pad + s) * HD + c * 8);
+  const float4 x = src[0], y = src[1];
+  uint4 o;
+  o.x = pack_bf16(x.x, x.y); o.y = pack_bf16(x.z, x.w); o.z = pack_bf16(y.x, y.y); o.w = pack_bf16(y.z, y.w);
+  *reinterpret_cast<uint4*>(dq + b * sb + s * ss + h * sh + c * 8) = o;
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 // A [B, S, H, 128] bf16 view with strides (sb, ss, sh, 1) becomes a 2-D TMA tensor whose rows are `ss` apart; batch and
 // head offsets fold into the row coordinate when they are multiples of ss, else into the column coordinate.
 struct View { const void* ptr; int B, S, H; long sb, ss, sh; };
 
-static CUtensorMap view_tmap(const View& v, Coord& c) {
+static CUtensorMap view_tmap(const View& v, Coord& c, uint32_t box_rows = 128) {
   long rows = v.S, cols = HD;
   c = Coord{0, 0, 0, 0};
   auto fold = [&](long stride, int n, int& col_mul, int& row_mul) {
@@ -290,7 +633,7 @@ static CUtensorMap view_tmap(const View& v, Coord& c) {
   fold(v.sh, v.H, c.col_h, c.row_h);
   if (cols > v.ss && rows > 1) nxd_throw("attention: unsupported q/k/v strides", __FILE__, __LINE__);
   if ((v.ss * 2) % 16 || ((uintptr_t)v.ptr % 16)) nxd_throw("attention: q/k/v must be 16-byte aligned", __FILE__, __LINE__);
-  return make_tmap_bf16_strided(v.ptr, (uint64_t)rows, (uint64_t)cols, (uint64_t)v.ss, 64, 128);
+  return make_tmap_bf16_strided(v.ptr, (uint64_t)rows, (uint64_t)cols, (uint64_t)v.ss, 64, box_rows);
 }
 
 }  // namespace fa
@@ -316,6 +659,48 @@ void flash_attn_fwd(const void* q, const void* k, const void* v, void* out, floa
   }
   dim3 grid((S_q + BM - 1) / BM, H, B);
   fa_fwd_kernel<<<grid, kThreads, kSmemFwd, st>>>(tq, tk, tv, (__nv_bfloat16*)out, p);
+  NXD_CUDA_CHECK(cudaGetLastError());
+}
+
+void flash_attn_bwd(const void* go, const void* q, const void* k, const void* v, const void* o, const float* lse, void* dq,
+                    void* dk, void* dv, float* stats, float* dq_acc, int B, int S_q, int S_kv, int H, int Hkv, int S_pad,
+                    const long* gs, const long* qs, const long* ks, const long* vs, const long* os, const long* dqs,
+                    const long* dks, const long* dvs, float scale, bool causal, cudaStream_t st) {
+  using namespace fa;
+  if (causal && S_q != S_kv) nxd_throw("attention: causal needs S_q == S_kv", __FILE__, __LINE__);
+  BwdParams p;
+  p.S_q = S_q; p.S_kv = S_kv; p.H = H; p.Hkv = Hkv; p.B = B; p.S_pad = S_pad;
+  const CUtensorMap tq = view_tmap(View{q, B, S_q, H, qs[0], qs[1], qs[2]}, p.q, BQ);
+  const CUtensorMap tg = view_tmap(View{go, B, S_q, H, gs[0], gs[1], gs[2]}, p.g, BQ);
+  const CUtensorMap tk = view_tmap(View{k, B, S_kv, Hkv, ks[0], ks[1], ks[2]}, p.k);
+  const CUtensorMap tv = view_tmap(View{v, B, S_kv, Hkv, vs[0], vs[1], vs[2]}, p.v);
+  p.dk_sb = dks[0]; p.dk_ss = dks[1]; p.dk_sh = dks[2];
+  p.dv_sb = dvs[0]; p.dv_ss = dvs[1]; p.dv_sh = dvs[2];
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal ? 1 : 0;
+  p.stats = stats; p.stats_stride = (long)B * H * S_pad + 64;
+  p.dq_acc = dq_acc;
+  NXD_CUDA_CHECK(cudaMemsetAsync(dq_acc, 0, (size_t)B * H * S_pad * HD * sizeof(float), st));
+  {
+    const long warps = (long)B * H * S_q;
+    const int threads = 256;
+    const long blocks = (warps * 32 + threads - 1) / threads;
+    fa_bwd_prep_kernel<<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)go, lse, stats,
+                                                            p.stats_stride, B, S_q, H, S_pad, os[0], os[1], os[2], gs[0],
+                                                            gs[1], gs[2], scale);
+  }
+  static bool configured = false;
+  if (!configured) {
+    NXD_CUDA_CHECK(cudaFuncSetAttribute(fa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd));
+    configured = true;
+  }
+  dim3 grid((S_kv + BN - 1) / BN, Hkv, B);
+  fa_bwd_kernel<<<grid, kThreadsBwd, kSmemBwd, st>>>(tq, tk, tv, tg, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, p);
+  {
+    const long n = (long)B * H * S_q * 16;
+    fa_bwd_dq_out_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dq, B, S_q, H, S_pad, dqs[0],
+                                                                     dqs[1], dqs[2]);
+  }
   NXD_CUDA_CHECK(cudaGetLastError());
 }
 

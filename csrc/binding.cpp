@@ -131,6 +131,46 @@ static void fused_adamw(const std::vector<Tensor>& p, const std::vector<Tensor>&
                    grad_scale.data_ptr<float>(), hf_form ? 1 : 0, stream());
 }
 
+static void gemm_fp8(const Tensor& a, const Tensor& b, Tensor out, const Tensor& scale_a, const Tensor& scale_b) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kFloat8_e4m3fn && b.scalar_type() == at::kFloat8_e4m3fn);
+  TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && out.is_contiguous() && out.scalar_type() == at::kBFloat16);
+  const int M = a.size(0), K = a.size(1), N = b.size(0);
+  TORCH_CHECK(b.size(1) == K && out.size(0) == M && out.size(1) == N && K % 16 == 0 && N % 8 == 0);
+  TORCH_CHECK(scale_a.scalar_type() == at::kFloat && scale_a.numel() == M && scale_b.scalar_type() == at::kFloat &&
+              scale_b.numel() == N && scale_a.is_contiguous() && scale_b.is_contiguous());
+  c10::cuda::CUDAGuard guard(a.device());
+  nxd::gemm_fp8(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, scale_a.data_ptr<float>(), scale_b.data_ptr<float>(),
+                stream());
+}
+
+// ---- grouped (MoE) GEMMs -------------------------------------------------------------------------
+static Tensor grouped_gemm(const Tensor& a, const Tensor& w, const Tensor& block_expert, int64_t block_rows, bool trans_b) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && a.dim() == 2 && a.is_contiguous());
+  TORCH_CHECK(w.scalar_type() == at::kBFloat16 && w.dim() == 3 && w.is_contiguous());
+  TORCH_CHECK(block_expert.scalar_type() == at::kInt && block_expert.is_cuda());
+  const int M = a.size(0), K = a.size(1), E = w.size(0);
+  const int N = trans_b ? w.size(1) : w.size(2);
+  TORCH_CHECK((trans_b ? w.size(2) : w.size(1)) == K && M % block_rows == 0 && K % 8 == 0 && N % 8 == 0);
+  TORCH_CHECK(block_expert.numel() * block_rows == M);
+  c10::cuda::CUDAGuard guard(a.device());
+  Tensor out = at::empty({M, N}, a.options());
+  nxd::grouped_gemm_bf16(a.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, K, E, trans_b, block_expert.data_ptr<int>(),
+                         (int)block_rows, nxd::kBF16, stream());
+  return out;
+}
+// dW[e] = x[rows of e]ᵀ · dy[rows of e]  → out [E, Mo, No] (bf16 or fp32), optionally accumulated
+static void grouped_wgrad(const Tensor& x, const Tensor& dy, Tensor out, const Tensor& seg_first_block, int64_t block_rows,
+                          bool accumulate) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.is_contiguous() && dy.scalar_type() == at::kBFloat16 &&
+              dy.is_contiguous() && out.is_contiguous() && out.dim() == 3);
+  TORCH_CHECK(seg_first_block.scalar_type() == at::kInt && seg_first_block.numel() == out.size(0) + 1);
+  TORCH_CHECK(x.size(0) == dy.size(0) && out.size(1) == x.size(1) && out.size(2) == dy.size(1));
+  TORCH_CHECK(x.size(1) % 8 == 0 && dy.size(1) % 8 == 0);
+  c10::cuda::CUDAGuard guard(x.device());
+  nxd::grouped_wgrad_bf16(x.data_ptr(), dy.data_ptr(), out.data_ptr(), x.size(0), x.size(1), dy.size(1), out.size(0),
+                          seg_first_block.data_ptr<int>(), (int)block_rows, dt_code(out), accumulate, stream());
+}
+
 // ---- attention ----------------------------------------------------------------------------------
 static void check_qkv(const Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.dim() == 4 && t.size(3) == 128 && t.stride(3) == 1,
@@ -150,6 +190,28 @@ static std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, cons
   nxd::flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), B, S, Skv, H, Hkv,
                       qs, ks, vs, os, (float)scale, causal, stream());
   return {out, lse};
+}
+
+static std::vector<Tensor> flash_attn_bwd(const Tensor& go, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& o,
+                                          const Tensor& lse, bool causal, double scale, bool sbhd_out) {
+  check_qkv(q, "q"); check_qkv(k, "k"); check_qkv(v, "v"); check_qkv(go, "grad_out"); check_qkv(o, "out");
+  const int B = q.size(0), S = q.size(1), H = q.size(2), Skv = k.size(1), Hkv = k.size(2);
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == (int64_t)B * H * S);
+  c10::cuda::CUDAGuard guard(q.device());
+  auto mk = [&](int s, int h) {
+    return sbhd_out ? at::empty({s, B, h, 128}, q.options()).transpose(0, 1) : at::empty({B, s, h, 128}, q.options());
+  };
+  Tensor dq = mk(S, H), dk = mk(Skv, Hkv), dv = mk(Skv, Hkv);
+  const int S_pad = (S + 63) / 64 * 64;
+  Tensor stats = at::empty({2, (int64_t)B * H * S_pad + 64}, q.options().dtype(at::kFloat));
+  Tensor dq_acc = at::empty({B, H, S_pad, 128}, q.options().dtype(at::kFloat));
+  auto st3 = [](const Tensor& t, long* out) { out[0] = t.stride(0); out[1] = t.stride(1); out[2] = t.stride(2); };
+  long gs[3], qs[3], ks[3], vs[3], os[3], dqs[3], dks[3], dvs[3];
+  st3(go, gs); st3(q, qs); st3(k, ks); st3(v, vs); st3(o, os); st3(dq, dqs); st3(dk, dks); st3(dv, dvs);
+  nxd::flash_attn_bwd(go.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(),
+                      dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), stats.data_ptr<float>(), dq_acc.data_ptr<float>(), B, S,
+                      Skv, H, Hkv, S_pad, gs, qs, ks, vs, os, dqs, dks, dvs, (float)scale, causal, stream());
+  return {dq, dk, dv};
 }
 
 // ---- GEMM ---------------------------------------------------------------------------------------
@@ -295,7 +357,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("fused_adamw", &fused_adamw);
   m.def("gemm_bf16", &gemm_bf16);
   m.def("gemm_bf16_2cta", &gemm_bf16_2cta);
+  m.def("gemm_fp8", &gemm_fp8);
+  m.def("grouped_gemm", &grouped_gemm);
+  m.def("grouped_wgrad", &grouped_wgrad);
   m.def("flash_attn_fwd", &flash_attn_fwd);
+  m.def("flash_attn_bwd", &flash_attn_bwd);
   m.def("ag_gemm_bf16", &ag_gemm_bf16);
   m.def("gemm_rs_bf16", &gemm_rs_bf16);
   m.def("tp_gemm_2cta", &tp_gemm_2cta);

@@ -60,12 +60,37 @@ struct CommDev {
   uint32_t rs_targets[kMaxRowBlocks];   // MODE 2: cumulative n-tile count expected per row-block counter
   const void* a_local;    // MODE 1: this rank's [rows_per_rank, K] shard
   void* rs_out;           // MODE 2: reduced [rows_per_rank, N] output
+  // grouped (MoE blockwise) modes.  MODE 3: every `grp_block_rows`-row block of A belongs to one expert whose weight
+  // matrix is `grp_b_rows` rows further down the stacked 2-D B tensor.  MODE 4 (wgrad): one output matrix per expert,
+  // reduced over that expert's row blocks [seg_first_block[e], seg_first_block[e+1]).
+  const float* scale_a;   // FP8: per-row (token) scales [M]
+  const float* scale_b;   // FP8: per-column (output channel) scales [N]
+  const int* block_expert;
+  const int* seg_first_block;
+  int grp_block_rows, grp_b_rows, num_groups;
+  long out_group_stride;
 };
+
+// MODE 4 tile → (expert, m_blk, n_blk, first k-block, number of k-blocks)
+struct GroupTile { int e, m_blk, n_blk, kb0, nkb; };
+NXD_DEVICE GroupTile group_tile(int tile, int tiles_m, int tiles_n, const CommDev& c) {
+  GroupTile g;
+  const int per = tiles_m * tiles_n;
+  g.e = tile / per;
+  const int in = tile - g.e * per;
+  g.m_blk = in % tiles_m;
+  g.n_blk = in / tiles_m;
+  const int b0 = c.seg_first_block[g.e], b1 = c.seg_first_block[g.e + 1];
+  const int per_blk = c.grp_block_rows / 64;
+  g.kb0 = b0 * per_blk;
+  g.nkb = (b1 - b0) * per_blk;
+  return g;
+}
 
 // tile index → (m_blk, n_blk).  `chunk_order` visits row-chunks (one per rank) in communication order.
 template <int MODE>
 NXD_DEVICE void tile_coords(int tile, int tiles_m, int tiles_n, const CommDev& c, int& m_blk, int& n_blk) {
-  if constexpr (MODE == 0) {
+  if constexpr (MODE == 0 || MODE == 3) {
     constexpr int GROUP = 8;  // rasterise 8 M-blocks at a time so B tiles are re-used from L2
     const int per_group = GROUP * tiles_n;
     const int g = tile / per_group;
@@ -87,7 +112,9 @@ NXD_DEVICE void tile_coords(int tile, int tiles_m, int tiles_n, const CommDev& c
   }
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR, int MODE, typename OutT>
+// FP8: operands are e4m3 bytes (both K-major), one k-block is 128 elements (= the same 128-byte swizzle row), the MMA is
+// kind::f8f6f4 with K = 32 per instruction, and the epilogue applies the outer product of per-row / per-column scales.
+template <bool A_KMAJOR, bool B_KMAJOR, int MODE, typename OutT, bool FP8 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  OutT* __restrict__ out, int M, int N, int K, int accumulate, CommDev comm) {
@@ -102,8 +129,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M, tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int num_tiles = (MODE == 4 ? comm.num_groups : 1) * tiles_m * tiles_n;
+  constexpr int KB_ELEMS = FP8 ? 2 * BLOCK_K : BLOCK_K;
+  const int num_kb_all = (K + KB_ELEMS - 1) / KB_ELEMS;
 
   // ---- one-time setup ------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -168,8 +196,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (lane == 0) {
         int stage = 0; uint32_t phase = 0;
         for (int tile = gemm_cta; tile < num_tiles; tile += gemm_ctas) {
-          int m_blk, n_blk;
-          tile_coords<MODE>(tile, tiles_m, tiles_n, comm, m_blk, n_blk);
+          int m_blk, n_blk, kb0 = 0, num_kb = num_kb_all, b_off = 0;
+          if constexpr (MODE == 4) {
+            const GroupTile g = group_tile(tile, tiles_m, tiles_n, comm);
+            m_blk = g.m_blk; n_blk = g.n_blk; kb0 = g.kb0; num_kb = g.nkb;
+          } else {
+            tile_coords<MODE>(tile, tiles_m, tiles_n, comm, m_blk, n_blk);
+          }
+          if constexpr (MODE == 3) b_off = comm.block_expert[(m_blk * BLOCK_M) / comm.grp_block_rows] * comm.grp_b_rows;
           if constexpr (MODE == 1) {
             const int mb_per_rank = comm.rows_per_rank / BLOCK_M;
             const uint32_t* f = (const uint32_t*)comm.peer_flags[comm.rank] + comm.flag_offset +
@@ -183,7 +217,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint32_t full = bar_full + 8 * stage;
             mbar_expect_tx(full, kStageBytes);
             const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
-            const int k0 = kb * BLOCK_K;
+            const int k0 = (kb0 + kb) * KB_ELEMS;
             if constexpr (A_KMAJOR) {
               tma_load_2d(sa, &tma_a, full, k0, m0);                          // box {64 k, 128 m}
             } else {
@@ -191,10 +225,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * 8192, &tma_a, full, m0 + j * 64, k0);  // box {64 m, 64 k}
             }
             if constexpr (B_KMAJOR) {
-              tma_load_2d(sb, &tma_b, full, k0, n0);                          // box {64 k, 256 n}
+              tma_load_2d(sb, &tma_b, full, k0, b_off + n0);                  // box {64 k, 256 n}
             } else {
 #pragma unroll
-              for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * 8192, &tma_b, full, n0 + j * 64, k0);  // box {64 n, 64 k}
+              for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * 8192, &tma_b, full, n0 + j * 64, b_off + k0);  // box {64 n, 64 k}
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -204,9 +238,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     } else if (warp == 1) {
       // ===== MMA issuer =====
       if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc(!A_KMAJOR, !B_KMAJOR, BLOCK_M, BLOCK_N);
+        constexpr uint32_t idesc = FP8 ? ((1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24))
+                                       : make_idesc(!A_KMAJOR, !B_KMAJOR, BLOCK_M, BLOCK_N);
         int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
         for (int tile = gemm_cta; tile < num_tiles; tile += gemm_ctas) {
+          int num_kb = num_kb_all;
+          if constexpr (MODE == 4) num_kb = group_tile(tile, tiles_m, tiles_n, comm).nkb;
           mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
           tcgen05_fence_after();
           const uint32_t tmem_d = tmem_base + as * BLOCK_N;
@@ -219,7 +256,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               // K-major: advance 32 B inside the 128 B swizzle row; MN-major: 16 k-rows × 128 B = 2 KB
               const uint64_t da = A_KMAJOR ? make_smem_desc(sa + k * 32, 16, 1024) : make_smem_desc(sa + k * 2048, 8192, 1024);
               const uint64_t db = B_KMAJOR ? make_smem_desc(sb + k * 32, 16, 1024) : make_smem_desc(sb + k * 2048, 8192, 1024);
-              tcgen05_mma_f16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              if constexpr (FP8) tcgen05_mma_f8(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              else tcgen05_mma_f16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             tcgen05_commit(bar_empty + 8 * stage);   // smem stage reusable once these MMAs retire
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -235,7 +273,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int as = 0; uint32_t aphase = 0;
       for (int tile = gemm_cta; tile < num_tiles; tile += gemm_ctas) {
         int m_blk, n_blk;
-        tile_coords<MODE>(tile, tiles_m, tiles_n, comm, m_blk, n_blk);
+        bool empty_group = false;
+        OutT* out_base = out;
+        if constexpr (MODE == 4) {
+          const GroupTile g = group_tile(tile, tiles_m, tiles_n, comm);
+          m_blk = g.m_blk; n_blk = g.n_blk; empty_group = g.nkb == 0;
+          out_base = out + (long)g.e * comm.out_group_stride;
+        } else {
+          tile_coords<MODE>(tile, tiles_m, tiles_n, comm, m_blk, n_blk);
+        }
         mbar_wait(bar_tfull + 8 * as, aphase);
         tcgen05_fence_after();
         const int row = m_blk * BLOCK_M + q * 32 + lane;
@@ -249,7 +295,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           uint8_t* base = (uint8_t*)comm.peer_bufs[owner] + comm.buf_offset;
           orow = (OutT*)base + ((size_t)comm.rank * comm.rows_per_rank + lrow) * (size_t)N;
         } else {
-          orow = out + (size_t)row * ld;
+          orow = out_base + (size_t)row * ld;
         }
         const bool row_ok = row < M;
 #pragma unroll 1
@@ -257,6 +303,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           uint32_t r[32];
           tcgen05_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, r);
           tcgen05_wait_ld();
+          if constexpr (FP8) {
+            const float sa = comm.scale_a[row_ok ? row : 0];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = n0 + c * 32 + j;
+              r[j] = __float_as_uint(__uint_as_float(r[j]) * sa * comm.scale_b[col < N ? col : 0]);
+            }
+          }
+          if (MODE == 4 && empty_group) {          // expert without tokens: the accumulator was never written
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+          }
           const int col0 = n0 + c * 32;
           if (row_ok && col0 < N) {
             if constexpr (sizeof(OutT) == 2) {
@@ -406,6 +464,20 @@ static CUtensorMap make_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint
   return m;
 }
 
+// e4m3 row-major [rows, cols] bytes; box = {128 k-bytes, box_rows}
+static CUtensorMap make_tmap_u8(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols};
+  cuuint32_t box[2] = {128, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) nxd_throw("cuTensorMapEncodeTiled (u8) failed: " + std::to_string((int)r), __FILE__, __LINE__);
+  return m;
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
@@ -482,6 +554,62 @@ void gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, boo
   else if (!AK && !BK) NXD_LAUNCH(false, false);
   else NXD_LAUNCH(false, true);
 #undef NXD_LAUNCH
+}
+
+// ---- grouped (MoE blockwise) GEMMs ---------------------------------------------------------------------------------
+// out[M,N] = A[M,K] · W[e(block)]: rows of A are grouped in `block_rows`-row blocks, block i uses expert block_expert[i].
+// trans_b: W is [E, N, K] (K-major) else [E, K, N] (MN-major).
+void grouped_gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, int E, bool trans_b,
+                       const int* block_expert, int block_rows, int out_dt, cudaStream_t st) {
+  if (block_rows % BLOCK_M) nxd_throw("grouped GEMM: block size must be a multiple of 128", __FILE__, __LINE__);
+  if (!trans_b && (K % BLOCK_K)) nxd_throw("grouped GEMM: K % 64 != 0 with [E,K,N] weights", __FILE__, __LINE__);
+  const CUtensorMap ta = make_tmap(a, M, K, BLOCK_K, BLOCK_M);
+  const CUtensorMap tb = trans_b ? make_tmap(b, (uint64_t)E * N, K, BLOCK_K, BLOCK_N) : make_tmap(b, (uint64_t)E * K, N, 64, BLOCK_K);
+  CommDev c{};
+  c.block_expert = block_expert; c.grp_block_rows = block_rows; c.grp_b_rows = trans_b ? N : K; c.num_groups = E;
+  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  if (trans_b) {
+    if (out_dt == kBF16) launch<true, true, 3, __nv_bfloat16>(ta, tb, out, M, N, K, false, c, grid, st);
+    else launch<true, true, 3, float>(ta, tb, out, M, N, K, false, c, grid, st);
+  } else {
+    if (out_dt == kBF16) launch<true, false, 3, __nv_bfloat16>(ta, tb, out, M, N, K, false, c, grid, st);
+    else launch<true, false, 3, float>(ta, tb, out, M, N, K, false, c, grid, st);
+  }
+}
+
+// out[e] [Mo, No] (+)= A[rows of e, Mo]ᵀ · B[rows of e, No]; expert e owns row blocks [seg_first_block[e], seg_first_block[e+1]).
+void grouped_wgrad_bf16(const void* a, const void* b, void* out, int rows_total, int Mo, int No, int E,
+                        const int* seg_first_block, int block_rows, int out_dt, bool accumulate, cudaStream_t st) {
+  if (block_rows % BLOCK_K) nxd_throw("grouped wgrad: block size must be a multiple of 64", __FILE__, __LINE__);
+  const CUtensorMap ta = make_tmap(a, rows_total, Mo, 64, BLOCK_K);
+  const CUtensorMap tb = make_tmap(b, rows_total, No, 64, BLOCK_K);
+  CommDev c{};
+  c.seg_first_block = seg_first_block; c.grp_block_rows = block_rows; c.num_groups = E; c.out_group_stride = (long)Mo * No;
+  const int tiles = E * ((Mo + BLOCK_M - 1) / BLOCK_M) * ((No + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  if (out_dt == kBF16) launch<false, false, 4, __nv_bfloat16>(ta, tb, out, Mo, No, rows_total, accumulate, c, grid, st);
+  else launch<false, false, 4, float>(ta, tb, out, Mo, No, rows_total, accumulate, c, grid, st);
+}
+
+// out[M,N] (bf16) = (a_e4m3[M,K] · b_e4m3[N,K]ᵀ) ∘ scale_a[M] ⊗ scale_b[N]   (quantised inference linear)
+void gemm_fp8(const void* a, const void* b, void* out, int M, int N, int K, const float* scale_a, const float* scale_b,
+              cudaStream_t st) {
+  if (K % 16) nxd_throw("fp8 GEMM needs K % 16 == 0", __FILE__, __LINE__);
+  const CUtensorMap ta = make_tmap_u8(a, M, K, BLOCK_M);
+  const CUtensorMap tb = make_tmap_u8(b, N, K, BLOCK_N);
+  CommDev c{};
+  c.scale_a = scale_a; c.scale_b = scale_b;
+  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  auto kern = gemm_bf16_kernel<true, true, 0, __nv_bfloat16, true>;
+  static bool configured = false;
+  if (!configured) {
+    NXD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  kern<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, (__nv_bfloat16*)out, M, N, K, 0, c);
+  NXD_CUDA_CHECK(cudaGetLastError());
 }
 
 bool gemm_self_check_supported() { return true; }

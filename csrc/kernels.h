@@ -64,9 +64,22 @@ void zero1_all_gather(const float* master, const int64_t* peer_bufs, long param_
                       int flag_off, uint32_t epoch, int rank, int world, long shard_numel, uint32_t* done_ctr, int param_dt,
                       cudaStream_t st);
 
+void gemm_fp8(const void* a, const void* b, void* out, int M, int N, int K, const float* scale_a, const float* scale_b,
+              cudaStream_t st);
+// ---- grouped (MoE blockwise) GEMMs, gemm_sm100.cu
+void grouped_gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, int E, bool trans_b,
+                       const int* block_expert, int block_rows, int out_dt, cudaStream_t st);
+void grouped_wgrad_bf16(const void* a, const void* b, void* out, int rows_total, int Mo, int No, int E,
+                        const int* seg_first_block, int block_rows, int out_dt, bool accumulate, cudaStream_t st);
+
 // ---- attention (attention_sm100.cu): q [B,S_q,H,128], k/v [B,S_kv,Hkv,128] bf16 views; strides = (b, s, h) in elements
 void flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int S_q, int S_kv, int H,
                     int Hkv, const long* qs, const long* ks, const long* vs, const long* os, float scale, bool causal,
                     cudaStream_t st);
+
+void flash_attn_bwd(const void* go, const void* q, const void* k, const void* v, const void* o, const float* lse, void* dq,
+                    void* dk, void* dv, float* stats, float* dq_acc, int B, int S_q, int S_kv, int H, int Hkv, int S_pad,
+                    const long* gs, const long* qs, const long* ks, const long* vs, const long* os, const long* dqs,
+                    const long* dks, const long* dvs, float scale, bool causal, cudaStream_t st);
 
 }  // namespace nxd

@@ -8,8 +8,9 @@ of ``block_size`` and each block is multiplied by exactly one expert's weights:
     block_to_expert[b]    : expert owning block b
     token_position_to_id  : flat [num_blocks·B] token id feeding each block slot (−1 = padding)
 
-On CUDA every block is a row-slab GEMM on the tcgen05 kernel (``ops.gemm``) — a grouped GEMM over
-``block_to_expert`` with contiguous expert segments, no per-token gather inside the kernel; on CPU it is a plain loop.
+On CUDA the two projections are grouped tcgen05 GEMMs (``ops.gemm.grouped_matmul`` → MODE 3/4 of
+``csrc/gemm_sm100.cu``): the block's expert only shifts the TMA coordinate of the weight tile, the backward runs the
+grouped dgrad and a per-expert segmented wgrad, and nothing syncs with the host.  On CPU it is a gathered einsum.
 """
 from __future__ import annotations
 
@@ -52,17 +53,20 @@ def blockwise_expert_mlp(hidden: torch.Tensor, expert_affinities: torch.Tensor, 
     """Dropless MoE MLP: ``out[t] = Σ_j aff[t, e_j] · MLP_{e_j}(hidden[t])``."""
     T, H = hidden.shape
     E = expert_affinities.shape[-1]
-    b2e, tp2id, _ = build_block_metadata(expert_index, E, block_size)
+    from ... import ops
+
+    b2e, tp2id, counts = build_block_metadata(expert_index, E, block_size)
     nb = b2e.numel()
+    blocks_per_e = (counts + block_size - 1) // block_size
+    seg_first = torch.cat([blocks_per_e.new_zeros(1), torch.cumsum(blocks_per_e, 0)])          # [E+1] block prefix sum
     valid = tp2id >= 0
     gather_ids = tp2id.clamp(min=0)
     x = hidden[gather_ids] * valid.unsqueeze(-1).to(hidden.dtype)                   # [nb·B, H]
-    x = x.view(nb, block_size, H)
     proj = experts.gate_up_proj if experts.glu_mlp else experts.up_proj
     w1, w2 = proj.weight, experts.down_proj.weight
-    h = torch.einsum("bth,bhi->bti", x, w1[b2e])
+    h = ops.gemm.grouped_matmul(x, w1, b2e, seg_first, block_size)
     h = experts.activation(h)
-    y = torch.einsum("bti,bih->bth", h, w2[b2e]).reshape(nb * block_size, H)
+    y = ops.gemm.grouped_matmul(h.contiguous(), w2, b2e, seg_first, block_size)
     aff = expert_affinities[gather_ids, b2e.repeat_interleave(block_size)] * valid.to(expert_affinities.dtype)
     if normalize:
         denom = expert_affinities.gather(1, expert_index).sum(-1, keepdim=True).clamp(min=1e-9)

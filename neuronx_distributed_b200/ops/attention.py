@@ -30,18 +30,44 @@ def _sdpa(q, k, v, causal: bool, scale: Optional[float]):
 def _own_kernel_ok(q, k, v) -> bool:
     if os.environ.get("NXD_DISABLE_OWN_ATTENTION", "0") == "1":
         return False
-    if not (q.is_cuda and q.dtype == torch.bfloat16 and q.shape[-1] == 128):
+    if not (q.is_cuda and q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16
+            and q.shape[-1] == 128 and q.dim() == 4):
         return False
     e = _ext.ext()
-    return e is not None and hasattr(e, "flash_attn_fwd") and q.shape[1] % 128 == 0 and k.shape[1] % 128 == 0
+    return e is not None and hasattr(e, "flash_attn_fwd")
+
+
+def _tma_view(t: torch.Tensor) -> torch.Tensor:
+    """The kernels read q/k/v through 2-D TMA maps built from (b, s, h) strides: head_dim must be contiguous and the batch /
+    head offsets must fold into rows or columns of that map (true for [B,S,H,D], [S,B,H,D], [B,H,S,D] memory and for slices
+    of a fused projection output); anything else is copied once."""
+    if t.stride(3) != 1 or t.data_ptr() % 16:
+        return t.contiguous()
+    ss = t.stride(1)
+    if ss % 8:
+        return t.contiguous()
+    cols = 128
+    for n, st in ((t.shape[0], t.stride(0)), (t.shape[2], t.stride(2))):
+        if n > 1 and not (st >= ss and st % ss == 0):
+            if st % 8:
+                return t.contiguous()
+            cols += (n - 1) * st
+    if cols > ss and t.shape[1] > 1:
+        return t.contiguous()
+    return t
 
 
 class _FlashAttn(torch.autograd.Function):
+    """tcgen05 flash attention (``csrc/attention_sm100.cu``): forward saves (q, k, v, o, lse); backward is the transposed
+    five-GEMM kernel.  Outputs/gradients are laid out ``[S,B,H,D]`` in memory (returned as ``[B,S,H,D]`` views) so the
+    model's ``[S,B,H·D]`` reshape is free."""
+
     @staticmethod
     def forward(ctx, q, k, v, causal, scale):
         e = _ext.ext()
+        q, k, v = _tma_view(q), _tma_view(k), _tma_view(v)
         _ext.count_launch()
-        o, lse = e.flash_attn_fwd(q.contiguous(), k.contiguous(), v.contiguous(), bool(causal), float(scale))
+        o, lse = e.flash_attn_fwd(q, k, v, bool(causal), float(scale), True)
         ctx.save_for_backward(q, k, v, o, lse)
         ctx.causal, ctx.scale = causal, scale
         return o
@@ -50,22 +76,15 @@ class _FlashAttn(torch.autograd.Function):
     def backward(ctx, go):
         q, k, v, o, lse = ctx.saved_tensors
         e = _ext.ext()
-        if hasattr(e, "flash_attn_bwd"):
-            _ext.count_launch(2)
-            dq, dk, dv = e.flash_attn_bwd(go.contiguous(), q, k, v, o, lse, bool(ctx.causal), float(ctx.scale))
-            return dq, dk, dv, None, None
-        # recompute through the library for the gradient until the bwd kernel lands
-        with torch.enable_grad():
-            qq, kk, vv = (t.detach().requires_grad_(True) for t in (q, k, v))
-            oo = _sdpa(qq, kk, vv, ctx.causal, ctx.scale)
-            dq, dk, dv = torch.autograd.grad(oo, (qq, kk, vv), go)
+        _ext.count_launch(4)   # memset + prep + main + dq convert
+        dq, dk, dv = e.flash_attn_bwd(_tma_view(go), q, k, v, o, lse, bool(ctx.causal), float(ctx.scale), True)
         return dq, dk, dv, None, None
 
 
 def flash_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True,
                     scale: Optional[float] = None) -> torch.Tensor:
     scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
-    if _own_kernel_ok(q, k, v):
+    if _own_kernel_ok(q, k, v) and (not causal or q.shape[1] == k.shape[1]):
         return _FlashAttn.apply(q, k, v, causal, scale)
     return _sdpa(q, k, v, causal, scale)
 

@@ -74,3 +74,58 @@ def linear_nt(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """``x[..., K] @ w[N, K]^T``."""
     x2 = x.reshape(-1, x.shape[-1])
     return matmul(x2, w, False, True).view(*x.shape[:-1], w.shape[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Grouped (MoE blockwise) GEMM: rows of ``x`` come in ``block_size``-row blocks, block i is multiplied by the weights of
+# expert ``block_to_expert[i]``.  CUDA: MODE 3/4 of ``csrc/gemm_sm100.cu`` (the per-block expert only shifts the TMA
+# coordinate of the weight tile — no per-block weight copies, no host sync); CPU / odd shapes: plain loop.
+# Role of the reference's blockwise NKI kernels (modules/moe/blockwise.py:180-468, 1037-1127).
+def _grouped_ok(x: torch.Tensor, w: torch.Tensor, block_size: int) -> bool:
+    e = _ext.ext()
+    return (x.is_cuda and e is not None and hasattr(e, "grouped_gemm") and x.dtype == torch.bfloat16
+            and w.dtype == torch.bfloat16 and block_size % 128 == 0 and w.shape[1] % 64 == 0 and w.shape[2] % 64 == 0
+            and os.environ.get("NXD_DISABLE_GROUPED_GEMM", "0") != "1")
+
+
+def _grouped_ref(x, w, b2e, block_size):
+    nb = b2e.numel()
+    xb = x.view(nb, block_size, x.shape[-1])
+    return torch.einsum("bth,bhi->bti", xb, w[b2e.long()]).reshape(nb * block_size, w.shape[-1])
+
+
+class _GroupedMatmul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b2e, seg_first_block, block_size):
+        ctx.save_for_backward(x, w, b2e, seg_first_block)
+        ctx.block_size = block_size
+        _ext.count_launch()
+        return _ext.ext().grouped_gemm(x.contiguous(), w.contiguous(), b2e, block_size, False)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, b2e, seg = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            _ext.count_launch()
+            gx = _ext.ext().grouped_gemm(gy, w.contiguous(), b2e, ctx.block_size, True)       # dy · W[e]ᵀ
+        if ctx.needs_input_grad[1]:
+            _ext.count_launch()
+            mg = getattr(w, "main_grad", None)
+            if mg is not None and fused_wgrad_enabled() and mg.dtype == torch.float32 and mg.is_contiguous():
+                fresh = getattr(w, "main_grad_fresh", False)
+                _ext.ext().grouped_wgrad(x.contiguous(), gy, mg.view_as(w), seg, ctx.block_size, not fresh)
+                w.main_grad_fresh = False
+            else:
+                gw = torch.empty_like(w)
+                _ext.ext().grouped_wgrad(x.contiguous(), gy, gw, seg, ctx.block_size, False)
+        return gx, gw, None, None, None
+
+
+def grouped_matmul(x: torch.Tensor, w: torch.Tensor, block_to_expert: torch.Tensor, seg_first_block: torch.Tensor,
+                   block_size: int) -> torch.Tensor:
+    """``y[i·B:(i+1)·B] = x[i·B:(i+1)·B] @ w[block_to_expert[i]]`` with ``x [nb·B, K]``, ``w [E, K, N]``."""
+    if _grouped_ok(x, w, block_size):
+        return _GroupedMatmul.apply(x, w, block_to_expert.int(), seg_first_block.int(), block_size)
+    return _grouped_ref(x, w, block_to_expert, block_size)

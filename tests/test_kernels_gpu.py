@@ -44,6 +44,18 @@ def test_tcgen05_gemm_all_layouts(gc):
     _assert_all(gc, n)
 
 
+def test_fp8_gemm(gc):
+    n = len(gc.RESULTS)
+    gc.check_fp8()
+    _assert_all(gc, n)
+
+
+def test_grouped_moe_gemm_fwd_dgrad_wgrad(gc):
+    n = len(gc.RESULTS)
+    gc.check_grouped()
+    _assert_all(gc, n)
+
+
 def test_gemm_python_frontend():
     from neuronx_distributed_b200.ops import gemm
 
@@ -58,3 +70,45 @@ def test_tiny_llama_trains_on_cuda_kernels():
     import __graft_entry__ as ge
 
     ge.smoke()
+
+
+@pytest.mark.parametrize("layout", ["bshd", "sbhd", "fused"])
+@pytest.mark.parametrize("causal", [True, False])
+def test_flash_attention_fwd_bwd_vs_fp32_reference(layout, causal):
+    """tcgen05 flash attention (fwd + 5-GEMM bwd) through the autograd front-end vs plain fp32 softmax(QKᵀ)V."""
+    import math
+
+    from neuronx_distributed_b200.ops import _ext, attention
+
+    assert hasattr(_ext.ext(), "flash_attn_fwd") and hasattr(_ext.ext(), "flash_attn_bwd")
+    torch.manual_seed(1)
+    B, S, H, Hkv, D = 2, 384, 4, 2, 128
+    dev = "cuda"
+    if layout == "bshd":
+        q, k, v = (torch.randn(B, S, h, D, device=dev).bfloat16() for h in (H, Hkv, Hkv))
+    elif layout == "sbhd":
+        q, k, v = (torch.randn(S, B, h, D, device=dev).bfloat16().transpose(0, 1) for h in (H, Hkv, Hkv))
+    else:
+        f = torch.randn(S, B, (H + 2 * Hkv) * D, device=dev).bfloat16()
+        q = f[..., : H * D].view(S, B, H, D).transpose(0, 1)
+        k = f[..., H * D:(H + Hkv) * D].view(S, B, Hkv, D).transpose(0, 1)
+        v = f[..., (H + Hkv) * D:].view(S, B, Hkv, D).transpose(0, 1)
+    q, k, v = (t.detach().requires_grad_(True) for t in (q, k, v))
+    n0 = _ext.launches()
+    o = attention.flash_attention(q, k, v, causal=causal)
+    go = torch.randn(B, S, H, D, device=dev).bfloat16()
+    o.backward(go)
+    assert _ext.launches() > n0, "own attention kernels did not run"
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    kk, vv = kf.repeat_interleave(H // Hkv, 2), vf.repeat_interleave(H // Hkv, 2)
+    s = torch.einsum("bqhd,bkhd->bhqk", qf, kk) / math.sqrt(D)
+    if causal:
+        s = s.masked_fill(~torch.ones(S, S, device=dev, dtype=torch.bool).tril(), float("-inf"))
+    ro = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), vv)
+    ro.backward(go.float())
+
+    def rel(a, b):
+        return ((a.float() - b).abs().max() / b.abs().max()).item()
+
+    assert rel(o, ro) < 2e-2
+    assert rel(q.grad, qf.grad) < 3e-2 and rel(k.grad, kf.grad) < 3e-2 and rel(v.grad, vf.grad) < 3e-2

@@ -87,7 +87,7 @@ def main():
             qq, kk, vv = (t.detach().float().requires_grad_(True) for t in (q, k, v))
             r2, _ = ref_attn(qq, kk, vv, causal, scale)
             r2.backward(go.float())
-            dq, dk, dv = e.flash_attn_bwd(go, q, k, v, o, lse, causal, scale)
+            dq, dk, dv = e.flash_attn_bwd(go, q, k, v, o, lse, causal, scale, True)
             res = {}
             for n, g, r in (("dq", dq, qq.grad), ("dk", dk, kk.grad), ("dv", dv, vv.grad)):
                 res[n] = round((g.float() - r).abs().max().item() / r.abs().max().item(), 5)
@@ -108,7 +108,7 @@ def main():
             if a.bwd and hasattr(e, "flash_attn_bwd"):
                 o, lse = e.flash_attn_fwd(q, k, v, True, scale, True)
                 go = torch.randn_like(o)
-                t_b = time_fn(lambda: e.flash_attn_bwd(go, q, k, v, o, lse, True, scale))
+                t_b = time_fn(lambda: e.flash_attn_bwd(go, q, k, v, o, lse, True, scale, True))
                 qr, kr, vr = (t.detach().requires_grad_(True) for t in (qt, kt, vt))
                 oo = torch.nn.functional.scaled_dot_product_attention(qr, kr, vr, is_causal=True)
                 got = go.transpose(1, 2)

@@ -204,6 +204,63 @@ def check_gemm_perf():
                cublas_tflops=fl / t_lib / 1e9)
 
 
+def check_fp8(perf=False):
+    """fp8 (e4m3) tcgen05 GEMM with row/column scales vs the fp32 product of the same quantised operands."""
+    from neuronx_distributed_b200.ops import gemm_fp8
+
+    torch.manual_seed(0)
+    for (M, N, K) in [(128, 256, 128), (200, 264, 208), (1024, 4096, 4096), (8, 512, 1024)]:
+        xq = torch.randn(M, K, device=dev).to(torch.float8_e4m3fn)
+        wq = torch.randn(N, K, device=dev).to(torch.float8_e4m3fn)
+        xs = torch.rand(M, device=dev) + 0.5
+        ws = torch.rand(N, device=dev) + 0.5
+        y = gemm_fp8.scaled_linear(xq, xs, wq, ws)
+        ref = (xq.float() @ wq.float().t()) * xs[:, None] * ws[None, :]
+        report(f"gemm_fp8_{M}x{N}x{K}", relerr(y, ref) < 1e-2, err=relerr(y, ref))
+    if perf:
+        M, N, K = 8192, 8192, 8192
+        xq = torch.randn(M, K, device=dev).to(torch.float8_e4m3fn); wq = torch.randn(N, K, device=dev).to(torch.float8_e4m3fn)
+        xs = torch.ones(M, device=dev); ws = torch.ones(N, device=dev)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        t = timeit(lambda: ops._ext.ext().gemm_fp8(xq, wq, out, xs, ws))
+        report("gemm_fp8_perf_8192", True, ms=t, tflops=2.0 * M * N * K / t / 1e9)
+
+
+def check_grouped(perf=False):
+    """Grouped (MoE blockwise) GEMMs: forward, dgrad and segmented wgrad vs fp32 einsum, through the autograd front-end."""
+    from neuronx_distributed_b200.modules.moe.blockwise import build_block_metadata
+
+    torch.manual_seed(0)
+    for (T, k, E, H, I, bs) in [(300, 2, 4, 256, 512, 128), (1000, 2, 8, 512, 1024, 256), (64, 1, 8, 128, 192, 128)]:
+        idx = torch.stack([torch.randperm(E, device=dev)[:k] for _ in range(T)])
+        b2e, tp2id, counts = build_block_metadata(idx, E, bs)
+        bpe = (counts + bs - 1) // bs
+        seg = torch.cat([bpe.new_zeros(1), torch.cumsum(bpe, 0)])
+        nb = b2e.numel()
+        valid = (tp2id >= 0).unsqueeze(-1)
+        x = (torch.randn(nb * bs, H, device=dev) * valid).bfloat16().requires_grad_(True)
+        w = (torch.randn(E, H, I, device=dev) / H ** 0.5).bfloat16().requires_grad_(True)
+        y = ops.gemm.grouped_matmul(x, w, b2e, seg, bs)
+        gy = (torch.randn_like(y) * valid).bfloat16()
+        y.backward(gy)
+        xf, wf = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+        yr = torch.einsum("bth,bhi->bti", xf.view(nb, bs, H), wf[b2e.long()]).reshape(nb * bs, I)
+        yr.backward(gy.float())
+        e = (relerr(y, yr), relerr(x.grad, xf.grad), relerr(w.grad, wf.grad))
+        report(f"grouped_gemm_T{T}_E{E}_H{H}_I{I}_b{bs}", max(e) < 2e-2, y=e[0], dx=e[1], dw=e[2])
+    if perf:
+        T, k, E, H, I, bs = 16384, 2, 8, 4096, 14336 * 2, 256          # Mixtral-8x7B gate_up, one 16k-token micro-batch
+        idx = torch.stack([torch.randperm(E, device=dev)[:k] for _ in range(T)])
+        b2e, tp2id, counts = build_block_metadata(idx, E, bs)
+        bpe = (counts + bs - 1) // bs
+        seg = torch.cat([bpe.new_zeros(1), torch.cumsum(bpe, 0)]).int()
+        nb = b2e.numel()
+        x = torch.randn(nb * bs, H, device=dev).bfloat16()
+        w = torch.randn(E, H, I, device=dev).bfloat16()
+        t = timeit(lambda: ops._ext.ext().grouped_gemm(x, w, b2e.int(), bs, False))
+        report("grouped_gemm_perf_mixtral_gate_up", True, ms=t, tflops=2.0 * nb * bs * H * I / t / 1e9)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     assert ops.extension_available(), ops._ext.load_error()
@@ -211,6 +268,10 @@ if __name__ == "__main__":
         check_elementwise()
     if what in ("gemm", "all"):
         check_gemm()
+    if what in ("fp8", "all"):
+        check_fp8(perf=what == "fp8")
+    if what in ("grouped", "all"):
+        check_grouped(perf=what == "grouped")
     if what in ("gemm2",):
         check_gemm_2cta()
     if what in ("gemm_perf", "all"):
