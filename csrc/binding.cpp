@@ -308,11 +308,13 @@ static void tp_gemm_2cta(int64_t mode, const Tensor& a, const Tensor& b, Tensor 
 // ---- ZeRO-1 collectives over peer memory
 static void zero1_reduce_scatter(const Tensor& peer_bufs, int64_t grad_off_bytes, const Tensor& peer_flags, int64_t flag_off,
                                  int64_t epoch, int64_t rank, int64_t world, int64_t shard_numel, double scale, Tensor out,
-                                 Tensor done_ctr, bool grads_fp32) {
+                                 Tensor done_ctr, bool grads_fp32, int64_t sub_begin, int64_t sub_len, int64_t max_ctas) {
+  TORCH_CHECK(sub_begin >= 0 && sub_len >= 0 && sub_begin + sub_len <= shard_numel && sub_begin % 8 == 0 && sub_len % 8 == 0);
   c10::cuda::CUDAGuard g(out.device());
   nxd::zero1_reduce_scatter(peer_bufs.data_ptr<int64_t>(), grad_off_bytes, peer_flags.data_ptr<int64_t>(), (int)flag_off,
-                            (uint32_t)epoch, (int)rank, (int)world, shard_numel, (float)scale, out.data_ptr<float>(),
-                            (uint32_t*)done_ctr.data_ptr(), grads_fp32 ? nxd::kF32 : nxd::kBF16, stream());
+                            (uint32_t)epoch, (int)rank, (int)world, shard_numel, sub_begin, sub_len, (float)scale,
+                            out.data_ptr<float>(), (uint32_t*)done_ctr.data_ptr(), grads_fp32 ? nxd::kF32 : nxd::kBF16,
+                            (int)max_ctas, stream());
 }
 static void zero1_all_gather(const Tensor& master, const Tensor& peer_bufs, int64_t param_off_bytes, const Tensor& peer_flags,
                              int64_t flag_off, int64_t epoch, int64_t rank, int64_t world, int64_t shard_numel,

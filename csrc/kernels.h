@@ -58,8 +58,8 @@ void gemm_bf16_2cta_tp(int mode, const void* a, const void* b, void* out_or_part
 
 // ---- zero1_comm.cu
 void zero1_reduce_scatter(const int64_t* peer_bufs, long grad_off_bytes, const int64_t* peer_flags, int flag_off,
-                          uint32_t epoch, int rank, int world, long shard_numel, float scale, float* out, uint32_t* done_ctr,
-                          int grad_dt, cudaStream_t st);
+                          uint32_t epoch, int rank, int world, long shard_numel, long sub_begin, long sub_len, float scale,
+                          float* out, uint32_t* done_ctr, int grad_dt, int max_ctas, cudaStream_t st);
 void zero1_all_gather(const float* master, const int64_t* peer_bufs, long param_off_bytes, const int64_t* peer_flags,
                       int flag_off, uint32_t epoch, int rank, int world, long shard_numel, uint32_t* done_ctr, int param_dt,
                       cudaStream_t st);

@@ -21,8 +21,11 @@ NXD_DEVICE void cross_rank_wait(const uint32_t* my_flags, int world, uint32_t ep
 template <typename G>
 __global__ void __launch_bounds__(512) zero1_rs_kernel(const int64_t* __restrict__ peer_bufs, long grad_off_bytes,
                                                        const int64_t* __restrict__ peer_flags, int flag_off, uint32_t epoch,
-                                                       int rank, int world, long shard_numel, float scale,
-                                                       float* __restrict__ out, uint32_t* __restrict__ done_ctr) {
+                                                       int rank, int world, long shard_numel, long sub_begin,
+                                                       long sub_len, float scale, float* __restrict__ out,
+                                                       uint32_t* __restrict__ done_ctr) {
+  // [sub_begin, sub_begin + sub_len) of this rank's shard is reduced (bucketed calls overlap the backward pass; a rank
+  // whose shard does not intersect the bucket passes sub_len = 0 and only takes part in the two barriers)
   // ---- entry barrier: tell every peer my gradient buffer is final, wait until all peers said so ----
   if (blockIdx.x == 0 && (int)threadIdx.x < world) {
     __threadfence_system();
@@ -31,7 +34,7 @@ __global__ void __launch_bounds__(512) zero1_rs_kernel(const int64_t* __restrict
   cross_rank_wait((const uint32_t*)peer_flags[rank] + flag_off, world, epoch);
 
   constexpr int VEC = 16 / sizeof(G);
-  const long nvec = shard_numel / VEC;
+  const long nvec = sub_len / VEC;
   const long stride = (long)gridDim.x * blockDim.x;
   for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
     float acc[VEC];
@@ -43,7 +46,7 @@ __global__ void __launch_bounds__(512) zero1_rs_kernel(const int64_t* __restrict
     for (int p = 0; p < 8; ++p) {
       if (p < world) {
         const int src = (rank + p) % world;      // start with the local copy, spread peers across ranks
-        const G* base = (const G*)((const uint8_t*)peer_bufs[src] + grad_off_bytes) + (long)rank * shard_numel;
+        const G* base = (const G*)((const uint8_t*)peer_bufs[src] + grad_off_bytes) + (long)rank * shard_numel + sub_begin;
         raw[p] = *(const uint4*)(base + v * VEC);
       }
     }
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(512) zero1_rs_kernel(const int64_t* __restrict
         for (int j = 0; j < VEC; ++j) acc[j] += to_f32<G>(g[j]);
       }
     }
-    float* o = out + v * VEC;
+    float* o = out + sub_begin + v * VEC;
 #pragma unroll
     for (int j = 0; j < VEC; j += 4)
       *(float4*)(o + j) = make_float4(acc[j] * scale, acc[j + 1] * scale, acc[j + 2] * scale, acc[j + 3] * scale);
@@ -120,16 +123,17 @@ static int sms() {
 }
 
 void zero1_reduce_scatter(const int64_t* peer_bufs, long grad_off_bytes, const int64_t* peer_flags, int flag_off,
-                          uint32_t epoch, int rank, int world, long shard_numel, float scale, float* out, uint32_t* done_ctr,
-                          int grad_dt, cudaStream_t st) {
+                          uint32_t epoch, int rank, int world, long shard_numel, long sub_begin, long sub_len, float scale,
+                          float* out, uint32_t* done_ctr, int grad_dt, int max_ctas, cudaStream_t st) {
   if (world > 8) nxd_throw("zero1 kernels support up to 8 ranks per group", __FILE__, __LINE__);
-  const int grid = sms();   // one CTA per SM; all co-resident so the last-block exit barrier cannot starve
+  // one CTA per SM by default; overlapped (bucketed) calls pass a small max_ctas so the backward GEMMs keep the SMs
+  const int grid = max_ctas > 0 && max_ctas < sms() ? max_ctas : sms();
   if (grad_dt == kF32)
     zero1_rs_kernel<float><<<grid, 512, 0, st>>>(peer_bufs, grad_off_bytes, peer_flags, flag_off, epoch, rank, world,
-                                                 shard_numel, scale, out, done_ctr);
+                                                 shard_numel, sub_begin, sub_len, scale, out, done_ctr);
   else
     zero1_rs_kernel<__nv_bfloat16><<<grid, 512, 0, st>>>(peer_bufs, grad_off_bytes, peer_flags, flag_off, epoch, rank, world,
-                                                         shard_numel, scale, out, done_ctr);
+                                                         shard_numel, sub_begin, sub_len, scale, out, done_ctr);
   NXD_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -117,6 +117,9 @@ class _GroupedMatmul(torch.autograd.Function):
                 fresh = getattr(w, "main_grad_fresh", False)
                 _ext.ext().grouped_wgrad(x.contiguous(), gy, mg.view_as(w), seg, ctx.block_size, not fresh)
                 w.main_grad_fresh = False
+                cb = getattr(w, "_nxd_grad_ready", None)
+                if cb is not None:
+                    cb(w)
             else:
                 gw = torch.empty_like(w)
                 _ext.ext().grouped_wgrad(x.contiguous(), gy, gw, seg, ctx.block_size, False)

@@ -48,11 +48,14 @@ class Zero1Symm:
         return t, off
 
     def reduce_scatter(self, grad_off: int, grad_dtype: torch.dtype, shard_numel: int, scale: float, out: torch.Tensor,
-                       group_idx: int) -> torch.Tensor:
+                       group_idx: int, sub_begin: int = 0, sub_len: Optional[int] = None, max_ctas: int = 0) -> torch.Tensor:
+        """Reduce ``[sub_begin, sub_begin+sub_len)`` of this rank's shard (default: all of it).  Every rank of the group
+        must make the same sequence of calls (a rank outside the bucket passes ``sub_len=0``)."""
         self.epoch += 1
         _ext.count_launch()
         _ext.ext().zero1_reduce_scatter(self.ws.ptrs, grad_off, self.ws.flag_ptrs, 32 * group_idx, self.epoch, self.rank,
-                                        self.world, shard_numel, scale, out, self.done, grad_dtype == torch.float32)
+                                        self.world, shard_numel, scale, out, self.done, grad_dtype == torch.float32,
+                                        sub_begin, shard_numel if sub_len is None else sub_len, max_ctas)
         return out
 
     def all_gather(self, master: torch.Tensor, param_off: int, param_dtype: torch.dtype, shard_numel: int, group_idx: int) -> None:

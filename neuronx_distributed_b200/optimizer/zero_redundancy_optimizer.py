@@ -26,6 +26,8 @@ offline (``optimizer/convert_zero_checkpoints.py``).
 """
 from __future__ import annotations
 
+import os
+
 import math
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple, Type
@@ -125,6 +127,8 @@ class Zero1Optimizer(torch.optim.Optimizer):
         use_master_weights: bool = True,
         process_group=None,
         grad_scale_divisor: Optional[float] = None,
+        overlap_grad_reduce: Optional[bool] = None,
+        overlap_ctas: int = 16,
         **defaults: Any,
     ):
         del pin_layout, grad_norm_groups, lazy_init, coalesce_cc  # XLA-only knobs
@@ -147,6 +151,16 @@ class Zero1Optimizer(torch.optim.Optimizer):
         super().__init__(params, dict(defaults))
         self._grad_norm: Optional[torch.Tensor] = None
         self._hooks = []
+        # Overlap of the gradient reduce-scatter with the backward pass (reference: bucketed reduce-scatter of the XLA
+        # ZeRO optimizer, trainer.py:258-285): the flat gradient buffer is cut into contiguous buckets; when the last
+        # gradient of a bucket has been produced (post-accumulate hook or the fused wgrad epilogue) its pull
+        # reduce-scatter is launched on a side stream with a handful of CTAs, so it runs under the remaining backward.
+        if overlap_grad_reduce is None:
+            overlap_grad_reduce = os.environ.get("NXD_ZERO1_OVERLAP", "0") == "1"
+        self.overlap_grad_reduce = bool(overlap_grad_reduce)
+        self.overlap_ctas = int(overlap_ctas)
+        self._sync_enabled = True
+        self._comm_stream = None
         self._build()
 
     # ------------------------------------------------------------------ setup
@@ -183,6 +197,76 @@ class Zero1Optimizer(torch.optim.Optimizer):
                 self._install_hook(s.param)
         self.base_optimizer = self.base_cls(base_groups, **{k: v for k, v in self.defaults.items()})
         self.base = self.base_optimizer
+        self._build_buckets()
+
+    # ------------------------------------------------------------------ overlapped (bucketed) reduce-scatter
+    def _build_buckets(self) -> None:
+        self._buckets = []          # (fg, begin, end, n_slots)
+        self._slot_buckets = {}     # id(param) -> [bucket index]
+        self._overlap_active = (self.overlap_grad_reduce and self.world > 1
+                                and all(fg.arena is not None for fg in self.flat_groups))
+        if not self._overlap_active:
+            return
+        for fg in self.flat_groups:
+            per = max(_ALIGN, (self.bucket_cap_rs // fg.grad_flat.element_size()) // _ALIGN * _ALIGN)
+            for begin in range(0, fg.total, per):
+                end = min(fg.total, begin + per)
+                members = [s for s in fg.slots if s.offset < end and s.offset + s.numel > begin]
+                if not members:
+                    continue       # padding-only tail: nothing to reduce, stays zero
+                bi = len(self._buckets)
+                # a weight used more than once per backward (tied embeddings: `shared`) signals once per use through
+                # the fused wgrad epilogue, so its buckets are never launched early (count + 1 is never reached)
+                tied = any(getattr(s.param, "shared", False) for s in members)
+                self._buckets.append((fg, begin, end, len(members) + (1 if tied else 0)))
+                for s in members:
+                    self._slot_buckets.setdefault(id(s.param), []).append(bi)
+        for fg in self.flat_groups:
+            for s in fg.slots:
+                s.param._nxd_grad_ready = self._grad_ready
+        self._comm_stream = torch.cuda.Stream()
+        self._reset_buckets()
+
+    def _reset_buckets(self) -> None:
+        self._bucket_remaining = [b[3] for b in self._buckets]
+        self._bucket_launched = [False] * len(self._buckets)
+
+    def set_grad_sync(self, enabled: bool) -> None:
+        """``False`` while accumulating non-final micro-batches (DDP ``no_sync`` semantics)."""
+        self._sync_enabled = bool(enabled)
+
+    def no_sync(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            old = self._sync_enabled
+            self._sync_enabled = False
+            try:
+                yield
+            finally:
+                self._sync_enabled = old
+        return ctx()
+
+    def _grad_ready(self, param) -> None:
+        if not (self._overlap_active and self._sync_enabled):
+            return
+        for bi in self._slot_buckets.get(id(param), ()):
+            self._bucket_remaining[bi] -= 1
+            if self._bucket_remaining[bi] == 0 and not self._bucket_launched[bi] and not getattr(param, "shared", False):
+                self._launch_bucket(bi)
+
+    def _launch_bucket(self, bi: int) -> None:
+        fg, begin, end, _ = self._buckets[bi]
+        lo, hi = fg.shard_range
+        a, b = max(begin, lo), min(end, hi)
+        cur = torch.cuda.current_stream()
+        self._comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self._comm_stream):
+            fg.arena.reduce_scatter(fg.grad_off, fg.grad_flat.dtype, fg.shard_numel, 1.0 / self.grad_scale_divisor, fg.rs_out,
+                                    fg.group_idx, sub_begin=max(a - lo, 0) if a < b else 0, sub_len=max(b - a, 0),
+                                    max_ctas=self.overlap_ctas)
+        self._bucket_launched[bi] = True
 
     def _install_hook(self, p: torch.nn.Parameter) -> None:
         def hook(param):
@@ -194,6 +278,9 @@ class Zero1Optimizer(torch.optim.Optimizer):
             else:
                 param.main_grad.add_(param.grad)
             param.grad = None
+            cb = getattr(param, "_nxd_grad_ready", None)
+            if cb is not None:
+                cb(param)
 
         self._hooks.append(p.register_post_accumulate_grad_hook(hook))
 
@@ -205,6 +292,8 @@ class Zero1Optimizer(torch.optim.Optimizer):
             for s in fg.slots:
                 s.param.grad = None
                 s.param.main_grad_fresh = True
+        if getattr(self, "_overlap_active", False):
+            self._reset_buckets()
 
     def _zero_untouched(self) -> None:
         for fg in self.flat_groups:
@@ -220,6 +309,8 @@ class Zero1Optimizer(torch.optim.Optimizer):
             if self.world == 1:
                 fg.grad_shard = fg.grad_flat[lo:hi]
                 continue
+            if fg.arena is not None and self._overlap_active:
+                continue           # handled bucket-wise below
             if fg.arena is not None:
                 fg.grad_shard = fg.arena.reduce_scatter(fg.grad_off, fg.grad_flat.dtype, fg.shard_numel,
                                                         1.0 / self.grad_scale_divisor, fg.rs_out, fg.group_idx)
@@ -244,6 +335,16 @@ class Zero1Optimizer(torch.optim.Optimizer):
                         blk = view[:, c0:c1].contiguous()
                         dist.reduce_scatter_tensor(out[c0:c1], blk.view(-1), group=self.pg)
             fg.grad_shard = out
+        if self._overlap_active:
+            # buckets whose last gradient never signalled (unused parameters, sync disabled during backward): now, in
+            # index order — identical on every rank, which the epoch handshake of the kernels relies on
+            for bi in range(len(self._buckets)):
+                if not self._bucket_launched[bi]:
+                    self._launch_bucket(bi)
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            for fg in self.flat_groups:
+                fg.grad_shard = fg.rs_out
+            self._reset_buckets()
 
     def _all_gather_params(self) -> None:
         if self.world == 1:

@@ -317,6 +317,9 @@ def wgrad(go2d: torch.Tensor, x2d: torch.Tensor, weight: torch.Tensor):
         fresh = getattr(weight, "main_grad_fresh", False)
         ops.gemm.matmul(go2d, x2d, True, False, out=mg, accumulate=not fresh)
         weight.main_grad_fresh = False
+        cb = getattr(weight, "_nxd_grad_ready", None)      # ZeRO-1 overlapped reduce-scatter: this gradient is final
+        if cb is not None:
+            cb(weight)
         return None
     return ops.gemm.matmul(go2d, x2d, True, False)
 
