@@ -153,6 +153,10 @@ def main(args) -> int:
     opt = nxd.initialize_parallel_optimizer(cfg, AdamW_FP32OptimParams, model.parameters(), lr=3e-4, betas=(0.9, 0.95),
                                             weight_decay=0.1)
     gbs = args.global_batch
+    mbs = getattr(args, "micro_batch", 0) or {1: 1, 2: 1, 4: 2, 8: 4}.get(args.gpus, 1)   # same rule as the other arm
+    mbs = max(1, min(mbs, gbs))
+    while gbs % mbs:
+        mbs -= 1
     gen = torch.Generator().manual_seed(7)
     n_host = args.steps + args.warmup + 2
     host_ids = [torch.randint(0, V, (gbs, S), generator=gen) for _ in range(n_host)]
@@ -163,12 +167,12 @@ def main(args) -> int:
     def train_step(ids_dev):
         opt.zero_grad()
         total = None
-        for mb in range(gbs):
-            ids = ids_dev[mb:mb + 1]
+        for mb in range(0, gbs, mbs):
+            ids = ids_dev[mb:mb + mbs]
             loss = model.run_train(ids, ids)
             total = loss if total is None else total + loss
         opt.step()
-        return total / gbs
+        return total / (gbs // mbs)
 
     def sync():
         dist.barrier()
@@ -212,7 +216,7 @@ def main(args) -> int:
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "dtype": "bf16",
             "data": "synthetic", "vs_baseline": value / (6.90 * 8192),
-            "config": {"model": "llama2-7b" if L == 32 else f"llama2-7b-{L}L(debug)", "global_batch": gbs, "micro_batch": 1,
+            "config": {"model": "llama2-7b" if L == 32 else f"llama2-7b-{L}L(debug)", "global_batch": gbs, "micro_batch": mbs,
                        "seq_len": S, "parallelism": f"tp{tp}" + ("+sp" if sp else ""),
                        "stack": "unmodified reference (baseline/_ref) + xla_stubs: NCCL collectives, cuBLAS GEMM, SDPA attention",
                        "final_loss": float(loss)},

@@ -14,6 +14,7 @@
 // Outputs: O (bf16, arbitrary b/s/h strides) and LSE (fp32 [B, H, S], natural log) for the backward.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "common.cuh"
@@ -42,6 +43,13 @@ NXD_DEVICE void tcgen05_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b
       : "memory");
 }
 NXD_DEVICE void tcgen05_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+NXD_DEVICE void tcgen05_st_32x16p(uint32_t taddr, const uint32_t* r) {   // first 16 registers of a larger array
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
@@ -177,25 +185,26 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
       tcgen05_fence_after();
       const int kv0 = j * BN;
       const bool masked = (p.causal && kv0 + BN - 1 > qt * BM) || (kv0 + BN > p.S_kv);
-      // ---- pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tcgen05_ld_32x32(tmem_S + lane_base + c * 32, r);
-        tcgen05_wait_ld();
-        if (masked) {
+      // ---- the whole S row (128 fp32) comes into registers with four back-to-back TMEM loads and one wait
+      uint32_t sr[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tcgen05_ld_32x32(tmem_S + lane_base + c * 32, sr[c]);
+      tcgen05_wait_ld();
+      if (masked) {      // diagonal / ragged tile: −inf in place, the exp below turns it into an exact 0
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int kv = kv0 + c * 32 + i;
-            const bool ok = kv < p.S_kv && (!p.causal || kv <= q_idx);
-            mx = fmaxf(mx, ok ? __uint_as_float(r[i]) : -INFINITY);
+            if (!(kv < p.S_kv && (!p.causal || kv <= q_idx))) sr[c][i] = 0xff800000u;
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
       }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(mx4[c], __uint_as_float(sr[c][i]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       if (j == 0) {
         m_ref = mx;
       } else {
@@ -217,28 +226,21 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
           }
         }
       }
-      // ---- pass 2: P = exp2(s·scale·log2e − m_ref·scale·log2e), packed bf16 over the S columns
+      // ---- P = exp2(s·scale·log2e − m_ref·scale·log2e), packed to bf16 in place and written over the S columns
       const float mb = m_ref * sl2;
-#pragma unroll 1
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tcgen05_ld_32x32(tmem_S + lane_base + c * 32, r);
-        tcgen05_wait_ld();
-        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2(fmaf(__uint_as_float(r[i]), sl2, -mb));
-          float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -mb));
-          if (masked) {
-            const int kv = kv0 + c * 32 + i;
-            if (!(kv < p.S_kv && (!p.causal || kv <= q_idx))) p0 = 0.f;
-            if (!(kv + 1 < p.S_kv && (!p.causal || kv + 1 <= q_idx))) p1 = 0.f;
-          }
-          l += p0 + p1;
-          pk[i >> 1] = pack_bf16(p0, p1);
+          const float p0 = ex2(fmaf(__uint_as_float(sr[c][i]), sl2, -mb));
+          const float p1 = ex2(fmaf(__uint_as_float(sr[c][i + 1]), sl2, -mb));
+          l4[c] += p0 + p1;
+          sr[c][i >> 1] = pack_bf16(p0, p1);
         }
-        tcgen05_st_32x16(tmem_S + lane_base + c * 16, pk);
+        tcgen05_st_32x16p(tmem_S + lane_base + c * 16, sr[c]);
       }
+      l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       tcgen05_wait_st();
       tcgen05_fence_before();
       mbar_arrive(bar_p);
@@ -304,6 +306,7 @@ struct BwdParams {
   const float* stats;          // [2][B*H*S_pad (+pad)] : lse·log2e , δ·scale
   long stats_stride;
   float* dq_acc;               // [B, H, S_pad, 128] fp32
+  int debug;                   // NXD_FA_DEBUG bits (perf triage only): 1 no bulk reduce, 2 no dQ staging, 4 no softmax math
 };
 
 NXD_DEVICE void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
@@ -328,9 +331,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = base + kOffK, sV = base + kOffV, sQ = base + kOffQ, sdO = base + kOffdO, sdS = base + kOffdS,
                  sdQ = base + kOffdQ, sStats = base + kOffStats, bars = base + kOffBars;
-  // barriers: kv | qf[3] | qe[3] | s[2] | p[2] | dq[2] | dqr[2] | acc | tmem slot
-  const uint32_t bar_kv = bars, bar_qf = bars + 8, bar_qe = bars + 32, bar_s = bars + 56, bar_p = bars + 72,
-                 bar_dq = bars + 88, bar_dqr = bars + 104, bar_acc = bars + 120, tmem_slot = bars + 128;
+  // barriers: kv | qf[3] | qe[3] | s[2] | dp | p | dq | dqr | acc | tmem slot
+  const uint32_t bar_kv = bars, bar_qf = bars + 8, bar_qe = bars + 32, bar_s = bars + 56, bar_dp = bars + 72,
+                 bar_p = bars + 80, bar_dq = bars + 88, bar_dqr = bars + 96, bar_acc = bars + 104, tmem_slot = bars + 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   const int group = p.H / p.Hkv;
@@ -343,9 +346,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
   if (threadIdx.x == 0) {
     mbar_init(bar_kv, 1);
     for (int i = 0; i < kQStages; ++i) { mbar_init(bar_qf + 8 * i, 1); mbar_init(bar_qe + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_s + 8 * i, 1); mbar_init(bar_p + 8 * i, 128); mbar_init(bar_dq + 8 * i, 1); mbar_init(bar_dqr + 8 * i, 128);
-    }
+    mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1);
+    mbar_init(bar_dp, 1); mbar_init(bar_p, 128); mbar_init(bar_dq, 1); mbar_init(bar_dqr, 128);
     mbar_init(bar_acc, 1);
     fence_barrier_init();
   }
@@ -358,7 +360,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tmem_dK = tmem_base, tmem_dV = tmem_base + 128, tmem_ST = tmem_base + 256, tmem_dP = tmem_base + 384;
+  // TMEM columns: dK [0,128) | dV [128,256) | Sᵀ/Pᵀ double buffer [256,384) | dPᵀ [384,448) | dQᵀ [448,512)
+  const uint32_t tmem_dK = tmem_base, tmem_dV = tmem_base + 128, tmem_ST = tmem_base + 256, tmem_dP = tmem_base + 384,
+                 tmem_dQ = tmem_base + 448;
 
   if (warp == 0) {
     if (lane == 0 && n_iter > 0) {
@@ -395,33 +399,43 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
       constexpr uint32_t idesc_acc = make_idesc(false, true, 128, HD);     // dK, dV
       constexpr uint32_t idesc_dq = make_idesc(true, true, 128, BQ);       // dQᵀ
       mbar_wait(bar_kv, 0);
-      auto issue_s = [&](int it) {
+      // Issue order per iteration `it` (everything on the tensor pipe retires in this order):
+      //   … Sᵀ_{it+1} already issued …  | wait softmax(it) | dPᵀ_{it+1} | dK_it dV_it | dQᵀ_it | Sᵀ_{it+2}
+      // so while the softmax warps work on tile it+1 the pipe runs dK/dV/dQ of tile it and Sᵀ of tile it+2.
+      auto issue_st = [&](int it) {
         const int qs = it % kQStages, st = it & 1;
         mbar_wait(bar_qf + 8 * qs, (uint32_t)((it / kQStages) & 1));
-        if (it >= 2) mbar_wait(bar_dqr + 8 * st, (uint32_t)(((it - 2) >> 1) & 1));   // dQᵀ_{it-2} drained from this region
         tcgen05_fence_after();
-        const uint32_t q_s = sQ + qs * kQTile, g_s = sdO + qs * kQTile;
+        const uint32_t q_s = sQ + qs * kQTile;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             tcgen05_mma_f16(tmem_ST + st * BQ, make_smem_desc(sK + kb * kHalf + kk * 32, 16, 1024),
                             make_smem_desc(q_s + kb * (kQTile / 2) + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
+        tcgen05_commit(bar_s + 8 * st);
+      };
+      auto issue_dp = [&](int it) {
+        const int qs = it % kQStages;
+        mbar_wait(bar_qf + 8 * qs, (uint32_t)((it / kQStages) & 1));
+        tcgen05_fence_after();
+        const uint32_t g_s = sdO + qs * kQTile;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            tcgen05_mma_f16(tmem_dP + st * BQ, make_smem_desc(sV + kb * kHalf + kk * 32, 16, 1024),
+            tcgen05_mma_f16(tmem_dP, make_smem_desc(sV + kb * kHalf + kk * 32, 16, 1024),
                             make_smem_desc(g_s + kb * (kQTile / 2) + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
-        tcgen05_commit(bar_s + 8 * st);
+        tcgen05_commit(bar_dp);
       };
-      issue_s(0);
+      issue_st(0);
+      issue_dp(0);
+      if (n_iter > 1) issue_st(1);
       for (int it = 0; it < n_iter; ++it) {
-        if (it + 1 < n_iter) issue_s(it + 1);
         const int qs = it % kQStages, st = it & 1;
-        const uint32_t ph = (uint32_t)((it >> 1) & 1);
-        mbar_wait(bar_p + 8 * st, ph);
+        mbar_wait(bar_p, (uint32_t)(it & 1));             // Pᵀ_it in TMEM, dSᵀ_it in smem, dPᵀ region consumed
         tcgen05_fence_after();
+        if (it + 1 < n_iter) issue_dp(it + 1);
         const uint32_t q_s = sQ + qs * kQTile, g_s = sdO + qs * kQTile, ds_s = sdS + st * kQTile;
 #pragma unroll
         for (int kk = 0; kk < BQ / 16; ++kk)
@@ -432,11 +446,16 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
           tcgen05_mma_ts(tmem_dV, tmem_ST + st * BQ + kk * 8, make_smem_desc(g_s + kk * 2048, kQTile / 2, 1024), idesc_acc,
                          (it | kk) ? 1u : 0u);
         tcgen05_commit(bar_qe + 8 * qs);
+        if (it >= 1) {
+          mbar_wait(bar_dqr, (uint32_t)((it - 1) & 1));   // dQᵀ_{it-1} has been read out of TMEM
+          tcgen05_fence_after();
+        }
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk)
-          tcgen05_mma_f16(tmem_dP + st * BQ, make_smem_desc(sK + kk * 2048, kHalf, 1024),
-                          make_smem_desc(ds_s + kk * 2048, kHalf, 1024), idesc_dq, kk ? 1u : 0u);
-        tcgen05_commit(bar_dq + 8 * st);
+          tcgen05_mma_f16(tmem_dQ, make_smem_desc(sK + kk * 2048, kHalf, 1024), make_smem_desc(ds_s + kk * 2048, kHalf, 1024),
+                          idesc_dq, kk ? 1u : 0u);
+        tcgen05_commit(bar_dq);
+        if (it + 2 < n_iter) issue_st(it + 2);            // overwrites Pᵀ_it — after dV_it in pipe order
       }
       tcgen05_commit(bar_acc);
     }
@@ -454,17 +473,20 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
       const int q0 = t * BQ;
       mbar_wait(bar_qf + 8 * qs, (uint32_t)((it / kQStages) & 1));     // stats (TMA-written) visible to this thread
       mbar_wait(bar_s + 8 * st, (uint32_t)((it >> 1) & 1));
+      mbar_wait(bar_dp, (uint32_t)(it & 1));
       tcgen05_fence_after();
       const bool masked = (p.causal && q0 < kv0 + BN - 1) || (q0 + BQ > p.S_q) || (kv0 + BN > p.S_kv);
       const uint32_t stats_s = sStats + qs * 512;
       const uint32_t ds_row = sdS + st * kQTile + row * 128;
-#pragma unroll 1
+      uint32_t sv[2][32], dpv[2][32];
+      tcgen05_ld_32x32(tmem_ST + st * BQ + lane_base, sv[0]);
+      tcgen05_ld_32x32(tmem_dP + lane_base, dpv[0]);
+      tcgen05_ld_32x32(tmem_ST + st * BQ + lane_base + 32, sv[1]);
+      tcgen05_ld_32x32(tmem_dP + lane_base + 32, dpv[1]);
+      tcgen05_wait_ld();
+#pragma unroll
       for (int h = 0; h < 2; ++h) {
-        uint32_t s[32], dp[32];
-        tcgen05_ld_32x32(tmem_ST + st * BQ + lane_base + h * 32, s);
-        tcgen05_ld_32x32(tmem_dP + st * BQ + lane_base + h * 32, dp);
-        tcgen05_wait_ld();
-        uint32_t pk[16], dk_[16];
+        if (!(p.debug & 4))
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           float4 l2, dl;
@@ -476,8 +498,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
           float pv[4], dsv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float pe = ex2(fmaf(__uint_as_float(s[i + e]), sl2, -l2a[e]));
-            float de = pe * fmaf(__uint_as_float(dp[i + e]), sc, -dla[e]);
+            float pe = ex2(fmaf(__uint_as_float(sv[h][i + e]), sl2, -l2a[e]));
+            float de = pe * fmaf(__uint_as_float(dpv[h][i + e]), sc, -dla[e]);
             if (masked) {
               const int q = q0 + h * 32 + i + e;
               if (!(kv < p.S_kv && q < p.S_q && (!p.causal || kv <= q))) { pe = 0.f; de = 0.f; }   // also kills NaN padding
@@ -485,22 +507,23 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
             pv[e] = pe;
             dsv[e] = de;
           }
-          pk[i >> 1] = pack_bf16(pv[0], pv[1]);      pk[(i >> 1) + 1] = pack_bf16(pv[2], pv[3]);
-          dk_[i >> 1] = pack_bf16(dsv[0], dsv[1]);   dk_[(i >> 1) + 1] = pack_bf16(dsv[2], dsv[3]);
+          // packed in place: element pair (i, i+1) → register i/2 (already consumed)
+          sv[h][i >> 1] = pack_bf16(pv[0], pv[1]);      sv[h][(i >> 1) + 1] = pack_bf16(pv[2], pv[3]);
+          dpv[h][i >> 1] = pack_bf16(dsv[0], dsv[1]);   dpv[h][(i >> 1) + 1] = pack_bf16(dsv[2], dsv[3]);
         }
-        tcgen05_st_32x16(tmem_ST + st * BQ + lane_base + h * 16, pk);
+        tcgen05_st_32x16p(tmem_ST + st * BQ + lane_base + h * 16, sv[h]);
         // dSᵀ row → smem, 128B-swizzled: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint32_t chunk = (uint32_t)(h * 4 + c) ^ (uint32_t)(row & 7);
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ds_row + chunk * 16), "r"(dk_[c * 4]), "r"(dk_[c * 4 + 1]),
-                       "r"(dk_[c * 4 + 2]), "r"(dk_[c * 4 + 3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ds_row + chunk * 16), "r"(dpv[h][c * 4]),
+                       "r"(dpv[h][c * 4 + 1]), "r"(dpv[h][c * 4 + 2]), "r"(dpv[h][c * 4 + 3]) : "memory");
         }
       }
       tcgen05_wait_st();
       fence_async_smem();
       tcgen05_fence_before();
-      mbar_arrive(bar_p + 8 * st);
+      mbar_arrive(bar_p);
     }
     // ---- epilogue: dK, dV
     if (n_iter > 0) {
@@ -545,26 +568,26 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
     for (int it = 0; it < n_iter; ++it) {
       const int st = it & 1;
       const int head = kvh * group + it / per_head, t = t0 + it % per_head;
-      mbar_wait(bar_dq + 8 * st, (uint32_t)((it >> 1) & 1));
+      mbar_wait(bar_dq, (uint32_t)(it & 1));
       tcgen05_fence_after();
       float* gdst = p.dq_acc + (((long)b * p.H + head) * p.S_pad + (long)t * BQ) * HD;
-#pragma unroll 1
+      uint32_t r[2][32];
+      tcgen05_ld_32x32(tmem_dQ + lane_base, r[0]);
+      tcgen05_ld_32x32(tmem_dQ + lane_base + 32, r[1]);
+      tcgen05_wait_ld();
+      tcgen05_fence_before();
+      mbar_arrive(bar_dqr);                     // the MMA warp may overwrite dQᵀ with the next tile right away
+      if (p.debug & 2) continue;
+#pragma unroll
       for (int h = 0; h < 2; ++h) {
-        uint32_t r[32];
-        tcgen05_ld_32x32(tmem_dP + st * BQ + lane_base + h * 32, r);
-        tcgen05_wait_ld();
-        if (h == 1) {
-          tcgen05_fence_before();
-          mbar_arrive(bar_dqr + 8 * st);
-        }
         if (tid == 0) bulk_wait_read0();        // previous bulk reduce has finished reading the staging tile
         named_bar(1, 128);
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(sdQ + c * 512 + d * 4), "r"(r[c]) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(sdQ + c * 512 + d * 4), "r"(r[h][c]) : "memory");
         fence_async_smem();
         named_bar(1, 128);
-        if (tid == 0) {
+        if (tid == 0 && !(p.debug & 1)) {
           bulk_reduce_add_f32(gdst + (long)h * 32 * HD, sdQ, 16384);
           bulk_commit();
         }
@@ -680,6 +703,7 @@ void flash_attn_bwd(const void* go, const void* q, const void* k, const void* v,
   p.causal = causal ? 1 : 0;
   p.stats = stats; p.stats_stride = (long)B * H * S_pad + 64;
   p.dq_acc = dq_acc;
+  { const char* e = getenv("NXD_FA_DEBUG"); p.debug = e ? atoi(e) : 0; }
   NXD_CUDA_CHECK(cudaMemsetAsync(dq_acc, 0, (size_t)B * H * S_pad * HD * sizeof(float), st));
   {
     const long warps = (long)B * H * S_q;

@@ -33,8 +33,9 @@ _FLAGS_RS = 2048
 _FLAGS_RS2 = 3072
 _NFLAGS = 4096
 _COMM_SMS = int(os.environ.get("NXD_AG_COMM_SMS", "16"))
-_COMM_CTAS_AG = int(os.environ.get("NXD_TP_COMM_CTAS_AG", "12"))     # CTA-pair kernels: must be even
-_COMM_CTAS_RS = int(os.environ.get("NXD_TP_COMM_CTAS_RS", "16"))
+# CTAs (out of 148) that only move data inside the fused kernels; even numbers (CTA pairs).  Mutable so benchmarks can sweep.
+CONFIG = {"comm_ctas_ag": int(os.environ.get("NXD_TP_COMM_CTAS_AG", "12")),
+          "comm_ctas_rs": int(os.environ.get("NXD_TP_COMM_CTAS_RS", "16"))}
 _USE_2CTA_TP = os.environ.get("NXD_TP_2CTA", "1") == "1"
 TILE_M2 = 256
 
@@ -85,7 +86,7 @@ class TPWorkspace:
         _ext.count_launch()
         if _USE_2CTA_TP and ms % TILE_M2 == 0 and out_dtype == torch.bfloat16 and hasattr(_ext.ext(), "tp_gemm_2cta"):
             _ext.ext().tp_gemm_2cta(1, a_shard, b, out, out, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs,
-                                    off, _FLAGS_AG, self.ag_epoch, self.rank, self.world, _COMM_CTAS_AG, self.counters, 0)
+                                    off, _FLAGS_AG, self.ag_epoch, self.rank, self.world, CONFIG["comm_ctas_ag"], self.counters, 0)
             # the kernel reads the own shard in place (no local copy); complete the gathered view for wgrad consumers
             gathered = self.ws.local_tensor(off, (M, K), torch.bfloat16)
             gathered[self.rank * ms:(self.rank + 1) * ms].copy_(a_shard)
@@ -108,11 +109,12 @@ class TPWorkspace:
             if self.partial is None or self.partial.numel() < M * N:
                 self.partial = torch.empty(M * N, dtype=torch.bfloat16, device=a.device)
             partial = self.partial[: M * N].view(M, N)
-            self.gemm_done_total = (self.gemm_done_total + 2 * self.sm_pairs - _COMM_CTAS_RS) & 0xFFFFFFFF
+            comm_ctas = CONFIG["comm_ctas_rs"]
+            self.gemm_done_total = (self.gemm_done_total + 2 * self.sm_pairs - comm_ctas) & 0xFFFFFFFF
             out = torch.empty(ms, N, dtype=torch.bfloat16, device=a.device)
             _ext.count_launch()
             _ext.ext().tp_gemm_2cta(2, a, b, out, partial, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs, off,
-                                    _FLAGS_RS2, self.rs2_calls, self.rank, self.world, _COMM_CTAS_RS, self.counters,
+                                    _FLAGS_RS2, self.rs2_calls, self.rank, self.world, comm_ctas, self.counters,
                                     self.gemm_done_total)
             return out
         self.rs_calls += 1

@@ -85,3 +85,47 @@ def _zero1_fused(rank, world):
 
 def test_zero1_fused_comm_matches_nccl():
     run_distributed(_zero1_fused, 2, use_cuda=True, timeout=240)
+
+
+def _zero1_overlap(rank, world):
+    """DP=2 ZeRO-1 with the bucketed reduce-scatter launched under the backward pass: bit-identical parameters to the
+    single reduce-scatter at step(), with and without gradient accumulation (no_sync on the first micro-batch)."""
+    import contextlib
+
+    from neuronx_distributed_b200.models.llama import LlamaConfig, LlamaForCausalLM
+    from neuronx_distributed_b200.optimizer import NeuronZero1Optimizer
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.utils.adamw_fp32_optim_params import AdamW_FP32OptimParams
+
+    dev = torch.device("cuda", rank)
+    results = {}
+    for overlap in (False, True):
+        if ps.model_parallel_is_initialized():
+            ps.destroy_model_parallel()
+        ps.initialize_model_parallel(tensor_model_parallel_size=1)
+        mcfg = LlamaConfig(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=3, num_attention_heads=2,
+                           dtype=torch.bfloat16, device=dev, max_position_embeddings=128, tie_word_embeddings=False)
+        torch.manual_seed(0); torch.cuda.manual_seed(0)
+        model = LlamaForCausalLM(mcfg)
+        opt = NeuronZero1Optimizer(model.parameters(), AdamW_FP32OptimParams, lr=1e-2, use_grad_acc_hook=True,
+                                   bucket_cap_mb_reduce_scatter=1, overlap_grad_reduce=overlap, grad_clipping=True, max_norm=1.0)
+        assert opt.arena is not None and opt._overlap_active == overlap
+        if overlap:
+            assert len(opt._buckets) > 2
+        for step in range(3):
+            opt.zero_grad()
+            for mb in range(2):
+                ids = torch.randint(0, 512, (1, 128), generator=torch.Generator().manual_seed(100 * step + 10 * mb + rank)).to(dev)
+                ctx = opt.no_sync() if mb == 0 else contextlib.nullcontext()
+                with ctx:
+                    loss, _ = model(input_ids=ids, labels=ids)
+                    (loss / 2).backward()
+            if overlap:
+                assert any(opt._bucket_launched), "no bucket was reduced during backward"
+            opt.step()
+        results[overlap] = opt.flat_groups[0].param_flat.float().clone()
+    assert torch.equal(results[True], results[False])
+
+
+def test_zero1_overlapped_reduce_scatter_is_exact():
+    run_distributed(_zero1_overlap, 2, use_cuda=True, timeout=240)

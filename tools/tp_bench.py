@@ -72,6 +72,26 @@ def main():
         own = timeit(lambda: comm.reduce_scatter(gemm.matmul(x, w, False, True), 0, g))
         lib = timeit(lambda: comm.reduce_scatter(torch.matmul(x, w.t()), 0, g))
         report(name, S, H, K, (world - 1) * (S // world) * H * 2, fused, own, lib)
+    # optional sweep: comm-CTA split × micro-batch rows (fused kernels only)
+    if "--sweep" in sys.argv:
+        sweep = []
+        for M in (4096, 16384):
+            if (M // world) % 256 or M // world // 128 > 64:
+                continue
+            for ag, rs in ((12, 16), (24, 24), (32, 32), (48, 48)):
+                _fused_impl.CONFIG["comm_ctas_ag"], _fused_impl.CONFIG["comm_ctas_rs"] = ag, rs
+                x = torch.randn(M // world, H, device="cuda", dtype=torch.bfloat16)
+                w = torch.randn(2 * I // world, H, device="cuda", dtype=torch.bfloat16)
+                t_ag = timeit(lambda: ws.ag_gemm(x, w, True), iters=10, warmup=3)
+                x2 = torch.randn(M, I // world, device="cuda", dtype=torch.bfloat16)
+                w2 = torch.randn(H, I // world, device="cuda", dtype=torch.bfloat16)
+                t_rs = timeit(lambda: ws.gemm_rs(x2, w2, True), iters=10, warmup=3)
+                rec = {"sweep": True, "M": M, "comm_ctas_ag": ag, "comm_ctas_rs": rs, "ag_gemm_gate_up_us": t_ag, "gemm_rs_down_us": t_rs}
+                sweep.append(rec)
+                if rank == 0:
+                    print(json.dumps(rec), flush=True)
+        _fused_impl.CONFIG["comm_ctas_ag"], _fused_impl.CONFIG["comm_ctas_rs"] = 12, 16
+        res.append({"sweep": sweep})
     # raw collectives for reference
     x = torch.randn(S // world, H, device="cuda", dtype=torch.bfloat16)
     y = torch.randn(S, H, device="cuda", dtype=torch.bfloat16)
