@@ -2,8 +2,7 @@
 // online softmax with one thread per query row.  Role parity: reference kernels/flash_attn.py:162-212
 // (nki_flash_attn_func → flash_fwd / flash_attn_bwd) and modules/attention call sites.
 //
-// Forward, one CTA per (128-query tile, head, batch); two CTAs are resident per SM so the softmax of one overlaps the
-// tensor-core work of the other (TMEM: 2 × 256 columns):
+// Forward, one CTA per (128-query tile, head, batch), one CTA per SM (TMEM: S double buffer + O = 384 of 512 columns):
 //   warp 0      TMA producer : Q once, then K_j / V_j tiles ([128 kv × 128 d] as two 128B-swizzled [128 × 64] boxes)
 //   warp 1      MMA issuer   : S = Q·K_jᵀ  (A, B K-major, 8 × UMMA 128×128×16)  → TMEM cols [0,128)
 //                              O += P·V_j (A = P read from TMEM, B = V MN-major)  → TMEM cols [128,256)
@@ -30,9 +29,10 @@ namespace fa {
 
 constexpr int BM = 128, BN = 128, HD = 128;
 constexpr int kThreads = 192;
+constexpr int kPolyPairs = 0;      // of every 8 element pairs, how many use ex2_poly in the forward softmax
 constexpr uint32_t kTile = BM * HD * 2;          // 32 KB
 constexpr uint32_t kHalf = kTile / 2;            // one [128 × 64] box
-constexpr uint32_t kSmemFwd = 3 * kTile + 1024 /*align*/ + 128 /*barriers*/;
+constexpr uint32_t kSmemFwd = 5 * kTile + 1024 /*align*/ + 128 /*barriers*/;
 
 NXD_DEVICE void tcgen05_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -41,6 +41,35 @@ NXD_DEVICE void tcgen05_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Warp-uniform issue helpers: the whole MMA warp runs the issue loop in convergent control flow and one elected lane
+// executes the tcgen05 instruction.  (Issuing from inside `if (lane == 0)` makes the compiler wrap every UTCHMMA in an
+// ELECT / BRA.U.ANY loop with R2UR round trips — ≈19 SASS instructions and ≈100 cycles per MMA, which made the single
+// issuing thread the bottleneck of the backward kernel: ncu source page, profiles/.)
+NXD_DEVICE void mma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+NXD_DEVICE void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+NXD_DEVICE void commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar) : "memory");
 }
 NXD_DEVICE void tcgen05_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -72,6 +101,13 @@ NXD_DEVICE float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): halves the issue slots of the softmax element math
+NXD_DEVICE uint64_t pack2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+NXD_DEVICE uint64_t pack2u(uint32_t a, uint32_t b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+NXD_DEVICE void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+NXD_DEVICE uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+NXD_DEVICE uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+NXD_DEVICE uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 NXD_DEVICE uint32_t pack_bf16(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -90,15 +126,32 @@ struct FwdParams {
   float* lse;                 // [B, H, S_q]
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+// exp2 on the FMA pipe (Cody–Waite split + degree-3 minimax on [-0.5, 0.5], rel. error ≈ 1e-4 — far below bf16's 4e-3):
+// the MUFU unit does 4 lanes/clk/SMSP, so a 128-wide row costs 1024 MUFU cycles per warp; moving ~30 % of the elements
+// here balances MUFU time against issue slots.
+NXD_DEVICE float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                   // 1.5·2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);             // f ∈ [-0.5, 0.5]
+  float pz = fmaf(f, 0.0550087f, 0.2422104f);      // minimax fit of 2^f, max rel. error 1.0e-4
+  pz = fmaf(pz, f, 0.6932829f);
+  pz = fmaf(pz, f, 1.0f);
+  return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
+}
+
+// One CTA per SM.  TMEM: S double buffer [0,256) (P_j is written over S_j in place), O [256,384).  Tensor-pipe order is
+// S_0 S_1 PV_0 S_2 PV_1 S_3 …: the QKᵀ of tile j+1 and the PV of tile j-1 run while the softmax warps work on tile j, so
+// the softmax (MUFU-bound) is the only serial chain and the tensor core is hidden behind it.
+__global__ void __launch_bounds__(kThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
               const __grid_constant__ CUtensorMap tv, __nv_bfloat16* __restrict__ out, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base, sK = smem_base + kTile, sV = smem_base + 2 * kTile;
-  const uint32_t bars = smem_base + 3 * kTile;
-  const uint32_t bar_q = bars, bar_kf = bars + 8, bar_vf = bars + 16, bar_ke = bars + 24, bar_ve = bars + 32,
-                 bar_s = bars + 40, bar_p = bars + 48, bar_o = bars + 56, tmem_slot = bars + 64;
+  const uint32_t sQ = smem_base, sK = smem_base + kTile, sV = smem_base + 3 * kTile;      // K, V: two stages each
+  const uint32_t bars = smem_base + 5 * kTile;
+  // q | kf[2] | vf[2] | ke[2] | ve[2] | s[2] | p[2] | o | tmem slot
+  const uint32_t bar_q = bars, bar_kf = bars + 8, bar_vf = bars + 24, bar_ke = bars + 40, bar_ve = bars + 56,
+                 bar_s = bars + 72, bar_p = bars + 88, bar_o = bars + 104, tmem_slot = bars + 112;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;    // heavy (late) query tiles first
   const int head = blockIdx.y, b = blockIdx.z;
@@ -107,12 +160,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
   const int n_kv = p.causal ? min(qt + 1, n_tiles_kv) : n_tiles_kv;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_kf, 1); mbar_init(bar_vf, 1); mbar_init(bar_ke, 1); mbar_init(bar_ve, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ke + 8 * i, 1); mbar_init(bar_ve + 8 * i, 1);
+      mbar_init(bar_s + 8 * i, 1); mbar_init(bar_p + 8 * i, 128);
+    }
+    mbar_init(bar_o, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tcgen05_alloc(tmem_slot, 256);
+    tcgen05_alloc(tmem_slot, 512);
     tcgen05_relinquish();
   }
   tcgen05_fence_before();
@@ -120,7 +177,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 256;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -132,44 +189,53 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
       const int kc = b * p.k.col_b + kvh * p.k.col_h, kr = b * p.k.row_b + kvh * p.k.row_h;
       const int vc = b * p.v.col_b + kvh * p.v.col_h, vr = b * p.v.row_b + kvh * p.v.row_h;
       for (int j = 0; j < n_kv; ++j) {
-        const uint32_t ph = (uint32_t)(j & 1);
-        mbar_wait(bar_ke, ph ^ 1);
-        mbar_expect_tx(bar_kf, kTile);
-        tma_load_2d(sK, &tk, bar_kf, kc, kr + j * BN);
-        tma_load_2d(sK + kHalf, &tk, bar_kf, kc + 64, kr + j * BN);
-        mbar_wait(bar_ve, ph ^ 1);
-        mbar_expect_tx(bar_vf, kTile);
-        tma_load_2d(sV, &tv, bar_vf, vc, vr + j * BN);
-        tma_load_2d(sV + kHalf, &tv, bar_vf, vc + 64, vr + j * BN);
+        const int st = j & 1;
+        const uint32_t ph = (uint32_t)((j >> 1) & 1);
+        mbar_wait(bar_ke + 8 * st, ph ^ 1);
+        mbar_expect_tx(bar_kf + 8 * st, kTile);
+        tma_load_2d(sK + st * kTile, &tk, bar_kf + 8 * st, kc, kr + j * BN);
+        tma_load_2d(sK + st * kTile + kHalf, &tk, bar_kf + 8 * st, kc + 64, kr + j * BN);
+        mbar_wait(bar_ve + 8 * st, ph ^ 1);
+        mbar_expect_tx(bar_vf + 8 * st, kTile);
+        tma_load_2d(sV + st * kTile, &tv, bar_vf + 8 * st, vc, vr + j * BN);
+        tma_load_2d(sV + st * kTile + kHalf, &tv, bar_vf + 8 * st, vc + 64, vr + j * BN);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // all 32 lanes run this loop; the helpers elect one lane per tcgen05 instruction
       constexpr uint32_t idesc_s = make_idesc(false, false, BM, BN);
       constexpr uint32_t idesc_o = make_idesc(false, true, BM, HD);
-      mbar_wait(bar_q, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const uint32_t ph = (uint32_t)(j & 1);
-        mbar_wait(bar_kf, ph);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(bar_kf + 8 * st, (uint32_t)((j >> 1) & 1));
         tcgen05_fence_after();
-        // S_j overwrites P_{j-1}; tcgen05.mma ops retire in issue order, so PV_{j-1} has consumed P before this lands
+        const uint32_t k_s = sK + st * kTile;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            tcgen05_mma_f16(tmem_S, make_smem_desc(sQ + kb * kHalf + kk * 32, 16, 1024),
-                            make_smem_desc(sK + kb * kHalf + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
-        tcgen05_commit(bar_ke);
-        tcgen05_commit(bar_s);
-        mbar_wait(bar_p, ph);
-        mbar_wait(bar_vf, ph);
+            mma_ss(tmem_S + st * BN, make_smem_desc(sQ + kb * kHalf + kk * 32, 16, 1024),
+                            make_smem_desc(k_s + kb * kHalf + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
+        commit_elect(bar_ke + 8 * st);
+        commit_elect(bar_s + 8 * st);
+      };
+      mbar_wait(bar_q, 0);
+      issue_s(0);
+      if (n_kv > 1) issue_s(1);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (uint32_t)((j >> 1) & 1);
+        mbar_wait(bar_p + 8 * st, ph);
+        mbar_wait(bar_vf + 8 * st, ph);
         tcgen05_fence_after();
+        const uint32_t v_s = sV + st * kTile;
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k)
-          tcgen05_mma_ts(tmem_O, tmem_S + k * 8, make_smem_desc(sV + k * 2048, kHalf, 1024), idesc_o, (j | k) ? 1u : 0u);
-        tcgen05_commit(bar_ve);
-        tcgen05_commit(bar_o);
+          mma_ts(tmem_O, tmem_S + st * BN + k * 8, make_smem_desc(v_s + k * 2048, kHalf, 1024), idesc_o, (j | k) ? 1u : 0u);
+        commit_elect(bar_ve + 8 * st);
+        commit_elect(bar_o);
+        if (j + 2 < n_kv) issue_s(j + 2);      // overwrites P_j — behind PV_j in pipe order
       }
     }
     __syncwarp();
@@ -181,14 +247,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
     const float sl2 = p.scale_log2;
     float m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(bar_s, (uint32_t)(j & 1));
+      const int st = j & 1;
+      const uint32_t tS = tmem_S + st * BN + lane_base;
+      mbar_wait(bar_s + 8 * st, (uint32_t)((j >> 1) & 1));
       tcgen05_fence_after();
       const int kv0 = j * BN;
       const bool masked = (p.causal && kv0 + BN - 1 > qt * BM) || (kv0 + BN > p.S_kv);
       // ---- the whole S row (128 fp32) comes into registers with four back-to-back TMEM loads and one wait
       uint32_t sr[4][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tcgen05_ld_32x32(tmem_S + lane_base + c * 32, sr[c]);
+      for (int c = 0; c < 4; ++c) tcgen05_ld_32x32(tS + c * 32, sr[c]);
       tcgen05_wait_ld();
       if (masked) {      // diagonal / ragged tile: −inf in place, the exp below turns it into an exact 0
 #pragma unroll
@@ -211,7 +279,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         const float m_new = fmaxf(m_ref, mx);
         const bool need = (m_new - m_ref) * sl2 > 8.f;
         if (__any_sync(0xffffffffu, need)) {
-          // S_j ready ⇒ PV_{j-1} retired (commit covers all earlier MMAs), so O is quiescent here
+          mbar_wait(bar_o, (uint32_t)((j - 1) & 1));      // PV_{j-1} retired: O is quiescent
+          tcgen05_fence_after();
           const float f = need ? ex2((m_ref - m_new) * sl2) : 1.f;
           if (need) m_ref = m_new;
           l *= f;
@@ -228,22 +297,31 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
       }
       // ---- P = exp2(s·scale·log2e − m_ref·scale·log2e), packed to bf16 in place and written over the S columns
       const float mb = m_ref * sl2;
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint64_t sl2_2 = pack2(sl2, sl2), nmb_2 = pack2(-mb, -mb);
+      uint64_t l2acc[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(sr[c][i]), sl2, -mb));
-          const float p1 = ex2(fmaf(__uint_as_float(sr[c][i + 1]), sl2, -mb));
-          l4[c] += p0 + p1;
+          float x0, x1;
+          unpack2(fma2(pack2u(sr[c][i], sr[c][i + 1]), sl2_2, nmb_2), x0, x1);
+          // kPolyPairs of every 8 pairs take the FMA-pipe exp2; 0 = all on MUFU (a lone warp per SMSP is issue-bound, not
+          // MUFU-bound, once the polynomial's 8 extra instructions are counted — measured, see profiles/)
+          const bool poly = ((i >> 1) & 7) < kPolyPairs;
+          const float p0 = poly ? ex2_poly(x0) : ex2(x0);
+          const float p1 = poly ? ex2_poly(x1) : ex2(x1);
+          l2acc[c] = add2(l2acc[c], pack2(p0, p1));
           sr[c][i >> 1] = pack_bf16(p0, p1);
         }
-        tcgen05_st_32x16p(tmem_S + lane_base + c * 16, sr[c]);
+        tcgen05_st_32x16p(tS + c * 16, sr[c]);
       }
+      float l4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { float a, bq; unpack2(l2acc[c], a, bq); l4[c] = a + bq; }
       l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       tcgen05_wait_st();
       tcgen05_fence_before();
-      mbar_arrive(bar_p);
+      mbar_arrive(bar_p + 8 * st);
     }
     // ---- epilogue: O / l → bf16, LSE
     mbar_wait(bar_o, (uint32_t)((n_kv - 1) & 1));
@@ -272,9 +350,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tcgen05_dealloc(tmem_base, 256);
+  if (warp == 1) tcgen05_dealloc(tmem_base, 512);
 }
-
 
 // ====================================================================================================================
 // Backward.  One CTA per (128-row KV tile, kv head, batch); it keeps K/V resident in smem and dK/dV resident in TMEM and
@@ -303,7 +380,7 @@ struct BwdParams {
   long dk_sb, dk_ss, dk_sh, dv_sb, dv_ss, dv_sh;
   float scale, scale_log2;
   int causal;
-  const float* stats;          // [2][B*H*S_pad (+pad)] : lse·log2e , δ·scale
+  const float* stats;          // [2][B*H*S_pad (+pad)] : −lse·log2e , −δ·scale
   long stats_stride;
   float* dq_acc;               // [B, H, S_pad, 128] fp32
   int debug;                   // NXD_FA_DEBUG bits (perf triage only): 1 no bulk reduce, 2 no dQ staging, 4 no softmax math
@@ -322,6 +399,47 @@ NXD_DEVICE void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 
 NXD_DEVICE void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 NXD_DEVICE void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 NXD_DEVICE void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Pᵀ = exp2(Sᵀ·c − lse₂[q]) and dSᵀ = Pᵀ ∘ (dPᵀ·scale − δ[q]·scale) for one thread's kv row × 64 q columns; both are packed
+// to bf16 in place (element pair (i, i+1) → register i/2).  MASKED is hoisted to a template parameter so the common tile
+// has no per-element branches.
+template <bool MASKED>
+NXD_DEVICE void bwd_tile_math(uint32_t (&sv)[2][32], uint32_t (&dpv)[2][32], uint32_t stats_s, float sl2, float sc, int kv,
+                              int q0, int S_q, int S_kv, int causal) {
+  const uint64_t sl2_2 = pack2(sl2, sl2), sc_2 = pack2(sc, sc);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 l2, dl;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(l2.x), "=f"(l2.y), "=f"(l2.z), "=f"(l2.w)
+                   : "r"(stats_s + (h * 32 + i) * 4));
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(dl.x), "=f"(dl.y), "=f"(dl.z), "=f"(dl.w)
+                   : "r"(stats_s + 256 + (h * 32 + i) * 4));
+      // stats hold −lse·log2e and −δ·scale, so both affine steps are single packed FMAs
+      const uint64_t nl2[2] = {pack2(l2.x, l2.y), pack2(l2.z, l2.w)}, ndl[2] = {pack2(dl.x, dl.y), pack2(dl.z, dl.w)};
+      float pv[4], dsv[4];
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) {
+        float x0, x1;
+        unpack2(fma2(pack2u(sv[h][i + 2 * e2], sv[h][i + 2 * e2 + 1]), sl2_2, nl2[e2]), x0, x1);
+        float p0 = ex2(x0), p1 = ex2(x1);
+        float d0, d1;
+        unpack2(mul2(pack2(p0, p1), fma2(pack2u(dpv[h][i + 2 * e2], dpv[h][i + 2 * e2 + 1]), sc_2, ndl[e2])), d0, d1);
+        if constexpr (MASKED) {
+          const int q = q0 + h * 32 + i + 2 * e2;
+          const bool ok0 = kv < S_kv && q < S_q && (!causal || kv <= q);
+          const bool ok1 = kv < S_kv && q + 1 < S_q && (!causal || kv <= q + 1);
+          p0 = ok0 ? p0 : 0.f; d0 = ok0 ? d0 : 0.f;      // selects, not branches; also kills NaN padding
+          p1 = ok1 ? p1 : 0.f; d1 = ok1 ? d1 : 0.f;
+        }
+        pv[2 * e2] = p0; pv[2 * e2 + 1] = p1; dsv[2 * e2] = d0; dsv[2 * e2 + 1] = d1;
+      }
+      sv[h][i >> 1] = pack_bf16(pv[0], pv[1]);      sv[h][(i >> 1) + 1] = pack_bf16(pv[2], pv[3]);
+      dpv[h][i >> 1] = pack_bf16(dsv[0], dsv[1]);   dpv[h][(i >> 1) + 1] = pack_bf16(dsv[2], dsv[3]);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreadsBwd, 1)
 fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
@@ -394,7 +512,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && n_iter > 0) {
+    if (n_iter > 0) {   // all 32 lanes run the issue loop; one elected lane executes each tcgen05 instruction
       constexpr uint32_t idesc_s = make_idesc(false, false, 128, BQ);      // Sᵀ, dPᵀ
       constexpr uint32_t idesc_acc = make_idesc(false, true, 128, HD);     // dK, dV
       constexpr uint32_t idesc_dq = make_idesc(true, true, 128, BQ);       // dQᵀ
@@ -411,9 +529,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            tcgen05_mma_f16(tmem_ST + st * BQ, make_smem_desc(sK + kb * kHalf + kk * 32, 16, 1024),
+            mma_ss(tmem_ST + st * BQ, make_smem_desc(sK + kb * kHalf + kk * 32, 16, 1024),
                             make_smem_desc(q_s + kb * (kQTile / 2) + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
-        tcgen05_commit(bar_s + 8 * st);
+        commit_elect(bar_s + 8 * st);
       };
       auto issue_dp = [&](int it) {
         const int qs = it % kQStages;
@@ -424,9 +542,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            tcgen05_mma_f16(tmem_dP, make_smem_desc(sV + kb * kHalf + kk * 32, 16, 1024),
+            mma_ss(tmem_dP, make_smem_desc(sV + kb * kHalf + kk * 32, 16, 1024),
                             make_smem_desc(g_s + kb * (kQTile / 2) + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
-        tcgen05_commit(bar_dp);
+        commit_elect(bar_dp);
       };
       issue_st(0);
       issue_dp(0);
@@ -439,25 +557,25 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         const uint32_t q_s = sQ + qs * kQTile, g_s = sdO + qs * kQTile, ds_s = sdS + st * kQTile;
 #pragma unroll
         for (int kk = 0; kk < BQ / 16; ++kk)
-          tcgen05_mma_f16(tmem_dK, make_smem_desc(ds_s + kk * 32, 16, 1024), make_smem_desc(q_s + kk * 2048, kQTile / 2, 1024),
+          mma_ss(tmem_dK, make_smem_desc(ds_s + kk * 32, 16, 1024), make_smem_desc(q_s + kk * 2048, kQTile / 2, 1024),
                           idesc_acc, (it | kk) ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < BQ / 16; ++kk)
-          tcgen05_mma_ts(tmem_dV, tmem_ST + st * BQ + kk * 8, make_smem_desc(g_s + kk * 2048, kQTile / 2, 1024), idesc_acc,
+          mma_ts(tmem_dV, tmem_ST + st * BQ + kk * 8, make_smem_desc(g_s + kk * 2048, kQTile / 2, 1024), idesc_acc,
                          (it | kk) ? 1u : 0u);
-        tcgen05_commit(bar_qe + 8 * qs);
+        commit_elect(bar_qe + 8 * qs);
         if (it >= 1) {
           mbar_wait(bar_dqr, (uint32_t)((it - 1) & 1));   // dQᵀ_{it-1} has been read out of TMEM
           tcgen05_fence_after();
         }
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk)
-          tcgen05_mma_f16(tmem_dQ, make_smem_desc(sK + kk * 2048, kHalf, 1024), make_smem_desc(ds_s + kk * 2048, kHalf, 1024),
+          mma_ss(tmem_dQ, make_smem_desc(sK + kk * 2048, kHalf, 1024), make_smem_desc(ds_s + kk * 2048, kHalf, 1024),
                           idesc_dq, kk ? 1u : 0u);
-        tcgen05_commit(bar_dq);
+        commit_elect(bar_dq);
         if (it + 2 < n_iter) issue_st(it + 2);            // overwrites Pᵀ_it — after dV_it in pipe order
       }
-      tcgen05_commit(bar_acc);
+      commit_elect(bar_acc);
     }
     __syncwarp();
   } else if (warp < 6) {
@@ -484,33 +602,12 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
       tcgen05_ld_32x32(tmem_ST + st * BQ + lane_base + 32, sv[1]);
       tcgen05_ld_32x32(tmem_dP + lane_base + 32, dpv[1]);
       tcgen05_wait_ld();
+      if (!(p.debug & 4)) {
+        if (masked) bwd_tile_math<true>(sv, dpv, stats_s, sl2, sc, kv, q0, p.S_q, p.S_kv, p.causal);
+        else bwd_tile_math<false>(sv, dpv, stats_s, sl2, sc, kv, q0, p.S_q, p.S_kv, p.causal);
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        if (!(p.debug & 4))
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float4 l2, dl;
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(l2.x), "=f"(l2.y), "=f"(l2.z), "=f"(l2.w)
-                       : "r"(stats_s + (h * 32 + i) * 4));
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(dl.x), "=f"(dl.y), "=f"(dl.z), "=f"(dl.w)
-                       : "r"(stats_s + 256 + (h * 32 + i) * 4));
-          const float l2a[4] = {l2.x, l2.y, l2.z, l2.w}, dla[4] = {dl.x, dl.y, dl.z, dl.w};
-          float pv[4], dsv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float pe = ex2(fmaf(__uint_as_float(sv[h][i + e]), sl2, -l2a[e]));
-            float de = pe * fmaf(__uint_as_float(dpv[h][i + e]), sc, -dla[e]);
-            if (masked) {
-              const int q = q0 + h * 32 + i + e;
-              if (!(kv < p.S_kv && q < p.S_q && (!p.causal || kv <= q))) { pe = 0.f; de = 0.f; }   // also kills NaN padding
-            }
-            pv[e] = pe;
-            dsv[e] = de;
-          }
-          // packed in place: element pair (i, i+1) → register i/2 (already consumed)
-          sv[h][i >> 1] = pack_bf16(pv[0], pv[1]);      sv[h][(i >> 1) + 1] = pack_bf16(pv[2], pv[3]);
-          dpv[h][i >> 1] = pack_bf16(dsv[0], dsv[1]);   dpv[h][(i >> 1) + 1] = pack_bf16(dsv[2], dsv[3]);
-        }
         tcgen05_st_32x16p(tmem_ST + st * BQ + lane_base + h * 16, sv[h]);
         // dSᵀ row → smem, 128B-swizzled: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
 #pragma unroll
@@ -619,8 +716,8 @@ __global__ void fa_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __
   acc = warp_sum(acc);
   if (lane == 0) {
     const long idx = ((long)b * H + h) * S_pad + s;
-    stats[idx] = lse[((long)b * H + h) * S + s] * 1.4426950408889634f;
-    stats[stats_stride + idx] = acc * scale;
+    stats[idx] = -lse[((long)b * H + h) * S + s] * 1.4426950408889634f;
+    stats[stats_stride + idx] = -acc * scale;
   }
 }
 
