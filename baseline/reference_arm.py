@@ -153,7 +153,7 @@ def main(args) -> int:
     opt = nxd.initialize_parallel_optimizer(cfg, AdamW_FP32OptimParams, model.parameters(), lr=3e-4, betas=(0.9, 0.95),
                                             weight_decay=0.1)
     gbs = args.global_batch
-    mbs = getattr(args, "micro_batch", 0) or {1: 1, 2: 1, 4: 2, 8: 4}.get(args.gpus, 1)   # same rule as the other arm
+    mbs = getattr(args, "micro_batch", 0) or {1: 2, 2: 2, 4: 4, 8: 4}.get(args.gpus, 1)   # same rule as the other arm
     mbs = max(1, min(mbs, gbs))
     while gbs % mbs:
         mbs -= 1

@@ -9,6 +9,9 @@
 //   warps 2-5 epilogue   (both)
 #include <cuda.h>
 
+#include <cstdlib>
+#include <string>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "sm100_ptx.cuh"
@@ -261,6 +264,7 @@ struct TpComm {
   uint32_t* tile_done;
   uint32_t* gemm_done;
   uint32_t gemm_done_target;
+  int push_tma;            // 1: pushers move data with TMA bulk copies through smem; 0: register-staged 16-byte copies
 };
 constexpr int kMaxRowBlocks = 64;
 
@@ -303,6 +307,40 @@ NXD_DEVICE void cta_copy16(uint8_t* dst, const uint8_t* src, size_t bytes) {
   for (; i < nvec; i += kThreads) d4[i] = s4[i];
 }
 
+// TMA push: one thread streams `bytes` (multiple of 16) from local global memory to a peer address through this CTA's
+// (otherwise idle) GEMM smem ring: cp.async.bulk global→smem (mbarrier completion) then smem→peer-global (bulk group).
+// Five 32 KB loads and one or two stores are in flight per CTA without using a single data register, which is what the
+// register-staged copy (48 KB in flight, one fence per block) could not do.  `phases` carries the ring's barrier parities
+// across calls.  Barriers: the comm CTA borrows bar_empty[] (count 1) of the GEMM pipeline it never runs.
+NXD_DEVICE void tma_push(uint8_t* dst, const uint8_t* src, size_t bytes, uint32_t smem_base, uint32_t bar0, uint32_t& phases) {
+  constexpr uint32_t CH = (uint32_t)kStageBytes;
+  constexpr int NST = kStages;
+  const int n = (int)((bytes + CH - 1) / CH);
+  auto chunk_bytes = [&](int c) { return (uint32_t)min((size_t)CH, bytes - (size_t)c * CH); };
+  auto load = [&](int c) {
+    const int st = c % NST;
+    const uint32_t b = bar0 + 8 * st, nb = chunk_bytes(c);
+    mbar_expect_tx(b, nb);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_base + st * CH), "l"(src + (size_t)c * CH), "r"(nb), "r"(b) : "memory");
+  };
+  for (int c = 0; c < n && c < NST; ++c) load(c);
+  for (int c = 0; c < n; ++c) {
+    const int st = c % NST;
+    mbar_wait(bar0 + 8 * st, (phases >> st) & 1u);
+    phases ^= 1u << st;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst + (size_t)c * CH), "r"(smem_base + st * CH), "r"(chunk_bytes(c)) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (c >= 1 && c - 1 + NST < n) {
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // store c-1 has drained its stage
+      load(c - 1 + NST);
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
 template <bool A_KMAJOR, bool B_KMAJOR, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -343,6 +381,7 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (is_comm) {
+    uint32_t push_phases = 0;
     if constexpr (MODE == 1) {
       // ---- all-gather pusher: (destination step, 128-row block) items.  The local chunk is NOT copied: GEMM tiles of
       //      the own chunk read the shard in place through `tma_a_local` and start immediately. -------------------
@@ -354,11 +393,19 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         const uint8_t* src = (const uint8_t*)comm.a_local + (size_t)mb * blk_bytes;
         uint8_t* d = (uint8_t*)comm.peer_bufs[dst] + comm.buf_offset +
                      ((size_t)comm.rank * blk128_per_rank + mb) * blk_bytes;
-        cta_copy16(d, src, blk_bytes);
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0)
-          st_release_sys((uint32_t*)comm.peer_flags[dst] + comm.flag_offset + comm.rank * kMaxRowBlocks + mb, comm.epoch);
+        if (comm.push_tma) {
+          if (threadIdx.x == 0) {
+            tma_push(d, src, blk_bytes, smem_base, bar_empty, push_phases);
+            __threadfence_system();
+            st_release_sys((uint32_t*)comm.peer_flags[dst] + comm.flag_offset + comm.rank * kMaxRowBlocks + mb, comm.epoch);
+          }
+        } else {
+          cta_copy16(d, src, blk_bytes);
+          __threadfence_system();
+          __syncthreads();
+          if (threadIdx.x == 0)
+            st_release_sys((uint32_t*)comm.peer_flags[dst] + comm.flag_offset + comm.rank * kMaxRowBlocks + mb, comm.epoch);
+        }
       }
     } else {
       // ---- reduce-scatter pusher: ship finished row blocks of remote chunks to their owners -------------------
@@ -372,15 +419,24 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           while (ld_acquire_gpu(comm.tile_done + gblk) < (uint32_t)tiles_n) __nanosleep(128);
           comm.tile_done[gblk] = 0;                                    // single consumer: re-arm for the next call
         }
-        __syncthreads();
         const uint8_t* src = (const uint8_t*)out + (size_t)gblk * blk_bytes;
         uint8_t* d = (uint8_t*)comm.peer_bufs[owner] + comm.buf_offset +
                      ((size_t)comm.rank * blk128_per_rank + mb) * blk_bytes;
-        cta_copy16(d, src, blk_bytes);
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0)
-          st_release_sys((uint32_t*)comm.peer_flags[owner] + comm.flag_offset + comm.rank * kMaxRowBlocks + mb, comm.epoch);
+        if (comm.push_tma) {
+          if (threadIdx.x == 0) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");    // epilogue (generic) writes → TMA (async proxy) reads
+            tma_push(d, src, blk_bytes, smem_base, bar_empty, push_phases);
+            __threadfence_system();
+            st_release_sys((uint32_t*)comm.peer_flags[owner] + comm.flag_offset + comm.rank * kMaxRowBlocks + mb, comm.epoch);
+          }
+        } else {
+          __syncthreads();
+          cta_copy16(d, src, blk_bytes);
+          __threadfence_system();
+          __syncthreads();
+          if (threadIdx.x == 0)
+            st_release_sys((uint32_t*)comm.peer_flags[owner] + comm.flag_offset + comm.rank * kMaxRowBlocks + mb, comm.epoch);
+        }
       }
     }
   } else if (warp == 0) {
@@ -640,6 +696,7 @@ void gemm_bf16_2cta_tp(int mode, const void* a, const void* b, void* out_or_part
   c.buf_offset = buf_offset; c.flag_offset = flag_offset; c.epoch = epoch; c.comm_ctas = comm_ctas;
   c.rows_per_rank = M / world; c.a_local = a_local; c.rs_out = rs_out; c.tile_done = tile_done; c.gemm_done = gemm_done;
   c.gemm_done_target = gemm_done_target;
+  { const char* e = getenv("NXD_TP_PUSH"); c.push_tma = (e && std::string(e) == "ldst") ? 0 : 1; }   // re-read per call (sweeps)
   if (M % world || c.rows_per_rank % g2::TILE_M || c.rows_per_rank / g2::CTA_M > g2::kMaxRowBlocks)
     nxd_throw("fused TP GEMM (CTA-pair) needs rows/rank to be a multiple of 256 and <= 8192", __FILE__, __LINE__);
   const int grid = (device_sm_count() / 2) * 2;

@@ -78,7 +78,8 @@ def main():
         for M in (4096, 16384):
             if (M // world) % 256 or M // world // 128 > 64:
                 continue
-            for ag, rs in ((12, 16), (24, 24), (32, 32), (48, 48)):
+            for push, ag, rs in (("tma", 8, 8), ("tma", 12, 16), ("tma", 24, 24), ("tma", 32, 32), ("ldst", 12, 16), ("ldst", 32, 32)):
+                os.environ["NXD_TP_PUSH"] = push
                 _fused_impl.CONFIG["comm_ctas_ag"], _fused_impl.CONFIG["comm_ctas_rs"] = ag, rs
                 x = torch.randn(M // world, H, device="cuda", dtype=torch.bfloat16)
                 w = torch.randn(2 * I // world, H, device="cuda", dtype=torch.bfloat16)
@@ -86,11 +87,12 @@ def main():
                 x2 = torch.randn(M, I // world, device="cuda", dtype=torch.bfloat16)
                 w2 = torch.randn(H, I // world, device="cuda", dtype=torch.bfloat16)
                 t_rs = timeit(lambda: ws.gemm_rs(x2, w2, True), iters=10, warmup=3)
-                rec = {"sweep": True, "M": M, "comm_ctas_ag": ag, "comm_ctas_rs": rs, "ag_gemm_gate_up_us": t_ag, "gemm_rs_down_us": t_rs}
+                rec = {"sweep": True, "M": M, "push": push, "comm_ctas_ag": ag, "comm_ctas_rs": rs, "ag_gemm_gate_up_us": t_ag, "gemm_rs_down_us": t_rs}
                 sweep.append(rec)
                 if rank == 0:
                     print(json.dumps(rec), flush=True)
         _fused_impl.CONFIG["comm_ctas_ag"], _fused_impl.CONFIG["comm_ctas_rs"] = 12, 16
+        os.environ["NXD_TP_PUSH"] = "tma"
         res.append({"sweep": sweep})
     # raw collectives for reference
     x = torch.randn(S // world, H, device="cuda", dtype=torch.bfloat16)
