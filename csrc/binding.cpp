@@ -143,6 +143,42 @@ static void gemm_fp8(const Tensor& a, const Tensor& b, Tensor out, const Tensor&
                 stream());
 }
 
+// ---- decode ---------------------------------------------------------------------------------------
+// q [B,1,H,128]; k/v cache [B,L,Hkv,128] (any b/s/h strides, head_dim contiguous); positions [B] int64 (attend to ≤ pos)
+static Tensor decode_attention(const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& positions, double scale) {
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && q.dim() == 4 && q.size(1) == 1 && q.size(3) == 128 && q.stride(3) == 1);
+  TORCH_CHECK(k.scalar_type() == at::kBFloat16 && k.dim() == 4 && k.size(3) == 128 && k.stride(3) == 1 && v.stride(3) == 1 &&
+              v.sizes() == k.sizes());
+  TORCH_CHECK(positions.scalar_type() == at::kLong && positions.is_cuda() && positions.is_contiguous() && positions.numel() == q.size(0));
+  const int B = q.size(0), H = q.size(2), L = k.size(1), Hkv = k.size(2);
+  TORCH_CHECK(H % Hkv == 0 && k.size(0) == B);
+  TORCH_CHECK(q.stride(2) % 8 == 0 && k.stride(1) % 8 == 0 && k.stride(2) % 8 == 0 && v.stride(1) % 8 == 0 && v.stride(2) % 8 == 0);
+  c10::cuda::CUDAGuard guard(q.device());
+  int splits = (2 * 148 + B * Hkv - 1) / (B * Hkv);
+  splits = std::max(1, std::min(std::min(splits, 32), (L + 127) / 128));
+  Tensor out = at::empty({B, 1, H, 128}, q.options());
+  Tensor part_o = at::empty({B * H * splits, 128}, q.options().dtype(at::kFloat));
+  Tensor part_ml = at::empty({B * H * splits, 2}, q.options().dtype(at::kFloat));
+  const long ks[3] = {k.stride(0), k.stride(1), k.stride(2)}, vs[3] = {v.stride(0), v.stride(1), v.stride(2)};
+  nxd::decode_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), positions.data_ptr<long>(), out.data_ptr(),
+                        part_o.data_ptr<float>(), part_ml.data_ptr<float>(), B, H, Hkv, L, ks, vs, q.stride(0), q.stride(2),
+                        out.stride(0), out.stride(2), (float)scale, splits, stream());
+  return out;
+}
+static Tensor gemv(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& residual) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && x.dim() == 2 && w.dim() == 2);
+  TORCH_CHECK(x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1) && x.size(0) >= 1 && x.size(0) <= 8 && x.size(1) % 8 == 0);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor y = at::empty({x.size(0), w.size(0)}, x.options());
+  const void* res = nullptr;
+  if (residual.has_value()) {
+    TORCH_CHECK(residual->is_contiguous() && residual->sizes() == y.sizes() && residual->scalar_type() == at::kBFloat16);
+    res = residual->data_ptr();
+  }
+  nxd::gemv_bf16(x.data_ptr(), w.data_ptr(), res, y.data_ptr(), x.size(0), w.size(0), x.size(1), stream());
+  return y;
+}
+
 // ---- grouped (MoE) GEMMs -------------------------------------------------------------------------
 static Tensor grouped_gemm(const Tensor& a, const Tensor& w, const Tensor& block_expert, int64_t block_rows, bool trans_b) {
   TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && a.dim() == 2 && a.is_contiguous());
@@ -359,6 +395,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("fused_adamw", &fused_adamw);
   m.def("gemm_bf16", &gemm_bf16);
   m.def("gemm_bf16_2cta", &gemm_bf16_2cta);
+  m.def("decode_attention", &decode_attention);
+  m.def("gemv", &gemv, py::arg("x"), py::arg("w"), py::arg("residual") = py::none());
   m.def("gemm_fp8", &gemm_fp8);
   m.def("grouped_gemm", &grouped_gemm);
   m.def("grouped_wgrad", &grouped_wgrad);

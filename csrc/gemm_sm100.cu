@@ -237,7 +237,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       __syncwarp();
     } else if (warp == 1) {
       // ===== MMA issuer =====
-      if (lane == 0) {
+      {   // whole warp, elected issue (see sm100_ptx.cuh)
         constexpr uint32_t idesc = FP8 ? ((1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24))
                                        : make_idesc(!A_KMAJOR, !B_KMAJOR, BLOCK_M, BLOCK_N);
         int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
@@ -256,13 +256,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               // K-major: advance 32 B inside the 128 B swizzle row; MN-major: 16 k-rows × 128 B = 2 KB
               const uint64_t da = A_KMAJOR ? make_smem_desc(sa + k * 32, 16, 1024) : make_smem_desc(sa + k * 2048, 8192, 1024);
               const uint64_t db = B_KMAJOR ? make_smem_desc(sb + k * 32, 16, 1024) : make_smem_desc(sb + k * 2048, 8192, 1024);
-              if constexpr (FP8) tcgen05_mma_f8(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-              else tcgen05_mma_f16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              if constexpr (FP8) tcgen05_mma_f8_e(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              else tcgen05_mma_f16_e(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            tcgen05_commit(bar_empty + 8 * stage);   // smem stage reusable once these MMAs retire
+            tcgen05_commit_e(bar_empty + 8 * stage);   // smem stage reusable once these MMAs retire
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          tcgen05_commit(bar_tfull + 8 * as);        // accumulator complete
+          tcgen05_commit_e(bar_tfull + 8 * as);        // accumulator complete
           if (++as == kAccStages) { as = 0; aphase ^= 1; }
         }
       }

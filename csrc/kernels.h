@@ -72,6 +72,12 @@ void grouped_gemm_bf16(const void* a, const void* b, void* out, int M, int N, in
 void grouped_wgrad_bf16(const void* a, const void* b, void* out, int rows_total, int Mo, int No, int E,
                         const int* seg_first_block, int block_rows, int out_dt, bool accumulate, cudaStream_t st);
 
+// ---- decode (decode.cu)
+void decode_attention(const void* q, const void* k, const void* v, const long* positions, void* out, float* part_o,
+                      float* part_ml, int B, int H, int Hkv, int L, const long* ks, const long* vs, long q_sb, long q_sh,
+                      long o_sb, long o_sh, float scale, int splits, cudaStream_t st);
+void gemv_bf16(const void* x, const void* w, const void* residual, void* y, int M, int N, int K, cudaStream_t st);
+
 // ---- attention (attention_sm100.cu): q [B,S_q,H,128], k/v [B,S_kv,Hkv,128] bf16 views; strides = (b, s, h) in elements
 void flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int S_q, int S_kv, int H,
                     int Hkv, const long* qs, const long* ks, const long* vs, const long* os, float scale, bool causal,

@@ -17,6 +17,7 @@ import torch
 from torch import nn
 from torch.utils.checkpoint import checkpoint
 
+from ..utils.profiling import nvtx_range
 from .. import ops
 from ..modules.qkv_linear import GQAQKVColumnParallelLinear
 from ..modules.rms_norm import RMSNorm
@@ -157,8 +158,10 @@ class LlamaDecoderLayer(nn.Module):
         self.mlp = LlamaMLP(cfg)
 
     def forward(self, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
-        x = x + self.self_attn(self.input_layernorm(x), cos, sin)
-        x = x + self.mlp(self.post_attention_layernorm(x))
+        with nvtx_range("attn"):
+            x = x + self.self_attn(self.input_layernorm(x), cos, sin)
+        with nvtx_range("mlp"):
+            x = x + self.mlp(self.post_attention_layernorm(x))
         return x
 
 

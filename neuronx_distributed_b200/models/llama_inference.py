@@ -123,6 +123,12 @@ def _decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, positio
     """q [B,1,H,D] vs cache k/v [B,L,Hkv,D]; keys beyond each sequence's position are masked."""
     B, _, H, D = q.shape
     Hkv, L = k.shape[2], k.shape[1]
+    e = ops._ext.ext() if q.is_cuda else None
+    if (e is not None and hasattr(e, "decode_attention") and D == 128 and q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16
+            and H // Hkv in (1, 2, 4, 8) and k.stride(3) == 1 and v.stride(3) == 1):
+        # flash-decoding kernel (csrc/decode.cu): split over the cache length, GQA group shares each K/V read
+        ops._ext.count_launch(2)
+        return e.decode_attention(q.contiguous(), k, v, positions.to(torch.long).contiguous(), 1.0 / math.sqrt(D))
     qt = q.transpose(1, 2)                                   # [B,H,1,D]
     kt, vt = k.transpose(1, 2), v.transpose(1, 2)
     if H != Hkv:

@@ -34,8 +34,19 @@ _FLAGS_RS2 = 3072
 _NFLAGS = 4096
 _COMM_SMS = int(os.environ.get("NXD_AG_COMM_SMS", "16"))
 # CTAs (out of 148) that only move data inside the fused kernels; even numbers (CTA pairs).  Mutable so benchmarks can sweep.
-CONFIG = {"comm_ctas_ag": int(os.environ.get("NXD_TP_COMM_CTAS_AG", "12")),
-          "comm_ctas_rs": int(os.environ.get("NXD_TP_COMM_CTAS_RS", "16"))}
+# Measured at TP=8 (profiles/tp_bench_tp8.json sweep): 12/16 is best for a 4096-row call, 24/24 for 16384 rows (the call is
+# NVLink-bound there and the TMA pushers need more CTAs to fill the links); 0 = pick by size.
+CONFIG = {"comm_ctas_ag": int(os.environ.get("NXD_TP_COMM_CTAS_AG", "0")),
+          "comm_ctas_rs": int(os.environ.get("NXD_TP_COMM_CTAS_RS", "0"))}
+
+
+def _comm_ctas(kind: str, rows: int) -> int:
+    v = CONFIG["comm_ctas_" + kind]
+    if v > 0:
+        return v
+    if rows >= 8192:
+        return 24
+    return 12 if kind == "ag" else 16
 _USE_2CTA_TP = os.environ.get("NXD_TP_2CTA", "1") == "1"
 TILE_M2 = 256
 
@@ -86,16 +97,30 @@ class TPWorkspace:
         _ext.count_launch()
         if _USE_2CTA_TP and ms % TILE_M2 == 0 and out_dtype == torch.bfloat16 and hasattr(_ext.ext(), "tp_gemm_2cta"):
             _ext.ext().tp_gemm_2cta(1, a_shard, b, out, out, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs,
-                                    off, _FLAGS_AG, self.ag_epoch, self.rank, self.world, CONFIG["comm_ctas_ag"], self.counters, 0)
+                                    off, _FLAGS_AG, self.ag_epoch, self.rank, self.world, _comm_ctas("ag", M), self.counters, 0)
             # the kernel reads the own shard in place (no local copy); complete the gathered view for wgrad consumers
             gathered = self.ws.local_tensor(off, (M, K), torch.bfloat16)
             gathered[self.rank * ms:(self.rank + 1) * ms].copy_(a_shard)
+            self._poison((1 - (self.ag_epoch & 1)) * self.ag_bytes, self.ag_bytes)
             return out, gathered
         else:
             _ext.ext().ag_gemm_bf16(a_shard, b, out, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs, off,
                                     _FLAGS_AG, self.ag_epoch, self.rank, self.world, _COMM_SMS)
         gathered = self.ws.local_tensor(off, (M, K), torch.bfloat16)
         return out, gathered
+
+    def _poison(self, off: int, nbytes: int) -> None:
+        """NXD_SYMM_POISON=1: NaN-fill the payload half that is NOT live, so any read of stale-epoch data shows up as NaN.
+        Safe with respect to peers: a rank only reaches call n+1 (which writes that half on its peers) after every peer has
+        finished call n-1, and the fill is stream-ordered before this rank's own call n+1."""
+        from ..utils.profiling import poison_enabled
+
+        if poison_enabled() and self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)       # debug mode: make the fill race-free by construction
+            self.ws.local_tensor(off, (nbytes // 2,), torch.bfloat16).fill_(float("nan"))
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
 
     # ------------------------------------------------------------------ GEMM → reduce-scatter
     def gemm_rs(self, a: torch.Tensor, b: torch.Tensor, trans_b: bool) -> torch.Tensor:
@@ -109,13 +134,14 @@ class TPWorkspace:
             if self.partial is None or self.partial.numel() < M * N:
                 self.partial = torch.empty(M * N, dtype=torch.bfloat16, device=a.device)
             partial = self.partial[: M * N].view(M, N)
-            comm_ctas = CONFIG["comm_ctas_rs"]
+            comm_ctas = _comm_ctas("rs", M)
             self.gemm_done_total = (self.gemm_done_total + 2 * self.sm_pairs - comm_ctas) & 0xFFFFFFFF
             out = torch.empty(ms, N, dtype=torch.bfloat16, device=a.device)
             _ext.count_launch()
             _ext.ext().tp_gemm_2cta(2, a, b, out, partial, trans_b, self.ws.local_ptr, self.ws.ptrs, self.ws.flag_ptrs, off,
                                     _FLAGS_RS2, self.rs2_calls, self.rank, self.world, comm_ctas, self.counters,
                                     self.gemm_done_total)
+            self._poison(2 * self.ag_bytes + (1 - (self.rs2_calls & 1)) * self.rs_bytes, self.rs_bytes)
             return out
         self.rs_calls += 1
         off = 2 * self.ag_bytes + (self.rs_calls & 1) * self.rs_bytes

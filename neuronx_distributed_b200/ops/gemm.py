@@ -44,6 +44,12 @@ def matmul(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: boo
     K = a.shape[0] if trans_a else a.shape[1]
     N = b.shape[0] if trans_b else b.shape[1]
     out_dtype = out_dtype or (out.dtype if out is not None else a.dtype)
+    if (M <= 8 and not trans_a and trans_b and out is None and out_dtype == torch.bfloat16 and a.is_cuda
+            and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and K % 8 == 0 and a.is_contiguous() and b.is_contiguous()
+            and _ext.ext() is not None and hasattr(_ext.ext(), "gemv") and os.environ.get("NXD_DISABLE_TCGEN05_GEMM", "0") != "1"):
+        # decode-time GEMV: a bandwidth problem (every weight byte read once), not a tensor-core one — csrc/decode.cu
+        _ext.count_launch()
+        return _ext.ext().gemv(a, b, None)
     if _eligible(a, b, M, N, K) and out_dtype in (torch.bfloat16, torch.float32):
         if out is None:
             out = torch.empty(M, N, dtype=out_dtype, device=a.device)

@@ -21,6 +21,7 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
+from ..utils.profiling import nvtx_range
 from ..parallel_layers import comm as pl_comm
 from ..parallel_layers import grads as pl_grads
 from ..parallel_layers import parallel_state as ps
@@ -372,7 +373,13 @@ class NxDPPModel(nn.Module):
             self._flush(batch)
             return self._reduce_grads()
         name = type(task).__name__
-        self.timeline.mark_event_start(f"{name}_mb{task.mb}_c{task.model_chunk}")
+        label = f"{name}_mb{task.mb}_c{task.model_chunk}"
+        self.timeline.mark_event_start(label)
+        with nvtx_range(label):
+            self._dispatch_task(task, batch)
+        self.timeline.mark_event_end(label)
+
+    def _dispatch_task(self, task, batch: P2PBatch) -> None:
         if isinstance(task, ForwardPreprocessTask):
             self._fwd_pre(task, batch)
         elif isinstance(task, ForwardStepTask):
@@ -387,7 +394,6 @@ class NxDPPModel(nn.Module):
             self._bwd_step(task)
         elif isinstance(task, BackwardPostprocessTask):
             self._bwd_post(task, batch)
-        self.timeline.mark_event_end(f"{name}_mb{task.mb}_c{task.model_chunk}")
 
     def _flush(self, batch: P2PBatch) -> None:
         recv_works, send_works = batch.launch()

@@ -44,6 +44,12 @@ def test_tcgen05_gemm_all_layouts(gc):
     _assert_all(gc, n)
 
 
+def test_decode_attention_and_gemv(gc):
+    n = len(gc.RESULTS)
+    gc.check_decode()
+    _assert_all(gc, n)
+
+
 def test_fp8_gemm(gc):
     n = len(gc.RESULTS)
     gc.check_fp8()

@@ -204,6 +204,41 @@ def check_gemm_perf():
                cublas_tflops=fl / t_lib / 1e9)
 
 
+def check_decode(perf=False):
+    """Decode kernels: flash-decoding attention vs fp32 softmax over the valid cache prefix; GEMV vs fp32 matmul."""
+    import math
+    e = ops._ext.ext()
+    torch.manual_seed(0)
+    for (B, L, H, Hkv) in [(1, 300, 8, 8), (3, 2048, 8, 2), (2, 1000, 16, 2), (4, 129, 4, 4)]:
+        D = 128
+        q = torch.randn(B, 1, H, D, device=dev).bfloat16()
+        k = torch.randn(B, L, Hkv, D, device=dev).bfloat16(); v = torch.randn(B, L, Hkv, D, device=dev).bfloat16()
+        pos = torch.randint(0, L, (B,), device=dev)
+        o = e.decode_attention(q, k, v, pos, 1.0 / math.sqrt(D))
+        G = H // Hkv
+        kf, vf = k.float().repeat_interleave(G, 2), v.float().repeat_interleave(G, 2)
+        sc = torch.einsum("bhd,blhd->bhl", q.float()[:, 0], kf) / math.sqrt(D)
+        mask = torch.arange(L, device=dev)[None, None, :] <= pos[:, None, None]
+        ref = torch.einsum("bhl,blhd->bhd", sc.masked_fill(~mask, float("-inf")).softmax(-1), vf)
+        report(f"decode_attn_B{B}_L{L}_H{H}_{Hkv}", relerr(o[:, 0], ref) < 1e-2, err=relerr(o[:, 0], ref))
+    for (M, N, K) in [(1, 4096, 4096), (4, 11008, 4096), (8, 1000, 264), (2, 32000, 5120)]:
+        x = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+        r = torch.randn(M, N, device=dev).bfloat16()
+        y = e.gemv(x, w, r)
+        ref = x.float() @ w.float().t() + r.float()
+        report(f"gemv_{M}x{N}x{K}", relerr(y, ref) < 1e-2, err=relerr(y, ref))
+    if perf:
+        N, K = 13824, 5120
+        x = torch.randn(1, K, device=dev).bfloat16(); w = torch.randn(N, K, device=dev).bfloat16()
+        t = timeit(lambda: e.gemv(x, w, None)); t2 = timeit(lambda: torch.matmul(x, w.t()))
+        report("gemv_perf_13b_mlp", True, own_us=t * 1e3, own_gbs=N * K * 2 / t / 1e6, cublas_us=t2 * 1e3)
+        B, L, H, Hkv = 1, 2048, 40, 40
+        q = torch.randn(B, 1, H, 128, device=dev).bfloat16(); k = torch.randn(B, L, Hkv, 128, device=dev).bfloat16(); v = torch.randn_like(k)
+        pos = torch.full((B,), L - 1, device=dev)
+        t = timeit(lambda: e.decode_attention(q, k, v, pos, 0.088))
+        report("decode_attn_perf_13b", True, own_us=t * 1e3, gbs=2 * L * Hkv * 256 / t / 1e6)
+
+
 def check_fp8(perf=False):
     """fp8 (e4m3) tcgen05 GEMM with row/column scales vs the fp32 product of the same quantised operands."""
     from neuronx_distributed_b200.ops import gemm_fp8
@@ -268,6 +303,8 @@ if __name__ == "__main__":
         check_elementwise()
     if what in ("gemm", "all"):
         check_gemm()
+    if what in ("decode", "all"):
+        check_decode(perf=what == "decode")
     if what in ("fp8", "all"):
         check_fp8(perf=what == "fp8")
     if what in ("grouped", "all"):

@@ -91,7 +91,7 @@ def main():
                 sweep.append(rec)
                 if rank == 0:
                     print(json.dumps(rec), flush=True)
-        _fused_impl.CONFIG["comm_ctas_ag"], _fused_impl.CONFIG["comm_ctas_rs"] = 12, 16
+        _fused_impl.CONFIG["comm_ctas_ag"], _fused_impl.CONFIG["comm_ctas_rs"] = 0, 0
         os.environ["NXD_TP_PUSH"] = "tma"
         res.append({"sweep": sweep})
     # raw collectives for reference
