@@ -143,6 +143,19 @@ static void gemm_fp8(const Tensor& a, const Tensor& b, Tensor out, const Tensor&
                 stream());
 }
 
+static Tensor oneshot_allreduce(const Tensor& x, const Tensor& peer_bufs, const Tensor& peer_flags, int64_t slot_bytes,
+                                Tensor state, int64_t rank, int64_t world) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && (x.scalar_type() == at::kBFloat16 || x.scalar_type() == at::kFloat));
+  const long nbytes = x.numel() * x.element_size();
+  TORCH_CHECK(nbytes % 16 == 0 && nbytes <= slot_bytes && state.scalar_type() == at::kInt && state.numel() >= 2);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = at::empty_like(x);
+  int ctas = (int)std::max<long>(1, std::min<long>(64, nbytes / 16384));
+  nxd::oneshot_allreduce(x.data_ptr(), out.data_ptr(), peer_bufs.data_ptr<int64_t>(), peer_flags.data_ptr<int64_t>(), slot_bytes,
+                         (uint32_t*)state.data_ptr(), (int)rank, (int)world, x.numel(), dt_code(x), ctas, stream());
+  return out;
+}
+
 // ---- decode ---------------------------------------------------------------------------------------
 // q [B,1,H,128]; k/v cache [B,L,Hkv,128] (any b/s/h strides, head_dim contiguous); positions [B] int64 (attend to ≤ pos)
 static Tensor decode_attention(const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& positions, double scale) {
@@ -395,6 +408,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("fused_adamw", &fused_adamw);
   m.def("gemm_bf16", &gemm_bf16);
   m.def("gemm_bf16_2cta", &gemm_bf16_2cta);
+  m.def("oneshot_allreduce", &oneshot_allreduce);
   m.def("decode_attention", &decode_attention);
   m.def("gemv", &gemv, py::arg("x"), py::arg("w"), py::arg("residual") = py::none());
   m.def("gemm_fp8", &gemm_fp8);

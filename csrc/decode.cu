@@ -48,10 +48,17 @@ __global__ void __launch_bounds__(kDecThreads) decode_attn_kernel(
   }
   const __nv_bfloat16* kb = kc + b * k_sb + (long)kvh * k_sh + l16 * 8;
   const __nv_bfloat16* vb = vc + b * v_sb + (long)kvh * v_sh + l16 * 8;
-  for (int s = s0 + warp * 2 + sub; s < s1; s += 8) {
+  for (int sbase = s0 + warp * 2; sbase < s1; sbase += 8) {      // warp-uniform trip count (full-mask shuffles inside)
+    const int s = sbase + sub;
+    const bool live = s < s1;
     float kf[8], vf[8];
-    load8(kb + (long)s * k_ss, kf, 1.f);
-    load8(vb + (long)s * v_ss, vf, 1.f);
+    if (live) {
+      load8(kb + (long)s * k_ss, kf, 1.f);
+      load8(vb + (long)s * v_ss, vf, 1.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
+    }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       float d = 0.f;
@@ -61,12 +68,14 @@ __global__ void __launch_bounds__(kDecThreads) decode_attn_kernel(
       d += __shfl_xor_sync(0xffffffffu, d, 2);
       d += __shfl_xor_sync(0xffffffffu, d, 4);
       d += __shfl_xor_sync(0xffffffffu, d, 8);            // score·log2e of (position s, head g) in all 16 lanes
-      const float mn = fmaxf(m[g], d);
-      const float corr = exp2f(m[g] - mn), p = exp2f(d - mn);
-      m[g] = mn;
-      l[g] = l[g] * corr + p;
+      if (live) {
+        const float mn = fmaxf(m[g], d);
+        const float corr = exp2f(m[g] - mn), p = exp2f(d - mn);
+        m[g] = mn;
+        l[g] = l[g] * corr + p;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[g][i] = fmaf(o[g][i], corr, p * vf[i]);
+        for (int i = 0; i < 8; ++i) o[g][i] = fmaf(o[g][i], corr, p * vf[i]);
+      }
     }
   }
   // merge the 2 position slots of the warp (lanes l16, l16+16), then the 4 warps through smem

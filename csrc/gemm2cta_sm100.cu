@@ -179,7 +179,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
-    if (leader) {   // whole warp, elected issue (see sm100_ptx.cuh)
+    if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc(!A_KMAJOR, !B_KMAJOR, TILE_M, TILE_N);
       int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -194,12 +194,12 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t da = A_KMAJOR ? make_smem_desc(sa + k * 32, 16, 1024) : make_smem_desc(sa + k * 2048, 8192, 1024);
             const uint64_t db = B_KMAJOR ? make_smem_desc(sb + k * 32, 16, 1024) : make_smem_desc(sb + k * 2048, 8192, 1024);
-            tcgen05_mma_f16_2cta_e(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            tcgen05_mma_f16_2cta(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tcgen05_commit_2cta_e(bar_empty + 8 * stage, 0b11);    // frees the stage in BOTH CTAs
+          tcgen05_commit_2cta(bar_empty + 8 * stage, 0b11);    // frees the stage in BOTH CTAs
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit_2cta_e(bar_tfull + 8 * as, 0b11);         // accumulators ready in both CTAs
+        tcgen05_commit_2cta(bar_tfull + 8 * as, 0b11);         // accumulators ready in both CTAs
         if (++as == kAcc) { as = 0; aphase ^= 1; }
       }
     }
@@ -487,7 +487,7 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (leader) {   // whole warp, elected issue (see sm100_ptx.cuh)
+    if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc(!A_KMAJOR, !B_KMAJOR, TILE_M, TILE_N);
       int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -502,12 +502,12 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t da = A_KMAJOR ? make_smem_desc(sa + k * 32, 16, 1024) : make_smem_desc(sa + k * 2048, 8192, 1024);
             const uint64_t db = B_KMAJOR ? make_smem_desc(sb + k * 32, 16, 1024) : make_smem_desc(sb + k * 2048, 8192, 1024);
-            tcgen05_mma_f16_2cta_e(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            tcgen05_mma_f16_2cta(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tcgen05_commit_2cta_e(bar_empty + 8 * stage, 0b11);
+          tcgen05_commit_2cta(bar_empty + 8 * stage, 0b11);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit_2cta_e(bar_tfull + 8 * as, 0b11);
+        tcgen05_commit_2cta(bar_tfull + 8 * as, 0b11);
         if (++as == kAcc) { as = 0; aphase ^= 1; }
       }
     }

@@ -237,7 +237,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       __syncwarp();
     } else if (warp == 1) {
       // ===== MMA issuer =====
-      {   // whole warp, elected issue (see sm100_ptx.cuh)
+      if (lane == 0) {
         constexpr uint32_t idesc = FP8 ? ((1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24))
                                        : make_idesc(!A_KMAJOR, !B_KMAJOR, BLOCK_M, BLOCK_N);
         int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
@@ -256,13 +256,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               // K-major: advance 32 B inside the 128 B swizzle row; MN-major: 16 k-rows × 128 B = 2 KB
               const uint64_t da = A_KMAJOR ? make_smem_desc(sa + k * 32, 16, 1024) : make_smem_desc(sa + k * 2048, 8192, 1024);
               const uint64_t db = B_KMAJOR ? make_smem_desc(sb + k * 32, 16, 1024) : make_smem_desc(sb + k * 2048, 8192, 1024);
-              if constexpr (FP8) tcgen05_mma_f8_e(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-              else tcgen05_mma_f16_e(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              if constexpr (FP8) tcgen05_mma_f8(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              else tcgen05_mma_f16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            tcgen05_commit_e(bar_empty + 8 * stage);   // smem stage reusable once these MMAs retire
+            tcgen05_commit(bar_empty + 8 * stage);   // smem stage reusable once these MMAs retire
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          tcgen05_commit_e(bar_tfull + 8 * as);        // accumulator complete
+          tcgen05_commit(bar_tfull + 8 * as);        // accumulator complete
           if (++as == kAccStages) { as = 0; aphase ^= 1; }
         }
       }
@@ -450,8 +450,20 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled is a DRIVER API call: it needs a current context on the calling thread.  Autograd worker threads may
+// reach us before any runtime call made the primary context current there (PyTorch's device guard skips cudaSetDevice when the
+// device index already matches, and the caching allocator can serve at::empty without touching the runtime) → error 201.
+static void ensure_driver_context() {
+  thread_local bool done = false;
+  if (!done) {
+    cudaFree(nullptr);      // forces the runtime to initialise / bind the primary context on this thread
+    done = true;
+  }
+}
+
 // 2-D bf16 row-major tensor [rows, cols] (cols contiguous); box = {box_cols, box_rows}; 128B swizzle.
 static CUtensorMap make_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
+  ensure_driver_context();
   CUtensorMap m;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
@@ -466,6 +478,7 @@ static CUtensorMap make_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint
 
 // e4m3 row-major [rows, cols] bytes; box = {128 k-bytes, box_rows}
 static CUtensorMap make_tmap_u8(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  ensure_driver_context();
   CUtensorMap m;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols};
@@ -490,6 +503,7 @@ CUtensorMap make_tmap_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint32
 // same, rows `row_stride_elems` apart (strided views: fused-QKV slices, [S,B,H,D] activations)
 CUtensorMap make_tmap_bf16_strided(const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                                    uint32_t box_cols, uint32_t box_rows) {
+  ensure_driver_context();
   CUtensorMap m;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {row_stride_elems * 2};

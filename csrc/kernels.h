@@ -72,6 +72,10 @@ void grouped_gemm_bf16(const void* a, const void* b, void* out, int M, int N, in
 void grouped_wgrad_bf16(const void* a, const void* b, void* out, int rows_total, int Mo, int No, int E,
                         const int* seg_first_block, int block_rows, int out_dt, bool accumulate, cudaStream_t st);
 
+// ---- one-shot all-reduce over peer memory (allreduce.cu)
+void oneshot_allreduce(const void* x, void* out, const int64_t* peer_bufs, const int64_t* peer_flags, long slot_bytes,
+                       uint32_t* state, int rank, int world, long numel, int dt, int ctas, cudaStream_t st);
+
 // ---- decode (decode.cu)
 void decode_attention(const void* q, const void* k, const void* v, const long* positions, void* out, float* part_o,
                       float* part_ml, int B, int H, int Hkv, int L, const long* ks, const long* vs, long q_sb, long q_sh,

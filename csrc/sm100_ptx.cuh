@@ -151,8 +151,10 @@ NXD_DEVICE void tcgen05_mma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t 
 
 // ---- elected issue: the whole (converged) MMA warp executes these; one elected lane runs the tcgen05 instruction.
 // Issuing from `if (lane == 0)` makes nvcc wrap every UTCHMMA in an ELECT / BRA.U.ANY loop with R2UR round trips (~20 SASS
-// instructions, ~100 cycles per MMA — see profiles/attention_ncu_summary_v2.txt); in warp-uniform code it is one predicated
-// UTCHMMA with descriptors computed on the uniform datapath.
+// instructions, ~100 cycles per MMA).  For the attention kernels (32-64-cycle UMMAs) that made the issuing thread the
+// bottleneck and the elected form fixed it.  For the big-tile GEMMs (128-cycle UMMAs) the elected form measured SLOWER
+// (8192^3: 1371 vs 1637 TFLOP/s — 32 lanes spinning on the mbarriers and R2UR.BROADCAST chains on the critical path), so
+// the GEMM kernels keep single-lane issue; these helpers are kept for small-tile kernels.
 NXD_DEVICE void tcgen05_mma_f16_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t"

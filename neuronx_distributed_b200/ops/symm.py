@@ -27,6 +27,10 @@ def reset() -> None:
     for ws in list(_WORKSPACES.values()):
         ws.close()
     _WORKSPACES.clear()
+    from . import _fused_impl, allreduce
+
+    allreduce.reset()
+    _fused_impl.reset()
 
 
 def available() -> bool:

@@ -62,6 +62,13 @@ def all_reduce(
     if isinstance(tensors, torch.Tensor):
         if n == 1:
             return None if async_op else tensors
+        if op == "sum" and not async_op and tensors.is_cuda:
+            from ..ops import allreduce as _oneshot     # small tensors: one-shot peer-memory kernel instead of NCCL
+
+            red = _oneshot.all_reduce_sum(tensors, group)
+            if red is not None:
+                tensors.copy_(red)
+                return tensors
         work = dist.all_reduce(tensors, op=rop, group=group, async_op=async_op)
         if op == "avg":
             assert not async_op

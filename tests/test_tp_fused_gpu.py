@@ -129,3 +129,44 @@ def _zero1_overlap(rank, world):
 
 def test_zero1_overlapped_reduce_scatter_is_exact():
     run_distributed(_zero1_overlap, 2, use_cuda=True, timeout=240)
+
+
+def _oneshot_ar(rank, world):
+    """One-shot peer-memory all-reduce vs NCCL: eager, repeated back-to-back (epoch / parity protocol) and under CUDA-graph
+    replay (device-side epoch)."""
+    import torch.distributed as dist
+
+    from neuronx_distributed_b200.ops import allreduce
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    g = ps.get_tensor_model_parallel_group()
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(rank)
+    for dtype, n in ((torch.bfloat16, 5120), (torch.float32, 4096 * 33), (torch.bfloat16, 8 * 16384)):
+        for it in range(5):
+            x = torch.randn(n, device=dev).to(dtype)
+            ref = x.clone().float()
+            dist.all_reduce(ref, group=g)
+            out = allreduce.all_reduce_sum(x, g)
+            assert out is not None
+            tol = 2e-2 if dtype == torch.bfloat16 else 1e-5
+            assert (out.float() - ref).abs().max() <= tol * ref.abs().max() + 1e-6
+    # graph replay: the same captured launch must stay correct over several replays with new inputs
+    x = torch.zeros(5120, device=dev, dtype=torch.bfloat16)
+    allreduce.all_reduce_sum(x, g)
+    torch.cuda.synchronize(); dist.barrier()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        y = allreduce.all_reduce_sum(x, g)
+    for it in range(4):
+        x.copy_(torch.full((5120,), float(it + rank), device=dev))
+        graph.replay()
+        torch.cuda.synchronize()
+        want = sum(it + r for r in range(world))
+        assert torch.allclose(y.float(), torch.full_like(y.float(), want)), (it, y[:4])
+    assert allreduce.all_reduce_sum(torch.randn(3, device=dev), g) is None      # not 16-byte sized → NCCL path
+
+
+def test_oneshot_allreduce_matches_nccl_and_replays_in_graphs():
+    run_distributed(_oneshot_ar, 2, use_cuda=True, timeout=240)
