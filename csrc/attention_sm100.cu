@@ -32,7 +32,7 @@ constexpr int kThreads = 192;
 constexpr int kPolyPairs = 0;      // of every 8 element pairs, how many use ex2_poly in the forward softmax
 constexpr uint32_t kTile = BM * HD * 2;          // 32 KB
 constexpr uint32_t kHalf = kTile / 2;            // one [128 × 64] box
-constexpr uint32_t kSmemFwd = 5 * kTile + 1024 /*align*/ + 128 /*barriers*/;
+constexpr uint32_t kSmemFwd = 6 * kTile + 1024 /*align*/ + 256 /*barriers*/;
 
 NXD_DEVICE void tcgen05_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -139,33 +139,52 @@ NXD_DEVICE float ex2_poly(float x) {
   return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
 }
 
-// One CTA per SM.  TMEM: S double buffer [0,256) (P_j is written over S_j in place), O [256,384).  Tensor-pipe order is
-// S_0 S_1 PV_0 S_2 PV_1 S_3 …: the QKᵀ of tile j+1 and the PV of tile j-1 run while the softmax warps work on tile j, so
-// the softmax (MUFU-bound) is the only serial chain and the tensor core is hidden behind it.
+// Persistent forward: one CTA per SM walks (q-tile, head, batch) work items in round-robin order.
+// TMEM: S double buffer [0,256) (P_j is written over S_j in place), O double buffer [256,512).  Tensor-pipe order is
+// S_0 S_1 PV_0 S_2 PV_1 S_3 … across item boundaries: the QKᵀ of the next tiles (including the first tiles of the NEXT work
+// item, whose Q sits in the second Q buffer) and the PV of the previous tile run while the softmax warps work on the current
+// tile, and the epilogue of item i (O_i → HBM) overlaps the first QKᵀ/PV of item i+1 (second O buffer).  The one-time costs
+// (TMEM allocation, barrier init, descriptor prefetch, first TMA round trip) are paid once per SM instead of once per tile.
+struct FwdItem { int qt, head, b, n_kv; };
+
+// Work order = (batch·head) major, q-tile minor — the order the hardware block scheduler would use, so the CTAs running at any
+// moment work on the same few heads and K/V stay in L2 (sorting all items heaviest-first instead made every CTA stream a
+// different head and re-read K/V from HBM for every q tile: 4.4 GB instead of 0.27 GB per call, measured 15 % slower).  The q
+// tile is rotated by the head index so that a CTA's round-robin slice (stride = grid size) mixes heavy and light causal tiles.
+NXD_DEVICE FwdItem fwd_item(int idx, int nq, int n_tiles_kv, const FwdParams& p) {
+  FwdItem it;
+  const int bh = idx / nq, j = idx % nq;
+  it.qt = nq - 1 - (j + bh) % nq;
+  it.head = bh % p.H;
+  it.b = bh / p.H;
+  it.n_kv = p.causal ? min(it.qt + 1, n_tiles_kv) : n_tiles_kv;
+  return it;
+}
+NXD_DEVICE int fwd_item_index(int k) { return k * (int)gridDim.x + (int)blockIdx.x; }
+
 __global__ void __launch_bounds__(kThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
               const __grid_constant__ CUtensorMap tv, __nv_bfloat16* __restrict__ out, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base, sK = smem_base + kTile, sV = smem_base + 3 * kTile;      // K, V: two stages each
-  const uint32_t bars = smem_base + 5 * kTile;
-  // q | kf[2] | vf[2] | ke[2] | ve[2] | s[2] | p[2] | o | tmem slot
-  const uint32_t bar_q = bars, bar_kf = bars + 8, bar_vf = bars + 24, bar_ke = bars + 40, bar_ve = bars + 56,
-                 bar_s = bars + 72, bar_p = bars + 88, bar_o = bars + 104, tmem_slot = bars + 112;
+  const uint32_t sQ = smem_base, sK = smem_base + 2 * kTile, sV = smem_base + 4 * kTile;   // Q, K, V: two stages each
+  const uint32_t bars = smem_base + 6 * kTile;
+  // qf[2] qe[2] kf[2] vf[2] ke[2] ve[2] s[2] p[2] pv oe[2] | tmem slot
+  const uint32_t bar_qf = bars, bar_qe = bars + 16, bar_kf = bars + 32, bar_vf = bars + 48, bar_ke = bars + 64,
+                 bar_ve = bars + 80, bar_s = bars + 96, bar_p = bars + 112, bar_pv = bars + 128, bar_oe = bars + 136,
+                 tmem_slot = bars + 152;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;    // heavy (late) query tiles first
-  const int head = blockIdx.y, b = blockIdx.z;
-  const int kvh = head / (p.H / p.Hkv);
+  const int nq = (p.S_q + BM - 1) / BM;
   const int n_tiles_kv = (p.S_kv + BN - 1) / BN;
-  const int n_kv = p.causal ? min(qt + 1, n_tiles_kv) : n_tiles_kv;
+  const int n_items = nq * p.H * p.B;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_qf + 8 * i, 1); mbar_init(bar_qe + 8 * i, 1);
       mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ke + 8 * i, 1); mbar_init(bar_ve + 8 * i, 1);
-      mbar_init(bar_s + 8 * i, 1); mbar_init(bar_p + 8 * i, 128);
+      mbar_init(bar_s + 8 * i, 1); mbar_init(bar_p + 8 * i, 128); mbar_init(bar_oe + 8 * i, 128);
     }
-    mbar_init(bar_o, 1);
+    mbar_init(bar_pv, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -182,23 +201,32 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
   if (warp == 0) {
     if (lane == 0) {
       prefetch_tmap(&tq); prefetch_tmap(&tk); prefetch_tmap(&tv);
-      const int qc = b * p.q.col_b + head * p.q.col_h, qr = b * p.q.row_b + head * p.q.row_h + qt * BM;
-      mbar_expect_tx(bar_q, kTile);
-      tma_load_2d(sQ, &tq, bar_q, qc, qr);
-      tma_load_2d(sQ + kHalf, &tq, bar_q, qc + 64, qr);
-      const int kc = b * p.k.col_b + kvh * p.k.col_h, kr = b * p.k.row_b + kvh * p.k.row_h;
-      const int vc = b * p.v.col_b + kvh * p.v.col_h, vr = b * p.v.row_b + kvh * p.v.row_h;
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (uint32_t)((j >> 1) & 1);
-        mbar_wait(bar_ke + 8 * st, ph ^ 1);
-        mbar_expect_tx(bar_kf + 8 * st, kTile);
-        tma_load_2d(sK + st * kTile, &tk, bar_kf + 8 * st, kc, kr + j * BN);
-        tma_load_2d(sK + st * kTile + kHalf, &tk, bar_kf + 8 * st, kc + 64, kr + j * BN);
-        mbar_wait(bar_ve + 8 * st, ph ^ 1);
-        mbar_expect_tx(bar_vf + 8 * st, kTile);
-        tma_load_2d(sV + st * kTile, &tv, bar_vf + 8 * st, vc, vr + j * BN);
-        tma_load_2d(sV + st * kTile + kHalf, &tv, bar_vf + 8 * st, vc + 64, vr + j * BN);
+      int g = 0;
+      for (int il = 0;; ++il) {
+        const int idx = fwd_item_index(il);
+        if (idx >= n_items) break;
+        const FwdItem it = fwd_item(idx, nq, n_tiles_kv, p);
+        const int kvh = it.head / (p.H / p.Hkv);
+        const int qb = il & 1;
+        mbar_wait(bar_qe + 8 * qb, (uint32_t)(((il >> 1) & 1) ^ 1));
+        const int qc = it.b * p.q.col_b + it.head * p.q.col_h, qr = it.b * p.q.row_b + it.head * p.q.row_h + it.qt * BM;
+        mbar_expect_tx(bar_qf + 8 * qb, kTile);
+        tma_load_2d(sQ + qb * kTile, &tq, bar_qf + 8 * qb, qc, qr);
+        tma_load_2d(sQ + qb * kTile + kHalf, &tq, bar_qf + 8 * qb, qc + 64, qr);
+        const int kc = it.b * p.k.col_b + kvh * p.k.col_h, kr = it.b * p.k.row_b + kvh * p.k.row_h;
+        const int vc = it.b * p.v.col_b + kvh * p.v.col_h, vr = it.b * p.v.row_b + kvh * p.v.row_h;
+        for (int j = 0; j < it.n_kv; ++j, ++g) {
+          const int st = g & 1;
+          const uint32_t ph = (uint32_t)((g >> 1) & 1);
+          mbar_wait(bar_ke + 8 * st, ph ^ 1);
+          mbar_expect_tx(bar_kf + 8 * st, kTile);
+          tma_load_2d(sK + st * kTile, &tk, bar_kf + 8 * st, kc, kr + j * BN);
+          tma_load_2d(sK + st * kTile + kHalf, &tk, bar_kf + 8 * st, kc + 64, kr + j * BN);
+          mbar_wait(bar_ve + 8 * st, ph ^ 1);
+          mbar_expect_tx(bar_vf + 8 * st, kTile);
+          tma_load_2d(sV + st * kTile, &tv, bar_vf + 8 * st, vc, vr + j * BN);
+          tma_load_2d(sV + st * kTile + kHalf, &tv, bar_vf + 8 * st, vc + 64, vr + j * BN);
+        }
       }
     }
     __syncwarp();
@@ -206,36 +234,53 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
     {   // all 32 lanes run this loop; the helpers elect one lane per tcgen05 instruction
       constexpr uint32_t idesc_s = make_idesc(false, false, BM, BN);
       constexpr uint32_t idesc_o = make_idesc(false, true, BM, HD);
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(bar_kf + 8 * st, (uint32_t)((j >> 1) & 1));
+      // cursor over the flattened (item, kv-tile) sequence of this CTA
+      struct Cur { int il, j, n_kv, g; bool ok; };
+      auto start = [&](int il, int g) {
+        Cur c{il, 0, 0, g, false};
+        const int idx = fwd_item_index(il);
+        if (idx < n_items) { c.n_kv = fwd_item(idx, nq, n_tiles_kv, p).n_kv; c.ok = true; }
+        return c;
+      };
+      auto advance = [&](Cur& c) {
+        ++c.g;
+        if (++c.j == c.n_kv) c = start(c.il + 1, c.g);
+      };
+      auto issue_s = [&](const Cur& c) {
+        const int st = c.g & 1, qb = c.il & 1;
+        if (c.j == 0) mbar_wait(bar_qf + 8 * qb, (uint32_t)((c.il >> 1) & 1));
+        mbar_wait(bar_kf + 8 * st, (uint32_t)((c.g >> 1) & 1));
         tcgen05_fence_after();
-        const uint32_t k_s = sK + st * kTile;
+        const uint32_t q_s = sQ + qb * kTile, k_s = sK + st * kTile;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            mma_ss(tmem_S + st * BN, make_smem_desc(sQ + kb * kHalf + kk * 32, 16, 1024),
-                            make_smem_desc(k_s + kb * kHalf + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
+            mma_ss(tmem_S + st * BN, make_smem_desc(q_s + kb * kHalf + kk * 32, 16, 1024),
+                   make_smem_desc(k_s + kb * kHalf + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
         commit_elect(bar_ke + 8 * st);
         commit_elect(bar_s + 8 * st);
+        if (c.j == c.n_kv - 1) commit_elect(bar_qe + 8 * qb);       // last QKᵀ of the item: its Q buffer is free
       };
-      mbar_wait(bar_q, 0);
-      issue_s(0);
-      if (n_kv > 1) issue_s(1);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (uint32_t)((j >> 1) & 1);
+      Cur ahead = start(0, 0), cur = ahead;
+      if (ahead.ok) { issue_s(ahead); advance(ahead); }
+      if (ahead.ok) { issue_s(ahead); advance(ahead); }
+      while (cur.ok) {
+        const int st = cur.g & 1, ob = cur.il & 1;
+        const uint32_t ph = (uint32_t)((cur.g >> 1) & 1);
         mbar_wait(bar_p + 8 * st, ph);
         mbar_wait(bar_vf + 8 * st, ph);
+        if (cur.j == 0) mbar_wait(bar_oe + 8 * ob, (uint32_t)(((cur.il >> 1) & 1) ^ 1));   // epilogue of item il-2 left O[ob]
         tcgen05_fence_after();
         const uint32_t v_s = sV + st * kTile;
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k)
-          mma_ts(tmem_O, tmem_S + st * BN + k * 8, make_smem_desc(v_s + k * 2048, kHalf, 1024), idesc_o, (j | k) ? 1u : 0u);
+          mma_ts(tmem_O + ob * HD, tmem_S + st * BN + k * 8, make_smem_desc(v_s + k * 2048, kHalf, 1024), idesc_o,
+                 (cur.j | k) ? 1u : 0u);
         commit_elect(bar_ve + 8 * st);
-        commit_elect(bar_o);
-        if (j + 2 < n_kv) issue_s(j + 2);      // overwrites P_j — behind PV_j in pipe order
+        commit_elect(bar_pv);
+        if (ahead.ok) { issue_s(ahead); advance(ahead); }        // overwrites P of tile g — behind PV_g in pipe order
+        advance(cur);
       }
     }
     __syncwarp();
@@ -243,110 +288,120 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const int q_idx = qt * BM + row;
     const float sl2 = p.scale_log2;
-    float m_ref = -INFINITY, l = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      const int st = j & 1;
-      const uint32_t tS = tmem_S + st * BN + lane_base;
-      mbar_wait(bar_s + 8 * st, (uint32_t)((j >> 1) & 1));
+    int g = 0;
+    for (int il = 0;; ++il) {
+      const int idx = fwd_item_index(il);
+      if (idx >= n_items) break;
+      const FwdItem it = fwd_item(idx, nq, n_tiles_kv, p);
+      const int qt = it.qt, ob = il & 1;
+      const int q_idx = qt * BM + row;
+      const uint32_t tO = tmem_O + ob * HD + lane_base;
+      float m_ref = -INFINITY, l = 0.f;
+      for (int j = 0; j < it.n_kv; ++j, ++g) {
+        const int st = g & 1;
+        const uint32_t tS = tmem_S + st * BN + lane_base;
+        mbar_wait(bar_s + 8 * st, (uint32_t)((g >> 1) & 1));
+        tcgen05_fence_after();
+        const int kv0 = j * BN;
+        const bool masked = (p.causal && kv0 + BN - 1 > qt * BM) || (kv0 + BN > p.S_kv);
+        // ---- the whole S row (128 fp32) comes into registers with four back-to-back TMEM loads and one wait
+        uint32_t sr[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tcgen05_ld_32x32(tS + c * 32, sr[c]);
+        tcgen05_wait_ld();
+        if (masked) {      // diagonal / ragged tile: −inf in place, the exp below turns it into an exact 0
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int kv = kv0 + c * 32 + i;
+              if (!(kv < p.S_kv && (!p.causal || kv <= q_idx))) sr[c][i] = 0xff800000u;
+            }
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(mx4[c], __uint_as_float(sr[c][i]));
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        if (j == 0) {
+          m_ref = mx;
+        } else {
+          const float m_new = fmaxf(m_ref, mx);
+          const bool need = (m_new - m_ref) * sl2 > 8.f;
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(bar_pv, (uint32_t)((g - 1) & 1));      // PV of the previous tile retired: O is quiescent
+            tcgen05_fence_after();
+            const float f = need ? ex2((m_ref - m_new) * sl2) : 1.f;
+            if (need) m_ref = m_new;
+            l *= f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t r[32];
+              tcgen05_ld_32x32(tO + c * 32, r);
+              tcgen05_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+              tcgen05_st_32x32(tO + c * 32, r);
+            }
+          }
+        }
+        // ---- P = exp2(s·scale·log2e − m_ref·scale·log2e), packed to bf16 in place and written over the S columns
+        const float mb = m_ref * sl2;
+        const uint64_t sl2_2 = pack2(sl2, sl2), nmb_2 = pack2(-mb, -mb);
+        uint64_t l2acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float x0, x1;
+            unpack2(fma2(pack2u(sr[c][i], sr[c][i + 1]), sl2_2, nmb_2), x0, x1);
+            // kPolyPairs of every 8 pairs take the FMA-pipe exp2; 0 = all on MUFU (a lone warp per SMSP is issue-bound, not
+            // MUFU-bound, once the polynomial's 8 extra instructions are counted — measured, see profiles/)
+            const bool poly = ((i >> 1) & 7) < kPolyPairs;
+            const float p0 = poly ? ex2_poly(x0) : ex2(x0);
+            const float p1 = poly ? ex2_poly(x1) : ex2(x1);
+            l2acc[c] = add2(l2acc[c], pack2(p0, p1));
+            sr[c][i >> 1] = pack_bf16(p0, p1);
+          }
+          tcgen05_st_32x16p(tS + c * 16, sr[c]);
+        }
+        float l4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { float a, bq; unpack2(l2acc[c], a, bq); l4[c] = a + bq; }
+        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        tcgen05_wait_st();
+        tcgen05_fence_before();
+        mbar_arrive(bar_p + 8 * st);
+      }
+      // ---- epilogue: O / l → bf16, LSE (the MMA warp is already working on the next item in the other O buffer)
+      mbar_wait(bar_pv, (uint32_t)((g - 1) & 1));
       tcgen05_fence_after();
-      const int kv0 = j * BN;
-      const bool masked = (p.causal && kv0 + BN - 1 > qt * BM) || (kv0 + BN > p.S_kv);
-      // ---- the whole S row (128 fp32) comes into registers with four back-to-back TMEM loads and one wait
-      uint32_t sr[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tcgen05_ld_32x32(tS + c * 32, sr[c]);
-      tcgen05_wait_ld();
-      if (masked) {      // diagonal / ragged tile: −inf in place, the exp below turns it into an exact 0
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kv = kv0 + c * 32 + i;
-            if (!(kv < p.S_kv && (!p.causal || kv <= q_idx))) sr[c][i] = 0xff800000u;
-          }
-      }
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(mx4[c], __uint_as_float(sr[c][i]));
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      if (j == 0) {
-        m_ref = mx;
-      } else {
-        const float m_new = fmaxf(m_ref, mx);
-        const bool need = (m_new - m_ref) * sl2 > 8.f;
-        if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(bar_o, (uint32_t)((j - 1) & 1));      // PV_{j-1} retired: O is quiescent
-          tcgen05_fence_after();
-          const float f = need ? ex2((m_ref - m_new) * sl2) : 1.f;
-          if (need) m_ref = m_new;
-          l *= f;
+      const float inv_l = 1.f / l;
+      const bool row_ok = q_idx < p.S_q;
+      __nv_bfloat16* orow = out + (long)it.b * p.o_sb + (long)q_idx * p.o_ss + (long)it.head * p.o_sh;
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tcgen05_ld_32x32(tmem_O + lane_base + c * 32, r);
-            tcgen05_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-            tcgen05_st_32x32(tmem_O + lane_base + c * 32, r);
-          }
-        }
-      }
-      // ---- P = exp2(s·scale·log2e − m_ref·scale·log2e), packed to bf16 in place and written over the S columns
-      const float mb = m_ref * sl2;
-      const uint64_t sl2_2 = pack2(sl2, sl2), nmb_2 = pack2(-mb, -mb);
-      uint64_t l2acc[4] = {0ull, 0ull, 0ull, 0ull};
-#pragma unroll
       for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tcgen05_ld_32x32(tO + c * 32, r);
+        tcgen05_wait_ld();
+        if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float x0, x1;
-          unpack2(fma2(pack2u(sr[c][i], sr[c][i + 1]), sl2_2, nmb_2), x0, x1);
-          // kPolyPairs of every 8 pairs take the FMA-pipe exp2; 0 = all on MUFU (a lone warp per SMSP is issue-bound, not
-          // MUFU-bound, once the polynomial's 8 extra instructions are counted — measured, see profiles/)
-          const bool poly = ((i >> 1) & 7) < kPolyPairs;
-          const float p0 = poly ? ex2_poly(x0) : ex2(x0);
-          const float p1 = poly ? ex2_poly(x1) : ex2(x1);
-          l2acc[c] = add2(l2acc[c], pack2(p0, p1));
-          sr[c][i >> 1] = pack_bf16(p0, p1);
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(r[v4 * 8 + 0]) * inv_l, __uint_as_float(r[v4 * 8 + 1]) * inv_l);
+            o.y = pack_bf16(__uint_as_float(r[v4 * 8 + 2]) * inv_l, __uint_as_float(r[v4 * 8 + 3]) * inv_l);
+            o.z = pack_bf16(__uint_as_float(r[v4 * 8 + 4]) * inv_l, __uint_as_float(r[v4 * 8 + 5]) * inv_l);
+            o.w = pack_bf16(__uint_as_float(r[v4 * 8 + 6]) * inv_l, __uint_as_float(r[v4 * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 32 + v4 * 8) = o;
+          }
         }
-        tcgen05_st_32x16p(tS + c * 16, sr[c]);
       }
-      float l4[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) { float a, bq; unpack2(l2acc[c], a, bq); l4[c] = a + bq; }
-      l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-      tcgen05_wait_st();
+      if (row_ok) p.lse[((long)it.b * p.H + it.head) * p.S_q + q_idx] = m_ref * p.scale + __logf(l);
       tcgen05_fence_before();
-      mbar_arrive(bar_p + 8 * st);
+      mbar_arrive(bar_oe + 8 * ob);
     }
-    // ---- epilogue: O / l → bf16, LSE
-    mbar_wait(bar_o, (uint32_t)((n_kv - 1) & 1));
-    tcgen05_fence_after();
-    const float inv_l = 1.f / l;
-    const bool row_ok = q_idx < p.S_q;
-    __nv_bfloat16* orow = out + (long)b * p.o_sb + (long)q_idx * p.o_ss + (long)head * p.o_sh;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tcgen05_ld_32x32(tmem_O + lane_base + c * 32, r);
-      tcgen05_wait_ld();
-      if (row_ok) {
-#pragma unroll
-        for (int v4 = 0; v4 < 4; ++v4) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(r[v4 * 8 + 0]) * inv_l, __uint_as_float(r[v4 * 8 + 1]) * inv_l);
-          o.y = pack_bf16(__uint_as_float(r[v4 * 8 + 2]) * inv_l, __uint_as_float(r[v4 * 8 + 3]) * inv_l);
-          o.z = pack_bf16(__uint_as_float(r[v4 * 8 + 4]) * inv_l, __uint_as_float(r[v4 * 8 + 5]) * inv_l);
-          o.w = pack_bf16(__uint_as_float(r[v4 * 8 + 6]) * inv_l, __uint_as_float(r[v4 * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c * 32 + v4 * 8) = o;
-        }
-      }
-    }
-    if (row_ok) p.lse[((long)b * p.H + head) * p.S_q + q_idx] = m_ref * p.scale + __logf(l);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -400,43 +455,68 @@ NXD_DEVICE void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "m
 NXD_DEVICE void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 NXD_DEVICE void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// Pᵀ = exp2(Sᵀ·c − lse₂[q]) and dSᵀ = Pᵀ ∘ (dPᵀ·scale − δ[q]·scale) for one thread's kv row × 64 q columns; both are packed
-// to bf16 in place (element pair (i, i+1) → register i/2).  MASKED is hoisted to a template parameter so the common tile
-// has no per-element branches.
+// Softmax-side math of one backward tile, split in two phases so the exp work (needs only Sᵀ, which the tensor pipe delivered a
+// full iteration ago) runs while dPᵀ of the same tile is still being computed:
+//   phase 1: Pᵀ = exp2(Sᵀ·c − lse₂[q])  → fp32 in registers (pf) + bf16 pairs packed in place into sv (element pair (i,i+1) → i/2)
+//   phase 2: dSᵀ = Pᵀ ∘ (dPᵀ·scale − δ[q]·scale) → bf16 pairs packed in place into dpv
+// The stats rows hold −lse·log2e and −δ·scale so both affine steps are single packed FMAs; MASKED is a template parameter so
+// the common tile has no per-element branches or selects.
 template <bool MASKED>
-NXD_DEVICE void bwd_tile_math(uint32_t (&sv)[2][32], uint32_t (&dpv)[2][32], uint32_t stats_s, float sl2, float sc, int kv,
-                              int q0, int S_q, int S_kv, int causal) {
-  const uint64_t sl2_2 = pack2(sl2, sl2), sc_2 = pack2(sc, sc);
+NXD_DEVICE void bwd_p_math(uint32_t (&sv)[2][32], float (&pf)[2][32], uint32_t stats_s, float sl2, int kv, int q0, int S_q,
+                           int S_kv, int causal) {
+  const uint64_t sl2_2 = pack2(sl2, sl2);
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      float4 l2, dl;
+      float4 l2;
       asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(l2.x), "=f"(l2.y), "=f"(l2.z), "=f"(l2.w)
                    : "r"(stats_s + (h * 32 + i) * 4));
-      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(dl.x), "=f"(dl.y), "=f"(dl.z), "=f"(dl.w)
-                   : "r"(stats_s + 256 + (h * 32 + i) * 4));
-      // stats hold −lse·log2e and −δ·scale, so both affine steps are single packed FMAs
-      const uint64_t nl2[2] = {pack2(l2.x, l2.y), pack2(l2.z, l2.w)}, ndl[2] = {pack2(dl.x, dl.y), pack2(dl.z, dl.w)};
-      float pv[4], dsv[4];
+      const uint64_t nl2[2] = {pack2(l2.x, l2.y), pack2(l2.z, l2.w)};
 #pragma unroll
       for (int e2 = 0; e2 < 2; ++e2) {
         float x0, x1;
         unpack2(fma2(pack2u(sv[h][i + 2 * e2], sv[h][i + 2 * e2 + 1]), sl2_2, nl2[e2]), x0, x1);
         float p0 = ex2(x0), p1 = ex2(x1);
-        float d0, d1;
-        unpack2(mul2(pack2(p0, p1), fma2(pack2u(dpv[h][i + 2 * e2], dpv[h][i + 2 * e2 + 1]), sc_2, ndl[e2])), d0, d1);
         if constexpr (MASKED) {
           const int q = q0 + h * 32 + i + 2 * e2;
-          const bool ok0 = kv < S_kv && q < S_q && (!causal || kv <= q);
-          const bool ok1 = kv < S_kv && q + 1 < S_q && (!causal || kv <= q + 1);
-          p0 = ok0 ? p0 : 0.f; d0 = ok0 ? d0 : 0.f;      // selects, not branches; also kills NaN padding
-          p1 = ok1 ? p1 : 0.f; d1 = ok1 ? d1 : 0.f;
+          p0 = (kv < S_kv && q < S_q && (!causal || kv <= q)) ? p0 : 0.f;          // selects; also kills NaN padding
+          p1 = (kv < S_kv && q + 1 < S_q && (!causal || kv <= q + 1)) ? p1 : 0.f;
         }
-        pv[2 * e2] = p0; pv[2 * e2 + 1] = p1; dsv[2 * e2] = d0; dsv[2 * e2 + 1] = d1;
+        pf[h][i + 2 * e2] = p0;
+        pf[h][i + 2 * e2 + 1] = p1;
       }
-      sv[h][i >> 1] = pack_bf16(pv[0], pv[1]);      sv[h][(i >> 1) + 1] = pack_bf16(pv[2], pv[3]);
-      dpv[h][i >> 1] = pack_bf16(dsv[0], dsv[1]);   dpv[h][(i >> 1) + 1] = pack_bf16(dsv[2], dsv[3]);
+      sv[h][i >> 1] = pack_bf16(pf[h][i], pf[h][i + 1]);
+      sv[h][(i >> 1) + 1] = pack_bf16(pf[h][i + 2], pf[h][i + 3]);
+    }
+  }
+}
+
+template <bool MASKED>
+NXD_DEVICE void bwd_ds_math(uint32_t (&dpv)[2][32], const float (&pf)[2][32], uint32_t stats_s, float sc) {
+  const uint64_t sc_2 = pack2(sc, sc);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 dl;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(dl.x), "=f"(dl.y), "=f"(dl.z), "=f"(dl.w)
+                   : "r"(stats_s + 256 + (h * 32 + i) * 4));
+      const uint64_t ndl[2] = {pack2(dl.x, dl.y), pack2(dl.z, dl.w)};
+      float dsv[4];
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) {
+        float d0, d1;
+        unpack2(mul2(pack2(pf[h][i + 2 * e2], pf[h][i + 2 * e2 + 1]),
+                     fma2(pack2u(dpv[h][i + 2 * e2], dpv[h][i + 2 * e2 + 1]), sc_2, ndl[e2])), d0, d1);
+        if constexpr (MASKED) {          // P is already exactly 0 where masked, but 0·NaN (padding garbage) must not leak
+          d0 = pf[h][i + 2 * e2] == 0.f ? 0.f : d0;
+          d1 = pf[h][i + 2 * e2 + 1] == 0.f ? 0.f : d1;
+        }
+        dsv[2 * e2] = d0; dsv[2 * e2 + 1] = d1;
+      }
+      dpv[h][i >> 1] = pack_bf16(dsv[0], dsv[1]);
+      dpv[h][(i >> 1) + 1] = pack_bf16(dsv[2], dsv[3]);
     }
   }
 }
@@ -591,24 +671,33 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
       const int q0 = t * BQ;
       mbar_wait(bar_qf + 8 * qs, (uint32_t)((it / kQStages) & 1));     // stats (TMA-written) visible to this thread
       mbar_wait(bar_s + 8 * st, (uint32_t)((it >> 1) & 1));
-      mbar_wait(bar_dp, (uint32_t)(it & 1));
       tcgen05_fence_after();
       const bool masked = (p.causal && q0 < kv0 + BN - 1) || (q0 + BQ > p.S_q) || (kv0 + BN > p.S_kv);
       const uint32_t stats_s = sStats + qs * 512;
       const uint32_t ds_row = sdS + st * kQTile + row * 128;
-      uint32_t sv[2][32], dpv[2][32];
+      // ---- phase 1 (needs only Sᵀ): Pᵀ, written back over Sᵀ in TMEM
+      uint32_t sv[2][32];
+      float pf[2][32];
       tcgen05_ld_32x32(tmem_ST + st * BQ + lane_base, sv[0]);
-      tcgen05_ld_32x32(tmem_dP + lane_base, dpv[0]);
       tcgen05_ld_32x32(tmem_ST + st * BQ + lane_base + 32, sv[1]);
+      tcgen05_wait_ld();
+      if (masked) bwd_p_math<true>(sv, pf, stats_s, sl2, kv, q0, p.S_q, p.S_kv, p.causal);
+      else bwd_p_math<false>(sv, pf, stats_s, sl2, kv, q0, p.S_q, p.S_kv, p.causal);
+      tcgen05_st_32x16p(tmem_ST + st * BQ + lane_base, sv[0]);
+      tcgen05_st_32x16p(tmem_ST + st * BQ + lane_base + 16, sv[1]);
+      // ---- phase 2 (dPᵀ of this tile was issued while phase 1 ran): dSᵀ → smem
+      mbar_wait(bar_dp, (uint32_t)(it & 1));
+      tcgen05_fence_after();
+      uint32_t dpv[2][32];
+      tcgen05_ld_32x32(tmem_dP + lane_base, dpv[0]);
       tcgen05_ld_32x32(tmem_dP + lane_base + 32, dpv[1]);
       tcgen05_wait_ld();
       if (!(p.debug & 4)) {
-        if (masked) bwd_tile_math<true>(sv, dpv, stats_s, sl2, sc, kv, q0, p.S_q, p.S_kv, p.causal);
-        else bwd_tile_math<false>(sv, dpv, stats_s, sl2, sc, kv, q0, p.S_q, p.S_kv, p.causal);
+        if (masked) bwd_ds_math<true>(dpv, pf, stats_s, sc);
+        else bwd_ds_math<false>(dpv, pf, stats_s, sc);
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        tcgen05_st_32x16p(tmem_ST + st * BQ + lane_base + h * 16, sv[h]);
         // dSᵀ row → smem, 128B-swizzled: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -777,8 +866,10 @@ void flash_attn_fwd(const void* q, const void* k, const void* v, void* out, floa
     NXD_CUDA_CHECK(cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd));
     configured = true;
   }
-  dim3 grid((S_q + BM - 1) / BM, H, B);
-  fa_fwd_kernel<<<grid, kThreads, kSmemFwd, st>>>(tq, tk, tv, (__nv_bfloat16*)out, p);
+  const int n_items = ((S_q + BM - 1) / BM) * H * B;
+  static int sms = 0;
+  if (!sms) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  fa_fwd_kernel<<<n_items < sms ? n_items : sms, kThreads, kSmemFwd, st>>>(tq, tk, tv, (__nv_bfloat16*)out, p);
   NXD_CUDA_CHECK(cudaGetLastError());
 }
 
