@@ -51,6 +51,14 @@ class KVCacheManager:
         self.k[layer].index_put_((b, positions), self._q(k[:, 0]))
         self.v[layer].index_put_((b, positions), self._q(v[:, 0]))
 
+    def write_window(self, layer: int, k: torch.Tensor, v: torch.Tensor, positions: torch.Tensor) -> None:
+        """k/v ``[B, W, H, D]`` written at positions ``positions[b] + 0..W-1`` (speculative verification / chunked prefill)."""
+        B, W = k.shape[0], k.shape[1]
+        b = torch.arange(B, device=k.device).unsqueeze(1).expand(B, W)
+        pos = (positions.unsqueeze(1) + torch.arange(W, device=k.device).unsqueeze(0)).clamp(max=self.k[layer].shape[1] - 1)
+        self.k[layer].index_put_((b, pos), self._q(k))
+        self.v[layer].index_put_((b, pos), self._q(v))
+
     def get(self, layer: int, length: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         k, v = self.k[layer], self.v[layer]
         if length is not None:

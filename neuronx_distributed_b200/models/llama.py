@@ -130,6 +130,9 @@ class LlamaAttention(nn.Module):
     def forward(self, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
         # x: [S(/tp), B, H]  →  q/k/v: [S, B, h_local*D]
         q, k, v = self.qkv_proj(x)
+        clip = getattr(self.cfg, "clip_qkv", None)
+        if clip is not None:                      # DBRX: clamp the projections (HF DbrxAttention clip_qkv)
+            q, k, v = q.clamp(-clip, clip), k.clamp(-clip, clip), v.clamp(-clip, clip)
         S, B = q.shape[0], q.shape[1]
         # [S,B,h,D] → [B,S,h,D] views (free when B == 1)
         q = q.reshape(S, B, self.num_heads_local, self.head_dim).transpose(0, 1)

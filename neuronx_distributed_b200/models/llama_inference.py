@@ -53,7 +53,16 @@ class LlamaForInference(nn.Module):
         q = q.reshape(S, B, att.num_heads_local, D).transpose(0, 1)
         k = k.reshape(S, B, att.num_kv_heads_local, D).transpose(0, 1)
         v = v.reshape(S, B, att.num_kv_heads_local, D).transpose(0, 1).contiguous()
-        if prefill:
+        if not prefill and S > 1:
+            # speculation window: W new tokens per sequence at positions p..p+W-1, causal among themselves, full cache before
+            W = S
+            idx = (positions.unsqueeze(1) + torch.arange(W, device=q.device).unsqueeze(0)).clamp(max=self.max_seq_len - 1)
+            cos, sin = self.rope_cos[idx], self.rope_sin[idx]                     # [B, W, D/2]
+            q, k = _rope_window(q, cos, sin), _rope_window(k, cos, sin)
+            self.kv.write_window(layer_idx, k, v, positions)
+            kc, vc = self.kv.get(layer_idx, kv_len)
+            o = _window_attention(q, kc, vc, positions)
+        elif prefill:
             cos, sin = self.rope_cos[:S], self.rope_sin[:S]
             q, k = ops.rope.apply_rotary(q, cos, sin), ops.rope.apply_rotary(k, cos, sin)
             self.kv.write_prefill(layer_idx, k, v)
@@ -97,6 +106,17 @@ class LlamaForInference(nn.Module):
         return self.sampler.sample(logits) if self.on_device_sampling else logits
 
     @torch.no_grad()
+    def speculation_forward(self, input_ids: torch.Tensor, positions: torch.Tensor, kv_len: Optional[int] = None) -> torch.Tensor:
+        """Verify a window: ``input_ids`` [B, W] placed at ``positions[b] .. positions[b]+W-1`` → greedy next token after
+        each of the W positions, ``[B, W]`` (reference ``examples/inference`` speculation model, ``speculation_length``)."""
+        h = self._body(input_ids, positions, False, kv_len)                      # [W, B, H]
+        logits = self.lm.lm_head(h).float()                                       # [W, B, V/tp]
+        W, B = logits.shape[:2]
+        if self.on_device_sampling:
+            return self.sampler.sample(logits.reshape(W * B, -1)).view(W, B).t()
+        return logits.transpose(0, 1)
+
+    @torch.no_grad()
     def generate(self, prompt_ids: torch.Tensor, max_new_tokens: int, prompt_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
         B, S = prompt_ids.shape
         lens = prompt_lens if prompt_lens is not None else torch.full((B,), S, device=prompt_ids.device, dtype=torch.long)
@@ -117,6 +137,27 @@ def _rope_per_batch(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> to
     x1, x2 = xf[..., :d2], xf[..., d2:]
     c, s = cos.unsqueeze(2), sin.unsqueeze(2)
     return torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1).to(x.dtype)
+
+
+def _rope_window(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    """x [B,W,H,D]; cos/sin [B,W,D/2]."""
+    d2 = x.shape[-1] // 2
+    xf = x.float()
+    x1, x2 = xf[..., :d2], xf[..., d2:]
+    c, s = cos.unsqueeze(2), sin.unsqueeze(2)
+    return torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1).to(x.dtype)
+
+
+def _window_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
+    """q [B,W,H,D] at positions p..p+W-1 vs cache k/v [B,L,Hkv,D]: token w sees cache entries ≤ p+w."""
+    B, W, H, D = q.shape
+    Hkv, L = k.shape[2], k.shape[1]
+    qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+    if H != Hkv:
+        kt, vt = kt.repeat_interleave(H // Hkv, 1), vt.repeat_interleave(H // Hkv, 1)
+    lim = positions[:, None] + torch.arange(W, device=q.device)[None, :]                       # [B, W]
+    mask = (torch.arange(L, device=q.device)[None, None, :] <= lim[:, :, None])[:, None]       # [B,1,W,L]
+    return torch.nn.functional.scaled_dot_product_attention(qt, kt, vt, attn_mask=mask).transpose(1, 2)
 
 
 def _decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:

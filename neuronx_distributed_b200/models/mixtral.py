@@ -1,6 +1,7 @@
-"""Mixtral-style sparse-MoE decoder (role of the reference's Mixtral/DBRX training examples,
-``examples/training/mixtral``): Llama attention + an :class:`modules.moe.MoE` feed-forward per layer, with the
-router auxiliary loss added to the LM loss."""
+"""Mixtral / DBRX style sparse-MoE decoders (role of the reference's ``examples/training/mixtral`` and
+``examples/training/dbrx``): Llama attention + an :class:`modules.moe.MoE` feed-forward per layer, with the router
+auxiliary loss added to the LM loss.  DBRX differs by bias-free LayerNorm instead of RMSNorm, clamped QKV projections
+(``clip_qkv``), 16 experts / top-4 with normalised top-k affinities (``DbrxConfig``)."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -23,18 +24,48 @@ class MixtralConfig(LlamaConfig):
     router_aux_loss_coef: float = 0.02
     capacity_factor: Optional[float] = None
     intermediate_size: int = 14336
+    norm_type: str = "rmsnorm"            # "layernorm" for DBRX (no bias)
+    clip_qkv: Optional[float] = None
+    normalize_top_k_affinities: bool = True
+
+
+@dataclass
+class DbrxConfig(MixtralConfig):
+    """databricks/dbrx-base shapes: d_model 6144, 40 layers, 48 heads / 8 kv heads, ffn 10752, 16 experts top-4, vocab 100352."""
+    vocab_size: int = 100352
+    hidden_size: int = 6144
+    num_hidden_layers: int = 40
+    num_attention_heads: int = 48
+    num_key_value_heads: int = 8
+    intermediate_size: int = 10752
+    num_local_experts: int = 16
+    num_experts_per_tok: int = 4
+    rope_theta: float = 500000.0
+    norm_type: str = "layernorm"
+    clip_qkv: Optional[float] = 8.0
+    router_aux_loss_coef: float = 0.05
+
+
+def _norm(cfg: MixtralConfig):
+    if cfg.norm_type == "layernorm":
+        from ..parallel_layers.layer_norm import LayerNorm
+
+        return LayerNorm(cfg.hidden_size, 1e-5, sequence_parallel_enabled=cfg.sequence_parallel_enabled, dtype=cfg.dtype,
+                         device=cfg.device, bias=False)
+    return RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, cfg.sequence_parallel_enabled, cfg.dtype, cfg.device)
 
 
 class MixtralDecoderLayer(nn.Module):
     def __init__(self, cfg: MixtralConfig):
         super().__init__()
         sp = cfg.sequence_parallel_enabled
-        self.input_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, sp, cfg.dtype, cfg.device)
-        self.post_attention_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, sp, cfg.dtype, cfg.device)
+        self.input_layernorm = _norm(cfg)
+        self.post_attention_layernorm = _norm(cfg)
         self.self_attn = LlamaAttention(cfg)
         ecfg = RoutedExpertsMLPOpsConfig(num_experts=cfg.num_local_experts, top_k=cfg.num_experts_per_tok,
                                          hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
-                                         hidden_act="silu", glu_mlp=True, capacity_factor=cfg.capacity_factor)
+                                         hidden_act="silu", glu_mlp=True, capacity_factor=cfg.capacity_factor,
+                                         normalize_top_k_affinities=cfg.normalize_top_k_affinities)
         self.mlp = MoE(RouterTopK(cfg.num_local_experts, cfg.num_experts_per_tok, cfg.hidden_size,
                                   sequence_parallel_enabled=sp, sequence_dimension=0, device=cfg.device),
                        ExpertMLPsV2(ecfg, sequence_parallel_enabled=sp, dtype=cfg.dtype, device=cfg.device),
@@ -58,7 +89,7 @@ class MixtralForCausalLM(nn.Module):
         self.embed_tokens = ParallelEmbedding(cfg.vocab_size, cfg.hidden_size, init_method=init, dtype=cfg.dtype,
                                               sequence_parallel_enabled=cfg.sequence_parallel_enabled, device=cfg.device)
         self.layers = nn.ModuleList([MixtralDecoderLayer(cfg) for _ in range(cfg.num_hidden_layers)])
-        self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps, cfg.sequence_parallel_enabled, cfg.dtype, cfg.device)
+        self.norm = _norm(cfg)
         self.lm_head = ColumnParallelLinear(cfg.hidden_size, cfg.vocab_size, bias=False, gather_output=False, init_method=init,
                                             sequence_parallel_enabled=cfg.sequence_parallel_enabled, sequence_dimension=0,
                                             dtype=cfg.dtype, device=cfg.device)

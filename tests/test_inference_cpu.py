@@ -78,3 +78,36 @@ def test_benchmark_report():
     b = Benchmark(lambda: sum(range(1000)), num_runs=5)
     rep = generate_report(b.run(), 128, 2)
     assert set(rep) >= {"latency_ms_p50", "latency_ms_p99", "latency_ms_avg", "throughput"} and rep["throughput"] > 0
+
+
+def _speculative(rank, world):
+    """Speculative decoding (draft proposes, target verifies a window in one forward) reproduces the target's own greedy
+    decoding token for token — with a draft that shares the target's weights (all accepted) and a random draft (mostly rejected)."""
+    from neuronx_distributed_b200.models.llama import LlamaConfig
+    from neuronx_distributed_b200.models.llama_inference import LlamaForInference
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.utils.speculative import speculative_generate
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+
+    def make(seed, layers):
+        torch.manual_seed(seed)
+        cfg = LlamaConfig(vocab_size=96, hidden_size=32, intermediate_size=64, num_hidden_layers=layers, num_attention_heads=4,
+                          num_key_value_heads=2, dtype=torch.float32, max_position_embeddings=64)
+        return LlamaForInference(cfg, batch_size=1, max_seq_len=64).eval()
+
+    target = make(1, 2)
+    prompt = torch.randint(0, 96, (1, 7), generator=torch.Generator().manual_seed(9))
+    want = target.generate(prompt, 12)
+    for draft in (make(1, 2), make(5, 1)):
+        target.kv.reset()
+        got, acc = speculative_generate(target, draft, prompt, 12, speculation_length=3)
+        assert torch.equal(got, want), (got, want, acc)
+    # same-weights draft: every proposal accepted
+    target.kv.reset()
+    _, acc = speculative_generate(target, make(1, 2), prompt, 12, speculation_length=3)
+    assert acc > 2.0
+
+
+def test_speculative_decoding_matches_greedy():
+    run_distributed(_speculative, 1, timeout=120)
