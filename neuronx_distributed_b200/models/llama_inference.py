@@ -20,14 +20,16 @@ from .llama import LlamaConfig, LlamaForCausalLM
 
 class LlamaForInference(nn.Module):
     def __init__(self, cfg: LlamaConfig, batch_size: int = 1, max_seq_len: int = 2048, on_device_sampling: bool = True,
-                 sampler: Optional[Sampler] = None):
+                 sampler: Optional[Sampler] = None, lm_cls=None):
+        """``lm_cls``: any decoder built from Llama attention blocks (``LlamaForCausalLM`` default; ``MixtralForCausalLM`` for
+        the MoE families — its layers' ``mlp`` returns ``(y, router_logits)``, handled in ``_body``)."""
         super().__init__()
         cfg.sequence_parallel_enabled = False
         cfg.activation_checkpointing = "none"
         self.cfg = cfg
-        self.lm = LlamaForCausalLM(cfg)
+        self.lm = (lm_cls or LlamaForCausalLM)(cfg)
         self.batch_size, self.max_seq_len = batch_size, max_seq_len
-        attn0 = self.lm.model.layers[0].self_attn
+        attn0 = self._core.layers[0].self_attn
         self.kv = KVCacheManager(cfg.num_hidden_layers, batch_size, max_seq_len, attn0.num_kv_heads_local, cfg.head_dim,
                                  dtype=cfg.dtype, device=cfg.device)
         self.sampler = sampler or Sampler(top_k=1, vocab_parallel=True)
@@ -35,6 +37,10 @@ class LlamaForInference(nn.Module):
         cos, sin = ops.rope.rope_tables(max_seq_len, cfg.head_dim, cfg.rope_theta, cfg.device, 0, cfg.rope_scaling_factor)
         self.register_buffer("rope_cos", cos, persistent=False)
         self.register_buffer("rope_sin", sin, persistent=False)
+
+    @property
+    def _core(self):
+        return getattr(self.lm, "model", self.lm)        # Llama nests the decoder under .model, Mixtral/DBRX do not
 
     def load_state_dict(self, sd, strict: bool = True):
         return self.lm.load_state_dict(sd, strict=strict)
@@ -79,11 +85,13 @@ class LlamaForInference(nn.Module):
         return x + att.o_proj(o)
 
     def _body(self, input_ids: torch.Tensor, positions: Optional[torch.Tensor], prefill: bool, kv_len: Optional[int]):
-        x = self.lm.model.embed_tokens(input_ids).transpose(0, 1).contiguous()     # [S, B, H]
-        for i, layer in enumerate(self.lm.model.layers):
+        core = self._core
+        x = core.embed_tokens(input_ids).transpose(0, 1).contiguous()               # [S, B, H]
+        for i, layer in enumerate(core.layers):
             x = self._attn_block(i, layer, x, positions, prefill, kv_len)
-            x = x + layer.mlp(layer.post_attention_layernorm(x))
-        return self.lm.model.norm(x)
+            y = layer.mlp(layer.post_attention_layernorm(x))
+            x = x + (y[0] if isinstance(y, tuple) else y)                           # MoE blocks also return router logits
+        return core.norm(x)
 
     # ------------------------------------------------------------------ entry points
     @torch.no_grad()
