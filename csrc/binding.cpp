@@ -167,8 +167,9 @@ static Tensor decode_attention(const Tensor& q, const Tensor& k, const Tensor& v
   TORCH_CHECK(H % Hkv == 0 && k.size(0) == B);
   TORCH_CHECK(q.stride(2) % 8 == 0 && k.stride(1) % 8 == 0 && k.stride(2) % 8 == 0 && v.stride(1) % 8 == 0 && v.stride(2) % 8 == 0);
   c10::cuda::CUDAGuard guard(q.device());
-  int splits = (2 * 148 + B * Hkv - 1) / (B * Hkv);
-  splits = std::max(1, std::min(std::min(splits, 32), (L + 127) / 128));
+  // enough CTAs for ~6 per SM (the kernel is latency-bound per CTA: 8 cache rows in flight), at least 64 rows per split
+  int splits = (6 * 148 + B * Hkv - 1) / (B * Hkv);
+  splits = std::max(1, std::min(std::min(splits, 64), (L + 63) / 64));
   Tensor out = at::empty({B, 1, H, 128}, q.options());
   Tensor part_o = at::empty({B * H * splits, 128}, q.options().dtype(at::kFloat));
   Tensor part_ml = at::empty({B * H * splits, 2}, q.options().dtype(at::kFloat));
