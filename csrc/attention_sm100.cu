@@ -788,7 +788,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
 
 // δ·scale and lse·log2e per (b, h, s): one warp per row of 128 elements.
 __global__ void fa_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ go,
-                                   const float* __restrict__ lse, float* __restrict__ stats, long stats_stride, int B, int S,
+                                   const float* __restrict__ lse, const float* __restrict__ dlse, float* __restrict__ stats,
+                                   long stats_stride, int B, int S,
                                    int H, int S_pad, long o_sb, long o_ss, long o_sh, long g_sb, long g_ss, long g_sh,
                                    float scale) {
   const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -806,7 +807,10 @@ __global__ void fa_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __
   if (lane == 0) {
     const long idx = ((long)b * H + h) * S_pad + s;
     stats[idx] = -lse[((long)b * H + h) * S + s] * 1.4426950408889634f;
-    stats[stats_stride + idx] = -acc * scale;
+    // a gradient flowing into LSE itself (ring attention merges blocks through their LSEs) adds g_lse·P to dS, i.e. it
+    // simply shifts δ: dS = P∘(dP − (δ − g_lse))
+    const float g_lse = dlse ? dlse[((long)b * H + h) * S + s] : 0.f;
+    stats[stats_stride + idx] = -(acc - g_lse) * scale;
   }
 }
 
@@ -873,7 +877,8 @@ void flash_attn_fwd(const void* q, const void* k, const void* v, void* out, floa
   NXD_CUDA_CHECK(cudaGetLastError());
 }
 
-void flash_attn_bwd(const void* go, const void* q, const void* k, const void* v, const void* o, const float* lse, void* dq,
+void flash_attn_bwd(const void* go, const void* q, const void* k, const void* v, const void* o, const float* lse,
+                    const float* dlse, void* dq,
                     void* dk, void* dv, float* stats, float* dq_acc, int B, int S_q, int S_kv, int H, int Hkv, int S_pad,
                     const long* gs, const long* qs, const long* ks, const long* vs, const long* os, const long* dqs,
                     const long* dks, const long* dvs, float scale, bool causal, cudaStream_t st) {
@@ -897,7 +902,7 @@ void flash_attn_bwd(const void* go, const void* q, const void* k, const void* v,
     const long warps = (long)B * H * S_q;
     const int threads = 256;
     const long blocks = (warps * 32 + threads - 1) / threads;
-    fa_bwd_prep_kernel<<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)go, lse, stats,
+    fa_bwd_prep_kernel<<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)go, lse, dlse, stats,
                                                             p.stats_stride, B, S_q, H, S_pad, os[0], os[1], os[2], gs[0],
                                                             gs[1], gs[2], scale);
   }

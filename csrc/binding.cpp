@@ -243,7 +243,8 @@ static std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, cons
 }
 
 static std::vector<Tensor> flash_attn_bwd(const Tensor& go, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& o,
-                                          const Tensor& lse, bool causal, double scale, bool sbhd_out) {
+                                          const Tensor& lse, bool causal, double scale, bool sbhd_out,
+                                          const c10::optional<Tensor>& dlse) {
   check_qkv(q, "q"); check_qkv(k, "k"); check_qkv(v, "v"); check_qkv(go, "grad_out"); check_qkv(o, "out");
   const int B = q.size(0), S = q.size(1), H = q.size(2), Skv = k.size(1), Hkv = k.size(2);
   TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == (int64_t)B * H * S);
@@ -258,7 +259,12 @@ static std::vector<Tensor> flash_attn_bwd(const Tensor& go, const Tensor& q, con
   auto st3 = [](const Tensor& t, long* out) { out[0] = t.stride(0); out[1] = t.stride(1); out[2] = t.stride(2); };
   long gs[3], qs[3], ks[3], vs[3], os[3], dqs[3], dks[3], dvs[3];
   st3(go, gs); st3(q, qs); st3(k, ks); st3(v, vs); st3(o, os); st3(dq, dqs); st3(dk, dks); st3(dv, dvs);
-  nxd::flash_attn_bwd(go.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(),
+  const float* dlse_p = nullptr;
+  if (dlse.has_value()) {
+    TORCH_CHECK(dlse->scalar_type() == at::kFloat && dlse->is_contiguous() && dlse->numel() == lse.numel());
+    dlse_p = dlse->data_ptr<float>();
+  }
+  nxd::flash_attn_bwd(go.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), dlse_p,
                       dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), stats.data_ptr<float>(), dq_acc.data_ptr<float>(), B, S,
                       Skv, H, Hkv, S_pad, gs, qs, ks, vs, os, dqs, dks, dvs, (float)scale, causal, stream());
   return {dq, dk, dv};
@@ -416,7 +422,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("grouped_gemm", &grouped_gemm);
   m.def("grouped_wgrad", &grouped_wgrad);
   m.def("flash_attn_fwd", &flash_attn_fwd);
-  m.def("flash_attn_bwd", &flash_attn_bwd);
+  m.def("flash_attn_bwd", &flash_attn_bwd, py::arg("go"), py::arg("q"), py::arg("k"), py::arg("v"), py::arg("o"), py::arg("lse"),
+        py::arg("causal"), py::arg("scale"), py::arg("sbhd_out"), py::arg("dlse") = py::none());
   m.def("ag_gemm_bf16", &ag_gemm_bf16);
   m.def("gemm_rs_bf16", &gemm_rs_bf16);
   m.def("tp_gemm_2cta", &tp_gemm_2cta);

@@ -87,7 +87,8 @@ void flash_attn_fwd(const void* q, const void* k, const void* v, void* out, floa
                     int Hkv, const long* qs, const long* ks, const long* vs, const long* os, float scale, bool causal,
                     cudaStream_t st);
 
-void flash_attn_bwd(const void* go, const void* q, const void* k, const void* v, const void* o, const float* lse, void* dq,
+void flash_attn_bwd(const void* go, const void* q, const void* k, const void* v, const void* o, const float* lse,
+                    const float* dlse, void* dq,
                     void* dk, void* dv, float* stats, float* dq_acc, int B, int S_q, int S_kv, int H, int Hkv, int S_pad,
                     const long* gs, const long* qs, const long* ks, const long* vs, const long* os, const long* dqs,
                     const long* dks, const long* dvs, float scale, bool causal, cudaStream_t st);

@@ -8,8 +8,9 @@ mask, a block that originated on a *later* rank is skipped, the local block is c
 
 B200 design: the ring transfer is an NCCL p2p exchange issued *before* the block's attention so it overlaps the
 compute; the exchange is itself an autograd node (its backward moves dK/dV the opposite way round the ring), so
-backward is the exact transpose of forward without a hand-written second pass.  Per-block attention is the
-flash kernel (returns LSE) on CUDA and an fp32 reference on CPU.
+backward is the exact transpose of forward without a hand-written second pass.  Per-block attention is the own tcgen05
+flash kernel with a differentiable LSE output (``ops.attention.flash_attention_with_lse``; head_dim 128, bf16), the SDPA
+flash op for other shapes on CUDA, and an fp32 reference on CPU.
 """
 from __future__ import annotations
 
@@ -25,6 +26,12 @@ from ...parallel_layers import parallel_state as ps
 def block_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool, scale: float
                     ) -> Tuple[torch.Tensor, torch.Tensor]:
     """q [B,Sq,H,D], k/v [B,Sk,Hkv,D] → (out [B,Sq,H,D], lse [B,H,Sq] fp32)."""
+    if q.is_cuda:
+        from ... import ops
+
+        own = ops.attention.flash_attention_with_lse(q, k, v, causal, scale)      # tcgen05 kernels, LSE differentiable
+        if own is not None:
+            return own
     hq, hkv = q.shape[2], k.shape[2]
     qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
     if hq != hkv:

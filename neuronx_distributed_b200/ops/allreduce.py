@@ -13,7 +13,9 @@ import torch.distributed as dist
 from . import _ext, symm
 
 _MAX_BYTES = int(os.environ.get("NXD_ONESHOT_AR_MAX_KB", "2048")) << 10
-_ENABLED = os.environ.get("NXD_ONESHOT_AR", "1") == "1"
+# "infer" (default): only under torch.no_grad()/inference_mode — the latency-bound decode path it was built for, validated on
+# 2 GPUs incl. CUDA-graph replay and in the 4-GPU training bench; "1": always; "0": never (NCCL only).
+_MODE = os.environ.get("NXD_ONESHOT_AR", "infer")
 _STATE: Dict[int, tuple] = {}
 
 
@@ -32,7 +34,9 @@ def reset() -> None:
 
 
 def eligible(x: torch.Tensor, group) -> bool:
-    if not (_ENABLED and x.is_cuda and x.dtype in (torch.bfloat16, torch.float32) and x.is_contiguous()):
+    if _MODE == "0" or (_MODE == "infer" and torch.is_grad_enabled()):
+        return False
+    if not (x.is_cuda and x.dtype in (torch.bfloat16, torch.float32) and x.is_contiguous()):
         return False
     nbytes = x.numel() * x.element_size()
     if nbytes == 0 or nbytes % 16 or nbytes > _MAX_BYTES:

@@ -81,6 +81,36 @@ class _FlashAttn(torch.autograd.Function):
         return dq, dk, dv, None, None
 
 
+class _FlashAttnLse(torch.autograd.Function):
+    """Same kernels, but LSE is a differentiable output: ring attention merges per-block results through their LSEs, and
+    a gradient into LSE only shifts δ in the backward kernel (``dS = P∘(dP − (δ − g_lse))``)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, causal, scale):
+        q, k, v = _tma_view(q), _tma_view(k), _tma_view(v)
+        _ext.count_launch()
+        o, lse = _ext.ext().flash_attn_fwd(q, k, v, bool(causal), float(scale), False)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.causal, ctx.scale = causal, scale
+        return o, lse
+
+    @staticmethod
+    def backward(ctx, go, g_lse):
+        q, k, v, o, lse = ctx.saved_tensors
+        _ext.count_launch(4)
+        go = torch.zeros_like(o) if go is None else go
+        dlse = None if g_lse is None else g_lse.float().contiguous()
+        dq, dk, dv = _ext.ext().flash_attn_bwd(_tma_view(go.to(o.dtype)), q, k, v, o, lse, bool(ctx.causal), float(ctx.scale), False, dlse)
+        return dq, dk, dv, None, None
+
+
+def flash_attention_with_lse(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool, scale: float):
+    """``(out [B,S,H,D], lse [B,H,S] fp32)`` on the tcgen05 kernels, or ``None`` when they do not apply."""
+    if _own_kernel_ok(q, k, v) and (not causal or q.shape[1] == k.shape[1]) and hasattr(_ext.ext(), "flash_attn_bwd"):
+        return _FlashAttnLse.apply(q, k, v, causal, scale)
+    return None
+
+
 def flash_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True,
                     scale: Optional[float] = None) -> torch.Tensor:
     scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])

@@ -118,3 +118,29 @@ def test_flash_attention_fwd_bwd_vs_fp32_reference(layout, causal):
 
     assert rel(o, ro) < 2e-2
     assert rel(q.grad, qf.grad) < 3e-2 and rel(k.grad, kf.grad) < 3e-2 and rel(v.grad, vf.grad) < 3e-2
+
+
+def test_flash_attention_lse_is_differentiable():
+    """Ring attention merges blocks through their LSEs: gradients must flow through the LSE output of the own kernels."""
+    import math
+
+    from neuronx_distributed_b200.ops import attention
+
+    torch.manual_seed(3)
+    B, S, Sk, H, D = 2, 256, 384, 4, 128
+    q = torch.randn(B, S, H, D, device="cuda").bfloat16().requires_grad_(True)
+    k = torch.randn(B, Sk, H, D, device="cuda").bfloat16().requires_grad_(True)
+    v = torch.randn(B, Sk, H, D, device="cuda").bfloat16().requires_grad_(True)
+    res = attention.flash_attention_with_lse(q, k, v, False, 1.0 / math.sqrt(D))
+    assert res is not None
+    o, lse = res
+    w_o = torch.randn_like(o); w_l = torch.randn_like(lse)
+    ((o.float() * w_o.float()).sum() + (lse * w_l).sum()).backward()
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("bqhd,bkhd->bhqk", qf, kf) / math.sqrt(D)
+    ro = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), vf)
+    rl = torch.logsumexp(s, -1)
+    ((ro * w_o.float()).sum() + (rl * w_l).sum()).backward()
+    rel = lambda a, b: ((a.float() - b).abs().max() / b.abs().max()).item()
+    assert rel(o, ro) < 2e-2 and (lse - rl).abs().max() < 2e-2
+    assert rel(q.grad, qf.grad) < 3e-2 and rel(k.grad, kf.grad) < 3e-2 and rel(v.grad, vf.grad) < 3e-2

@@ -139,6 +139,7 @@ def _oneshot_ar(rank, world):
     from neuronx_distributed_b200.ops import allreduce
     from neuronx_distributed_b200.parallel_layers import parallel_state as ps
 
+    allreduce._MODE = "1"
     ps.initialize_model_parallel(tensor_model_parallel_size=world)
     g = ps.get_tensor_model_parallel_group()
     dev = torch.device("cuda", rank)
