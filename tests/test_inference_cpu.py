@@ -111,3 +111,36 @@ def _speculative(rank, world):
 
 def test_speculative_decoding_matches_greedy():
     run_distributed(_speculative, 1, timeout=120)
+
+
+def _flash_decode(rank, world):
+    """Sequence-sharded KV cache inside a KV-replica group: distributed flash-decoding equals full attention over the whole cache."""
+    import math
+
+    import torch.distributed as dist
+
+    from neuronx_distributed_b200.modules.attention.flash_decode import flash_decode_attention, write_decode_sharded
+
+    g = dist.group.WORLD
+    B, L, Hl, Hkv, D = 3, 16, 2, 1, 8                       # each rank has 2 query heads; both ranks share 1 kv head
+    gen = torch.Generator().manual_seed(4)
+    k_full = torch.randn(B, L, Hkv, D, generator=gen); v_full = torch.randn(B, L, Hkv, D, generator=gen)
+    q_all = torch.randn(B, 1, world * Hl, D, generator=gen)
+    positions = torch.tensor([3, 9, 15])
+    l_local = L // world
+    k_loc = k_full[:, rank * l_local:(rank + 1) * l_local].clone(); v_loc = v_full[:, rank * l_local:(rank + 1) * l_local].clone()
+    # the newest token's K/V arrives through the sharded write
+    k_new = torch.randn(B, 1, Hkv, D, generator=gen); v_new = torch.randn(B, 1, Hkv, D, generator=gen)
+    write_decode_sharded(k_loc, v_loc, k_new, v_new, positions, rank)
+    b = torch.arange(B)
+    k_full[b, positions] = k_new[:, 0]; v_full[b, positions] = v_new[:, 0]
+    q = q_all[:, :, rank * Hl:(rank + 1) * Hl]
+    out = flash_decode_attention(q, k_loc, v_loc, positions, g)
+    s = torch.einsum("bhd,blhd->bhl", q[:, 0], k_full.repeat_interleave(Hl, 2)) / math.sqrt(D)
+    mask = torch.arange(L)[None, :] <= positions[:, None]
+    ref = torch.einsum("bhl,blhd->bhd", s.masked_fill(~mask[:, None], float("-inf")).softmax(-1), v_full.repeat_interleave(Hl, 2))
+    torch.testing.assert_close(out[:, 0], ref, rtol=1e-5, atol=1e-5)
+
+
+def test_distributed_flash_decoding_matches_full_attention():
+    run_distributed(_flash_decode, 2, timeout=60)
