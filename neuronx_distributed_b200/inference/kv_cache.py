@@ -59,6 +59,17 @@ class KVCacheManager:
         self.k[layer].index_put_((b, pos), self._q(k))
         self.v[layer].index_put_((b, pos), self._q(v))
 
+    def compact_window(self, positions: torch.Tensor, src_offsets: torch.Tensor) -> None:
+        """After tree verification: entry ``positions[b] + src_offsets[b, i]`` (an accepted tree node) moves to
+        ``positions[b] + i`` for every layer, so the accepted path becomes a contiguous continuation of the sequence."""
+        B, n = src_offsets.shape
+        b = torch.arange(B, device=positions.device).unsqueeze(1).expand(B, n)
+        src = positions.unsqueeze(1) + src_offsets
+        dst = positions.unsqueeze(1) + torch.arange(n, device=positions.device).unsqueeze(0)
+        for layer in range(self.num_layers):
+            self.k[layer].index_put_((b, dst), self.k[layer][b, src])
+            self.v[layer].index_put_((b, dst), self.v[layer][b, src])
+
     def get(self, layer: int, length: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         k, v = self.k[layer], self.v[layer]
         if length is not None:

@@ -50,7 +50,7 @@ class LlamaForInference(nn.Module):
 
     # ------------------------------------------------------------------ shared pieces
     def _attn_block(self, layer_idx: int, layer, x: torch.Tensor, positions: Optional[torch.Tensor], prefill: bool,
-                    kv_len: Optional[int]) -> torch.Tensor:
+                    kv_len: Optional[int], tree=None) -> torch.Tensor:
         att = layer.self_attn
         h = layer.input_layernorm(x)
         q, k, v = att.qkv_proj(h)                          # [S, B, h*D]
@@ -62,12 +62,15 @@ class LlamaForInference(nn.Module):
         if not prefill and S > 1:
             # speculation window: W new tokens per sequence at positions p..p+W-1, causal among themselves, full cache before
             W = S
-            idx = (positions.unsqueeze(1) + torch.arange(W, device=q.device).unsqueeze(0)).clamp(max=self.max_seq_len - 1)
+            # linear window: node w sits at sequence position p+w; Medusa tree: node w sits at p+depth[w] (its cache SLOT is
+            # still p+w) and sees only its ancestors inside the window
+            depth = torch.arange(W, device=q.device) if tree is None else tree[1]
+            idx = (positions.unsqueeze(1) + depth.unsqueeze(0)).clamp(max=self.max_seq_len - 1)
             cos, sin = self.rope_cos[idx], self.rope_sin[idx]                     # [B, W, D/2]
             q, k = _rope_window(q, cos, sin), _rope_window(k, cos, sin)
             self.kv.write_window(layer_idx, k, v, positions)
             kc, vc = self.kv.get(layer_idx, kv_len)
-            o = _window_attention(q, kc, vc, positions)
+            o = _window_attention(q, kc, vc, positions, None if tree is None else tree[0])
         elif prefill:
             cos, sin = self.rope_cos[:S], self.rope_sin[:S]
             q, k = ops.rope.apply_rotary(q, cos, sin), ops.rope.apply_rotary(k, cos, sin)
@@ -84,11 +87,11 @@ class LlamaForInference(nn.Module):
         o = o.transpose(0, 1).reshape(S, B, att.num_heads_local * D)
         return x + att.o_proj(o)
 
-    def _body(self, input_ids: torch.Tensor, positions: Optional[torch.Tensor], prefill: bool, kv_len: Optional[int]):
+    def _body(self, input_ids: torch.Tensor, positions: Optional[torch.Tensor], prefill: bool, kv_len: Optional[int], tree=None):
         core = self._core
         x = core.embed_tokens(input_ids).transpose(0, 1).contiguous()               # [S, B, H]
         for i, layer in enumerate(core.layers):
-            x = self._attn_block(i, layer, x, positions, prefill, kv_len)
+            x = self._attn_block(i, layer, x, positions, prefill, kv_len, tree)
             y = layer.mlp(layer.post_attention_layernorm(x))
             x = x + (y[0] if isinstance(y, tuple) else y)                           # MoE blocks also return router logits
         return core.norm(x)
@@ -114,15 +117,19 @@ class LlamaForInference(nn.Module):
         return self.sampler.sample(logits) if self.on_device_sampling else logits
 
     @torch.no_grad()
-    def speculation_forward(self, input_ids: torch.Tensor, positions: torch.Tensor, kv_len: Optional[int] = None) -> torch.Tensor:
+    def speculation_forward(self, input_ids: torch.Tensor, positions: torch.Tensor, kv_len: Optional[int] = None,
+                            tree_mask: Optional[torch.Tensor] = None, tree_depth: Optional[torch.Tensor] = None,
+                            return_hidden: bool = False):
         """Verify a window: ``input_ids`` [B, W] placed at ``positions[b] .. positions[b]+W-1`` → greedy next token after
-        each of the W positions, ``[B, W]`` (reference ``examples/inference`` speculation model, ``speculation_length``)."""
-        h = self._body(input_ids, positions, False, kv_len)                      # [W, B, H]
+        each of the W positions, ``[B, W]`` (reference ``examples/inference`` speculation model, ``speculation_length``).
+        With ``tree_mask [W, W]`` (True = node row sees node column) and ``tree_depth [W]`` the window is a Medusa candidate
+        tree instead of a chain.  ``return_hidden`` also returns the final hidden states ``[B, W, H]`` (Medusa heads input)."""
+        tree = None if tree_mask is None else (tree_mask.bool(), tree_depth.long())
+        h = self._body(input_ids, positions, False, kv_len, tree)                # [W, B, H]
         logits = self.lm.lm_head(h).float()                                       # [W, B, V/tp]
         W, B = logits.shape[:2]
-        if self.on_device_sampling:
-            return self.sampler.sample(logits.reshape(W * B, -1)).view(W, B).t()
-        return logits.transpose(0, 1)
+        out = self.sampler.sample(logits.reshape(W * B, -1)).view(W, B).t() if self.on_device_sampling else logits.transpose(0, 1)
+        return (out, h.transpose(0, 1)) if return_hidden else out
 
     @torch.no_grad()
     def generate(self, prompt_ids: torch.Tensor, max_new_tokens: int, prompt_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -156,15 +163,24 @@ def _rope_window(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch
     return torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1).to(x.dtype)
 
 
-def _window_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
-    """q [B,W,H,D] at positions p..p+W-1 vs cache k/v [B,L,Hkv,D]: token w sees cache entries ≤ p+w."""
+def _window_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, positions: torch.Tensor,
+                      tree_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B,W,H,D] in cache slots p..p+W-1 vs cache k/v [B,L,Hkv,D].  Chain: token w sees slots ≤ p+w.  Tree (``tree_mask``
+    [W,W]): node w sees every slot < p (the committed sequence) and the window slots of its ancestors."""
     B, W, H, D = q.shape
     Hkv, L = k.shape[2], k.shape[1]
     qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
     if H != Hkv:
         kt, vt = kt.repeat_interleave(H // Hkv, 1), vt.repeat_interleave(H // Hkv, 1)
-    lim = positions[:, None] + torch.arange(W, device=q.device)[None, :]                       # [B, W]
-    mask = (torch.arange(L, device=q.device)[None, None, :] <= lim[:, :, None])[:, None]       # [B,1,W,L]
+    cols = torch.arange(L, device=q.device)
+    if tree_mask is None:
+        lim = positions[:, None] + torch.arange(W, device=q.device)[None, :]                   # [B, W]
+        mask = (cols[None, None, :] <= lim[:, :, None])[:, None]                               # [B,1,W,L]
+    else:
+        rel = cols[None, :] - positions[:, None]                                               # [B, L] slot index inside the window
+        inside = (rel >= 0) & (rel < W)
+        tm = tree_mask.to(q.device)[:, rel.clamp(0, W - 1)].permute(1, 0, 2)                   # [B, W, L]
+        mask = ((rel < 0)[:, None, :] | (inside[:, None, :] & tm))[:, None]
     return torch.nn.functional.scaled_dot_product_attention(qt, kt, vt, attn_mask=mask).transpose(1, 2)
 
 
