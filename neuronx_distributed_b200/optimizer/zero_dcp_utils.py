@@ -41,7 +41,13 @@ def load_optim_state_dict(path: str, inner) -> Dict[str, Any]:
 
     r = dist.get_rank(inner.pg)
     d = os.path.join(path, f"zero1_rank_{r:02d}_of_{dist.get_world_size(inner.pg):02d}")
-    target = _to_dtensor_dict(inner)
+    # allocate the load targets from the checkpoint's own metadata: a freshly built optimizer has no Adam moments yet, so its
+    # live state cannot serve as the template
+    from torch.distributed.checkpoint.metadata import TensorStorageMetadata
+
+    md = dcp.FileSystemReader(d).read_metadata()
+    target = {k: torch.empty(tuple(v.size), dtype=v.properties.dtype) for k, v in md.state_dict_metadata.items()
+              if isinstance(v, TensorStorageMetadata)}
     dcp.load(target, checkpoint_id=d, no_dist=True)
     layout = torch.load(os.path.join(d, "layout.pt"), weights_only=False)
     base_state = {}

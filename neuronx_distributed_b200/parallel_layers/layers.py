@@ -132,7 +132,10 @@ class BaseParallelLayer(nn.Module):
 
 
 def _group_info(group) -> Tuple[Any, int, int]:
-    group = group if group is not None else ps.get_tensor_model_parallel_group()
+    if group is None:
+        # default TP group: honour the cached size/rank overrides (reference parallel_state.py:895-926), which is how
+        # ``inference.NxDParallelState`` builds any rank's shard in a single process for offline checkpoint sharding
+        return ps.get_tensor_model_parallel_group(), ps.get_tensor_model_parallel_size(), ps.get_tensor_model_parallel_rank()
     return group, dist.get_world_size(group), dist.get_rank(group)
 
 
