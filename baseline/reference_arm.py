@@ -180,7 +180,18 @@ def main(args) -> int:
             torch.cuda.synchronize()
 
     for i in range(args.warmup):
-        train_step(dev_ids[i])
+        try:
+            train_step(dev_ids[i])
+        except torch.cuda.OutOfMemoryError:
+            # the un-fused reference keeps more activation memory than the other arm; on ONE GPU (no peers to desynchronise)
+            # fall back to micro-batch 1 instead of failing — the JSON line reports the micro-batch actually used
+            if world != 1 or mbs == 1:
+                raise
+            opt.zero_grad()
+            import gc
+            gc.collect(); torch.cuda.empty_cache()
+            mbs = 1
+            train_step(dev_ids[i])
     sync()
     if cpu_debug:
         sync(); t0 = time.perf_counter()
