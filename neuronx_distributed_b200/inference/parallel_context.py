@@ -4,9 +4,7 @@ sharding and shape-only construction.  Implemented with the parallel-state rank/
 from __future__ import annotations
 
 import contextlib
-from typing import Optional
 
-import torch
 import torch.distributed as dist
 
 from ..parallel_layers import parallel_state as ps

@@ -9,7 +9,7 @@ along ``partition_dim`` into ``num_partitions * partition_stride`` chunks and ra
 """
 from __future__ import annotations
 
-from typing import Any, Dict, Optional
+from typing import Any, Dict
 
 import torch
 from torch import nn

@@ -4,7 +4,6 @@ self-attention / intermediate / output linears swapped for Column/RowParallelLin
 ``[B, S, H]`` layout (no sequence parallelism in the reference's BERT recipe), bidirectional attention with a padding mask."""
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import Optional
 

@@ -10,7 +10,7 @@ RoPE, RMSNorm, attention and the loss are the hand-written kernels in ``ops/``.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional, Tuple
 
 import torch
@@ -21,7 +21,6 @@ from ..utils.profiling import nvtx_range
 from .. import ops
 from ..modules.qkv_linear import GQAQKVColumnParallelLinear
 from ..modules.rms_norm import RMSNorm
-from ..parallel_layers import mappings
 from ..parallel_layers import parallel_state as ps
 from ..parallel_layers.layers import ColumnParallelLinear, ParallelEmbedding, RowParallelLinear
 from ..parallel_layers.loss_functions import parallel_cross_entropy

@@ -5,15 +5,13 @@ No sequence parallelism at inference: Row-parallel outputs are all-reduced."""
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Tuple
+from typing import Optional
 
 import torch
 from torch import nn
 
 from .. import ops
 from ..inference.kv_cache import KVCacheManager
-from ..operators import argmax as dist_argmax
-from ..parallel_layers import parallel_state as ps
 from ..utils.sampling import Sampler
 from .llama import LlamaConfig, LlamaForCausalLM
 

@@ -1,7 +1,7 @@
 """LoRA configuration (reference ``modules/lora/config.py:6-148``)."""
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Union
 
 

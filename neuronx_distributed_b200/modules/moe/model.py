@@ -8,7 +8,7 @@ from typing import Optional, Tuple
 import torch
 from torch import nn
 
-from ...parallel_layers import comm, mappings
+from ...parallel_layers import mappings
 from ...parallel_layers import parallel_state as ps
 from . import token_shuffling
 

@@ -1,7 +1,7 @@
 """MoE configuration objects (reference ``modules/moe/moe_configs.py:22-273``)."""
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional
 
 import torch

@@ -22,7 +22,6 @@ from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
-from torch import nn
 from torch.nn import init
 from torch.nn.parameter import Parameter
 

@@ -19,12 +19,12 @@ Protocol state (epochs, cumulative counters) lives in :class:`TPWorkspace`, one 
 from __future__ import annotations
 
 import os
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
-from . import _ext, gemm, symm
+from . import _ext, symm
 
 BLOCK_M = 128
 MAX_ROW_BLOCKS = 64

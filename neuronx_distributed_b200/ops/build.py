@@ -6,7 +6,6 @@ pages map to our code."""
 from __future__ import annotations
 
 import os
-import shutil
 import sys
 from pathlib import Path
 

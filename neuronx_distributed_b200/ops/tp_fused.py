@@ -8,12 +8,9 @@ extension exposes the kernels; selection can be forced off with ``NXD_TP_BACKEND
 from __future__ import annotations
 
 import os
-from typing import Optional
 
 import torch
-import torch.distributed as dist
 
-from . import _ext
 
 _BACKEND = os.environ.get("NXD_TP_BACKEND", "fused")
 

@@ -7,7 +7,7 @@ scale) and write its updated shard into every peer's parameter buffer (push all-
 from __future__ import annotations
 
 import os
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist

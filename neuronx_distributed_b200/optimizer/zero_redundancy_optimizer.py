@@ -28,9 +28,8 @@ from __future__ import annotations
 
 import os
 
-import math
-from dataclasses import dataclass, field
-from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple, Type
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, Iterable, List, Optional, Tuple, Type
 
 import torch
 import torch.distributed as dist

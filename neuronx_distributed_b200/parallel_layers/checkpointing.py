@@ -16,7 +16,7 @@ import torch.distributed as dist
 from torch import nn
 
 from . import parallel_state as ps
-from .utils import cast_all, create_local_weight
+from .utils import cast_all
 
 
 def _chkpt_dir(base: str, with_dp: bool = False) -> str:

@@ -11,7 +11,7 @@ GEMM+collective kernels in ``ops/tp_fused.py``.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Union
+from typing import Sequence, Union
 
 import torch
 import torch.distributed as dist

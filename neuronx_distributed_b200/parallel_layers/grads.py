@@ -17,12 +17,11 @@ import os
 from typing import Dict, Iterable, List, Optional, Sequence, Union
 
 import torch
-import torch.distributed as dist
 
 from ..utils.logger import get_logger
 from . import comm
 from . import parallel_state as ps
-from .utils import param_is_not_shared, param_is_not_tensor_parallel_duplicate
+from .utils import param_is_not_shared
 
 logger = get_logger()
 _ALLREDUCE_BUCKET_CAP_MB = 512

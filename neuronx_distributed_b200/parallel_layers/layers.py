@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import math
 import warnings
-from typing import Any, Callable, Dict, Optional, Sequence, Tuple, Union
+from typing import Any, Callable, Dict, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -31,7 +31,6 @@ from torch import nn
 from torch.nn import init
 from torch.nn.parameter import Parameter
 
-from ..utils import cpu_mode, get_device
 from ..utils.logger import get_logger
 from . import comm, mappings
 from . import parallel_state as ps

@@ -17,7 +17,6 @@ coincides with this for tp=1.
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 import torch.distributed as dist

@@ -13,7 +13,7 @@ from torch import nn
 
 from . import parallel_state as ps
 from .layers import ColumnParallelLinear, RowParallelLinear
-from .utils import create_local_weight, divide
+from .utils import divide
 
 
 def get_number_of_extra_heads(num_heads: int, tp_degree: int) -> int:

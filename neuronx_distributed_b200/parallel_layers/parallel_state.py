@@ -20,7 +20,6 @@ Design (B200-first, not a port):
 """
 from __future__ import annotations
 
-import itertools
 import os
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union

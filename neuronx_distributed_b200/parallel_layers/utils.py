@@ -6,12 +6,11 @@ weight sharder key off those attributes, so the names are part of the on-disk/AP
 """
 from __future__ import annotations
 
-import collections
-from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
-from ..utils import cpu_mode, get_device
+from ..utils import get_device
 from . import parallel_state as ps
 
 _MODEL_PARALLEL_ATTRIBUTE_DEFAULTS: Dict[str, Any] = {

@@ -9,7 +9,7 @@ Shape/dtype metadata travels once per (direction, chunk) over the gloo PP group 
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Any, Dict, List, Optional, Sequence, Tuple
+from typing import Any, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist

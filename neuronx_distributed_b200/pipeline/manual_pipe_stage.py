@@ -4,7 +4,6 @@ from __future__ import annotations
 
 from typing import Callable, List, Optional, Sequence
 
-import torch
 from torch import nn
 
 from .partition import create_partitions

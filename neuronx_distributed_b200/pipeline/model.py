@@ -14,8 +14,7 @@ B200 design (differs from the XLA engine):
 """
 from __future__ import annotations
 
-import inspect
-from typing import Any, Callable, Dict, Iterator, List, Optional, Sequence, Tuple, Type
+from typing import Any, Callable, Dict, List, Optional, Tuple, Type
 
 import torch
 import torch.distributed as dist

@@ -9,9 +9,8 @@ shared by several stages (tied embeddings).
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Any, Callable, Dict, List, Optional, Sequence, Set, Tuple, Type
+from typing import Dict, List, Optional, Sequence, Set, Tuple
 
-import torch
 import torch.fx as fx
 from torch import nn
 from torch.fx.passes.split_module import split_module

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import enum
 from dataclasses import dataclass
-from typing import Any, Dict, Optional, TypedDict
+from typing import Any, TypedDict
 
 import torch
 

@@ -13,7 +13,7 @@ from torch import nn
 from ..parallel_layers import mappings
 from ..parallel_layers.layers import ColumnParallelLinear, RowParallelLinear
 from ..parallel_layers.utils import set_tensor_model_parallel_attributes
-from .quantization_config import ActivationQuantizationType, QuantizationType, QuantizedDtype, ScaleDtype
+from .quantization_config import ActivationQuantizationType, QuantizationType, QuantizedDtype
 from .quantization_utils import (dequantize_blockwise, quantize_activation_dynamic, quantize_blockwise,
                                  quantize_per_channel, quantize_per_tensor)
 

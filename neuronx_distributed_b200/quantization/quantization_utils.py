@@ -5,7 +5,6 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
-from .quantization_config import QuantizedDtype
 
 _QMAX = {torch.int8: 127.0, torch.float8_e4m3fn: 448.0, torch.float8_e5m2: 57344.0}
 

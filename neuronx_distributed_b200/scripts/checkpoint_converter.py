@@ -10,7 +10,7 @@ from __future__ import annotations
 import argparse
 import os
 import re
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 

@@ -12,7 +12,7 @@ import random
 import shutil
 import time
 from abc import ABC, abstractmethod
-from typing import Any, Callable, List, Optional
+from typing import Any, Callable, List
 
 import torch
 

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import contextlib
 import math
-from typing import Callable, Dict, Iterator, Optional
+from typing import Callable, Dict, Optional
 
 import torch
 import torch.distributed as dist
