@@ -14,9 +14,7 @@ transformers 4.x; this image ships 5.x).
 from __future__ import annotations
 
 import json
-import math
 import os
-import subprocess
 import sys
 import time
 

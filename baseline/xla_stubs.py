@@ -19,7 +19,7 @@ import importlib.abc
 import importlib.machinery
 import sys
 import types
-from typing import Any, List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 import torch.distributed as dist

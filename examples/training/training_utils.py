@@ -5,7 +5,7 @@ from __future__ import annotations
 import json
 import os
 import time
-from typing import Dict, Iterator, Optional
+from typing import Dict, Iterator
 
 import numpy as np
 import torch

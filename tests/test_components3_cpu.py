@@ -1,7 +1,6 @@
 """Quantised expert layers, fp8 KV cache, decode-time fused MoE block, and the Lightning integration driven without Lightning
 (its base classes are import-gated stand-ins in this image)."""
 import torch
-from torch import nn
 
 from dist_utils import run_distributed
 

@@ -1,7 +1,6 @@
 """Unit tests of the model-building components that the bigger model tests only touch indirectly: GQA-QKV with KV replication,
 input-channel parallel conv, pad_model, RNG tracker, grad norm / clip, DistributedLogprob, the extra routers, shared experts,
 token shuffling."""
-import math
 
 import torch
 from torch import nn

@@ -1,6 +1,5 @@
 """Tiny Llama: TP=2 (+SP, +ZeRO-1) must reproduce the TP=1 loss curve (role of the reference's
 combinatorial 4-layer-Llama parity runs)."""
-import pytest
 import torch
 
 from dist_utils import run_distributed

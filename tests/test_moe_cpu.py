@@ -1,5 +1,4 @@
 """MoE correctness vs a dense per-token reference (role of reference test_impl_correctness.py)."""
-import pytest
 import torch
 
 from dist_utils import run_distributed

@@ -6,7 +6,6 @@ gpurun_out/gpu_check.jsonl.  Comparison target is always a plain PyTorch fp32 re
 import json
 import os
 import sys
-import time
 
 import torch
 
