@@ -34,27 +34,9 @@ constexpr uint32_t kTile = BM * HD * 2;          // 32 KB
 constexpr uint32_t kHalf = kTile / 2;            // one [128 × 64] box
 constexpr uint32_t kSmemFwd = 6 * kTile + 1024 /*align*/ + 256 /*barriers*/;
 
-NXD_DEVICE void tcgen05_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Warp-uniform issue helpers: the whole MMA warp runs the issue loop in convergent control flow and one elected lane
-// executes the tcgen05 instruction.  (Issuing from inside `if (lane == 0)` makes the compiler wrap every UTCHMMA in an
-// ELECT / BRA.U.ANY loop with R2UR round trips — ≈19 SASS instructions and ≈100 cycles per MMA, which made the single
-// issuing thread the bottleneck of the backward kernel: ncu source page, profiles/.)
-NXD_DEVICE void mma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
+// Warp-uniform issue: the whole MMA warp runs the issue loop in convergent control flow and one elected lane executes each
+// tcgen05 instruction (helpers tcgen05_mma_f16_e / tcgen05_commit_e in sm100_ptx.cuh explain why; mma_ts is the variant whose
+// A operand is read from TMEM — P of the forward, Pᵀ of the backward).
 NXD_DEVICE void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t"
@@ -63,13 +45,6 @@ NXD_DEVICE void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
-}
-NXD_DEVICE void commit_elect(uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(bar) : "memory");
 }
 NXD_DEVICE void tcgen05_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -256,11 +231,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            mma_ss(tmem_S + st * BN, make_smem_desc(q_s + kb * kHalf + kk * 32, 16, 1024),
+            tcgen05_mma_f16_e(tmem_S + st * BN, make_smem_desc(q_s + kb * kHalf + kk * 32, 16, 1024),
                    make_smem_desc(k_s + kb * kHalf + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
-        commit_elect(bar_ke + 8 * st);
-        commit_elect(bar_s + 8 * st);
-        if (c.j == c.n_kv - 1) commit_elect(bar_qe + 8 * qb);       // last QKᵀ of the item: its Q buffer is free
+        tcgen05_commit_e(bar_ke + 8 * st);
+        tcgen05_commit_e(bar_s + 8 * st);
+        if (c.j == c.n_kv - 1) tcgen05_commit_e(bar_qe + 8 * qb);       // last QKᵀ of the item: its Q buffer is free
       };
       Cur ahead = start(0, 0), cur = ahead;
       if (ahead.ok) { issue_s(ahead); advance(ahead); }
@@ -277,8 +252,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         for (int k = 0; k < BN / 16; ++k)
           mma_ts(tmem_O + ob * HD, tmem_S + st * BN + k * 8, make_smem_desc(v_s + k * 2048, kHalf, 1024), idesc_o,
                  (cur.j | k) ? 1u : 0u);
-        commit_elect(bar_ve + 8 * st);
-        commit_elect(bar_pv);
+        tcgen05_commit_e(bar_ve + 8 * st);
+        tcgen05_commit_e(bar_pv);
         if (ahead.ok) { issue_s(ahead); advance(ahead); }        // overwrites P of tile g — behind PV_g in pipe order
         advance(cur);
       }
@@ -609,9 +584,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            mma_ss(tmem_ST + st * BQ, make_smem_desc(sK + kb * kHalf + kk * 32, 16, 1024),
+            tcgen05_mma_f16_e(tmem_ST + st * BQ, make_smem_desc(sK + kb * kHalf + kk * 32, 16, 1024),
                             make_smem_desc(q_s + kb * (kQTile / 2) + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
-        commit_elect(bar_s + 8 * st);
+        tcgen05_commit_e(bar_s + 8 * st);
       };
       auto issue_dp = [&](int it) {
         const int qs = it % kQStages;
@@ -622,9 +597,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            mma_ss(tmem_dP, make_smem_desc(sV + kb * kHalf + kk * 32, 16, 1024),
+            tcgen05_mma_f16_e(tmem_dP, make_smem_desc(sV + kb * kHalf + kk * 32, 16, 1024),
                             make_smem_desc(g_s + kb * (kQTile / 2) + kk * 32, 16, 1024), idesc_s, (kb | kk) ? 1u : 0u);
-        commit_elect(bar_dp);
+        tcgen05_commit_e(bar_dp);
       };
       issue_st(0);
       issue_dp(0);
@@ -637,25 +612,25 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         const uint32_t q_s = sQ + qs * kQTile, g_s = sdO + qs * kQTile, ds_s = sdS + st * kQTile;
 #pragma unroll
         for (int kk = 0; kk < BQ / 16; ++kk)
-          mma_ss(tmem_dK, make_smem_desc(ds_s + kk * 32, 16, 1024), make_smem_desc(q_s + kk * 2048, kQTile / 2, 1024),
+          tcgen05_mma_f16_e(tmem_dK, make_smem_desc(ds_s + kk * 32, 16, 1024), make_smem_desc(q_s + kk * 2048, kQTile / 2, 1024),
                           idesc_acc, (it | kk) ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < BQ / 16; ++kk)
           mma_ts(tmem_dV, tmem_ST + st * BQ + kk * 8, make_smem_desc(g_s + kk * 2048, kQTile / 2, 1024), idesc_acc,
                          (it | kk) ? 1u : 0u);
-        commit_elect(bar_qe + 8 * qs);
+        tcgen05_commit_e(bar_qe + 8 * qs);
         if (it >= 1) {
           mbar_wait(bar_dqr, (uint32_t)((it - 1) & 1));   // dQᵀ_{it-1} has been read out of TMEM
           tcgen05_fence_after();
         }
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk)
-          mma_ss(tmem_dQ, make_smem_desc(sK + kk * 2048, kHalf, 1024), make_smem_desc(ds_s + kk * 2048, kHalf, 1024),
+          tcgen05_mma_f16_e(tmem_dQ, make_smem_desc(sK + kk * 2048, kHalf, 1024), make_smem_desc(ds_s + kk * 2048, kHalf, 1024),
                           idesc_dq, kk ? 1u : 0u);
-        commit_elect(bar_dq);
+        tcgen05_commit_e(bar_dq);
         if (it + 2 < n_iter) issue_st(it + 2);            // overwrites Pᵀ_it — after dV_it in pipe order
       }
-      commit_elect(bar_acc);
+      tcgen05_commit_e(bar_acc);
     }
     __syncwarp();
   } else if (warp < 6) {
