@@ -209,13 +209,20 @@ def main(args) -> int:
     value = gbs * S * args.steps / (ms_total / 1e3)
     e2e = None
     if not args.no_e2e:
-        sync(); t0 = time.perf_counter(); h2d = d2h = 0
+        sync(); h2d = d2h = 0
+        if cpu_debug:
+            t0 = time.perf_counter()
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True); e0.record()
         for i in range(args.steps):
             h = host_ids[i % len(host_ids)]
             ids = h.to(dev, non_blocking=True); h2d += h.numel() * h.element_size()
             lv = train_step(ids).float().cpu(); d2h += lv.numel() * lv.element_size()
-        sync()
-        tt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if cpu_debug:
+            sync(); dt = time.perf_counter() - t0
+        else:
+            e1.record(); sync(); dt = e0.elapsed_time(e1) / 1e3          # CUDA events, as in the other arm
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": gbs * S * args.steps / float(tt), "unit": "tokens/s", "h2d_bytes_per_step": h2d // args.steps,
                "d2h_bytes_per_step": d2h // args.steps}
