@@ -19,7 +19,6 @@ import os
 import statistics
 import subprocess
 import sys
-import time  # noqa: F401 (ClockSampler thread)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
