@@ -264,7 +264,7 @@ struct TpComm {
   uint32_t* tile_done;
   uint32_t* gemm_done;
   uint32_t gemm_done_target;
-  int push_tma;            // 1: pushers move data with TMA bulk copies through smem; 0: register-staged 16-byte copies
+  int push_tma;            // 0: register-staged 16-byte copies; 1: TMA bulk copies through smem, per item; 2: streaming across items
 };
 constexpr int kMaxRowBlocks = 64;
 
@@ -341,6 +341,76 @@ NXD_DEVICE void tma_push(uint8_t* dst, const uint8_t* src, size_t bytes, uint32_
   asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 
+// Streaming variant of tma_push (push_tma == 2, opt-in until measured): the smem ring is kept full ACROSS the CTA's items — no
+// drain between 1 MB blocks.  Item k's flag is published as soon as all of its store groups have COMPLETED, which
+// `cp.async.bulk.wait_group NST` guarantees for every group older than the newest NST ones; only when the next item is not
+// ready yet (GEMM→RS) or at the very end is the pipeline drained.  `item(k, src, dst, flag)` yields the k-th item of this CTA,
+// `ready(k)` blocks until its source is complete (no-op for the all-gather).
+template <typename ItemFn, typename ReadyFn, typename PendingFn>
+NXD_DEVICE void tma_push_stream(int n_items, size_t item_bytes, uint32_t epoch, uint32_t smem_base, uint32_t bar0,
+                                uint32_t& phases, ItemFn item, ReadyFn ready, PendingFn is_ready) {
+  constexpr uint32_t CH = (uint32_t)kStageBytes;
+  constexpr int NST = kStages;
+  const int cpi = (int)((item_bytes + CH - 1) / CH);          // chunks per item
+  const long total = (long)n_items * cpi;
+  int next_flag = 0;                                          // items [0, next_flag) have been published
+  auto publish_upto = [&](int k_end) {                        // caller guarantees completion of those items' stores
+    if (next_flag >= k_end) return;
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    __threadfence_system();
+    for (; next_flag < k_end; ++next_flag) {
+      const uint8_t* s_; uint8_t* d_; uint32_t* f_;
+      item(next_flag, s_, d_, f_);
+      st_release_sys(f_, epoch);
+    }
+  };
+  auto chunk_bytes = [&](int c) { return (uint32_t)min((size_t)CH, item_bytes - (size_t)c * CH); };
+  long issued = 0;                                            // loads issued so far (global chunk index)
+  int ready_upto = 0;                                         // items [0, ready_upto) are known to be loadable
+  auto load = [&](long g) {
+    const int k = (int)(g / cpi), c = (int)(g % cpi);
+    const uint8_t* s_; uint8_t* d_; uint32_t* f_;
+    item(k, s_, d_, f_);
+    const int st = (int)(g % NST);
+    const uint32_t b = bar0 + 8 * st, nb = chunk_bytes(c);
+    mbar_expect_tx(b, nb);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_base + st * CH), "l"(s_ + (size_t)c * CH), "r"(nb), "r"(b) : "memory");
+  };
+  for (long g = 0; g < total; ++g) {
+    // keep up to NST-1 loads ahead of the store cursor; never load from an item that is not ready
+    while (issued < total && issued < g + NST - 1 + (g == 0 ? 1 : 0)) {
+      const int k = (int)(issued / cpi);
+      if (k >= ready_upto) {
+        if (!is_ready(k)) {
+          if (issued > g) break;                              // there is still loaded work to store: come back later
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // nothing in flight to overlap with: drain, publish, block
+          publish_upto((int)(g / cpi));
+          ready(k);
+        }
+        asm volatile("fence.proxy.async.global;" ::: "memory");       // generic-proxy producer writes → async-proxy reads
+        ready_upto = k + 1;
+      }
+      if (issued >= NST) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(1) : "memory");   // stage reuse: its old store has drained
+      load(issued++);
+    }
+    const int k = (int)(g / cpi), c = (int)(g % cpi), st = (int)(g % NST);
+    const uint8_t* s_; uint8_t* d_; uint32_t* f_;
+    item(k, s_, d_, f_);
+    mbar_wait(bar0 + 8 * st, (phases >> st) & 1u);
+    phases ^= 1u << st;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(d_ + (size_t)c * CH), "r"(smem_base + st * CH), "r"(chunk_bytes(c)) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    // every group older than the newest NST has fully completed after this wait → items that ended there can be flagged
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(NST) : "memory");
+    const long done_upto = g - NST;                           // global chunk index whose store is certainly complete
+    if (done_upto >= 0) publish_upto((int)((done_upto + 1) / cpi));
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  publish_upto(n_items);
+}
+
 template <bool A_KMAJOR, bool B_KMAJOR, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -387,6 +457,20 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       //      the own chunk read the shard in place through `tma_a_local` and start immediately. -------------------
       const int items = (comm.world - 1) * blk128_per_rank;
       const size_t blk_bytes = (size_t)CTA_M * K * 2;
+      if (comm.push_tma == 2) {
+        if (threadIdx.x == 0) {
+          const int mine = ((int)blockIdx.x < items) ? (items - 1 - (int)blockIdx.x) / comm.comm_ctas + 1 : 0;
+          auto item = [&](int k, const uint8_t*& src, uint8_t*& d, uint32_t*& f) {
+            const int it = (int)blockIdx.x + k * comm.comm_ctas;
+            const int step = it / blk128_per_rank + 1, mb = it % blk128_per_rank;
+            const int dst = (comm.rank + step) % comm.world;
+            src = (const uint8_t*)comm.a_local + (size_t)mb * blk_bytes;
+            d = (uint8_t*)comm.peer_bufs[dst] + comm.buf_offset + ((size_t)comm.rank * blk128_per_rank + mb) * blk_bytes;
+            f = (uint32_t*)comm.peer_flags[dst] + comm.flag_offset + comm.rank * kMaxRowBlocks + mb;
+          };
+          tma_push_stream(mine, blk_bytes, comm.epoch, smem_base, bar_empty, push_phases, item, [](int) {}, [](int) { return true; });
+        }
+      } else
       for (int it = blockIdx.x; it < items; it += comm.comm_ctas) {
         const int step = it / blk128_per_rank + 1, mb = it % blk128_per_rank;
         const int dst = (comm.rank + step) % comm.world;
@@ -411,6 +495,34 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       // ---- reduce-scatter pusher: ship finished row blocks of remote chunks to their owners -------------------
       const int items = (comm.world - 1) * blk128_per_rank;
       const size_t blk_bytes = (size_t)CTA_M * N * 2;
+      if (comm.push_tma == 2) {
+        if (threadIdx.x == 0) {
+          const int mine = ((int)blockIdx.x < items) ? (items - 1 - (int)blockIdx.x) / comm.comm_ctas + 1 : 0;
+          auto gblk_of = [&](int k, int& owner, int& mb) {
+            const int it = (int)blockIdx.x + k * comm.comm_ctas;
+            const int step = it / blk128_per_rank;
+            mb = it % blk128_per_rank;
+            owner = (comm.rank + 1 + step) % comm.world;
+            return owner * blk128_per_rank + mb;
+          };
+          auto item = [&](int k, const uint8_t*& src, uint8_t*& d, uint32_t*& f) {
+            int owner, mb;
+            const int gblk = gblk_of(k, owner, mb);
+            src = (const uint8_t*)out + (size_t)gblk * blk_bytes;
+            d = (uint8_t*)comm.peer_bufs[owner] + comm.buf_offset + ((size_t)comm.rank * blk128_per_rank + mb) * blk_bytes;
+            f = (uint32_t*)comm.peer_flags[owner] + comm.flag_offset + comm.rank * kMaxRowBlocks + mb;
+          };
+          auto is_ready = [&](int k) {
+            int owner, mb;
+            const int gblk = gblk_of(k, owner, mb);
+            if (ld_acquire_gpu(comm.tile_done + gblk) < (uint32_t)tiles_n) return false;
+            comm.tile_done[gblk] = 0;                                  // single consumer: re-arm for the next call
+            return true;
+          };
+          auto ready = [&](int k) { while (!is_ready(k)) __nanosleep(128); };
+          tma_push_stream(mine, blk_bytes, comm.epoch, smem_base, bar_empty, push_phases, item, ready, is_ready);
+        }
+      } else
       for (int it = blockIdx.x; it < items; it += comm.comm_ctas) {
         const int step = it / blk128_per_rank, mb = it % blk128_per_rank;
         const int owner = (comm.rank + 1 + step) % comm.world;
@@ -696,7 +808,8 @@ void gemm_bf16_2cta_tp(int mode, const void* a, const void* b, void* out_or_part
   c.buf_offset = buf_offset; c.flag_offset = flag_offset; c.epoch = epoch; c.comm_ctas = comm_ctas;
   c.rows_per_rank = M / world; c.a_local = a_local; c.rs_out = rs_out; c.tile_done = tile_done; c.gemm_done = gemm_done;
   c.gemm_done_target = gemm_done_target;
-  { const char* e = getenv("NXD_TP_PUSH"); c.push_tma = (e && std::string(e) == "ldst") ? 0 : 1; }   // re-read per call (sweeps)
+  { const char* e = getenv("NXD_TP_PUSH");      // re-read per call (sweeps): ldst | tma (default) | stream (opt-in, see tma_push_stream)
+    c.push_tma = !e ? 1 : (std::string(e) == "ldst" ? 0 : (std::string(e) == "stream" ? 2 : 1)); }
   if (M % world || c.rows_per_rank % g2::TILE_M || c.rows_per_rank / g2::CTA_M > g2::kMaxRowBlocks)
     nxd_throw("fused TP GEMM (CTA-pair) needs rows/rank to be a multiple of 256 and <= 8192", __FILE__, __LINE__);
   const int grid = (device_sm_count() / 2) * 2;

@@ -78,7 +78,8 @@ def main():
         for M in (4096, 16384):
             if (M // world) % 256 or M // world // 128 > 64:
                 continue
-            for push, ag, rs in (("tma", 8, 8), ("tma", 12, 16), ("tma", 24, 24), ("tma", 32, 32), ("ldst", 12, 16), ("ldst", 32, 32)):
+            for push, ag, rs in (("tma", 12, 16), ("tma", 24, 24), ("tma", 32, 32), ("stream", 12, 16), ("stream", 24, 24),
+                                 ("stream", 32, 32), ("ldst", 12, 16)):
                 os.environ["NXD_TP_PUSH"] = push
                 _fused_impl.CONFIG["comm_ctas_ag"], _fused_impl.CONFIG["comm_ctas_rs"] = ag, rs
                 x = torch.randn(M // world, H, device="cuda", dtype=torch.bfloat16)
