@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--backend", default=os.environ.get("NXD_TP_BACKEND", "fused"), choices=["fused", "nccl"])
     ap.add_argument("--act-ckpt", default="none", choices=["none", "full"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-comm-report", action="store_true", help="skip the extra 'nocomm' pass that measures exposed TP communication")
     ap.add_argument("--micro-batch", type=int, default=0,
                     help="sequences per forward/backward (0 = auto: 2 up to 2 GPUs, 4 beyond — fewer fp32 wgrad read-modify-write "
                          "passes and TP collectives off their latency floor; 4 does not fit in 180 GB at TP=1); same value in both arms")
@@ -231,6 +232,32 @@ def main():
         e2e = {"value": tokens_per_step * args.steps / float(tt.item()), "unit": "tokens/s",
                "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps}
 
+    # ---- exposed tensor-parallel communication (BASELINE metric): same step with the TP collectives replaced by local copies of
+    #      the same shape ("nocomm" backend, numerically meaningless) → exposed = t(step) − t(nocomm step).  Runs last because it
+    #      trashes the weights; any failure only drops this key.
+    comm_report = None
+    if world > 1 and args.backend == "fused" and not args.no_comm_report:
+        try:
+            ops.tp_fused.set_backend("nocomm")
+            train_step(dev_ids[0])
+            sync()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for i in range(args.steps):
+                train_step(dev_ids[args.warmup + i])
+            c1.record()
+            sync()
+            tc = torch.tensor([c0.elapsed_time(c1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            nocomm_ms = float(tc.item()) / args.steps
+            comm_report = {"compute_only_ms_per_step": nocomm_ms,
+                           "exposed_tp_collective_ms_per_step": ms_total / args.steps - nocomm_ms,
+                           "method": "same step with Column/Row TP collectives replaced by local copies (tp backend 'nocomm')"}
+        except Exception as e:  # noqa: BLE001
+            comm_report = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
+        finally:
+            ops.tp_fused.set_backend(args.backend)
+
     if rank == 0:
         out = {
             "metric": "Llama-2-7B training tokens/sec (whole job, device-timed, max over ranks)",
@@ -245,7 +272,7 @@ def main():
                        "baseline_note": "vs_baseline divides by the only published number: Trn1 32-core gate 6.90 seq/s @ seq 8192",
                        "final_loss": final_loss, "loss_trace": [round(float(x), 4) for x in trace],
                        "grad_norm": float(opt.grad_norm) if opt.grad_norm is not None else None},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "comm": comm_report,
         }
         print(json.dumps(out), flush=True)
     dist.barrier()
