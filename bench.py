@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--backend", default=os.environ.get("NXD_TP_BACKEND", "fused"), choices=["fused", "nccl"])
     ap.add_argument("--act-ckpt", default="none", choices=["none", "full"])
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-comm-report", action="store_true", help="skip the extra 'nocomm' pass that measures exposed TP communication")
+    ap.add_argument("--comm-report", action="store_true",
+                    help="extra pass after the timed regions: same step with the TP collectives replaced by local copies → reports the "
+                         "exposed TP-collective time per step (opt-in until validated on hardware)")
     ap.add_argument("--micro-batch", type=int, default=0,
                     help="sequences per forward/backward (0 = auto: 2 up to 2 GPUs, 4 beyond — fewer fp32 wgrad read-modify-write "
                          "passes and TP collectives off their latency floor; 4 does not fit in 180 GB at TP=1); same value in both arms")
@@ -236,7 +238,7 @@ def main():
     #      the same shape ("nocomm" backend, numerically meaningless) → exposed = t(step) − t(nocomm step).  Runs last because it
     #      trashes the weights; any failure only drops this key.
     comm_report = None
-    if world > 1 and args.backend == "fused" and not args.no_comm_report:
+    if world > 1 and args.backend == "fused" and args.comm_report:
         try:
             ops.tp_fused.set_backend("nocomm")
             train_step(dev_ids[0])
