@@ -13,6 +13,13 @@ from torch import nn
 from ..utils import cpu_mode, get_device
 from ..utils.logger import get_logger
 
+
+def move_model_to_device(model: nn.Module, device: Optional[torch.device] = None) -> nn.Module:
+    """Reference ``utils/model_utils.py`` re-exports this helper; the implementation lives with the TP utilities."""
+    from ..parallel_layers.utils import move_model_to_device as _move
+
+    return _move(model, device)
+
 logger = get_logger()
 
 _PARALLEL_ATTRS = ("tensor_model_parallel", "partition_dim", "partition_stride", "num_partitions", "rank_ordering",
