@@ -58,4 +58,22 @@ def shard_state_dict_for_rank(model: nn.Module, full_sd: Dict[str, Any], rank: i
     for k, v in sd.items():
         p = params.get(k)
         out[k] = shard_tensor(v, p, rank, world) if (p is not None and isinstance(v, torch.Tensor)) else v
+    # parameters whose tensor lives under another key / format in the checkpoint (quantised layers reading torch
+    # ``_packed_params`` entries): fetch through the parameter's ``get_tensor_from_state_dict`` hook (reference
+    # quantization_layers.py:185-186, trace/trace.py shard_children)
+    consumed = set()
+    for k, p in params.items():
+        getter = getattr(p, "get_tensor_from_state_dict", None)
+        if getter is None:
+            continue
+        prefix = k[: k.rfind(".") + 1]
+        try:
+            t = getter(prefix=prefix, state_dict=sd)
+        except (RuntimeError, KeyError):
+            continue
+        if t is not None and (k not in sd or t is not sd[k]):
+            out[k] = shard_tensor(t, p, rank, world)
+            consumed.update(x for x in sd if x.startswith(prefix + "_packed_params") or x == prefix + "zero_point")
+    for x in consumed:
+        out.pop(x, None)
     return out

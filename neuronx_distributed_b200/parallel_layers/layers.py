@@ -39,6 +39,7 @@ from .utils import (
     EmbeddingUtility,
     create_local_weight,
     divide,
+    get_padding_length,
     set_tensor_model_parallel_attributes,
 )
 
@@ -49,10 +50,6 @@ _SP_ATTR = "sequence_parallel_enabled"
 
 def _tag_sequence_parallel(param: torch.Tensor, enabled: bool) -> None:
     setattr(param, _SP_ATTR, enabled)
-
-
-def get_padding_length(size: int, multiple: int) -> int:
-    return (-size) % multiple
 
 
 # --------------------------------------------------------------------------------------

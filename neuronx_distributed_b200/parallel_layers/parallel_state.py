@@ -137,6 +137,25 @@ class RankMesh:
 ParallelGroups = RankMesh  # name kept for API familiarity (reference :105)
 
 
+def ascending_ring_PG_group(lnc_size: int = 1, cluster_ranks_nonexp=None, cluster_ranks_exp=None, tp: int = 1, dp: int = 1,
+                            pp: int = 1, ep_model_degree: int = 1, ep_data_degree: int = 1, cp: int = 1) -> RankMesh:
+    """Rank-placement policy: consecutive ranks form a TP group (reference parallel_state.py:107-175).
+
+    Behind an NVSwitch every GPU is one hop from every other, so this is the ONLY placement policy here: it keeps a TP
+    group inside one NVLink domain (8 GPUs) and puts DP / PP across nodes.  The reference's second policy
+    (:177-325, interleaved rings for the Trn2 torus) has no B200 counterpart and maps to this one.
+    """
+    return RankMesh(tp * dp * pp * cp, tp, pp, cp, ep_model_degree)
+
+
+ascending_descending_ring_PG_group = ascending_ring_PG_group
+
+
+def get_logic_chosen(lnc_size: int = 1, hardware_type: Any = None, tp: int = 1):
+    """Reference parallel_state.py:341-357 picks a placement by hardware generation; B200 has one."""
+    return ascending_ring_PG_group
+
+
 def arrange_kv_groups(
     num_tensor_model_parallel_groups: int = 1,
     tensor_model_parallel_size: int = 1,

@@ -188,3 +188,88 @@ def get_local_world_size() -> int:
 
 def requires_init_pg_override() -> bool:
     return False
+
+
+def get_padding_length(numerator: int, denominator: int) -> int:
+    """Elements to append so that ``numerator`` becomes a multiple of ``denominator`` (reference utils.py:128-135)."""
+    return (-numerator) % denominator
+
+
+def is_pjrt_device() -> bool:
+    """There is no XLA runtime here (reference utils.py:171); kept so that ported scripts can branch on it."""
+    return False
+
+
+def _autocast_dtype() -> torch.dtype:
+    return torch.get_autocast_dtype("cuda" if torch.cuda.is_available() else "cpu")
+
+
+def _autocast_on() -> bool:
+    return torch.is_autocast_enabled("cuda") if torch.cuda.is_available() else torch.is_autocast_enabled("cpu")
+
+
+def _cast_nested(value, dtype):
+    if isinstance(value, torch.Tensor):
+        return value.to(dtype) if value.is_floating_point() and value.dtype is not torch.float64 else value
+    if isinstance(value, (str, bytes)) or type(value).__module__ == "numpy":
+        return value
+    if isinstance(value, dict):
+        return {k: _cast_nested(v, dtype) for k, v in value.items()}
+    if isinstance(value, (list, tuple)):
+        return type(value)(_cast_nested(v, dtype) for v in value)
+    return value
+
+
+def cast_if_autocast_enabled(*args):
+    """Cast floating tensors nested in ``args`` to the active autocast dtype (reference utils.py:202-207)."""
+    return args if not _autocast_on() else _cast_nested(args, _autocast_dtype())
+
+
+def verify_casted_dtype(value) -> None:
+    """Assert that every tensor nested in ``value`` already has the autocast dtype (reference utils.py:269-286)."""
+    if not _autocast_on():
+        return
+    if isinstance(value, torch.Tensor):
+        assert value.dtype == _autocast_dtype(), f"Datatype of tensor is expected to be {_autocast_dtype()}, got {value.dtype} instead"
+    elif isinstance(value, dict):
+        for v in value.values():
+            verify_casted_dtype(v)
+    elif isinstance(value, (list, tuple)):
+        for v in value:
+            verify_casted_dtype(v)
+
+
+def move_all_tensor_to_cpu(data, convert: bool = True):
+    """Synchronise and (optionally) copy every device tensor nested in ``data`` to host memory — one stream sync for the
+    whole structure instead of one per tensor (role of reference utils.py:230-243)."""
+    if torch.cuda.is_available():
+        torch.cuda.current_stream().synchronize()
+    if not convert:
+        return data
+
+    def walk(v):
+        if isinstance(v, torch.Tensor):
+            return v.to("cpu") if v.device.type != "cpu" else v
+        if isinstance(v, dict):
+            return type(v)((k, walk(x)) for k, x in v.items())
+        if isinstance(v, (list, tuple)):
+            return type(v)(walk(x) for x in v)
+        return v
+
+    return walk(data)
+
+
+def indices_split_along_dim(tensor: Optional[torch.Tensor], dim: int, rank: int, num_partitions: int) -> Optional[torch.Tensor]:
+    """Index vector selecting partition ``rank`` of ``num_partitions`` contiguous slices of ``tensor`` along ``dim``
+    (reference utils.py:288-316) — used with ``index_select`` where the rank is a device tensor (SPMDRank)."""
+    if tensor is None:
+        return None
+    per = divide(tensor.size(dim), num_partitions)
+    return torch.arange(per, device=tensor.device) + rank * per
+
+
+def initialize_fallback_parallel_state(device: Optional[torch.device] = None) -> None:
+    """Single-process world for layers constructed without ``initialize_model_parallel`` (reference utils.py:318-331)."""
+    from . import parallel_state
+
+    parallel_state.initialize_fallback_parallel_state()
