@@ -8,13 +8,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .model_utils import ACT2FN  # noqa: F401  (single activation table for the MoE package)
 from .moe_parallel_layers import ExpertFusedColumnParallelLinear, ExpertFusedRowParallelLinear
-
-ACT2FN = {
-    "silu": F.silu, "swish": F.silu, "gelu": F.gelu, "relu": F.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh,
-    "gelu_new": lambda x: F.gelu(x, approximate="tanh"), "gelu_pytorch_tanh": lambda x: F.gelu(x, approximate="tanh"),
-    "quick_gelu": lambda x: x * torch.sigmoid(1.702 * x),
-}
 
 
 class Experts(nn.Module):
@@ -23,7 +18,7 @@ class Experts(nn.Module):
                  dtype=torch.float32, device=None, input_layer_init_method=None, output_layer_init_method=None,
                  tensor_model_parallel_group=None, hidden_act_scaling_factor: float = 1.0, hidden_act_bias: float = 0.0,
                  gate_clamp_upper_limit=None, gate_clamp_lower_limit=None, up_clamp_upper_limit=None,
-                 up_clamp_lower_limit=None):
+                 up_clamp_lower_limit=None, bias: bool = False, expert_model_parallel_group=None, is_prefill: bool = True):
         super().__init__()
         self.glu_mlp, self.glu_type = glu_mlp, glu_type
         self.act = ACT2FN[hidden_act]
@@ -33,14 +28,19 @@ class Experts(nn.Module):
         if glu_mlp:
             self.gate_up_proj = ExpertFusedColumnParallelLinear(
                 num_experts, hidden_size, 2 * intermediate_size, dtype=dtype, device=device, stride=2,
-                init_method=input_layer_init_method, tensor_model_parallel_group=tensor_model_parallel_group)
+                init_method=input_layer_init_method, tensor_model_parallel_group=tensor_model_parallel_group, bias=bias,
+                expert_model_parallel_group=expert_model_parallel_group, is_prefill=is_prefill, is_fused_gate_up=True)
         else:
             self.up_proj = ExpertFusedColumnParallelLinear(
                 num_experts, hidden_size, intermediate_size, dtype=dtype, device=device,
-                init_method=input_layer_init_method, tensor_model_parallel_group=tensor_model_parallel_group)
+                init_method=input_layer_init_method, tensor_model_parallel_group=tensor_model_parallel_group, bias=bias,
+                expert_model_parallel_group=expert_model_parallel_group, is_prefill=is_prefill)
         self.down_proj = ExpertFusedRowParallelLinear(
             num_experts, intermediate_size, hidden_size, reduce_output=reduce_output, dtype=dtype, device=device,
-            init_method=output_layer_init_method, tensor_model_parallel_group=tensor_model_parallel_group)
+            init_method=output_layer_init_method, tensor_model_parallel_group=tensor_model_parallel_group, bias=bias,
+            expert_model_parallel_group=expert_model_parallel_group, is_prefill=is_prefill)
+
+        self.local_expert_ids = self.down_proj.local_expert_ids
 
     def activation(self, h: torch.Tensor) -> torch.Tensor:
         if not self.glu_mlp:

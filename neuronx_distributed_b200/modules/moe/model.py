@@ -34,6 +34,12 @@ class MoE(nn.Module):
 
             self.moe_fused_tkg = MoEFusedTKG(router, expert_mlps, shared_experts, rmsnorm, tkg_config)
 
+    def _shared(self, full: torch.Tensor, seq_len: int) -> torch.Tensor:
+        try:
+            return self.shared_experts(full, seq_len)
+        except TypeError:                                   # user-supplied module with the one-argument signature
+            return self.shared_experts(full)
+
     def _reduce(self, y: torch.Tensor) -> torch.Tensor:
         ep = ps.get_expert_model_parallel_size()
         tp_group = self.tensor_parallel_group if self.tensor_parallel_group is not None else ps.get_tensor_model_parallel_group()
@@ -58,10 +64,20 @@ class MoE(nn.Module):
             full = mappings.gather_from_sequence_parallel_region(x, self.sequence_dimension, to_model_parallel=True,
                                                                  process_group=self.tensor_parallel_group)
         shape = full.shape
-        y = self.expert_mlps(full.reshape(-1, shape[-1]), aff, idx, seq_len=shape[self.sequence_dimension]).view(shape)
+        seq_len = shape[self.sequence_dimension]
+        y = self.expert_mlps(full.reshape(-1, shape[-1]), aff, idx, seq_len=seq_len, padding_mask=padding_mask).view(shape)
+        shared_complete = None
         if self.shared_experts is not None:
-            y = y + self.shared_experts(full)
+            if (getattr(self.shared_experts, "sequence_parallel_enabled", False) and self.sequence_parallel_enabled
+                    and seq_len > 1):
+                # SP shared experts hold replicated weights: run on the LOCAL sequence shard, complete result, no collective;
+                # added after the routed experts' reduce-scatter (reference shared_experts.py SP flow)
+                shared_complete = self._shared(x, seq_len)
+            else:
+                y = y + self._shared(full, seq_len)
         y = self._reduce(y)
+        if shared_complete is not None:
+            y = y + shared_complete
         if perm is not None:
             y = token_shuffling.token_unshuffle(y, perm, self.sequence_dimension)
         out: Tuple = (y,)

@@ -7,6 +7,15 @@ from typing import Optional
 import torch
 
 
+def to_torch_dtype(dtype_str) -> torch.dtype:
+    """``"bfloat16"`` → ``torch.bfloat16`` (reference moe_configs.py:13-20); torch dtypes pass through."""
+    if isinstance(dtype_str, torch.dtype):
+        return dtype_str
+    table = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}
+    assert dtype_str in table, f"Unsupported dtype: {dtype_str}"
+    return table[dtype_str]
+
+
 @dataclass
 class RouterConfig:
     act_fn: str = "softmax"                 # "softmax" | "sigmoid"

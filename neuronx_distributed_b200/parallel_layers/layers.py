@@ -98,19 +98,12 @@ def _initialize_parameter_sharded(
         init_method(param)
 
 
-class BaseParallelLayer(nn.Module):
-    """Brings up a single-rank parallel state if the user never initialised one
-    (reference layers.py:167-183)."""
-
-    def __init__(self, device: Optional[torch.device] = None):
-        super().__init__()
-        if not ps.model_parallel_is_initialized():
-            warnings.warn("parallel state is not initialized; falling back to a single-rank world")
-            ps.initialize_fallback_parallel_state()
+class ProcessGroupSafeDeepcopy:
+    """Mixin: ``copy.deepcopy`` of a module that stores process groups.  Groups are shared by reference (they cannot be
+    pickled / copied) and the parallel attributes on parameters survive the copy (``Parameter.__deepcopy__`` drops custom
+    attributes; bound-method attributes such as state-dict hooks are re-bound to nothing and simply carried over)."""
 
     def __deepcopy__(self, memo):
-        """Process groups are shared by reference (they cannot be pickled/copied) and the parallel attributes on
-        parameters survive the copy (``Parameter.__deepcopy__`` drops custom attributes)."""
         import copy
 
         new = self.__class__.__new__(self.__class__)
@@ -125,6 +118,35 @@ class BaseParallelLayer(nn.Module):
                 if not hasattr(p_new, ak):
                     setattr(p_new, ak, av)
         return new
+
+
+class BaseParallelLayer(ProcessGroupSafeDeepcopy, nn.Module):
+    """Brings up a single-rank parallel state if the user never initialised one
+    (reference layers.py:167-183)."""
+
+    def __init__(self, device: Optional[torch.device] = None):
+        super().__init__()
+        if not ps.model_parallel_is_initialized():
+            warnings.warn("parallel state is not initialized; falling back to a single-rank world")
+            ps.initialize_fallback_parallel_state()
+
+
+class BaseParallelLinear(BaseParallelLayer):
+    """Common base of the TP linears (reference layers.py:535-558): default initialisers and the inference-only guard for
+    padded layers."""
+
+    arg_init_method: Optional[Callable[..., Any]] = None
+    pad: bool = False
+
+    def _init_weight(self, w: torch.Tensor) -> None:
+        if self.arg_init_method is None:
+            init.kaiming_uniform_(w, a=math.sqrt(5))
+        else:
+            self.arg_init_method(w)
+
+    def _check_pad_false_for_training(self) -> None:
+        if self.pad and self.training:
+            raise RuntimeError("`pad=True` is only supported for inference. Set model.eval()")
 
 
 def _group_info(group) -> Tuple[Any, int, int]:
@@ -497,7 +519,7 @@ def linear_with_async_allreduce(
 # --------------------------------------------------------------------------------------
 # Column / Row parallel linear
 # --------------------------------------------------------------------------------------
-class ColumnParallelLinear(BaseParallelLayer):
+class ColumnParallelLinear(BaseParallelLinear):
     """``Y = X A^T + b`` with ``A`` split along its output dim: ``A = [A_1; …; A_p]``.
 
     Arguments mirror reference layers.py:587-607.  ``stride`` >1 interleaves fused matrices
@@ -590,8 +612,7 @@ class ColumnParallelLinear(BaseParallelLayer):
                         rank=self._tp_rank, world_size=tp))
 
     def forward(self, input: torch.Tensor, slice_indices: Optional[torch.Tensor] = None, *_: Any):  # noqa: A002
-        if self.pad and self.training:
-            raise RuntimeError("`pad=True` is only supported for inference. Set model.eval()")
+        self._check_pad_false_for_training()
         tp = self.tensor_model_parallel_size
         weight = self.weight if slice_indices is None else self.weight.index_select(0, slice_indices)
         if self.sequence_parallel_enabled:
@@ -627,7 +648,7 @@ class ColumnParallelLinear(BaseParallelLayer):
             model_state_dict[bkey] = F.pad(model_state_dict[bkey], (0, self.pad_size))
 
 
-class RowParallelLinear(BaseParallelLayer):
+class RowParallelLinear(BaseParallelLinear):
     """``Y = X A^T + b`` with ``A`` split along its input dim; partial products are summed
     across TP — all-reduce, or reduce-scatter along the sequence dim under SP (reference
     layers.py:815-1063)."""
@@ -706,9 +727,10 @@ class RowParallelLinear(BaseParallelLayer):
             with torch.no_grad():
                 init.uniform_(self.bias, -bound, bound)
 
-    def forward(self, input_: torch.Tensor):
-        if self.pad and self.training:
-            raise RuntimeError("`pad=True` is only supported for inference. Set model.eval()")
+    def forward(self, input_: torch.Tensor, slice_indices: Optional[torch.Tensor] = None, *_: Any):
+        """``slice_indices`` selects input-feature columns of the local weight (decode-time slicing of replicated weights,
+        reference layers.py:971-1000)."""
+        self._check_pad_false_for_training()
         tp = self.tensor_model_parallel_size
         if self.input_is_parallel:
             x = input_
@@ -720,8 +742,9 @@ class RowParallelLinear(BaseParallelLayer):
             out_mode = "none"
         else:
             out_mode = "scatter" if self.sequence_parallel_enabled else "reduce"
+        weight = self.weight if slice_indices is None else self.weight.index_select(1, slice_indices)
         out = tp_linear(
-            x, self.weight, None, "none", out_mode, self.sequence_dimension, self.tensor_parallel_group,
+            x, weight, None, "none", out_mode, self.sequence_dimension, self.tensor_parallel_group,
             self.reduce_dtype,
         )
         if self.skip_bias_add:
@@ -774,6 +797,24 @@ class _ConvWithAsyncAllReduce(torch.autograd.Function):
         if work is not None:
             work.wait()
         return gx, gw, gb, None, None, None, None, None, None
+
+
+Conv2dWithInputGradAllReduce = _ConvWithAsyncAllReduce        # reference name (layers.py:1066)
+
+
+def conv2d_with_weight_grad_allreduce(input: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],  # noqa: A002
+                                      stride: Tuple[int, int], padding: Tuple[int, int], allreduce_weight_grad: bool,
+                                      dilation: Tuple[int, int] = (1, 1), groups: int = 1, group=None) -> torch.Tensor:
+    """Functional form (reference layers.py:1132-1150).  The flag's name is historical: the collective it enables is the
+    all-reduce of the *input* gradient over the TP group (output-channel-parallel convolutions), issued before the
+    weight-gradient kernel so the two overlap."""
+    from .utils import cast_if_autocast_enabled
+
+    input, weight, bias = cast_if_autocast_enabled(input, weight, bias)  # noqa: A001
+    group = group if group is not None else ps.get_tensor_model_parallel_group()
+    with torch.autocast(device_type="cuda" if input.is_cuda else "cpu", enabled=False):
+        return _ConvWithAsyncAllReduce.apply(input, weight, bias, _pair(stride), _pair(padding), _pair(dilation), groups,
+                                             allreduce_weight_grad, group)
 
 
 class BaseParallelConv(BaseParallelLayer):

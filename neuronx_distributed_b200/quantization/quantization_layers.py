@@ -32,7 +32,7 @@ from torch.nn.parameter import Parameter
 from ..modules.moe.moe_parallel_layers import ExpertFusedLinear, ExpertFusedLinearWithAsyncCommunication
 from ..parallel_layers import mappings
 from ..parallel_layers import parallel_state as ps
-from ..parallel_layers.layers import LinearWithAsyncCommunication, _group_info
+from ..parallel_layers.layers import LinearWithAsyncCommunication, ProcessGroupSafeDeepcopy, _group_info
 from ..parallel_layers.utils import divide, get_padding_length, set_tensor_model_parallel_attributes
 from .dequantize import blockwise_scale_dequantize, direct_cast_dequantize, scale_dequantize
 from .microscaling.mx_torch import quantize_mx
@@ -114,7 +114,7 @@ class QuantizedParallelLinearLayerStateDictAdaptor:
         raise RuntimeError(f"Cannot find {prefix + 'input_scale'} in state_dict")
 
 
-class BaseQuantizeParallelLinear(nn.Module, metaclass=ABCMeta):
+class BaseQuantizeParallelLinear(ProcessGroupSafeDeepcopy, nn.Module, metaclass=ABCMeta):
     """Parameter set-up shared by all quantised parallel layers (reference :73-354)."""
 
     autograd_func_class = LinearWithAsyncCommunication
@@ -612,6 +612,9 @@ class _QuantizedExpertMixin(ExpertFusedLinear):
             self.ep = ps.get_expert_model_parallel_size()
         self.expert_model_parallel_group = expert_model_parallel_group
         self._n_local_experts = self.num_local_experts = divide(num_experts, self.ep)
+        r = dist.get_rank(expert_model_parallel_group) if expert_model_parallel_group is not None else \
+            ps.get_expert_model_parallel_rank()
+        self.local_expert_ids = ps.get_experts_for_expert_parallel_rank(r, num_experts, self.ep)
         self.is_prefill, self.is_fused_gate_up = is_prefill, is_fused_gate_up
 
     def _expert_bias(self, y: torch.Tensor, expert_indices: Optional[torch.Tensor], scale: float = 1.0) -> torch.Tensor:
@@ -647,7 +650,7 @@ class QuantizedExpertFusedColumnParallel(QuantizedColumnParallel, _QuantizedExpe
                          tensor_model_parallel_group=tensor_model_parallel_group, block_axis=block_axis,
                          block_size=block_size, scale_dtype=scale_dtype, rank_ordering=rank_ordering)
         for k in ("num_experts", "ep", "expert_model_parallel_group", "_n_local_experts", "num_local_experts",
-                  "is_prefill", "is_fused_gate_up"):
+                  "is_prefill", "is_fused_gate_up", "local_expert_ids"):
             self.__dict__[k] = saved[k]
         self._mark_expert_parallel_weights(expert_parallel_group_size=self.ep, is_prefill=is_prefill)
 
@@ -704,7 +707,7 @@ class QuantizedExpertFusedRowParallel(QuantizedRowParallel, _QuantizedExpertMixi
                          tensor_model_parallel_group=tensor_model_parallel_group, block_axis=block_axis,
                          block_size=block_size, scale_dtype=scale_dtype, rank_ordering=rank_ordering)
         for k in ("num_experts", "ep", "expert_model_parallel_group", "_n_local_experts", "num_local_experts",
-                  "is_prefill", "is_fused_gate_up"):
+                  "is_prefill", "is_fused_gate_up", "local_expert_ids"):
             self.__dict__[k] = saved[k]
         self._mark_expert_parallel_weights(expert_parallel_group_size=self.ep, is_prefill=is_prefill)
 

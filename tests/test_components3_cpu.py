@@ -20,7 +20,7 @@ def _quant_moe(rank, world):
     E, k, H, I, T = 4, 2, 32, 64, 6
     cfg = RoutedExpertsMLPOpsConfig(num_experts=E, top_k=k, hidden_size=H, intermediate_size=I)
     router, experts = RouterTopK(E, k, H), ExpertMLPsV2(cfg)
-    shared = SharedExperts(H, 16)
+    shared = SharedExperts(H, 16, fused_gate_up_projection=True)
     norm = RMSNorm(H)
     layer = MoE(router, experts, shared_experts=shared).eval()
     x = torch.randn(T, 1, H, generator=torch.Generator().manual_seed(1))

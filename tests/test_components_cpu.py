@@ -142,7 +142,7 @@ def _moe_parts(rank, world):
     assert all(int(e) // 2 in allowed[t].tolist() for t in range(T) for e in idx2[t])
     # shared experts: partial output summed over TP == dense SwiGLU MLP with the gathered weights
     torch.manual_seed(4)
-    se = SharedExperts(H, 12, num_shared_experts=2)
+    se = SharedExperts(H, 12, num_shared_experts=2, fused_gate_up_projection=True)
     y = mappings.reduce_from_tensor_model_parallel_region(se(x))
     import torch.distributed as dist
     gu = _all_gather_cat(se.gate_up_proj.weight.detach(), world); dn = _all_gather_cat(se.down_proj.weight.detach(), world)
@@ -151,6 +151,43 @@ def _moe_parts(rank, world):
         gte, up = (x @ w_gu.t()).chunk(2, -1)
         ref = ref + (nn.functional.silu(gte) * up) @ w_dn.t()
     torch.testing.assert_close(y, ref, rtol=1e-4, atol=1e-4)
+    # separate gate / up projections (the reference's default key names), plain and stored-transposed: load ONE full
+    # [out, in] checkpoint into both through the sharder (preshard hook transposes) → identical outputs
+    from neuronx_distributed_b200.inference.sharding import shard_state_dict_for_rank
+    from neuronx_distributed_b200.modules.moe.shared_experts import ColumnParallelLinearTransposed, RowParallelLinearTransposed
+
+    g = torch.Generator().manual_seed(11)
+    full = {"gate_proj.weight": torch.randn(24, H, generator=g) * 0.3, "up_proj.weight": torch.randn(24, H, generator=g) * 0.3,
+            "down_proj.weight": torch.randn(H, 24, generator=g) * 0.3}
+    dense = (nn.functional.silu(x @ full["gate_proj.weight"].t()) * (x @ full["up_proj.weight"].t())) @ full["down_proj.weight"].t()
+    outs = []
+    for transposed in (False, True):
+        se2 = SharedExperts(H, 12, num_shared_experts=2, transpose_weights=transposed).eval()
+        assert set(dict(se2.named_parameters())) == {"gate_proj.weight", "up_proj.weight", "down_proj.weight"}
+        if transposed:
+            assert isinstance(se2.gate_proj, ColumnParallelLinearTransposed) and isinstance(se2.down_proj, RowParallelLinearTransposed)
+            assert se2.gate_proj.weight.shape == (H, 24 // world) and se2.gate_proj.weight.partition_dim == 1
+            assert se2.down_proj.weight.shape == (24 // world, H) and se2.down_proj.weight.partition_dim == 0
+        se2.load_state_dict(shard_state_dict_for_rank(se2, full, rank, world))
+        outs.append(mappings.reduce_from_tensor_model_parallel_region(se2(x, seq_len=T)))
+        torch.testing.assert_close(outs[-1], dense, rtol=1e-4, atol=1e-4)
+    # backward through the transposed layers
+    se2.train()
+    xg = x.clone().requires_grad_(True)
+    mappings.reduce_from_tensor_model_parallel_region(se2(xg)).sum().backward()
+    assert xg.grad is not None and se2.gate_proj.weight.grad.shape == se2.gate_proj.weight.shape
+    # sequence-parallel mode: replicated weights; prefill needs no collective, decode slices the replicated weight by rank
+    torch.manual_seed(5)
+    for fused in (False, True):
+        se3 = SharedExperts(H, 12, num_shared_experts=2, sequence_parallel_enabled=True, fused_gate_up_projection=fused).eval()
+        names = ("gate_up_proj", "down_proj") if fused else ("gate_proj", "up_proj", "down_proj")
+        for n in names:                                                       # replicated: make every rank hold rank 0's copy
+            dist.broadcast(getattr(se3, n).weight.data, 0)
+        assert se3.down_proj.weight.shape == (H, 24)                          # full, not sharded
+        full_out = se3(x, seq_len=T)                                          # prefill: complete result locally
+        tok = x[:1]
+        part = se3(tok, seq_len=1)                                            # decode: this rank's partial sum
+        torch.testing.assert_close(mappings.reduce_from_tensor_model_parallel_region(part), full_out[:1], rtol=1e-4, atol=1e-4)
 
 
 def test_routers_and_shared_experts_tp2():
