@@ -7,7 +7,7 @@ TP kernels (their collectives included), exactly as the reference's recompute re
 collectives."""
 from __future__ import annotations
 
-from typing import Callable
+from typing import Callable, Optional
 
 import torch
 from torch import nn
@@ -17,9 +17,10 @@ _PREFIX = "_checkpoint_wrapped_module."
 
 
 class NxDCheckpointWrapper(nn.Module):
-    def __init__(self, module: nn.Module):
+    def __init__(self, module: nn.Module, checkpoint_impl=None, checkpoint_fn: Optional[Callable] = None, **checkpoint_fn_kwargs):
         super().__init__()
         self._checkpoint_wrapped_module = module
+        self._checkpoint_fn, self._checkpoint_fn_kwargs = checkpoint_fn, checkpoint_fn_kwargs
         self._register_state_dict_hook(self._strip_prefix)
         self.register_load_state_dict_pre_hook(self._add_prefix)
 
@@ -39,6 +40,8 @@ class NxDCheckpointWrapper(nn.Module):
     def forward(self, *args, **kwargs):
         if not torch.is_grad_enabled():
             return self._checkpoint_wrapped_module(*args, **kwargs)
+        if self._checkpoint_fn is not None:
+            return self._checkpoint_fn(self._checkpoint_wrapped_module, *args, **self._checkpoint_fn_kwargs, **kwargs)
         return checkpoint(self._checkpoint_wrapped_module, *args, use_reentrant=False, **kwargs)
 
     def named_parameters(self, *args, **kwargs):
@@ -52,15 +55,25 @@ class NxDCheckpointWrapper(nn.Module):
             return getattr(self._checkpoint_wrapped_module, name)
 
 
-def apply_activation_checkpointing(model: nn.Module, check_fn: Callable[[nn.Module], bool] = lambda _: True) -> None:
+def checkpoint_wrapper(module: nn.Module, checkpoint_impl=None, checkpoint_fn: Optional[Callable] = None,
+                       **checkpoint_fn_kwargs) -> nn.Module:
+    """Wrap ONE module (reference :31-52).  ``checkpoint_fn(module, *args, **kwargs)`` replaces the default
+    non-reentrant ``torch.utils.checkpoint.checkpoint``; ``checkpoint_impl`` is accepted for signature compatibility
+    (there is no XLA reentrancy restriction here)."""
+    return NxDCheckpointWrapper(module, checkpoint_impl, checkpoint_fn, **checkpoint_fn_kwargs)
+
+
+def apply_activation_checkpointing(model: nn.Module, checkpoint_wrapper_fn: Optional[Callable] = None,
+                                   check_fn: Callable[[nn.Module], bool] = lambda _: True) -> None:
     """Wrap (in place) every sub-module for which ``check_fn`` is true."""
+    wrap = checkpoint_wrapper_fn or checkpoint_wrapper
 
     def _recurse(parent: nn.Module):
         for name, child in list(parent.named_children()):
             if isinstance(child, NxDCheckpointWrapper):
                 continue
             if check_fn(child):
-                setattr(parent, name, NxDCheckpointWrapper(child))
+                setattr(parent, name, wrap(child))
             else:
                 _recurse(child)
 

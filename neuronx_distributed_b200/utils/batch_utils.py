@@ -29,3 +29,13 @@ def get_batch_on_this_context_parallel_rank(batch: Dict[str, Any], seq_dim: int 
         if isinstance(v, torch.Tensor) and v.dim() > seq_dim and v.shape[seq_dim] % cp == 0:
             out[k] = v.chunk(cp, dim=seq_dim)[r].contiguous()
     return out
+
+
+def shift_labels(batch: Dict[str, Any], label_pad_token_id: int = -100) -> Dict[str, Any]:
+    """``labels[:, t] ← labels[:, t+1]`` with ``-100`` in the last column (reference :4-16): done BEFORE a sequence is split
+    over context-parallel ranks, so the model must not shift again."""
+    out = dict(batch)
+    if "labels" in out:
+        lab = out["labels"]
+        out["labels"] = torch.cat([lab[:, 1:], lab.new_full((lab.shape[0], 1), label_pad_token_id)], dim=1)
+    return out

@@ -9,6 +9,7 @@ from __future__ import annotations
 import logging
 import os
 import sys
+from typing import Any
 
 _LEVELS = {
     "off": logging.CRITICAL + 10,
@@ -20,6 +21,22 @@ _LEVELS = {
     "trace": 5,
 }
 logging.addLevelName(5, "TRACE")
+
+
+class PackagePathFilter(logging.Filter):
+    """Adds ``record.relativepath`` = the source path relative to the longest ``sys.path`` entry containing it, so log lines
+    show ``neuronx_distributed_b200/pipeline/model.py:123`` instead of an absolute path (reference logger.py:38-49)."""
+
+    def filter(self, record: Any) -> bool:
+        import sys
+
+        record.relativepath = record.pathname
+        for root in sorted((os.path.abspath(p) for p in sys.path if p), key=len, reverse=True):
+            root = root if root.endswith(os.sep) else root + os.sep
+            if record.pathname.startswith(root):
+                record.relativepath = os.path.relpath(record.pathname, root)
+                break
+        return True
 
 
 class _RankZeroFilter(logging.Filter):

@@ -14,13 +14,14 @@ from ..utils import cpu_mode, get_device
 from ..utils.logger import get_logger
 
 
+logger = get_logger()
+
+
 def move_model_to_device(model: nn.Module, device: Optional[torch.device] = None) -> nn.Module:
     """Reference ``utils/model_utils.py`` re-exports this helper; the implementation lives with the TP utilities."""
     from ..parallel_layers.utils import move_model_to_device as _move
 
     return _move(model, device)
-
-logger = get_logger()
 
 _PARALLEL_ATTRS = ("tensor_model_parallel", "partition_dim", "partition_stride", "num_partitions", "rank_ordering",
                    "sequence_parallel_enabled", "shared", "expert_model_parallel", "fused_qkv", "qkv_sections")
@@ -75,8 +76,26 @@ def init_on_device(device: torch.device, include_buffers: bool = False):
         nn.Module.register_buffer = old_register_buffer
 
 
-def preserve_parallel_attributes(model: nn.Module) -> Dict[str, Dict]:
-    return {n: {k: v for k, v in p.__dict__.items() if k in _PARALLEL_ATTRS} for n, p in model.named_parameters()}
+class _SavedParallelAttributes(dict):
+    """``{param_name: {attr: value}}`` that can also be used as ``with preserve_parallel_attributes(model): …`` — the
+    attributes are written back on exit (operations such as ``to_empty`` / re-materialisation create new Parameter
+    objects and drop custom attributes; reference :164-202 is a context manager)."""
+
+    def __init__(self, model: nn.Module, data: Dict[str, Dict]):
+        super().__init__(data)
+        self._model = model
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        restore_parallel_attributes(self._model, self)
+        return False
+
+
+def preserve_parallel_attributes(model: nn.Module) -> _SavedParallelAttributes:
+    return _SavedParallelAttributes(
+        model, {n: {k: v for k, v in p.__dict__.items() if k in _PARALLEL_ATTRS} for n, p in model.named_parameters()})
 
 
 def restore_parallel_attributes(model: nn.Module, saved: Dict[str, Dict]) -> None:
@@ -155,3 +174,106 @@ def get_delay_tracing(nxd_config) -> bool:
 
 def check_delay_tracing(nxd_config) -> bool:
     return False
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# shared (tied) weights, availability probes, structure filters (reference utils/model_utils.py:48-161, 244-253, 370-386)
+# ---------------------------------------------------------------------------------------------------------------------
+def analyze_shared_parameters(module: nn.Module, shared_parameters=None, prefix: str = ""):
+    """Groups of parameter names that refer to the same Parameter object (``[["embed.weight", "lm_head.weight"], …]``)."""
+    groups: Dict[int, list] = {}
+    for name, p in module.named_parameters(prefix=prefix, remove_duplicate=False):
+        groups.setdefault(id(p), []).append(name)
+    return [names for names in groups.values() if len(names) > 1]
+
+
+def _resolve(module: nn.Module, path: str):
+    parent_path, _, leaf = path.rpartition(".")
+    parent = module.get_submodule(parent_path) if parent_path else module
+    return parent, leaf
+
+
+def retie_shared_weights(module: nn.Module, shared_weight_names) -> None:
+    """Make every name of a group point at the first name's Parameter again (after ``to_empty`` / load / device moves)."""
+    for names in shared_weight_names:
+        parent, leaf = _resolve(module, names[0])
+        ref = getattr(parent, leaf)
+        for other in names[1:]:
+            p2, l2 = _resolve(module, other)
+            setattr(p2, l2, ref)
+
+
+@contextlib.contextmanager
+def preserve_shared_weights(model: nn.Module, ignore_hf: bool = False):
+    """Record the tied-parameter groups on entry and re-tie them on exit (HF models re-tie through ``tie_weights``)."""
+    use_hf = is_hf_pretrained_model(model) and not ignore_hf
+    names = None if use_hf else analyze_shared_parameters(model)
+    try:
+        yield
+    finally:
+        if use_hf:
+            model.tie_weights()
+        else:
+            retie_shared_weights(model, names)
+
+
+def is_hf_transformers_available() -> bool:
+    import importlib.util
+
+    return importlib.util.find_spec("transformers") is not None
+
+
+def is_hf_accelerate_available() -> bool:
+    import importlib.util
+
+    return importlib.util.find_spec("accelerate") is not None
+
+
+def is_nxdt_available() -> bool:
+    import importlib.util
+
+    return importlib.util.find_spec("neuronx_distributed_training") is not None
+
+
+def is_nxdt_pretrained_model(model: nn.Module) -> bool:
+    if not is_nxdt_available():
+        return False
+    from neuronx_distributed_training.models.megatron.module import MegatronModule  # type: ignore
+
+    return isinstance(model, MegatronModule)
+
+
+def recursive_filter(item, predicate):
+    """Copy of a nested dict / list / tuple / set keeping only the tensors for which ``predicate(tensor)`` holds
+    (non-tensor leaves are always kept) — e.g. ``recursive_filter(state, lambda t: not t.is_meta)``."""
+    def keep(obj) -> bool:
+        return predicate(obj) if isinstance(obj, torch.Tensor) else True
+
+    if isinstance(item, dict):
+        return {k: recursive_filter(v, predicate) for k, v in item.items() if keep(v)}
+    if isinstance(item, (list, tuple, set)):
+        return type(item)(recursive_filter(v, predicate) for v in item if keep(v))
+    return item if keep(item) else None
+
+
+def has_fake_tensors(model: nn.Module, ignored_params=None) -> bool:
+    """True if any (non-ignored) parameter has no storage yet (meta device / FakeTensor) and must be materialised."""
+    from torch._subclasses.fake_tensor import FakeTensor
+
+    ignored = {id(p) for p in (ignored_params or ())}
+    return any((p.device.type == "meta" or isinstance(p, FakeTensor)) and id(p) not in ignored for p in model.parameters())
+
+
+import enum as _enum  # noqa: E402
+
+
+class LogicalNCConfig(_enum.IntEnum):
+    """Logical cores per device.  A B200 is ONE logical device (its two dies share L2/HBM coherently and are scheduled
+    as one 148-SM grid), so only ``LNC_1`` is ever returned; ``LNC_2`` exists for configs ported from Trn2."""
+
+    LNC_1 = 1
+    LNC_2 = 2
+
+
+def get_platform_lnc() -> LogicalNCConfig:
+    return LogicalNCConfig.LNC_1

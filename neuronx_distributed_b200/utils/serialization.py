@@ -60,3 +60,22 @@ def find_loss_from_output_and_spec(output: Any, spec: Any) -> torch.Tensor:
             if v is not False and v is not None:
                 return find_loss_from_output_and_spec(output[i], v)
     raise ValueError(f"no loss selected by spec {spec!r}")
+
+
+def compress_to_string(obj: Any) -> str:
+    """Pickle → base64 text (pipeline metadata travels between stages as strings; reference :14-20)."""
+    import base64
+    import pickle
+
+    return base64.b64encode(pickle.dumps(obj)).decode("utf-8")
+
+
+def uncompress_from_string(serialized_data_string: str) -> Any:
+    import base64
+    import pickle
+
+    return pickle.loads(base64.b64decode(serialized_data_string.encode("utf-8")))
+
+
+def is_instance_namedtuple(iterable: Any) -> bool:
+    return isinstance(iterable, tuple) and hasattr(iterable, "_fields") and type(iterable).__base__ is tuple

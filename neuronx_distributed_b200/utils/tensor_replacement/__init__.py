@@ -8,6 +8,9 @@ from typing import Dict, List, Optional
 import torch
 from torch import nn
 
+from .model_modification import modify_model_for_tensor_replacement, patch_forward_with_additional_args  # noqa: F401
+from .registry import RuntimeRegister  # noqa: F401
+
 
 class TensorReplacementRegistry:
     _inst: Optional["TensorReplacementRegistry"] = None

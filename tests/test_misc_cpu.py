@@ -1,4 +1,7 @@
 """Operators, sampling, capture/replacement, CP batch split, activation checkpoint wrapper, meta-device init, EP MoE."""
+import pytest
+import os
+
 import torch
 from torch import nn
 
@@ -49,6 +52,78 @@ def test_capture_and_replacement():
     torch.testing.assert_close(y2, m[2](torch.relu(inj)))
     tr.disable_tensor_replacement()
     torch.testing.assert_close(m(x), y)
+
+    # reference-style API: inputs, nested outputs, manual tensors with a budget, ordering, hooks removed on disable
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = nn.Linear(4, 4)
+
+        def forward(self, h, scale=None):
+            out = self.lin(h) * (1 if scale is None else scale)
+            tc.register_tensor("pre_act", out)
+            tc.register_tensor("pre_act", out + 1)                     # same name twice → suffixed key
+            tc.register_tensor("over_budget", out)
+            return {"hidden": torch.relu(out), "aux": (out, out * 2)}
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = Block(), nn.Linear(4, 2)
+
+        def forward(self, h):
+            return self.b(self.a(h, scale=torch.tensor(2.0))["hidden"])
+
+    net = Net()
+    assert tc.get_available_modules(net) == ["a", "a.lin", "b"]
+    with pytest.raises(ValueError):
+        tc.enable_tensor_capture(net, ["nope"])
+    net = tc.enable_tensor_capture(net, ["b", "a"], max_tensors=2, capture_inputs=True)
+    out = net(x)
+    d = tc.get_captured_tensors_dict()
+    assert list(d) == ["b.inputs.0", "b.outputs", "a.inputs.0", "a.inputs.kwargs.scale", "a.outputs.aux.0", "a.outputs.aux.1",
+                       "a.outputs.hidden", "manual_pre_act", "manual_pre_act_1"], list(d)
+    torch.testing.assert_close(d["b.outputs"], out)
+    torch.testing.assert_close(d["a.outputs.aux.1"], 2 * d["a.outputs.aux.0"])
+    torch.testing.assert_close(d["manual_pre_act_1"], d["manual_pre_act"] + 1)
+    reg = tc.TensorRegistry.get_instance()
+    assert reg.get_manual_tensor_count() == 2 and reg.get_monitored_tensor_count() == 7 and reg.get_total_tensor_count() == 9
+    reg.model_info.manual_tensors["l0.moe_auto"] = torch.zeros(3); reg.model_info.manual_tensors["l1.moe_auto"] = torch.ones(3)
+    assert reg.get_manual_tensors()["auto_moe_stats.expert_index"].shape == (2, 3)
+    assert tc.get_captured_tensors(clear=True) and not tc.get_captured_tensors_dict()
+    net = tc.disable_tensor_capture(net)
+    net(x)
+    assert not tc.get_captured_tensors_dict() and not reg.model_info.hooks
+
+    # golden-side capture of an eager model: one file per (phase, step, tensor)
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as td:
+        net = tc.modify_hf_eager_model_for_tensor_capture(net, ["b"], tensor_capture_save_dir=td)
+        net(x); net(x)
+        files = sorted(os.listdir(td))
+        assert files == ["captured_tensors_cte_step_1_module_b.outputs.pt", "captured_tensors_tkg_step_2_module_b.outputs.pt"], files
+        torch.testing.assert_close(torch.load(os.path.join(td, files[0])), out)
+        net = tc.restore_model(net)
+        net(x)
+        assert len(os.listdir(td)) == 2
+
+    # replacement as trailing (tensor, mask) arguments: the same prepared model replaces nothing / one layer / part of a layer
+    tr.RuntimeRegister.module_superset = ["0", "2"]
+    m2, hooks = tr.modify_model_for_tensor_replacement(m)
+    zeros0, zeros2 = torch.zeros(3, 4), torch.zeros(3, 2)
+    off = torch.zeros((), dtype=torch.bool)
+    torch.testing.assert_close(m2(x, zeros0, zeros2, off, off), y)
+    torch.testing.assert_close(m2(x, inj, zeros2, ~off, off), y2)
+    part = torch.zeros(3, 2, dtype=torch.bool); part[0] = True
+    got = m2(x, zeros0, torch.full((3, 2), 7.0), off, part)
+    assert (got[0] == 7).all() and torch.allclose(got[1:], y[1:])
+    with pytest.raises(ValueError):
+        m2(x, zeros0, off)
+    assert not tr.RuntimeRegister._tr_runtime_list                      # cleared after every forward
+    for h in hooks.values():
+        h.remove()
+    m.forward = m._nxd_tr_original_forward
+    tr.RuntimeRegister.module_superset = []
 
 
 def test_medusa_buffers():
@@ -143,3 +218,105 @@ def _ep(rank, world):
 
 def test_expert_parallel_all_to_all_training():
     run_distributed(_ep, 2, timeout=90)
+
+
+def test_small_utils(tmp_path):
+    """Medusa step helpers, serialization helpers, label shift, checkpoint_wrapper, duplicate-tensor check, timeline,
+    autocast casting helpers, shared-weight helpers."""
+    import json
+    import logging
+    from collections import namedtuple
+
+    from neuronx_distributed_b200.parallel_layers.utils import (cast_if_autocast_enabled, get_padding_length,
+                                                                indices_split_along_dim, move_all_tensor_to_cpu,
+                                                                verify_casted_dtype)
+    from neuronx_distributed_b200.utils.activation_checkpoint import NxDCheckpointWrapper, checkpoint_wrapper
+    from neuronx_distributed_b200.utils.batch_utils import shift_labels
+    from neuronx_distributed_b200.utils.logger import PackagePathFilter
+    from neuronx_distributed_b200.utils.medusa_utils import (evaluate_posterior, generate_candidates, generate_medusa_buffers,
+                                                            update_inference_inputs)
+    from neuronx_distributed_b200.utils.model_utils import (analyze_shared_parameters, has_fake_tensors, preserve_shared_weights,
+                                                           recursive_filter, retie_shared_weights)
+    from neuronx_distributed_b200.utils.safetensors_utils import check_for_duplicate_tensors
+    from neuronx_distributed_b200.utils.serialization import compress_to_string, is_instance_namedtuple, uncompress_from_string
+    from neuronx_distributed_b200.utils.timeline import DistributedTimeline, Event
+
+    # Medusa: tree of 6 nodes over 3 heads × top-3; the model "confirms" the path 7 → 100 → 103 and rejects 106
+    b = generate_medusa_buffers([(0,), (1,), (0, 0), (0, 1), (1, 0), (0, 0, 0)], topk=3)
+    H, K = 3, 3
+    cart, tree = generate_candidates(torch.arange(100, 100 + H * K).view(H, 1, 1, K), torch.tensor([[[7, 8]]]),
+                                     b["tree_indices"], b["retrieve_indices"])
+    assert tree.tolist() == [[7, 100, 101, 103, 104, 103, 106]] and cart[0].tolist() == [7, 100, 103, 106]
+    ver = torch.zeros(cart.shape[0], cart.shape[1], 1, dtype=torch.long)
+    ver[:, 0, 0], ver[:, 1, 0], ver[:, 2, 0] = 100, 103, 999
+    best, n_acc = evaluate_posterior(ver, cart)
+    assert int(best) == 0 and int(n_acc) == 2
+    ids, lg, mlg, new_tok, sel = update_inference_inputs(torch.tensor([[1, 2, 3]]), cart, best, n_acc, b["retrieve_indices"], None,
+                                                        ver, torch.zeros(H, cart.shape[0], cart.shape[1], K, dtype=torch.long), 0)
+    assert ids.tolist() == [[1, 2, 3, 7, 100, 103]] and new_tok == 3 and sel.tolist() == [3, 4, 6]
+    assert lg.shape == (1, 1, 1) and int(lg) == 999 and mlg.shape == (H, 1, 1, K)
+    best0, n0 = evaluate_posterior(torch.full_like(ver, 5), cart)                      # nothing matches → path 0, length 0
+    assert int(best0) == 0 and int(n0) == 0
+
+    P = namedtuple("P", "a b")
+    assert uncompress_from_string(compress_to_string({"x": (1, [2]), "t": torch.ones(2)}))["x"] == (1, [2])
+    assert is_instance_namedtuple(P(1, 2)) and not is_instance_namedtuple((1, 2))
+    sb = shift_labels({"input_ids": torch.arange(6).view(2, 3), "labels": torch.arange(6).view(2, 3)})
+    assert sb["labels"].tolist() == [[1, 2, -100], [4, 5, -100]] and sb["input_ids"].tolist() == [[0, 1, 2], [3, 4, 5]]
+
+    calls = []
+    lin = nn.Linear(4, 4)
+    w = checkpoint_wrapper(lin, checkpoint_fn=lambda mod, *a, **k: (calls.append(1), mod(*a, **k))[1])
+    assert isinstance(w, NxDCheckpointWrapper) and set(w.state_dict()) == {"weight", "bias"}
+    w(torch.randn(2, 4, requires_grad=True)).sum().backward()
+    assert calls == [1] and lin.weight.grad is not None
+
+    t = torch.randn(4, 4)
+    ck = {"a": t, "b": t, "c": torch.randn(2)}
+    assert set(check_for_duplicate_tensors(dict(ck))) == {"a", "b", "c"}               # default: warn only
+    assert set(check_for_duplicate_tensors(dict(ck), remove_duplicate_tensors=True)) == {"a", "c"}
+    with pytest.raises(RuntimeError):
+        check_for_duplicate_tensors({"x": t[:2], "y": t[2:]}, remove_duplicate_tensors=True)
+
+    path = tmp_path / "trace.json"
+    tl = DistributedTimeline(str(path))
+    tl.mark_event_start("fwd"); tl.mark_event_end("fwd"); tl.mark_step_end()
+    tl.mark_event_start("bwd"); tl.mark_event_end("bwd"); tl.mark_step_end()
+    events = json.loads(path.read_text().rstrip().rstrip(",") + "]")
+    assert [(e["name"], e["ph"]) for e in events] == [("fwd", "B"), ("fwd", "E"), ("bwd", "B"), ("bwd", "E")] and tl.step == 2
+    assert Event("x", 0).start == -1
+    off = DistributedTimeline(None)
+    off.mark_event_start("x"); off.mark_step_end()                                      # disabled: no-ops
+
+    rec = logging.LogRecord("n", logging.INFO, __file__, 1, "m", None, None)
+    assert PackagePathFilter().filter(rec) and not os.path.isabs(rec.relativepath)
+
+    assert get_padding_length(30, 8) == 2 and get_padding_length(32, 8) == 0
+    assert indices_split_along_dim(torch.zeros(8, 3), 0, 2, 4).tolist() == [4, 5]
+    assert indices_split_along_dim(None, 0, 0, 2) is None
+    x32 = torch.ones(2)
+    assert cast_if_autocast_enabled(x32)[0].dtype == torch.float32
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        a, (bb, c), d = cast_if_autocast_enabled(x32, (x32.double(), torch.ones(1, dtype=torch.long)), "s")
+        assert a.dtype == torch.bfloat16 and bb.dtype == torch.float64 and c.dtype == torch.long and d == "s"
+        verify_casted_dtype((a, {"k": a}))
+        with pytest.raises(AssertionError):
+            verify_casted_dtype(x32)
+    assert move_all_tensor_to_cpu({"a": [x32]})["a"][0] is x32
+
+    class Tied(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.e, self.h = nn.Embedding(10, 4), nn.Linear(4, 10, bias=False)
+            self.h.weight = self.e.weight
+
+    m = Tied()
+    assert analyze_shared_parameters(m) == [["e.weight", "h.weight"]]
+    with preserve_shared_weights(m):
+        m.h.weight = nn.Parameter(torch.zeros(10, 4))
+    assert m.h.weight is m.e.weight
+    m.h.weight = nn.Parameter(torch.zeros(10, 4))
+    retie_shared_weights(m, [["e.weight", "h.weight"]])
+    assert m.h.weight is m.e.weight
+    assert has_fake_tensors(nn.Linear(2, 2, device="meta")) and not has_fake_tensors(m)
+    assert recursive_filter({"a": x32, "b": [torch.zeros(1, device="meta"), 3]}, lambda t_: not t_.is_meta) == {"a": x32, "b": [3]}
