@@ -20,7 +20,7 @@ def __getattr__(name):
     import importlib
 
     lazy = {
-        "pipeline": ".pipeline", "kernels": ".kernels", "trace": ".inference", "inference": ".inference",
+        "pipeline": ".pipeline", "kernels": ".kernels", "trace": ".trace", "inference": ".inference",
         "modules": ".modules", "models": ".models", "optimizer": ".optimizer", "trainer": ".trainer",
         "quantization": ".quantization", "operators": ".operators", "lightning": ".lightning",
     }

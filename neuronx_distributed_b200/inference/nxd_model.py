@@ -4,7 +4,11 @@
 * each :class:`BucketProgram` owns persistent input buffers and, on CUDA, a captured graph: ``forward`` copies the
   inputs into the static buffers, replays the graph and returns the static outputs;
 * state (KV cache) lives in the wrapped module and is shared by all programs;
-* ``save``/``load`` persist weights as per-rank safetensors."""
+* ``save``/``load`` persist weights as per-rank safetensors.
+
+Two ways to fill it: ``add_program`` (v1 ``ModelBuilder.add(key, …)`` buckets) and ``add(key, trace_artifacts,
+compilation_artifacts)`` (v2 ``trace`` → ``compile`` units, reference :87-194), after which ``forward`` accepts positional
+and keyword tensors, orders the keyword ones by the traced signature and routes by (argument names, shapes)."""
 from __future__ import annotations
 
 import os
@@ -48,25 +52,137 @@ class BucketProgram:
         return self.static_out
 
 
+class StateInitializer(nn.Module):
+    """Allocates the state (KV-cache) buffers of a model: one zero tensor per ``(name → shape, dtype)`` entry on this rank's
+    device (reference ``base_nxd_model.py:11-33`` creates them for every local rank of the process; here a process drives
+    exactly one GPU)."""
+
+    def __init__(self, shapes: Dict[str, Sequence[int]], dtypes: Dict[str, torch.dtype], local_ranks_size: int = 1):
+        super().__init__()
+        self.shapes, self.dtypes, self.local_ranks_size = dict(shapes), dict(dtypes), local_ranks_size
+
+    def forward(self) -> List[Dict[str, torch.Tensor]]:
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        return [{k: torch.zeros(tuple(self.shapes[k]), dtype=self.dtypes[k], device=dev) for k in self.shapes}
+                for _ in range(self.local_ranks_size)]
+
+
 class BaseNxDModel(nn.Module):
-    pass
+    """Interface of the runtime model (reference ``base_nxd_model.py:36-182``)."""
+
+    def get_available_keys(self):
+        raise NotImplementedError
+
+    def set_weights(self, sharded_checkpoint):
+        raise NotImplementedError
+
+    def to_neuron(self):
+        raise NotImplementedError
+
+    def replace_weights(self, sharded_checkpoint):
+        raise NotImplementedError
+
+    def router(self, inputs, arg_names=None):
+        raise NotImplementedError
+
+
+SUPPORTED_FORWARD_MODES = {"default", "ranked", "ranked_to_cpu", "async"}
 
 
 class NxDModel(BaseNxDModel):
-    def __init__(self, world_size: int = 1, router: Any = None, start_rank: Optional[int] = None, local_ranks_size: Optional[int] = None):
+    def __init__(self, world_size: int = 1, router: Any = None, start_rank: Optional[int] = None,
+                 local_ranks_size: Optional[int] = None, state_initializer: Optional[StateInitializer] = None,
+                 layout_transformer: Any = None):
         super().__init__()
         self.world_size, self.custom_router = world_size, router
+        if start_rank is None:
+            assert local_ranks_size is None or local_ranks_size == world_size, \
+                f"{local_ranks_size=} but start_rank is not defined. If local_ranks_size is set, the start rank must also be set."
+            self.start_rank, self.local_ranks_size = 0, world_size
+        else:
+            assert local_ranks_size is not None, \
+                f"{start_rank=} but found local_ranks_size to be unset. If setting start_rank, local_ranks_size must also be set."
+            self.start_rank, self.local_ranks_size = start_rank, local_ranks_size
         self.programs: Dict[str, List[BucketProgram]] = {}
+        # v2 units: key → (trace artifacts, compilation artifacts)
+        self.units: Dict[str, Tuple[Any, Any]] = {}
+        self.model_params: List[Any] = []
+        self.input_shape_map: Dict[str, List[str]] = {}
+        self.state_initializer = state_initializer
+        self.states: List[Dict[str, torch.Tensor]] = []
+        self.layout_transformer = layout_transformer
         self.loaded_on_device = False
 
+    @property
+    def loaded_on_neuron(self) -> bool:               # reference attribute name
+        return self.loaded_on_device
+
+    # ---- construction ------------------------------------------------------------------
     def add_program(self, prog: BucketProgram) -> None:
         self.programs.setdefault(prog.key, []).append(prog)
         self.programs[prog.key].sort(key=lambda p: sum(int(torch.tensor(s).prod()) for s in p.shapes))
 
-    def get_available_keys(self) -> List[str]:
-        return list(self.programs)
+    def add(self, key: str, trace_artifacts: Any, compilation_artifacts: Any) -> "NxDModel":
+        """Register one traced + compiled bucket (reference :87-194).  All buckets of one NxDModel must come from the same
+        ``forward`` signature; two buckets may not share (argument names, shapes, dtypes)."""
+        if key in self.units:
+            raise KeyError(f"key {key!r} is already registered")
+        params = [(p.param_name, p.is_positional) for p in trace_artifacts.model_params]
+        if self.model_params and params != self.model_params:
+            raise ValueError(f"bucket {key!r} was traced from a different signature: {params} vs {self.model_params}")
+        sig = self._route_key([a.param_name for a in trace_artifacts.provided_args], [a.tensor for a in trace_artifacts.provided_args])
+        # two buckets with the same route are legal (e.g. prefill vs speculation programs of one shape): forward() then
+        # requires ``model_name``
+        self.model_params = params
+        self.input_shape_map.setdefault(sig, []).append(key)
+        self.units[key] = (trace_artifacts, compilation_artifacts)
+        return self
 
-    def router(self, inputs: Sequence[torch.Tensor], key: Optional[str] = None) -> BucketProgram:
+    @staticmethod
+    def _route_key(names: Sequence[str], tensors: Sequence[torch.Tensor]) -> str:
+        return ";".join(f"{n}:{tuple(t.shape)}:{t.dtype}" for n, t in zip(names, tensors))
+
+    def get_available_keys(self) -> List[str]:
+        return list(self.programs) + list(self.units)
+
+    def _unit(self, key: str):
+        if key not in self.units:
+            raise KeyError(f"{key!r} is not a registered bucket; available: {self.get_available_keys()}")
+        return self.units[key]
+
+    def get_hlo(self, key: str):
+        """The reference returns the HLO proto of a bucket; the B200 analogue is the bucket's call description."""
+        return self._unit(key)[0].describe()
+
+    def get_metaneff(self, key: str):
+        return self._unit(key)[0].metaneff
+
+    def get_neff(self, key: str) -> bytes:
+        return self._unit(key)[1].get_neff_bytes()
+
+    # ---- routing / execution -------------------------------------------------------------
+    def convert_dict_to_ordered_list(self, inputs: Dict[str, Any], num_pos_args: int) -> Tuple[List[Any], List[str]]:
+        """Keyword inputs → list ordered by the traced signature; returns it with the names of ALL supplied arguments
+        (positional ones first)."""
+        names = [n for n, _ in self.model_params]
+        pos = names[:num_pos_args]
+        unknown = set(inputs) - set(names)
+        if unknown:
+            raise KeyError(f"unexpected keyword inputs {sorted(unknown)}; the traced signature has {names}")
+        dup = set(inputs) & set(pos)
+        if dup:
+            raise KeyError(f"{sorted(dup)} given both positionally and by keyword")
+        ordered = [n for n in names[num_pos_args:] if n in inputs]
+        return [inputs[n] for n in ordered], pos + ordered
+
+    def router(self, inputs: Sequence[torch.Tensor], arg_names: Optional[Sequence[str]] = None, key: Optional[str] = None):
+        """v2 (``arg_names`` given): list of bucket keys whose traced (names, shapes, dtypes) equal the call's.
+        v1: the matching :class:`BucketProgram`."""
+        if arg_names is not None:
+            sig = self._route_key(arg_names, inputs)
+            if sig not in self.input_shape_map:
+                raise KeyError(f"no bucket was traced for inputs {sig}; known routes: {list(self.input_shape_map)}")
+            return list(self.input_shape_map[sig])
         if self.custom_router is not None:
             r = self.custom_router(inputs)
             if isinstance(r, BucketProgram):
@@ -79,39 +195,171 @@ class NxDModel(BaseNxDModel):
                     return p
         raise ValueError(f"no compiled bucket for input shapes {[tuple(t.shape) for t in inputs]} (keys {keys})")
 
-    def forward(self, *inputs: torch.Tensor, model_name: Optional[str] = None, forward_mode: str = "default"):
-        return self.router(inputs, model_name)(*inputs)
+    def _my_rank_index(self, n: int) -> int:
+        if n == 1:
+            return 0
+        import torch.distributed as dist
 
-    # ---- weights -----------------------------------------------------------------------
-    def set_weights(self, sharded_checkpoint: Sequence[Dict[str, torch.Tensor]]) -> None:
+        r = dist.get_rank() if dist.is_initialized() else 0
+        return (r - self.start_rank) if n == self.local_ranks_size else r
+
+    def forward(self, *args, model_name: Optional[str] = None, forward_mode: str = "default", **kwargs):
+        """``default``: tensors in, this bucket's outputs out.  ``ranked`` / ``ranked_to_cpu`` / ``async``: every input is a
+        list with one tensor per rank (this process uses its own entry) and every output comes back as a one-per-local-rank
+        list — ``async`` returns without synchronising (CUDA launches are asynchronous anyway; call ``.cpu()`` to block),
+        ``ranked_to_cpu`` copies the outputs to host."""
+        assert forward_mode in SUPPORTED_FORWARD_MODES, f"{forward_mode=} is not supported. It must be one of {SUPPORTED_FORWARD_MODES}"
+        if not self.units:                                   # v1 programs
+            return self.router(args, key=model_name)(*args)
+        if not self.loaded_on_device:
+            raise RuntimeError("Model not initialized. Call set_weights() followed by to_neuron()")
+        kw, names = self.convert_dict_to_ordered_list(kwargs, len(args))
+        inputs = list(args) + kw
+        if forward_mode != "default":
+            inputs = [x[self._my_rank_index(len(x))] if isinstance(x, (list, tuple)) else x for x in inputs]
+        routes = self.router(inputs, names)
+        if len(routes) > 1:
+            assert model_name is not None, (f"Got {len(routes)} possible routes but model_name wasn't provided. The Model "
+                                            "Name must be provided if input routing is ambiguous.")
+            assert model_name in routes, f"{model_name=} is not among the routes for these inputs: {routes}"
+        else:
+            assert model_name is None or model_name == routes[0], \
+                f"Provided model_name does not match model name found by the shape router. Found {routes[0]} but got {model_name}"
+            model_name = routes[0]
+        ta, ca = self.units[model_name]
+        out = ta.packer(ca.program(*ta.flattener(inputs)))
+        if forward_mode == "default":
+            return out
+        flat = list(out) if isinstance(out, (list, tuple)) else [out]
+        if forward_mode == "ranked_to_cpu":
+            flat = [t.cpu() if isinstance(t, torch.Tensor) else t for t in flat]
+        return [[t] for t in flat]                           # [output][local rank]
+
+    # ---- weights / state -----------------------------------------------------------------
+    def _unique_modules(self) -> List[nn.Module]:
+        seen: Dict[int, nn.Module] = {}
+        for progs in self.programs.values():
+            for p in progs:
+                if isinstance(p.module, nn.Module):
+                    seen[id(p.module)] = p.module
+        for ta, _ in self.units.values():
+            if isinstance(ta.model, nn.Module):
+                seen[id(ta.model)] = ta.model
+        return list(seen.values())
+
+    def _my_shard(self, sharded_checkpoint: Sequence[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:
         from ..parallel_layers import parallel_state as ps
 
         r = ps.get_tensor_model_parallel_rank() if ps.model_parallel_is_initialized() else 0
-        sd = sharded_checkpoint[r] if len(sharded_checkpoint) > r else sharded_checkpoint[0]
-        seen = set()
-        for progs in self.programs.values():
-            for p in progs:
-                if id(p.module) not in seen:
-                    seen.add(id(p.module))
-                    p.module.load_state_dict(sd, strict=False)
+        if len(sharded_checkpoint) == self.world_size and self.world_size > r:
+            return sharded_checkpoint[r]
+        return sharded_checkpoint[min(r - self.start_rank, len(sharded_checkpoint) - 1)] if len(sharded_checkpoint) > 1 \
+            else sharded_checkpoint[0]
 
-    def to_neuron(self) -> None:     # reference name; weights already live on the device
+    def set_weights(self, sharded_checkpoint: Sequence[Dict[str, torch.Tensor]]) -> None:
+        """Copy this rank's shard INTO the existing parameter tensors (their addresses are baked into captured graphs)."""
+        sd = self._my_shard(sharded_checkpoint)
+        for m in self._unique_modules():
+            own = dict(m.named_parameters())
+            own.update(dict(m.named_buffers()))
+            with torch.no_grad():
+                for k, v in sd.items():
+                    if k in own and tuple(own[k].shape) == tuple(v.shape):
+                        own[k].copy_(v)
+        self._weights_set = True
+
+    def replace_weights(self, sharded_checkpoint: Sequence[Dict[str, torch.Tensor]]) -> None:
+        """Swap in new weights after the model is live (LoRA merge, checkpoint hot-swap): same in-place copy, graphs stay
+        valid."""
+        self.set_weights(sharded_checkpoint)
+
+    def to_neuron(self) -> None:     # reference name
+        """Mark the model ready: weights already live on the device (``set_weights`` copied in place, or the module was built
+        with real weights); create the state buffers if a :class:`StateInitializer` was given."""
+        if self.state_initializer is not None and not self.states:
+            self.states = self.state_initializer()
         self.loaded_on_device = True
 
     to_device = to_neuron
 
-    def save(self, path: str, save_weights: bool = False) -> None:
+    def _find_buffer(self, buffer_key: str) -> torch.Tensor:
+        for st in self.states:
+            if buffer_key in st:
+                return st[buffer_key]
+        for m in self._unique_modules():
+            for n, b in list(m.named_buffers()) + list(m.named_parameters()):
+                if n == buffer_key:
+                    return b
+        raise KeyError(f"no state / weight buffer named {buffer_key!r}")
+
+    def read_from_neuron_buffer(self, buffer_key: str, rank: int = 0) -> torch.Tensor:
+        """Host copy of a state (KV cache) or weight buffer of this process's rank."""
+        return self._find_buffer(buffer_key).detach().cpu()
+
+    def write_to_neuron_buffer(self, tensor: torch.Tensor, buffer_key: str, rank: int = 0) -> None:
+        dst = self._find_buffer(buffer_key)
+        assert tuple(dst.shape) == tuple(tensor.shape), f"shape mismatch for {buffer_key}: {tuple(tensor.shape)} vs {tuple(dst.shape)}"
+        with torch.no_grad():
+            dst.copy_(tensor.to(dst.dtype))
+
+    # ---- persistence ---------------------------------------------------------------------
+    def save(self, path_to_save: str, save_weights: bool = False) -> None:
+        """Directory with ``nxd_model_meta.pt`` (bucket keys, signatures, example input shapes; the module object itself when
+        it pickles, so ``load`` can re-capture without user code) and optionally ``weights_<i>_tp<rank>.safetensors``."""
         from ..parallel_layers import parallel_state as ps
         from ..utils.safetensors_utils import save_state_dict_safetensors
 
-        os.makedirs(path, exist_ok=True)
-        meta = {k: [{"shapes": p.shapes, "dtypes": [str(d) for d in p.dtypes]} for p in v] for k, v in self.programs.items()}
-        torch.save(meta, os.path.join(path, "nxd_model_meta.pt"))
+        os.makedirs(path_to_save, exist_ok=True)
+        meta: Dict[str, Any] = {
+            "world_size": self.world_size, "model_params": self.model_params,
+            "programs": {k: [{"shapes": p.shapes, "dtypes": [str(d) for d in p.dtypes]} for p in v] for k, v in self.programs.items()},
+            "units": {k: {"inputs": ta.input_signature(), "outputs": ta.output_spec, "flags": ca.compiler_args}
+                      for k, (ta, ca) in self.units.items()},
+        }
+        mods = self._unique_modules()
+        if self.units and len(mods) == 1:
+            try:
+                import io
+                import pickle
+
+                buf = io.BytesIO()
+                pickle.dump(mods[0], buf)
+                meta["module_pickle"] = buf.getvalue()
+            except Exception:  # noqa: BLE001  (process groups, lambdas … → load() then needs ``model=``)
+                meta["module_pickle"] = None
+        torch.save(meta, os.path.join(path_to_save, "nxd_model_meta.pt"))
         if save_weights:
             r = ps.get_tensor_model_parallel_rank() if ps.model_parallel_is_initialized() else 0
-            seen = {}
-            for progs in self.programs.values():
-                for p in progs:
-                    seen[id(p.module)] = p.module
-            for i, m in enumerate(seen.values()):
-                save_state_dict_safetensors(m.state_dict(), os.path.join(path, f"weights_{i}_tp{r}.safetensors"))
+            for i, m in enumerate(mods):
+                save_state_dict_safetensors(m.state_dict(), os.path.join(path_to_save, f"weights_{i}_tp{r}.safetensors"))
+
+    @classmethod
+    def load(cls, path_to_model: str, start_rank: Optional[int] = None, local_ranks_size: Optional[int] = None,
+             model: Optional[nn.Module] = None, device: Optional[torch.device] = None) -> "NxDModel":
+        """Rebuild a saved v2 model: re-trace and re-capture every bucket from the recorded input signatures.  ``model`` is
+        needed when the module could not be pickled at save time."""
+        import pickle
+
+        from ..parallel_layers import parallel_state as ps
+        from ..utils.safetensors_utils import load_state_dict_safetensors
+        from .functions import compile as _compile
+        from .functions import trace as _trace
+
+        meta = torch.load(os.path.join(path_to_model, "nxd_model_meta.pt"), weights_only=False)
+        if model is None:
+            if not meta.get("module_pickle"):
+                raise ValueError("the saved model does not embed its module; pass model=<the nn.Module>")
+            model = pickle.loads(meta["module_pickle"])
+        dev = device or (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+        model = model.to(dev)
+        r = ps.get_tensor_model_parallel_rank() if ps.model_parallel_is_initialized() else 0
+        wpath = os.path.join(path_to_model, f"weights_0_tp{r}.safetensors")
+        if os.path.exists(wpath):
+            model.load_state_dict(load_state_dict_safetensors(wpath), strict=False)
+        nxd = cls(world_size=meta["world_size"], start_rank=start_rank, local_ranks_size=local_ranks_size)
+        for key, u in meta["units"].items():
+            tensors = {n: torch.zeros(shape, dtype=getattr(torch, dt.replace("torch.", "")), device=dev) for n, shape, dt in u["inputs"]}
+            ta = _trace(model, None, tensors)
+            nxd.add(key, ta, _compile(ta, None, None, u.get("flags"), key))
+        nxd._weights_set = os.path.exists(wpath)
+        return nxd

@@ -32,14 +32,36 @@ def _run_preshard_hooks(model: nn.Module, sd: Dict[str, Any]) -> None:
             break
 
 
+def _select_local_experts(full: torch.Tensor, param: torch.Tensor, global_rank: int, world: int) -> torch.Tensor:
+    """Expert-parallel parameters hold ``E/ep`` experts on dim 0: keep the experts owned by this rank's EP coordinate
+    (reference trace/trace.py:762-776; rank layout ``[ep, tp]`` with TP fastest — ``parallel_state`` grid order)."""
+    if not getattr(param, "expert_model_parallel", False) or full.shape[0] == param.shape[0]:
+        return full
+    from ..parallel_layers import parallel_state as ps
+
+    ep = full.shape[0] // param.shape[0]
+    tp = max(1, world // ep)
+    ep_rank = (global_rank // tp) % ep
+    dist_spec = getattr(param, "expert_distribution", None)
+    ids = list(dist_spec[ep_rank]) if dist_spec is not None else ps.get_experts_for_expert_parallel_rank(ep_rank, full.shape[0], ep)
+    idx = torch.as_tensor(ids, dtype=torch.long)
+    if full.dtype in (torch.float8_e4m3fn, torch.float8_e5m2):                 # no fp8 gather on CPU: index the byte view
+        return full.view(torch.int8)[idx].view(full.dtype)
+    if full.dtype in (torch.uint16, torch.uint32):
+        alias = torch.int16 if full.dtype == torch.uint16 else torch.int32
+        return full.view(alias)[idx].view(full.dtype)
+    return full[idx]
+
+
 def shard_tensor(full: torch.Tensor, param: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    full = _select_local_experts(full, param, rank, world)
     if not getattr(param, "tensor_model_parallel", False):
         return full
     dim = param.partition_dim
     stride = getattr(param, "partition_stride", 1)
     nparts = getattr(param, "num_partitions", world)
     order = getattr(param, "rank_ordering", None)
-    r = order[rank] if order else rank
+    r = (order[rank] if order else rank) % nparts
     if getattr(param, "fused_qkv", False) and full.shape[dim] != param.shape[dim] * nparts:
         raise ValueError("fused qkv tensor has unexpected size; run preshard hooks first")
     if full.shape[dim] == param.shape[dim]:
