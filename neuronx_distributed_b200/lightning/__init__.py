@@ -7,3 +7,5 @@ from .strategy import NeuronXLAStrategy, NxDStrategy  # noqa: F401
 from .checkpoint_io import NeuronCheckpointIO  # noqa: F401
 from .logger import NeuronTensorBoardLogger  # noqa: F401
 from .callbacks import NeuronHooksCallback, NeuronTQDMProgressBar  # noqa: F401
+from .accelerator import NeuronXLAAccelerator  # noqa: F401
+from .precision_plugin import NeuronXLAPrecisionPlugin  # noqa: F401

@@ -242,3 +242,52 @@ class GQAQKVColumnParallelLinear(BaseParallelLayer):
                 model_state_dict[kk], model_state_dict[kv] = k, v
             changed = True
         return changed
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# functional form (reference qkv_linear.py:43-368)
+# ---------------------------------------------------------------------------------------------------------------------
+def gqa_qkv_linear_with_async_allreduce(input: torch.Tensor, weight_q, weight_k, weight_v, bias_q, bias_k, bias_v,  # noqa: A002
+                                        async_grad_allreduce: bool, sequence_parallel_enabled: bool, kv_size_multiplier: int = 1,
+                                        weight_qkv=None, bias_qkv=None, fuse_qkv: bool = False, output_size_q: Optional[int] = None,
+                                        output_size_kv: Optional[int] = None, reduce_dtype: torch.dtype = torch.float32,
+                                        sequence_dimension: int = 0, process_group=None, kv_group=None):
+    """``(q, k, v) = split(x · [Wq; Wk; Wv]ᵀ)`` as ONE GEMM on the local shards.
+
+    * ``sequence_parallel_enabled`` — the input is all-gathered along the sequence dim inside the GEMM kernel (fused
+      AG→GEMM over NVLink peer memory) and its gradient is reduce-scattered; otherwise ``async_grad_allreduce`` all-reduces
+      the input gradient over the TP group, overlapped with the weight-gradient GEMM;
+    * ``kv_size_multiplier > 1`` — K/V heads are replicated across groups of TP ranks: the K and V gradients are summed over
+      the KV-shared group (``parallel_state.get_kv_shared_group``) so the replicas stay identical."""
+    group = process_group if process_group is not None else ps.get_tensor_model_parallel_group()
+    tp = dist.get_world_size(group)
+    if fuse_qkv:
+        w, b = weight_qkv, bias_qkv
+        qp = output_size_q if output_size_q is not None else None
+        kvp = output_size_kv
+        assert qp is not None and kvp is not None, "output_size_q / output_size_kv (per-partition sizes) are required with fuse_qkv"
+    else:
+        w = torch.cat([weight_q, weight_k, weight_v], dim=0)
+        b = torch.cat([bias_q, bias_k, bias_v], dim=0) if bias_q is not None else None
+        qp, kvp = weight_q.shape[0], weight_k.shape[0]
+    in_mode = "gather" if sequence_parallel_enabled else ("copy" if (async_grad_allreduce and tp > 1) else "none")
+    out = tp_linear(input, w, None, in_mode, "none", sequence_dimension, group, reduce_dtype)
+    if b is not None:
+        out = out + b
+    q, k, v = torch.split(out, [qp, kvp, kvp], dim=-1)
+    if kv_size_multiplier > 1:
+        kvg = kv_group if kv_group is not None else ps.get_kv_shared_group()
+        k, v = _KVGradSum.apply(k, kvg, reduce_dtype), _KVGradSum.apply(v, kvg, reduce_dtype)
+    return q, k, v
+
+
+class GQAQKVLinearWithAsyncCommunication:
+    """Name-compatible façade (reference :43-327): ``apply`` takes the reference's positional arguments."""
+
+    @staticmethod
+    def apply(input, weight_q, weight_k, weight_v, bias_q, bias_k, bias_v, async_grad_allreduce, sequence_parallel_enabled,  # noqa: A002
+              kv_size_multiplier=1, weight_qkv=None, bias_qkv=None, fuse_qkv=False, output_size_q=None, output_size_kv=None,
+              reduce_dtype=torch.float32):
+        return gqa_qkv_linear_with_async_allreduce(input, weight_q, weight_k, weight_v, bias_q, bias_k, bias_v, async_grad_allreduce,
+                                                   sequence_parallel_enabled, kv_size_multiplier, weight_qkv, bias_qkv, fuse_qkv,
+                                                   output_size_q, output_size_kv, reduce_dtype)

@@ -26,3 +26,19 @@ def topk(tensor: torch.Tensor, k: int, dim: int, gather_dim: Optional[int] = Non
     alli = comm.all_gather(gidx, dim=dim, group=group)
     fv, pos = torch.topk(allv, k, dim=dim)
     return fv, torch.gather(alli, dim, pos)
+
+
+def get_topk_implementation(use_topk_rotated_kernel: bool = False, lnc: int = 1, stages: int = 1):
+    """``(topk_unsorted, topk_sorted, stages)`` — the local top-k used inside the distributed one (reference :14-28).
+    ``torch.topk`` on CUDA is a radix-select kernel and is used for both; ``use_topk_rotated_kernel`` / ``lnc`` select an
+    NKI kernel variant in the reference and are accepted for compatibility."""
+    if use_topk_rotated_kernel:
+        assert stages == 1, "stages other than 1 is not supported when using topk_rotated kernel"
+
+    def topk_unsorted(t: torch.Tensor, k: int, dim: Optional[int] = None):
+        return torch.topk(t, k, dim=-1 if dim is None else dim, sorted=False)
+
+    def topk_sorted(t: torch.Tensor, k: int, dim: Optional[int] = None):
+        return torch.topk(t, k, dim=-1 if dim is None else dim, sorted=True)
+
+    return topk_unsorted, topk_sorted, stages

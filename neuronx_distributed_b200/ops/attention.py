@@ -117,13 +117,3 @@ def flash_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: b
     if _own_kernel_ok(q, k, v) and (not causal or q.shape[1] == k.shape[1]):
         return _FlashAttn.apply(q, k, v, causal, scale)
     return _sdpa(q, k, v, causal, scale)
-
-
-# reference-compatible names (kernels/flash_attn.py:162, kernels/ring_attention_kernel.py:118)
-def nki_flash_attn_func(q, k, v, lnc: int = 1, dropout_p: float = 0.0, softmax_scale=None, causal: bool = True,
-                        transpose_nki_inputs: bool = True):
-    """Reference layout is ``[B, H, S, D]``; returns the same layout."""
-    del lnc, transpose_nki_inputs
-    assert dropout_p == 0.0, "attention dropout is not supported by the fused kernel"
-    o = flash_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), causal, softmax_scale)
-    return o.transpose(1, 2)

@@ -80,30 +80,119 @@ def reshard(full: Dict[str, Any], new_dp: int) -> List[Dict[str, Any]]:
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# reference-named helpers (convert_zero_checkpoints.py:15-177) + CLI
+# ---------------------------------------------------------------------------------------------------------------------
+def _optim_dir(args) -> str:
+    """``--input_dir`` may be the checkpoint tag directory (reference) or its ``optim`` sub-directory."""
+    d = os.path.join(args.input_dir, "optim")
+    return d if os.path.isdir(d) else args.input_dir
+
+
+def is_full(args) -> bool:
+    return any(f.startswith("full") for f in os.listdir(_optim_dir(args)))
+
+
+def is_xser(args) -> bool:
+    """Tensors stored out of line (``<file>.tensors/`` directories next to the ``.pt`` stubs)."""
+    d = _optim_dir(args)
+    return any(f.endswith(".tensors") and os.path.isdir(os.path.join(d, f)) for f in os.listdir(d))
+
+
+def get_parallel_info(args):
+    """``(dp, tp, pp)`` sizes inferred from the file names (``dp == 0`` for a full checkpoint)."""
+    dp = tp = pp = -1
+    for f in os.listdir(_optim_dir(args)):
+        if not f.endswith(".pt"):
+            continue
+        nums = [int(n) for n in re.findall(r"\d+", f)]
+        if f.startswith("full") and len(nums) >= 2:
+            tp, pp = max(tp, nums[0]), max(pp, nums[1])
+        elif len(nums) >= 3:
+            dp, tp, pp = max(dp, nums[0]), max(tp, nums[1]), max(pp, nums[2])
+    return dp + 1, tp + 1, pp + 1
+
+
+def _load_any(path: str) -> Dict[str, Any]:
+    """Plain ``torch.save`` file or an out-of-line (xser) one."""
+    if os.path.isdir(path + ".tensors"):
+        from ..trainer.checkpoint import _xser_load
+        from ..trainer.checkpoint_storage import FilesysCheckpointStorage
+
+        d, f = os.path.split(path)
+        return _xser_load(FilesysCheckpointStorage(d), f, None, 1, 0)
+    return _load(path)
+
+
+def merge_optim_dp_checkpoints(args, tp_rank: int, pp_rank: int) -> Dict[str, Any]:
+    files = _dp_files(_optim_dir(args), tp_rank, pp_rank)
+    if not files:
+        raise FileNotFoundError(f"no optimizer shards for tp={tp_rank} pp={pp_rank} under {_optim_dir(args)}")
+    return merge_shards([_load_any(f) for f in files])
+
+
+def split_and_save_ckpts(args, merged_ckpt: Dict[str, Any], tp_rank: int, pp_rank: int) -> None:
+    out = os.path.join(args.output_dir, "optim") if getattr(args, "nested_output", False) else args.output_dir
+    os.makedirs(out, exist_ok=True)
+    for r, sd in enumerate(reshard(merged_ckpt, args.new_dp_size)):
+        torch.save(sd, os.path.join(out, f"dp_rank_{r:02d}_tp_rank_{tp_rank:02d}_pp_rank_{pp_rank:02d}.pt"))
+
+
+def _save_full(args, full: Dict[str, Any], tp: int, pp: int) -> None:
+    out = os.path.join(args.output_dir, "optim") if getattr(args, "nested_output", False) else args.output_dir
+    os.makedirs(out, exist_ok=True)
+    torch.save({"full": full, "named": full_to_named(full)}, os.path.join(out, f"full_tp_rank_{tp:02d}_pp_rank_{pp:02d}.pt"))
+
+
+def _sharded_to_full_task(args, tp_rank: int, pp_rank: int) -> None:
+    _save_full(args, merge_optim_dp_checkpoints(args, tp_rank, pp_rank), tp_rank, pp_rank)
+
+
+def _full_to_sharded_task(args, tp_rank: int, pp_rank: int) -> None:
+    full = _load(os.path.join(_optim_dir(args), f"full_tp_rank_{tp_rank:02d}_pp_rank_{pp_rank:02d}.pt"))["full"]
+    split_and_save_ckpts(args, full, tp_rank, pp_rank)
+
+
+def _sharded_to_sharded_task(args, tp_rank: int, pp_rank: int) -> None:
+    split_and_save_ckpts(args, merge_optim_dp_checkpoints(args, tp_rank, pp_rank), tp_rank, pp_rank)
+
+
 def main(argv=None) -> int:
-    ap = argparse.ArgumentParser(description="Convert ZeRO-1 optimizer checkpoints: sharded → full / re-sharded")
-    ap.add_argument("--input_dir", required=True, help="<ckpt>/<tag>/optim")
+    ap = argparse.ArgumentParser(description="Convert ZeRO-1 optimizer checkpoints: sharded ↔ full, or re-shard for a new dp size")
+    ap.add_argument("--input_dir", required=True, help="checkpoint tag directory (containing optim/) or the optim directory itself")
     ap.add_argument("--output_dir", required=True)
+    ap.add_argument("--num_workers", type=int, default=1, help="(tp, pp) coordinates converted concurrently")
+    ap.add_argument("--dp_size", type=int, default=None, help="target data-parallel size when converting to sharded")
+    ap.add_argument("--tp_size", type=int, default=None, help="override the tp size inferred from the file names")
+    ap.add_argument("--pp_size", type=int, default=None, help="override the pp size inferred from the file names")
     ap.add_argument("--convert_to_full", action="store_true")
     ap.add_argument("--convert_to_sharded", action="store_true")
-    ap.add_argument("--dp_size", type=int, default=None, help="target data-parallel size when re-sharding")
-    ap.add_argument("--tp_size", type=int, default=1)
-    ap.add_argument("--pp_size", type=int, default=1)
-    a = ap.parse_args(argv)
-    os.makedirs(a.output_dir, exist_ok=True)
-    for pp in range(a.pp_size):
-        for tp in range(a.tp_size):
-            files = _dp_files(a.input_dir, tp, pp)
-            if not files:
-                raise FileNotFoundError(f"no optimizer shards for tp={tp} pp={pp} under {a.input_dir}")
-            full = merge_shards([_load(f) for f in files])
-            if a.convert_to_full:
-                torch.save({"full": full, "named": full_to_named(full)},
-                           os.path.join(a.output_dir, f"full_tp_rank_{tp:02d}_pp_rank_{pp:02d}.pt"))
-            if a.convert_to_sharded:
-                assert a.dp_size, "--dp_size is required with --convert_to_sharded"
-                for r, sd in enumerate(reshard(full, a.dp_size)):
-                    torch.save(sd, os.path.join(a.output_dir, f"dp_rank_{r:02d}_tp_rank_{tp:02d}_pp_rank_{pp:02d}.pt"))
+    a, _ = ap.parse_known_args(argv)
+    if not (a.convert_to_full or a.convert_to_sharded):
+        ap.error("one of --convert_to_full / --convert_to_sharded is required")
+    a.nested_output = os.path.isdir(os.path.join(a.input_dir, "optim"))       # mirror the input's directory convention
+    a.is_xser, a.new_dp_size = is_xser(a), a.dp_size
+    dp, tp, pp = get_parallel_info(a)
+    a.dp_size, a.tp_size, a.pp_size = dp, a.tp_size or tp, a.pp_size or pp
+    tasks = []
+    if a.convert_to_full:
+        if is_full(a):
+            raise ValueError("Invalid inputs: convert full optim states to full optim states")
+        tasks.append(_sharded_to_full_task)
+    if a.convert_to_sharded:
+        assert a.new_dp_size, "--dp_size is required with --convert_to_sharded"
+        tasks.append(_full_to_sharded_task if is_full(a) else _sharded_to_sharded_task)
+    coords = [(t, p) for p in range(a.pp_size) for t in range(a.tp_size)]
+    for task in tasks:
+        if a.num_workers > 1:
+            import concurrent.futures
+
+            with concurrent.futures.ThreadPoolExecutor(max_workers=a.num_workers) as ex:
+                for f in [ex.submit(task, a, t, p) for t, p in coords]:
+                    f.result()
+        else:
+            for t, p in coords:
+                task(a, t, p)
     return 0
 
 

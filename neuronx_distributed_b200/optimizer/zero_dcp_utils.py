@@ -62,3 +62,18 @@ def load_optim_state_dict(path: str, inner) -> Dict[str, Any]:
         base_state[g] = st
     return {"state": base_state, "base_state": base_state, "param_groups": layout["param_groups"],
             "shape_info": layout["shape_info"], "sharded_master_weights": smw}
+
+
+def get_dcp_aux_infos(model: torch.nn.Module, optim) -> Dict[str, Any]:
+    """Side information a DCP save/load of the optimizer needs (reference ``zero_dcp_utils.py:372-380``): which parameter
+    object / parameter NAME every optimizer param id stands for, and the flat-shard ``shape_info`` of the ZeRO-1 state."""
+    inner = getattr(optim, "optimizer", optim)
+    names = {id(p): n for n, p in model.named_parameters()}
+    pid_to_params, pid_to_names, pid = {}, {}, 0
+    for group in inner.param_groups:
+        for p in group["params"]:
+            pid_to_params[pid] = p
+            pid_to_names[pid] = names.get(id(p))
+            pid += 1
+    sd = inner.state_dict() if hasattr(inner, "state_dict") else {}
+    return {"optim_pid_to_params": pid_to_params, "optim_pid_to_pnames": pid_to_names, "shape_info": sd.get("shape_info")}

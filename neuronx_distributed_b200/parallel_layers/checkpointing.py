@@ -102,3 +102,10 @@ def load(chkpt_path: str, model: Optional[nn.Module] = None, model_or_optimizer:
             target.load_state_dict(sd)
     _barrier()
     return ckpt
+
+
+def ensure_directory_exists(filename: str) -> None:
+    """Create the parent directory of ``filename`` (reference checkpointing.py:26-29)."""
+    d = os.path.dirname(filename)
+    if d:
+        os.makedirs(d, exist_ok=True)

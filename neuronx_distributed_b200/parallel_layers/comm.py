@@ -11,7 +11,7 @@ GEMM+collective kernels in ``ops/tp_fused.py``.
 """
 from __future__ import annotations
 
-from typing import Sequence, Union
+from typing import Optional, Sequence, Union
 
 import torch
 import torch.distributed as dist
@@ -174,3 +174,33 @@ def send(x: torch.Tensor, dst: int, group=None):
 
 def recv(x: torch.Tensor, src: int, group=None):
     return dist.recv(x, src=src, group=group)
+
+
+def gloo_reduce_scatter(output: torch.Tensor, input: torch.Tensor, op="sum", group=None, async_op: bool = False):  # noqa: A002
+    """gloo has no reduce-scatter: reduce to the group's first rank, then scatter equal chunks of dim 0 into ``output``
+    (reference comm.py:82-130).  ``reduce_scatter`` above uses all-reduce + slice instead (one collective, no root
+    hot-spot); this form is kept for callers that need the out-parameter signature."""
+    group = _tp(group)
+    n = dist.get_world_size(group)
+    ranks = dist.get_process_group_ranks(group)
+    red = _REDUCE_OPS[op] if isinstance(op, str) else op
+    buf = input.contiguous().clone()
+    dist.reduce(buf, dst=ranks[0], op=red, group=group)
+    chunks = [c.contiguous() for c in buf.chunk(n, dim=0)] if dist.get_rank() == ranks[0] else None
+    dist.scatter(output, chunks, src=ranks[0], group=group)
+    return output
+
+
+def cpu_reduce_scatter(reduce_type: str, input: torch.Tensor, scale: float = 1, scatter_dim: int = 0, shard_count=None,  # noqa: A002
+                       groups=None, output: Optional[torch.Tensor] = None, pin_layout: bool = True) -> torch.Tensor:
+    """``xm.reduce_scatter`` signature on CPU tensors (reference comm.py:32-79)."""
+    group = _tp(groups)
+    n = dist.get_world_size(group)
+    assert shard_count is None or shard_count == n, f"shard_count {shard_count} must equal the group size {n}"
+    res = reduce_scatter(input, scatter_dim, group, reduce_type if reduce_type in _REDUCE_OPS else "sum")
+    if scale != 1:
+        res = res * scale
+    if output is not None:
+        output.copy_(res)
+        return output
+    return res

@@ -226,3 +226,17 @@ def round_robin_scatter_to_process_group_spmd(
     size = x.shape[partition_dim] // n
     idx = rank.reshape(-1)[:1].to(torch.long) + torch.arange(size, device=x.device) * n
     return torch.index_select(x, partition_dim, idx)
+
+
+def nonzero_partition_dim_swap(func):
+    """Decorator for ``f(x, partition_dim, …)`` collectives that are written for dim 0 only: transpose the partition dim to
+    the front, call with dim 0, transpose back (reference mappings.py:27-40)."""
+    import functools
+
+    @functools.wraps(func)
+    def wrapped(x, partition_dim: int, *args, **kwargs):
+        if partition_dim % x.dim() == 0:
+            return func(x, 0, *args, **kwargs)
+        return func(x.transpose(0, partition_dim), 0, *args, **kwargs).transpose(0, partition_dim)
+
+    return wrapped

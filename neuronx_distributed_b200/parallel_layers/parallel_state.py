@@ -20,6 +20,7 @@ Design (B200-first, not a port):
 """
 from __future__ import annotations
 
+import enum
 import os
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
@@ -151,9 +152,26 @@ def ascending_ring_PG_group(lnc_size: int = 1, cluster_ranks_nonexp=None, cluste
 ascending_descending_ring_PG_group = ascending_ring_PG_group
 
 
+class PG_Group_Logic(enum.Enum):  # noqa: N801  (reference spelling, :326-335)
+    """Callable enum of rank-placement policies; both members resolve to the NVSwitch placement."""
+
+    LOGIC1 = ("ascending", "Ascending Ring PG Group")
+    LOGIC2 = ("ascending_descending", "Ascending Descending Ring PG Group")
+
+    def __init__(self, ident: str, description: str):
+        self.ident, self.description = ident, description
+
+    @property
+    def func(self):
+        return ascending_ring_PG_group
+
+    def __call__(self, *args, **kwargs):
+        return ascending_ring_PG_group(*args, **kwargs)
+
+
 def get_logic_chosen(lnc_size: int = 1, hardware_type: Any = None, tp: int = 1):
     """Reference parallel_state.py:341-357 picks a placement by hardware generation; B200 has one."""
-    return ascending_ring_PG_group
+    return PG_Group_Logic.LOGIC1
 
 
 def arrange_kv_groups(

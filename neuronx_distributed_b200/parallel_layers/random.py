@@ -86,6 +86,7 @@ def get_rng_tracker() -> RNGStatesTracker:
 
 # reference name kept as an alias so user code ports unchanged
 get_xla_rng_tracker = get_rng_tracker
+XLARNGStatesTracker = RNGStatesTracker       # reference class name (random.py:20); the states here are CUDA / CPU generator states
 
 
 def model_parallel_manual_seed(seed: int) -> None:

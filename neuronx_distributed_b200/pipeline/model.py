@@ -14,6 +14,7 @@ B200 design (differs from the XLA engine):
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Any, Callable, Dict, List, Optional, Tuple, Type
 
 import torch
@@ -51,6 +52,16 @@ class _Stage:
 
     def __init__(self, index: int, module: nn.Module, io: part.StageIO):
         self.index, self.module, self.io = index, module, io
+
+
+@contextlib.contextmanager
+def mark_timeline(timeline, msg: str):
+    """``with mark_timeline(tl, "fwd mb3"): …`` brackets an event (reference pipeline/model.py:61-67)."""
+    timeline.mark_event_start(msg)
+    try:
+        yield
+    finally:
+        timeline.mark_event_end(msg)
 
 
 class NxDPPModel(nn.Module):

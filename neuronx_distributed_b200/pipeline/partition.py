@@ -167,3 +167,40 @@ def analyze_shared_weights_across_stages(split: fx.GraphModule, stage_modules: L
             if not any(st == s for st, _ in seen[id(p)]):
                 seen[id(p)].append((s, name))
     return [v for v in seen.values() if len(v) > 1]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# IO annotation helpers with the reference's names (pipeline/partition.py:46-130)
+# ---------------------------------------------------------------------------------------------------------------------
+class PipelineIO:
+    """Annotation of one value crossing a stage boundary: FX node ``name``; ``input_idx`` / ``output_idx`` = its position
+    among the stage's inputs / outputs (``None`` = not used that way, i.e. passed along); ``metadata`` = tensor metas when it
+    carries tensors; ``obj`` = the python object when it is not a tensor."""
+
+    def __init__(self, name: str, input_idx: Optional[int] = None, output_idx: Optional[int] = None, metadata=None, obj=None):
+        self.name, self.input_idx, self.output_idx, self.metadata, self.obj = name, input_idx, output_idx, metadata, obj
+
+    def __repr__(self) -> str:
+        return f"PipelineIO_{self.name}_input_idx_{self.input_idx}_output_idx_{self.output_idx}_metadata_{self.metadata}"
+
+
+def adding_live_obj_for_previous_stages(stage_id_to_IO_input_names, stage_id_to_IO_output_names, obj_name: str,  # noqa: N803
+                                        current_stage: int) -> None:
+    """``obj_name`` is needed after ``current_stage`` but produced earlier: walk back to the producing stage and mark the
+    value as an input AND output (pass-along) of every stage in between, so it is forwarded hop by hop."""
+    if current_stage < 0:
+        raise RuntimeError(f"{obj_name} is missing from all previous stages, stage_id_to_IO_output_names {stage_id_to_IO_output_names}")
+    ins, outs = stage_id_to_IO_input_names[current_stage], stage_id_to_IO_output_names[current_stage]
+    if obj_name not in ins and obj_name not in outs:
+        adding_live_obj_for_previous_stages(stage_id_to_IO_input_names, stage_id_to_IO_output_names, obj_name, current_stage - 1)
+        ins[obj_name] = PipelineIO(obj_name)
+        outs[obj_name] = PipelineIO(obj_name)
+    elif obj_name not in outs:                       # consumed here and needed later: forward it as well
+        outs[obj_name] = PipelineIO(obj_name)
+
+
+def iterate_graph_model_outputs(output_node_args):
+    """Yield the values of an FX output node's ``args`` (always a 1-tuple holding either one node or a tuple of them)."""
+    assert isinstance(output_node_args, tuple) and len(output_node_args) == 1, f"Unsupported output args found {output_node_args}"
+    first = output_node_args[0]
+    yield from (first if isinstance(first, (tuple, list)) else output_node_args)

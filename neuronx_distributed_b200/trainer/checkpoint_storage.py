@@ -148,6 +148,26 @@ class FilesysCheckpointStorage(BaseCheckpointStorage):
             return 0.0
 
 
+def is_slow_down_error(exception: BaseException) -> bool:
+    """S3 asks clients to back off with these error codes (reference :250-268); anything else is a real failure."""
+    msg = str(exception)
+    return any(f"<Code>{c}</Code>" in msg or c in msg for c in ("SlowDown", "RequestTimeout", "InternalError", "Throttling"))
+
+
+class wait_decrementing_with_jitter:  # noqa: N801  (reference spelling, :236-241)
+    """Back-off policy: sleep a random 1…⌈max_sleep / attempt⌉ seconds — the window SHRINKS with every attempt because by
+    then the thundering herd of ranks has already been spread out by the first, widest draw."""
+
+    def __init__(self, max_sleep: float) -> None:
+        self.max_sleep = max_sleep
+
+    def __call__(self, retry_state) -> float:
+        import math
+
+        attempt = getattr(retry_state, "attempt_number", retry_state)
+        return float(random.randint(1, max(1, math.ceil(self.max_sleep / max(1, int(attempt))))))
+
+
 class S3CheckpointStorage(BaseCheckpointStorage):
     """``s3://bucket/prefix`` storage (reference :236-605).  Requires boto3."""
 
@@ -168,16 +188,14 @@ class S3CheckpointStorage(BaseCheckpointStorage):
         return os.path.normpath(os.path.join(self.prefix, name)).lstrip("./")
 
     def _retry(self, fn: Callable, *a, **k):  # pragma: no cover - needs network
-        world = int(os.environ.get("WORLD_SIZE", "1"))
-        for attempt in range(self.MAX_RETRY):
+        wait = wait_decrementing_with_jitter(max_sleep=int(os.environ.get("WORLD_SIZE", "50000")) / 10000)
+        for attempt in range(1, self.MAX_RETRY + 1):
             try:
                 return fn(*a, **k)
             except Exception as e:  # noqa: BLE001
-                msg = str(e)
-                if not any(t in msg for t in ("SlowDown", "Timeout", "RequestTimeout", "Throttl")) or attempt == self.MAX_RETRY - 1:
+                if not is_slow_down_error(e) or attempt == self.MAX_RETRY:
                     raise
-                # jitter window shrinks with every attempt; scaled by job size so ranks spread out
-                time.sleep(random.uniform(0, max(1.0, world / 64.0) * (self.MAX_RETRY - attempt)))
+                time.sleep(wait(attempt))
 
     def dir_exists(self, dirname: str) -> bool:  # pragma: no cover
         r = self._retry(self.s3.list_objects_v2, Bucket=self.bucket, Prefix=self._key(dirname).rstrip("/") + "/", MaxKeys=1)

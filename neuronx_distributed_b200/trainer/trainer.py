@@ -199,3 +199,18 @@ def initialize_optimizer_from_class(nxd_config: dict, optimizer_class, parameter
 def initialize_parallel_optimizer(nxd_config: dict, optimizer_class, parameters, **defaults) -> NxDOptimizer:
     params = list(parameters)
     return NxDOptimizer(initialize_optimizer_from_class(nxd_config, optimizer_class, params, **defaults), nxd_config)
+
+
+def filter_to_local_parameter_group(optimizer, model) -> None:
+    """Pipeline-parallel models own only their stage's parameters: rewrite ``optimizer.param_groups`` in place so each group
+    keeps just the parameters that are materialised on this rank (reference trainer.py:325-335).  Works with the mapping a
+    partitioned model exposes (``meta_device_parameter_map``: original → local parameter) and, without one, by dropping
+    parameters that are still on the meta device."""
+    mapping = getattr(model, "meta_device_parameter_map", None)
+    for group in optimizer.param_groups:
+        kept = []
+        for p in group["params"]:
+            q = mapping.get(p, None) if mapping is not None else p
+            if q is not None and q.device.type != "meta":
+                kept.append(q)
+        group["params"] = kept

@@ -70,3 +70,21 @@ def test_convert_zero_checkpoints(tmp_path):
     cat = torch.cat([p["sharded_master_weights"][0] for p in parts])
     orig = full["full"]["master"][0]
     torch.testing.assert_close(cat[: orig.numel()], orig)
+    # reference CLI conventions: tag directory as input (optim/ inside), sizes inferred from file names, full → sharded
+    from types import SimpleNamespace
+
+    from neuronx_distributed_b200.optimizer.convert_zero_checkpoints import (get_parallel_info, is_full, is_xser,
+                                                                             merge_optim_dp_checkpoints)
+    tag = SimpleNamespace(input_dir=str(tmp_path / "s1"))
+    assert get_parallel_info(tag) == (2, 1, 1) and not is_full(tag) and not is_xser(tag)
+    merged = merge_optim_dp_checkpoints(tag, 0, 0)
+    torch.testing.assert_close(merged["master"][0], orig)
+    main(["--input_dir", str(tmp_path / "s1"), "--output_dir", str(tmp_path / "full2"), "--convert_to_full", "--num_workers", "2"])
+    assert is_full(SimpleNamespace(input_dir=str(tmp_path / "full2")))
+    assert get_parallel_info(SimpleNamespace(input_dir=str(tmp_path / "full2"))) == (0, 1, 1)
+    main(["--input_dir", str(tmp_path / "full2"), "--output_dir", str(tmp_path / "re2"), "--convert_to_sharded", "--dp_size", "2"])
+    back = [torch.load(tmp_path / "re2" / "optim" / f"dp_rank_{r:02d}_tp_rank_00_pp_rank_00.pt", weights_only=False) for r in range(2)]
+    torch.testing.assert_close(torch.cat([p["sharded_master_weights"][0] for p in back])[: orig.numel()], orig)
+    import pytest
+    with pytest.raises(ValueError):
+        main(["--input_dir", str(tmp_path / "full2"), "--output_dir", str(tmp_path / "x"), "--convert_to_full"])
