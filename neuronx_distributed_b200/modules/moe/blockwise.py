@@ -277,3 +277,54 @@ class TorchBlockwiseTraining(torch.autograd.Function):
             gw1[e] += xt.t() @ ggu
             gx.index_add_(0, t, ggu @ w1[e].float().t())
         return gx.to(x.dtype), gaff.to(aff.dtype), None, None, gw1.to(w1.dtype), gw2.to(w2.dtype)
+
+
+def _dyn_slice(tensor: torch.Tensor, starts, sizes) -> torch.Tensor:
+    """Slice with start offsets that may be 0-d device tensors WITHOUT reading them on the host (CUDA-graph safe): gather
+    along each dim with ``start + arange(size)``; python ints take the free ``narrow`` path."""
+    out = tensor
+    for d, (st, sz) in enumerate(zip(starts, sizes)):
+        if isinstance(st, torch.Tensor):
+            out = out.index_select(d, st.reshape(()).to(torch.long) + torch.arange(sz, device=out.device))
+        else:
+            out = out.narrow(d, int(st), sz)
+    return out
+
+
+def dynamic_slice_3D(tensor, start0, start1, start2, size0, size1, size2):  # noqa: N802
+    return _dyn_slice(tensor, (start0, start1, start2), (size0, size1, size2))
+
+
+def dynamic_slice_2D(tensor, start0, start1, size0, size1):  # noqa: N802
+    return _dyn_slice(tensor, (start0, start1), (size0, size1))
+
+
+def dynamic_slice_1D(tensor, start0, size0):  # noqa: N802
+    return _dyn_slice(tensor, (start0,), (size0,))
+
+
+def get_data(tensor, transform=None):
+    """``tensor.data`` (optionally transformed), ``None`` passing through."""
+    if tensor is None:
+        return None
+    return transform(tensor.data) if transform else tensor.data
+
+
+class BlockwiseMatmulMXNKIFunc:
+    """Blockwise MLP on MXFP4 expert weights (reference :1037-1127).  ``gate_up_proj_weight`` / ``down_proj_weight`` are
+    K-major x4-packed ``[E, N, K/4]`` (uint16) with E8M0 ``*_scale`` ``[E, N, K/32]`` — the layout of
+    ``moe_fused_tkg_mx.pack_expert_weight_mxfp4``.  Inference only: the weights are expanded to bf16 ``[E, K, N]`` once per
+    call and fed to the grouped GEMM (a block-scaled grouped UMMA would consume them packed)."""
+
+    @staticmethod
+    def apply(hidden_states, expert_affinities_masked, gate_up_proj_weight, down_proj_weight, token_position_to_id,
+              block_to_expert, gate_up_proj_scale=None, down_proj_scale=None, block_size: int = 512, **kw):
+        from .moe_fused_tkg_mx import _dequant
+
+        dt = hidden_states.dtype if hidden_states.dtype in (torch.bfloat16, torch.float16, torch.float32) else torch.bfloat16
+        w1 = _dequant(gate_up_proj_weight, gate_up_proj_scale).transpose(1, 2).to(dt).contiguous()
+        w2 = _dequant(down_proj_weight, down_proj_scale).transpose(1, 2).to(dt).contiguous()
+        known = {k: v for k, v in kw.items() if k in BlockwiseMatmulArgs.__dataclass_fields__}
+        with torch.no_grad():
+            return blockwise_matmul(BlockwiseMatmulArgs(hidden_states, expert_affinities_masked, w1, w2, token_position_to_id,
+                                                        block_to_expert, block_size, **known))

@@ -661,3 +661,156 @@ class NxDPPModel(nn.Module):
 
     def get_model_layers(self) -> List[str]:
         return self._layer_names()
+
+    # =================================================================== reference-named entry points
+    # (reference pipeline/model.py: trace :353, partition :383, cut_pipeline_stage :718, register_shared_weights :486, …)
+    def trace(self, args=None, kwargs=None, input_names: Optional[List[str]] = None, leaf_modules: Optional[List[Any]] = None,
+              autowrap_functions=None, autowrap_modules=None, autowrap_obj_methods=None, tracer_cls=None) -> None:
+        """Record the tracing options; the FX trace itself runs together with the cut in :meth:`partition` (the graph is
+        only ever needed to be split)."""
+        assert not self.partitioned, "the model is already partitioned"
+        if input_names is None and (args is not None or kwargs is not None):
+            import inspect
+
+            sig = list(inspect.signature(self.original_torch_module.forward).parameters)
+            input_names = sig[: len(args or [])] + list((kwargs or {}).keys())
+        if input_names is not None:
+            self.input_names = list(input_names)
+        if leaf_modules:
+            self.leaf_module_cls = list(self.leaf_module_cls) + [m for m in leaf_modules if isinstance(m, type)]
+        self.autowrap_functions = tuple(autowrap_functions or self.autowrap_functions)
+        self.autowrap_modules = tuple(autowrap_modules or self.autowrap_modules)
+        self.tracer_cls = tracer_cls or self.tracer_cls
+        self._traced_requested = True
+
+    def cut_pipeline_stage(self, cut_point: str) -> None:
+        """Add a cut AFTER the module named ``cut_point`` (must be called before :meth:`partition`)."""
+        assert not self.partitioned, "cut_pipeline_stage must be called before the model is partitioned"
+        names = {n for n, _ in self.original_torch_module.named_modules()}
+        assert cut_point in names, f"{cut_point} is not a module of the model"
+        if cut_point not in self.pipeline_cuts:
+            self.pipeline_cuts.append(cut_point)
+
+    def partition(self) -> None:
+        """Trace + split at the registered cuts and keep this rank's stage(s)."""
+        if self.partitioned:
+            return
+        if self.manual_pp_partition:
+            return self._manual_partition()
+        order = {n: i for i, (n, _) in enumerate(self.original_torch_module.named_modules())}
+        self.pipeline_cuts.sort(key=lambda c: order.get(c, 0))
+        self.trace_and_partition()
+
+    def perform_delayed_tracing_and_partition(self, *args, **kwargs) -> None:
+        """Delayed tracing (trace on the first batch) is never needed here — FX tracing does not depend on tensor shapes —
+        so this just partitions if the constructor did not."""
+        self.partition()
+
+    def maybe_materialize_local_module(self) -> None:
+        """Give storage to this rank's stage(s) if the model was built on the meta device (and only to them)."""
+        self.move_model_to_device()
+
+    def register_shared_weights(self, weight_pairs: Optional[List[Any]] = None) -> None:
+        """Tied weights are discovered from parameter identity during partitioning (``analyze_shared_weights_across_stages``);
+        extra groups can be declared as lists of original parameter names, e.g. ``[["embed.weight", "lm_head.weight"]]``."""
+        for names in weight_pairs or []:
+            mine = [self.original_name_to_local_name[n] for n in names if n in self.original_name_to_local_name]
+            params = dict(self.local_stage_modules.named_parameters(prefix="local_stage_modules", remove_duplicate=False))
+            p = params[mine[0]] if mine else None
+            stages = sorted({st.index for st in self.stages} if mine else set())
+            self.shared_weight_groups.append({"stages": stages, "pp_ranks": list(range(self.pp_size)), "param": p, "pg": None,
+                                              "names": list(names)})
+        if weight_pairs and not self._debug_mode:
+            self._create_shared_weight_groups()
+
+    def create_schedule(self, train: bool = True):
+        return self._make_schedule(train)
+
+    def clear_minibatch_state(self) -> None:
+        """Drop every per-step buffer (activations kept for backward, received gradients, pending handles, losses)."""
+        for name in ("_act", "_out", "_inp_leaves", "_grad_in"):
+            getattr(self, name, {}).clear()
+        for name in ("_pending", "_pending_sends", "_losses"):
+            lst = getattr(self, name, None)
+            if lst is not None:
+                lst.clear()
+        self._mbs = []
+
+    def get_current_stage(self, model_chunk_id: int = 0) -> int:
+        """Global stage index of local chunk ``model_chunk_id`` (``chunk · pp_size + pp_rank``)."""
+        return self.stages[model_chunk_id].index if self.stages else model_chunk_id * self.pp_size + self.pp_rank
+
+    def is_last_stage(self, model_chunk_id: Optional[int] = None) -> bool:
+        chunk = len(self.stages) - 1 if model_chunk_id is None else model_chunk_id
+        return self.get_current_stage(chunk) == self.num_stages - 1
+
+    def is_last_pp_rank_last_model_chunk(self, model_chunk_id: int) -> bool:
+        return self.pp_rank == self.pp_size - 1 and model_chunk_id == self.virtual_pipeline_size - 1
+
+    def get_batch_iterator(self, batch: Dict[str, Any]):
+        """Iterator over the micro-batches of ``batch`` (dim 0 split into ``num_microbatches`` equal parts)."""
+        return iter(self._split_microbatches(batch))
+
+    @staticmethod
+    def custom_backward(output: torch.Tensor, grad_output: Optional[torch.Tensor]) -> None:
+        """Backward through ``output`` even after its storage was released by :meth:`maybe_deallocate_output_tensor` — the
+        autograd engine only needs the graph, not the values (reference :890-925, after Megatron-LM)."""
+        assert output.numel() == 1 or grad_output is not None or output.numel() > 0
+        if grad_output is None:
+            assert output.numel() == 1, "implicit grad requires scalar output."
+            grad_output = torch.ones_like(output, memory_format=torch.preserve_format)
+        torch.autograd.backward((output,), (grad_output,))
+
+    def maybe_deallocate_output_tensor(self, model_chunk_id: int = 0) -> None:
+        """After a stage's outputs were sent downstream, free their storage (only the autograd graph is needed for the
+        backward of this stage): enabled by ``deallocate_pipeline_outputs``."""
+        if not self.deallocate_pipeline_outputs:
+            return
+        for (mb, chunk), outs in list(getattr(self, "_out", {}).items()):
+            if chunk != model_chunk_id:
+                continue
+            for t in outs.values():
+                if isinstance(t, torch.Tensor) and t._base is None and t.requires_grad:
+                    t.data = torch.empty((1,), device=t.device, dtype=t.dtype)
+
+    # ---- full-module style accessors (a pipeline rank sees its local stage modules) ----------------------------------
+    def named_buffers(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
+        return self.local_named_buffers(prefix, recurse)
+
+    def buffers(self, recurse: bool = True):
+        for _, b in self.local_named_buffers(recurse=recurse):
+            yield b
+
+    def local_buffers(self, recurse: bool = True):
+        return self.buffers(recurse)
+
+    def local_named_children(self):
+        return self.local_stage_modules.named_children()
+
+    def translate_origin_state_dict_to_local_state_dict(self, origin_state_dict: Dict[str, Any]) -> Dict[str, Any]:
+        """Keys of the un-partitioned model → keys of ``local_stage_modules`` (entries of other stages are dropped)."""
+        out = {}
+        for k, v in origin_state_dict.items():
+            lk = self.original_name_to_local_name.get(k)
+            if lk is None:
+                lk = next((loc for loc, orig in self.local_name_to_original_name.items() if orig == k), None)
+            if lk is not None:
+                out[lk] = v
+        return out
+
+    def translate_local_state_dict_to_origin_state_dict(self, local_state_dict: Dict[str, Any]) -> Dict[str, Any]:
+        return {self.local_name_to_original_name.get(k, k): v for k, v in local_state_dict.items()}
+
+    def construct_state_dict_per_model_chunk(self, state_dict: Dict[str, Any], strict: bool = True) -> List[Dict[str, Any]]:
+        """Split an original-key state dict into one dict per local model chunk (keys relative to the chunk's module)."""
+        per_chunk: List[Dict[str, Any]] = [dict() for _ in self.stages]
+        local = self.translate_origin_state_dict_to_local_state_dict(state_dict)
+        for k, v in local.items():
+            _, chunk, rest = k.split(".", 2)
+            per_chunk[int(chunk)][rest] = v
+        if strict:
+            for i, st in enumerate(self.stages):
+                missing = set(st.module.state_dict().keys()) - set(per_chunk[i])
+                if missing:
+                    raise RuntimeError(f"missing keys for model chunk {i}: {sorted(missing)[:5]}…")
+        return per_chunk

@@ -143,6 +143,34 @@ def _pp_worker(rank, world, pp, vpp, tie, out_path):
     assert all(k in dict(ref.state_dict()) for k in sd)
     ev = ppm.run_eval(input_ids=ids, labels=ids)
     assert ev is not None
+    # reference-named accessors / translators
+    assert ppm.get_current_stage(0) == rank and ppm.is_last_stage() == (rank == pp - 1 and True)
+    assert ppm.is_last_pp_rank_last_model_chunk(vpp - 1) == (rank == pp - 1)
+    assert len(list(ppm.get_batch_iterator({"input_ids": ids, "labels": ids}))) == 4
+    assert type(ppm.create_schedule(train=True)).__name__.startswith("Train")
+    local_sd = ppm.local_stage_modules.state_dict(prefix="local_stage_modules.")
+    origin = ppm.translate_local_state_dict_to_origin_state_dict(local_sd)
+    assert set(origin) == set(sd)
+    back = ppm.translate_origin_state_dict_to_local_state_dict({**ref.state_dict()})
+    assert set(back) == set(local_sd)
+    chunks = ppm.construct_state_dict_per_model_chunk(ref.state_dict(), strict=True)
+    assert len(chunks) == vpp and all(set(c) == set(st.module.state_dict()) for c, st in zip(chunks, ppm.stages))
+    assert list(ppm.buffers()) == list(ppm.local_buffers()) and [n for n, _ in ppm.local_named_children()] == [str(i) for i in range(vpp)]
+    ppm.clear_minibatch_state()
+    assert not ppm._act and not ppm._losses
+    t = torch.ones(3, requires_grad=True)
+    out = (t * 2).sum()
+    NxDPPModel.custom_backward(out, None)
+    assert t.grad.tolist() == [2, 2, 2]
+    # two-step construction: declare cuts, then partition (no transformer_layer_cls)
+    torch.manual_seed(0)
+    m2 = NxDPPModel(Toy(tie=tie), num_microbatches=4, output_loss_value_spec=True, broadcast_and_average_loss=True)
+    assert not m2.partitioned
+    m2.trace(kwargs={"input_ids": ids, "labels": ids}, leaf_modules=[Block])
+    if pp == 2 and vpp == 1:
+        m2.cut_pipeline_stage("layers.1")
+        m2.partition()
+        torch.testing.assert_close(m2.run_train(input_ids=ids, labels=ids).float(), ref_loss.detach().float(), rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize("pp,vpp,tie", [(2, 1, False), (2, 2, False), (2, 1, True)])
