@@ -470,6 +470,43 @@ class Zero1Optimizer(torch.optim.Optimizer):
     def add_param_group(self, param_group: Dict[str, Any]) -> None:
         super().add_param_group(param_group)
 
+    # ---- per-rank shard files (reference :107-160; superseded by ``nxd.save_checkpoint`` there and here) ----------------
+    @staticmethod
+    def _shard_path(output_dir: str) -> str:
+        return os.path.join(output_dir, "optim.dp_rank_{:02d}.tp_rank_{:02d}".format(ps.get_data_parallel_rank(),
+                                                                                      ps.get_tensor_model_parallel_rank()))
+
+    def save_sharded_state_dict(self, output_dir: str, num_workers_per_step: int = 8) -> None:
+        """Write this rank's optimizer shard to ``<output_dir>/optim.dp_rank_XX.tp_rank_YY``.  At most
+        ``num_workers_per_step`` local ranks write at the same time (bounds host memory / file-system pressure)."""
+        from ..parallel_layers.utils import get_local_world_size, move_all_tensor_to_cpu
+
+        os.makedirs(output_dir, exist_ok=True)
+        sd = self.state_dict()
+        sd["dp_rank"], sd["tp_rank"] = ps.get_data_parallel_rank(), ps.get_tensor_model_parallel_rank()
+        local_rank = int(os.environ.get("LOCAL_RANK", dist.get_rank() if dist.is_initialized() else 0))
+        waves = max(1, -(-get_local_world_size() // max(1, num_workers_per_step)))
+        for wave in range(waves):
+            if local_rank // max(1, num_workers_per_step) == wave:
+                torch.save(move_all_tensor_to_cpu(sd), self._shard_path(output_dir))
+            if dist.is_initialized() and waves > 1:
+                dist.barrier()
+        if dist.is_initialized():
+            dist.barrier()
+
+    def load_sharded_state_dict(self, output_dir: str, num_workers_per_step: int = 8) -> None:
+        from ..parallel_layers.utils import get_local_world_size
+
+        local_rank = int(os.environ.get("LOCAL_RANK", dist.get_rank() if dist.is_initialized() else 0))
+        waves = max(1, -(-get_local_world_size() // max(1, num_workers_per_step)))
+        for wave in range(waves):
+            if local_rank // max(1, num_workers_per_step) == wave:
+                sd = torch.load(self._shard_path(output_dir), map_location="cpu", weights_only=False)
+                sd.pop("dp_rank", None), sd.pop("tp_rank", None)
+                self.load_state_dict(sd)
+            if dist.is_initialized() and waves > 1:
+                dist.barrier()
+
 
 class NeuronZero1Optimizer(Zero1Optimizer):
     """Reference-named entry point."""
@@ -551,6 +588,26 @@ class NeuronEPZero1Optimizer(torch.optim.Optimizer):
                     fg.param_flat[lo:hi].copy_(fg.master_shard)
                 fg.base_param.grad = None
             o._all_gather_params()
+
+    @property
+    def sharding_groups(self):
+        """``(dp groups for the dense parameters, expert-dp groups for the expert parameters)`` as rank lists."""
+        return ps.get_data_parallel_replica_groups(), ps.get_expert_data_parallel_replica_groups()
+
+    def save_sharded_state_dict(self, output_dir: str, num_workers_per_step: int = 8) -> None:
+        os.makedirs(output_dir, exist_ok=True)
+        path = os.path.join(output_dir, "optim.dp_rank_{:02d}.tp_rank_{:02d}".format(ps.get_data_parallel_rank(),
+                                                                                      ps.get_tensor_model_parallel_rank()))
+        from ..parallel_layers.utils import move_all_tensor_to_cpu
+
+        torch.save(move_all_tensor_to_cpu(self.state_dict()), path)
+        if dist.is_initialized():
+            dist.barrier()
+
+    def load_sharded_state_dict(self, output_dir: str, num_workers_per_step: int = 8) -> None:
+        path = os.path.join(output_dir, "optim.dp_rank_{:02d}.tp_rank_{:02d}".format(ps.get_data_parallel_rank(),
+                                                                                      ps.get_tensor_model_parallel_rank()))
+        self.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
 
     def state_dict(self):
         return {"non_ep": self.non_ep.state_dict() if self.non_ep else None,

@@ -117,10 +117,49 @@ class CheckpointIOState:
             _barrier()
             if _rank() == 0:
                 storage.save_text("1", os.path.join(tag, "done"))
-                for t in _determine_remove_tags(storage, num_kept):
-                    storage.remove_dir(t)
             _barrier()
+            self.submit_remove(num_kept, async_remove=False)
+            self.wait_remove()
         self.items = []
+
+    # -- removal of old checkpoints (reference :246-315) ------------------------------------
+    def submit_remove(self, num_kept: Optional[int], async_remove: bool = False, remove_tags: Optional[List[str]] = None) -> None:
+        """Delete all but the newest ``num_kept`` completed checkpoints (or exactly ``remove_tags``).  Rank 0 first deletes the
+        ``done`` markers — a crash in the middle of a deletion then leaves an *incomplete* tag, never a corrupt one that looks
+        complete — and then the files, on the IO thread when ``async_remove``; directories go in :meth:`wait_remove`."""
+        storage = self.storage
+        assert storage is not None, "begin() must be called first"
+        tags = list(remove_tags) if remove_tags else _determine_remove_tags(storage, num_kept)
+        _barrier()
+        if not tags:
+            return
+        self._remove_tags = tags
+        if _rank() == 0:
+            storage.remove_files([os.path.join(t, "done") for t in tags])
+
+            def job():
+                storage.remove_dirs(tags)
+                return True
+
+            if async_remove and self.executor is not None:
+                self.remove_future = self.executor.submit(job)
+            else:
+                job()
+
+    def wait_remove(self) -> None:
+        if self.remove_future is not None:
+            self.remove_future.result()
+            self.remove_future = None
+        self._remove_tags = None
+        _barrier()                                # nobody lists tags while rank 0 may still be deleting
+
+    def add_dcp_save_task(self, checkpoint_dir: BaseCheckpointStorage, state_dict: dict, optimizer, model, ckpt_path: str) -> None:
+        """ZeRO-1 optimizer state through ``torch.distributed.checkpoint`` (re-shardable on load; reference :161-169)."""
+        from ..optimizer import zero_dcp_utils as dcp_utils
+
+        path = os.path.join(checkpoint_dir.dirname(), ckpt_path, "optim")
+        inner = getattr(optimizer, "optimizer", optimizer)
+        dcp_utils.save_optim_state_dict(path, state_dict, inner)
 
     def _finish_async(self, storage, tag, num_kept) -> None:
         prev = self.save_future
@@ -143,9 +182,9 @@ class CheckpointIOState:
             _barrier()
             if _rank() == 0:
                 storage.save_text("1", os.path.join(tag, "done"))
-                for t in _determine_remove_tags(storage, num_kept):
-                    storage.remove_dir(t)
             _barrier()
+            self.submit_remove(num_kept, async_remove=False)
+            self.wait_remove()
 
     def wait_all(self) -> None:
         self.wait_save()

@@ -12,7 +12,7 @@ import random
 import shutil
 import time
 from abc import ABC, abstractmethod
-from typing import Any, Callable, List
+from typing import Optional, Any, Callable, List
 
 import torch
 
@@ -63,6 +63,22 @@ class BaseCheckpointStorage(ABC):
     def find_files(self, dirname: str, pattern: str) -> List[str]:
         return []
 
+    def find_subdirs_contain_path(self, pattern: str, search_depth: int, search_root: Optional[str] = None,
+                                  max_count: Optional[int] = None, sort_by_mdate: bool = False) -> List[str]:
+        """Directories (relative to the storage root) that contain a file matching ``pattern`` at most ``search_depth``
+        levels below ``search_root`` (reference :65-77) — e.g. every tag directory that has a ``done`` marker."""
+        files = self.find_files(pattern, search_depth + 1, search_root, max_count, sort_by_mdate)
+        return [os.path.dirname(f) for f in files]
+
+    def remove_dirs(self, dirnames: List[str]) -> None:
+        for d in dirnames:
+            self.remove_dir(d)
+
+    def remove_files(self, filenames: List[str]) -> None:
+        for f in filenames:
+            if self.file_exists(f):
+                self.remove_file(f)
+
     def _sort_tags(self, tags: List[str]) -> List[str]:
         return sorted(tags, key=lambda t: self._tag_time(t))
 
@@ -92,15 +108,31 @@ class FilesysCheckpointStorage(BaseCheckpointStorage):
             return []
         return [x for x in os.listdir(d) if os.path.isdir(os.path.join(d, x))]
 
-    def find_files(self, dirname: str, pattern: str) -> List[str]:
+    def find_files(self, dirname, pattern=None, search_root: Optional[str] = None, max_count: Optional[int] = None,
+                   sort_by_mdate: bool = False) -> List[str]:
+        """Two call forms: ``find_files(dirname, pattern)`` (everything below ``dirname``) and the reference's
+        ``find_files(pattern, search_depth, search_root=None, max_count=None, sort_by_mdate=False)`` (:176-205), which bounds
+        the walk depth, optionally sorts newest first and truncates."""
         import fnmatch
 
+        if isinstance(pattern, int):
+            pat, depth, root_rel = dirname, pattern, search_root or ""
+        else:
+            pat, depth, root_rel = pattern, None, dirname
+        base = self._p(root_rel)
         out = []
-        for root, _dirs, files in os.walk(self._p(dirname)):
+        for root, dirs, files in os.walk(base):
+            level = 0 if root == base else os.path.relpath(root, base).count(os.sep) + 1
+            if depth is not None and level >= depth:
+                dirs[:] = []
+                if level > depth:
+                    continue
             for f in files:
-                if fnmatch.fnmatch(f, pattern):
+                if fnmatch.fnmatch(f, pat):
                     out.append(os.path.relpath(os.path.join(root, f), self._dirname))
-        return out
+        if sort_by_mdate:
+            out.sort(key=lambda f: os.path.getmtime(self._p(f)), reverse=True)
+        return out[:max_count] if max_count is not None else out
 
     def create_dir(self, dirname: str, exist_ok: bool = True) -> None:
         os.makedirs(self._p(dirname), exist_ok=exist_ok)

@@ -18,10 +18,54 @@ class NxDOptimizer(torch.optim.Optimizer):
         self.optimizer = optimizer
         self.nxd_config = nxd_config
         self._grad_norm: Optional[torch.Tensor] = None
-        self.param_groups = optimizer.param_groups
-        self.defaults = getattr(optimizer, "defaults", {})
-        self.state = getattr(optimizer, "state", {})
         self._is_zero = isinstance(optimizer, (Zero1Optimizer, NeuronEPZero1Optimizer))
+
+    # the wrapper owns no optimizer state of its own: these are live views of the wrapped optimizer (reference :30-55),
+    # so LR schedulers that mutate ``param_groups`` and code that replaces ``state`` act on the real thing
+    @property
+    def state(self):
+        return self.optimizer.state
+
+    @state.setter
+    def state(self, value) -> None:
+        self.optimizer.state = value
+
+    @property
+    def param_groups(self):
+        return self.optimizer.param_groups
+
+    @param_groups.setter
+    def param_groups(self, value) -> None:
+        self.optimizer.param_groups = value
+
+    @property
+    def defaults(self):
+        return getattr(self.optimizer, "defaults", {})
+
+    @defaults.setter
+    def defaults(self, value) -> None:
+        self.optimizer.defaults = value
+
+    def add_param_group(self, param_group) -> None:
+        self.optimizer.add_param_group(param_group)
+
+    def __getstate__(self):
+        return {"optimizer": self.optimizer, "nxd_config": self.nxd_config, "_grad_norm": None, "_is_zero": self._is_zero}
+
+    def __setstate__(self, state) -> None:
+        self.__dict__.update(state)
+
+    def __repr__(self) -> str:
+        return f"NxDOptimizer({self.optimizer!r})"
+
+    def save_state_dict(self, output_dir: str, num_workers_per_step: int = 8) -> None:
+        """Deprecated in the reference (:150-155) in favour of ``save_checkpoint``; kept: per-(dp, tp) rank shard files."""
+        assert self.nxd_config["optimizer_config"]["zero_one_enabled"], "save_state_dict needs the ZeRO-1 optimizer"
+        self.optimizer.save_sharded_state_dict(output_dir, num_workers_per_step)
+
+    def load_state_dict_from(self, output_dir: str, num_workers_per_step: int = 8) -> None:
+        assert self.nxd_config["optimizer_config"]["zero_one_enabled"], "load_state_dict_from needs the ZeRO-1 optimizer"
+        self.optimizer.load_sharded_state_dict(output_dir, num_workers_per_step)
 
     @property
     def grad_norm(self) -> Optional[torch.Tensor]:

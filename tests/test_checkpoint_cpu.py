@@ -98,3 +98,52 @@ def _legacy(rank, world, root):
 
 def test_legacy_checkpoint(tmp_path):
     run_distributed(_legacy, 2, str(tmp_path), timeout=120)
+
+
+def _optimizer_views_and_shard_files(rank, world, root):
+    """NxDOptimizer exposes live views of the wrapped optimizer; deprecated per-rank shard files still round-trip."""
+    nxd, model, opt = _build(1, True)                        # tp=1 → dp=world: ZeRO-1 shards over both ranks
+    _step(model, opt, 0)
+    assert opt.param_groups is opt.optimizer.param_groups and opt.state is opt.optimizer.state
+    opt.param_groups[0]["lr"] = 0.5
+    assert opt.optimizer.param_groups[0]["lr"] == 0.5 and "lr" in opt.defaults
+    opt.save_state_dict(root)
+    assert os.path.isfile(os.path.join(root, f"optim.dp_rank_{rank:02d}.tp_rank_00"))
+    before = [p.detach().clone() for p in model.parameters()]
+    l1 = _step(model, opt, 1)
+    for p, b in zip(model.parameters(), before):              # roll the weights back, reload the optimizer, redo the step
+        p.data.copy_(b)
+    opt.load_state_dict_from(root)
+    opt.optimizer._all_gather_params() if hasattr(opt.optimizer, "_all_gather_params") else None
+    l2 = _step(model, opt, 1)
+    assert abs(l1 - l2) < 1e-5, (l1, l2)
+    # storage helpers + explicit removal API
+    from neuronx_distributed_b200.trainer.checkpoint import CheckpointIOState
+    from neuronx_distributed_b200.trainer.checkpoint_storage import create_checkpoint_storage
+
+    st = create_checkpoint_storage(os.path.join(root, "ck"))
+    if rank == 0:
+        for i, t in enumerate(("t1", "t2", "t3")):
+            st.save_text("1", f"{t}/checkpoint"); st.save_text("1", f"{t}/done"); st.save_text("x", f"{t}/model/w.pt")
+            for f in ("checkpoint", "done"):                 # distinct creation times (tags are ordered by age)
+                os.utime(os.path.join(root, "ck", t, f), (1000 + i, 1000 + i))
+            os.utime(os.path.join(root, "ck", t), (1000 + i, 1000 + i))
+    import torch.distributed as dist
+    dist.barrier()
+    assert sorted(st.find_subdirs_contain_path("done", 1)) == ["t1", "t2", "t3"]
+    assert st.find_files("w.pt", 1) == [] and len(st.find_files("w.pt", 2)) == 3 and len(st.find_files("w.pt", 2, max_count=2)) == 2
+    io = CheckpointIOState(async_save=True)
+    io.storage = st
+    io.submit_remove(num_kept=1, async_remove=True)
+    io.wait_remove()
+    assert st.list_completed_checkpoint_tags() == ["t3"], (rank, st.list_completed_checkpoint_tags(), os.listdir(os.path.join(root, "ck")))
+    assert not os.path.exists(os.path.join(root, "ck", "t1"))
+    dist.barrier()
+    if rank == 0:
+        st.remove_files(["t3/done", "nope"])
+    dist.barrier()
+    assert st.list_completed_checkpoint_tags() == []
+
+
+def test_optimizer_views_shard_files_and_removal(tmp_path):
+    run_distributed(_optimizer_views_and_shard_files, 2, str(tmp_path), timeout=150)
