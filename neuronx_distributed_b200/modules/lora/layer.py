@@ -13,11 +13,17 @@ from .config import LoraConfig
 class LoraLayer(nn.Module):
     """Common state: base layer, low-rank pair, scaling, merge bookkeeping."""
 
+    adapter_layer_names = ("lora_A", "lora_B", "lora_embedding_A", "lora_embedding_B")
+    other_param_names = ("lora_rank", "lora_alpha", "scaling", "lora_dropout")
+
     def __init__(self, base_layer: nn.Module, config: LoraConfig):
+        if config.lora_rank <= 0:
+            raise ValueError(f"`lora_rank` should be a positive integer value but the value passed is {config.lora_rank}")
         super().__init__()
         self.base_layer = base_layer
         self.lora_config = config
         self.r, self.scaling = config.lora_rank, config.scaling
+        self.lora_rank, self.lora_alpha, self.lora_dropout = config.lora_rank, config.lora_alpha, config.lora_dropout
         self.dropout = nn.Dropout(config.lora_dropout) if config.lora_dropout > 0 else nn.Identity()
         self.merged = False
         for p in base_layer.parameters():
@@ -33,10 +39,47 @@ class LoraLayer(nn.Module):
     def delta_weight(self) -> torch.Tensor:
         raise NotImplementedError
 
-    def merge(self) -> None:
-        if not self.merged:
-            self.base_layer.weight.data += self.delta_weight().to(self.base_layer.weight.dtype)
-            self.merged = True
+    def get_delta_weight(self) -> torch.Tensor:
+        """``scaling · B·A`` in the base weight's layout (reference name)."""
+        return self.delta_weight()
+
+    def get_base_layer(self) -> nn.Module:
+        """Innermost wrapped layer (adapters may wrap adapters)."""
+        base = self
+        while hasattr(base, "base_layer"):
+            base = base.base_layer
+        return base
+
+    def update_layer(self, *args, **kwargs) -> None:
+        """(Re)create the low-rank pair for the current config — subclasses build it in ``__init__``; calling this
+        re-initialises the adapter weights in place."""
+        a = getattr(self, "lora_A", None)
+        b = getattr(self, "lora_B", None)
+        if a is not None and b is not None and hasattr(a, "weight"):
+            self.init_lora_parameters(a.weight.data, b.weight.data)
+
+    @staticmethod
+    def transpose(weight):
+        return nn.Parameter(weight.T) if isinstance(weight, nn.Parameter) else weight.T
+
+    def __repr__(self) -> str:
+        return "lora." + super().__repr__()
+
+    def merge(self, safe_merge: bool = False) -> None:
+        """Fold the adapter into the base weight.  ``safe_merge`` merges into a copy first and refuses non-finite results
+        (a broken adapter must not poison the served base weights)."""
+        if self.merged:
+            return
+        w = self.base_layer.weight
+        delta = self.delta_weight().to(w.dtype)
+        if safe_merge:
+            merged = w.data + delta
+            if not torch.isfinite(merged).all():
+                raise ValueError("NaNs detected in the merged weights. The adapter seems to be broken")
+            w.data.copy_(merged)
+        else:
+            w.data += delta
+        self.merged = True
 
     def unmerge(self) -> None:
         if self.merged:

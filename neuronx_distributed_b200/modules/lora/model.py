@@ -33,16 +33,40 @@ def _wrap(module: nn.Module, cfg: LoraConfig) -> Optional[nn.Module]:
     return None
 
 
+WEIGHTS_NAME = "adapter_model.pt"
+CONFIG_NAME = "adapter_config.json"
+
+
 class LoraModel(nn.Module):
+    ColumnParallelLinear_lora_type = "ColumnParallelLinear"
+    RowParallelLinear_lora_type = "RowParallelLinear"
+    GQAQKVParallelLinear_lora_type = "GQAQKVParallelLinear"
+
     def __init__(self, module: nn.Module, config: LoraConfig):
         super().__init__()
         self.module = module
         self.lora_config = config
-        self.modules_to_save: List[str] = []
+        self.modules_to_save: List[str] = list(config.modules_to_save or [])
+        self.lora_module_parallel_types: Dict[str, str] = {}
+        self.lora_ckpt: Optional[Dict[str, Any]] = None
+        self.is_config_saved = self.is_checkpoint_loaded = self.is_base_model_loaded = False
         if config.enable_lora:
             self.inject_adapter()
-        if config.load_lora_from_ckpt and config.lora_save_path:
+        if config.load_lora_from_ckpt and config.lora_save_path and os.path.isdir(config.lora_save_path):
             self.load_lora(config.lora_save_path, config.lora_load_tag)
+
+    # reference-named flags
+    @property
+    def is_lora_enabled(self) -> bool:
+        return any(isinstance(m, LoraLayer) for m in self.module.modules())
+
+    @property
+    def is_lora_merged(self) -> bool:
+        return any(isinstance(m, LoraLayer) and m.merged for m in self.module.modules())
+
+    @property
+    def is_verbose_enabled(self) -> bool:
+        return bool(self.lora_config.lora_verbose)
 
     # ------------------------------------------------------------------ injection
     def _is_target(self, name: str) -> bool:
@@ -64,6 +88,13 @@ class LoraModel(nn.Module):
             parent_name, _, leaf = name.rpartition(".")
             parent = self.module.get_submodule(parent_name) if parent_name else self.module
             setattr(parent, leaf, wrapped)
+            if isinstance(wrapped, LoraGQAQKVParallelLinear):
+                self.lora_module_parallel_types[name] = self.GQAQKVParallelLinear_lora_type
+                self.lora_kv_size_multiplier = getattr(child, "kv_size_multiplier", 1)
+            elif isinstance(child, ColumnParallelLinear):
+                self.lora_module_parallel_types[name] = self.ColumnParallelLinear_lora_type
+            elif isinstance(child, RowParallelLinear):
+                self.lora_module_parallel_types[name] = self.RowParallelLinear_lora_type
             replaced += 1
         if replaced == 0:
             raise ValueError(f"no module matched LoRA target_modules={self.lora_config.target_modules}")
@@ -73,7 +104,8 @@ class LoraModel(nn.Module):
         bias = self.lora_config.bias
         for n, p in self.module.named_parameters():
             is_lora = "lora_" in n
-            p.requires_grad_(is_lora or (bias == "all" and n.endswith("bias")))
+            keep = any(t in n for t in self.modules_to_save)
+            p.requires_grad_(is_lora or keep or (bias == "all" and n.endswith("bias")))
         if bias == "lora_only":
             for m in self.module.modules():
                 if isinstance(m, LoraLayer) and getattr(m.base_layer, "bias", None) is not None:
@@ -140,7 +172,140 @@ class LoraModel(nn.Module):
     def state_dict(self, *a, **k):
         if self.lora_config.save_lora_base:
             return self.module.state_dict(*a, **k)
-        return self.lora_state_dict()
+        sd = self.lora_state_dict()
+        for key, v in self.module.state_dict().items():                       # extra trainable modules travel with the adapter
+            if self.modules_to_save and any(t in key for t in self.modules_to_save):
+                sd["base_model.model." + key] = v
+        if self.lora_config.merge_sharded_lora:
+            sd = self.merge_sharded_lora_weights(sd)
+        return sd
+
+    # ------------------------------------------------------------------ reference-named surface (model.py:366-746)
+    def get_base_model(self) -> nn.Module:
+        return self.module
+
+    def generate(self, *args, **kwargs):
+        return self.module.generate(*args, **kwargs)
+
+    def named_parameters(self, *args, **kwargs):
+        yield from self.module.named_parameters(*args, **kwargs)
+
+    def module_state_dict(self) -> Dict[str, Any]:
+        return self.module.state_dict()
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return next(self.module.parameters()).dtype
+
+    @property
+    def config(self):
+        return getattr(self.module, "config", None) or self.lora_config
+
+    def update_state_dict_keys(self, state_dict: Dict[str, Any]) -> Dict[str, Any]:
+        """Keys of the un-adapted model → keys of the adapted one (``x.weight`` → ``x.base_layer.weight``), in place."""
+        for mkey in self.module_state_dict():
+            if ".base_layer" in mkey:
+                plain = mkey.replace(".base_layer", "")
+                if plain in state_dict:
+                    state_dict[mkey] = state_dict.pop(plain)
+        return state_dict
+
+    def merge_sharded_lora_weights(self, state_dict: Dict[str, Any]) -> Dict[str, Any]:
+        """Turn TP-sharded adapter halves into full matrices (all-gather over the TP group): ``lora_B`` of column-parallel
+        bases along dim 0, ``lora_A`` of row-parallel bases along the last dim, GQA-QKV ``lora_B`` along dim 0 minus the
+        KV replicas — the result is a single-device (HF-PEFT loadable) adapter."""
+        from ...parallel_layers import comm
+        from ...parallel_layers import parallel_state as ps
+
+        if not ps.model_parallel_is_initialized() or ps.get_tensor_model_parallel_size() == 1:
+            return state_dict
+        for name, w in list(state_dict.items()):
+            if name == "lora_config" or ".lora_" not in name or not isinstance(w, torch.Tensor):
+                continue
+            base = name.split(".lora_")[0]
+            base = base[len("base_model.model."):] if base.startswith("base_model.model.") else base
+            kind = self.lora_module_parallel_types.get(base)
+            if kind == self.ColumnParallelLinear_lora_type and ".lora_B" in name:
+                state_dict[name] = comm.all_gather(w.contiguous(), dim=0)
+            elif kind == self.RowParallelLinear_lora_type and ".lora_A" in name:
+                state_dict[name] = comm.all_gather(w.contiguous(), dim=w.dim() - 1)
+            elif kind == self.GQAQKVParallelLinear_lora_type and ".lora_B" in name:
+                full = comm.all_gather(w.contiguous(), dim=0)
+                state_dict[name] = torch.chunk(full, getattr(self, "lora_kv_size_multiplier", 1))[0] \
+                    if ("lora_B_k" in name or "lora_B_v" in name) else full
+        return state_dict
+
+    def save_config(self, save_dir: Optional[str] = None) -> str:
+        """``adapter_config.json`` with the adapter-defining fields (HF-PEFT compatible ``r`` included)."""
+        import json
+
+        d = save_dir or self.lora_config.lora_save_dir
+        assert d, "no save directory"
+        os.makedirs(d, exist_ok=True)
+        f = os.path.join(d, CONFIG_NAME)
+        with open(f, "w") as w:
+            json.dump(self.lora_config.selected_fields_to_save(), w, indent=2, sort_keys=True)
+        self.is_config_saved = True
+        return f
+
+    def load_checkpoint(self, lora_config: LoraConfig) -> None:
+        """Parse the adapter checkpoint named by ``lora_config`` (single-device file ``<dir>[/<tag>]/adapter_model.pt`` or this
+        rank's ``adapter_tp_rank_XX_pp_rank_YY.pt``): adopt the stored adapter configuration and keep the tensors for
+        :meth:`load_lora_adapter`."""
+        import json
+        from dataclasses import replace
+
+        d = lora_config.lora_save_dir
+        assert d, "lora_save_dir is not set"
+        out = os.path.join(d, lora_config.lora_load_tag) if lora_config.lora_load_tag else d
+        cands = [os.path.join(out, WEIGHTS_NAME)]
+        from ...parallel_layers import parallel_state as ps
+        if ps.model_parallel_is_initialized():
+            cands.insert(0, os.path.join(out, f"adapter_tp_rank_{ps.get_tensor_model_parallel_rank():02d}_pp_rank_"
+                                              f"{ps.get_pipeline_model_parallel_rank():02d}.pt"))
+        path = next((c for c in cands if os.path.isfile(c)), None)
+        if path is None:
+            raise FileNotFoundError(f"{cands[-1]} is not found.")
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        tensors = ckpt.get("state_dict", ckpt)
+        stored = ckpt.get("lora_config")
+        if stored is None:
+            cfg_file = os.path.join(d, CONFIG_NAME)
+            if not os.path.isfile(cfg_file):
+                raise FileNotFoundError(f"Please name the file for LoRA confiugration as {CONFIG_NAME}.")
+            stored = json.load(open(cfg_file))
+        fields = {k: v for k, v in stored.items() if k in LoraConfig.__dataclass_fields__}
+        self.lora_config = replace(lora_config, **fields)
+        self.lora_ckpt = {k: v for k, v in tensors.items() if k != "lora_config"}
+        self.is_checkpoint_loaded = True
+
+    def load_lora_adapter(self):
+        """Inject adapters (if not yet) and load the tensors parsed by :meth:`load_checkpoint`."""
+        assert self.lora_ckpt is not None, "call load_checkpoint() first"
+        if not self.is_lora_enabled and not (self.lora_config.save_lora_base and self.lora_config.merge_lora):
+            self.inject_adapter()
+        sd = {(k[len("base_model.model."):] if k.startswith("base_model.model.") else k): v for k, v in self.lora_ckpt.items()}
+        res = self.module.load_state_dict(sd, strict=False)
+        self.print_model_info()
+        return res
+
+    def get_nb_trainable_parameters(self):
+        trainable = sum(p.numel() for p in self.module.parameters() if p.requires_grad)
+        return trainable, sum(p.numel() for p in self.module.parameters())
+
+    def print_trainable_parameters(self) -> None:
+        from ...utils.logger import get_logger
+
+        t, a = self.get_nb_trainable_parameters()
+        get_logger().info(f"trainable params: {t:,d} || all params: {a:,d} || trainable%: {100 * t / max(a, 1)}")
+
+    def print_model_info(self) -> None:
+        if self.is_verbose_enabled:
+            from ...utils.logger import get_logger
+
+            get_logger().info("LoRA model: %s", self.module)
+            get_logger().info("LoRA configuration: %s", self.lora_config)
+            self.print_trainable_parameters()
 
     def load_state_dict(self, sd, strict: bool = True):
         sd = {(k[len("base_model.model."):] if k.startswith("base_model.model.") else k): v for k, v in sd.items()}

@@ -23,6 +23,49 @@ def test_lora_linear_merge_roundtrip():
     lm.unmerge_lora()
     torch.testing.assert_close(lm(x), y, rtol=1e-4, atol=1e-5)
     assert all(k.startswith("base_model.model.") for k in lm.lora_state_dict())
+    # reference-named surface
+    import json, os, tempfile
+    import pytest
+    from neuronx_distributed_b200.modules.lora.layer import LoraLayer
+
+    assert lm.get_base_model() is m and lm.dtype == torch.float32 and lm.is_lora_enabled and not lm.is_lora_merged
+    t, a = lm.get_nb_trainable_parameters()
+    assert 0 < t < a and t == sum(p.numel() for n, p in lm.named_parameters() if "lora_" in n)
+    lay = next(mod for mod in lm.modules() if isinstance(mod, LoraLayer))
+    assert lay.get_base_layer() is lay.base_layer and repr(lay).startswith("lora.")
+    torch.testing.assert_close(lay.get_delta_weight(), lay.delta_weight())
+    assert lay.transpose(torch.ones(2, 3)).shape == (3, 2) and "lora_A" in LoraLayer.adapter_layer_names
+    lay.lora_B.weight.data.fill_(float("nan"))
+    with pytest.raises(ValueError, match="NaNs"):
+        lay.merge(safe_merge=True)
+    assert not lay.merged and torch.isfinite(lay.base_layer.weight).all()            # base weights untouched
+    lay.update_layer()
+    assert lay.lora_B.weight.abs().sum() == 0                                        # re-initialised (B = 0)
+    full = {"0.weight": torch.zeros(16, 8), "0.bias": torch.zeros(16), "2.weight": torch.zeros(4, 16), "2.bias": torch.zeros(4)}
+    upd = lm.update_state_dict_keys(dict(full))
+    assert set(upd) == {"0.base_layer.weight", "0.base_layer.bias", "2.base_layer.weight", "2.base_layer.bias"}
+    sel = cfg.selected_fields_to_save()
+    assert sel["r"] == 4 and set(sel) == set(cfg.get_selected_fields()) | {"r"}
+    with tempfile.TemporaryDirectory() as d:
+        f = lm.save_config(d)
+        assert json.load(open(f))["lora_alpha"] == 8 and os.path.basename(f) == "adapter_config.json"
+        # single-device adapter file without an embedded config → parsed together with adapter_config.json
+        torch.save(lm.lora_state_dict(), os.path.join(d, "adapter_model.pt"))
+        fresh = LoraModel(nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.Linear(16, 4)), LoraConfig(enable_lora=False))
+        assert not fresh.is_lora_enabled
+        fresh.load_checkpoint(LoraConfig(lora_save_dir=d, lora_rank=99))
+        assert fresh.lora_config.lora_rank == 4 and fresh.is_checkpoint_loaded
+        res = fresh.load_lora_adapter()
+        assert fresh.is_lora_enabled and not res.unexpected_keys
+        with pytest.raises(FileNotFoundError):
+            fresh.load_checkpoint(LoraConfig(lora_save_dir=os.path.join(d, "missing")))
+    # modules_to_save: listed modules stay trainable and travel with the adapter
+    lm3 = LoraModel(nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.Linear(16, 4)),
+                    LoraConfig(lora_rank=2, target_modules=["0"], modules_to_save=["2"]))
+    assert lm3.module[2].weight.requires_grad and not lm3.module[0].base_layer.weight.requires_grad
+    assert any(k.endswith("2.weight") for k in lm3.state_dict())
+    with pytest.raises(ValueError):
+        LoraModel(nn.Sequential(nn.Linear(2, 2)), LoraConfig(lora_rank=0, target_modules=["0"]))
 
 
 def _tp_lora(rank, world, tmp):
@@ -60,6 +103,20 @@ def _tp_lora(rank, world, tmp):
     lm2 = LoraModel(Net(), LoraConfig(lora_rank=2, lora_alpha=4, target_modules=["up_proj", "down_proj"]))
     lm2.load_lora(tmp, "t0")
     torch.testing.assert_close(lm2(x), y)
+    # merged (un-sharded) adapter: B of the column layer / A of the row layer gathered over TP → same on every rank
+    import torch.distributed as dist
+
+    assert lm.lora_module_parallel_types == {"up_proj": "ColumnParallelLinear", "down_proj": "RowParallelLinear"}
+    merged = lm.merge_sharded_lora_weights(lm.lora_state_dict())
+    b_up = merged["base_model.model.up_proj.lora_B.weight"]
+    a_dn = merged["base_model.model.down_proj.lora_A.weight"]
+    assert b_up.shape == (16, 2) and a_dn.shape == (2, 16)
+    for t in (b_up, a_dn):
+        got = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(got, t.contiguous())
+        assert all(torch.equal(g, got[0]) for g in got)
+    lm.lora_config.merge_sharded_lora = True
+    assert lm.state_dict()["base_model.model.up_proj.lora_B.weight"].shape == (16, 2)
 
 
 def test_tp_lora(tmp_path):
