@@ -43,3 +43,36 @@ class NeuronTensorBoardLogger:
         else:
             self._file.write(json.dumps({"step": step, "time": time.time(), **{k: float(v) for k, v in metrics.items()}}) + "\n")
             self._file.flush()
+
+    # ---- TensorBoard-logger surface (reference logger.py:24-139) ----------------------------------------------------------
+    @property
+    def experiment(self):
+        """The underlying writer (a ``SummaryWriter`` when TensorBoard is importable, else the JSON-lines file handle);
+        created lazily on the printing rank only, ``None`` elsewhere."""
+        if not self.should_print():
+            return None
+        if self._writer is None and self._file is None:
+            self._open()
+        return self._writer if self._writer is not None else self._file
+
+    def print_step(self) -> bool:
+        """Alias of :meth:`should_print` (reference spelling)."""
+        return self.should_print()
+
+    def log_graph(self, model, input_array=None) -> None:
+        """Graph export is skipped: a TP/PP-sharded model has no single-process graph to draw."""
+
+    def save(self) -> None:
+        if self._writer is not None:
+            self._writer.flush()
+        if self._file is not None:
+            self._file.flush()
+
+    def finalize(self, status: str = "success") -> None:
+        self.save()
+        if self._writer is not None:
+            self._writer.close()
+            self._writer = None
+        if self._file is not None:
+            self._file.close()
+            self._file = None

@@ -67,3 +67,33 @@ class NeuronLTModule(LightningModule):
 
     def forward(self, *a, **k):
         return self.model(*a, **k)
+
+    # ---- hooks Lightning calls that the NxD wrappers already cover (reference :89-139) ---------------------------------
+    def configure_gradient_clipping(self, *args, **kwargs) -> None:
+        """Clipping runs inside ``NxDOptimizer.step`` / the ZeRO-1 optimizer (global norm over TP / PP / EP groups)."""
+
+    def clip_gradients(self, *args, **kwargs) -> None:
+        """See :meth:`configure_gradient_clipping`."""
+
+    def on_train_batch_end(self, *args, **kwargs) -> None:
+        """User hook."""
+
+    def named_parameters(self, *args, **kwargs):
+        if self.model is None:
+            return iter(())
+        return self.model.named_parameters(*args, **kwargs)
+
+    def state_dict(self, *args, **kwargs):
+        return self.model.state_dict() if self.model is not None else {}
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        return self.model.load_state_dict(state_dict, strict=strict)
+
+    def get_param_groups_by_weight_decay(self, weight_decay: float = 0.01, no_decay=("bias", "norm")):
+        """Two optimizer groups: decayed weights and un-decayed biases / norm gains.  Uses the LOCAL parameters of a
+        pipeline-partitioned model.  Override for other policies."""
+        m = self.model
+        named = list(m.local_named_parameters()) if getattr(m, "partitioned", False) and hasattr(m, "local_named_parameters") \
+            else list(m.named_parameters())
+        return [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": weight_decay},
+                {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]

@@ -16,6 +16,19 @@ def to_torch_dtype(dtype_str) -> torch.dtype:
     return table[dtype_str]
 
 
+def _from_kwargs(cls, kwargs: dict):
+    """Build a config dataclass from a loose kwargs dict: known fields are consumed (popped), the rest is left for the
+    caller — the reference's ``from_kwargs`` protocol (moe_configs.py), dtype strings accepted."""
+    import dataclasses
+
+    picked = {}
+    for f in dataclasses.fields(cls):
+        if f.name in kwargs:
+            v = kwargs.pop(f.name)
+            picked[f.name] = to_torch_dtype(v) if f.name == "dtype" and isinstance(v, str) else v
+    return cls(**picked)
+
+
 @dataclass
 class RouterConfig:
     act_fn: str = "softmax"                 # "softmax" | "sigmoid"
@@ -25,6 +38,15 @@ class RouterConfig:
     jitter_eps: float = 0.0
     bias: bool = False
     apply_act_fn_over_topk: bool = False
+
+    @classmethod
+    def from_kwargs(cls, **kwargs) -> "RouterConfig":
+        kwargs = dict(kwargs)
+        if "router_act_fn" in kwargs:
+            kwargs.setdefault("act_fn", kwargs.pop("router_act_fn"))
+        if "router_dtype" in kwargs:
+            kwargs.setdefault("dtype", kwargs.pop("router_dtype"))
+        return _from_kwargs(cls, kwargs)
 
 
 @dataclass
@@ -43,6 +65,12 @@ class BlockwiseMatmulConfig:
     @classmethod
     def default(cls) -> "BlockwiseMatmulConfig":
         return cls()
+
+    @classmethod
+    def from_kwargs(cls, **kwargs) -> "BlockwiseMatmulConfig":
+        kwargs = dict(kwargs)
+        kwargs.pop("blockwise_nki_autograd_cls", None)       # kernel-class selection has no counterpart (one grouped GEMM)
+        return _from_kwargs(cls, kwargs)
 
 
 @dataclass
@@ -67,6 +95,24 @@ class RoutedExpertsMLPOpsConfig:
     enable_spmd_rank: bool = False
     input_layer_init_method: Optional[object] = None
     output_layer_init_method: Optional[object] = None
+    use_index_calc_kernel: bool = True
+    is_prefill: bool = True
+    expert_distribution: Optional[list] = None       # [ep_rank][slot] → logical expert id (redundant experts allowed)
+
+    def __post_init__(self):
+        self.local_redudancy_degree = self.bincount_2d(self.expert_distribution, self.num_experts) \
+            if self.expert_distribution else None
+
+    @staticmethod
+    def bincount_2d(expert_distribution, num_experts: int):
+        """``[ep_rank][expert]`` → how many replicas of each logical expert an EP rank hosts."""
+        out = []
+        for row in expert_distribution:
+            counts = [0] * num_experts
+            for e in row:
+                counts[int(e)] += 1
+            out.append(counts)
+        return out
 
 
 @dataclass

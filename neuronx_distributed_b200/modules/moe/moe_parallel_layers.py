@@ -145,6 +145,32 @@ class _ExpertFusedBase(BaseParallelLayer, ExpertFusedLinear):
             self.master_weight = torch.stack(masters)
         return w
 
+    def set_weight_and_bias_config(self) -> None:
+        """Override point: full logical weight shape ``(E, in, out)`` and the TP partition dim (reference :234-246)."""
+        self.weight_shape = (self.num_experts, self.input_size, self.output_size)
+
+    def init_weight_cpu(self) -> None:
+        """Re-draw this rank's expert shards from the per-expert seeded full weights."""
+        with torch.no_grad():
+            self.weight.data.copy_(self._make(self.weight_shape, self.weight_partition_dim).data)
+
+    def initialize_weight_and_bias(self) -> None:
+        self.set_weight_and_bias_config()
+        self.init_weight_cpu()
+        if self.bias is not None:
+            with torch.no_grad():
+                self.bias.zero_()
+
+    def preshard_hook(self, model_state_dict, prefix: str) -> None:
+        """Full checkpoints may store per-expert tensors (``….experts.<e>.<proj>.weight``, HF Mixtral style ``[out, in]``):
+        stack them into this layer's single ``[E, in, out]`` entry when that entry is missing."""
+        if prefix in model_state_dict:
+            return
+        base = prefix[: prefix.rfind(".") + 1]
+        pat = base + "{e}.weight"
+        if all(pat.format(e=e) in model_state_dict for e in range(self.num_experts)):
+            model_state_dict[prefix] = torch.stack([model_state_dict.pop(pat.format(e=e)).t() for e in range(self.num_experts)])
+
     def _make_bias(self, size: int, partitioned: bool):
         b = nn.Parameter(torch.zeros(self.num_local_experts, size, dtype=self.dtype, device=self.device))
         if partitioned:

@@ -29,6 +29,24 @@ class RouterBase(nn.Module):
         self.linear_router = nn.Linear(hidden_size, num_experts, bias=bias, dtype=dtype, device=device)
         for p in self.linear_router.parameters():
             setattr(p, "sequence_parallel_enabled", sequence_parallel_enabled)
+        self.bias, self.store_transposed_weights = bias, store_transposed_weights
+        if store_transposed_weights:
+            # inference: a second copy ``[H, E]`` so the decode-time router GEMV streams the weight along its contiguous dim
+            # (reference routing.py:96-104, filled from the checkpoint by ``preshard_hook``)
+            self.weight_T = nn.Parameter(self.linear_router.weight.detach().t().contiguous().clone(), requires_grad=False)
+
+    def preshard_hook(self, model_state_dict, prefix: str) -> None:
+        """Full checkpoints carry only ``linear_router.weight``: derive ``weight_T`` from it."""
+        if not self.store_transposed_weights:
+            return
+        base = prefix
+        for suffix in ("linear_router.weight", "weight_T", "weight"):
+            if base.endswith(suffix):
+                base = base[: -len(suffix)]
+                break
+        src = base + "linear_router.weight"
+        if src in model_state_dict:
+            model_state_dict[base + "weight_T"] = model_state_dict[src].detach().t().contiguous().clone()
 
     def get_router_logits(self, hidden_states: torch.Tensor) -> torch.Tensor:
         if self.sequence_parallel_enabled:
@@ -37,6 +55,9 @@ class RouterBase(nn.Module):
         x = hidden_states.reshape(-1, self.hidden_size)
         if self.training and self.jitter_eps > 0:
             x = x * torch.empty_like(x).uniform_(1.0 - self.jitter_eps, 1.0 + self.jitter_eps)
+        if self.store_transposed_weights and not self.training:
+            out = x.to(self.weight_T.dtype) @ self.weight_T
+            return (out if self.linear_router.bias is None else out + self.linear_router.bias).float()
         w = self.linear_router.weight
         return F.linear(x.to(w.dtype), w, self.linear_router.bias).float()
 
@@ -64,6 +85,8 @@ class RouterTopK(RouterBase):
 
 
 class RouterSinkhorn(RouterBase):
+    DEFAULT_SINKHORN_ITERS = 30
+
     """Top-1 routing balanced with Sinkhorn iterations during training (Megatron-style)."""
 
     def __init__(self, *a, sinkhorn_iterations: int = 30, sinkhorn_tol: Optional[float] = None, **k):
@@ -110,9 +133,10 @@ class GroupLimitedRouter(RouterBase):
         self.n_group, self.topk_group, self.routed_scaling_factor = n_group, topk_group, routed_scaling_factor
         self.e_score_correction_bias = nn.Parameter(torch.zeros(self.num_experts, dtype=torch.float32), requires_grad=False)
 
-    def forward(self, hidden_states: torch.Tensor):
-        logits = self.get_router_logits(hidden_states)
-        scores = self.apply_activation_fn(logits)
+    def noaux_tc_top_k(self, scores: torch.Tensor):
+        """Auxiliary-loss-free top-k (reference routing.py:391-413): add the learned per-expert correction bias (selection
+        only), score every group by the sum of its two best experts, keep the ``topk_group`` best groups, pick the ``top_k``
+        experts among them.  Returns ``(topk_idx, scores)`` — the affinities stay the UNbiased scores."""
         biased = scores + self.e_score_correction_bias.unsqueeze(0)
         T = biased.shape[0]
         g = biased.view(T, self.n_group, -1)
@@ -121,6 +145,11 @@ class GroupLimitedRouter(RouterBase):
         gmask = torch.zeros_like(group_scores).scatter_(1, gidx, 1.0)
         emask = gmask.unsqueeze(-1).expand(T, self.n_group, g.shape[-1]).reshape(T, -1)
         masked = biased.masked_fill(emask == 0, float("-inf"))
-        idx = masked.topk(self.top_k, dim=-1).indices
+        return masked.topk(self.top_k, dim=-1).indices, scores
+
+    def forward(self, hidden_states: torch.Tensor):
+        logits = self.get_router_logits(hidden_states)
+        scores = self.apply_activation_fn(logits)
+        idx, _ = self.noaux_tc_top_k(scores)
         aff = scores * self.routed_scaling_factor
         return logits, aff.to(hidden_states.dtype), idx.long()

@@ -25,6 +25,12 @@ class RMSNorm(nn.Module):
         self.sequence_parallel_enabled = sequence_parallel_enabled
         setattr(self.weight, "sequence_parallel_enabled", sequence_parallel_enabled)
 
+    def reset_parameters(self) -> None:
+        """Re-initialise after meta-device materialisation (``reinit_model`` calls it): unit gain."""
+        with torch.no_grad():
+            self.weight.fill_(1.0)
+        setattr(self.weight, "sequence_parallel_enabled", self.sequence_parallel_enabled)
+
     def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
         return rms_norm(hidden_states, self.weight, self.variance_epsilon)
 

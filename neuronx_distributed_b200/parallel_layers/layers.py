@@ -67,7 +67,8 @@ def _initialize_parameter_from_master(
 ) -> Optional[torch.Tensor]:
     """Initialise the *full* fp32 weight (identical on all ranks) and copy this rank's slice
     into ``param`` — results do not depend on the TP degree (reference layers.py:111-164)."""
-    set_tensor_model_parallel_attributes(param, True, partition_dim, stride, num_partitions)
+    if not hasattr(param, "tensor_model_parallel"):          # re-initialisation keeps the attributes it already has
+        set_tensor_model_parallel_attributes(param, True, partition_dim, stride, num_partitions)
     if ps.get_aot_mode() or param.device.type == "meta":
         return None
     shape = list(param.shape)
@@ -178,6 +179,23 @@ class SPMDRank(nn.Module):
     def get_rank(self) -> torch.Tensor:
         return self.rank
 
+    def initialize_expert_indices(self, num_local_experts: int) -> Parameter:
+        """Per-rank list of the expert ids this rank owns, kept as a WEIGHT ``[1, num_local_experts]`` (dim 0 sharded over
+        the world) so that one captured program serves every rank (reference layers.py:1571-1593).  Filled for the current
+        EP rank; a full checkpoint provides ``[world, num_local_experts]``."""
+        self.local_expert_indices = Parameter(torch.zeros((1, num_local_experts), dtype=torch.int32), requires_grad=False)
+        set_tensor_model_parallel_attributes(self.local_expert_indices, True, 0, 1, num_partitions=self.world_size)
+        try:
+            ep, r = ps.get_expert_model_parallel_size(), ps.get_expert_model_parallel_rank()
+            ids = ps.get_experts_for_expert_parallel_rank(r, num_local_experts * ep, ep)
+            self.local_expert_indices.data.copy_(torch.as_tensor(ids, dtype=torch.int32).view(1, -1))
+        except AssertionError:
+            pass
+        return self.local_expert_indices
+
+    def get_local_expert_indices(self) -> torch.Tensor:
+        return self.local_expert_indices
+
     def forward(self) -> torch.Tensor:
         return self.rank
 
@@ -256,11 +274,17 @@ class ParallelEmbedding(BaseParallelLayer):
             shape = (self.num_embeddings_per_partition, embedding_dim)
         device = device if device is not None else torch.device("cpu")
         self.weight = Parameter(torch.empty(*shape, device=device, dtype=dtype))
-        _initialize_parameter_from_master(
-            self.weight, self.weight_partition_dim, tp, init_method, param_dtype=dtype, rank=tp_rank
-        )
+        self.init_method, self.dtype, self._tp_rank = init_method, dtype, tp_rank
+        self.init_weight_cpu()
         if rank_ordering is not None:
             self.weight.rank_ordering = list(rank_ordering)
+
+    def init_weight_cpu(self) -> None:
+        """(Re-)initialise from a full master table drawn identically on every rank (reference layers.py:325-332)."""
+        _initialize_parameter_from_master(
+            self.weight, self.weight_partition_dim, self.tensor_model_parallel_size, self.init_method,
+            param_dtype=self.dtype, rank=self._tp_rank
+        )
 
     def _embed(self, ids: torch.Tensor) -> torch.Tensor:
         return F.embedding(
@@ -565,12 +589,10 @@ class ColumnParallelLinear(BaseParallelLinear):
         self.reduce_dtype, self.rank_ordering = reduce_dtype, rank_ordering
         self.arg_init_method = init_method
         self.async_tensor_model_parallel_allreduce = not sequence_parallel_enabled and tp > 1
-        self.weight_partition_dim = 0
         self.master_weight: Optional[torch.Tensor] = None
-        self.weight = Parameter(
-            torch.empty(self.output_size_per_partition, input_size, dtype=dtype, device=self.device)
-        )
-        self.bias_shape = (self.output_size_per_partition,) if not gather_output else (self.output_size,)
+        self.add_bias = bias
+        self.set_weight_and_bias_config()
+        self.weight = Parameter(torch.empty(*self.weight_shape, dtype=dtype, device=self.device))
         if bias:
             # bias is sharded like the weight unless the output is gathered (then it is
             # replicated and added after the gather) — reference :700-722
@@ -583,22 +605,28 @@ class ColumnParallelLinear(BaseParallelLinear):
             self.register_parameter("bias", None)
         self.initialize_weight_and_bias()
 
-    def _init_weight(self, w: torch.Tensor) -> None:
-        if self.arg_init_method is None:
-            init.kaiming_uniform_(w, a=math.sqrt(5))
-        else:
-            self.arg_init_method(w)
+    def set_weight_and_bias_config(self) -> None:
+        """Shapes / partition dims of this rank's parameters — the override point for layers with another weight layout
+        (reference layers.py:660-671)."""
+        self.weight_shape = (self.output_size_per_partition, self.input_size)
+        self.weight_partition_dim = 0
+        self.bias_shape = ((self.output_size,) if self.gather_output else (self.output_size_per_partition,))
+        self.bias_partition_dim = 0
+
+    def init_weight_cpu(self) -> None:
+        """Draw the FULL weight (identical on every rank) and keep this rank's slice — TP-degree independent init."""
+        master = _initialize_parameter_from_master(
+            self.weight, self.weight_partition_dim, self.tensor_model_parallel_size, self._init_weight,
+            return_master_param=self.keep_master_weight, param_dtype=self.dtype, stride=self.stride, rank=self._tp_rank,
+        )
+        if self.keep_master_weight:
+            self.master_weight = master
 
     def initialize_weight_and_bias(self) -> None:
         tp = self.tensor_model_parallel_size
-        master = _initialize_parameter_from_master(
-            self.weight, 0, tp, self._init_weight, return_master_param=self.keep_master_weight,
-            param_dtype=self.dtype, stride=self.stride, rank=self._tp_rank,
-        )
+        self.init_weight_cpu()
         if self.rank_ordering is not None:
             self.weight.rank_ordering = list(self.rank_ordering)
-        if self.keep_master_weight:
-            self.master_weight = master
         if self.bias is not None and self.arg_init_method is None and self.weight.device.type != "meta":
             bound = 1 / math.sqrt(self.input_size) if self.input_size > 0 else 0
             with torch.no_grad():
@@ -694,13 +722,12 @@ class RowParallelLinear(BaseParallelLinear):
         self.arg_init_method = init_method
         if sequence_parallel_enabled and not input_is_parallel:
             raise RuntimeError("To enable `sequence_parallel_enabled`, `input_is_parallel` must be `True`")
-        self.weight_partition_dim = 1
         self.master_weight: Optional[torch.Tensor] = None
-        self.weight = Parameter(
-            torch.empty(output_size, self.input_size_per_partition, dtype=dtype, device=self.device)
-        )
+        self.add_bias = bias
+        self.set_weight_and_bias_config()
+        self.weight = Parameter(torch.empty(*self.weight_shape, dtype=dtype, device=self.device))
         if bias:
-            self.bias = Parameter(torch.zeros(output_size, dtype=dtype, device=self.device))
+            self.bias = Parameter(torch.zeros(*self.bias_shape, dtype=dtype, device=self.device))
             _tag_sequence_parallel(self.bias, sequence_parallel_enabled)
         else:
             self.register_parameter("bias", None)
@@ -712,16 +739,25 @@ class RowParallelLinear(BaseParallelLinear):
         else:
             self.arg_init_method(w)
 
-    def initialize_weight_and_bias(self) -> None:
+    def set_weight_and_bias_config(self) -> None:
+        """Override point (reference layers.py:909-918)."""
+        self.weight_shape = (self.output_size, self.input_size_per_partition)
+        self.weight_partition_dim = 1
+        self.bias_shape = (self.output_size,)
+
+    def init_weight_cpu(self) -> None:
         master = _initialize_parameter_from_master(
-            self.weight, 1, self.tensor_model_parallel_size, self._init_weight,
+            self.weight, self.weight_partition_dim, self.tensor_model_parallel_size, self._init_weight,
             return_master_param=self.keep_master_weight, param_dtype=self.dtype, stride=self.stride,
             rank=self._tp_rank,
         )
-        if self.rank_ordering is not None:
-            self.weight.rank_ordering = list(self.rank_ordering)
         if self.keep_master_weight:
             self.master_weight = master
+
+    def initialize_weight_and_bias(self) -> None:
+        self.init_weight_cpu()
+        if self.rank_ordering is not None:
+            self.weight.rank_ordering = list(self.rank_ordering)
         if self.bias is not None and self.arg_init_method is None and self.weight.device.type != "meta":
             bound = 1 / math.sqrt(self.input_size) if self.input_size > 0 else 0
             with torch.no_grad():
@@ -819,16 +855,26 @@ def conv2d_with_weight_grad_allreduce(input: torch.Tensor, weight: torch.Tensor,
 
 class BaseParallelConv(BaseParallelLayer):
     def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
-                 padding_mode, partition_dim, dtype, device, init_method, keep_master_weight, group):
+                 padding_mode, partition_dim, dtype, device, init_method, keep_master_weight, group, partition_pad=False):
         super().__init__(device=device)
         if groups != 1:
             raise NotImplementedError("grouped convolution is not supported by the parallel conv layers")
         if padding_mode != "zeros":
             raise NotImplementedError("only zero padding is supported")
-        self.in_channels, self.out_channels = in_channels, out_channels
         self.kernel_size, self.stride = _pair(kernel_size), _pair(stride)
         self.padding, self.dilation, self.groups = _pair(padding), _pair(dilation), groups
         self.tensor_parallel_group, self.tensor_model_parallel_size, self._tp_rank = _group_info(group)
+        # ``partition_pad``: zero-pad the partitioned channel count up to a multiple of tp (reference layers.py:1195-1211);
+        # padded output channels are cut after the gather, padded input channels see zero input
+        self.partition_pad, self.partition_pad_size = partition_pad, 0
+        if partition_pad:
+            n = out_channels if partition_dim == 0 else in_channels
+            self.partition_pad_size = get_padding_length(n, self.tensor_model_parallel_size)
+            if partition_dim == 0:
+                out_channels += self.partition_pad_size
+            else:
+                in_channels += self.partition_pad_size
+        self.in_channels, self.out_channels = in_channels, out_channels
         self.partition_dim, self.dtype = partition_dim, dtype
         self.arg_init_method, self.keep_master_weight = init_method, keep_master_weight
         self.device = device if device is not None else torch.device("cpu")
@@ -866,10 +912,21 @@ class OutputChannelParallelConv2d(BaseParallelConv):
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
                  bias=True, padding_mode="zeros", gather_output=True, dtype=torch.float32, device=None,
-                 init_method=None, keep_master_weight=False, tensor_model_parallel_group=None):
+                 init_method=None, keep_master_weight=False, partition_pad=False, tensor_model_parallel_group=None):
         super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
-                         padding_mode, 0, dtype, device, init_method, keep_master_weight, tensor_model_parallel_group)
+                         padding_mode, 0, dtype, device, init_method, keep_master_weight, tensor_model_parallel_group,
+                         partition_pad)
         self.gather_output = gather_output
+
+    def preshard_hook(self, model_state_dict: Dict[str, Any], prefix: str) -> None:
+        """Zero-pad a full checkpoint's weight / bias along the output-channel dim (reference :1419-1429)."""
+        if not self.partition_pad or self.partition_pad_size == 0:
+            return
+        w = model_state_dict[prefix]
+        if self.out_channels != w.shape[0] + self.partition_pad_size:
+            raise RuntimeError(f"State dict {prefix} is of an unexpected size {w.shape[0]} expected "
+                               f"{self.out_channels - self.partition_pad_size}")
+        model_state_dict[prefix] = F.pad(w, (0, 0) * (w.dim() - 1) + (0, self.partition_pad_size))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         tp = self.tensor_model_parallel_size
@@ -877,6 +934,8 @@ class OutputChannelParallelConv2d(BaseParallelConv):
                                             self.groups, tp > 1, self.tensor_parallel_group)
         if self.gather_output:
             out = mappings.gather_from_tensor_model_parallel_region_with_dim(out, 1, self.tensor_parallel_group)
+            if self.partition_pad and self.partition_pad_size > 0:
+                out = out.narrow(1, 0, self.out_channels - self.partition_pad_size)
         return out
 
 
@@ -886,13 +945,24 @@ class InputChannelParallelConv2d(BaseParallelConv):
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
                  bias=True, padding_mode="zeros", input_is_parallel=False, dtype=torch.float32, device=None,
-                 init_method=None, keep_master_weight=False, tensor_model_parallel_group=None):
+                 init_method=None, keep_master_weight=False, partition_pad=False, tensor_model_parallel_group=None):
         super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
-                         padding_mode, 1, dtype, device, init_method, keep_master_weight, tensor_model_parallel_group)
+                         padding_mode, 1, dtype, device, init_method, keep_master_weight, tensor_model_parallel_group,
+                         partition_pad)
         self.input_is_parallel = input_is_parallel
+
+    def preshard_hook(self, model_state_dict: Dict[str, Any], prefix: str) -> None:
+        if not self.partition_pad or self.partition_pad_size == 0 or not prefix.endswith("weight"):
+            return
+        w = model_state_dict[prefix]
+        if self.in_channels != w.shape[1] + self.partition_pad_size:
+            raise RuntimeError(f"State dict {prefix} is of an unexpected size {w.shape[1]}")
+        model_state_dict[prefix] = F.pad(w, (0, 0, 0, 0, 0, self.partition_pad_size))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not self.input_is_parallel:
+            if self.partition_pad and self.partition_pad_size > 0:
+                x = F.pad(x, (0, 0, 0, 0, 0, self.partition_pad_size))
             x = mappings.scatter_input_channels_to_tensor_model_parallel_region(x, self.tensor_parallel_group)
         out = _ConvWithAsyncAllReduce.apply(x, self.weight, None, self.stride, self.padding, self.dilation,
                                             self.groups, False, self.tensor_parallel_group)

@@ -143,8 +143,12 @@ class Train1F1BSchedule(PipeSchedule):
 
     def __init__(self, num_microbatches: int, stages: int, stage_id: int):
         super().__init__(num_microbatches, stages, stage_id)
-        self.num_warmup_steps = min(stages - stage_id - 1, num_microbatches)
-        self.num_steady_state_microbatches = num_microbatches - self.num_warmup_steps
+        self.get_microbatche_schedule()
+
+    def get_microbatche_schedule(self) -> None:     # (sic) reference spelling, scheduler.py:179
+        """Phase lengths of this stage: warm-up forwards, steady 1F1B pairs, cool-down backwards."""
+        self.num_warmup_steps = min(self.stages - self.stage_id - 1, self.num_microbatches)
+        self.num_steady_state_microbatches = self.num_microbatches - self.num_warmup_steps
         self.num_remaining_microbatches = self.num_warmup_steps
 
     def compute_order(self) -> List[Slot]:
@@ -195,11 +199,16 @@ class TrainInterleavedSchedule(PipeSchedule):
         self.num_model_chunks = num_model_chunks
         self.fused_send_recv, self.fused_fwd_bwd = fused_send_recv, fused_fwd_bwd
         self.use_odd_even_scheduler = use_odd_even_scheduler
-        self.num_microbatches_steps = num_microbatches * num_model_chunks
-        if num_microbatches == stages:
+        self.get_step_schedule()
+
+    def get_step_schedule(self) -> None:
+        """Phase lengths in (micro-batch × chunk) steps: all-forward-then-all-backward when ``num_microbatches == stages``,
+        otherwise ``2·(stages − stage − 1) + (chunks − 1)·stages`` warm-up forwards (reference scheduler.py:296-317)."""
+        self.num_microbatches_steps = self.num_microbatches * self.num_model_chunks
+        if self.num_microbatches == self.stages:
             self.num_warmup_steps = self.num_microbatches_steps
         else:
-            self.num_warmup_steps = min((stages - stage_id - 1) * 2 + (num_model_chunks - 1) * stages,
+            self.num_warmup_steps = min((self.stages - self.stage_id - 1) * 2 + (self.num_model_chunks - 1) * self.stages,
                                         self.num_microbatches_steps)
         self.num_steady_state_steps = self.num_microbatches_steps - self.num_warmup_steps
         self.num_remaining_steps = self.num_warmup_steps

@@ -44,6 +44,22 @@ class Sampler:
         return idx.gather(-1, choice).squeeze(-1)
 
 
+def _multinomial(self, token_logits: torch.Tensor, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Top-k multinomial sampling by inverse CDF (reference sampling.py:27-77): softmax over the k best logits, one uniform
+    draw per row, the sample is the number of CDF entries below the draw.  Branch-free and free of host synchronisation
+    (``torch.multinomial`` validates its input on the host), hence CUDA-graph capturable."""
+    if self.top_k == 1:
+        return torch.argmax(token_logits, dim=1)
+    vals, idx = torch.topk(token_logits, min(self.top_k, token_logits.shape[1]), dim=1)
+    cdf = torch.softmax(vals.float() / max(self.temperature, 1e-6), dim=1).cumsum(dim=1)
+    u = torch.rand((cdf.shape[0], 1), device=token_logits.device, generator=generator)
+    counts = ((cdf - u) < 0).sum(dim=1).clamp(max=idx.shape[1] - 1)
+    return idx.gather(1, counts.unsqueeze(1)).flatten()
+
+
+Sampler.multinomial = _multinomial
+
+
 def create_sampler(neuron_config=None, **kw) -> Sampler:
     if neuron_config is not None:
         kw = {**{k: getattr(neuron_config, k) for k in ("top_k", "top_p", "temperature", "do_sample") if hasattr(neuron_config, k)}, **kw}

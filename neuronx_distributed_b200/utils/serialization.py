@@ -32,6 +32,26 @@ class SerializationManager:
                 stubs.append(leaf)
         return (stubs, spec), tensors
 
+    def extract_stubs(self, skeleton: Any) -> List[TensorStub]:
+        """The tensor placeholders of a serialised skeleton, in tensor order (what a receiver must allocate)."""
+        stubs, _ = skeleton
+        return [s for s in stubs if isinstance(s, TensorStub)]
+
+    @staticmethod
+    def catch_and_raise_for_large_object(obj: Any):
+        """Context manager turning a ``RecursionError`` while walking a very deep object into a ``RuntimeError`` naming
+        the object's class (reference :96-101)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            try:
+                yield
+            except RecursionError:
+                raise RuntimeError(obj.__class__.__name__) from None
+
+        return ctx()
+
     def deserialize(self, skeleton: Any, tensors: List[torch.Tensor]) -> Any:
         stubs, spec = skeleton
         leaves = [tensors[s.index] if isinstance(s, TensorStub) else s for s in stubs]
