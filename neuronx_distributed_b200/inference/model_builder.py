@@ -78,6 +78,73 @@ class ModelBuilder:
 
     compile = trace
 
+    # ---- pieces of the v1 build exposed by the reference (model_builder.py:700-1369) -------------------------------------
+    def build_nxd_model(self) -> NxDModel:
+        return self.trace()
+
+    def build_state_initializer(self):
+        """State (KV-cache) buffers = the registered buffers of the bucket modules; returns an initialiser that re-creates
+        them zero-filled (shapes / dtypes are taken from the live buffers)."""
+        from .nxd_model import StateInitializer
+
+        shapes, dtypes = {}, {}
+        for e in self.entries.values():
+            inst = e["instance"]
+            module = inst.get()[0] if isinstance(inst, BaseModelInstance) else inst
+            if isinstance(module, nn.Module):
+                for n, b in module.named_buffers():
+                    shapes[n], dtypes[n] = list(b.shape), b.dtype
+        return StateInitializer(shapes, dtypes, 1) if shapes else None
+
+    def build_flattener_map(self) -> Dict[str, Callable]:
+        return {f"{k}_{i}": (lambda inputs: list(inputs)) for k, e in self.entries.items() for i in range(len(e["examples"]))}
+
+    def build_packer(self) -> Callable:
+        return lambda outputs: outputs
+
+    def shard_weights(self, rank: int, model_container: Any = None, serialize_path: Optional[str] = None) -> Dict[str, torch.Tensor]:
+        """Rank ``rank``'s shard of the checkpoint returned by ``checkpoint_loader`` (preshard hooks applied)."""
+        assert self.checkpoint_loader is not None, "a checkpoint_loader is required"
+        model = self.model
+        if model is None and model_container is not None:
+            inst = getattr(model_container, "model_instance", model_container)
+            model = inst.get()[0] if isinstance(inst, BaseModelInstance) else inst
+        assert model is not None, "no model to take the parallel attributes from"
+        return shard_checkpoint(self.checkpoint_loader(), model, self.tp_degree, start_rank=rank, end_rank=rank,
+                                serialize_path=serialize_path)[0]
+
+    def shard_weights_with_cache(self, rank: int, model_container: Any = None, serialize_path: Optional[str] = None):
+        """Same as :meth:`shard_weights` but pre-processes (hooks, key clean-up) the full checkpoint only once."""
+        if not hasattr(self, "_ckpt_cache"):
+            self._ckpt_cache = self.checkpoint_loader()
+        loader, self.checkpoint_loader = self.checkpoint_loader, (lambda: dict(self._ckpt_cache))
+        try:
+            return self.shard_weights(rank, model_container, serialize_path)
+        finally:
+            self.checkpoint_loader = loader
+
+    @staticmethod
+    def cast_weights(checkpoint: Dict[str, torch.Tensor], model: nn.Module) -> Dict[str, torch.Tensor]:
+        """Cast floating checkpoint tensors to the dtype of the parameter they load into (bf16 models from fp32 files)."""
+        params = dict(model.named_parameters())
+        for k, v in list(checkpoint.items()):
+            p = params.get(k)
+            if p is not None and isinstance(v, torch.Tensor) and v.is_floating_point() and p.is_floating_point() \
+                    and v.dtype != p.dtype and v.element_size() > 1 and p.element_size() > 1:
+                checkpoint[k] = v.to(p.dtype)
+        return checkpoint
+
+    def write_neff_to_file(self, nxd_model: NxDModel, path: str) -> None:
+        """The reference dumps the compiled NEFFs; the analogue here is the bucket description of the runtime model."""
+        os.makedirs(path, exist_ok=True)
+        with open(os.path.join(path, "programs.txt"), "w") as f:
+            for k, progs in nxd_model.programs.items():
+                for p in progs:
+                    f.write(f"{k}: shapes={p.shapes} dtypes={p.dtypes} cuda_graph={p.graph is not None}\n")
+
+    def transform_weight_layout_with_overriden_option(self, *args, **kwargs) -> None:
+        """No weight-layout transformation exists (see ``trace/hlo_utils.py``)."""
+
     def shard_checkpoint(self, serialize_path: Optional[str] = None) -> List[Dict[str, torch.Tensor]]:
         assert self.model is not None and self.checkpoint_loader is not None
         return shard_checkpoint(self.checkpoint_loader(), self.model, self.tp_degree, serialize_path=serialize_path)

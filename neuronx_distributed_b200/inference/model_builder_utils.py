@@ -17,6 +17,12 @@ class ModelBuilderConstants:
     DEFAULT_WORLD_SIZE = 1
     LAYOUT_TRANSFORMER_KEY = "layout_transformer"        # kept for API parity; weights need no re-layout between buckets
     DEFAULT_KEY_PREFIX = "model"
+    DEFAULT_COMPILER_WORKDIR = "/tmp/nxd_b200_workdir/"
+    LOG_FILE_DEFAULT_NAME = "log-capture.txt"
+    GRAPH_HLO_FILE = "program.txt"                        # per-bucket description written by ``compile`` (no HLO here)
+    NEFF_FILE = "program.txt"
+    WRAPPED_NEFF_FILE = "program.txt"
+    METANEFF_FILE = "metadata.txt"
 
 
 @dataclass

@@ -282,6 +282,49 @@ class NxDModel(BaseNxDModel):
 
     to_device = to_neuron
 
+    # ---- v1 runtime names (reference trace/spmd.py:180-291) ------------------------------------------------------------
+    def initialize(self, checkpoint: Sequence[Dict[str, torch.Tensor]], start_rank_tensor: Any = None) -> None:
+        """Load the sharded checkpoint and create the state buffers (v1: one call; v2: ``set_weights`` + ``to_neuron``)."""
+        if start_rank_tensor is not None:
+            self.start_rank = int(start_rank_tensor)
+        self.set_weights(checkpoint)
+        self.to_neuron()
+
+    def initialize_with_saved_weights(self, start_rank_tensor: Any = None) -> None:
+        """The modules already hold their weights (built with real weights or restored by :meth:`load`)."""
+        if start_rank_tensor is not None:
+            self.start_rank = int(start_rank_tensor)
+        self._weights_set = True
+        self.to_neuron()
+
+    def initialize_spmd_models(self, states, weights, start_rank_id: int = 0) -> None:
+        self.states = list(states) if states else self.states
+        self.initialize(weights, start_rank_id)
+
+    def mock_initialization(self, mock: bool = True) -> None:
+        """Mark the model initialised without weights (shape-only dry runs)."""
+        self.loaded_on_device = bool(mock)
+
+    def forward_ranked(self, *args, model_name: Optional[str] = None, **kwargs):
+        return self.forward(*args, model_name=model_name, forward_mode="ranked", **kwargs)
+
+    def forward_async(self, *args, model_name: Optional[str] = None, **kwargs):
+        return self.forward(*args, model_name=model_name, forward_mode="async", **kwargs)
+
+    @property
+    def dtype(self) -> Optional[torch.dtype]:
+        for m in self._unique_modules():
+            for p in m.parameters():
+                return p.dtype
+        return None
+
+    @property
+    def config(self):
+        for m in self._unique_modules():
+            if hasattr(m, "config"):
+                return m.config
+        return None
+
     def _find_buffer(self, buffer_key: str) -> torch.Tensor:
         for st in self.states:
             if buffer_key in st:

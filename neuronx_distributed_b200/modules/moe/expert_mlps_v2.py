@@ -184,6 +184,81 @@ class ExpertMLPsV2(ProcessGroupSafeDeepcopy, nn.Module):
         b2e, tp2id, _ = build_block_metadata(expert_index, self.num_experts, block_size or self.bw.block_size)
         return b2e[:num_blocks], tp2id[: num_blocks * (block_size or self.bw.block_size)]
 
+    # ------------------------------------------------------------------ redundant experts (reference :919-1077)
+    # An ``expert_distribution`` may host a hot logical expert on several EP ranks (or twice on one).  Tokens routed to such
+    # an expert are split by token position between its replicas so that nothing is computed twice.
+    @staticmethod
+    def allocate_token_blocks(local_redudancy_degree: torch.Tensor, tokens_per_expert):
+        """``local_redudancy_degree [ep, E]`` (replicas of expert e hosted by EP rank g) → inclusive token-position ranges
+        ``(start [ep, E], end [ep, E])``: expert e's ``tokens_per_expert`` positions are cut into equal blocks, one per
+        replica, handed out in EP-rank order; the last replica also takes the remainder."""
+        deg = local_redudancy_degree.to(torch.int32)
+        total = deg.sum(0)                                                       # replicas per expert
+        upto = torch.cumsum(deg, 0, dtype=torch.int32)
+        before = upto - deg
+        tpe = torch.as_tensor(tokens_per_expert, dtype=torch.int32, device=deg.device)
+        block = (tpe // total.clamp(min=1)).to(torch.int32)
+        rem = (tpe % total.clamp(min=1)).to(torch.int32)
+        start = before * block
+        end = upto * block - 1 + (upto == total).to(torch.int32) * rem
+        return start.to(torch.int32), end.to(torch.int32)
+
+    @staticmethod
+    def generate_local_expert_boolean_mask(local_expert_indices: torch.Tensor, num_experts: int) -> torch.Tensor:
+        """``[slots]`` logical ids of this rank's physical slots → ``[E, slots]`` one-hot-per-column boolean map."""
+        ids = torch.arange(num_experts, dtype=torch.int32, device=local_expert_indices.device).unsqueeze(1)
+        return ids == local_expert_indices.reshape(1, -1).to(torch.int32)
+
+    @staticmethod
+    def generate_mask_with_no_local_redundancy(mask: torch.Tensor) -> torch.Tensor:
+        """Keep only the FIRST slot of every logical expert that appears more than once on this rank."""
+        first = torch.cumsum(mask.to(torch.int32), dim=1) == 1
+        return first & mask
+
+    @staticmethod
+    def generate_local_expert_id_no_local_redundancy(mask: torch.Tensor, device=None) -> torch.Tensor:
+        """``[E, slots]`` map → per-slot logical expert id, ``-1`` for slots masked out as local duplicates."""
+        ids = torch.arange(mask.shape[0], dtype=torch.int32, device=mask.device).unsqueeze(1).expand_as(mask)
+        return torch.where(mask, ids, torch.full_like(ids, -1)).max(dim=0).values
+
+    def generate_local_expert_mask_with_redundancy(self, local_expert_mask: torch.Tensor, local_expert_indices: torch.Tensor,
+                                                   expert_start_ids: torch.Tensor, expert_end_ids: torch.Tensor,
+                                                   num_experts: int, rank) -> torch.Tensor:
+        """``local_expert_mask [T, slots]`` restricted to the token-position range this rank's replica of each expert is
+        responsible for (see :meth:`allocate_token_blocks`), and zeroed for slots that duplicate another local slot."""
+        slots = local_expert_indices.reshape(-1).long()
+        r = int(rank) if not isinstance(rank, torch.Tensor) else rank.reshape(-1)[0].long()
+        lo, hi = expert_start_ids[r, slots][None, :], expert_end_ids[r, slots][None, :]
+        pos = torch.arange(local_expert_mask.shape[0], device=local_expert_mask.device)[:, None]
+        out = local_expert_mask.masked_fill(~((pos >= lo) & (pos <= hi)), 0)
+        uniq = self.generate_local_expert_id_no_local_redundancy(
+            self.generate_mask_with_no_local_redundancy(self.generate_local_expert_boolean_mask(slots, num_experts)))
+        return out.masked_fill((uniq == -1)[None, :], 0)
+
+    @staticmethod
+    def get_block_conditions(block_size: int, num_blocks: int, token_position_to_id: torch.Tensor) -> torch.Tensor:
+        """``[num_blocks]`` int32: 1 where a block holds at least one real token (``-1`` = padding) — lets a persistent
+        grouped-GEMM kernel skip empty blocks without a host round trip."""
+        return (token_position_to_id.view(num_blocks, block_size) != -1).any(dim=1).to(torch.int32)
+
+    def use_index_calc_kernel(self, total_tokens: int) -> bool:
+        """Whether the block / token index computation runs as one device pass (always available here: sort + prefix
+        sums); the reference's extra shape restrictions do not apply, its config switches are honoured."""
+        if self.training or not self.is_prefill or not getattr(self.routed_experts_mlp_config, "use_index_calc_kernel", True):
+            return False
+        return can_use_find_index_kernel(total_tokens, self.bw.block_size, len(self.local_expert_ids))
+
+    def initialize_mlp_op(self, tensor_model_parallel_group=None, expert_model_parallel_group=None, is_prefill: bool = True):
+        """(Re)build the expert weights for the given groups (reference :148-177) and return them."""
+        self.mlp_op = self._build_experts(tensor_model_parallel_group, expert_model_parallel_group, is_prefill)
+        self.local_expert_ids = self.mlp_op.local_expert_ids
+        return self.mlp_op
+
+    def get_blockwise_expert_and_token_mapping_kernel(self, total_tokens: int, num_blocks: int, expert_mask: torch.Tensor,
+                                                      expert_index: torch.Tensor, block_size: Optional[int] = None, **kw):
+        """Same result as :meth:`get_blockwise_expert_and_token_mapping` (both are device passes here)."""
+        return self.get_blockwise_expert_and_token_mapping(total_tokens, num_blocks, expert_mask, expert_index, block_size, **kw)
+
     # ------------------------------------------------------------------ modes
     def setup_all_experts(self, hidden_states, expert_affinities, expert_index, chosen_expert_indices=None, padding_mask=None):
         num_experts = self.num_experts if chosen_expert_indices is None else len(chosen_expert_indices)

@@ -19,6 +19,11 @@ class PPTimeline:
         self._open: Dict[str, Any] = {}
         self.step = 0
 
+    @property
+    def should_record(self) -> bool:
+        """Recording is on whenever a trace file was given (the reference force-disables its pipeline timeline)."""
+        return self.enabled
+
     def mark_event_start(self, label: str) -> None:
         if not self.enabled:
             return

@@ -44,6 +44,12 @@ class NxDCheckpointWrapper(nn.Module):
             return self._checkpoint_fn(self._checkpoint_wrapped_module, *args, **self._checkpoint_fn_kwargs, **kwargs)
         return checkpoint(self._checkpoint_wrapped_module, *args, use_reentrant=False, **kwargs)
 
+    def named_modules(self, *args, **kwargs):
+        """Module names without the wrapper's prefix, so name-based tools (LoRA targets, tensor capture, pipeline cuts) see
+        the same names with and without activation checkpointing."""
+        for name, m in super().named_modules(*args, **kwargs):
+            yield name.replace(_PREFIX, ""), m              # children lose the prefix; the wrapped module keeps its own name
+
     def named_parameters(self, *args, **kwargs):
         for name, p in super().named_parameters(*args, **kwargs):
             yield name.replace(_PREFIX, ""), p
