@@ -1,8 +1,12 @@
 #!/usr/bin/env python
-"""Llama inference with a LoRA adapter on the attention projections (adapter merged for serving, then unmerged) — counterpart of
-the reference's ``examples/inference/run_llama_lora.py``.
+"""Llama inference with LoRA — counterpart of the reference's ``examples/inference/run_llama_lora.py``.
+
+* default: ONE adapter on the attention / MLP output projections, served merged and un-merged;
+* ``--multi_lora N``: N adapters resident at once (``modules.lora.serving``), a batch whose requests use different adapters
+  (and one request the base model) is decoded in one pass.
 
   python examples/inference/run_llama_lora.py --lora_rank 8
+  python examples/inference/run_llama_lora.py --multi_lora 3
 """
 import argparse
 import os
@@ -29,6 +33,7 @@ def main():
     p.add_argument("--lora_rank", type=int, default=8)
     p.add_argument("--prompt_length", type=int, default=16)
     p.add_argument("--max_new_tokens", type=int, default=8)
+    p.add_argument("--multi_lora", type=int, default=0, help="number of adapters served concurrently (0 = single merged adapter)")
     a = p.parse_args()
     dev = init_distributed()
     ps.initialize_model_parallel(tensor_model_parallel_size=a.tp_degree)
@@ -37,6 +42,8 @@ def main():
     cfg = LlamaConfig(vocab_size=4096, hidden_size=256, intermediate_size=704, num_hidden_layers=2, num_attention_heads=8,
                       dtype=dtype, device=dev, max_position_embeddings=L)
     torch.manual_seed(0)
+    if a.multi_lora > 0:
+        return multi_lora(a, cfg, dev, L)
     model = LlamaForInference(cfg, batch_size=1, max_seq_len=L).eval()
     prompt = torch.randint(0, cfg.vocab_size, (1, a.prompt_length), device=dev)
     base = model.generate(prompt, a.max_new_tokens)
@@ -56,6 +63,36 @@ def main():
     if dist.get_rank() == 0:
         print(f"{n_adapters} LoRA adapters (rank {a.lora_rank}); merged == unmerged adapter output: {bool(torch.equal(with_adapter, merged))}; "
               f"differs from base model: {not bool(torch.equal(with_adapter, base))}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def multi_lora(a, cfg, dev, L):
+    from neuronx_distributed_b200.modules.lora import LoraServingConfig, LoraServingModel
+
+    n, B = a.multi_lora, a.multi_lora + 1
+    model = LlamaForInference(cfg, batch_size=B, max_seq_len=L).eval()
+    scfg = LoraServingConfig(max_loras=n, max_lora_rank=a.lora_rank, target_modules=["o_proj", "down_proj"])
+    model.lm = LoraServingModel(model.lm, scfg)
+    g = torch.Generator().manual_seed(1)
+    for slot in range(n):                           # stand-ins for trained adapters: full (un-sharded) HF-PEFT style tensors
+        sd = {}
+        for name, layer in model.lm.lora_layers().items():
+            base = layer.base_layer
+            sd[f"base_model.model.{name}.lora_A.weight"] = torch.randn(a.lora_rank, base.input_size, generator=g) * 0.05
+            sd[f"base_model.model.{name}.lora_B.weight"] = torch.randn(base.output_size, a.lora_rank, generator=g) * 0.05
+        model.lm.load_adapter(slot, {"state_dict": sd, "lora_config": {"lora_alpha": 2 * a.lora_rank, "lora_rank": a.lora_rank}})
+    prompt = torch.randint(0, cfg.vocab_size, (1, a.prompt_length), device=dev).expand(B, -1).contiguous()
+    ids = torch.tensor(list(range(n)) + [-1], device=dev)           # request i uses adapter i, the last one the base model
+    model.lm.set_adapter_ids(ids)
+    mixed = model.generate(prompt, a.max_new_tokens)
+    model.lm.set_adapter_ids(None)
+    model.kv.reset()
+    base = model.generate(prompt, a.max_new_tokens)
+    if dist.get_rank() == 0:
+        same_as_base = [bool(torch.equal(mixed[i], base[i])) for i in range(B)]
+        print(f"{n} adapters resident, batch of {B} requests decoded together; request equals base-model output: {same_as_base} "
+              f"(expected {[False] * n + [True]})", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

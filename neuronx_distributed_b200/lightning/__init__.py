@@ -9,3 +9,4 @@ from .logger import NeuronTensorBoardLogger  # noqa: F401
 from .callbacks import NeuronHooksCallback, NeuronTQDMProgressBar  # noqa: F401
 from .accelerator import NeuronXLAAccelerator  # noqa: F401
 from .precision_plugin import NeuronXLAPrecisionPlugin  # noqa: F401
+from .trainer import Trainer  # noqa: F401

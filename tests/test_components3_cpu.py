@@ -88,5 +88,58 @@ def _lightning(rank, world):
     assert isinstance(HAVE_LIGHTNING, bool)
 
 
+def _lightning_fit(rank, world, tmp):
+    """The package's own fit loop drives strategy → module → callbacks → logger → checkpoint IO in Lightning's call order,
+    and resumes from the checkpoint it wrote."""
+    import os
+
+    from neuronx_distributed_b200.lightning import (NeuronCheckpointIO, NeuronLTModule, NeuronTensorBoardLogger, NxDStrategy, Trainer)
+    from neuronx_distributed_b200.models.llama import LlamaConfig, LlamaForCausalLM
+    from neuronx_distributed_b200.trainer import neuronx_distributed_config
+
+    cfg = neuronx_distributed_config(tensor_parallel_size=world, optimizer_config={"zero_one_enabled": True, "grad_clipping": True})
+    mcfg = LlamaConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=1, num_attention_heads=4,
+                       dtype=torch.float32, max_position_embeddings=16)
+
+    def model_fn():
+        torch.manual_seed(3)
+        return LlamaForCausalLM(mcfg)
+
+    ids = torch.randint(0, 64, (2, 16), generator=torch.Generator().manual_seed(9))
+    batches = [{"input_ids": ids, "labels": ids}] * 8
+    events = []
+
+    class Cb:
+        def on_train_start(self, trainer, module):
+            events.append("start")
+
+        def on_train_batch_end(self, trainer, module, *a):
+            events.append("batch")
+
+        def on_train_end(self, trainer, module):
+            events.append("end")
+
+    def run(max_steps, resume=None):
+        mod = NeuronLTModule(cfg, model_fn, torch.optim.AdamW, opt_kwargs={"lr": 1e-2}, grad_accum_steps=2)
+        tr = Trainer(strategy=NxDStrategy(nxd_config=cfg), callbacks=[Cb()], logger=NeuronTensorBoardLogger(tmp, "fit"),
+                     max_steps=max_steps, default_root_dir=os.path.join(tmp, "ck"), every_n_train_steps=2,
+                     plugins=[NeuronCheckpointIO(save_load_xser=True)])
+        tr.fit(mod, train_dataloaders=batches, ckpt_path=resume)
+        return tr, mod
+
+    tr, mod = run(4)
+    assert tr.global_step == 4 and events[0] == "start" and events[-1] == "end" and events.count("batch") == 8
+    assert "loss" in tr.callback_metrics and os.path.isfile(os.path.join(tmp, "ck", "step_4", "done"))
+    loss4 = float(mod.model.run_eval(input_ids=ids, labels=ids))
+    events.clear()
+    tr2, mod2 = run(5, resume=os.path.join(tmp, "ck", "step_4"))
+    assert tr2.global_step == 5 and events.count("batch") == 2            # resumed at 4 → one more optimizer step (2 micro-batches)
+    assert float(mod2.model.run_eval(input_ids=ids, labels=ids)) < loss4
+
+
+def test_lightning_fit_loop_checkpoint_resume(tmp_path):
+    run_distributed(_lightning_fit, 2, str(tmp_path), timeout=180)
+
+
 def test_lightning_module_trains_without_lightning_installed():
     run_distributed(_lightning, 2, timeout=120)

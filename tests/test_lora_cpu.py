@@ -121,3 +121,81 @@ def _tp_lora(rank, world, tmp):
 
 def test_tp_lora(tmp_path):
     run_distributed(_tp_lora, 2, str(tmp_path), timeout=90)
+
+
+def _multi_lora(rank, world):
+    """Mixed-adapter batch == per-request single-adapter results; full adapters are sharded on load; TP matches dense."""
+    import json, os, tempfile
+
+    from neuronx_distributed_b200.modules.lora import LoraServingConfig, LoraServingModel
+    from neuronx_distributed_b200.parallel_layers import ColumnParallelLinear, RowParallelLinear, mappings
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.parallel_layers.utils import gather_full_weight
+    import torch.distributed as dist
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    H, F, L = 8, 16, 3
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.up_proj = ColumnParallelLinear(H, F, bias=False, gather_output=False)
+            self.down_proj = RowParallelLinear(F, H, bias=False, input_is_parallel=True)
+
+        def forward(self, x):
+            return self.down_proj(torch.tanh(self.up_proj(x)))
+
+    torch.manual_seed(0)
+    net = Net().eval()
+    full_up = gather_full_weight([t for t in _gather(net.up_proj.weight.data, world)], 0, 1)
+    full_dn = gather_full_weight([t for t in _gather(net.down_proj.weight.data, world)], 1, 1)
+    cfg = LoraServingConfig(max_loras=L, max_lora_rank=4, target_modules=["up_proj", "down_proj"])
+    assert LoraServingConfig.from_json_string(cfg.to_json_string()).max_lora_rank == 4
+    sm = LoraServingModel(net, cfg).eval()
+    g = torch.Generator().manual_seed(7)
+    adapters = []
+    for slot, r in enumerate((2, 4)):                                   # two adapters with different ranks (slot 2 stays empty)
+        sd = {"base_model.model.up_proj.lora_A.weight": torch.randn(r, H, generator=g), "base_model.model.up_proj.lora_B.weight": torch.randn(F, r, generator=g),
+              "base_model.model.down_proj.lora_A.weight": torch.randn(r, F, generator=g), "base_model.model.down_proj.lora_B.weight": torch.randn(H, r, generator=g)}
+        adapters.append((sd, 2.0 * r))
+        sm.load_adapter(slot, {"state_dict": sd, "lora_config": {"lora_alpha": 2.0 * r, "lora_rank": r}})
+    assert sm.slots[1]["modules"] == 2 and sm.lora_layers()["up_proj"].lora_B.shape == (L, F // world, 4)
+
+    def dense(x, which):
+        wu, wd = full_up.clone(), full_dn.clone()
+        if which >= 0:
+            sd, alpha = adapters[which]
+            r = sd["base_model.model.up_proj.lora_A.weight"].shape[0]
+            wu += (alpha / r) * sd["base_model.model.up_proj.lora_B.weight"] @ sd["base_model.model.up_proj.lora_A.weight"]
+            wd += (alpha / r) * sd["base_model.model.down_proj.lora_B.weight"] @ sd["base_model.model.down_proj.lora_A.weight"]
+        return torch.tanh(x @ wu.t()) @ wd.t()
+
+    x = torch.randn(4, 5, H, generator=torch.Generator().manual_seed(3))
+    ids = [1, -1, 0, 1]
+    with torch.no_grad():
+        y = sm(x, adapter_ids=ids)
+        want = torch.stack([dense(x[b], ids[b]) for b in range(4)])
+        torch.testing.assert_close(y, want, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(sm(x), dense(x, -1), rtol=1e-4, atol=1e-4)            # no ids → base model
+        torch.testing.assert_close(sm(x, adapter_ids=0), dense(x, 0), rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(sm(x, adapter_ids=[2, 2, 2, 2]), dense(x, -1), rtol=1e-4, atol=1e-4)   # empty slot = zeros
+        sm.unload_adapter(1)
+        torch.testing.assert_close(sm(x, adapter_ids=ids), torch.stack([dense(x[b], ids[b] if ids[b] != 1 else -1) for b in range(4)]),
+                                   rtol=1e-4, atol=1e-4)
+    try:
+        sm.load_adapter(0, {"x.lora_A.weight": torch.zeros(2, 2)})
+        raise SystemExit("expected ValueError")
+    except ValueError:
+        pass
+
+
+def _gather(t, world):
+    import torch.distributed as dist
+
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t.contiguous())
+    return out
+
+
+def test_multi_adapter_serving_tp2():
+    run_distributed(_multi_lora, 2, timeout=120)
