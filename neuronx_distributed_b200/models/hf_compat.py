@@ -34,7 +34,8 @@ import torch.distributed as dist
 from ..parallel_layers import parallel_state as ps
 from ..scripts.checkpoint_converter import gqa_q_head_permutation
 
-__all__ = ["config_from_hf", "hf_to_nxd_state_dict", "nxd_to_hf_state_dict", "read_hf_state_dict", "load_hf_checkpoint",
+__all__ = ["config_from_hf", "hf_to_nxd_state_dict", "nxd_to_hf_state_dict", "hf_to_nxd_bert_state_dict", "nxd_to_hf_bert_state_dict",
+           "hf_to_nxd_vit_state_dict", "nxd_to_hf_vit_state_dict", "read_hf_state_dict", "load_hf_checkpoint",
            "gather_full_state_dict", "save_hf_checkpoint"]
 
 
@@ -284,6 +285,115 @@ def nxd_to_hf_state_dict(full_sd: Dict[str, torch.Tensor], cfg, kv_size_multipli
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# encoder families (BERT, ViT) and GPT-NeoX: pure renames + QKV fusion; GPT-NeoX already uses the HF names and layout
+# ---------------------------------------------------------------------------------------------------------------------
+_BERT_RENAMES = [
+    (r"^bert\.encoder\.layer\.(\d+)\.attention\.self\.(query|key|value)\.", r"bert.layers.\1.attention.\2."),
+    (r"^bert\.encoder\.layer\.(\d+)\.attention\.output\.dense\.", r"bert.layers.\1.attention.dense."),
+    (r"^bert\.encoder\.layer\.(\d+)\.attention\.output\.LayerNorm\.", r"bert.layers.\1.attention_norm."),
+    (r"^bert\.encoder\.layer\.(\d+)\.intermediate\.dense\.", r"bert.layers.\1.intermediate."),
+    (r"^bert\.encoder\.layer\.(\d+)\.output\.dense\.", r"bert.layers.\1.output."),
+    (r"^bert\.encoder\.layer\.(\d+)\.output\.LayerNorm\.", r"bert.layers.\1.output_norm."),
+    (r"^bert\.pooler\.dense\.", "bert.pooler."),
+    (r"^cls\.predictions\.transform\.dense\.", "transform."),
+    (r"^cls\.predictions\.transform\.LayerNorm\.", "transform_norm."),
+    (r"^cls\.predictions\.decoder\.", "decoder."),
+    (r"^cls\.seq_relationship\.", "seq_relationship."),
+]
+_BERT_INVERSE = [
+    (r"^bert\.layers\.(\d+)\.attention\.(query|key|value)\.", r"bert.encoder.layer.\1.attention.self.\2."),
+    (r"^bert\.layers\.(\d+)\.attention\.dense\.", r"bert.encoder.layer.\1.attention.output.dense."),
+    (r"^bert\.layers\.(\d+)\.attention_norm\.", r"bert.encoder.layer.\1.attention.output.LayerNorm."),
+    (r"^bert\.layers\.(\d+)\.intermediate\.", r"bert.encoder.layer.\1.intermediate.dense."),
+    (r"^bert\.layers\.(\d+)\.output\.", r"bert.encoder.layer.\1.output.dense."),
+    (r"^bert\.layers\.(\d+)\.output_norm\.", r"bert.encoder.layer.\1.output.LayerNorm."),
+    (r"^bert\.pooler\.", "bert.pooler.dense."),
+    (r"^transform\.", "cls.predictions.transform.dense."),
+    (r"^transform_norm\.", "cls.predictions.transform.LayerNorm."),
+    (r"^decoder\.", "cls.predictions.decoder."),
+    (r"^seq_relationship\.", "cls.seq_relationship."),
+]
+
+
+def _rename(sd: Dict[str, torch.Tensor], rules) -> Dict[str, torch.Tensor]:
+    out = {}
+    for k, v in sd.items():
+        for pat, rep in rules:
+            k2, n = re.subn(pat, rep, k)
+            if n:
+                k = k2
+                break
+        out[k] = v
+    return out
+
+
+def hf_to_nxd_bert_state_dict(hf_sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """HF ``BertForPreTraining`` names → ``models.bert.BertForPreTraining`` (same tensors; ``cls.predictions.bias`` is the
+    decoder bias; ``position_ids`` buffers are dropped)."""
+    out = _rename({k: v for k, v in hf_sd.items() if not k.endswith("position_ids")}, _BERT_RENAMES)
+    if "cls.predictions.bias" in out:
+        out.setdefault("decoder.bias", out["cls.predictions.bias"])
+        del out["cls.predictions.bias"]
+    out.setdefault("decoder.weight", out.get("bert.embeddings.word_embeddings.weight"))
+    return out
+
+
+def nxd_to_hf_bert_state_dict(full_sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    out = _rename(full_sd, _BERT_INVERSE)
+    if "cls.predictions.decoder.bias" in out:
+        out["cls.predictions.bias"] = out["cls.predictions.decoder.bias"]
+    return out
+
+
+def hf_to_nxd_vit_state_dict(hf_sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """HF ``ViTForImageClassification`` names → ``models.vit`` (query / key / value fused to one ``qkv`` ``[q; k; v]``,
+    sharded with stride 3)."""
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in hf_sd.items():
+        k = k[len("vit."):] if k.startswith("vit.") else k
+        k = k.replace("embeddings.patch_embeddings.projection.", "embeddings.projection.")
+        k = re.sub(r"^encoder\.layer\.(\d+)\.", r"layers.\1.", k)
+        k = k.replace("attention.output.dense.", "out.").replace("intermediate.dense.", "fc1.").replace("output.dense.", "fc2.")
+        out[k] = v
+    for k in [k for k in out if k.endswith("attention.attention.query.weight")]:
+        base = k[: -len("attention.attention.query.weight")]
+        for kind in ("weight", "bias"):
+            parts = [out.pop(f"{base}attention.attention.{p}.{kind}", None) for p in ("query", "key", "value")]
+            if parts[0] is not None:
+                out[f"{base}qkv.{kind}"] = torch.cat(parts, 0)
+    return out
+
+
+def nxd_to_hf_vit_state_dict(full_sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in full_sd.items():
+        m = re.match(r"^layers\.(\d+)\.(.*)$", k)
+        if m is None:
+            k2 = k if k.startswith("classifier.") else "vit." + k.replace("embeddings.projection.", "embeddings.patch_embeddings.projection.")
+            out[k2] = v
+            continue
+        base, rest = f"vit.encoder.layer.{m.group(1)}.", m.group(2)
+        if rest.startswith("qkv."):
+            kind = rest.split(".", 1)[1]
+            for p, t in zip(("query", "key", "value"), v.chunk(3, 0)):
+                out[f"{base}attention.attention.{p}.{kind}"] = t
+        else:
+            rest = rest.replace("out.", "attention.output.dense.", 1) if rest.startswith("out.") else rest
+            rest = rest.replace("fc1.", "intermediate.dense.", 1) if rest.startswith("fc1.") else rest
+            rest = rest.replace("fc2.", "output.dense.", 1) if rest.startswith("fc2.") else rest
+            out[base + rest] = v
+    return out
+
+
+def _encoder_family(model) -> Optional[str]:
+    name = type(model).__name__.lower()
+    for fam in ("bert", "vit", "gptneox"):
+        if fam in name.replace("_", ""):
+            return fam
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # files
 # ---------------------------------------------------------------------------------------------------------------------
 def read_hf_state_dict(path: str) -> Dict[str, torch.Tensor]:
@@ -365,9 +475,17 @@ def load_hf_checkpoint(model, path_or_state, cfg=None, strict: bool = True):
     ``load_state_dict`` result."""
     from ..inference.sharding import shard_state_dict_for_rank
 
+    hf_sd = path_or_state if isinstance(path_or_state, dict) else read_hf_state_dict(os.fspath(path_or_state))
+    fam = _encoder_family(model)
+    if fam is not None:                               # BERT / ViT: renames (+ QKV fusion); GPT-NeoX: HF names as they are
+        full = {"bert": hf_to_nxd_bert_state_dict, "vit": hf_to_nxd_vit_state_dict, "gptneox": dict}[fam](hf_sd)
+        full = {k: v for k, v in full.items() if not k.endswith(("rotary_emb.inv_freq", "attention.bias", "attention.masked_bias"))}
+        want = model.state_dict()
+        local = shard_state_dict_for_rank(model, full, ps.get_tensor_model_parallel_rank(), ps.get_tensor_model_parallel_size())
+        local = {k: (v.to(want[k].dtype) if k in want and isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in local.items()}
+        return model.load_state_dict(local, strict=strict)
     root, dec, head = _layout(model)
     cfg = cfg or _config_of(model, root)
-    hf_sd = path_or_state if isinstance(path_or_state, dict) else read_hf_state_dict(os.fspath(path_or_state))
     full = _to_model_keys(hf_to_nxd_state_dict(hf_sd, cfg, **_kv_args(root)), dec, head)
     rank, world = ps.get_tensor_model_parallel_rank(), ps.get_tensor_model_parallel_size()
     local = shard_state_dict_for_rank(root, full, rank, world)

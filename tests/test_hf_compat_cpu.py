@@ -170,3 +170,71 @@ def test_moe_convert_checkpoints_cli(tmp_path):
     subprocess.run(cli + ["--convert_to_full_state", "--input_dir", out, "--output_dir", merged], check=True, timeout=300)
     back = torch.load(os.path.join(merged, "pytorch_model.bin"), weights_only=True)
     assert set(back) == set(disk) and all(torch.equal(back[k], disk[k]) for k in disk)
+
+
+def _encoders(rank, world):
+    """BERT, ViT and GPT-NeoX: HF state dict → TP-sharded built-in model → same outputs as ``transformers``; and back."""
+    from neuronx_distributed_b200.models import bert, gpt_neox, hf_compat, vit
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.parallel_layers.mappings import gather_from_tensor_model_parallel_region as gather
+
+    ps.initialize_model_parallel(world)
+    torch.manual_seed(0)
+    ids = torch.randint(0, 64, (2, 16), generator=torch.Generator().manual_seed(1))
+
+    # ---- BERT (MLM + NSP heads)
+    hc = transformers.BertConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                 max_position_embeddings=32, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, attn_implementation="eager")
+    hf = transformers.BertForPreTraining(hc).eval()
+    with torch.no_grad():
+        hf.cls.predictions.bias.normal_()                                     # tied to decoder.bias in HF
+    m = bert.BertForPreTraining(bert.BertConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                                max_position_embeddings=32, hidden_dropout_prob=0.0, dtype=torch.float32)).eval()
+    res = hf_compat.load_hf_checkpoint(m, hf.state_dict())
+    assert not res.missing_keys and not res.unexpected_keys, res
+    tt = torch.zeros_like(ids)
+    with torch.no_grad():
+        ref = hf(input_ids=ids, token_type_ids=tt)
+        _, (mlm, nsp) = m(ids, tt)
+    assert float((gather(mlm) - ref.prediction_logits).abs().max()) < 2e-5
+    assert float((nsp - ref.seq_relationship_logits).abs().max()) < 2e-5
+
+    # ---- ViT
+    hc = transformers.ViTConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4, image_size=32, patch_size=8,
+                                num_labels=10, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, attn_implementation="eager")
+    hf = transformers.ViTForImageClassification(hc).eval()
+    v = vit.ViTForImageClassification(vit.ViTConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4, image_size=32,
+                                                    patch_size=8, num_labels=10, dtype=torch.float32)).eval()
+    res = hf_compat.load_hf_checkpoint(v, hf.state_dict())
+    assert not res.missing_keys and not res.unexpected_keys, res
+    px = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        assert float((v(px) - hf(pixel_values=px).logits).abs().max()) < 2e-5
+    sd = hf.state_dict()
+    back = hf_compat.nxd_to_hf_vit_state_dict(hf_compat.hf_to_nxd_vit_state_dict(sd))
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+
+    # ---- GPT-NeoX (HF names and per-head interleaved QKV are used as they are)
+    hc = transformers.GPTNeoXConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                    max_position_embeddings=32, rotary_pct=0.25, attn_implementation="eager")
+    hf = transformers.GPTNeoXForCausalLM(hc).eval()
+    n = gpt_neox.GPTNeoXForCausalLM(gpt_neox.GPTNeoXConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                                                           num_attention_heads=4, max_position_embeddings=32, dtype=torch.float32)).eval()
+    res = hf_compat.load_hf_checkpoint(n, hf.state_dict())
+    assert not res.missing_keys and not res.unexpected_keys, res
+    with torch.no_grad():
+        out = n(ids)
+    lg = gather(out[1] if isinstance(out, tuple) else out)
+    lg = lg.transpose(0, 1) if lg.shape[0] == 16 else lg
+    assert float((lg - hf(ids).logits).abs().max()) < 2e-5
+
+    # BERT names round trip
+    hb = transformers.BertForPreTraining(transformers.BertConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=1,
+                                                                 num_attention_heads=4, max_position_embeddings=32)).state_dict()
+    hb = {k: v for k, v in hb.items() if not k.endswith("position_ids")}
+    back = hf_compat.nxd_to_hf_bert_state_dict(hf_compat.hf_to_nxd_bert_state_dict(hb))
+    assert set(back) == set(hb) and all(torch.equal(back[k], hb[k]) for k in hb)
+
+
+def test_hf_bert_vit_neox_parity():
+    run_distributed(_encoders, 2, timeout=300)
