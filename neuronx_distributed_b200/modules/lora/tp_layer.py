@@ -82,6 +82,8 @@ class LoraGQAQKVParallelLinear(LoraLayer):
 
     def forward(self, x: torch.Tensor):
         q, k, v = self.base_layer(x)
+        if self.merged:
+            return q, k, v
         from ...parallel_layers import mappings
 
         xin = self.dropout(x)
@@ -92,5 +94,39 @@ class LoraGQAQKVParallelLinear(LoraLayer):
         s = self.scaling
         return q + self.lora_B_q(a) * s, k + self.lora_B_k(a) * s, v + self.lora_B_v(a) * s
 
-    def merge(self) -> None:
-        raise NotImplementedError("merging into fused GQA-QKV weights is done offline by the checkpoint converter")
+    def get_qkv(self, layer):
+        """The (local) Q / K / V weights of a GQA-QKV layer as three views (reference ``lora/tp_layer.py:137-146``); for the
+        fused layout these are slices of ``weight_qkv`` so in-place updates land in the fused parameter."""
+        if getattr(layer, "fuse_qkv", False):
+            sizes = [layer.q_output_size_per_partition, layer.kv_output_size_per_partition, layer.kv_output_size_per_partition]
+            return torch.split(layer.weight_qkv, sizes, dim=0)
+        return layer.weight_q, layer.weight_k, layer.weight_v
+
+    def get_delta_weight(self):
+        """``(ΔW_q, ΔW_k, ΔW_v)`` of this rank: ``B_x · A · scaling`` (``B_x`` is the local column shard)."""
+        a = self.lora_A.weight
+        return tuple((b.weight @ a) * self.scaling for b in (self.lora_B_q, self.lora_B_k, self.lora_B_v))
+
+    def merge(self, safe_merge: bool = False) -> None:
+        """Fold the adapter into the base Q / K / V shards (reference :100-120).  ``safe_merge`` checks for non-finite values
+        before touching the weights."""
+        if self.merged:
+            return
+        deltas = self.get_delta_weight()
+        targets = self.get_qkv(self.base_layer)
+        if safe_merge:
+            for t, d in zip(targets, deltas):
+                if not torch.isfinite(t.data + d.to(t.dtype)).all():
+                    raise ValueError("NaNs detected in the merged weights. The adapter seems to be broken")
+        with torch.no_grad():
+            for t, d in zip(targets, deltas):
+                t.data.add_(d.to(t.dtype))
+        self.merged = True
+
+    def unmerge(self) -> None:
+        if not self.merged:
+            return
+        with torch.no_grad():
+            for t, d in zip(self.get_qkv(self.base_layer), self.get_delta_weight()):
+                t.data.sub_(d.to(t.dtype))
+        self.merged = False

@@ -24,6 +24,10 @@ class MoEFusedTKG(nn.Module):
         object.__setattr__(self, "_norm", rmsnorm)
         self.config = config or MoEFusedTKGConfig()
 
+    def preshard_hook(self, model_state_dict, prefix: str) -> None:
+        """Nothing to re-arrange: the block holds references to the prefill modules' parameters (whose own hooks run) and
+        owns none itself (reference ``moe_fused_tkg.py:449-450``)."""
+
     def forward(self, hidden_states: torch.Tensor, residual: Optional[torch.Tensor] = None):
         x = hidden_states if residual is None else hidden_states + residual
         h = self._norm(x) if self._norm is not None else x

@@ -200,54 +200,187 @@ class wait_decrementing_with_jitter:  # noqa: N801  (reference spelling, :236-24
         return float(random.randint(1, max(1, math.ceil(self.max_sleep / max(1, int(attempt))))))
 
 
-class S3CheckpointStorage(BaseCheckpointStorage):
-    """``s3://bucket/prefix`` storage (reference :236-605).  Requires boto3."""
+_s3_resource = None
+_s3_client = None
+_s3_transfer_manager = None
 
-    MAX_RETRY = 10
 
-    def __init__(self, dirname: str):
-        super().__init__(dirname)
-        try:
-            import boto3  # type: ignore
-        except ImportError as e:  # pragma: no cover - boto3 is not in the offline image
-            raise RuntimeError("S3CheckpointStorage needs boto3, which is not installed in this environment") from e
-        assert dirname.startswith("s3://")
-        rest = dirname[len("s3://"):]
-        self.bucket, _, self.prefix = rest.partition("/")
-        self.s3 = boto3.client("s3")
+def _retrying(fn: Callable) -> Callable:
+    """Call ``fn`` again (≤ ``MAX_RETRY`` attempts, decreasing jitter) while S3 answers with a back-off error."""
+    import functools
 
-    def _key(self, name: str) -> str:
-        return os.path.normpath(os.path.join(self.prefix, name)).lstrip("./")
-
-    def _retry(self, fn: Callable, *a, **k):  # pragma: no cover - needs network
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
         wait = wait_decrementing_with_jitter(max_sleep=int(os.environ.get("WORLD_SIZE", "50000")) / 10000)
-        for attempt in range(1, self.MAX_RETRY + 1):
+        for attempt in range(1, S3CheckpointStorage.MAX_RETRY + 1):
             try:
                 return fn(*a, **k)
             except Exception as e:  # noqa: BLE001
-                if not is_slow_down_error(e) or attempt == self.MAX_RETRY:
+                if not is_slow_down_error(e) or attempt == S3CheckpointStorage.MAX_RETRY:
                     raise
-                time.sleep(wait(attempt))
+                time.sleep(wait(attempt) * S3CheckpointStorage.SLEEP_SCALE)
+    return wrapped
 
-    def dir_exists(self, dirname: str) -> bool:  # pragma: no cover
-        r = self._retry(self.s3.list_objects_v2, Bucket=self.bucket, Prefix=self._key(dirname).rstrip("/") + "/", MaxKeys=1)
-        return r.get("KeyCount", 0) > 0
 
-    def file_exists(self, filename: str) -> bool:  # pragma: no cover
-        try:
-            self._retry(self.s3.head_object, Bucket=self.bucket, Key=self._key(filename))
-            return True
-        except Exception:  # noqa: BLE001
-            return False
+class S3CheckpointStorage(BaseCheckpointStorage):
+    """``s3://bucket/prefix`` storage (reference :286-608).  Needs ``boto3`` (import-gated: not part of the offline image; the
+    tests run this class against an in-memory stand-in of the client).  One client per process; every request goes through
+    the throttling-aware retry."""
 
-    def is_checkpoint_xser(self, dirname: str) -> bool:  # pragma: no cover
-        r = self._retry(self.s3.list_objects_v2, Bucket=self.bucket, Prefix=self._key(dirname).rstrip("/") + "/")
-        return any(".tensors/" in o["Key"] for o in r.get("Contents", []))
+    S3_PATH_PREFIX = "s3://"
+    MAX_RETRY = 10
+    SLEEP_SCALE = 1.0                        # tests set this to 0 so that injected SlowDown errors do not sleep
+    retry_with_jitter = staticmethod(_retrying)
 
-    def list_dirs(self, dirname: str) -> List[str]:  # pragma: no cover
-        pfx = self._key(dirname).rstrip("/") + "/" if dirname not in (".", "") else (self.prefix.rstrip("/") + "/" if self.prefix else "")
-        r = self._retry(self.s3.list_objects_v2, Bucket=self.bucket, Prefix=pfx, Delimiter="/")
-        return [c["Prefix"][len(pfx):].rstrip("/") for c in r.get("CommonPrefixes", [])]
+    def __init__(self, dirname: str, crt_config: Optional[dict] = None):
+        super().__init__(dirname)
+        self._bucket, self._base_key = S3CheckpointStorage.parse_path(dirname)
+        if self._base_key and not self._base_key.endswith("/"):
+            self._base_key += "/"
+        self.crt_config = dict(crt_config or {})
+        S3CheckpointStorage.get_client()     # fail early (clear message) when boto3 is missing
+
+    # ---- names ---------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def parse_path(s3_path: str):
+        """``"s3://bucket/a/b"`` → ``("bucket", "a/b")``; ``"s3://bucket"`` → ``("bucket", None)``."""
+        head = S3CheckpointStorage.S3_PATH_PREFIX
+        if not s3_path.startswith(head):
+            raise RuntimeError(f"Error: invalid s3 path: {s3_path} because it does not start with {head}")
+        rest = s3_path[len(head):]
+        if not rest:
+            raise RuntimeError(f"Error: invalid s3 path: {s3_path} that is empty")
+        bucket, sep, key = rest.partition("/")
+        return bucket, (key or None) if sep else None
+
+    def convert_path_to_key(self, path: str) -> str:
+        path = os.path.normpath(path).lstrip("./") if path not in ("", ".") else ""
+        return path if self._base_key is None else self._base_key + path
+
+    _key = convert_path_to_key
+
+    @property
+    def bucket(self) -> str:
+        return self._bucket
+
+    @property
+    def prefix(self) -> str:
+        return (self._base_key or "").rstrip("/")
+
+    # ---- client --------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _ensure_s3_resource_and_client():
+        global _s3_resource, _s3_client
+        if _s3_client is None:
+            try:
+                import boto3  # type: ignore
+            except ImportError as e:
+                raise RuntimeError("S3CheckpointStorage needs boto3, which is not installed in this environment") from e
+            try:
+                import botocore.config  # type: ignore
+
+                cfg = botocore.config.Config(max_pool_connections=max(1, (os.cpu_count() or 1) // 4))
+                _s3_resource = boto3.Session().resource("s3", config=cfg)
+                _s3_client = _s3_resource.meta.client
+            except ImportError:
+                _s3_client = boto3.client("s3")
+                _s3_resource = None
+        return _s3_resource, _s3_client
+
+    @staticmethod
+    def get_resource():
+        return S3CheckpointStorage._ensure_s3_resource_and_client()[0]
+
+    @staticmethod
+    def get_client():
+        return S3CheckpointStorage._ensure_s3_resource_and_client()[1]
+
+    @property
+    def s3(self):
+        return S3CheckpointStorage.get_client()
+
+    def get_transfer_manager(self, config=None):
+        """Process-wide ``s3transfer`` manager for multi-part transfers (``None`` when s3transfer is unavailable: single
+        requests are used then)."""
+        global _s3_transfer_manager
+        if _s3_transfer_manager is None:
+            try:
+                from boto3.s3.transfer import TransferConfig, create_transfer_manager  # type: ignore
+
+                _s3_transfer_manager = create_transfer_manager(self.s3, config or TransferConfig())
+            except Exception:  # noqa: BLE001
+                _s3_transfer_manager = None
+        return _s3_transfer_manager
+
+    def _retry(self, fn: Callable, *a, **k):
+        return _retrying(fn)(*a, **k)
+
+    def _list(self, prefix: str, delimiter: Optional[str] = None, max_keys: Optional[int] = None):
+        """All pages of ``list_objects_v2`` → (contents, common prefixes)."""
+        contents, prefixes, token = [], [], None
+        while True:
+            kw = dict(Bucket=self._bucket, Prefix=prefix)
+            if delimiter:
+                kw["Delimiter"] = delimiter
+            if max_keys:
+                kw["MaxKeys"] = max_keys
+            if token:
+                kw["ContinuationToken"] = token
+            r = self._retry(self.s3.list_objects_v2, **kw)
+            contents += r.get("Contents", [])
+            prefixes += [c["Prefix"] for c in r.get("CommonPrefixes", [])]
+            token = r.get("NextContinuationToken")
+            if not token or (max_keys and len(contents) + len(prefixes) >= max_keys):
+                return contents, prefixes
+
+    def _dir_key(self, dirname: str) -> str:
+        k = self.convert_path_to_key(dirname)
+        return k if (not k or k.endswith("/")) else k + "/"
+
+    # ---- BaseCheckpointStorage -----------------------------------------------------------------------------------------
+    def dir_exists(self, dirname: str) -> bool:
+        contents, prefixes = self._list(self._dir_key(dirname), max_keys=1)
+        return bool(contents or prefixes)
+
+    def file_exists(self, filename: str) -> bool:
+        key = self.convert_path_to_key(filename)
+        contents, _ = self._list(key, max_keys=1)
+        return any(o["Key"] == key for o in contents)
+
+    def is_checkpoint_xser(self, dirname: str) -> bool:
+        contents, _ = self._list(self._dir_key(dirname))
+        return any(".tensors/" in o["Key"] for o in contents)
+
+    def list_dirs(self, dirname: str) -> List[str]:
+        pfx = self._dir_key(dirname)
+        _, prefixes = self._list(pfx, delimiter="/")
+        return [p[len(pfx):].rstrip("/") for p in prefixes]
+
+    def find_files(self, dirname, pattern=None, search_root: Optional[str] = None, max_count: Optional[int] = None,
+                   sort_by_mdate: bool = False) -> List[str]:
+        """Two call forms, like the file-system back-end: ``find_files(dirname, pattern)`` — files under ``dirname`` whose
+        base name matches the glob; ``find_files(pattern, search_depth, search_root, max_count, sort_by_mdate)`` — the
+        reference's depth-limited search (paths relative to the storage root)."""
+        import fnmatch
+
+        if isinstance(pattern, int):
+            glob_pat, depth, root = dirname, pattern, search_root or ""
+        else:
+            glob_pat, depth, root = pattern or "*", None, dirname
+        pfx = self._dir_key(root)
+        contents, _ = self._list(pfx)
+        base = self._base_key or ""
+        hits = []
+        for o in contents:
+            rel = o["Key"][len(pfx):]
+            if depth is not None and rel.count("/") >= depth:
+                continue
+            if fnmatch.fnmatch(os.path.basename(rel), glob_pat):
+                hits.append((o.get("LastModified", 0), o["Key"][len(base):]))
+        if sort_by_mdate:
+            hits.sort(key=lambda t: t[0])
+        out = [h[1] for h in hits]
+        return out[:max_count] if max_count else out
 
     def create_dir(self, dirname: str, exist_ok: bool = True) -> None:
         pass  # S3 has no directories
@@ -255,33 +388,71 @@ class S3CheckpointStorage(BaseCheckpointStorage):
     def create_shared_dir(self, dirname: str, exist_ok: bool = True, process_group=None) -> None:
         pass
 
-    def remove_dir(self, dirname: str) -> None:  # pragma: no cover
-        pfx = self._key(dirname).rstrip("/") + "/"
+    def remove_dir(self, dirname: str) -> None:
+        pfx = self._dir_key(dirname)
         while True:
-            r = self._retry(self.s3.list_objects_v2, Bucket=self.bucket, Prefix=pfx)
-            objs = [{"Key": o["Key"]} for o in r.get("Contents", [])]
+            contents, _ = self._list(pfx, max_keys=1000)
+            objs = [{"Key": o["Key"]} for o in contents[:1000]]
             if not objs:
                 break
-            self._retry(self.s3.delete_objects, Bucket=self.bucket, Delete={"Objects": objs})
+            self._retry(self.s3.delete_objects, Bucket=self._bucket, Delete={"Objects": objs})
 
-    def remove_file(self, filename: str) -> None:  # pragma: no cover
-        self._retry(self.s3.delete_object, Bucket=self.bucket, Key=self._key(filename))
+    def remove_file(self, filename: str) -> None:
+        self._retry(self.s3.delete_object, Bucket=self._bucket, Key=self.convert_path_to_key(filename))
 
-    def save_text(self, text: str, filename: str) -> None:  # pragma: no cover
-        self._retry(self.s3.put_object, Bucket=self.bucket, Key=self._key(filename), Body=text.encode())
+    def save_text(self, text: str, filename: str) -> None:
+        self._retry(self.s3.put_object, Bucket=self._bucket, Key=self.convert_path_to_key(filename), Body=text.encode())
 
-    def save_object(self, obj: Any, filename: str) -> None:  # pragma: no cover
+    def upload_stream_to_file(self, stream_creator, filename: str, chunk_size_MB: int = 64, max_concurrency: int = 10,
+                              use_threads: bool = True) -> None:
+        """Upload what ``stream_creator`` produces — an object with ``create_stream()`` (reference), a callable returning a
+        binary stream, or the stream itself."""
+        stream = stream_creator.create_stream() if hasattr(stream_creator, "create_stream") else (
+            stream_creator() if callable(stream_creator) else stream_creator)
+        stream.seek(0)
+        kw = {}
+        try:
+            from boto3.s3.transfer import TransferConfig  # type: ignore
+
+            kw["Config"] = TransferConfig(use_threads=use_threads, multipart_chunksize=chunk_size_MB << 20, max_concurrency=max_concurrency)
+        except Exception:  # noqa: BLE001
+            pass
+        key = self.convert_path_to_key(filename)
+
+        def attempt():
+            stream.seek(0)                    # a failed attempt may have consumed part of the stream
+            self.s3.upload_fileobj(stream, self._bucket, key, **kw)
+
+        self._retry(attempt)
+
+    def download_file_to_stream(self, filename: str, chunk_size_MB: int = 64, max_concurrency: int = 15) -> io.BytesIO:
+        """One ``get_object`` (no extra transfer threads: tensor loading already runs from several threads per process)."""
+        r = self._retry(self.s3.get_object, Bucket=self._bucket, Key=self.convert_path_to_key(filename))
+        stream = io.BytesIO(r["Body"].read())
+        stream.seek(0)
+        return stream
+
+    def save_object(self, obj: Any, filename: str) -> None:
         buf = io.BytesIO()
         torch.save(obj, buf)
-        buf.seek(0)
-        self._retry(self.s3.upload_fileobj, buf, self.bucket, self._key(filename))
+        self.upload_stream_to_file(buf, filename)
 
-    def load_object(self, filename: str, map_location=None) -> Any:  # pragma: no cover
-        buf = io.BytesIO()
-        self._retry(self.s3.download_fileobj, self.bucket, self._key(filename), buf)
-        buf.seek(0)
-        return torch.load(buf, map_location=map_location, weights_only=False)
+    def load_object(self, filename: str, map_location=None) -> Any:
+        return torch.load(self.download_file_to_stream(filename), map_location=map_location, weights_only=False)
+
+    def load_text(self, filename: str) -> str:
+        return self.download_file_to_stream(filename).read().decode()
+
+    def _tag_time(self, tag: str) -> float:
+        key = self.convert_path_to_key(os.path.join(tag, "checkpoint"))
+        contents, _ = self._list(key, max_keys=1)
+        for o in contents:
+            if o["Key"] == key:
+                lm = o.get("LastModified", 0)
+                return lm.timestamp() if hasattr(lm, "timestamp") else float(lm)
+        return 0.0
 
 
-def create_checkpoint_storage(dirname: str) -> BaseCheckpointStorage:
-    return S3CheckpointStorage(dirname) if dirname.startswith("s3://") else FilesysCheckpointStorage(dirname)
+def create_checkpoint_storage(dirname: str, crt_config: Optional[dict] = None) -> BaseCheckpointStorage:
+    return S3CheckpointStorage(dirname, crt_config) if dirname.startswith(S3CheckpointStorage.S3_PATH_PREFIX) \
+        else FilesysCheckpointStorage(dirname)

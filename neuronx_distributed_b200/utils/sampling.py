@@ -41,6 +41,13 @@ class Sampler:
             choice = probs.argmax(-1, keepdim=True)
         else:
             choice = torch.multinomial(probs, 1, generator=generator)
+            if self.vocab_parallel:
+                # every TP rank holds the same candidates but its own RNG stream: continue with rank 0's draw everywhere
+                from ..parallel_layers import parallel_state as ps
+
+                if ps.model_parallel_is_initialized() and ps.get_tensor_model_parallel_size() > 1:
+                    torch.distributed.broadcast(choice, src=ps.get_tensor_model_parallel_src_rank(),
+                                                group=ps.get_tensor_model_parallel_group())
         return idx.gather(-1, choice).squeeze(-1)
 
 

@@ -147,3 +147,50 @@ def _optimizer_views_and_shard_files(rank, world, root):
 
 def test_optimizer_views_shard_files_and_removal(tmp_path):
     run_distributed(_optimizer_views_and_shard_files, 2, str(tmp_path), timeout=150)
+
+
+def _s3_ckpt(rank, world, fake_root):
+    """The whole save / rotate / load flow against ``s3://`` (fake client shared through a directory), with injected
+    SlowDown errors on every 7th request."""
+    import sys
+
+    import fake_boto3
+
+    os.environ["FAKE_S3_ROOT"], os.environ["FAKE_S3_SLOWDOWN_EVERY"] = fake_root, "7"
+    sys.modules["boto3"] = fake_boto3
+    from neuronx_distributed_b200.trainer import checkpoint_storage as cs
+
+    cs.S3CheckpointStorage.SLEEP_SCALE = 0.0
+    assert cs.S3CheckpointStorage.parse_path("s3://bkt/a/b") == ("bkt", "a/b") and cs.S3CheckpointStorage.parse_path("s3://bkt") == ("bkt", None)
+    root = "s3://bkt/run1"
+    nxd, model, opt = _build(2, True)
+    for i in range(2):
+        _step(model, opt, i)
+    for i, tag in enumerate(["step_1", "step_2", "step_3"]):
+        nxd.save_checkpoint(root, tag, model=model, optimizer=opt, user_content={"step": i + 1}, use_xser=(i % 2 == 0),
+                            async_save=(i == 1), num_kept_ckpts=2)
+    nxd.finalize_checkpoint()
+    st = cs.create_checkpoint_storage(root)
+    assert isinstance(st, cs.S3CheckpointStorage) and st.convert_path_to_key("step_3/done") == "run1/step_3/done"
+    assert st.list_completed_checkpoint_tags() == ["step_2", "step_3"]
+    assert st.is_checkpoint_xser("step_3/model") and not st.is_checkpoint_xser("step_2/model")
+    assert st.file_exists("step_3/done") and not st.file_exists("step_3/don") and st.dir_exists("step_3") and not st.dir_exists("step_1")
+    assert sorted(st.find_subdirs_contain_path("done", 1)) == ["step_2", "step_3"]
+    assert len(st.find_files("step_3/model", "*.pt")) >= 1
+    assert nxd.has_checkpoint(root)
+    want = _step(model, opt, 100)
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    ps.destroy_model_parallel()
+    _, model2, opt2 = _build(2, True)
+    assert nxd.load_checkpoint(root, tag=None, model=model2, optimizer=opt2) == {"step": 3}
+    assert abs(_step(model2, opt2, 100) - want) < 1e-4
+    # reference helper names
+    st.upload_stream_to_file(lambda: __import__("io").BytesIO(b"abc"), f"misc/blob{rank}")
+    assert st.download_file_to_stream(f"misc/blob{rank}").read() == b"abc" and st.load_text(f"misc/blob{rank}") == "abc"
+    st.remove_file(f"misc/blob{rank}")
+    assert not st.file_exists(f"misc/blob{rank}")
+
+
+def test_s3_storage_against_fake_client(tmp_path):
+    run_distributed(_s3_ckpt, 2, str(tmp_path / "s3"), timeout=180)

@@ -73,6 +73,22 @@ def _spmd_pad_lora(rank, world, tmp):
     assert trainable and all("lora_" in n for n in trainable)
     sum(t.sum() for t in out).backward()
     assert any(p_.grad is not None for n, p_ in lm.named_parameters() if "lora_B" in n)
+    # merge / unmerge into the fused [q_r; k_r; v_r] parameter: same outputs as the un-merged adapter, exact restore
+    lora_layer = next(m for m in lm.modules() if type(m).__name__ == "LoraGQAQKVParallelLinear")
+    with torch.no_grad():
+        for b in (lora_layer.lora_B_q, lora_layer.lora_B_k, lora_layer.lora_B_v):
+            b.weight.normal_(generator=torch.Generator().manual_seed(5 + rank))
+    w0 = lora_layer.base_layer.weight_qkv.detach().clone()
+    ref = [t.detach().clone() for t in lm(xin)]
+    assert not all(torch.allclose(a_, b_) for a_, b_ in zip(ref, base))
+    lora_layer.merge(safe_merge=True)
+    assert lora_layer.merged and len(lora_layer.get_qkv(lora_layer.base_layer)) == 3
+    for a_, b_ in zip(lm(xin), ref):
+        torch.testing.assert_close(a_, b_, atol=1e-5, rtol=1e-5)
+    lora_layer.unmerge()
+    torch.testing.assert_close(lora_layer.base_layer.weight_qkv, w0, atol=1e-6, rtol=0)
+    for a_, b_ in zip(lm(xin), ref):
+        torch.testing.assert_close(a_, b_, atol=1e-5, rtol=1e-5)
 
 
 def test_spmd_rank_hooks_pad_cumsum_lora_gqa(tmp_path):
@@ -186,3 +202,52 @@ def _zero_dcp_and_ep(rank, world, tmp):
 
 def test_zero1_dcp_roundtrip_and_ep_zero1(tmp_path):
     run_distributed(_zero_dcp_and_ep, 2, str(tmp_path), timeout=180)
+
+
+def _dcp_phase(rank, world, tmp, phase):
+    """ZeRO-1 DCP checkpoint written at DP=2 and resumed at another DP degree: the re-sliced Adam state must give exactly
+    the step the original run takes next (same global batch, split over more / fewer ranks)."""
+    import torch.distributed as dist
+
+    from neuronx_distributed_b200.optimizer import NeuronZero1Optimizer
+    from neuronx_distributed_b200.optimizer import zero_dcp_utils as dcp
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=1)
+
+    def make():
+        torch.manual_seed(0)
+        m = nn.Sequential(nn.Linear(8, 24), nn.Tanh(), nn.Linear(24, 5))
+        return m, NeuronZero1Optimizer(m.parameters(), torch.optim.AdamW, lr=1e-2, grad_clipping=True, max_norm=1.0)
+
+    def step(m, o, seed):
+        x = torch.randn(8, 8, generator=torch.Generator().manual_seed(seed)).chunk(world)[rank]     # global batch of 8 rows
+        o.zero_grad(); m(x).pow(2).mean().backward(); o.step()
+
+    m, o = make()
+    if phase == "save":
+        step(m, o, 1); step(m, o, 2)
+        dcp.save_optim_state_dict(os.path.join(tmp, "optim"), o.state_dict(), o)
+        if rank == 0:
+            torch.save(m.state_dict(), os.path.join(tmp, "model.pt"))
+        step(m, o, 3)
+        if rank == 0:
+            torch.save(m.state_dict(), os.path.join(tmp, "after.pt"))
+        dist.barrier()
+        return
+    m.load_state_dict(torch.load(os.path.join(tmp, "model.pt")))
+    for fg in o.flat_groups:                                   # parameters live in the flat buffer; refresh the fp32 master shard
+        lo, hi = fg.shard_range
+        fg.master_shard.copy_(fg.param_flat[lo:hi])
+    assert not os.path.isdir(os.path.join(tmp, "optim", f"zero1_rank_{rank:02d}_of_{world:02d}"))
+    o.load_state_dict(dcp.load_optim_state_dict(os.path.join(tmp, "optim"), o))
+    step(m, o, 3)
+    want = torch.load(os.path.join(tmp, "after.pt"))
+    for k, v in m.state_dict().items():
+        torch.testing.assert_close(v, want[k], rtol=1e-5, atol=1e-6)
+
+
+def test_zero1_dcp_resume_at_other_dp_degree(tmp_path):
+    run_distributed(_dcp_phase, 2, str(tmp_path), "save", timeout=180)
+    run_distributed(_dcp_phase, 4, str(tmp_path), "load", timeout=180)
+    run_distributed(_dcp_phase, 1, str(tmp_path), "load", timeout=180)

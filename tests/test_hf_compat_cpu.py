@@ -238,3 +238,49 @@ def _encoders(rank, world):
 
 def test_hf_bert_vit_neox_parity():
     run_distributed(_encoders, 2, timeout=300)
+
+
+def _adapter(rank, world):
+    """``HuggingFaceGenerationAdapter.generate``: left-padded batch, greedy tokens equal ``transformers``' generate; EOS fills
+    with pad; sampling draws identical tokens on every TP rank; logits processors see the full vocabulary."""
+    import torch.distributed as dist
+
+    from neuronx_distributed_b200.inference.hf_adapter import HuggingFaceGenerationAdapter
+    from neuronx_distributed_b200.models import hf_compat
+    from neuronx_distributed_b200.models.llama_inference import LlamaForInference
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    ps.initialize_model_parallel(world)
+    hc, hf = _hf("llama", 2)
+    cfg = hf_compat.config_from_hf(hc, dtype=torch.float32)
+    srv = LlamaForInference(cfg, batch_size=2, max_seq_len=32).eval()
+    hf_compat.load_hf_checkpoint(srv, hf.state_dict())
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.randint(1, 128, (9,), generator=g), torch.randint(1, 128, (5,), generator=g)
+    ids = torch.zeros(2, 9, dtype=torch.long)
+    mask = torch.zeros(2, 9, dtype=torch.long)
+    ids[0], mask[0] = a, 1
+    ids[1, 4:], mask[1, 4:] = b, 1                                               # left padded, as HF tokenizers do for generation
+    want = hf.generate(ids, attention_mask=mask, max_new_tokens=6, do_sample=False, pad_token_id=0)
+    gen = HuggingFaceGenerationAdapter(srv, pad_token_id=0)
+    got = gen.generate(ids, attention_mask=mask, max_new_tokens=6)
+    assert torch.equal(got, want), (got, want)
+    # EOS: stop row 0 at its 3rd generated token; the rest of that row is pad, the other row continues
+    eos = int(want[0, 9 + 2])
+    got = gen.generate(ids, attention_mask=mask, max_new_tokens=6, eos_token_id=eos)
+    want_eos = hf.generate(ids, attention_mask=mask, max_new_tokens=6, do_sample=False, pad_token_id=0, eos_token_id=eos)
+    assert torch.equal(got[:, : want_eos.shape[1]], want_eos) and bool((got[:, want_eos.shape[1]:] == 0).all())
+    # sampling: every TP rank must continue with the same token
+    torch.manual_seed(100 + rank)                                                # deliberately different RNG streams
+    s = gen.generate(ids, attention_mask=mask, max_new_tokens=5, do_sample=True, top_k=8, top_p=0.9, temperature=0.7)
+    ref = s.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(s, ref) and s.shape == (2, 14)
+    # a logits processor that forbids everything except token 7
+    only7 = lambda hist, logits: torch.full_like(logits, float("-inf")).index_fill_(-1, torch.tensor([7]), 0.0)  # noqa: E731
+    assert bool((gen.generate(ids, attention_mask=mask, max_new_tokens=3, logits_processor=[only7])[:, 9:] == 7).all())
+    assert srv.on_device_sampling                                               # restored
+
+
+def test_hf_generation_adapter():
+    run_distributed(_adapter, 2, timeout=300)
