@@ -27,6 +27,7 @@ from training_utils import Throughput, init_distributed, synthetic_batches  # no
 def main():
     p = argparse.ArgumentParser()
     p.add_argument("--model", default="tiny", choices=["tiny", "7b", "13b", "70b"])
+    p.add_argument("--pretrained_hf", default=None, help="HF Llama directory (config.json + safetensors): continue pre-training / fine-tune from it")
     p.add_argument("--tensor_parallel_size", type=int, default=2)
     p.add_argument("--pipeline_parallel_size", type=int, default=2)
     p.add_argument("--virtual_pipeline_size", type=int, default=1)
@@ -50,12 +51,18 @@ def main():
     kw = dict(sequence_parallel_enabled=sp, dtype=dtype, max_position_embeddings=a.seq_len)
     mcfg = {"7b": llama2_7b_config, "13b": llama2_13b_config, "70b": llama2_70b_config}.get(a.model, lambda **k: LlamaConfig(
         vocab_size=4096, hidden_size=512, intermediate_size=1408, num_hidden_layers=8, num_attention_heads=8, **k))(**kw)
+    if a.pretrained_hf:                                          # architecture from the HF config, weights loaded after sharding
+        from neuronx_distributed_b200.models import hf_compat
+
+        mcfg = hf_compat.config_from_hf(a.pretrained_hf, **kw)
 
     def model_fn():
         torch.manual_seed(1234)
         return LlamaForCausalLM(mcfg)
 
     model = nxd.initialize_parallel_model(cfg, model_fn)
+    if a.pretrained_hf:
+        hf_compat.load_hf_checkpoint(model, a.pretrained_hf)     # every rank keeps its (tp, pp) shard only
     opt = nxd.initialize_parallel_optimizer(cfg, AdamW_FP32OptimParams, model.parameters(), lr=a.lr)
     dp = ps.get_data_parallel_size()
     data = synthetic_batches(mcfg.vocab_size, a.num_microbatches, a.seq_len, 1 + ps.get_data_parallel_rank(), dev)

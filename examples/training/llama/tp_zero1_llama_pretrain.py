@@ -28,6 +28,7 @@ from training_utils import (Throughput, TrainingMetrics, init_distributed, linea
 def get_args():
     p = argparse.ArgumentParser()
     p.add_argument("--model", default="7b", choices=["tiny", "7b", "13b", "70b"])
+    p.add_argument("--pretrained_hf", default=None, help="HF Llama directory (config.json + safetensors): continue pre-training / fine-tune from it")
     p.add_argument("--num_layers", type=int, default=-1)
     p.add_argument("--tensor_parallel_size", type=int, default=8)
     p.add_argument("--context_parallel_size", type=int, default=1)
@@ -74,6 +75,10 @@ def main():
               context_parallel=a.context_parallel_size > 1)
     mcfg = {"7b": llama2_7b_config, "13b": llama2_13b_config, "70b": llama2_70b_config}.get(a.model, lambda **k: LlamaConfig(
         vocab_size=4096, hidden_size=512, intermediate_size=1408, num_hidden_layers=4, num_attention_heads=8, **k))(**kw)
+    if a.pretrained_hf:                                          # architecture from the HF config, weights loaded after sharding
+        from neuronx_distributed_b200.models import hf_compat
+
+        mcfg = hf_compat.config_from_hf(a.pretrained_hf, **kw)
     if a.num_layers > 0:
         mcfg.num_hidden_layers = a.num_layers
 
@@ -84,6 +89,8 @@ def main():
         return LlamaForCausalLM(mcfg)
 
     model = nxd.initialize_parallel_model(cfg, model_fn)
+    if a.pretrained_hf:
+        hf_compat.load_hf_checkpoint(model, a.pretrained_hf)     # every rank keeps its (tp, pp) shard only
     opt = nxd.initialize_parallel_optimizer(cfg, AdamW_FP32OptimParams, model.parameters(), lr=a.lr, betas=(a.beta1, a.beta2),
                                             weight_decay=a.weight_decay)
     sched = linear_warmup_cosine(opt.optimizer if hasattr(opt, "optimizer") else opt, a.warmup_steps, a.max_steps)

@@ -469,6 +469,41 @@ def _to_canonical_key(k: str, dec: str, head: Optional[str]) -> Optional[str]:
     return k[len(dec):] if k.startswith(dec) else None
 
 
+def _unwrap(model):
+    """``(module, pipeline_model)``: strips the trainer's ``NxDModel`` wrapper; for a pipeline-partitioned model returns the
+    original (un-partitioned) module — whose local layers share their Parameters with the stage modules — and the
+    ``NxDPPModel`` that owns the partition."""
+    from ..pipeline.model import NxDPPModel
+    from ..trainer.model import NxDModel
+
+    if isinstance(model, NxDModel):
+        model = model.module
+    if isinstance(model, NxDPPModel):
+        return model.original_torch_module, model
+    return model, None
+
+
+def _load_into_pipeline_stage(pp, original, hf_sd, cfg, strict: bool):
+    """Each (tp, pp) rank keeps the tensors of ITS stage only: the translated full state is filtered to the modules that own
+    a local parameter before any slicing happens."""
+    from ..inference.sharding import shard_state_dict_for_rank
+
+    root, dec, head = _layout(original)
+    cfg = cfg or _config_of(original, root)
+    full = _to_model_keys(hf_to_nxd_state_dict(hf_sd, cfg, **_kv_args(root)), dec, head)
+    local_names = set(pp.original_name_to_local_name)
+    local_mods = {n.rpartition(".")[0] for n in local_names}
+    full = {k: v for k, v in full.items() if k in local_names or k.rpartition(".")[0] in local_mods}
+    local = shard_state_dict_for_rank(root, full, ps.get_tensor_model_parallel_rank(), ps.get_tensor_model_parallel_size())
+    want = pp.local_state_dict()
+    missing = [k for k in want if k not in local]
+    if strict and missing:
+        raise RuntimeError(f"HF checkpoint lacks tensors for local parameters: {missing[:8]}")
+    local = {k: (v.to(want[k].dtype) if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in local.items() if k in want}
+    pp.load_state_dict(local, strict=False)
+    return torch.nn.modules.module._IncompatibleKeys(missing, [])
+
+
 def load_hf_checkpoint(model, path_or_state, cfg=None, strict: bool = True):
     """Load an HF checkpoint (directory, file or state dict) into ``model`` — a ``LlamaForCausalLM`` / ``MixtralForCausalLM`` /
     serving wrapper built under the current TP (and EP) groups; every rank slices its own shard.  Returns the
@@ -476,6 +511,9 @@ def load_hf_checkpoint(model, path_or_state, cfg=None, strict: bool = True):
     from ..inference.sharding import shard_state_dict_for_rank
 
     hf_sd = path_or_state if isinstance(path_or_state, dict) else read_hf_state_dict(os.fspath(path_or_state))
+    model, pp = _unwrap(model)
+    if pp is not None:
+        return _load_into_pipeline_stage(pp, model, hf_sd, cfg, strict)
     fam = _encoder_family(model)
     if fam is not None:                               # BERT / ViT: renames (+ QKV fusion); GPT-NeoX: HF names as they are
         full = {"bert": hf_to_nxd_bert_state_dict, "vit": hf_to_nxd_vit_state_dict, "gptneox": dict}[fam](hf_sd)

@@ -139,6 +139,8 @@ class NxDPPModel(nn.Module):
         self.local_stage_modules = nn.ModuleList()
         self._losses: List[torch.Tensor] = []
         self.training_mode = True
+        if auto_partition and transformer_layer_cls is None and not manual_pp_partition:
+            raise ValueError("auto_partition needs transformer_layer_cls (the block class whose instances are distributed over the stages)")
         if manual_pp_partition:
             self._manual_partition()
         elif transformer_layer_cls is not None or self.pipeline_cuts:
@@ -612,10 +614,10 @@ class NxDPPModel(nn.Module):
         return loss
 
     # =================================================================== local accessors
-    def local_named_parameters(self, prefix: str = "", recurse: bool = True):
+    def local_named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
         seen = set()
         for name, p in self.local_stage_modules.named_parameters(prefix="local_stage_modules", recurse=recurse):
-            if id(p) in seen:
+            if remove_duplicate and id(p) in seen:
                 continue
             seen.add(id(p))
             yield prefix + self.local_name_to_original_name.get(name, name), p
@@ -628,7 +630,7 @@ class NxDPPModel(nn.Module):
         return self.local_parameters(recurse)
 
     def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
-        return self.local_named_parameters(prefix, recurse)
+        return self.local_named_parameters(prefix, recurse, remove_duplicate)
 
     def local_named_buffers(self, prefix: str = "", recurse: bool = True):
         for name, b in self.local_stage_modules.named_buffers(prefix="local_stage_modules", recurse=recurse):

@@ -9,7 +9,7 @@ shared by several stages (tied embeddings).
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Set, Tuple
+from typing import Any, Dict, List, Optional, Sequence, Set, Tuple
 
 import torch.fx as fx
 from torch import nn
@@ -62,7 +62,30 @@ def trace_model(model: nn.Module, input_names: Optional[Sequence[str]], leaf_mod
                 concrete[name] = p.default
     tracer = (tracer_cls or _LeafTracer)(leaf, tuple(autowrap_functions) + tuple(PARALLEL_FUNCTIONS), autowrap_modules)
     graph = tracer.trace(model, concrete_args=concrete or None)
+    _drop_specialised_placeholders(graph, concrete)
     return fx.GraphModule(model, graph)
+
+
+def _drop_specialised_placeholders(graph: fx.Graph, concrete: Dict[str, Any]) -> None:
+    """``concrete_args`` with a non-``None`` default leave a placeholder plus ``torch._assert(arg == default)`` in the graph;
+    the pipeline never feeds those arguments (they are constants of the traced program), so remove the check and the
+    placeholder instead of making every caller pass the default again."""
+    for node in list(graph.nodes):
+        if node.op != "placeholder" or not any(node.target == n or str(node.target).startswith(n + "_") for n in concrete):
+            continue
+        chain, frontier = [], [node]
+        while frontier:
+            cur = frontier.pop()
+            for u in cur.users:
+                if u not in chain:
+                    chain.append(u)
+                    frontier.append(u)
+        if any(u.op == "output" for u in chain):
+            continue                                   # really used by the program: leave it alone
+        order = {n: i for i, n in enumerate(graph.nodes)}
+        for u in sorted(chain, key=order.__getitem__, reverse=True):
+            graph.erase_node(u)
+        graph.erase_node(node)
 
 
 @dataclass

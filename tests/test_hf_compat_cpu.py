@@ -284,3 +284,33 @@ def _adapter(rank, world):
 
 def test_hf_generation_adapter():
     run_distributed(_adapter, 2, timeout=300)
+
+
+def _pp_load(rank, world):
+    """HF checkpoint → TP=2 × PP=2 partitioned model (each rank keeps its stage's shard only) → the HF loss."""
+    import neuronx_distributed_b200 as nxd
+    from neuronx_distributed_b200.models import hf_compat
+    from neuronx_distributed_b200.models.llama import LlamaDecoderLayer, LlamaForCausalLM
+
+    torch.manual_seed(0)
+    hc = transformers.LlamaConfig(vocab_size=128, hidden_size=64, intermediate_size=96, num_hidden_layers=4, num_attention_heads=8,
+                                  num_key_value_heads=2, max_position_embeddings=64, attn_implementation="eager")
+    hf = transformers.LlamaForCausalLM(hc).eval()
+    cfg = nxd.neuronx_distributed_config(tensor_parallel_size=2, pipeline_parallel_size=2, pipeline_config={
+        "num_microbatches": 2, "input_names": ["input_ids", "labels"], "output_loss_value_spec": True, "auto_partition": True,
+        "transformer_layer_cls": LlamaDecoderLayer})
+    mcfg = hf_compat.config_from_hf(hc, dtype=torch.float32)
+    model = nxd.initialize_parallel_model(cfg, lambda: LlamaForCausalLM(mcfg))
+    res = hf_compat.load_hf_checkpoint(model, hf.state_dict())
+    assert not res.missing_keys
+    assert all(("layers.0." in k or "layers.1." in k or "embed" in k) == (rank < 2) for k in model.state_dict() if "norm.weight" != k[-11:] or "layers" in k)
+    ids = torch.randint(0, 128, (4, 16), generator=torch.Generator().manual_seed(1))
+    loss = model.run_eval(input_ids=ids, labels=ids)
+    with torch.no_grad():
+        ref = hf(ids, labels=ids).loss
+    if rank >= 2:                                                  # last stage owns the loss
+        assert abs(float(loss) - float(ref)) < 1e-5, (float(loss), float(ref))
+
+
+def test_hf_load_into_tp_pp_model():
+    run_distributed(_pp_load, 4, timeout=300)
