@@ -209,6 +209,8 @@ class LlamaModel(nn.Module):
 
 
 class LlamaForCausalLM(nn.Module):
+    _no_split_modules = ["LlamaDecoderLayer"]      # unit of activation checkpointing / pipeline partitioning (HF convention)
+
     def __init__(self, cfg: LlamaConfig):
         super().__init__()
         self.config = cfg
