@@ -33,6 +33,9 @@ def main():
     p.add_argument("--max_new_tokens", type=int, default=16)
     p.add_argument("--seq_len", type=int, default=128)
     p.add_argument("--check_accuracy", action="store_true")
+    p.add_argument("--do_sample", action="store_true")
+    p.add_argument("--top_k", type=int, default=50)
+    p.add_argument("--top_p", type=float, default=0.95)
     a = p.parse_args()
     import transformers
 
@@ -59,24 +62,25 @@ def main():
     else:
         g = torch.Generator().manual_seed(1)
         ids = [torch.randint(3, cfg.vocab_size, (n,), generator=g) for n in (9, 6)][: len(prompts)]
-    model = LlamaForInference(cfg, batch_size=1, max_seq_len=a.seq_len).eval()
+    lm_cls = None
+    if hasattr(cfg, "num_local_experts"):                        # Mixtral / DBRX checkpoints: same serving wrapper, MoE decoder
+        from neuronx_distributed_b200.models.mixtral import MixtralForCausalLM as lm_cls
+    model = LlamaForInference(cfg, batch_size=1, max_seq_len=a.seq_len, lm_cls=lm_cls).eval()
     res = hf_compat.load_hf_checkpoint(model, state)
     assert not res.missing_keys, res.missing_keys
 
+    from neuronx_distributed_b200.inference.hf_adapter import HuggingFaceGenerationAdapter
+
+    generate = HuggingFaceGenerationAdapter(model, eos_token_id=getattr(tokenizer, "eos_token_id", None), pad_token_id=0).generate
     outs = []
-    for seq in ids:
-        n = seq.numel()
-        tok = model.context_encoding(seq.view(1, -1).to(dev), torch.tensor([n - 1], device=dev))
-        gen = [int(tok[0])]
-        for i in range(a.max_new_tokens - 1):
-            tok = model.token_generation(tok.view(1, 1), torch.tensor([n + i], device=dev))
-            gen.append(int(tok[0]))
-        outs.append(gen)
+    for seq in ids:                                              # same keyword arguments as transformers' generate()
+        full = generate(seq.view(1, -1).to(dev), max_new_tokens=a.max_new_tokens, do_sample=a.do_sample, top_k=a.top_k, top_p=a.top_p)
+        outs.append(full[0, seq.numel():].tolist())
     if rank0:
         for i, (seq, gen) in enumerate(zip(ids, outs)):
             text = tokenizer.decode(seq.tolist() + gen, skip_special_tokens=True) if tokenizer is not None else gen
             print(f"Generated {i + 1}: {text}")
-    if a.check_accuracy and rank0:
+    if a.check_accuracy and rank0 and not a.do_sample:
         if hf_model is None:
             hf_model = transformers.AutoModelForCausalLM.from_pretrained(a.model_path, torch_dtype=torch.float32).eval()
         agree = total = 0

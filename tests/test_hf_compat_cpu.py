@@ -314,3 +314,27 @@ def _pp_load(rank, world):
 
 def test_hf_load_into_tp_pp_model():
     run_distributed(_pp_load, 4, timeout=300)
+
+
+def _mixtral_serving(rank, world):
+    """MoE family through the serving wrapper (``lm_cls=MixtralForCausalLM``): HF Mixtral weights, greedy == ``generate``."""
+    from neuronx_distributed_b200.inference.hf_adapter import HuggingFaceGenerationAdapter
+    from neuronx_distributed_b200.models import hf_compat
+    from neuronx_distributed_b200.models.llama_inference import LlamaForInference
+    from neuronx_distributed_b200.models.mixtral import MixtralForCausalLM
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    ps.initialize_model_parallel(world)
+    hc, hf = _hf("mixtral", 2)
+    cfg = hf_compat.config_from_hf(hc, dtype=torch.float32)
+    srv = LlamaForInference(cfg, batch_size=1, max_seq_len=32, lm_cls=MixtralForCausalLM).eval()
+    res = hf_compat.load_hf_checkpoint(srv, hf.state_dict())
+    assert not res.missing_keys and not res.unexpected_keys
+    prompt = torch.randint(1, 128, (1, 7), generator=torch.Generator().manual_seed(4))
+    want = hf.generate(prompt, max_new_tokens=6, do_sample=False, pad_token_id=0)
+    got = HuggingFaceGenerationAdapter(srv, pad_token_id=0).generate(prompt, max_new_tokens=6)
+    assert torch.equal(got, want), (got, want)
+
+
+def test_hf_mixtral_serving_generation():
+    run_distributed(_mixtral_serving, 2, timeout=300)
