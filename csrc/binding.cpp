@@ -47,6 +47,34 @@ static std::vector<Tensor> rmsnorm_bwd(const Tensor& g, const Tensor& x, const T
   return {dx, dw};
 }
 
+static std::vector<Tensor> add_rmsnorm_fwd(const Tensor& x, const Tensor& r, const Tensor& w, double eps) {
+  CHECK_IN(x); CHECK_IN(r); CHECK_IN(w);
+  TORCH_CHECK(x.dim() == 2 && r.sizes() == x.sizes() && w.numel() == x.size(1) && w.scalar_type() == x.scalar_type() &&
+              r.scalar_type() == x.scalar_type());
+  c10::cuda::CUDAGuard g(x.device());
+  auto h = at::empty_like(x);
+  auto y = at::empty_like(x);
+  auto rstd = at::empty({x.size(0), 1}, x.options().dtype(at::kFloat));
+  if (x.size(0) > 0)
+    nxd::add_rmsnorm_fwd(x.data_ptr(), r.data_ptr(), w.data_ptr(), h.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(),
+                         (int)x.size(0), (int)x.size(1), (float)eps, dt_code(x), stream());
+  return {y, h, rstd};
+}
+
+static std::vector<Tensor> add_rmsnorm_bwd(const Tensor& gy, const Tensor& gh, const Tensor& h, const Tensor& w, const Tensor& rstd) {
+  CHECK_IN(gy); CHECK_IN(gh); CHECK_IN(h); CHECK_IN(w); CHECK_IN(rstd);
+  c10::cuda::CUDAGuard guard(h.device());
+  const int rows = (int)h.size(0), H = (int)h.size(1);
+  auto dh = at::empty_like(h);
+  auto dw = at::zeros({H}, h.options().dtype(at::kFloat));
+  if (rows > 0) {
+    auto partial = at::empty({nxd::rmsnorm_bwd_num_partials(rows), H}, h.options().dtype(at::kFloat));
+    nxd::add_rmsnorm_bwd(gy.data_ptr(), gh.data_ptr(), h.data_ptr(), w.data_ptr(), rstd.data_ptr<float>(), dh.data_ptr(),
+                         partial.data_ptr<float>(), dw.data_ptr<float>(), rows, H, dt_code(h), stream());
+  }
+  return {dh, dw};
+}
+
 static Tensor swiglu_fwd(const Tensor& gu) {
   CHECK_IN(gu);
   c10::cuda::CUDAGuard g(gu.device());
@@ -405,6 +433,8 @@ static Tensor symm_view(int64_t id, int64_t offset, const std::vector<int64_t>& 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("add_rmsnorm_fwd", &add_rmsnorm_fwd);
+  m.def("add_rmsnorm_bwd", &add_rmsnorm_bwd);
   m.def("swiglu_fwd", &swiglu_fwd);
   m.def("swiglu_bwd", &swiglu_bwd);
   m.def("rope_apply", &rope_apply);

@@ -13,6 +13,11 @@ void rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, i
 int rmsnorm_bwd_num_partials(int rows);
 void rmsnorm_bwd(const void* g, const void* x, const void* w, const float* rstd, void* dx, float* partial, float* dw,
                  int rows, int H, int dt, cudaStream_t st);
+// residual-add fused with RMSNorm (fused_norm.cu)
+void add_rmsnorm_fwd(const void* x, const void* r, const void* w, void* h, void* y, float* rstd, int rows, int H, float eps,
+                     int dt, cudaStream_t st);
+void add_rmsnorm_bwd(const void* gy, const void* gh, const void* h, const void* w, const float* rstd, void* dh, float* partial,
+                     float* dw, int rows, int H, int dt, cudaStream_t st);
 void swiglu_fwd(const void* gu, void* out, long rows, int I, int dt, cudaStream_t st);
 void swiglu_bwd(const void* go, const void* gu, void* dgu, long rows, int I, int dt, cudaStream_t st);
 void rope_apply(const void* x, void* out, const float* cos_t, const float* sin_t, int B, int S, int Hh, int D, long sb,

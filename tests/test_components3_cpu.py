@@ -143,3 +143,53 @@ def test_lightning_fit_loop_checkpoint_resume(tmp_path):
 
 def test_lightning_module_trains_without_lightning_installed():
     run_distributed(_lightning, 2, timeout=120)
+
+
+def test_add_rms_norm_matches_unfused_composition(monkeypatch):
+    """``ops.norm.add_rms_norm`` (residual add fused with RMSNorm): values and all three gradients equal the two-op form; the
+    Llama block gives the same loss and gradients with the fusion switched on."""
+    from neuronx_distributed_b200.ops import norm
+
+    g = torch.Generator().manual_seed(0)
+    x, r = torch.randn(3, 5, 32, generator=g, requires_grad=True), torch.randn(3, 5, 32, generator=g, requires_grad=True)
+    w = torch.randn(32, generator=g).abs().requires_grad_(True)
+    y, h = norm.add_rms_norm(x, r, w, 1e-5)
+    cot_y, cot_h = torch.randn(3, 5, 32, generator=g), torch.randn(3, 5, 32, generator=g)
+    (y * cot_y).sum().backward(retain_graph=True)
+    (h * cot_h).sum().backward()
+    got = [t.grad.clone() for t in (x, r, w)]
+    for t in (x, r, w):
+        t.grad = None
+    h2 = x + r
+    y2 = norm.rms_norm(h2, w, 1e-5)
+    ((y2 * cot_y).sum() + (h2 * cot_h).sum()).backward()
+    torch.testing.assert_close(y, y2)
+    torch.testing.assert_close(h, h2)
+    for a, b in zip(got, (x.grad, r.grad, w.grad)):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
+
+
+def _fused_block(rank, world):
+    from neuronx_distributed_b200.models import llama
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    ps.initialize_model_parallel(world)
+    cfg = llama.LlamaConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                            dtype=torch.float32, max_position_embeddings=16, sequence_parallel_enabled=True)
+    ids = torch.randint(0, 64, (2, 16), generator=torch.Generator().manual_seed(1))
+    out = []
+    for fused in (False, True):
+        llama._FUSED_ADD_NORM = fused
+        torch.manual_seed(0)
+        m = llama.LlamaForCausalLM(cfg)
+        loss, _ = m(ids, labels=ids)
+        loss.backward()
+        out.append((loss.detach(), [p.grad.clone() for p in m.parameters()]))
+    llama._FUSED_ADD_NORM = False
+    torch.testing.assert_close(out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_llama_block_with_fused_add_norm():
+    run_distributed(_fused_block, 2, timeout=120)

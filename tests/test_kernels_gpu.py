@@ -144,3 +144,35 @@ def test_flash_attention_lse_is_differentiable():
     rel = lambda a, b: ((a.float() - b).abs().max() / b.abs().max()).item()
     assert rel(o, ro) < 2e-2 and (lse - rl).abs().max() < 2e-2
     assert rel(q.grad, qf.grad) < 3e-2 and rel(k.grad, kf.grad) < 3e-2 and rel(v.grad, vf.grad) < 3e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_fused_add_rmsnorm_vs_fp32_reference(dtype):
+    """``csrc/fused_norm.cu``: h = x + r, y = rmsnorm(h)·w and the fused backward, against plain fp32 PyTorch."""
+    from neuronx_distributed_b200.ops import _ext, norm
+
+    assert _ext.ext() is not None and hasattr(_ext.ext(), "add_rmsnorm_fwd"), _ext.load_error()
+    torch.manual_seed(0)
+    rows, H = 1000, 4096
+    x = torch.randn(rows, H, device="cuda", dtype=dtype, requires_grad=True)
+    r = torch.randn(rows, H, device="cuda", dtype=dtype, requires_grad=True)
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).to(dtype).requires_grad_(True)
+    cy, ch = torch.randn(rows, H, device="cuda", dtype=dtype), torch.randn(rows, H, device="cuda", dtype=dtype)
+    before = _ext.launches()
+    y, h = norm.add_rms_norm(x, r, w, 1e-5)
+    ((y * cy).sum() + (h * ch).sum()).backward()
+    assert _ext.launches() - before == 3                       # forward + backward (row kernel + dW reduction)
+    xf, rf, wf = (t.detach().float().requires_grad_(True) for t in (x, r, w))
+    hf = (xf + rf).to(dtype).float() if dtype != torch.float32 else xf + rf     # the kernel normalises the STORED sum
+    hr = xf + rf
+    yr = hf * torch.rsqrt(hf.pow(2).mean(-1, keepdim=True) + 1e-5) * wf
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert (h.float() - hr).abs().max() <= (1e-6 if dtype == torch.float32 else 6e-2)
+    assert (y.float() - yr).abs().max() / yr.abs().max() < tol
+    # gradients against autograd of the fp32 composition
+    h2 = xf + rf
+    y2 = h2 * torch.rsqrt(h2.pow(2).mean(-1, keepdim=True) + 1e-5) * wf
+    ((y2 * cy.float()).sum() + (h2 * ch.float()).sum()).backward()
+    for got, want in ((x.grad, xf.grad), (r.grad, rf.grad), (w.grad, wf.grad)):
+        assert (got.float() - want).abs().max() / want.abs().max() < tol
+    assert torch.equal(x.grad, r.grad)
