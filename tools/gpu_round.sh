@@ -23,5 +23,7 @@ for r in gemm2cta fa_kernels elementwise; do
 done
 echo "=== bench (1 GPU, both arms)"
 timeout 400 python bench.py --steps 4 --warmup 3 2>&1 | tail -1 | cut -c1-1500
+echo "== A/B: residual-add fused with the post-attention RMSNorm (csrc/fused_norm.cu)"
+NXD_FUSED_ADD_NORM=1 timeout 400 python bench.py --steps 4 --warmup 3 2>&1 | tail -1 | cut -c1-400
 timeout 500 python bench.py --impl reference --steps 3 --warmup 3 --no-e2e 2>&1 | tail -1 | cut -c1-500
 ls -la gpurun_out | tail -12
