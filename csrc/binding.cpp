@@ -430,6 +430,90 @@ static Tensor symm_view(int64_t id, int64_t offset, const std::vector<int64_t>& 
   return at::from_blob(base + offset, shape, opts);
 }
 
+// ---- NVLS symmetric memory (symm_vmm.cpp) + fused TP kernels on it (tp_nvls_sm100.cu) + stand-alone collectives ----------
+static py::tuple vmm_begin(int64_t nbytes, int64_t rank, int64_t world, bool want_multicast) {
+  auto b = nxd::vmm_begin((size_t)nbytes, (int)rank, (int)world, want_multicast);
+  return py::make_tuple(b.id, b.sock_name, b.multicast_supported, (int64_t)b.size);
+}
+static py::tuple vmm_ptrs(int64_t id, bool multicast_everywhere) {
+  auto p = nxd::vmm_ptrs(id, multicast_everywhere);
+  return py::make_tuple(p.peer, p.multicast, (int64_t)p.size);
+}
+static Tensor vmm_view(int64_t id, int64_t offset, const std::vector<int64_t>& shape, py::object dtype) {
+  size_t nbytes = 0;
+  auto* base = (uint8_t*)nxd::vmm_local(id, &nbytes);
+  auto st = torch::python::detail::py_object_to_dtype(dtype);
+  int64_t need = at::elementSize(st);
+  for (auto d : shape) need *= d;
+  TORCH_CHECK(offset >= 0 && (size_t)(offset + need) <= nbytes, "vmm_view out of range");
+  int dev; cudaGetDevice(&dev);
+  auto opts = at::TensorOptions().dtype(st).device(at::kCUDA, dev);
+  return at::from_blob(base + offset, shape, opts);
+}
+
+// mode 1: a = shard [M/world, K] → out [M, N]; gathered A = region payload at buf_offset.
+// mode 2: a = [M, K] → out [M/world, N]; partials live in the region payload at buf_offset.  Returns reducer claims used.
+static int64_t tp_gemm_nvls(int64_t mode, const Tensor& a, const Tensor& b, Tensor out, bool trans_b, const Tensor& peer_bases,
+                            int64_t mc_base, int64_t local_base, int64_t buf_offset, int64_t flag_offset, int64_t epoch,
+                            int64_t rank, int64_t world, int64_t comm_ctas, Tensor counters, int64_t claim_base, bool wire_fp32) {
+  CHECK_IN(a); CHECK_IN(b); CHECK_IN(out);
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && out.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(counters.scalar_type() == at::kInt && counters.numel() >= 64 + 8 * 256);
+  c10::cuda::CUDAGuard g(a.device());
+  const int K = (int)a.size(1);
+  const int N = (int)(trans_b ? b.size(0) : b.size(1));
+  auto* ctr = (uint32_t*)counters.data_ptr();           // [0] = reducer claim counter, [64..] = tile_done per 128-row block
+  if (mode == 1) {
+    const int M = (int)a.size(0) * (int)world;
+    TORCH_CHECK(out.size(0) == M && out.size(1) == N);
+    return nxd::gemm_bf16_2cta_nvls(1, nullptr, b.data_ptr(), out.data_ptr(), nullptr, a.data_ptr(), M, N, K, trans_b, (int)rank,
+                                    (int)world, peer_bases.data_ptr<int64_t>(), mc_base, local_base, buf_offset, flag_offset,
+                                    (uint32_t)epoch, (int)comm_ctas, ctr + 64, ctr, 0u, false, stream());
+  }
+  const int M = (int)a.size(0);
+  TORCH_CHECK(out.size(0) * world == M && out.size(1) == N);
+  return nxd::gemm_bf16_2cta_nvls(2, a.data_ptr(), b.data_ptr(), nullptr, out.data_ptr(), nullptr, M, N, K, trans_b, (int)rank,
+                                  (int)world, peer_bases.data_ptr<int64_t>(), mc_base, local_base, buf_offset, flag_offset,
+                                  (uint32_t)epoch, (int)comm_ctas, ctr + 64, ctr, (uint32_t)claim_base, wire_fp32, stream());
+}
+
+static Tensor nvls_allreduce(const Tensor& x, const c10::optional<Tensor>& residual, const Tensor& peer_bases, int64_t mc_base,
+                             int64_t local_base, int64_t flag_off, int64_t data_off, int64_t half_bytes, Tensor state,
+                             int64_t rank, int64_t world) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && (x.scalar_type() == at::kBFloat16 || x.scalar_type() == at::kFloat));
+  TORCH_CHECK(state.scalar_type() == at::kInt && state.numel() >= 2 + 128);
+  if (residual) TORCH_CHECK(residual->is_contiguous() && residual->scalar_type() == x.scalar_type() && residual->numel() == x.numel());
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = at::empty_like(x);
+  const long nbytes = x.numel() * x.element_size();
+  int ctas = (int)std::max<long>(1, std::min<long>(64, nbytes / 16384));
+  nxd::nvls_allreduce(x.data_ptr(), residual ? residual->data_ptr() : nullptr, out.data_ptr(), peer_bases.data_ptr<int64_t>(),
+                      mc_base, local_base, flag_off, data_off, half_bytes, (uint32_t*)state.data_ptr(), (int)rank, (int)world,
+                      x.numel(), dt_code(x), ctas, stream());
+  return out;
+}
+static void nvls_all_gather(const Tensor& x, const c10::optional<Tensor>& out, const Tensor& peer_bases, int64_t mc_base,
+                            int64_t local_base, int64_t flag_off, int64_t data_off, int64_t half_bytes, Tensor state, int64_t rank,
+                            int64_t world, int64_t ctas) {
+  CHECK_IN(x);
+  c10::cuda::CUDAGuard guard(x.device());
+  const long bytes = x.numel() * x.element_size();
+  if (out) TORCH_CHECK(out->is_contiguous() && (long)(out->numel() * out->element_size()) == bytes * world);
+  nxd::nvls_all_gather(x.data_ptr(), out ? out->data_ptr() : nullptr, peer_bases.data_ptr<int64_t>(), mc_base, local_base, flag_off,
+                       data_off, half_bytes, (uint32_t*)state.data_ptr(), (int)rank, (int)world, bytes, (int)ctas, stream());
+}
+static Tensor nvls_reduce_scatter(const Tensor& x, const Tensor& peer_bases, int64_t mc_base, int64_t local_base, int64_t flag_off,
+                                  int64_t data_off, int64_t half_bytes, Tensor state, int64_t rank, int64_t world, int64_t ctas) {
+  CHECK_IN(x);
+  TORCH_CHECK(x.numel() % world == 0);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = at::empty({x.numel() / world}, x.options());
+  nxd::nvls_reduce_scatter(x.data_ptr(), out.data_ptr(), peer_bases.data_ptr<int64_t>(), mc_base, local_base, flag_off, data_off,
+                           half_bytes, (uint32_t*)state.data_ptr(), (int)rank, (int)world, x.numel() / world, dt_code(x), (int)ctas,
+                           stream());
+  return out;
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
@@ -463,4 +547,17 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("symm_open", &symm_open);
   m.def("symm_free", &nxd::symm_free);
   m.def("symm_view", &symm_view);
+  m.def("vmm_begin", &vmm_begin);
+  m.def("vmm_send", &nxd::vmm_send);
+  m.def("vmm_recv", &nxd::vmm_recv);
+  m.def("vmm_bind", &nxd::vmm_bind);
+  m.def("vmm_ptrs", &vmm_ptrs);
+  m.def("vmm_free", &nxd::vmm_free);
+  m.def("vmm_view", &vmm_view);
+  m.def("tp_gemm_nvls", &tp_gemm_nvls);
+  m.def("nvls_allreduce", &nvls_allreduce, py::arg("x"), py::arg("residual"), py::arg("peer_bases"), py::arg("mc_base"),
+        py::arg("local_base"), py::arg("flag_off"), py::arg("data_off"), py::arg("half_bytes"), py::arg("state"), py::arg("rank"),
+        py::arg("world"));
+  m.def("nvls_all_gather", &nvls_all_gather);
+  m.def("nvls_reduce_scatter", &nvls_reduce_scatter);
 }

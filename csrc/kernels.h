@@ -61,6 +61,22 @@ void gemm_bf16_2cta_tp(int mode, const void* a, const void* b, void* out_or_part
                        const int64_t* peer_flags, long buf_offset, int flag_offset, uint32_t epoch, int comm_ctas,
                        uint32_t* tile_done, uint32_t* gemm_done, uint32_t gemm_done_target, cudaStream_t st);
 
+// NVLS (multicast / in-switch reduce) variants, tp_nvls_sm100.cu
+int gemm_bf16_2cta_nvls(int mode, const void* a, const void* b, void* out, void* rs_out, const void* a_local, int M, int N, int K,
+                        bool trans_b, int rank, int world, const int64_t* peer_bases, int64_t mc_base, int64_t local_base,
+                        long buf_offset, long flag_offset, uint32_t epoch, int comm_ctas, uint32_t* tile_done, uint32_t* claim,
+                        uint32_t claim_base, bool wire_fp32, cudaStream_t st);
+
+// stand-alone NVLS collectives (nvls_coll.cu); `state` = [2 + 128] u32 device words (epoch, CTA counter, per-CTA barrier counts)
+void nvls_allreduce(const void* x, const void* residual, void* out, const int64_t* peer_bases, int64_t mc_base, int64_t local_base,
+                    long flag_off, long data_off, long half_bytes, uint32_t* state, int rank, int world, long numel, int dt,
+                    int ctas, cudaStream_t st);
+void nvls_all_gather(const void* x, void* out, const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off,
+                     long data_off, long half_bytes, uint32_t* state, int rank, int world, long bytes, int ctas, cudaStream_t st);
+void nvls_reduce_scatter(const void* x, void* out, const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off,
+                         long data_off, long half_bytes, uint32_t* state, int rank, int world, long chunk_numel, int dt, int ctas,
+                         cudaStream_t st);
+
 // ---- zero1_comm.cu
 void zero1_reduce_scatter(const int64_t* peer_bufs, long grad_off_bytes, const int64_t* peer_flags, int flag_off,
                           uint32_t epoch, int rank, int world, long shard_numel, long sub_begin, long sub_len, float scale,

@@ -194,11 +194,12 @@ class GQAQKVColumnParallelLinear(BaseParallelLayer):
         tp = self.tensor_model_parallel_size
         w, b = self._weights()
         in_mode = "gather" if self.sequence_parallel_enabled else ("copy" if tp > 1 else "none")
+        qp, kvp = self.q_output_size_per_partition, self.kv_output_size_per_partition
+        m = self.kv_size_multiplier
         out = tp_linear(input, w, None, in_mode, "none", self.sequence_dimension, self.tensor_parallel_group,
-                        self.reduce_dtype)
+                        self.reduce_dtype, dgrad_col_scale=(qp, 1.0 / m) if m > 1 else None)
         if b is not None:
             out = out + b
-        qp, kvp = self.q_output_size_per_partition, self.kv_output_size_per_partition
         q, k, v = torch.split(out, [qp, kvp, kvp], dim=-1)
         if self.kv_size_multiplier > 1:
             k = _KVGradSum.apply(k, self.kv_group, self.reduce_dtype)
@@ -271,7 +272,8 @@ def gqa_qkv_linear_with_async_allreduce(input: torch.Tensor, weight_q, weight_k,
         b = torch.cat([bias_q, bias_k, bias_v], dim=0) if bias_q is not None else None
         qp, kvp = weight_q.shape[0], weight_k.shape[0]
     in_mode = "gather" if sequence_parallel_enabled else ("copy" if (async_grad_allreduce and tp > 1) else "none")
-    out = tp_linear(input, w, None, in_mode, "none", sequence_dimension, group, reduce_dtype)
+    out = tp_linear(input, w, None, in_mode, "none", sequence_dimension, group, reduce_dtype,
+                    dgrad_col_scale=(qp, 1.0 / kv_size_multiplier) if kv_size_multiplier > 1 else None)
     if b is not None:
         out = out + b
     q, k, v = torch.split(out, [qp, kvp, kvp], dim=-1)

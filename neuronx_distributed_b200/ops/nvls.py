@@ -1,0 +1,88 @@
+"""Stand-alone collectives on the NVLS symmetric region (``csrc/nvls_coll.cu``): in-switch all-reduce
+(``multimem.ld_reduce``), multicast all-gather (``multimem.st``) and reduce-scatter — one kernel each, CUDA-graph
+capturable (the call counter lives in device memory), no NCCL call.  Without a multicast mapping (two ranks on one GPU in
+the loopback tests, fabrics without NVLS) the same kernels run over unicast peer pointers.
+
+Used by ``parallel_layers.comm.all_reduce`` for latency-bound tensors (decode-time RowParallelLinear /
+ParallelEmbedding outputs without sequence parallel — reference layers.py:1040-1043, mappings.py:196-211) and by
+``tools/nvls_probe.py`` for the link-bandwidth numbers in ``profiles/``.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _ext, symm
+
+_FLAG_BYTES = 4096                     # 128 per-CTA barrier counters, padded
+_STATE: Dict[tuple, "_Coll"] = {}
+
+
+class _Coll:
+    def __init__(self, group, kind: str, half_bytes: int):
+        self.group = group
+        self.half_bytes = int(half_bytes)
+        self.ws = symm.get_vmm_workspace(group, f"nvls_{kind}", _FLAG_BYTES + 2 * self.half_bytes)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.state = torch.zeros(2 + 128, dtype=torch.int32, device=dev)
+
+    @property
+    def args(self):
+        ws = self.ws
+        return (ws.ptrs, ws.mc_ptr, ws.local_ptr, 0, _FLAG_BYTES, self.half_bytes, self.state, ws.rank, ws.world)
+
+
+def _coll(group, kind: str, need_bytes: int, default_mb: int) -> _Coll:
+    key = (id(group), kind)
+    c = _STATE.get(key)
+    if c is None or c.half_bytes < need_bytes:
+        half = max(int(need_bytes), default_mb << 20)
+        half = (half + (1 << 21) - 1) & ~((1 << 21) - 1)
+        c = _STATE[key] = _Coll(group, kind, half)
+    return c
+
+
+def reset() -> None:
+    _STATE.clear()
+
+
+def available(group=None) -> bool:
+    e = _ext.ext()
+    return e is not None and hasattr(e, "nvls_allreduce") and symm.vmm_available()
+
+
+def has_multicast(group) -> bool:
+    """True when ``group``'s NVLS workspace got a multicast mapping (allocates the all-reduce workspace on first use)."""
+    return _coll(group, "ar", 0, int(os.environ.get("NXD_NVLS_AR_MAX_MB", "8"))).ws.has_multicast
+
+
+def all_reduce_sum(x: torch.Tensor, group, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``sum_over_ranks(x) (+ residual)`` as a new tensor.  bf16 / fp32, contiguous, bytes % 16 == 0."""
+    nbytes = x.numel() * x.element_size()
+    c = _coll(group, "ar", nbytes, int(os.environ.get("NXD_NVLS_AR_MAX_MB", "8")))
+    _ext.count_launch()
+    return _ext.ext().nvls_allreduce(x, residual, *c.args)
+
+
+def all_gather(x: torch.Tensor, group, ctas: int = 32) -> torch.Tensor:
+    """Concatenation over ranks along dim 0 (the shard is multicast into every rank's symmetric buffer, then copied out)."""
+    world = dist.get_world_size(group)
+    nbytes = x.numel() * x.element_size()
+    c = _coll(group, "ag", nbytes * world, 64)
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    _ext.count_launch()
+    _ext.ext().nvls_all_gather(x.contiguous(), out, *c.args, int(ctas))
+    return out
+
+
+def reduce_scatter_sum(x: torch.Tensor, group, ctas: int = 32) -> torch.Tensor:
+    """``x`` = [world * n, ...] on every rank → this rank's [n, ...] chunk of the sum."""
+    world = dist.get_world_size(group)
+    nbytes = x.numel() * x.element_size()
+    c = _coll(group, "rs", nbytes, 64)
+    _ext.count_launch()
+    out = _ext.ext().nvls_reduce_scatter(x.contiguous(), *c.args, int(ctas))
+    return out.view((x.shape[0] // world,) + tuple(x.shape[1:]))

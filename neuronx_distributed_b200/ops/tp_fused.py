@@ -52,7 +52,7 @@ class _NoComm:
         ms = out.shape[0] // self.world
         return out[:ms].contiguous().view(x.shape[0] // self.world, *x.shape[1:-1], weight.shape[0])
 
-    def backward(self, x, weight, gy, has_bias, need_gx, need_gw, gathered=None):
+    def backward(self, x, weight, gy, has_bias, need_gx, need_gw, gathered=None, gy_dgrad=None):
         from . import gemm
         from ..parallel_layers.layers import wgrad
 

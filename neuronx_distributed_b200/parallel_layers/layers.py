@@ -383,10 +383,11 @@ class _TPLinear(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight, bias, in_mode, out_mode, seq_dim, group, reduce_dtype, save_for_backward):
+    def forward(ctx, x, weight, bias, in_mode, out_mode, seq_dim, group, reduce_dtype, save_for_backward, dgrad_col_scale=None):
         from .. import ops
 
         ctx.in_mode, ctx.out_mode, ctx.seq_dim, ctx.group = in_mode, out_mode, seq_dim, group
+        ctx.dgrad_col_scale = dgrad_col_scale
         ctx.reduce_dtype = reduce_dtype
         ctx.has_bias = bias is not None
         ctx.x_requires_grad = x.requires_grad
@@ -429,6 +430,14 @@ class _TPLinear(torch.autograd.Function):
         in_mode, out_mode = ctx.in_mode, ctx.out_mode
         gbias = None
         gy = gy.contiguous()
+        # GQA with replicated KV heads: the K/V output gradients arrive summed over the KV-shared group (needed by wgrad);
+        # the input gradient is later summed over the whole TP group, so the dgrad GEMM sees those columns scaled by
+        # 1/multiplier (reference qkv_linear.py:183-198).
+        gy_d = gy
+        if ctx.dgrad_col_scale is not None and ctx.x_requires_grad:
+            start, scale = ctx.dgrad_col_scale
+            gy_d = gy.clone()
+            gy_d[..., start:] *= scale
         if ctx.fused:
             if ctx.has_gathered:
                 x, weight, gathered = ctx.saved_tensors
@@ -436,8 +445,8 @@ class _TPLinear(torch.autograd.Function):
                 (x, weight), gathered = ctx.saved_tensors, None
             fused = ops.tp_fused.dispatch(x, weight, in_mode, out_mode, seq_dim, group)
             gx, gw, gbias = fused.backward(x, weight, gy, ctx.has_bias, ctx.x_requires_grad, weight.requires_grad,
-                                           gathered)
-            return gx, gw, gbias, None, None, None, None, None, None
+                                           gathered, gy_dgrad=(gy_d if gy_d is not gy else None))
+            return gx, gw, gbias, None, None, None, None, None, None, None
         x, weight = ctx.saved_tensors
 
         # ---- grad wrt the GEMM output (undo the output collective) -----------------
@@ -452,7 +461,8 @@ class _TPLinear(torch.autograd.Function):
         gx = None
         work = None
         if ctx.x_requires_grad:
-            gx = ops.gemm.matmul(_flat2d(g_out), weight, False, False).view(*g_out.shape[:-1], weight.shape[1])
+            g_d = g_out if gy_d is gy else gy_d          # dgrad_col_scale is only used with out_mode "none" (g_out is gy)
+            gx = ops.gemm.matmul(_flat2d(g_d), weight, False, False).view(*g_out.shape[:-1], weight.shape[1])
             if n > 1 and in_mode == "copy":
                 work = comm.all_reduce(gx, group=group, async_op=True)  # overlaps wgrad
             elif n > 1 and in_mode == "gather":
@@ -466,7 +476,7 @@ class _TPLinear(torch.autograd.Function):
             gw = wgrad(_flat2d(g_out), _flat2d(total), weight)
         if work is not None:
             work.wait()
-        return gx, gw, gbias, None, None, None, None, None, None
+        return gx, gw, gbias, None, None, None, None, None, None, None
 
 
 def tp_linear(
@@ -480,7 +490,11 @@ def tp_linear(
     reduce_dtype: Optional[torch.dtype] = None,
     save_for_backward: bool = True,
     autocast: bool = False,
+    dgrad_col_scale=None,
 ) -> torch.Tensor:
+    """``dgrad_col_scale=(first_col, scale)``: output-gradient columns ``>= first_col`` are multiplied by ``scale`` for the
+    input-gradient GEMM only (weight gradient sees them unscaled) — the GQA KV-replication correction."""
+    assert dgrad_col_scale is None or out_mode == "none"
     group = group if group is not None else ps.get_tensor_model_parallel_group()
     if autocast or torch.is_autocast_enabled():
         dt = torch.get_autocast_dtype("cuda" if x.is_cuda else "cpu") if torch.is_autocast_enabled() else x.dtype
@@ -488,8 +502,9 @@ def tp_linear(
         weight = weight.to(dt)
         bias = bias.to(dt) if bias is not None else None
         with torch.autocast(device_type="cuda" if x.is_cuda else "cpu", enabled=False):
-            return _TPLinear.apply(x, weight, bias, in_mode, out_mode, seq_dim, group, reduce_dtype, save_for_backward)
-    return _TPLinear.apply(x, weight, bias, in_mode, out_mode, seq_dim, group, reduce_dtype, save_for_backward)
+            return _TPLinear.apply(x, weight, bias, in_mode, out_mode, seq_dim, group, reduce_dtype, save_for_backward,
+                                   dgrad_col_scale)
+    return _TPLinear.apply(x, weight, bias, in_mode, out_mode, seq_dim, group, reduce_dtype, save_for_backward, dgrad_col_scale)
 
 
 class LinearWithAsyncCommunication:
