@@ -14,6 +14,7 @@ synthetic tokens and random-init weights.  Rank 0 prints ONE JSON line.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -40,9 +41,12 @@ def parse():
     ap.add_argument("--backend", default=os.environ.get("NXD_TP_BACKEND", "fused"), choices=["fused", "nccl"])
     ap.add_argument("--act-ckpt", default="none", choices=["none", "full"])
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--comm-report", action="store_true",
-                    help="extra pass after the timed regions: same step with the TP collectives replaced by local copies → reports the "
-                         "exposed TP-collective time per step (opt-in until validated on hardware)")
+    ap.add_argument("--no-comm-report", action="store_true",
+                    help="skip the extra pass after the timed regions (same step with the TP collectives replaced by local copies) "
+                         "that reports the exposed TP-collective time per step")
+    ap.add_argument("--tp", type=int, default=0, help="tensor-parallel degree (default: gpus / dp)")
+    ap.add_argument("--dp", type=int, default=1, help="data-parallel degree: ZeRO-1 shards the optimizer over it and its gradient "
+                                                      "reduce-scatter kernel runs in the step (BASELINE config 3: --gpus 8 --tp 4 --dp 2)")
     ap.add_argument("--micro-batch", type=int, default=0,
                     help="sequences per forward/backward (0 = auto: 2 up to 2 GPUs, 4 beyond — fewer fp32 wgrad read-modify-write "
                          "passes and TP collectives off their latency floor; 4 does not fit in 180 GB at TP=1); same value in both arms")
@@ -112,6 +116,28 @@ def run_reference(args):
         return 0
 
 
+def _tp_comm_info(tp: int, backend: str) -> dict:
+    """What crosses NVLink on the TP hot path, stated in the JSON line (wire precision must be in `config`)."""
+    if tp == 1:
+        return {"tp_collectives": "none (tp=1)", "wire_dtype": "n/a"}
+    if backend != "fused":
+        return {"tp_collectives": "NCCL all-gather / reduce-scatter + own GEMM", "wire_dtype": "fp32 reduce-scatter (reduce_dtype), bf16 all-gather"}
+    try:
+        from neuronx_distributed_b200.ops import _fused_impl
+        from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+        ws = _fused_impl.workspace(ps.get_tensor_model_parallel_group())
+        if ws.nv is not None and ws.nvls_enabled():
+            mode = "NVLS multimem.st all-gather / multimem.ld_reduce reduce-scatter fused in the GEMM kernels" if ws.nv.has_multicast \
+                else "NVLS kernels on unicast peer pointers (no multicast mapping)"
+            wd = _fused_impl.wire_dtype()
+            return {"tp_collectives": mode,
+                    "wire_dtype": "bf16 partials, fp32 accumulation in the switch (one rounding)" if wd == "bf16" else "fp32 partials (reference reduce_dtype)"}
+        return {"tp_collectives": "cudaIpc peer pushes fused in the GEMM kernels", "wire_dtype": "bf16 partials, fp32 accumulation at the owner"}
+    except Exception as e:  # noqa: BLE001
+        return {"tp_collectives": f"unknown ({type(e).__name__})", "wire_dtype": "unknown"}
+
+
 def _micro_batch(args) -> int:
     mbs = args.micro_batch if args.micro_batch > 0 else {1: 2, 2: 2, 4: 4, 8: 4}.get(args.gpus, 1)
     mbs = max(1, min(mbs, args.global_batch))
@@ -143,7 +169,11 @@ def main():
     from neuronx_distributed_b200.utils.adamw_fp32_optim_params import AdamW_FP32OptimParams
 
     ops.tp_fused.set_backend(args.backend)
-    tp = world
+    dp = max(1, args.dp)
+    tp = args.tp if args.tp > 0 else world // dp
+    assert tp * dp == world, f"--tp {tp} x --dp {dp} != {world} GPUs"
+    if dp > 1:
+        os.environ.setdefault("NXD_ZERO1_OVERLAP", "1")        # bucketed reduce-scatter launched under the backward
     sp = tp > 1
     cfg = nxd.neuronx_distributed_config(
         tensor_parallel_size=tp, sequence_parallel=sp,
@@ -164,6 +194,14 @@ def main():
                                             betas=(0.9, 0.95), weight_decay=0.1)
     gbs, S = args.global_batch, args.seq
     mbs = _micro_batch(args)
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    dp_rank = ps.get_data_parallel_rank()
+    assert gbs % dp == 0, "global batch must divide by dp"
+    per_dp = gbs // dp
+    mbs = max(1, min(mbs, per_dp))
+    while per_dp % mbs:
+        mbs -= 1
     V = mcfg.vocab_size
     gen = torch.Generator().manual_seed(7)
     n_host = args.steps + args.warmup + 2
@@ -173,12 +211,16 @@ def main():
     def train_step(ids_dev):
         opt.zero_grad()
         total = None
-        for mb in range(0, gbs, mbs):
+        n_mb = per_dp // mbs
+        for i, mb in enumerate(range(dp_rank * per_dp, (dp_rank + 1) * per_dp, mbs)):
             ids = ids_dev[mb:mb + mbs]
-            loss = model.run_train(input_ids=ids, labels=ids)
+            # gradient accumulation: only the last micro-batch may release ZeRO-1 buckets to the overlapped reduce-scatter
+            ctx = opt.no_sync() if (dp > 1 and i < n_mb - 1 and hasattr(opt, "no_sync")) else contextlib.nullcontext()
+            with ctx:
+                loss = model.run_train(input_ids=ids, labels=ids)
             total = loss if total is None else total + loss
         opt.step()
-        return total / (gbs // mbs)
+        return total / n_mb
 
     def sync():
         dist.barrier()
@@ -238,7 +280,7 @@ def main():
     #      the same shape ("nocomm" backend, numerically meaningless) → exposed = t(step) − t(nocomm step).  Runs last because it
     #      trashes the weights; any failure only drops this key.
     comm_report = None
-    if world > 1 and args.backend == "fused" and args.comm_report:
+    if tp > 1 and args.backend == "fused" and not args.no_comm_report:
         try:
             ops.tp_fused.set_backend("nocomm")
             train_step(dev_ids[0])
@@ -268,8 +310,11 @@ def main():
             "vs_baseline": value / PUBLISHED_TOKENS_PER_S, "dtype": "bf16", "data": "synthetic",
             "impl": "ours",
             "config": {"model": "llama2-7b" if args.layers == 32 else f"llama2-7b-{args.layers}L(debug)",
-                       "global_batch": gbs, "micro_batch": mbs, "seq_len": S, "parallelism": f"tp{tp}" + ("+sp" if sp else ""),
-                       "optimizer": "AdamW fp32 master + fp32 grad-acc (ZeRO-1, dp=1)", "tp_backend": args.backend,
+                       "global_batch": gbs, "micro_batch": mbs, "seq_len": S,
+                       "parallelism": f"tp{tp}" + ("+sp" if sp else "") + (f" x dp{dp}" if dp > 1 else ""),
+                       "optimizer": f"AdamW fp32 master + fp32 grad-acc (ZeRO-1, dp={dp}"
+                                    + (", bucketed reduce-scatter overlapped with backward" if dp > 1 else "") + ")",
+                       "tp_backend": args.backend, **_tp_comm_info(tp, args.backend),
                        "act_ckpt": args.act_ckpt, "l2": "inputs(weights+activations)>>L2, no flush needed",
                        "baseline_note": "vs_baseline divides by the only published number: Trn1 32-core gate 6.90 seq/s @ seq 8192",
                        "final_loss": final_loss, "loss_trace": [round(float(x), 4) for x in trace],

@@ -23,10 +23,10 @@ namespace g2 {
 template <bool A_KMAJOR, bool B_KMAJOR, typename OutT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                      OutT* __restrict__ out, int M, int N, int K, int accumulate) {
+                      const __grid_constant__ CUtensorMap tma_out, OutT* __restrict__ out, int M, int N, int K, int accumulate) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + kStages * kStageBytes);
+  uint64_t* bars = (uint64_t*)(smem + kBarOffset);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kStages + 2 * kAcc);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStages);
   const uint32_t bar_tfull = smem_u32(bars + 2 * kStages), bar_tempty = smem_u32(bars + 2 * kStages + kAcc);
@@ -124,28 +124,37 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     // ===== epilogue (both CTAs; own 128 TMEM lanes) =====
     const int q = warp & 3;
     const uint32_t tempty_leader = mapa_shared(bar_tempty, 0);
+    const bool use_tma_store = sizeof(OutT) == 2 && !accumulate;     // fp32 / read-modify-write outputs keep direct stores
+    const bool issuer = threadIdx.x == 64;
+    uint32_t slab_ctr = 0;
     int as = 0; uint32_t aphase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       int m_blk, n_blk;
       tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
       mbar_wait(bar_tfull + 8 * as, aphase);
       tcgen05_fence_after();
-      const int row = m_blk * TILE_M + (int)cta * CTA_M + q * 32 + lane;
       const int n0 = n_blk * TILE_N;
-      OutT* orow = out + (size_t)row * N;
-      const bool row_ok = row < M;
+      if (use_tma_store) {
+        epilogue_tile_tma(tmem_base + ((uint32_t)(q * 32) << 16) + as * TILE_N, smem_base + kEpiOffset, &tma_out,
+                          m_blk * TILE_M + (int)cta * CTA_M, n0, N, q, lane, issuer, slab_ctr);
+      } else {
+        const int row = m_blk * TILE_M + (int)cta * CTA_M + q * 32 + lane;
+        OutT* orow = out + (size_t)row * N;
+        const bool row_ok = row < M;
 #pragma unroll 1
-      for (int c = 0; c < TILE_N / 32; ++c) {
-        uint32_t r[32];
-        tcgen05_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * TILE_N + c * 32, r);
-        tcgen05_wait_ld();
-        const int col0 = n0 + c * 32;
-        if (row_ok && col0 < N) store_chunk<OutT>(orow, col0, N, r, accumulate);
+        for (int c = 0; c < TILE_N / 32; ++c) {
+          uint32_t r[32];
+          tcgen05_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * TILE_N + c * 32, r);
+          tcgen05_wait_ld();
+          const int col0 = n0 + c * 32;
+          if (row_ok && col0 < N) store_chunk<OutT>(orow, col0, N, r, accumulate);
+        }
       }
       tcgen05_fence_before();
       mbar_arrive_cluster(tempty_leader + 8 * as);   // leader's barrier collects both CTAs' epilogues
       if (++as == kAcc) { as = 0; aphase ^= 1; }
     }
+    if (issuer) bulk_wait<0>();      // staging smem must outlive the last stores' reads; output complete at kernel end
   }
 
   tcgen05_fence_before();
@@ -327,7 +336,7 @@ gemm_bf16_2cta_tp_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   using OutT = __nv_bfloat16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + kStages * kStageBytes);
+  uint64_t* bars = (uint64_t*)(smem + kBarOffset);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kStages + 2 * kAcc);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStages);
   const uint32_t bar_tfull = smem_u32(bars + 2 * kStages), bar_tempty = smem_u32(bars + 2 * kStages + kAcc);
@@ -656,15 +665,15 @@ CUtensorMap make_tmap_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint32
 int device_sm_count();
 
 template <bool AK, bool BK_, typename OutT>
-static void launch2(const CUtensorMap& ta, const CUtensorMap& tb, void* out, int M, int N, int K, bool accumulate, int grid,
-                    cudaStream_t st) {
+static void launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, void* out, int M, int N, int K,
+                    bool accumulate, int grid, cudaStream_t st) {
   auto kern = g2::gemm_bf16_2cta_kernel<AK, BK_, OutT>;
   static bool configured = false;
   if (!configured) {
     NXD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::kSmem));
     configured = true;
   }
-  kern<<<grid, g2::kThreads, g2::kSmem, st>>>(ta, tb, (OutT*)out, M, N, K, accumulate ? 1 : 0);
+  kern<<<grid, g2::kThreads, g2::kSmem, st>>>(ta, tb, to, (OutT*)out, M, N, K, accumulate ? 1 : 0);
   NXD_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -673,13 +682,17 @@ void gemm_bf16_2cta(const void* a, const void* b, void* out, int M, int N, int K
   const bool AK = !trans_a, BK_ = trans_b;
   const CUtensorMap ta = AK ? make_tmap_bf16(a, M, K, g2::BK, g2::CTA_M) : make_tmap_bf16(a, K, M, 64, g2::BK);
   const CUtensorMap tb = BK_ ? make_tmap_bf16(b, N, K, g2::BK, g2::HALF_N) : make_tmap_bf16(b, K, N, 64, g2::BK);
+  // output map for the TMA-store epilogue (bf16, non-accumulating; needs a 16-byte row pitch) — otherwise a dummy
+  const bool tma_out_ok = out_dt == kBF16 && !accumulate && N % 8 == 0;
+  const CUtensorMap to = tma_out_ok ? make_tmap_bf16(out, M, N, g2::kEpiSlabCols, g2::CTA_M) : ta;
+  if (out_dt == kBF16 && !accumulate && !tma_out_ok) nxd_throw("gemm_bf16_2cta: bf16 output needs N % 8 == 0", __FILE__, __LINE__);
   const int tiles = ((M + g2::TILE_M - 1) / g2::TILE_M) * ((N + g2::TILE_N - 1) / g2::TILE_N);
   const int pairs = device_sm_count() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
 #define NXD_L2(AKv, BKv)                                                                          \
   do {                                                                                            \
-    if (out_dt == kBF16) launch2<AKv, BKv, __nv_bfloat16>(ta, tb, out, M, N, K, accumulate, grid, st); \
-    else launch2<AKv, BKv, float>(ta, tb, out, M, N, K, accumulate, grid, st);                   \
+    if (out_dt == kBF16) launch2<AKv, BKv, __nv_bfloat16>(ta, tb, to, out, M, N, K, accumulate, grid, st); \
+    else launch2<AKv, BKv, float>(ta, tb, to, out, M, N, K, accumulate, grid, st);               \
   } while (0)
   if (AK && BK_) NXD_L2(true, true);
   else if (AK && !BK_) NXD_L2(true, false);

@@ -109,14 +109,14 @@ NXD_DEVICE void nvls_coords_rs(int tile, int tiles_n, const NvlsComm& c, int& m_
 template <bool B_KMAJOR, int MODE, bool WIRE32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_bf16_2cta_nvls_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                           const __grid_constant__ CUtensorMap tma_a_local, void* __restrict__ out_raw, int M, int N, int K,
-                           NvlsComm comm) {
+                           const __grid_constant__ CUtensorMap tma_a_local, const __grid_constant__ CUtensorMap tma_out,
+                           void* __restrict__ out_raw, int M, int N, int K, NvlsComm comm) {
   using OutT = typename std::conditional<(MODE == 2 && WIRE32), float, __nv_bfloat16>::type;
   OutT* out = (OutT*)out_raw;
   extern __shared__ uint8_t smem_raw[];
   __shared__ int s_item;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + kStages * kStageBytes);
+  uint64_t* bars = (uint64_t*)(smem + kBarOffset);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kStages + 2 * kAcc);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStages);
   const uint32_t bar_tfull = smem_u32(bars + 2 * kStages), bar_tempty = smem_u32(bars + 2 * kStages + kAcc);
@@ -136,6 +136,7 @@ gemm_bf16_2cta_nvls_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
     prefetch_tmap(&tma_a);
     prefetch_tmap(&tma_b);
     prefetch_tmap(&tma_a_local);
+    prefetch_tmap(&tma_out);
     for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 2); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < kAcc; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 2 * 128); }
     fence_barrier_init();
@@ -154,20 +155,55 @@ gemm_bf16_2cta_nvls_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
       constexpr int rows_part = CTA_M / kAgParts;
       const int items = blk128_per_rank * kAgParts;
       const size_t nvec = (size_t)rows_part * K / 8;          // 16-byte vectors per item
+      int ring_pos = 0;
+      uint32_t ring_phases = 0;
       for (int it = blockIdx.x; it < items; it += comm.comm_ctas) {
         const int mb = it / kAgParts, part = it - mb * kAgParts;
         const size_t row0 = (size_t)mb * CTA_M + part * rows_part;
         const uint4* src = (const uint4*)((const uint8_t*)comm.a_local + row0 * K * 2);
         const size_t dst_off = (size_t)comm.buf_offset + ((size_t)comm.rank * comm.rows_per_rank + row0) * K * 2;
         if (comm.mc_base != nullptr) {
-          uint4* dst = (uint4*)(comm.mc_base + dst_off);
-          for (size_t base = threadIdx.x; base < nvec; base += (size_t)U * kThreads) {
-            uint4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) { const size_t i = base + (size_t)u * kThreads; if (i < nvec) v[u] = ld_nc_v4(src + i); }
-#pragma unroll
-            for (int u = 0; u < U; ++u) { const size_t i = base + (size_t)u * kThreads; if (i < nvec) multimem_st_v4(dst + i, v[u]); }
+          // Stage the item through this CTA's (otherwise idle) 192 KB GEMM ring with TMA bulk loads — six 32 KB chunks
+          // in flight per CTA without a data register — and fan it out with multimem.st from shared memory.  (The first
+          // version kept 8 x 16 B per thread in registers: 24 KB in flight per CTA, measured 13 GB/s per CTA.)
+          constexpr uint32_t CH = (uint32_t)kStageBytes;
+          const uint32_t item_bytes = (uint32_t)(nvec * 16);
+          const int nch = (int)((item_bytes + CH - 1) / CH);
+          auto chunk_bytes = [&](int c) { return min(CH, item_bytes - (uint32_t)c * CH); };
+          uint8_t* dst = comm.mc_base + dst_off;
+          // prologue: fill the ring (stages are free: the previous item ended with a CTA barrier after its last reads)
+          if (threadIdx.x == 0) {
+            for (int c = 0; c < nch && c < kStages; ++c) {
+              const uint32_t b = bar_empty + 8 * ((ring_pos + c) % kStages), nb = chunk_bytes(c);
+              mbar_expect_tx(b, nb);
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                           ::"r"(smem_base + ((ring_pos + c) % kStages) * CH), "l"((const uint8_t*)src + (size_t)c * CH), "r"(nb), "r"(b)
+                           : "memory");
+            }
           }
+          for (int c = 0; c < nch; ++c) {
+            const int st = (ring_pos + c) % kStages;
+            mbar_wait(bar_empty + 8 * st, (ring_phases >> st) & 1u);
+            ring_phases ^= 1u << st;
+            const uint32_t nb = chunk_bytes(c);
+            const uint32_t sbase = smem_base + st * CH;
+            uint8_t* d = dst + (size_t)c * CH;
+            for (uint32_t o = threadIdx.x * 16u; o < nb; o += kThreads * 16u) {
+              uint4 v;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sbase + o));
+              multimem_st_v4(d + o, v);
+            }
+            if (c + kStages < nch) {
+              __syncthreads();                                   // everyone has read this stage: refill it
+              if (threadIdx.x == 0) {
+                const uint32_t b = bar_empty + 8 * st, nb2 = chunk_bytes(c + kStages);
+                mbar_expect_tx(b, nb2);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sbase), "l"((const uint8_t*)src + (size_t)(c + kStages) * CH), "r"(nb2), "r"(b) : "memory");
+              }
+            }
+          }
+          ring_pos = (ring_pos + nch) % kStages;
         } else {
           for (size_t base = threadIdx.x; base < nvec; base += (size_t)U * kThreads) {
             uint4 v[U];
@@ -266,6 +302,18 @@ gemm_bf16_2cta_nvls_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
     // ===== epilogue (both CTAs; own 128 TMEM lanes) =====
     const int q = warp & 3;
     const uint32_t tempty_leader = mapa_shared(bar_tempty, 0);
+    const bool issuer = threadIdx.x == 64;
+    uint32_t slab_ctr = 0;
+    int prev_gblk = -1;
+    // MODE 2: a finished 128-row block of partials is announced to its owner (by whichever CTA stored its last tile)
+    auto signal_block = [&](int gblk) {
+      if (atom_add_acqrel_gpu(comm.tile_done + gblk, 1u) == (uint32_t)(tiles_n - 1)) {
+        comm.tile_done[gblk] = 0;                                    // re-arm for the next call
+        const int owner = gblk / blk128_per_rank, mb = gblk - owner * blk128_per_rank;
+        uint32_t* f = (uint32_t*)((uint8_t*)comm.peer_bases[owner] + comm.flag_offset) + (size_t)comm.rank * kNvlsMaxRowBlocks + mb;
+        st_release_sys(f, comm.epoch);
+      }
+    };
     int as = 0; uint32_t aphase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       int m_blk, n_blk;
@@ -273,35 +321,53 @@ gemm_bf16_2cta_nvls_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
       else nvls_coords_rs(tile, tiles_n, comm, m_blk, n_blk);
       mbar_wait(bar_tfull + 8 * as, aphase);
       tcgen05_fence_after();
-      const int row = m_blk * TILE_M + (int)cta * CTA_M + q * 32 + lane;
+      const int row0 = m_blk * TILE_M + (int)cta * CTA_M;
       const int n0 = n_blk * TILE_N;
-      OutT* orow = out + (size_t)row * N;
+      if constexpr (MODE == 2 && WIRE32) {
+        OutT* orow = out + (size_t)(row0 + q * 32 + lane) * N;
 #pragma unroll 1
-      for (int c = 0; c < TILE_N / 32; ++c) {
-        uint32_t r[32];
-        tcgen05_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * TILE_N + c * 32, r);
-        tcgen05_wait_ld();
-        const int col0 = n0 + c * 32;
-        if (col0 < N) store_chunk<OutT>(orow, col0, N, r, 0);
-      }
-      tcgen05_fence_before();
-      mbar_arrive_cluster(tempty_leader + 8 * as);
-      if constexpr (MODE == 2) {
-        // partial tile → visible system-wide, then count it; whoever completes the 128-row block tells its owner
-        __threadfence_system();
+        for (int c = 0; c < TILE_N / 32; ++c) {
+          uint32_t r[32];
+          tcgen05_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * TILE_N + c * 32, r);
+          tcgen05_wait_ld();
+          const int col0 = n0 + c * 32;
+          if (col0 < N) store_chunk<OutT>(orow, col0, N, r, 0);
+        }
+        tcgen05_fence_before();
+        mbar_arrive_cluster(tempty_leader + 8 * as);
+        __threadfence_system();                                       // partial tile visible system-wide, then count it
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) {
-          const int gblk = (m_blk * TILE_M + (int)cta * CTA_M) / CTA_M;
-          if (atom_add_acqrel_gpu(comm.tile_done + gblk, 1u) == (uint32_t)(tiles_n - 1)) {
-            comm.tile_done[gblk] = 0;                                    // re-arm for the next call
-            const int owner = gblk / blk128_per_rank, mb = gblk - owner * blk128_per_rank;
-            uint32_t* f = (uint32_t*)((uint8_t*)comm.peer_bases[owner] + comm.flag_offset) +
-                          (size_t)comm.rank * kNvlsMaxRowBlocks + mb;
-            st_release_sys(f, comm.epoch);
+        if (issuer) signal_block(row0 / CTA_M);
+      } else {
+        const int groups = epilogue_tile_tma(tmem_base + ((uint32_t)(q * 32) << 16) + as * TILE_N, smem_base + kEpiOffset, &tma_out,
+                                             row0, n0, N, q, lane, issuer, slab_ctr);
+        tcgen05_fence_before();
+        mbar_arrive_cluster(tempty_leader + 8 * as);
+        if constexpr (MODE == 2) {
+          // the TMA stores of THIS tile stay in flight; the previous tile's are complete once at most `groups` bulk groups
+          // are pending → announce the previous tile now (one tile of latency instead of a drain per tile)
+          if (issuer) {
+            if (prev_gblk >= 0) {
+              bulk_wait_n(groups);
+              fence_proxy_async_global();
+              __threadfence_system();
+              signal_block(prev_gblk);
+            }
+            prev_gblk = row0 / CTA_M;
           }
         }
       }
       if (++as == kAcc) { as = 0; aphase ^= 1; }
+    }
+    if (issuer) {
+      bulk_wait<0>();
+      if constexpr (MODE == 2 && !WIRE32) {
+        if (prev_gblk >= 0) {
+          fence_proxy_async_global();
+          __threadfence_system();
+          signal_block(prev_gblk);
+        }
+      }
     }
   }
 
@@ -389,15 +455,15 @@ CUtensorMap make_tmap_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint32
 int device_sm_count();
 
 template <bool BK_, int MODE, bool W32>
-static void launch_nvls(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, void* out, int M, int N, int K,
-                        const g2::NvlsComm& c, int grid, cudaStream_t st) {
+static void launch_nvls(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& to, void* out, int M,
+                        int N, int K, const g2::NvlsComm& c, int grid, cudaStream_t st) {
   auto kern = g2::gemm_bf16_2cta_nvls_kernel<BK_, MODE, W32>;
   static bool configured = false;
   if (!configured) {
     NXD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::kSmem));
     configured = true;
   }
-  kern<<<grid, g2::kThreads, g2::kSmem, st>>>(ta, tb, tal, out, M, N, K, c);
+  kern<<<grid, g2::kThreads, g2::kSmem, st>>>(ta, tb, tal, to, out, M, N, K, c);
   NXD_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -423,17 +489,19 @@ int gemm_bf16_2cta_nvls(int mode, const void* a, const void* b, void* out, void*
     const CUtensorMap ta = make_tmap_bf16(payload, M, K, g2::BK, g2::CTA_M);
     const CUtensorMap tal = make_tmap_bf16(a_local, c.rows_per_rank, K, g2::BK, g2::CTA_M);
     const CUtensorMap tb = trans_b ? make_tmap_bf16(b, N, K, g2::BK, g2::HALF_N) : make_tmap_bf16(b, K, N, 64, g2::BK);
-    if (trans_b) launch_nvls<true, 1, false>(ta, tb, tal, out, M, N, K, c, grid, st);
-    else launch_nvls<false, 1, false>(ta, tb, tal, out, M, N, K, c, grid, st);
+    const CUtensorMap to = make_tmap_bf16(out, M, N, g2::kEpiSlabCols, g2::CTA_M);
+    if (trans_b) launch_nvls<true, 1, false>(ta, tb, tal, to, out, M, N, K, c, grid, st);
+    else launch_nvls<false, 1, false>(ta, tb, tal, to, out, M, N, K, c, grid, st);
     return 0;
   }
   const CUtensorMap ta = make_tmap_bf16(a, M, K, g2::BK, g2::CTA_M);
   const CUtensorMap tb = trans_b ? make_tmap_bf16(b, N, K, g2::BK, g2::HALF_N) : make_tmap_bf16(b, K, N, 64, g2::BK);
   void* partial = (void*)payload;
-  if (trans_b) { if (wire_fp32) launch_nvls<true, 2, true>(ta, tb, ta, partial, M, N, K, c, grid, st);
-                 else launch_nvls<true, 2, false>(ta, tb, ta, partial, M, N, K, c, grid, st); }
-  else { if (wire_fp32) launch_nvls<false, 2, true>(ta, tb, ta, partial, M, N, K, c, grid, st);
-         else launch_nvls<false, 2, false>(ta, tb, ta, partial, M, N, K, c, grid, st); }
+  const CUtensorMap to = wire_fp32 ? ta : make_tmap_bf16(partial, M, N, g2::kEpiSlabCols, g2::CTA_M);
+  if (trans_b) { if (wire_fp32) launch_nvls<true, 2, true>(ta, tb, ta, to, partial, M, N, K, c, grid, st);
+                 else launch_nvls<true, 2, false>(ta, tb, ta, to, partial, M, N, K, c, grid, st); }
+  else { if (wire_fp32) launch_nvls<false, 2, true>(ta, tb, ta, to, partial, M, N, K, c, grid, st);
+         else launch_nvls<false, 2, false>(ta, tb, ta, to, partial, M, N, K, c, grid, st); }
   return (c.rows_per_rank / g2::CTA_M) * (g2::CTA_M / g2::kRsRowsPerItem) + grid;
 }
 

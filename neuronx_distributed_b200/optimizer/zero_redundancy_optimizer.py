@@ -204,6 +204,17 @@ class Zero1Optimizer(torch.optim.Optimizer):
         self._slot_buckets = {}     # id(param) -> [bucket index]
         self._overlap_active = (self.overlap_grad_reduce and self.world > 1
                                 and all(fg.arena is not None for fg in self.flat_groups))
+        tp = 1
+        if self._overlap_active and ps.model_parallel_is_initialized():
+            tp = ps.get_tensor_model_parallel_size()
+            # context parallel averages EVERY gradient over the CP group at step() (grads.allreduce_context_parallel_gradients)
+            # and the pipeline engine back-propagates several micro-batches per step without a no_sync() bracket: in both
+            # cases a bucket reduced during backward would miss contributions → fall back to the reduce-scatter at step()
+            if ps.get_context_model_parallel_size() > 1 or ps.get_pipeline_model_parallel_size() > 1:
+                from ..utils.logger import get_logger
+
+                get_logger("zero1").warning("overlap_grad_reduce disabled: context/pipeline parallelism finalise gradients at step()")
+                self._overlap_active = False
         if not self._overlap_active:
             return
         for fg in self.flat_groups:
@@ -216,7 +227,12 @@ class Zero1Optimizer(torch.optim.Optimizer):
                 bi = len(self._buckets)
                 # a weight used more than once per backward (tied embeddings: `shared`) signals once per use through
                 # the fused wgrad epilogue, so its buckets are never launched early (count + 1 is never reached)
-                tied = any(getattr(s.param, "shared", False) for s in members)
+                # ... and so are weights with more than one use per backward that are not PP-`shared`
+                # (tie_word_embeddings without PP: the fused lm_head wgrad signals before the embedding gradient arrives).
+                # Sequence-parallel-tagged parameters (norm / bias / router weights, TP all-reduce of their gradient at
+                # step() in the reference, grads.py:330-346) get that all-reduce in the gradient hook instead, see
+                # `_grad_ready`, so their buckets can still go early.
+                tied = any(getattr(s.param, "shared", False) or getattr(s.param, "_nxd_multi_use", False) for s in members)
                 self._buckets.append((fg, begin, end, len(members) + (1 if tied else 0)))
                 for s in members:
                     self._slot_buckets.setdefault(id(s.param), []).append(bi)
@@ -224,6 +240,7 @@ class Zero1Optimizer(torch.optim.Optimizer):
             for s in fg.slots:
                 s.param._nxd_grad_ready = self._grad_ready
         self._comm_stream = torch.cuda.Stream()
+        self._sp_eager_tp = tp > 1
         self._reset_buckets()
 
     def _reset_buckets(self) -> None:
@@ -250,9 +267,15 @@ class Zero1Optimizer(torch.optim.Optimizer):
     def _grad_ready(self, param) -> None:
         if not (self._overlap_active and self._sync_enabled):
             return
+        if getattr(self, "_sp_eager_tp", False) and getattr(param, "sequence_parallel_enabled", False) \
+                and not getattr(param, "_nxd_sp_reduced", False):
+            # this rank saw S/tp of the tokens: the gradient is final only after the TP sum.  Done here (a few KB, one-shot
+            # all-reduce) so the bucket can be reduce-scattered under the backward; NxDOptimizer.step skips it later.
+            comm.all_reduce(param.main_grad, group=ps.get_tensor_model_parallel_group())
+            param._nxd_sp_reduced = True
         for bi in self._slot_buckets.get(id(param), ()):
             self._bucket_remaining[bi] -= 1
-            if self._bucket_remaining[bi] == 0 and not self._bucket_launched[bi] and not getattr(param, "shared", False):
+            if self._bucket_remaining[bi] == 0 and not self._bucket_launched[bi]:
                 self._launch_bucket(bi)
 
     def _launch_bucket(self, bi: int) -> None:
@@ -291,6 +314,8 @@ class Zero1Optimizer(torch.optim.Optimizer):
             for s in fg.slots:
                 s.param.grad = None
                 s.param.main_grad_fresh = True
+                if getattr(s.param, "_nxd_sp_reduced", False):
+                    s.param._nxd_sp_reduced = False
         if getattr(self, "_overlap_active", False):
             self._reset_buckets()
 

@@ -220,7 +220,10 @@ def allreduce_sequence_parallel_gradients(optimizer) -> None:
     TP rank → sum their grads over TP (coalesced per dtype)."""
     if ps.get_tensor_model_parallel_size() == 1:
         return
-    grads = _optimizer_grads(optimizer, lambda p: getattr(p, "sequence_parallel_enabled", False))
+    # `_nxd_sp_reduced`: the ZeRO-1 optimizer already summed this gradient over TP in its gradient hook (overlapped
+    # reduce-scatter mode), once, on the fully accumulated value
+    grads = _optimizer_grads(optimizer, lambda p: getattr(p, "sequence_parallel_enabled", False)
+                             and not getattr(p, "_nxd_sp_reduced", False))
     by_dtype: Dict[torch.dtype, List[torch.Tensor]] = {}
     for g in grads:
         by_dtype.setdefault(g.dtype, []).append(g)

@@ -78,6 +78,16 @@ class NxDOptimizer(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = True) -> None:
         self.optimizer.zero_grad(set_to_none=set_to_none)
 
+    def no_sync(self):
+        """Context manager for the non-final micro-batches of a gradient-accumulation step (DDP semantics): the ZeRO-1
+        optimizer does not release gradient buckets to its overlapped reduce-scatter inside it.  A no-op otherwise."""
+        inner = getattr(self.optimizer, "no_sync", None)
+        if inner is not None:
+            return inner()
+        import contextlib
+
+        return contextlib.nullcontext()
+
     def state_dict(self) -> Any:
         return self.optimizer.state_dict()
 

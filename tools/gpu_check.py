@@ -180,7 +180,8 @@ def check_gemm_2cta():
     e.gemm_bf16_2cta(a, b, out, False, True, True)
     report("gemm2cta_f32_accumulate", relerr(out, a.float() @ b.float().t() + 1) < 1e-3)
     for (M, N, K) in [(4096, 1536, 4096), (4096, 4096, 1376), (4096, 12288, 4096), (4096, 22016, 4096), (4096, 4096, 11008),
-                      (8192, 8192, 8192)]:
+                      (8192, 8192, 8192), (4096, 4096, 512), (16384, 4096, 512), (16384, 4096, 1376), (16384, 4096, 1536),
+                      (4096, 4096, 2048), (16384, 1536, 4096), (16384, 2752, 4096)]:
         a = torch.randn(M, K, device=dev, dtype=torch.bfloat16); b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         t2 = timeit(lambda: e.gemm_bf16_2cta(a, b, out, False, True, False))
