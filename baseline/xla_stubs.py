@@ -105,11 +105,21 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
 # group resolution: the reference passes ``groups=[[ranks], …]`` (replica groups) to xm.* collectives
 # ------------------------------------------------------------------------------------------------
 _PG_CACHE = {}
+_PG_BY_ID = {}          # id(groups) → (groups, pg): the reference passes the same replica-group lists on every call
 
 
 def _pg_for(groups: Optional[Sequence[Sequence[int]]]):
     if groups is None:
         return dist.group.WORLD
+    hit = _PG_BY_ID.get(id(groups))
+    if hit is not None and hit[0] is groups:
+        return hit[1]
+    pg = _pg_for_slow(groups)
+    _PG_BY_ID[id(groups)] = (groups, pg)      # keeps `groups` alive, so the id cannot be recycled
+    return pg
+
+
+def _pg_for_slow(groups):
     me = dist.get_rank()
     mine = None
     for g in groups:
@@ -152,9 +162,19 @@ def _xm_all_gather(value, dim=0, groups=None, output=None, pin_layout=True):
     if n == 1:
         return value
     v = value.contiguous()
-    parts = [torch.empty_like(v) for _ in range(n)]
-    dist.all_gather(parts, v, group=pg)
-    res = torch.cat(parts, dim=dim)
+    if dist.get_backend(pg) == "gloo":             # CPU plumbing check only
+        parts = [torch.empty_like(v) for _ in range(n)]
+        dist.all_gather(parts, v, group=pg)
+        res = torch.cat(parts, dim=dim)
+    else:
+        dim = dim % v.dim()
+        if dim == 0:
+            res = torch.empty((n * v.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+            dist.all_gather_into_tensor(res, v, group=pg)          # one NCCL call straight into the result, no cat copy
+        else:
+            stacked = torch.empty((n,) + tuple(v.shape), dtype=v.dtype, device=v.device)
+            dist.all_gather_into_tensor(stacked, v, group=pg)
+            res = torch.cat(list(stacked.unbind(0)), dim=dim)
     if output is not None:                      # torch_xla writes into `output` when given
         output.copy_(res)
         return output
@@ -316,13 +336,27 @@ class ZeroRedundancyOptimizer(torch.optim.Optimizer):
                 if k != "params":
                     bg[k] = v
         self.base_optimizer.step()
-        for p, s in self._pairs:
-            sh = s.data.to(p.dtype)
-            if n > 1:
-                full = torch.empty((sh.shape[0] * n, sh.shape[1]), dtype=p.dtype, device=p.device)
-                dist.all_gather_into_tensor(full, sh.contiguous(), group=self.pg)
-            else:
-                full = sh
+        if n == 1 and all(s.data.numel() == p.data.numel() for p, s in self._pairs):
+            # one multi-tensor cast+copy for all parameters (torch_xla coalesces this too) instead of 2 kernels per parameter
+            torch._foreach_copy_([p.data.view(-1) for p, _ in self._pairs], [s.data.view(-1) for _, s in self._pairs])
+            for _, s in self._pairs:
+                s.grad = None
+            return
+        fulls = []
+        shs = [s.data.to(p.dtype).contiguous() for p, s in self._pairs]
+        for (p, s), sh in zip(self._pairs, shs):
+            fulls.append(torch.empty((sh.shape[0] * n, sh.shape[1]), dtype=p.dtype, device=p.device) if n > 1 else sh)
+        if n > 1:
+            try:
+                cm = dist._coalescing_manager(group=self.pg, device=shs[0].device, async_ops=False)
+            except Exception:  # noqa: BLE001
+                import contextlib
+
+                cm = contextlib.nullcontext()
+            with cm:                                        # one NCCL group launch for all parameters (bucketed all-gather)
+                for full, sh in zip(fulls, shs):
+                    dist.all_gather_into_tensor(full, sh, group=self.pg)
+        for (p, s), full in zip(self._pairs, fulls):
             rows = p.shape[0] if p.dim() > 0 else 1
             p.data.copy_(full[:rows].reshape(p.shape))
             s.grad = None
@@ -424,5 +458,11 @@ def install() -> None:
         setattr(torch.classes, "neuron", _Dummy())
     except Exception:
         pass
-    _XlaDeviceRewrite().__enter__()
     _INSTALLED = True
+
+
+def device_rewrite():
+    """Context manager: `device="xla"` literals → the CUDA device.  Entered only around the reference's parallel-state /
+    model construction (the one literal on our path is parallel_state.py:655), NOT process-wide: a global
+    TorchFunctionMode would tax every torch call of the timed step with a Python `__torch_function__` hop."""
+    return _XlaDeviceRewrite()

@@ -35,6 +35,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "decode", "pp"],
+                    help="train (default, the headline: Llama-2-7B training tokens/s) | decode (BASELINE config 5: Llama-2-13B "
+                         "inference latency, batch 1, seq 2048) | pp (BASELINE config 4: GPT-NeoX-20B TP x PP=2 1F1B training)")
     ap.add_argument("--seq", type=int, default=4096)
     ap.add_argument("--global-batch", type=int, default=4)
     ap.add_argument("--layers", type=int, default=32, help="32 = Llama-2-7B (anything else is a debug run)")
@@ -148,6 +151,22 @@ def _micro_batch(args) -> int:
 
 def main():
     args = parse()
+    if args.mode != "train":
+        if args.impl == "reference":
+            # the reference's inference path needs neuronx-cc (HLO → NEFF) and its PP engine needs XLA send/recv emulation over
+            # 2-rank all-gathers of torch_xla tensors: neither exists on a CUDA box
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "mode": args.mode,
+                                  "unavailable": "reference inference needs neuronx-cc/NEFF and its pipeline engine needs torch_xla lazy tensors; only the training arm runs on CUDA"}))
+            return 0
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        if args.mode == "decode":
+            import bench_decode
+
+            return bench_decode.main(args)
+        import bench_pp
+
+        return bench_pp.main(args)
     if args.impl == "reference":
         return run_reference(args)
     import torch
@@ -208,6 +227,8 @@ def main():
     host_ids = [torch.randint(0, V, (gbs, S), generator=gen).pin_memory() for _ in range(n_host)]
     dev_ids = [h.to(dev) for h in host_ids]      # every step sees a fresh synthetic batch
 
+    phases = [] if os.environ.get("NXD_BENCH_PHASES", "0") == "1" else None     # debug: device time of optimizer.step()
+
     def train_step(ids_dev):
         opt.zero_grad()
         total = None
@@ -219,7 +240,12 @@ def main():
             with ctx:
                 loss = model.run_train(input_ids=ids, labels=ids)
             total = loss if total is None else total + loss
-        opt.step()
+        if phases is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); opt.step(); e1.record()
+            phases.append((e0, e1))
+        else:
+            opt.step()
         return total / n_mb
 
     def sync():
@@ -321,6 +347,10 @@ def main():
                        "grad_norm": float(opt.grad_norm) if opt.grad_norm is not None else None},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "comm": comm_report,
         }
+        if phases:
+            torch.cuda.synchronize()
+            ts = [a.elapsed_time(b) for a, b in phases[args.warmup:args.warmup + args.steps]]
+            out["optimizer_step_ms"] = sum(ts) / max(1, len(ts))
         print(json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()

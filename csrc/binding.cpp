@@ -481,7 +481,7 @@ static Tensor nvls_allreduce(const Tensor& x, const c10::optional<Tensor>& resid
                              int64_t local_base, int64_t flag_off, int64_t data_off, int64_t half_bytes, Tensor state,
                              int64_t rank, int64_t world) {
   TORCH_CHECK(x.is_cuda() && x.is_contiguous() && (x.scalar_type() == at::kBFloat16 || x.scalar_type() == at::kFloat));
-  TORCH_CHECK(state.scalar_type() == at::kInt && state.numel() >= 2 + 128);
+  TORCH_CHECK(state.scalar_type() == at::kInt && state.numel() >= 2 + 1024);
   if (residual) TORCH_CHECK(residual->is_contiguous() && residual->scalar_type() == x.scalar_type() && residual->numel() == x.numel());
   c10::cuda::CUDAGuard guard(x.device());
   Tensor out = at::empty_like(x);
@@ -491,6 +491,23 @@ static Tensor nvls_allreduce(const Tensor& x, const c10::optional<Tensor>& resid
                       mc_base, local_base, flag_off, data_off, half_bytes, (uint32_t*)state.data_ptr(), (int)rank, (int)world,
                       x.numel(), dt_code(x), ctas, stream());
   return out;
+}
+// y[M<=8, N] = sum over ranks of x[M, K] · w[N, K]ᵀ (+ residual): GEMV fused with the in-switch all-reduce
+static Tensor gemv_allreduce(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& residual, const Tensor& peer_bases,
+                             int64_t mc_base, int64_t local_base, int64_t flag_off, int64_t data_off, int64_t half_bytes, Tensor state,
+                             int64_t rank, int64_t world) {
+  CHECK_IN(x); CHECK_IN(w);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1));
+  TORCH_CHECK(state.scalar_type() == at::kInt && state.numel() >= 2 + 1024);
+  const int M = (int)x.size(0), N = (int)w.size(0), K = (int)x.size(1);
+  if (residual) TORCH_CHECK(residual->is_contiguous() && residual->scalar_type() == at::kBFloat16 && residual->numel() == (int64_t)M * N);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor y = at::empty({M, N}, x.options());
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  nxd::gemv_allreduce(x.data_ptr(), w.data_ptr(), residual ? residual->data_ptr() : nullptr, y.data_ptr(), M, N, K,
+                      peer_bases.data_ptr<int64_t>(), mc_base, local_base, flag_off, data_off, half_bytes, (uint32_t*)state.data_ptr(),
+                      (int)rank, (int)world, sms * 4, stream());
+  return y;
 }
 static void nvls_all_gather(const Tensor& x, const c10::optional<Tensor>& out, const Tensor& peer_bases, int64_t mc_base,
                             int64_t local_base, int64_t flag_off, int64_t data_off, int64_t half_bytes, Tensor state, int64_t rank,
@@ -556,6 +573,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("vmm_view", &vmm_view);
   m.def("tp_gemm_nvls", &tp_gemm_nvls);
   m.def("nvls_allreduce", &nvls_allreduce, py::arg("x"), py::arg("residual"), py::arg("peer_bases"), py::arg("mc_base"),
+        py::arg("local_base"), py::arg("flag_off"), py::arg("data_off"), py::arg("half_bytes"), py::arg("state"), py::arg("rank"),
+        py::arg("world"));
+  m.def("gemv_allreduce", &gemv_allreduce, py::arg("x"), py::arg("w"), py::arg("residual"), py::arg("peer_bases"), py::arg("mc_base"),
         py::arg("local_base"), py::arg("flag_off"), py::arg("data_off"), py::arg("half_bytes"), py::arg("state"), py::arg("rank"),
         py::arg("world"));
   m.def("nvls_all_gather", &nvls_all_gather);

@@ -67,10 +67,13 @@ int gemm_bf16_2cta_nvls(int mode, const void* a, const void* b, void* out, void*
                         long buf_offset, long flag_offset, uint32_t epoch, int comm_ctas, uint32_t* tile_done, uint32_t* claim,
                         uint32_t claim_base, bool wire_fp32, cudaStream_t st);
 
-// stand-alone NVLS collectives (nvls_coll.cu); `state` = [2 + 128] u32 device words (epoch, CTA counter, per-CTA barrier counts)
+// stand-alone NVLS collectives (nvls_coll.cu); `state` = [2 + 1024] u32 device words (epoch, CTA counter, per-CTA barrier counts)
 void nvls_allreduce(const void* x, const void* residual, void* out, const int64_t* peer_bases, int64_t mc_base, int64_t local_base,
                     long flag_off, long data_off, long half_bytes, uint32_t* state, int rank, int world, long numel, int dt,
                     int ctas, cudaStream_t st);
+void gemv_allreduce(const void* x, const void* w, const void* residual, void* y, int M, int N, int K, const int64_t* peer_bases,
+                    int64_t mc_base, int64_t local_base, long flag_off, long data_off, long half_bytes, uint32_t* state, int rank,
+                    int world, int max_ctas, cudaStream_t st);
 void nvls_all_gather(const void* x, void* out, const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off,
                      long data_off, long half_bytes, uint32_t* state, int rank, int world, long bytes, int ctas, cudaStream_t st);
 void nvls_reduce_scatter(const void* x, void* out, const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off,

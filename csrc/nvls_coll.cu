@@ -14,7 +14,7 @@
 
 namespace nxd {
 
-constexpr int kNvlsCollMaxCtas = 128;
+constexpr int kNvlsCollMaxCtas = 1024;
 
 NXD_DEVICE void mm_red_add_release_u32(uint32_t* mc, uint32_t v) {
   asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
@@ -215,6 +215,94 @@ __global__ void __launch_bounds__(512) nvls_reduce_scatter_kernel(const T* __res
   finish_call(state, epoch);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused decode-time GEMV → all-reduce (RowParallelLinear without sequence parallel at batch 1..8: o_proj / down_proj of every
+// layer; reference layers.py:1040-1043).  y[M<=8, N] = sum over ranks of x_r[M, K] · W_r[N, K]ᵀ (+ residual).
+// One warp per output column streams its weight row once (16-byte loads, fp32 accumulation), the fp32 partials go to this
+// rank's OWN symmetric slot, CTA i of every rank meets in a cross-rank barrier (one multimem.red per CTA), and the same CTA
+// then reads the in-switch fp32 sum of its columns with multimem.ld_reduce — one launch instead of GEMV + copy-in +
+// all-reduce, partials never rounded to bf16 (the reference's reduce_dtype=fp32).
+template <int M>
+__global__ void __launch_bounds__(256) gemv_allreduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                             const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y,
+                                                             int N, int K, NvlsRegion r, uint32_t* __restrict__ state) {
+  const uint32_t epoch = ld_acquire_sys(state) + 1u;
+  const long base = r.data_off + (long)(epoch & 1u) * r.half_bytes;
+  float* slot = (float*)(r.local_base + base);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = (N + 7) / 8;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int n = g * 8 + warp;
+    if (n >= N) continue;
+    float acc[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) acc[m] = 0.f;
+    const __nv_bfloat16* wr = w + (long)n * K;
+#pragma unroll 4
+    for (int k = lane * 8; k < K; k += 256) {
+      const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wr + k));
+      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+      float wf[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(w2[i]); wf[2 * i] = f.x; wf[2 * i + 1] = f.y; }
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(x + (long)m * K + k);
+        const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(x2[i]);
+          acc[m] = fmaf(f.x, wf[2 * i], acc[m]);
+          acc[m] = fmaf(f.y, wf[2 * i + 1], acc[m]);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      const float v = warp_sum(acc[m]);
+      if (lane == 0) slot[(long)m * N + n] = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  cta_barrier_all_ranks(r, state);
+  // reduce the same column groups: thread t handles (row t/2, 4 columns of the group's 8)
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    if ((int)threadIdx.x < 2 * M) {
+      const int m = threadIdx.x >> 1, c0 = g * 8 + (threadIdx.x & 1) * 4;
+      if (c0 < N) {                                     // N % 4 == 0 (checked by the launcher)
+        const long off = base + ((long)m * N + c0) * 4;
+        float4 v;
+        if (r.mc_base != nullptr) {
+          const uint4 raw = mm_ld_reduce<float>(r.mc_base + off);
+          v = make_float4(__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w));
+        } else {
+          v = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int p = 0; p < r.world; ++p) {
+            uint4 raw;
+            const void* src = (const uint8_t*)r.peer_bases[p] + off;
+            asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(src) : "memory");
+            v.x += __uint_as_float(raw.x); v.y += __uint_as_float(raw.y); v.z += __uint_as_float(raw.z); v.w += __uint_as_float(raw.w);
+          }
+        }
+        if (residual != nullptr) {
+          const uint2 rr = *reinterpret_cast<const uint2*>(residual + (long)m * N + c0);
+          const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+          const float2 a = __bfloat1622float2(r2[0]), b = __bfloat1622float2(r2[1]);
+          v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+        }
+        uint2 o;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+        o2[0] = __floats2bfloat162_rn(v.x, v.y);
+        o2[1] = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(y + (long)m * N + c0) = o;
+      }
+    }
+  }
+  finish_call(state, epoch);
+}
+
 static NvlsRegion make_region(const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off, long data_off,
                               long half_bytes, int rank, int world) {
   NvlsRegion r;
@@ -237,6 +325,32 @@ void nvls_allreduce(const void* x, const void* residual, void* out, const int64_
     nvls_allreduce_kernel<float><<<ctas, 512, 0, st>>>((const float*)x, (const float*)residual, (float*)out, r, state, numel);
   else
     nxd_throw("nvls_allreduce: bf16 or fp32 only", __FILE__, __LINE__);
+  NXD_CUDA_CHECK(cudaGetLastError());
+}
+
+void gemv_allreduce(const void* x, const void* w, const void* residual, void* y, int M, int N, int K, const int64_t* peer_bases,
+                    int64_t mc_base, int64_t local_base, long flag_off, long data_off, long half_bytes, uint32_t* state, int rank,
+                    int world, int max_ctas, cudaStream_t st) {
+  if (N % 8 || K % 8 || (long)M * N * 4 > half_bytes) nxd_throw("gemv_allreduce: N, K multiples of 8 and M*N*4 bytes within the slot", __FILE__, __LINE__);
+  const NvlsRegion r = make_region(peer_bases, mc_base, local_base, flag_off, data_off, half_bytes, rank, world);
+  int grid = (N + 7) / 8;
+  if (grid > max_ctas) grid = max_ctas;                  // every CTA must be resident: they meet in a cross-rank barrier
+  if (grid > kNvlsCollMaxCtas) grid = kNvlsCollMaxCtas;
+#define NXD_GAR(Mv)                                                                                                       \
+  gemv_allreduce_kernel<Mv><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const __nv_bfloat16*)residual, \
+                                                  (__nv_bfloat16*)y, N, K, r, state)
+  switch (M) {
+    case 1: NXD_GAR(1); break;
+    case 2: NXD_GAR(2); break;
+    case 3: NXD_GAR(3); break;
+    case 4: NXD_GAR(4); break;
+    case 5: NXD_GAR(5); break;
+    case 6: NXD_GAR(6); break;
+    case 7: NXD_GAR(7); break;
+    case 8: NXD_GAR(8); break;
+    default: nxd_throw("gemv_allreduce: M must be 1..8", __FILE__, __LINE__);
+  }
+#undef NXD_GAR
   NXD_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -55,7 +55,7 @@ _NVLS_MODE = os.environ.get("NXD_TP_NVLS", "1")
 _NVLS_FLAG_BYTES = 64 << 10          # AG flags [world][256][4] u32 at 0, RS flags [world][256] u32 at 32 KB
 _NVLS_RS_FLAG_OFF = 32 << 10
 NVLS_MAX_ROW_BLOCKS = 256
-NVLS_CONFIG = {"comm_ctas_ag": int(os.environ.get("NXD_NVLS_COMM_CTAS_AG", "8")),
+NVLS_CONFIG = {"comm_ctas_ag": int(os.environ.get("NXD_NVLS_COMM_CTAS_AG", "16")),
                "comm_ctas_rs": int(os.environ.get("NXD_NVLS_COMM_CTAS_RS", "8"))}
 
 
@@ -139,9 +139,14 @@ class TPWorkspace:
                 self.nv.close()
             self.nv = None
         self.nv_checked = True
-        self.nv_ag_epoch = self.nv_rs_epoch = self.nv_claim_base = 0
-        self.nv_counters = torch.zeros(64 + 8 * NVLS_MAX_ROW_BLOCKS, dtype=torch.int32,
-                                       device=torch.device("cuda", torch.cuda.current_device()))
+        # Protocol state is NEVER reset: epochs stay monotonic across re-layouts.  The VMM allocator hands back the SAME region
+        # when it is already large enough (its granularity is hundreds of MB), and that region's flags still hold the epochs of
+        # earlier calls — restarting the epochs at 1 made consumers see "flag >= epoch" immediately and read stale payload
+        # (found by tools/nvls_bench.py --stage numerics with NXD_SYMM_MIN_MB=1; profiles/README.md).  A brand-new region has
+        # zero flags, which is consistent with any epoch.  Counters are at rest (zero / claim base) between kernels.
+        if self.nv_counters is None:
+            self.nv_counters = torch.zeros(64 + 8 * NVLS_MAX_ROW_BLOCKS, dtype=torch.int32,
+                                           device=torch.device("cuda", torch.cuda.current_device()))
 
     def _nv_off_ag(self, parity: int) -> int:
         return _NVLS_FLAG_BYTES + parity * self.nv_ag_bytes

@@ -53,6 +53,13 @@ def all_reduce_sum(x: torch.Tensor, group) -> Optional[torch.Tensor]:
     make the same decision — it depends only on shape/dtype, which are identical across ranks for TP collectives."""
     if not eligible(x, group):
         return None
+    if os.environ.get("NXD_NVLS_AR", "1") == "1":
+        from . import nvls
+
+        # in-switch reduction (multimem.ld_reduce) when the group's symmetric region has an NVLS multicast mapping:
+        # one local write + one reduced read per element instead of `world` peer writes + `world` local reads
+        if nvls.available() and nvls.has_multicast(group):
+            return nvls.all_reduce_sum(x, group)
     ws, state = _workspace(group)
     _ext.count_launch()
     return _ext.ext().oneshot_allreduce(x, ws.ptrs, ws.flag_ptrs, _MAX_BYTES, state, ws.rank, ws.world)

@@ -17,7 +17,7 @@ import torch.distributed as dist
 
 from . import _ext, symm
 
-_FLAG_BYTES = 4096                     # 128 per-CTA barrier counters, padded
+_FLAG_BYTES = 4096                     # 1024 per-CTA barrier counters
 _STATE: Dict[tuple, "_Coll"] = {}
 
 
@@ -27,7 +27,12 @@ class _Coll:
         self.half_bytes = int(half_bytes)
         self.ws = symm.get_vmm_workspace(group, f"nvls_{kind}", _FLAG_BYTES + 2 * self.half_bytes)
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.state = torch.zeros(2 + 128, dtype=torch.int32, device=dev)
+        # the device-side call / barrier counters belong to the REGION (its flag words count the same events): when a larger
+        # request is served by the same (already big enough) region, the counters must carry over, not restart at zero
+        st = getattr(self.ws, "_coll_state", None)
+        if st is None:
+            st = self.ws._coll_state = torch.zeros(2 + 1024, dtype=torch.int32, device=dev)
+        self.state = st
 
     @property
     def args(self):
@@ -65,6 +70,21 @@ def all_reduce_sum(x: torch.Tensor, group, residual: Optional[torch.Tensor] = No
     c = _coll(group, "ar", nbytes, int(os.environ.get("NXD_NVLS_AR_MAX_MB", "8")))
     _ext.count_launch()
     return _ext.ext().nvls_allreduce(x, residual, *c.args)
+
+
+def gemv_all_reduce(x: torch.Tensor, weight: torch.Tensor, group, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``sum_over_ranks(x @ weightᵀ) (+ residual)`` for ``x`` [M<=8, K] bf16, ``weight`` [N, K] bf16 in ONE kernel (decode-time
+    RowParallelLinear): the GEMV's fp32 partials are reduced in the switch, never rounded to bf16 in between."""
+    M, N = x.shape[0], weight.shape[0]
+    c = _coll(group, "gemv_ar", M * N * 4, 1)
+    _ext.count_launch()
+    return _ext.ext().gemv_allreduce(x, weight, residual, *c.args)
+
+
+def gemv_all_reduce_eligible(x2d: torch.Tensor, weight: torch.Tensor) -> bool:
+    return (x2d.is_cuda and x2d.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x2d.shape[0] <= 8
+            and weight.shape[0] % 8 == 0 and weight.shape[1] % 8 == 0 and x2d.is_contiguous() and weight.is_contiguous()
+            and available() and os.environ.get("NXD_GEMV_AR", "1") == "1")
 
 
 def all_gather(x: torch.Tensor, group, ctas: int = 32) -> torch.Tensor:

@@ -408,6 +408,15 @@ class _TPLinear(torch.autograd.Function):
             if save_for_backward:
                 ctx.save_for_backward(x, weight)
             total = comm.all_gather(x, dim=seq_dim, group=group) if (in_mode == "gather" and n > 1) else x
+            if (n > 1 and out_mode == "reduce" and not torch.is_grad_enabled() and total.is_cuda
+                    and total.numel() // total.shape[-1] <= 8 and ops.tp_fused.get_backend() == "fused"
+                    and ops.nvls.gemv_all_reduce_eligible(total.reshape(-1, total.shape[-1]), weight)):
+                # decode-time Row-parallel linear: GEMV and the all-reduce of its fp32 partials in ONE kernel
+                # (csrc/nvls_coll.cu gemv_allreduce_kernel; in-switch reduction when the group has an NVLS mapping)
+                y = ops.nvls.gemv_all_reduce(total.reshape(-1, total.shape[-1]), weight, group).view(*total.shape[:-1], weight.shape[0])
+                if bias is not None:
+                    y = y + bias
+                return y
             y = ops.gemm.linear_nt(total, weight)          # tcgen05 kernel on CUDA bf16, torch.matmul otherwise
             if n > 1 and out_mode in ("scatter", "reduce"):
                 od = y.dtype

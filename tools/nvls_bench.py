@@ -164,7 +164,9 @@ def stage_numerics(g, force):
                 eq = bool(torch.equal(gathered, full))
                 worst = max(worst, e1)
                 if e1 > 2e-2 or not eq:
-                    emit({"stage": "numerics", "FAIL": "ag_gemm", "ms": ms, "N": N, "K": K, "trans_b": trans_b, "it": it, "relerr": e1, "gathered_equal": eq})
+                    bad = (gathered != full).view(WORLD, -1).any(dim=1).tolist()
+                    emit({"stage": "numerics", "FAIL": "ag_gemm", "ms": ms, "N": N, "K": K, "trans_b": trans_b, "it": it, "relerr": e1, "gathered_equal": eq,
+                          "bad_source_chunks": bad, "epoch": ws.nv_ag_epoch})
     emit({"stage": "numerics", "op": "ag_gemm", "worst_relerr_vs_fp32": worst})
     for wire in ("bf16", "fp32"):
         os.environ["NXD_TP_WIRE"] = wire
@@ -181,7 +183,9 @@ def stage_numerics(g, force):
                     e1 = relerr(out, ref)
                     worst = max(worst, e1)
                     if e1 > 2e-2:
-                        emit({"stage": "numerics", "FAIL": "gemm_rs", "wire": wire, "ms": ms, "N": N, "K": K, "trans_b": trans_b, "it": it, "relerr": e1})
+                        d = (out.float() - ref).abs().view(ms // 128, 128, -1).amax(dim=(1, 2)) / (ref.abs().max() + 1e-6)
+                        emit({"stage": "numerics", "FAIL": "gemm_rs", "wire": wire, "ms": ms, "N": N, "K": K, "trans_b": trans_b, "it": it, "relerr": e1,
+                              "per_128row_block": [round(float(v), 3) for v in d[:16]], "grew": ws.nv_rs_bytes, "epoch": ws.nv_rs_epoch})
         emit({"stage": "numerics", "op": "gemm_rs", "wire": wire, "worst_relerr_vs_fp32": worst})
     os.environ["NXD_TP_WIRE"] = "bf16"
     # regrowth: a larger shape mid-stream re-allocates the region (barrier + epoch reset) and must keep working
@@ -194,7 +198,14 @@ def stage_numerics(g, force):
     w2 = torch.randn(512, 1024, device="cuda", dtype=torch.bfloat16) * 0.05
     out2, _ = ws.ag_gemm(x2, w2, True)
     ref2, _ = _ref_ag_gemm(x2, w2, True, g)
-    emit({"stage": "numerics", "op": "regrowth", "grew": ws.nv_ag_bytes > before, "relerr_big": relerr(out, ref), "relerr_after": relerr(out2, ref2)})
+    rec = {"stage": "numerics", "op": "regrowth", "grew": ws.nv_ag_bytes > before, "relerr_big": relerr(out, ref), "relerr_after": relerr(out2, ref2)}
+    full = torch.empty(WORLD * x.shape[0], x.shape[1], device="cuda", dtype=x.dtype)
+    dist.all_gather_into_tensor(full, x, group=g)
+    out_b, gathered_b = ws.ag_gemm(x, w, True)            # same big shape again (no regrowth now)
+    rec["relerr_big_second_call"] = relerr(out_b, ref)
+    rec["gathered_equal_second_call"] = bool(torch.equal(gathered_b, full))
+    rec["nan_rows_first_call"] = int(torch.isnan(out.float()).any(dim=1).sum())
+    emit(rec)
 
 
 def stage_perf(g, rows_list, sweep):
@@ -238,7 +249,7 @@ def stage_perf(g, rows_list, sweep):
                 for c in (2, 4, 8, 16, 24):
                     _fused_impl.NVLS_CONFIG["comm_ctas_ag"] = c
                     rec[f"nvls_c{c}_us"] = timeit(lambda: ws.ag_gemm(x, w, True), iters=10, warmup=3)
-                _fused_impl.NVLS_CONFIG["comm_ctas_ag"] = 8
+                _fused_impl.NVLS_CONFIG["comm_ctas_ag"] = 16
             else:
                 rec.update(variants(lambda: ws.ag_gemm(x, w, True)))
                 rec["nccl_plus_own_gemm_us"] = timeit(lambda: gemm.matmul(comm.all_gather(x, 0, g), w, False, True))
