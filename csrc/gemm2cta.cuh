@@ -71,18 +71,27 @@ NXD_DEVICE void store_chunk(OutT* orow, int col0, int N, const uint32_t (&r)[32]
   } else {
     if (col0 + 32 <= N) {
       float4* dst = (float4*)(orow + col0);
+      if (accumulate == 2) {                 // split-K partial: vector atomic add (fire-and-forget reduction at L2)
 #pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
-                               __uint_as_float(r[4 * v + 3]));
-        if (accumulate) { const float4 p = dst[v]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-        dst[v] = o;
+        for (int v = 0; v < 8; ++v)
+          asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                       ::"l"(dst + v), "f"(__uint_as_float(r[4 * v])), "f"(__uint_as_float(r[4 * v + 1])),
+                         "f"(__uint_as_float(r[4 * v + 2])), "f"(__uint_as_float(r[4 * v + 3])) : "memory");
+      } else {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                                 __uint_as_float(r[4 * v + 3]));
+          if (accumulate) { const float4 p = dst[v]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+          dst[v] = o;
+        }
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         if (col0 + j < N) {
           float v = __uint_as_float(r[j]);
+          if (accumulate == 2) { atomicAdd(((float*)orow) + col0 + j, v); continue; }
           if (accumulate) v += ((float*)orow)[col0 + j];
           ((float*)orow)[col0 + j] = v;
         }

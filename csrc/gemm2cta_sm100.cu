@@ -23,7 +23,11 @@ namespace g2 {
 template <bool A_KMAJOR, bool B_KMAJOR, typename OutT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                      const __grid_constant__ CUtensorMap tma_out, OutT* __restrict__ out, int M, int N, int K, int accumulate) {
+                      const __grid_constant__ CUtensorMap tma_out, OutT* __restrict__ out, int M, int N, int K, int accumulate,
+                      int split_k) {
+  // accumulate: 0 store, 1 read-modify-write, 2 atomic add (split-K: `split_k` CTA pairs share one output tile, each
+  // reduces a K range and adds its fp32 partial with red.global.add.v4 — used for the weight-gradient GEMMs whose output
+  // has too few tiles to fill the 74 CTA pairs while K = tokens is huge)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + kBarOffset);
@@ -38,6 +42,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
   const int tiles_m = (M + TILE_M - 1) / TILE_M, tiles_n = (N + TILE_N - 1) / TILE_N;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + BK - 1) / BK;
+  const int kb_per = (num_kb + split_k - 1) / split_k;       // k-blocks per split (host guarantees no empty split)
+  const int num_units = num_tiles * split_k;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
@@ -64,12 +70,14 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     // ===== TMA producer (both CTAs) =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int unit = pair; unit < num_units; unit += num_pairs) {
+        const int tile = unit % num_tiles, ks = unit / num_tiles;
         int m_blk, n_blk;
         tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
         const int m0 = m_blk * TILE_M + (int)cta * CTA_M;
         const int n0 = n_blk * TILE_N + (int)cta * HALF_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb1 = min(num_kb, (ks + 1) * kb_per);
+        for (int kb = ks * kb_per; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t full = bar_full + 8 * stage;          // same offset in the leader's smem
           if (leader) mbar_expect_tx(full, 2 * kStageBytes);
@@ -98,11 +106,13 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc(!A_KMAJOR, !B_KMAJOR, TILE_M, TILE_N);
       int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int unit = pair; unit < num_units; unit += num_pairs) {
+        const int ks = unit / num_tiles;
         mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * TILE_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = ks * kb_per, kb1 = min(num_kb, (ks + 1) * kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
@@ -110,7 +120,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t da = A_KMAJOR ? make_smem_desc(sa + k * 32, 16, 1024) : make_smem_desc(sa + k * 2048, 8192, 1024);
             const uint64_t db = B_KMAJOR ? make_smem_desc(sb + k * 32, 16, 1024) : make_smem_desc(sb + k * 2048, 8192, 1024);
-            tcgen05_mma_f16_2cta(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            tcgen05_mma_f16_2cta(tmem_d, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           tcgen05_commit_2cta(bar_empty + 8 * stage, 0b11);    // frees the stage in BOTH CTAs
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -128,7 +138,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     const bool issuer = threadIdx.x == 64;
     uint32_t slab_ctr = 0;
     int as = 0; uint32_t aphase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    for (int unit = pair; unit < num_units; unit += num_pairs) {
+      const int tile = unit % num_tiles;
       int m_blk, n_blk;
       tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
       mbar_wait(bar_tfull + 8 * as, aphase);
@@ -666,14 +677,14 @@ int device_sm_count();
 
 template <bool AK, bool BK_, typename OutT>
 static void launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, void* out, int M, int N, int K,
-                    bool accumulate, int grid, cudaStream_t st) {
+                    int accumulate, int split_k, int grid, cudaStream_t st) {
   auto kern = g2::gemm_bf16_2cta_kernel<AK, BK_, OutT>;
   static bool configured = false;
   if (!configured) {
     NXD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::kSmem));
     configured = true;
   }
-  kern<<<grid, g2::kThreads, g2::kSmem, st>>>(ta, tb, to, (OutT*)out, M, N, K, accumulate ? 1 : 0);
+  kern<<<grid, g2::kThreads, g2::kSmem, st>>>(ta, tb, to, (OutT*)out, M, N, K, accumulate, split_k);
   NXD_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -688,11 +699,34 @@ void gemm_bf16_2cta(const void* a, const void* b, void* out, int M, int N, int K
   if (out_dt == kBF16 && !accumulate && !tma_out_ok) nxd_throw("gemm_bf16_2cta: bf16 output needs N % 8 == 0", __FILE__, __LINE__);
   const int tiles = ((M + g2::TILE_M - 1) / g2::TILE_M) * ((N + g2::TILE_N - 1) / g2::TILE_N);
   const int pairs = device_sm_count() / 2;
-  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  // Split-K for fp32 outputs (weight gradients): K = tokens is long while the output often has fewer tiles than the
+  // chip has CTA pairs (TP=8: 32-176 tiles on 74 pairs).  Pick the split that minimises waves/split with a small cost per
+  // extra partial (atomic epilogue traffic); every split keeps >= 16 k-blocks so the mainloop still amortises its epilogue.
+  int split = 1;
+  const char* split_env = getenv("NXD_GEMM_SPLITK");            // re-read per call: A/B sweeps toggle it at run time
+  const bool split_enabled = !(split_env && split_env[0] == '0');
+  const int num_kb = (K + g2::BK - 1) / g2::BK;
+  if (out_dt == kF32 && split_enabled && N % 4 == 0) {
+    double best = (double)((tiles + pairs - 1) / pairs);
+    for (int s2 = 2; s2 <= 8; ++s2) {
+      if (num_kb / s2 < 16) break;
+      const int per = (num_kb + s2 - 1) / s2;
+      if (per * (s2 - 1) >= num_kb) continue;                       // would leave an empty split
+      const double cost = (double)((tiles * s2 + pairs - 1) / pairs) / s2 * (1.0 + 0.04 * (s2 - 1));
+      if (cost < best - 1e-9) { best = cost; split = s2; }
+    }
+  }
+  int acc_mode = accumulate ? 1 : 0;
+  if (split > 1) {
+    if (!accumulate) NXD_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)M * N * sizeof(float), st));   // partials add into zeros
+    acc_mode = 2;
+  }
+  const int units = tiles * split;
+  const int grid = 2 * (units < pairs ? units : pairs);
 #define NXD_L2(AKv, BKv)                                                                          \
   do {                                                                                            \
-    if (out_dt == kBF16) launch2<AKv, BKv, __nv_bfloat16>(ta, tb, to, out, M, N, K, accumulate, grid, st); \
-    else launch2<AKv, BKv, float>(ta, tb, to, out, M, N, K, accumulate, grid, st);               \
+    if (out_dt == kBF16) launch2<AKv, BKv, __nv_bfloat16>(ta, tb, to, out, M, N, K, acc_mode, split, grid, st); \
+    else launch2<AKv, BKv, float>(ta, tb, to, out, M, N, K, acc_mode, split, grid, st);          \
   } while (0)
   if (AK && BK_) NXD_L2(true, true);
   else if (AK && !BK_) NXD_L2(true, false);

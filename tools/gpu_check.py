@@ -179,6 +179,22 @@ def check_gemm_2cta():
     out = torch.ones(M, N, device=dev, dtype=torch.float32)
     e.gemm_bf16_2cta(a, b, out, False, True, True)
     report("gemm2cta_f32_accumulate", relerr(out, a.float() @ b.float().t() + 1) < 1e-3)
+    # weight-gradient layout (A, B MN-major), fp32 output, few tiles and a long K → split-K with atomic fp32 partials
+    for (M, N, K) in [(512, 4096, 16384), (4096, 512, 16384), (1536, 4096, 8192), (2752, 4096, 16384)]:
+        a = torch.randn(K, M, device=dev, dtype=torch.bfloat16); b = torch.randn(K, N, device=dev, dtype=torch.bfloat16)
+        ref = a.float().t() @ b.float()
+        out = torch.empty(M, N, device=dev, dtype=torch.float32)
+        e.gemm_bf16_2cta(a, b, out, True, False, False)
+        e1 = relerr(out, ref)
+        e.gemm_bf16_2cta(a, b, out, True, False, True)             # accumulate on top: 2x
+        e2 = relerr(out, 2 * ref)
+        report(f"gemm2cta_splitk_wgrad_{M}x{N}x{K}", e1 < 2e-3 and e2 < 2e-3, err=e1, err_acc=e2)
+        import os as _os
+        t_on = timeit(lambda: e.gemm_bf16_2cta(a, b, out, True, False, True))
+        _os.environ["NXD_GEMM_SPLITK"] = "0"
+        t_off = timeit(lambda: e.gemm_bf16_2cta(a, b, out, True, False, True))
+        _os.environ["NXD_GEMM_SPLITK"] = "1"
+        report(f"gemm2cta_splitk_perf_{M}x{N}x{K}", True, splitk_tflops=2.0 * M * N * K / t_on / 1e9, no_split_tflops=2.0 * M * N * K / t_off / 1e9)
     for (M, N, K) in [(4096, 1536, 4096), (4096, 4096, 1376), (4096, 12288, 4096), (4096, 22016, 4096), (4096, 4096, 11008),
                       (8192, 8192, 8192), (4096, 4096, 512), (16384, 4096, 512), (16384, 4096, 1376), (16384, 4096, 1536),
                       (4096, 4096, 2048), (16384, 1536, 4096), (16384, 2752, 4096)]:
