@@ -455,7 +455,8 @@ static Tensor vmm_view(int64_t id, int64_t offset, const std::vector<int64_t>& s
 // mode 2: a = [M, K] → out [M/world, N]; partials live in the region payload at buf_offset.  Returns reducer claims used.
 static int64_t tp_gemm_nvls(int64_t mode, const Tensor& a, const Tensor& b, Tensor out, bool trans_b, const Tensor& peer_bases,
                             int64_t mc_base, int64_t local_base, int64_t buf_offset, int64_t flag_offset, int64_t epoch,
-                            int64_t rank, int64_t world, int64_t comm_ctas, Tensor counters, int64_t claim_base, bool wire_fp32) {
+                            int64_t rank, int64_t world, int64_t comm_ctas, Tensor counters, int64_t claim_base, bool wire_fp32,
+                            bool gemm_join) {
   CHECK_IN(a); CHECK_IN(b); CHECK_IN(out);
   TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && out.scalar_type() == at::kBFloat16);
   TORCH_CHECK(counters.scalar_type() == at::kInt && counters.numel() >= 64 + 8 * 256);
@@ -468,13 +469,13 @@ static int64_t tp_gemm_nvls(int64_t mode, const Tensor& a, const Tensor& b, Tens
     TORCH_CHECK(out.size(0) == M && out.size(1) == N);
     return nxd::gemm_bf16_2cta_nvls(1, nullptr, b.data_ptr(), out.data_ptr(), nullptr, a.data_ptr(), M, N, K, trans_b, (int)rank,
                                     (int)world, peer_bases.data_ptr<int64_t>(), mc_base, local_base, buf_offset, flag_offset,
-                                    (uint32_t)epoch, (int)comm_ctas, ctr + 64, ctr, 0u, false, stream());
+                                    (uint32_t)epoch, (int)comm_ctas, ctr + 64, ctr, 0u, false, true, stream());
   }
   const int M = (int)a.size(0);
   TORCH_CHECK(out.size(0) * world == M && out.size(1) == N);
   return nxd::gemm_bf16_2cta_nvls(2, a.data_ptr(), b.data_ptr(), nullptr, out.data_ptr(), nullptr, M, N, K, trans_b, (int)rank,
                                   (int)world, peer_bases.data_ptr<int64_t>(), mc_base, local_base, buf_offset, flag_offset,
-                                  (uint32_t)epoch, (int)comm_ctas, ctr + 64, ctr, (uint32_t)claim_base, wire_fp32, stream());
+                                  (uint32_t)epoch, (int)comm_ctas, ctr + 64, ctr, (uint32_t)claim_base, wire_fp32, gemm_join, stream());
 }
 
 static Tensor nvls_allreduce(const Tensor& x, const c10::optional<Tensor>& residual, const Tensor& peer_bases, int64_t mc_base,

@@ -65,7 +65,7 @@ void gemm_bf16_2cta_tp(int mode, const void* a, const void* b, void* out_or_part
 int gemm_bf16_2cta_nvls(int mode, const void* a, const void* b, void* out, void* rs_out, const void* a_local, int M, int N, int K,
                         bool trans_b, int rank, int world, const int64_t* peer_bases, int64_t mc_base, int64_t local_base,
                         long buf_offset, long flag_offset, uint32_t epoch, int comm_ctas, uint32_t* tile_done, uint32_t* claim,
-                        uint32_t claim_base, bool wire_fp32, cudaStream_t st);
+                        uint32_t claim_base, bool wire_fp32, bool gemm_join, cudaStream_t st);
 
 // stand-alone NVLS collectives (nvls_coll.cu); `state` = [2 + 1024] u32 device words (epoch, CTA counter, per-CTA barrier counts)
 void nvls_allreduce(const void* x, const void* residual, void* out, const int64_t* peer_bases, int64_t mc_base, int64_t local_base,

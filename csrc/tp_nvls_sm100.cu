@@ -55,6 +55,8 @@ struct NvlsComm {
   uint32_t* tile_done;         // MODE 2: local per-128-row-block tile counters
   uint32_t* claim;             // MODE 2: reducer work counter (monotonic across calls)
   uint32_t claim_base;
+  int gemm_join;               // MODE 2: GEMM CTAs become reducers after their tiles (1) or exit and free their SMs for a
+                               // concurrently launched kernel, e.g. the weight-gradient GEMM on a side stream (0)
 };
 
 NXD_DEVICE void multimem_st_v4(void* mc, const uint4& v) {
@@ -381,6 +383,7 @@ gemm_bf16_2cta_nvls_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
     const size_t esz = WIRE32 ? 4 : 2;
     const size_t groups = (size_t)kRsRowsPerItem * N / 8;           // 8 output elements (16 bytes of bf16) per group
     __syncthreads();
+    if (is_comm || comm.gemm_join)
     for (;;) {
       if (threadIdx.x == 0) s_item = (int)(atomicAdd(comm.claim, 1u) - comm.claim_base);
       __syncthreads();
@@ -473,12 +476,13 @@ static void launch_nvls(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
 int gemm_bf16_2cta_nvls(int mode, const void* a, const void* b, void* out, void* rs_out, const void* a_local, int M, int N, int K,
                         bool trans_b, int rank, int world, const int64_t* peer_bases, int64_t mc_base, int64_t local_base,
                         long buf_offset, long flag_offset, uint32_t epoch, int comm_ctas, uint32_t* tile_done, uint32_t* claim,
-                        uint32_t claim_base, bool wire_fp32, cudaStream_t st) {
+                        uint32_t claim_base, bool wire_fp32, bool gemm_join, cudaStream_t st) {
   g2::NvlsComm c{};
   c.rank = rank; c.world = world; c.peer_bases = peer_bases; c.mc_base = (uint8_t*)mc_base; c.local_base = (uint8_t*)local_base;
   c.buf_offset = buf_offset; c.flag_offset = flag_offset; c.epoch = epoch; c.comm_ctas = comm_ctas & ~1;
   c.rows_per_rank = M / world; c.a_local = a_local; c.rs_out = rs_out; c.tile_done = tile_done; c.claim = claim;
   c.claim_base = claim_base;
+  c.gemm_join = (gemm_join || c.comm_ctas == 0) ? 1 : 0;
   if (M % world || c.rows_per_rank % g2::TILE_M || c.rows_per_rank / g2::CTA_M > g2::kNvlsMaxRowBlocks || N % 8 || K % 8)
     nxd_throw("fused TP GEMM (NVLS) needs rows/rank to be a multiple of 256 and <= 32768, N and K multiples of 8", __FILE__, __LINE__);
   const int grid = (device_sm_count() / 2) * 2;
@@ -502,7 +506,7 @@ int gemm_bf16_2cta_nvls(int mode, const void* a, const void* b, void* out, void*
                  else launch_nvls<true, 2, false>(ta, tb, ta, to, partial, M, N, K, c, grid, st); }
   else { if (wire_fp32) launch_nvls<false, 2, true>(ta, tb, ta, to, partial, M, N, K, c, grid, st);
          else launch_nvls<false, 2, false>(ta, tb, ta, to, partial, M, N, K, c, grid, st); }
-  return (c.rows_per_rank / g2::CTA_M) * (g2::CTA_M / g2::kRsRowsPerItem) + grid;
+  return (c.rows_per_rank / g2::CTA_M) * (g2::CTA_M / g2::kRsRowsPerItem) + (c.gemm_join ? grid : c.comm_ctas);
 }
 
 }  // namespace nxd

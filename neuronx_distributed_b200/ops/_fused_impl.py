@@ -59,6 +59,38 @@ NVLS_CONFIG = {"comm_ctas_ag": int(os.environ.get("NXD_NVLS_COMM_CTAS_AG", "16")
                "comm_ctas_rs": int(os.environ.get("NXD_NVLS_COMM_CTAS_RS", "8"))}
 
 
+# Weight-gradient GEMMs on a side stream (NVLS path): at TP=8 the fused dgrad kernels are NVLink-bound, their GEMM CTAs
+# finish early and exit (gemm_join=0) while a few comm CTAs keep pulling; the weight-gradient GEMM of the same layer has no
+# communication at all, so it is launched on a second stream and fills the SMs the fused kernel vacates.
+_SIDE_WGRAD = os.environ.get("NXD_TP_SIDE_WGRAD", "1") == "1"
+_SIDE = {"stream": None, "joined": True}
+
+
+def _side_stream() -> "torch.cuda.Stream":
+    if _SIDE["stream"] is None:
+        _SIDE["stream"] = torch.cuda.Stream()
+    return _SIDE["stream"]
+
+
+def _join_side_at_backward_end() -> bool:
+    """Once per backward pass: the main stream waits for the side-stream weight gradients before the autograd engine
+    returns (optimizer.step / the next forward read main_grad on the main stream)."""
+    if not _SIDE["joined"]:
+        return True
+    _SIDE["joined"] = False
+
+    def join():
+        torch.cuda.current_stream().wait_stream(_side_stream())
+        _SIDE["joined"] = True
+
+    try:
+        torch.autograd.Variable._execution_engine.queue_callback(join)
+        return True
+    except RuntimeError:                     # not inside a backward pass (backward() called by hand): the caller joins at once
+        _SIDE["joined"] = True
+        return False
+
+
 def wire_dtype() -> str:
     """Dtype of the partial sums that cross NVLink in the fused GEMM→reduce-scatter: ``bf16`` (default; the switch
     accumulates in fp32, one rounding at the end) or ``fp32`` (``NXD_TP_WIRE=fp32``: the reference's reduce_dtype=fp32 wire
@@ -92,6 +124,7 @@ class TPWorkspace:
         self.nv_claim_base = 0
         self.nv_counters: Optional[torch.Tensor] = None
         self.nv_checked = False
+        self._ag_reader_event = None        # side-stream reader of the most recent gathered buffer (see ag_gemm_nvls)
         self.sm_pairs = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count // 2
 
     def _ensure(self, ag_bytes: int, rs_bytes: int) -> None:
@@ -159,16 +192,23 @@ class TPWorkspace:
         M = ms * self.world
         N = b.shape[0] if trans_b else b.shape[1]
         self._ensure_nvls(M * K * 2, 0)
+        ev = self._ag_reader_event
+        if ev is not None:
+            # a side-stream weight gradient is (was) reading the gathered buffer of the PREVIOUS all-gather.  Peers may
+            # overwrite that parity as soon as they have seen this rank's pushes of THIS call (DESIGN §2.2 invariant), so this
+            # call must not start before that reader is done.
+            torch.cuda.current_stream().wait_event(ev)
+            self._ag_reader_event = None
         self.nv_ag_epoch += 1
         off = self._nv_off_ag(self.nv_ag_epoch & 1)
         out = torch.empty(M, N, dtype=torch.bfloat16, device=a_shard.device)
         _ext.count_launch()
         _ext.ext().tp_gemm_nvls(1, a_shard, b, out, trans_b, self.nv.ptrs, self.nv.mc_ptr, self.nv.local_ptr, off, 0,
-                                self.nv_ag_epoch, self.rank, self.world, NVLS_CONFIG["comm_ctas_ag"], self.nv_counters, 0, False)
+                                self.nv_ag_epoch, self.rank, self.world, NVLS_CONFIG["comm_ctas_ag"], self.nv_counters, 0, False, True)
         # the multicast store also lands in this rank's own buffer: the gathered view is complete without a local copy
         return out, self.nv.local_tensor(off, (M, K), torch.bfloat16)
 
-    def gemm_rs_nvls(self, a: torch.Tensor, b: torch.Tensor, trans_b: bool) -> torch.Tensor:
+    def gemm_rs_nvls(self, a: torch.Tensor, b: torch.Tensor, trans_b: bool, gemm_join: bool = True) -> torch.Tensor:
         M, K = a.shape
         N = b.shape[0] if trans_b else b.shape[1]
         ms = M // self.world
@@ -180,7 +220,7 @@ class TPWorkspace:
         _ext.count_launch()
         used = _ext.ext().tp_gemm_nvls(2, a, b, out, trans_b, self.nv.ptrs, self.nv.mc_ptr, self.nv.local_ptr, off,
                                        _NVLS_RS_FLAG_OFF, self.nv_rs_epoch, self.rank, self.world, NVLS_CONFIG["comm_ctas_rs"],
-                                       self.nv_counters, self.nv_claim_base, w32)
+                                       self.nv_counters, self.nv_claim_base, w32, bool(gemm_join))
         self.nv_claim_base = (self.nv_claim_base + int(used)) & 0xFFFFFFFF
         return out
 
@@ -228,12 +268,12 @@ class TPWorkspace:
             dist.barrier(group=self.group)
 
     # ------------------------------------------------------------------ GEMM → reduce-scatter
-    def gemm_rs(self, a: torch.Tensor, b: torch.Tensor, trans_b: bool) -> torch.Tensor:
+    def gemm_rs(self, a: torch.Tensor, b: torch.Tensor, trans_b: bool, gemm_join: bool = True) -> torch.Tensor:
         M, K = a.shape
         N = b.shape[0] if trans_b else b.shape[1]
         ms = M // self.world
         if ms % TILE_M2 == 0 and ms // BLOCK_M <= NVLS_MAX_ROW_BLOCKS and self.nvls_enabled():
-            return self.gemm_rs_nvls(a, b, trans_b)
+            return self.gemm_rs_nvls(a, b, trans_b, gemm_join)
         if ms // BLOCK_M > MAX_ROW_BLOCKS:
             raise RuntimeError(f"fused GEMM→RS without NVLS supports at most {MAX_ROW_BLOCKS * BLOCK_M} rows per rank (got {ms})")
         self._ensure(0, M * N * 2)
@@ -301,6 +341,33 @@ def _wgrad(go2d, x2d, weight):
     return wgrad(go2d, x2d, weight)
 
 
+def _side_wgrad_ok(ws: "TPWorkspace", weight: torch.Tensor, wanted: bool) -> bool:
+    """Side-stream weight gradients need the fused main_grad epilogue (the GEMM writes the optimizer's fp32 buffer itself, so
+    nothing is returned through autograd from the side stream) and the NVLS kernels (gemm_join)."""
+    mg = getattr(weight, "main_grad", None)
+    from . import gemm as _gemm
+
+    return bool(wanted and _SIDE_WGRAD and mg is not None and mg.dtype == torch.float32 and mg.is_contiguous()
+                and mg.shape == weight.shape and _gemm.fused_wgrad_enabled() and ws.nv is not None and ws.nvls_enabled())
+
+
+def _wgrad_on_side(ready_event, go2d: torch.Tensor, x2d: torch.Tensor, weight: torch.Tensor):
+    """Launch ``main_grad (+)= goᵀ @ x`` on the side stream after ``ready_event``; returns an event recorded after it."""
+    side = _side_stream()
+    deferred_join = _join_side_at_backward_end()
+    side.wait_event(ready_event)
+    go2d.record_stream(side)                 # the caching allocator must not hand these blocks out while the side GEMM reads them
+    x2d.record_stream(side)
+    with torch.cuda.stream(side):
+        r = _wgrad(go2d, x2d, weight)
+        assert r is None
+        done = torch.cuda.Event()
+        done.record()
+    if not deferred_join:
+        torch.cuda.current_stream().wait_event(done)
+    return done
+
+
 def _flat(x: torch.Tensor) -> torch.Tensor:
     return x.reshape(-1, x.shape[-1])
 
@@ -322,12 +389,20 @@ class _ColumnSP:
         g2 = _flat(gy).contiguous()
         gbias = g2.float().sum(0).to(gy.dtype) if has_bias else None
         gx = gw = None
+        side = _side_wgrad_ok(self.ws, weight, need_gw and need_gx)
+        ev = None
+        if side:
+            ev = torch.cuda.Event()
+            ev.record()                                                   # g2 / gathered are complete here
         if need_gx:
             gd = g2 if gy_dgrad is None else _flat(gy_dgrad).contiguous()
-            gx2 = self.ws.gemm_rs(gd, weight, False)                     # RS(g @ W)
+            gx2 = self.ws.gemm_rs(gd, weight, False, gemm_join=not side)  # RS(g @ W); GEMM CTAs exit early when the wgrad follows
             gx = gx2.view(x.shape)
         if need_gw:
-            gw = _wgrad(g2, gathered, weight)                            # gᵀ @ AG(x)
+            if side:
+                _wgrad_on_side(ev, g2, gathered, weight)                  # gᵀ @ AG(x) under the reduce-scatter tail
+            else:
+                gw = _wgrad(g2, gathered, weight)                         # gᵀ @ AG(x)
         return gx, gw, gbias
 
 
@@ -348,7 +423,15 @@ class _RowSP:
         gbias = g2.float().sum(0).to(gy.dtype) if has_bias else None
         gx2, g_full = self.ws.ag_gemm(g2, weight, False)                 # AG(g) @ W
         gx = gx2.view(x.shape) if need_gx else None
-        gw = _wgrad(g_full, _flat(x), weight) if need_gw else None       # AG(g)ᵀ @ x
+        gw = None
+        if need_gw:
+            if _side_wgrad_ok(self.ws, weight, True):
+                ev = torch.cuda.Event()
+                ev.record()                                               # the fused kernel (and with it the gather) is done
+                done = _wgrad_on_side(ev, g_full, _flat(x), weight)       # AG(g)ᵀ @ x, overlapping whatever follows
+                self.ws._ag_reader_event = done                           # the next all-gather call waits for this reader
+            else:
+                gw = _wgrad(g_full, _flat(x), weight)                     # AG(g)ᵀ @ x
         return gx, gw, gbias
 
 
