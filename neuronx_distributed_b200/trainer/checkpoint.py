@@ -190,15 +190,37 @@ class CheckpointIOState:
         self.wait_save()
 
     def finalize_shutdown(self) -> None:
+        """atexit flush of an asynchronous save.  The process group may already be gone, so ranks cannot barrier: every
+        rank drops a `<tag>/.async_done/rank_N` marker after ITS writes finished and rank 0 publishes `done` only once all
+        `world` markers exist (bounded wait); otherwise the tag stays incomplete and auto-resume skips it — a tag is never
+        marked complete while another rank was still writing (or had crashed)."""
         try:
             if self.save_future is not None:
                 self.save_future.result()
                 self.save_future = None
             pend = getattr(self, "_pending_done", None)
-            if pend is not None and _rank() == 0:
+            if pend is not None:
+                import time
+
                 storage, tag, _ = pend
-                storage.save_text("1", os.path.join(tag, "done"))
                 self._pending_done = None
+                world = int(os.environ.get("WORLD_SIZE", "1"))
+                rank = int(os.environ.get("RANK", "0"))
+                try:
+                    if dist.is_initialized():
+                        world, rank = dist.get_world_size(), dist.get_rank()
+                except Exception:                     # noqa: BLE001 - group already destroyed
+                    pass
+                storage.save_text("1", os.path.join(tag, ".async_done", f"rank_{rank}"))
+                if rank == 0:
+                    deadline = time.time() + float(os.environ.get("NXD_ASYNC_CKPT_SHUTDOWN_WAIT_S", "120"))
+                    while time.time() < deadline:
+                        if all(storage.file_exists(os.path.join(tag, ".async_done", f"rank_{r}")) for r in range(world)):
+                            storage.save_text("1", os.path.join(tag, "done"))
+                            break
+                        time.sleep(0.2)
+                    else:
+                        logger.warning("async checkpoint %s left incomplete at shutdown: not every rank finished writing", tag)
         finally:
             if self.executor is not None:
                 self.executor.shutdown(wait=True)
@@ -332,6 +354,10 @@ def save_checkpoint(
     io.begin(storage, tag)
     ep = ps.get_expert_model_parallel_size() > 1
     dp_rank, dp_size = ps.get_data_parallel_rank(), ps.get_data_parallel_size()
+    # Under expert parallelism a model / non-ZeRO optimizer file is keyed by ep_rank and replicated only over the EXPERT
+    # data-parallel group (reference checkpoint.py:443-474, 545-585: edp_size / edp_rank): that group spreads the xser tensor
+    # bins, and exactly one member (edp_rank 0) writes the plain file, the ref file and the info file.
+    rep_rank, rep_size = (ps.get_expert_data_parallel_rank(), ps.get_expert_data_parallel_size()) if ep else (dp_rank, dp_size)
 
     opt_has_master = False
     if optimizer is not None:
@@ -341,15 +367,17 @@ def save_checkpoint(
         inner = getattr(optimizer, "optimizer", optimizer)
         zero1 = zero1_optimizer or isinstance(inner, (Zero1Optimizer, NeuronEPZero1Optimizer))
         opt_has_master = _zero1_states_have_master_weights(sd)
-        path = _get_path(os.path.join(tag, "optim"), dp=zero1, ep=False)
+        # ZeRO-1 state is per dp rank (every rank owns a different shard); a plain optimizer's state is replicated over the
+        # (expert-)data-parallel group and differs between EP ranks (reference `_get_path("optim", ep=True)`)
+        path = _get_path(os.path.join(tag, "optim"), dp=zero1, ep=(ep and not zero1))
         if use_zero1_dcp and zero1:
             from ..optimizer import zero_dcp_utils
 
             zero_dcp_utils.save_optim_state_dict(os.path.join(storage.dirname(), tag, "optim"), sd, inner)
         elif use_xser:
-            writers, wrank = (1, 0) if zero1 else (dp_size, dp_rank)
+            writers, wrank = (1, 0) if zero1 else (rep_size, rep_rank)
             _xser_tasks(sd, path, writers, wrank, io)
-        elif zero1 or dp_rank == 0:
+        elif zero1 or rep_rank == 0:
             io.add_save_task(_to_cpu(sd), path + ".pt")
 
     if model is not None:
@@ -360,8 +388,8 @@ def save_checkpoint(
             sd = model.state_dict() if hasattr(model, "state_dict") else model
             path = _get_path(os.path.join(tag, "model"), dp=False, ep=ep)
             if use_xser:
-                _xser_tasks(sd, path, dp_size, dp_rank, io)
-            elif dp_rank == 0 or ep:
+                _xser_tasks(sd, path, rep_size, rep_rank, io)
+            elif rep_rank == 0:
                 io.add_save_task(_to_cpu(sd), path + ".pt")
 
     if _rank() == 0:
@@ -397,23 +425,28 @@ def load_checkpoint(
     model_dir, optim_dir = os.path.join(tag, "model"), os.path.join(tag, "optim")
     use_xser = storage.is_checkpoint_xser(model_dir) or storage.is_checkpoint_xser(optim_dir)
     dp_group, dp_size, dp_rank = ps.get_data_parallel_group(), ps.get_data_parallel_size(), ps.get_data_parallel_rank()
+    if ep:      # replicas of an ep_rank-keyed file live in the expert-data-parallel group (see save_checkpoint)
+        rep_group, rep_size, rep_rank = (ps.get_expert_data_parallel_group(), ps.get_expert_data_parallel_size(),
+                                         ps.get_expert_data_parallel_rank())
+    else:
+        rep_group, rep_size, rep_rank = dp_group, dp_size, dp_rank
 
     if model is not None and storage.dir_exists(model_dir):
         p = _get_path(model_dir, dp=False, ep=ep)
-        sd = _xser_load(storage, p, dp_group, dp_size, dp_rank) if use_xser else storage.load_object(p + ".pt", "cpu")
+        sd = _xser_load(storage, p, rep_group, rep_size, rep_rank) if use_xser else storage.load_object(p + ".pt", "cpu")
         model.load_state_dict(sd, strict=strict)
     if optimizer is not None:
         from ..optimizer.zero_redundancy_optimizer import NeuronEPZero1Optimizer, Zero1Optimizer
 
         inner = getattr(optimizer, "optimizer", optimizer)
         zero1 = isinstance(inner, (Zero1Optimizer, NeuronEPZero1Optimizer))
-        p = _get_path(optim_dir, dp=zero1, ep=False)
+        p = _get_path(optim_dir, dp=zero1, ep=(ep and not zero1))
         if use_zero1_dcp and zero1:
             from ..optimizer import zero_dcp_utils
 
             sd = zero_dcp_utils.load_optim_state_dict(os.path.join(storage.dirname(), optim_dir), inner)
         elif use_xser:
-            sd = _xser_load(storage, p, dp_group, 1 if zero1 else dp_size, 0 if zero1 else dp_rank)
+            sd = _xser_load(storage, p, rep_group, 1 if zero1 else rep_size, 0 if zero1 else rep_rank)
         else:
             sd = storage.load_object(p + ".pt", "cpu")
         optimizer.load_state_dict(sd)

@@ -26,8 +26,7 @@ class AdamW_FP32OptimParams(Optimizer):
     def step(self, closure: Optional[Callable] = None):
         loss = closure() if closure is not None else None
         for group in self.param_groups:
-            ps_, gs, ms, vs, lowp = [], [], [], [], []
-            step = None
+            ps_, gs, ms, vs, lowp, steps = [], [], [], [], [], []
             for p in group["params"]:
                 g = p.grad if p.grad is not None else getattr(p, "main_grad", None)
                 if g is None:
@@ -40,7 +39,7 @@ class AdamW_FP32OptimParams(Optimizer):
                     if p.dtype != torch.float32:
                         st["master"] = p.detach().float().clone()
                 st["step"] += 1
-                step = st["step"]
+                steps.append(st["step"])
                 if "master" in st:
                     ps_.append(st["master"])
                     lowp.append(p.data)
@@ -54,15 +53,18 @@ class AdamW_FP32OptimParams(Optimizer):
                 continue
             b1, b2 = group["betas"]
             has_low = [x is not None for x in lowp]
+            # one fused multi-tensor launch per (low-precision copy?, step count): the bias correction is a per-parameter
+            # quantity — parameters that joined later (un-frozen, or without a gradient in earlier steps) have their own count
             for want_low in (True, False):
-                idx = [i for i, h in enumerate(has_low) if h == want_low]
-                if not idx:
-                    continue
-                ops.optim.fused_adamw_(
-                    [ps_[i] for i in idx], [gs[i] for i in idx], [ms[i] for i in idx], [vs[i] for i in idx],
-                    group["lr"], b1, b2, group["eps"], group["weight_decay"],
-                    step, self.grad_scale,
-                    [lowp[i] for i in idx] if want_low else None,
-                    hf_form=True, correct_bias=group["correct_bias"],
-                )
+                for step in sorted(set(steps)):
+                    idx = [i for i, h in enumerate(has_low) if h == want_low and steps[i] == step]
+                    if not idx:
+                        continue
+                    ops.optim.fused_adamw_(
+                        [ps_[i] for i in idx], [gs[i] for i in idx], [ms[i] for i in idx], [vs[i] for i in idx],
+                        group["lr"], b1, b2, group["eps"], group["weight_decay"],
+                        step, self.grad_scale,
+                        [lowp[i] for i in idx] if want_low else None,
+                        hf_form=True, correct_bias=group["correct_bias"],
+                    )
         return loss

@@ -194,3 +194,56 @@ def _s3_ckpt(rank, world, fake_root):
 
 def test_s3_storage_against_fake_client(tmp_path):
     run_distributed(_s3_ckpt, 2, str(tmp_path / "s3"), timeout=180)
+
+
+def _ep_ckpt(rank, world, root, use_xser, zero1):
+    """EP=2 on 4 ranks (tp=1 → dp=4, expert-dp=2): model files are keyed by ep_rank and written once per expert-DP group;
+    a plain optimizer's state is keyed by ep_rank too; restoring into fresh objects reproduces the next step on every rank."""
+    import neuronx_distributed_b200 as n
+    from neuronx_distributed_b200.models.mixtral import MixtralConfig, MixtralForCausalLM
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.utils.adamw_fp32_optim_params import AdamW_FP32OptimParams
+
+    def build():
+        cfg = n.neuronx_distributed_config(tensor_parallel_size=1, expert_parallel_size=2,
+                                           optimizer_config={"zero_one_enabled": zero1, "grad_clipping": True, "max_grad_norm": 1.0})
+        mcfg = MixtralConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=1, num_attention_heads=4,
+                             num_local_experts=4, num_experts_per_tok=2, dtype=torch.float32, max_position_embeddings=16)
+        torch.manual_seed(0)
+        model = n.initialize_parallel_model(cfg, lambda: MixtralForCausalLM(mcfg))
+        opt = n.initialize_parallel_optimizer(cfg, AdamW_FP32OptimParams, model.parameters(), lr=1e-2)
+        return model, opt
+
+    def step(model, opt, seed):
+        ids = torch.randint(0, 64, (2, 16), generator=torch.Generator().manual_seed(1000 * seed + ps.get_data_parallel_rank()))
+        opt.zero_grad()
+        loss = model.run_train(input_ids=ids, labels=ids)
+        opt.step()
+        return float(loss)
+
+    model, opt = build()
+    for i in range(2):
+        step(model, opt, i)
+    n.save_checkpoint(root, "s", model=model, optimizer=opt, use_xser=use_xser)
+    n.finalize_checkpoint()
+    epr = ps.get_expert_model_parallel_rank()
+    base = os.path.join(root, "s", "model", f"dp_rank_00_ep_rank_{epr:02d}_tp_rank_00_pp_rank_00")
+    assert os.path.exists(base if use_xser else base + ".pt"), base
+    if use_xser:
+        info = torch.load(base + ".info.pt", weights_only=False)
+        files = set(os.listdir(base + ".tensors"))
+        assert files == {f"tensor_{i}.pt" for i in info}, (sorted(files), sorted(info))     # every bin was written
+    if not zero1:
+        ob = os.path.join(root, "s", "optim", f"dp_rank_00_ep_rank_{epr:02d}_tp_rank_00_pp_rank_00")
+        assert os.path.exists(ob if use_xser else ob + ".pt"), ob
+    want = step(model, opt, 7)
+    ps.destroy_model_parallel()
+    model2, opt2 = build()
+    n.load_checkpoint(root, tag="s", model=model2, optimizer=opt2)
+    got = step(model2, opt2, 7)
+    assert abs(got - want) < 1e-4, (rank, got, want)
+
+
+@pytest.mark.parametrize("use_xser,zero1", [(False, False), (True, False), (True, True)])
+def test_trainer_checkpoint_expert_parallel(tmp_path, use_xser, zero1):
+    run_distributed(_ep_ckpt, 4, str(tmp_path), use_xser, zero1, timeout=240)
