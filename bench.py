@@ -191,8 +191,9 @@ def main():
     dp = max(1, args.dp)
     tp = args.tp if args.tp > 0 else world // dp
     assert tp * dp == world, f"--tp {tp} x --dp {dp} != {world} GPUs"
-    if dp > 1:
-        os.environ.setdefault("NXD_ZERO1_OVERLAP", "1")        # bucketed reduce-scatter launched under the backward
+    # dp > 1: ZeRO-1's reduce-scatter / all-gather kernels run in optimizer.step().  The bucketed variant that launches them
+    # under the backward (NXD_ZERO1_OVERLAP=1) measured SLOWER on 2 GPUs (610 vs 393 ms/step: its 16 resident CTAs keep the
+    # persistent 148-CTA GEMMs from being fully resident, so every GEMM runs a second partial wave) and stays opt-in.
     sp = tp > 1
     cfg = nxd.neuronx_distributed_config(
         tensor_parallel_size=tp, sequence_parallel=sp,
@@ -339,7 +340,8 @@ def main():
                        "global_batch": gbs, "micro_batch": mbs, "seq_len": S,
                        "parallelism": f"tp{tp}" + ("+sp" if sp else "") + (f" x dp{dp}" if dp > 1 else ""),
                        "optimizer": f"AdamW fp32 master + fp32 grad-acc (ZeRO-1, dp={dp}"
-                                    + (", bucketed reduce-scatter overlapped with backward" if dp > 1 else "") + ")",
+                                    + (", peer-memory reduce-scatter / all-gather kernels" if dp > 1 else "")
+                                    + (", bucketed under backward" if dp > 1 and os.environ.get("NXD_ZERO1_OVERLAP", "0") == "1" else "") + ")",
                        "tp_backend": args.backend, **_tp_comm_info(tp, args.backend),
                        "act_ckpt": args.act_ckpt, "l2": "inputs(weights+activations)>>L2, no flush needed",
                        "baseline_note": "vs_baseline divides by the only published number: Trn1 32-core gate 6.90 seq/s @ seq 8192",

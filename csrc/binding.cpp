@@ -98,8 +98,7 @@ static Tensor rope_apply(const Tensor& x, const Tensor& cos_t, const Tensor& sin
   c10::cuda::CUDAGuard g(x.device());
   auto out = at::empty(x.sizes(), x.options());
   const int es = (int)x.element_size();
-  TORCH_CHECK((reinterpret_cast<uintptr_t>(x.data_ptr()) % 16) == 0 && (x.stride(0) * es) % 16 == 0 &&
-              (x.stride(1) * es) % 16 == 0 && (x.stride(2) * es) % 16 == 0, "rope: 16-byte alignment required");
+  (void)es;      // unaligned / odd rotary dims take the scalar kernel (csrc/elementwise.cu rope_scalar_kernel)
   if (x.numel())
     nxd::rope_apply(x.data_ptr(), out.data_ptr(), cos_t.data_ptr<float>(), sin_t.data_ptr<float>(), (int)x.size(0),
                     (int)x.size(1), (int)x.size(2), (int)x.size(3), x.stride(0), x.stride(1), x.stride(2), (float)sign,
@@ -182,6 +181,25 @@ static Tensor oneshot_allreduce(const Tensor& x, const Tensor& peer_bufs, const 
   nxd::oneshot_allreduce(x.data_ptr(), out.data_ptr(), peer_bufs.data_ptr<int64_t>(), peer_flags.data_ptr<int64_t>(), slot_bytes,
                          (uint32_t*)state.data_ptr(), (int)rank, (int)world, x.numel(), dt_code(x), ctas, stream());
   return out;
+}
+
+// q [B,1,H,D], k/v [B,1,Hkv,D] (views of the fused QKV GEMV output), cache [B,L,Hkv,D]: rotate q → new tensor, rotate k and
+// copy v straight into the cache row positions[b]
+static Tensor decode_rope_kv(const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& positions, const Tensor& cos_t,
+                             const Tensor& sin_t, Tensor kc, Tensor vc) {
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && q.dim() == 4 && q.size(1) == 1 && q.stride(3) == 1);
+  TORCH_CHECK(k.scalar_type() == at::kBFloat16 && k.dim() == 4 && k.size(1) == 1 && k.stride(3) == 1 && v.stride(3) == 1 && v.sizes() == k.sizes());
+  TORCH_CHECK(kc.scalar_type() == at::kBFloat16 && kc.dim() == 4 && kc.stride(3) == 1 && vc.sizes() == kc.sizes() && vc.strides() == kc.strides());
+  TORCH_CHECK(positions.scalar_type() == at::kLong && positions.is_contiguous() && positions.numel() == q.size(0));
+  CHECK_IN(cos_t); CHECK_IN(sin_t);
+  TORCH_CHECK(cos_t.scalar_type() == at::kFloat && cos_t.size(1) == q.size(3) / 2 && cos_t.size(0) >= kc.size(1));
+  c10::cuda::CUDAGuard g(q.device());
+  const int B = (int)q.size(0), H = (int)q.size(2), Hkv = (int)k.size(2), D = (int)q.size(3), L = (int)kc.size(1);
+  Tensor q_out = at::empty({B, 1, H, D}, q.options());
+  nxd::decode_rope_kv(q.data_ptr(), k.data_ptr(), v.data_ptr(), positions.data_ptr<long>(), cos_t.data_ptr<float>(),
+                      sin_t.data_ptr<float>(), q_out.data_ptr(), kc.data_ptr(), vc.data_ptr(), B, H, Hkv, D, L, q.stride(0), q.stride(2),
+                      k.stride(0), k.stride(2), v.stride(0), v.stride(2), kc.stride(0), kc.stride(1), kc.stride(2), stream());
+  return q_out;
 }
 
 // ---- decode ---------------------------------------------------------------------------------------
@@ -549,6 +567,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16_2cta", &gemm_bf16_2cta);
   m.def("oneshot_allreduce", &oneshot_allreduce);
   m.def("decode_attention", &decode_attention);
+  m.def("decode_rope_kv", &decode_rope_kv);
   m.def("gemv", &gemv, py::arg("x"), py::arg("w"), py::arg("residual") = py::none());
   m.def("gemm_fp8", &gemm_fp8);
   m.def("grouped_gemm", &grouped_gemm);

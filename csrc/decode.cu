@@ -177,7 +177,56 @@ __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restri
   }
 }
 
+// Decode-time RoPE + KV-cache append in ONE launch (was ~25 tiny elementwise / index_put kernels per layer in the token-
+// generation graph): q [B,H,D] rotated into q_out, k rotated and v copied into the cache row positions[b].  One warp per head
+// row; cos/sin rows gathered by position.  HF rotate-half convention (csrc/elementwise.cu rope_kernel).
+__global__ void __launch_bounds__(128) decode_rope_kv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                            const __nv_bfloat16* __restrict__ v, const long* __restrict__ positions,
+                                                            const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                                            __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ kc,
+                                                            __nv_bfloat16* __restrict__ vc, int B, int H, int Hkv, int D, int L,
+                                                            long q_sb, long q_sh, long k_sb, long k_sh, long v_sb, long v_sh,
+                                                            long c_sb, long c_ss, long c_sh) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int rows = B * (H + 2 * Hkv);
+  if (warp >= rows) return;
+  const int b = warp / (H + 2 * Hkv), r = warp % (H + 2 * Hkv);
+  long pos = positions[b];
+  pos = pos < 0 ? 0 : (pos >= L ? L - 1 : pos);
+  const int half = D / 2;
+  if (r < H + Hkv) {                                   // q or k head: rotate
+    const bool is_q = r < H;
+    const int h = is_q ? r : r - H;
+    const __nv_bfloat16* src = is_q ? q + b * q_sb + (long)h * q_sh : k + b * k_sb + (long)h * k_sh;
+    __nv_bfloat16* dst = is_q ? q_out + ((long)b * H + h) * D : kc + b * c_sb + pos * c_ss + (long)h * c_sh;
+    const float* cr = cos_t + pos * half;
+    const float* sr = sin_t + pos * half;
+    for (int c = lane; c < half; c += 32) {
+      const float a = __bfloat162float(src[c]), bb = __bfloat162float(src[half + c]);
+      const float cs = cr[c], sn = sr[c];
+      dst[c] = __float2bfloat16_rn(a * cs - bb * sn);
+      dst[half + c] = __float2bfloat16_rn(bb * cs + a * sn);
+    }
+  } else {                                             // v head: copy
+    const int h = r - H - Hkv;
+    const __nv_bfloat16* src = v + b * v_sb + (long)h * v_sh;
+    __nv_bfloat16* dst = vc + b * c_sb + pos * c_ss + (long)h * c_sh;
+    for (int c = lane; c < D; c += 32) dst[c] = src[c];
+  }
+}
+
 }  // namespace
+
+void decode_rope_kv(const void* q, const void* k, const void* v, const long* positions, const float* cos_t, const float* sin_t,
+                    void* q_out, void* kc, void* vc, int B, int H, int Hkv, int D, int L, long q_sb, long q_sh, long k_sb, long k_sh,
+                    long v_sb, long v_sh, long c_sb, long c_ss, long c_sh, cudaStream_t st) {
+  const int rows = B * (H + 2 * Hkv);
+  const int grid = (rows * 32 + 127) / 128;
+  decode_rope_kv_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, positions,
+                                              cos_t, sin_t, (__nv_bfloat16*)q_out, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, B, H, Hkv, D, L,
+                                              q_sb, q_sh, k_sb, k_sh, v_sb, v_sh, c_sb, c_ss, c_sh);
+  NXD_CUDA_CHECK(cudaGetLastError());
+}
 
 void decode_attention(const void* q, const void* k, const void* v, const long* positions, void* out, float* part_o,
                       float* part_ml, int B, int H, int Hkv, int L, const long* ks, const long* vs, long q_sb, long q_sh,

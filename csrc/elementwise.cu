@@ -367,10 +367,39 @@ void swiglu_bwd(const void* go, const void* gu, void* dgu, long rows, int I, int
   NXD_CUDA_CHECK(cudaGetLastError());
 }
 
+// any even D (partial rotary dims such as GPT-NeoX-20B's 24 of 96): one element pair per thread
+template <typename T>
+__global__ void __launch_bounds__(256) rope_scalar_kernel(const T* __restrict__ x, T* __restrict__ out,
+                                                          const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                                          int B, int S, int Hh, int D, long sb, long ss, long sh, float sign) {
+  const int half = D / 2;
+  const size_t total = (size_t)B * S * Hh * half;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % half);
+    size_t t = idx / half;
+    const int h = (int)(t % Hh); t /= Hh;
+    const int s = (int)(t % S);
+    const int b = (int)(t / S);
+    const T* src = x + b * sb + s * ss + h * sh;
+    T* dst = out + (((size_t)b * S + s) * Hh + h) * D;
+    const float cs = cos_t[(size_t)s * half + c], sn = sin_t[(size_t)s * half + c] * sign;
+    const float a = to_f32<T>(src[c]), bb = to_f32<T>(src[half + c]);
+    dst[c] = from_f32<T>(a * cs - bb * sn);
+    dst[half + c] = from_f32<T>(bb * cs + a * sn);
+  }
+}
+
 void rope_apply(const void* x, void* out, const float* cos_t, const float* sin_t, int B, int S, int Hh, int D, long sb,
                 long ss, long sh, float sign, int dt, cudaStream_t st) {
   DISPATCH_DTYPE(dt, {
-    if ((D / 2) % Pack16<T>::N) nxd_throw("rope: D/2 must be a multiple of the vector width", __FILE__, __LINE__);
+    if (D % 2) nxd_throw("rope: D must be even", __FILE__, __LINE__);
+    if ((D / 2) % Pack16<T>::N || ((uintptr_t)x % 16) || (sb * sizeof(T)) % 16 || (ss * sizeof(T)) % 16 || (sh * sizeof(T)) % 16) {
+      const size_t total = (size_t)B * S * Hh * (D / 2);
+      const int grid = (int)min((size_t)num_sms() * 16, (total + 255) / 256);
+      rope_scalar_kernel<T><<<max(grid, 1), 256, 0, st>>>((const T*)x, (T*)out, cos_t, sin_t, B, S, Hh, D, sb, ss, sh, sign);
+      NXD_CUDA_CHECK(cudaGetLastError());
+      return;
+    }
     const size_t total = (size_t)B * S * Hh * ((D / 2) / Pack16<T>::N);
     const int grid = (int)min((size_t)num_sms() * 16, (total + 255) / 256);
     rope_kernel<T><<<max(grid, 1), 256, 0, st>>>((const T*)x, (T*)out, cos_t, sin_t, B, S, Hh, D, sb, ss, sh, sign);

@@ -104,6 +104,9 @@ void oneshot_allreduce(const void* x, void* out, const int64_t* peer_bufs, const
 void decode_attention(const void* q, const void* k, const void* v, const long* positions, void* out, float* part_o,
                       float* part_ml, int B, int H, int Hkv, int L, const long* ks, const long* vs, long q_sb, long q_sh,
                       long o_sb, long o_sh, float scale, int splits, cudaStream_t st);
+void decode_rope_kv(const void* q, const void* k, const void* v, const long* positions, const float* cos_t, const float* sin_t,
+                    void* q_out, void* kc, void* vc, int B, int H, int Hkv, int D, int L, long q_sb, long q_sh, long k_sb, long k_sh,
+                    long v_sb, long v_sh, long c_sb, long c_ss, long c_sh, cudaStream_t st);
 void gemv_bf16(const void* x, const void* w, const void* residual, void* y, int M, int N, int K, cudaStream_t st);
 
 // ---- attention (attention_sm100.cu): q [B,S_q,H,128], k/v [B,S_kv,Hkv,128] bf16 views; strides = (b, s, h) in elements

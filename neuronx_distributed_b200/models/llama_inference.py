@@ -74,6 +74,14 @@ class LlamaForInference(nn.Module):
             q, k = ops.rope.apply_rotary(q, cos, sin), ops.rope.apply_rotary(k, cos, sin)
             self.kv.write_prefill(layer_idx, k, v)
             o = ops.attention.flash_attention(q, k, v, causal=True)
+        elif (q.is_cuda and q.dtype == torch.bfloat16 and self.kv.kv_quant is None and self.kv.seq_shards == 1
+              and ops._ext.ext() is not None and hasattr(ops._ext.ext(), "decode_rope_kv")):
+            # one launch: RoPE of q and k at each sequence's position + append of k / v to the cache (csrc/decode.cu)
+            ops._ext.count_launch()
+            q = ops._ext.ext().decode_rope_kv(q, k, v, positions.to(torch.long).contiguous(), self.rope_cos, self.rope_sin,
+                                              self.kv.k[layer_idx], self.kv.v[layer_idx])
+            kc, vc = self.kv.get(layer_idx, kv_len)
+            o = _decode_attention(q, kc, vc, positions)
         else:
             # one new token per sequence at its own position
             cos = self.rope_cos[positions].unsqueeze(1)     # [B, 1, D/2] → per-batch tables
@@ -83,14 +91,20 @@ class LlamaForInference(nn.Module):
             kc, vc = self.kv.get(layer_idx, kv_len)
             o = _decode_attention(q, kc, vc, positions)
         o = o.transpose(0, 1).reshape(S, B, att.num_heads_local * D)
-        return x + att.o_proj(o)
+        return _row_linear_plus_residual(att.o_proj, o, x)
 
     def _body(self, input_ids: torch.Tensor, positions: Optional[torch.Tensor], prefill: bool, kv_len: Optional[int], tree=None):
         core = self._core
         x = core.embed_tokens(input_ids).transpose(0, 1).contiguous()               # [S, B, H]
         for i, layer in enumerate(core.layers):
             x = self._attn_block(i, layer, x, positions, prefill, kv_len, tree)
-            y = layer.mlp(layer.post_attention_layernorm(x))
+            mlp = layer.mlp
+            if hasattr(mlp, "gate_up_proj") and hasattr(mlp, "down_proj") and not prefill and x.shape[0] * x.shape[1] <= 8:
+                # dense decode MLP: the residual add rides in the down-projection's GEMV(+all-reduce) epilogue
+                hmid = ops.act.swiglu(mlp.gate_up_proj(layer.post_attention_layernorm(x)))
+                x = _row_linear_plus_residual(mlp.down_proj, hmid, x)
+                continue
+            y = mlp(layer.post_attention_layernorm(x))
             x = x + (y[0] if isinstance(y, tuple) else y)                           # MoE blocks also return router logits
         return core.norm(x)
 
@@ -141,6 +155,26 @@ class LlamaForInference(nn.Module):
             out.append(tok)
             pos = pos + 1
         return torch.stack(out, dim=1)
+
+
+def _row_linear_plus_residual(lin, inp: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
+    """``residual + RowParallelLinear(inp)``.  At decode (<= 8 rows, bf16, no bias) this is ONE kernel: the GEMV with the residual
+    in its epilogue (tp = 1) or the fused GEMV + in-switch all-reduce + residual (tp > 1, csrc/nvls_coll.cu)."""
+    M = inp.numel() // inp.shape[-1]
+    w = lin.weight
+    e = ops._ext.ext() if inp.is_cuda else None
+    if (e is not None and M <= 8 and inp.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and getattr(lin, "bias", None) is None
+            and not torch.is_grad_enabled() and getattr(lin, "reduce_output", True) and w.shape[1] % 8 == 0 and w.shape[0] % 8 == 0
+            and not getattr(lin, "sequence_parallel_enabled", False)):
+        x2 = inp.reshape(M, inp.shape[-1]).contiguous()
+        r2 = residual.reshape(M, residual.shape[-1]).contiguous()
+        tp = lin.tensor_model_parallel_size
+        if tp == 1 and hasattr(e, "gemv"):
+            ops._ext.count_launch()
+            return e.gemv(x2, w, r2).view_as(residual)
+        if tp > 1 and ops.tp_fused.get_backend() == "fused" and ops.nvls.gemv_all_reduce_eligible(x2, w):
+            return ops.nvls.gemv_all_reduce(x2, w, lin.tensor_parallel_group, residual=r2).view_as(residual)
+    return residual + lin(inp)
 
 
 def _rope_per_batch(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:

@@ -27,7 +27,7 @@ class _Rope(torch.autograd.Function):
     def forward(ctx, x, cos, sin):
         ctx.save_for_backward(cos, sin)
         if _ext.use_cuda(x, cos, sin) and x.dtype in (torch.bfloat16, torch.float16, torch.float32) \
-                and x.stride(-1) == 1 and x.shape[-1] % 8 == 0:
+                and x.stride(-1) == 1 and x.shape[-1] % 2 == 0:
             ctx.cuda = True
             _ext.count_launch()
             return _ext.ext().rope_apply(x, cos.contiguous().float(), sin.contiguous().float(), 1.0)

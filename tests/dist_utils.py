@@ -27,7 +27,14 @@ def _worker(rank, world, port, fn, args, use_cuda, errq):
                           LOCAL_RANK=str(rank), LOCAL_WORLD_SIZE=str(world))
         import torch.distributed as dist
 
-        if use_cuda:
+        if use_cuda == "loopback":
+            # every rank on cuda:0 — NCCL refuses two ranks on one device, so the control plane is gloo; the peer-memory
+            # kernels (VMM fd exchange / cudaIpc both work intra-device) run their real flag / epoch protocols between the
+            # two processes' contexts, which the GPU time-slices
+            torch.cuda.set_device(0)
+            os.environ["NXD_LOOPBACK"] = "1"
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+        elif use_cuda:
             torch.cuda.set_device(rank)
             dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
         else:

@@ -176,3 +176,32 @@ def test_fused_add_rmsnorm_vs_fp32_reference(dtype):
     for got, want in ((x.grad, xf.grad), (r.grad, rf.grad), (w.grad, wf.grad)):
         assert (got.float() - want).abs().max() / want.abs().max() < tol
     assert torch.equal(x.grad, r.grad)
+
+
+@pytest.mark.gpu
+def test_decode_rope_kv_fused_vs_separate_ops():
+    """RoPE of q/k at per-sequence positions + KV-cache append in one launch vs the eager composition."""
+    from neuronx_distributed_b200 import ops
+    from neuronx_distributed_b200.models.llama_inference import _rope_per_batch
+
+    e = ops._ext.ext()
+    dev = torch.device("cuda")
+    B, H, Hkv, D, L = 3, 8, 4, 128, 64
+    torch.manual_seed(0)
+    qkv = torch.randn(1, B, (H + 2 * Hkv) * D, device=dev, dtype=torch.bfloat16)
+    q, k, v = torch.split(qkv, [H * D, Hkv * D, Hkv * D], dim=-1)
+    q = q.reshape(1, B, H, D).transpose(0, 1)
+    k = k.reshape(1, B, Hkv, D).transpose(0, 1)
+    v = v.reshape(1, B, Hkv, D).transpose(0, 1).contiguous()
+    cos, sin = ops.rope.rope_tables(L, D, 10000.0, dev)
+    pos = torch.tensor([5, 0, 63], device=dev)
+    kc = torch.zeros(B, L, Hkv, D, device=dev, dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    q_out = e.decode_rope_kv(q, k, v, pos, cos, sin, kc, vc)
+    q_ref = _rope_per_batch(q, cos[pos].unsqueeze(1), sin[pos].unsqueeze(1))
+    k_ref = _rope_per_batch(k, cos[pos].unsqueeze(1), sin[pos].unsqueeze(1))
+    torch.testing.assert_close(q_out.float(), q_ref.float(), atol=2e-2, rtol=2e-2)
+    b = torch.arange(B, device=dev)
+    torch.testing.assert_close(kc[b, pos].float(), k_ref[:, 0].float(), atol=2e-2, rtol=2e-2)
+    assert torch.equal(vc[b, pos], v[:, 0])
+    assert int((kc != 0).any(dim=-1).any(dim=-1).sum()) == B          # exactly one cache row per sequence was written
