@@ -23,6 +23,8 @@ import threading
 from concurrent.futures import Future, ThreadPoolExecutor
 from typing import Any, Dict, List, Optional, Tuple
 
+import contextlib
+
 import torch
 import torch.distributed as dist
 
@@ -34,14 +36,60 @@ logger = get_logger()
 
 
 class TensorReference:
-    """Stub left in an xser reference file in place of a tensor (pickle-compatible role of
-    ``torch_xla.utils.serialization.TensorReference``)."""
+    """Stub left in an xser reference file in place of a tensor.  Pickled under the NAME the reference's files use —
+    ``torch_xla.utils.serialization.TensorReference`` (same single attribute ``tid``) — so xser checkpoints written by the
+    reference load here and checkpoints written here load there (``NXD_XSER_NATIVE_PICKLE=1`` keeps this module's own name)."""
 
     def __init__(self, tid: int):
         self.tid = tid
 
     def __repr__(self) -> str:
         return f"TensorReference({self.tid})"
+
+
+_XLA_SER = "torch_xla.utils.serialization"
+
+
+@contextlib.contextmanager
+def _torch_xla_pickle_names():
+    """While active, ``torch_xla.utils.serialization.TensorReference`` resolves to :class:`TensorReference` (and that is the
+    name pickle writes for it).  If the real torch_xla is importable nothing is shimmed except the class identity on load."""
+    import sys
+    import types
+
+    created = []
+    for name in ("torch_xla", "torch_xla.utils", _XLA_SER):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []                                  # behaves as a package for the sub-module lookups
+            sys.modules[name] = m
+            created.append(name)
+    ser = sys.modules[_XLA_SER]
+    prev = getattr(ser, "TensorReference", None)
+    ser.TensorReference = TensorReference
+    old_mod = TensorReference.__module__
+    if os.environ.get("NXD_XSER_NATIVE_PICKLE", "0") != "1":
+        TensorReference.__module__ = _XLA_SER
+    try:
+        yield
+    finally:
+        TensorReference.__module__ = old_mod
+        if prev is not None:
+            ser.TensorReference = prev
+        elif _XLA_SER not in created:
+            try:
+                del ser.TensorReference
+            except AttributeError:
+                pass
+        for name in created:
+            sys.modules.pop(name, None)
+
+
+class _RawBytes:
+    """Already-serialised payload: storages write it verbatim (``save_object`` of anything else goes through torch.save)."""
+
+    def __init__(self, data: bytes):
+        self.data = data
 
 
 def _get_path(prefix: str, tp: bool = True, pp: bool = True, dp: bool = False, ep: bool = False) -> str:
@@ -289,7 +337,12 @@ def _xser_tasks(state: Any, path: str, writers: int, writer_rank: int, iostate: 
     for tid in bins[writer_rank % max(1, writers)]:
         iostate.add_save_task(_to_cpu(tensors[tid]), os.path.join(path + ".tensors", f"tensor_{tid}.pt"))
     if writer_rank == 0:
-        iostate.add_save_task(ref, path)
+        import io as _io
+
+        buf = _io.BytesIO()
+        with _torch_xla_pickle_names():            # serialised NOW (tiny object) under the reference's class name
+            torch.save(ref, buf)
+        iostate.add_save_task(_RawBytes(buf.getvalue()), path)
         info = {i: {"dtype": t.dtype, "shape": tuple(t.shape),
                     "expert_model_parallel": bool(getattr(t, "expert_model_parallel", False))} for i, t in enumerate(tensors)}
         iostate.add_save_task(info, path + ".info.pt")
@@ -297,7 +350,8 @@ def _xser_tasks(state: Any, path: str, writers: int, writer_rank: int, iostate: 
 
 def _xser_load(storage: BaseCheckpointStorage, path: str, group, readers: int, reader_rank: int) -> Any:
     """One reader per replica group loads each tensor file and broadcasts it (reference :347-432)."""
-    ref = storage.load_object(path, map_location="cpu")
+    with _torch_xla_pickle_names():                # files written by the reference name torch_xla's TensorReference
+        ref = storage.load_object(path, map_location="cpu")
     info = storage.load_object(path + ".info.pt", map_location="cpu")
     tensors: Dict[int, torch.Tensor] = {}
     from ..utils import get_device

@@ -165,6 +165,13 @@ class FilesysCheckpointStorage(BaseCheckpointStorage):
 
     def save_object(self, obj: Any, filename: str) -> None:
         path = self._p(filename)
+        if type(obj).__name__ == "_RawBytes":            # pre-serialised payload (trainer/checkpoint.py)
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            tmp = path + ".tmp"
+            with open(tmp, "wb") as f:
+                f.write(obj.data)
+            os.replace(tmp, path)
+            return
         os.makedirs(os.path.dirname(path), exist_ok=True)
         tmp = path + ".tmp"
         torch.save(obj, tmp)
@@ -434,7 +441,10 @@ class S3CheckpointStorage(BaseCheckpointStorage):
 
     def save_object(self, obj: Any, filename: str) -> None:
         buf = io.BytesIO()
-        torch.save(obj, buf)
+        if type(obj).__name__ == "_RawBytes":            # pre-serialised payload (trainer/checkpoint.py)
+            buf.write(obj.data)
+        else:
+            torch.save(obj, buf)
         self.upload_stream_to_file(buf, filename)
 
     def load_object(self, filename: str, map_location=None) -> Any:

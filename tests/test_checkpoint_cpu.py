@@ -247,3 +247,32 @@ def _ep_ckpt(rank, world, root, use_xser, zero1):
 @pytest.mark.parametrize("use_xser,zero1", [(False, False), (True, False), (True, True)])
 def test_trainer_checkpoint_expert_parallel(tmp_path, use_xser, zero1):
     run_distributed(_ep_ckpt, 4, str(tmp_path), use_xser, zero1, timeout=240)
+
+
+def test_xser_reference_files_use_torch_xla_tensor_reference_name(tmp_path):
+    """xser ref files are interchangeable with the reference's: the stub class is pickled as
+    ``torch_xla.utils.serialization.TensorReference`` and a file that names that class loads here without torch_xla."""
+    import io
+    import pickletools
+    import sys
+
+    from neuronx_distributed_b200.trainer import checkpoint as ck
+
+    tensors = []
+    ref = ck._flatten_tensors({"w": torch.ones(2), "n": {"b": torch.zeros(1)}, "step": 3}, tensors)
+    buf = io.BytesIO()
+    with ck._torch_xla_pickle_names():
+        torch.save(ref, buf)
+    assert "torch_xla" not in sys.modules                      # the shim does not leak
+    raw = buf.getvalue()
+    import zipfile
+
+    with zipfile.ZipFile(io.BytesIO(raw)) as z:
+        pkl = z.read([n for n in z.namelist() if n.endswith("data.pkl")][0])
+    ops_ = [(op.name, arg) for op, arg, _ in pickletools.genops(pkl)]
+    assert any(a == "torch_xla.utils.serialization TensorReference" or a == "torch_xla.utils.serialization" for _, a in ops_ if isinstance(a, str)), ops_[:12]
+    with ck._torch_xla_pickle_names():
+        back = torch.load(io.BytesIO(raw), weights_only=False)
+    assert isinstance(back["w"], ck.TensorReference) and back["w"].tid == 0 and back["n"]["b"].tid == 1 and back["step"] == 3
+    out = ck._unflatten_tensors(back, {0: tensors[0], 1: tensors[1]})
+    assert torch.equal(out["w"], torch.ones(2))
