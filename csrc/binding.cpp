@@ -183,6 +183,40 @@ static Tensor oneshot_allreduce(const Tensor& x, const Tensor& peer_bufs, const 
   return out;
 }
 
+// ---- row selection (sampling) -------------------------------------------------------------------------
+static py::tuple row_argmax(const Tensor& x, int64_t index_offset) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.stride(1) == 1, "row_argmax: [rows, V] with contiguous last dim");
+  c10::cuda::CUDAGuard g(x.device());
+  auto val = at::empty({x.size(0)}, x.options().dtype(at::kFloat));
+  auto idx = at::empty({x.size(0)}, x.options().dtype(at::kLong));
+  nxd::row_argmax(x.data_ptr(), val.data_ptr<float>(), idx.data_ptr<long>(), (int)x.size(0), (int)x.size(1), x.stride(0), index_offset,
+                  dt_code(x), stream());
+  return py::make_tuple(val, idx);
+}
+static bool row_topk_supported(int64_t V, int64_t k) { return nxd::row_topk_supported((int)V, (int)k); }
+static py::tuple row_topk(const Tensor& x, int64_t k, int64_t index_offset) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.stride(1) == 1, "row_topk: [rows, V] with contiguous last dim");
+  c10::cuda::CUDAGuard g(x.device());
+  auto vals = at::empty({x.size(0), k}, x.options().dtype(at::kFloat));
+  auto idx = at::empty({x.size(0), k}, x.options().dtype(at::kLong));
+  nxd::row_topk(x.data_ptr(), vals.data_ptr<float>(), idx.data_ptr<long>(), (int)x.size(0), (int)x.size(1), (int)k, x.stride(0),
+                index_offset, dt_code(x), stream());
+  return py::make_tuple(vals, idx);
+}
+
+// expert_index [T, k] (int32 / int64) → (block_to_expert [nb], token_position_to_id [nb*B], tokens_per_expert [E]) int64
+static py::tuple moe_block_metadata(const Tensor& expert_index, int64_t num_experts, int64_t block_size, int64_t num_blocks) {
+  CHECK_IN(expert_index);
+  TORCH_CHECK(expert_index.dim() == 2 && (expert_index.scalar_type() == at::kLong || expert_index.scalar_type() == at::kInt));
+  c10::cuda::CUDAGuard g(expert_index.device());
+  auto o = expert_index.options().dtype(at::kLong);
+  auto b2e = at::empty({num_blocks}, o), tp2id = at::empty({num_blocks * block_size}, o), counts = at::empty({num_experts}, o);
+  nxd::moe_block_metadata(expert_index.data_ptr(), expert_index.scalar_type() == at::kLong, expert_index.numel(), (int)expert_index.size(1),
+                          (int)num_experts, (int)block_size, (int)num_blocks, b2e.data_ptr<long>(), tp2id.data_ptr<long>(),
+                          counts.data_ptr<long>(), stream());
+  return py::make_tuple(b2e, tp2id, counts);
+}
+
 // q [B,1,H,D], k/v [B,1,Hkv,D] (views of the fused QKV GEMV output), cache [B,L,Hkv,D]: rotate q → new tensor, rotate k and
 // copy v straight into the cache row positions[b]
 static Tensor decode_rope_kv(const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& positions, const Tensor& cos_t,
@@ -568,6 +602,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("oneshot_allreduce", &oneshot_allreduce);
   m.def("decode_attention", &decode_attention);
   m.def("decode_rope_kv", &decode_rope_kv);
+  m.def("moe_block_metadata", &moe_block_metadata);
+  m.def("row_argmax", &row_argmax);
+  m.def("row_topk", &row_topk);
+  m.def("row_topk_supported", &row_topk_supported);
   m.def("gemv", &gemv, py::arg("x"), py::arg("w"), py::arg("residual") = py::none());
   m.def("gemm_fp8", &gemm_fp8);
   m.def("grouped_gemm", &grouped_gemm);

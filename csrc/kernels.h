@@ -100,6 +100,15 @@ void grouped_wgrad_bf16(const void* a, const void* b, void* out, int rows_total,
 void oneshot_allreduce(const void* x, void* out, const int64_t* peer_bufs, const int64_t* peer_flags, long slot_bytes,
                        uint32_t* state, int rank, int world, long numel, int dt, int ctas, cudaStream_t st);
 
+// ---- row selection for sampling (select.cu)
+void row_argmax(const void* x, float* val, long* idx, int rows, int V, long row_stride, long index_offset, int dt, cudaStream_t st);
+bool row_topk_supported(int V, int k);
+void row_topk(const void* x, float* vals, long* idxs, int rows, int V, int k, long row_stride, long index_offset, int dt,
+              cudaStream_t st);
+
+void moe_block_metadata(const void* expert_index, bool idx64, long n, int k, int E, int B, int nb, long* block_to_expert, long* tp2id,
+                        long* counts, cudaStream_t st);
+
 // ---- decode (decode.cu)
 void decode_attention(const void* q, const void* k, const void* v, const long* positions, void* out, float* part_o,
                       float* part_ml, int B, int H, int Hkv, int L, const long* ks, const long* vs, long q_sb, long q_sh,

@@ -31,6 +31,14 @@ def build_block_metadata(expert_index: torch.Tensor, num_experts: int, block_siz
     Entirely on device (sort + cumsum), no host sync."""
     T, k = expert_index.shape
     nb = get_num_blocks(T, k, num_experts, block_size)
+    if expert_index.is_cuda and num_experts <= 256 and expert_index.dtype in (torch.int32, torch.int64):
+        from ... import ops
+
+        e = ops._ext.ext()
+        if e is not None and hasattr(e, "moe_block_metadata"):
+            # one launch, no sort (csrc/select.cu moe_block_metadata_kernel — role of the reference's index-build NKI kernels)
+            ops._ext.count_launch()
+            return e.moe_block_metadata(expert_index.contiguous(), int(num_experts), int(block_size), int(nb))
     flat_e = expert_index.reshape(-1)
     token_ids = torch.arange(T, device=expert_index.device).repeat_interleave(k)
     order = torch.argsort(flat_e, stable=True)

@@ -2,8 +2,8 @@
 
 local (max, argmax) → ONE all-gather of the packed ``[..., 2]`` (value, global index) pairs over the group →
 final argmax of the ``tp`` candidates.  Ties resolve to the smallest global index, like ``torch.argmax`` on
-the gathered tensor.  The reference's multi-stage "cascaded max" NKI kernel (K10) is a single fused
-``torch.max`` pass per shard on CUDA — a [B, V/tp] row reduction is a one-kernel HBM-bound op."""
+the gathered tensor.  The reference's multi-stage "cascaded max" NKI kernel (K10) is ``csrc/select.cu::row_argmax_kernel``
+here: one CTA per row, 16-byte loads, value + index in one pass (``torch.max`` on CPU / other dims)."""
 from __future__ import annotations
 
 from typing import Optional
@@ -20,7 +20,13 @@ def argmax(tensor: torch.Tensor, dim: int, gather_dim: Optional[int] = None, kee
     group = process_group if process_group is not None else ps.get_tensor_model_parallel_group()
     n = dist.get_world_size(group)
     dim = dim % tensor.dim()
-    val, idx = torch.max(tensor, dim=dim, keepdim=True)
+    if dim == tensor.dim() - 1 and tensor.is_cuda:
+        from ..ops import select as _select           # one-pass row arg-max kernel (csrc/select.cu, role of NKI cascaded_max)
+
+        val, idx = _select.row_max(tensor)
+        val, idx = val.unsqueeze(dim).to(tensor.dtype), idx.unsqueeze(dim)
+    else:
+        val, idx = torch.max(tensor, dim=dim, keepdim=True)
     if n == 1:
         return idx if keepdim else idx.squeeze(dim)
     r = dist.get_rank(group) if rank_id is None else rank_id.reshape(-1)[0].to(idx.device)

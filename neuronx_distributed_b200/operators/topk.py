@@ -17,7 +17,13 @@ def topk(tensor: torch.Tensor, k: int, dim: int, gather_dim: Optional[int] = Non
     n = dist.get_world_size(group)
     dim = dim % tensor.dim()
     kk = min(k, tensor.shape[dim])
-    vals, idx = torch.topk(tensor, kk, dim=dim)
+    if dim == tensor.dim() - 1 and tensor.is_cuda:
+        from ..ops import select as _select           # smem-staged k-pass selection kernel (csrc/select.cu, role of nkilib topk)
+
+        vals, idx = _select.row_topk(tensor, kk)
+        vals = vals.to(tensor.dtype)
+    else:
+        vals, idx = torch.topk(tensor, kk, dim=dim)
     if n == 1:
         return vals, idx
     r = dist.get_rank(group) if rank_id is None else rank_id.reshape(-1)[0].to(idx.device)

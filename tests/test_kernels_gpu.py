@@ -205,3 +205,41 @@ def test_decode_rope_kv_fused_vs_separate_ops():
     torch.testing.assert_close(kc[b, pos].float(), k_ref[:, 0].float(), atol=2e-2, rtol=2e-2)
     assert torch.equal(vc[b, pos], v[:, 0])
     assert int((kc != 0).any(dim=-1).any(dim=-1).sum()) == B          # exactly one cache row per sequence was written
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_row_argmax_and_topk_kernels_vs_torch(dtype):
+    from neuronx_distributed_b200.ops import select
+
+    dev = torch.device("cuda")
+    torch.manual_seed(1)
+    for rows, V in ((3, 4000), (2, 32016), (5, 1001)):
+        x = torch.randn(rows, V, device=dev).to(dtype)
+        v, i = select.row_max(x, index_offset=7)
+        rv, ri = torch.max(x.float(), dim=-1)
+        torch.testing.assert_close(v, rv)
+        assert torch.equal(x.float().gather(1, (i - 7).unsqueeze(1)).squeeze(1), rv)      # an index of the maximum …
+        first = (x.float() == rv.unsqueeze(1)).float().argmax(dim=1)
+        assert torch.equal(i - 7, first)                                                   # … the smallest one
+        for k in (1, 8, 50):
+            tv, ti = select.row_topk(x, k)
+            rtv, _ = torch.topk(x.float(), k, dim=-1)
+            torch.testing.assert_close(tv, rtv)
+            assert torch.equal(x.float().gather(1, ti), tv)
+
+
+@pytest.mark.gpu
+def test_moe_block_metadata_kernel_matches_sort_based_build():
+    import os
+
+    from neuronx_distributed_b200.modules.moe import blockwise
+
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    for T, k, E, B in ((4096, 2, 8, 512), (1000, 2, 16, 128), (300, 4, 64, 128), (8192, 1, 4, 256)):
+        idx = torch.stack([torch.randperm(E, device=dev)[:k] for _ in range(T)])
+        got = blockwise.build_block_metadata(idx, E, B)                       # CUDA kernel
+        want = blockwise.build_block_metadata(idx.cpu(), E, B)                # sort + cumsum path
+        for a, b, name in zip(got, want, ("block_to_expert", "token_position_to_id", "tokens_per_expert")):
+            assert torch.equal(a.cpu(), b), (name, T, k, E, B)
