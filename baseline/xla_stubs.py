@@ -168,13 +168,18 @@ def _xm_all_gather(value, dim=0, groups=None, output=None, pin_layout=True):
         res = torch.cat(parts, dim=dim)
     else:
         dim = dim % v.dim()
-        if dim == 0:
-            res = torch.empty((n * v.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
-            dist.all_gather_into_tensor(res, v, group=pg)          # one NCCL call straight into the result, no cat copy
-        else:
-            stacked = torch.empty((n,) + tuple(v.shape), dtype=v.dtype, device=v.device)
-            dist.all_gather_into_tensor(stacked, v, group=pg)
-            res = torch.cat(list(stacked.unbind(0)), dim=dim)
+        try:
+            if dim == 0:
+                res = torch.empty((n * v.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+                dist.all_gather_into_tensor(res, v, group=pg)      # one NCCL call straight into the result, no cat copy
+            else:
+                stacked = torch.empty((n,) + tuple(v.shape), dtype=v.dtype, device=v.device)
+                dist.all_gather_into_tensor(stacked, v, group=pg)
+                res = torch.cat(list(stacked.unbind(0)), dim=dim)
+        except (RuntimeError, ValueError, TypeError):              # e.g. a 0-d tensor: list form handles everything
+            parts = [torch.empty_like(v) for _ in range(n)]
+            dist.all_gather(parts, v, group=pg)
+            res = torch.cat(parts, dim=dim) if v.dim() else torch.stack(parts)
     if output is not None:                      # torch_xla writes into `output` when given
         output.copy_(res)
         return output
@@ -338,10 +343,13 @@ class ZeroRedundancyOptimizer(torch.optim.Optimizer):
         self.base_optimizer.step()
         if n == 1 and all(s.data.numel() == p.data.numel() for p, s in self._pairs):
             # one multi-tensor cast+copy for all parameters (torch_xla coalesces this too) instead of 2 kernels per parameter
-            torch._foreach_copy_([p.data.view(-1) for p, _ in self._pairs], [s.data.view(-1) for _, s in self._pairs])
-            for _, s in self._pairs:
-                s.grad = None
-            return
+            try:
+                torch._foreach_copy_([p.data.view(-1) for p, _ in self._pairs], [s.data.view(-1) for _, s in self._pairs])
+                for _, s in self._pairs:
+                    s.grad = None
+                return
+            except Exception:          # noqa: BLE001 - any doubt: the plain per-parameter loop below is always valid
+                pass
         fulls = []
         shs = [s.data.to(p.dtype).contiguous() for p, s in self._pairs]
         for (p, s), sh in zip(self._pairs, shs):

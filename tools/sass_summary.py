@@ -2,7 +2,7 @@
 import collections, re, subprocess, sys
 so = sys.argv[1] if len(sys.argv) > 1 else "neuronx_distributed_b200/_build/nxd_b200_C.so"
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-pat = re.compile(r"\b(UTCHMMA(?:\.2CTA)?|UTCQMMA\S*|UTMALDG\S*|UTMASTG\S*|UBLK\S*|LDTM\S*|STTM\S*|UTCBAR\S*|UTCCP\S*|SYNCS\.\S+|HMMA\S*|MEMBAR\.\S+|RED\.E\S*|ATOM\S*|(?:LD|ST)\.E\S*SYS\S*|LDG\.E\S*|STG\.E\S*)")
+pat = re.compile(r"\b(LDGMC\S*|STGMC\S*|REDGMC\S*|REDG\S*|UTCHMMA(?:\.2CTA)?|UTCQMMA\S*|UTMALDG\S*|UTMASTG\S*|UBLK\S*|LDTM\S*|STTM\S*|UTCBAR\S*|UTCCP\S*|SYNCS\.\S+|HMMA\S*|MEMBAR\.\S+|RED\.E\S*|ATOM\S*|(?:LD|ST)\.E\S*SYS\S*|LDG\.E\S*|STG\.E\S*)")
 cur, counts = None, collections.OrderedDict()
 for line in txt.splitlines():
     m = re.search(r"Function : (\S+)", line)
