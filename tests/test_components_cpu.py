@@ -10,7 +10,7 @@ from dist_utils import run_distributed
 
 def _gqa(rank, world):
     """kv_heads (1) < tp (2): KV weights are replicated ×2; q/k/v equal the un-sharded projection; dK/dV weight grads are summed
-    over the KV-shared group so both replicas carry the full gradient."""
+    over the KV-shared group so both replicas carry the full gradient; the input gradient equals the dense model's."""
     from neuronx_distributed_b200.modules.qkv_linear import GQAQKVColumnParallelLinear
     from neuronx_distributed_b200.parallel_layers import parallel_state as ps
 
@@ -33,6 +33,10 @@ def _gqa(rank, world):
         # d/dWk of 2·sum(k) summed over the 2 replicas (KV-shared group all-reduce) = 2 · 2 · Σ x
         want = 2.0 * world * x.detach().sum((0, 1)).expand(nkv * D, H)
         torch.testing.assert_close(gk, want, rtol=1e-4, atol=1e-4)
+        # dL/dx equals the DENSE model's: the K/V head feeds `world` per-rank loss terms, i.e. L = Σq + world·(2Σk + 3Σv).
+        # (Before the 1/multiplier correction of the dgrad path the replicated K/V contribution was counted world times.)
+        dense_gx = (wq.sum(0) + world * (2.0 * wk[: nkv * D].sum(0) + 3.0 * wv[: nkv * D].sum(0))).expand_as(x)
+        torch.testing.assert_close(x.grad, dense_gx, rtol=1e-4, atol=1e-4)
         ps.destroy_model_parallel(); ps.initialize_model_parallel(tensor_model_parallel_size=world)
 
 
