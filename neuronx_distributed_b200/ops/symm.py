@@ -171,7 +171,7 @@ def get_vmm_workspace(group, purpose: str, nbytes: int, multicast: Optional[bool
     if ws is not None and ws.nbytes >= nbytes:
         return ws
     if ws is not None:
-        torch.cuda.synchronize()
+        _sync()
         dist.barrier(group=group)
         ws.close()
     e = _ext.ext()
@@ -194,7 +194,7 @@ def get_vmm_workspace(group, purpose: str, nbytes: int, multicast: Optional[bool
     mc_everywhere = everyone and all(o[0] for o in oks2)
     ptrs, mc_ptr, size = e.vmm_ptrs(handle, mc_everywhere)
     reasons = [o[1] for o in oks + oks2 if o[1]]
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     ws = VmmWorkspace(group=group, rank=rank, world=world, nbytes=int(size), handle=handle,
                       ptrs=torch.tensor(ptrs, dtype=torch.int64, device=dev), ptr_list=list(ptrs), local_ptr=ptrs[rank],
                       mc_ptr=int(mc_ptr), mc_error="; ".join(sorted(set(reasons))))
@@ -203,14 +203,19 @@ def get_vmm_workspace(group, purpose: str, nbytes: int, multicast: Optional[bool
 
         why = ws.mc_error or ("ranks share a device" if same_device else "device reports no multicast support")
         get_logger("symm").warning("NVLS multicast unavailable for workspace '%s' (%s): using unicast peer accesses", purpose, why)
-    torch.cuda.synchronize()
+    _sync()
     dist.barrier(group=group)
     _VMM_WORKSPACES[key] = ws
     return ws
 
 
+def _sync() -> None:
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
 def _device_uuid() -> str:
     try:
         return str(torch.cuda.get_device_properties(torch.cuda.current_device()).uuid)
-    except Exception:
-        return f"dev{torch.cuda.current_device()}"
+    except Exception:                                    # noqa: BLE001 - no uuid attribute / no CUDA (host-logic tests)
+        return f"dev{os.environ.get('LOCAL_RANK', os.environ.get('RANK', '0'))}"
