@@ -250,3 +250,33 @@ def _shard_inplace(rank, world):
 
 def test_get_sharded_checkpoint_tp_ep_quantized():
     run_distributed(_shard_inplace, 2, timeout=120)
+
+
+def test_autobucketing_spacing_and_routers():
+    import torch
+
+    from neuronx_distributed_b200.inference import autobucketing as ab
+
+    assert ab.generate_buckets(128, 1024) == [128, 256, 512, 1024]
+    assert ab.generate_buckets(128, 1500) == [128, 256, 512, 1024, 1500]
+    assert ab.generate_buckets(128, 1100) == [128, 256, 512, 1100]            # 1024 is within sqrt(2) of 1100: dropped
+    assert ab.generate_buckets(512, 512) == [512] and ab.pick_bucket([128, 256], 130) == 256
+    buckets = [4, 8, 16]
+    ids = torch.zeros(2, 16, dtype=torch.long)
+    ids[0, :3], ids[1, :6] = 7, 9                                             # right padded: 3 and 6 real tokens
+    mask = (ids != 0).long()
+    seq_ids = torch.arange(2)
+    out, idx = ab.context_encoding_router([ids, mask, seq_ids], buckets, "right", pad_token=0)
+    assert idx == 1 and out[0].shape == (2, 8) and out[1].shape == (2, 8) and out[2] is seq_ids
+    assert torch.equal(out[0], ids[:, :8])
+    lids = torch.zeros(2, 16, dtype=torch.long)
+    lids[0, -3:], lids[1, -6:] = 7, 9                                         # left padded
+    out, idx = ab.get_context_encoder_bk()([lids, seq_ids], buckets, "left", 0)
+    assert idx == 1 and torch.equal(out[0], lids[:, 8:16])
+    # token generation: positions 3 and 7 → needs 8 cache slots → bucket 8; position 8 → bucket 16
+    tok, pos = torch.ones(2, 1, dtype=torch.long), torch.tensor([[3], [7]])
+    am = torch.ones(2, 16, dtype=torch.long)
+    out, idx = ab.token_generation_router([tok, am, pos], buckets, "right")
+    assert idx == 1 and out[1].shape == (2, 8) and out[0] is tok
+    out, idx = ab.get_token_generation_bk()([tok, torch.tensor([[3], [8]])], buckets, "right")
+    assert idx == 2
