@@ -320,3 +320,24 @@ def test_small_utils(tmp_path):
     assert m.h.weight is m.e.weight
     assert has_fake_tensors(nn.Linear(2, 2, device="meta")) and not has_fake_tensors(m)
     assert recursive_filter({"a": x32, "b": [torch.zeros(1, device="meta"), 3]}, lambda t_: not t_.is_meta) == {"a": x32, "b": [3]}
+
+
+def test_nvls_protocol_model_catches_epoch_reset_and_passes_monotonic():
+    """tools/sim_nvls_protocol.py: random rank interleavings of AG / RS call sequences with a region re-layout in the middle.
+    Monotonic epochs never produce a stale read or a premature overwrite; the round-2 bug (epochs reset while the reused region
+    keeps old flags) is caught."""
+    import importlib.util
+    import os
+
+    import pytest
+
+    spec = importlib.util.spec_from_file_location("sim_nvls_protocol", os.path.join(os.path.dirname(__file__), "..", "tools", "sim_nvls_protocol.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    calls = ["ag", "rs", "ag", "ag", "rs", "ag", "rs", "rs"]
+    for seed in range(25):
+        for reuse, reset in ((True, False), (False, False), (False, True)):
+            sim.simulate(3, calls, 2, 4, reuse, reset, seed)
+    with pytest.raises(sim.StaleRead):
+        for seed in range(10):
+            sim.simulate(3, calls, 2, 4, True, True, seed)
