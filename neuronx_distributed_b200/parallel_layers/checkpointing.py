@@ -54,14 +54,15 @@ def save(checkpoint: Dict[str, Any], output_dir: str, save_serially: bool = True
     if down_cast_bf16:
         state = cast_all(state, torch.float32, torch.bfloat16)
     if save_xser:
-        from ..trainer.checkpoint import _flatten_tensors
+        from ..trainer.checkpoint import _flatten_tensors, _torch_xla_pickle_names
 
         tensors = []
         ref = _flatten_tensors(state, tensors)
         os.makedirs(os.path.join(d, "checkpoint.pt.tensors"), exist_ok=True)
         for i, t in enumerate(tensors):
             torch.save(t, os.path.join(d, "checkpoint.pt.tensors", f"tensor_{i}.pt"))
-        torch.save(ref, os.path.join(d, "checkpoint.pt"))
+        with _torch_xla_pickle_names():                # stubs pickled as torch_xla.utils.serialization.TensorReference
+            torch.save(ref, os.path.join(d, "checkpoint.pt"))
     else:
         torch.save(state, os.path.join(d, "checkpoint.pt"))
     _barrier()
@@ -83,7 +84,10 @@ def load(chkpt_path: str, model: Optional[nn.Module] = None, model_or_optimizer:
     if sharded:
         d = _chkpt_dir(chkpt_path)
         f = os.path.join(d, "checkpoint.pt")
-        ckpt = torch.load(f, map_location="cpu", weights_only=False)
+        from ..trainer.checkpoint import _torch_xla_pickle_names
+
+        with _torch_xla_pickle_names():                # xser reference files (ours or the reference's) name that class
+            ckpt = torch.load(f, map_location="cpu", weights_only=False)
         if load_xser or os.path.isdir(f + ".tensors"):
             from ..trainer.checkpoint import _unflatten_tensors
 

@@ -446,7 +446,11 @@ class CheckpointConverterBase:
         _xser_tasks(partial_state, f, 1, 0, io)
         for obj, name in io.items:
             os.makedirs(os.path.dirname(name), exist_ok=True)
-            torch.save(obj, name)
+            if type(obj).__name__ == "_RawBytes":          # the reference-named TensorReference pickle, already serialised
+                with open(name, "wb") as fh:
+                    fh.write(obj.data)
+            else:
+                torch.save(obj, name)
 
     def save_full(self, args, full_state) -> None:
         path = args.output_dir
