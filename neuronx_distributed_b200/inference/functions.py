@@ -4,8 +4,9 @@
 ``trace`` validates the call (no ``*args/**kwargs`` in the signature, only ``None`` defaults, every required parameter
 supplied, tensors only), binds the example inputs to parameter names and runs the bucket once in eager mode to record the
 output structure.  ``compile`` warms the bucket up on a side stream and captures it into a CUDA graph with persistent
-input / output buffers (eager on CPU).  ``compile_wlo`` / ``compile_layout_transformer`` exist for API parity: buckets share
-the parameter tensors and the GEMMs consume one stored layout, so no weight-layout pass is required on B200."""
+input / output buffers (eager on CPU).  ``compile_wlo`` splits the priority bucket's launch plan
+(``launch_plan.py``) into a layout transformer — the launches that depend only on frozen weights — and the per-call plan;
+``compile_layout_transformer`` packages the transformer for ``NxDModel``."""
 from __future__ import annotations
 
 import inspect
@@ -150,8 +151,8 @@ def trace(model: Union[Callable, nn.Module], args=None, kwargs: Optional[Dict[st
 class _Program:
     """One bucket: static input buffers + (optionally) a captured CUDA graph."""
 
-    def __init__(self, ta: TraceArtifacts, use_graph: bool, warmup: int):
-        self.ta = ta
+    def __init__(self, ta: TraceArtifacts, use_graph: bool, warmup: int, runner: Optional[Callable] = None):
+        self.ta, self.runner = ta, runner
         self.names = [a.param_name for a in ta.provided_args]
         self.static_in = [a.tensor.clone() for a in ta.provided_args]
         self.graph, self.static_out = None, None
@@ -168,6 +169,8 @@ class _Program:
                 self.static_out = self._run(self.static_in)
 
     def _run(self, tensors):
+        if self.runner is not None:                              # a LaunchPlan: positional, in the traced order
+            return self.runner(*tensors)
         return self.ta.model(**dict(zip(self.names, tensors)))
 
     def __call__(self, *tensors: torch.Tensor):
@@ -188,25 +191,52 @@ def compile(trace_artifacts: TraceArtifacts, metaneff: Any = None, compiler_work
         compiler_workdir, metaneff = metaneff, None
     flags = append_default_compiler_flags(compiler_args)
     use_graph = not _flag(flags, "--no-cuda-graph", False)
-    prog = _Program(trace_artifacts, use_graph, int(_flag(flags, "--warmup", 2)))
+    from .launch_plan import LaunchPlan
+
+    plan = None
+    if isinstance(trace_artifacts.model, LaunchPlan) or _flag(flags, "--plan", False):
+        plan = trace_artifacts.record_plan()                     # the program interprets the recorded launches
+    prog = _Program(trace_artifacts, use_graph, int(_flag(flags, "--warmup", 2)), runner=plan)
     if compiler_workdir is not None:
         os.makedirs(compiler_workdir, exist_ok=True)
         with open(os.path.join(compiler_workdir, f"{key or 'model'}.program.txt"), "w") as f:
             f.write(repr(trace_artifacts.describe()) + f"\ncaptured_cuda_graph={prog.graph is not None}\nflags={flags}\n")
     return CompilationArtifacts(program=prog, key=key or "", compiler_workdir=None if compiler_workdir is None else str(compiler_workdir),
-                                compiler_args=flags, captured=prog.graph is not None)
+                                compiler_args=flags, captured=prog.graph is not None, plan=plan)
 
 
 def compile_wlo(trace_artifacts: TraceArtifacts, metaneff: Any = None, compiler_workdir=None, compiler_args: Optional[str] = None,
                 key: Optional[str] = None) -> WLOArtifacts:
-    c = compile(trace_artifacts, metaneff, compiler_workdir, compiler_args, key)
-    return WLOArtifacts(program=c.program, key=c.key, compiler_workdir=c.compiler_workdir, compiler_args=c.compiler_args,
-                        captured=c.captured)
+    """Compile the priority bucket with weight-layout optimisation (reference ``functions.py:compile_wlo``): record the
+    bucket's launch plan, hoist every launch that depends only on frozen weights into a layout-transformer plan (run once
+    per weight load), and capture the remaining per-call plan.  Weights in ``weights_to_skip_layout_optimization`` and
+    state buffers are left alone."""
+    if isinstance(metaneff, (str, os.PathLike)) and compiler_workdir is None:
+        compiler_workdir, metaneff = metaneff, None
+    flags = append_default_compiler_flags(compiler_args)
+    use_graph = not _flag(flags, "--no-cuda-graph", False)
+    plan = trace_artifacts.record_plan()
+    transformer, main, tmap = plan.hoist_weight_only(skip=trace_artifacts.weight_names_to_skip)
+    main.apply_transformer(transformer)
+    prog = _Program(trace_artifacts, use_graph, int(_flag(flags, "--warmup", 2)), runner=main)
+    if compiler_workdir is not None:
+        os.makedirs(compiler_workdir, exist_ok=True)
+        main.save(os.path.join(compiler_workdir, f"{key or 'model'}.plan.json"))
+        transformer.save(os.path.join(compiler_workdir, f"{key or 'model'}.layout_transformer.plan.json"))
+    logger.info("WLO %s: %d launches hoisted into the layout transformer, %d per call", key, len(transformer.nodes), len(main.nodes))
+    return WLOArtifacts(program=prog, key=key or "", compiler_workdir=None if compiler_workdir is None else str(compiler_workdir),
+                        compiler_args=flags, captured=prog.graph is not None, plan=main, transformer=transformer,
+                        layout_transform_map=tmap)
 
 
-def compile_layout_transformer(wlo_artifacts: WLOArtifacts = None, priority_model_weight_name_to_idx: Optional[Dict[str, int]] = None,
-                               compiler_workdir=None, **_unused) -> LayoutTransformerArtifacts:
-    return LayoutTransformerArtifacts()
+def compile_layout_transformer(wlo_artifacts: Optional[WLOArtifacts] = None,
+                               priority_model_weight_name_to_idx: Optional[Dict[str, int]] = None, compiler_workdir=None,
+                               **_unused) -> LayoutTransformerArtifacts:
+    """Package the transformer extracted by :func:`compile_wlo` (reference ``functions.py:compile_layout_transformer``)."""
+    lt = LayoutTransformerArtifacts()
+    if wlo_artifacts is not None and getattr(wlo_artifacts, "transformer", None) is not None:
+        lt.transformers[wlo_artifacts.key] = (wlo_artifacts.transformer, wlo_artifacts.plan)
+    return lt
 
 
 def shard_checkpoint(checkpoint: Dict[str, torch.Tensor], model: nn.Module, start_rank: Optional[int] = None,

@@ -49,11 +49,30 @@ class TraceArtifacts:
     weight_name_to_idx: Dict[str, int] = field(default_factory=dict)
     weight_names_to_skip: set = field(default_factory=set)
     state_names: List[str] = field(default_factory=list)   # buffers the call mutates (KV cache …)
+    _plan: Any = field(default=None, repr=False)           # LaunchPlan of the bucket, recorded on demand
+
+    def record_plan(self):
+        """The bucket's :class:`~.launch_plan.LaunchPlan` (recorded by one more eager run of the example inputs — state
+        buffers are written once more, like in the tracing run)."""
+        if self._plan is None:
+            from .launch_plan import LaunchPlan, record
+
+            if isinstance(self.model, LaunchPlan):
+                self._plan = self.model
+            else:
+                self._plan = record(self.model, [a.tensor for a in self.provided_args],
+                                    [a.param_name for a in self.provided_args], call_with_kwargs=True)
+        return self._plan
 
     # reference field names, so that generic code written against them keeps working
     @property
     def hlo(self) -> Dict[str, Any]:
-        return self.describe()
+        """The reference's traced program is an HLO module; here: the call description, plus the bucket's launch plan (JSON
+        form, key ``"plan"``) once one was recorded."""
+        d = self.describe()
+        if self._plan is not None:
+            d["plan"] = self._plan.to_json()
+        return d
 
     @property
     def metaneff(self) -> Dict[str, Any]:
@@ -84,25 +103,40 @@ class CompilationArtifacts:
     compiler_workdir: Optional[str] = None
     compiler_args: Optional[str] = None
     captured: bool = False
+    plan: Any = None                                       # LaunchPlan the program interprets (None: the module itself runs)
 
     def get_neff_bytes(self) -> bytes:
         """The reference returns the NEFF file; the nearest B200 artefact is a description of the captured program."""
         return repr({"key": self.key, "captured_cuda_graph": self.captured, "args": self.compiler_args}).encode()
 
 
+@dataclass
 class WLOArtifacts(CompilationArtifacts):
-    """Weight-layout-optimised compilation (reference :92-104).  tcgen05 GEMMs read the weights through TMA descriptors
-    in their stored K-major layout in every bucket, so there is nothing to re-lay-out; the class exists so that
-    ``compile_wlo`` callers get the type they expect."""
+    """Weight-layout-optimised compilation of the priority bucket (reference :92-104).  The reference lets the compiler
+    pick weight layouts and extracts a transformer program from the HLO; here the bucket's launch plan is split by
+    :meth:`LaunchPlan.hoist_weight_only`: everything that depends only on frozen weights (casts, transposes,
+    de-quantisation, input-independent masks / tables) moves into ``transformer`` — run once per weight load — and
+    ``plan`` (what the program interprets / what is captured into the CUDA graph) consumes its results."""
+    transformer: Any = None
+    layout_transform_map: Dict[str, List[str]] = field(default_factory=dict)
 
 
 @dataclass
 class LayoutTransformerArtifacts:
-    """Identity weight transform (see :class:`WLOArtifacts`)."""
+    """The weight → derived-weight programs of the compiled buckets (reference :127-157), keyed by bucket."""
     key: str = ModelBuilderConstants.LAYOUT_TRANSFORMER_KEY
+    transformers: Dict[str, Any] = field(default_factory=dict)          # bucket key → (transformer plan, consumer plan)
 
-    def construct_layout_transformer_object(self, local_ranks_size: int):
-        return lambda weights: weights
+    def construct_layout_transformer_object(self, local_ranks_size: int = 1):
+        """Callable that re-derives the hoisted constants from the (already updated, in place) weights of every bucket."""
+        pairs = list(self.transformers.values())
+
+        def transform(weights=None):
+            for transformer, main in pairs:
+                main.apply_transformer(transformer)
+            return weights
+
+        return transform
 
 
 def generate_key(trace_artifacts: TraceArtifacts, key: Optional[str] = None) -> str:

@@ -4,7 +4,11 @@
 * each :class:`BucketProgram` owns persistent input buffers and, on CUDA, a captured graph: ``forward`` copies the
   inputs into the static buffers, replays the graph and returns the static outputs;
 * state (KV cache) lives in the wrapped module and is shared by all programs;
-* ``save``/``load`` persist weights as per-rank safetensors.
+* ``save``/``load`` persist weights as per-rank safetensors; ``save(portable=True)`` (= the reference's
+  ``convert_nxd_model_to_torchscript_model`` + ``torch.jit.save``) writes every bucket as a launch plan
+  (``launch_plan.py``) so that ``load`` needs no model code;
+* buckets compiled with ``compile_wlo`` come with a layout-transformer plan that re-derives the hoisted constants after
+  every ``set_weights`` / ``replace_weights``.
 
 Two ways to fill it: ``add_program`` (v1 ``ModelBuilder.add(key, …)`` buckets) and ``add(key, trace_artifacts,
 compilation_artifacts)`` (v2 ``trace`` → ``compile`` units, reference :87-194), after which ``forward`` accepts positional
@@ -111,6 +115,7 @@ class NxDModel(BaseNxDModel):
         self.state_initializer = state_initializer
         self.states: List[Dict[str, torch.Tensor]] = []
         self.layout_transformer = layout_transformer
+        self._layout_pairs: Dict[str, Tuple[Any, Any]] = dict(getattr(layout_transformer, "transformers", None) or {})
         self.loaded_on_device = False
 
     @property
@@ -136,6 +141,8 @@ class NxDModel(BaseNxDModel):
         self.model_params = params
         self.input_shape_map.setdefault(sig, []).append(key)
         self.units[key] = (trace_artifacts, compilation_artifacts)
+        if getattr(compilation_artifacts, "transformer", None) is not None:
+            self._layout_pairs[key] = (compilation_artifacts.transformer, compilation_artifacts.plan)
         return self
 
     @staticmethod
@@ -152,7 +159,7 @@ class NxDModel(BaseNxDModel):
 
     def get_hlo(self, key: str):
         """The reference returns the HLO proto of a bucket; the B200 analogue is the bucket's call description."""
-        return self._unit(key)[0].describe()
+        return self._unit(key)[0].hlo
 
     def get_metaneff(self, key: str):
         return self._unit(key)[0].metaneff
@@ -256,16 +263,38 @@ class NxDModel(BaseNxDModel):
         return sharded_checkpoint[min(r - self.start_rank, len(sharded_checkpoint) - 1)] if len(sharded_checkpoint) > 1 \
             else sharded_checkpoint[0]
 
-    def set_weights(self, sharded_checkpoint: Sequence[Dict[str, torch.Tensor]]) -> None:
-        """Copy this rank's shard INTO the existing parameter tensors (their addresses are baked into captured graphs)."""
-        sd = self._my_shard(sharded_checkpoint)
+    def _named_state(self) -> List[Dict[str, torch.Tensor]]:
+        """Name → tensor maps of everything that holds weights / state: the wrapped modules and the constants of plan-backed
+        buckets (several buckets bind the same tensors)."""
+        from .launch_plan import LaunchPlan
+
+        maps: List[Dict[str, torch.Tensor]] = []
         for m in self._unique_modules():
             own = dict(m.named_parameters())
             own.update(dict(m.named_buffers()))
-            with torch.no_grad():
+            maps.append(own)
+        seen = set()
+        for ta, ca in self.units.values():
+            for plan in (ta.model, getattr(ca, "plan", None)):
+                if isinstance(plan, LaunchPlan) and id(plan) not in seen:
+                    seen.add(id(plan))
+                    maps.append({n: t for n, t in plan.named_constants().items() if not n.startswith(("_const_", "_derived_"))})
+        return maps
+
+    def _run_layout_transformers(self) -> None:
+        for transformer, main in self._layout_pairs.values():
+            main.apply_transformer(transformer)
+
+    def set_weights(self, sharded_checkpoint: Sequence[Dict[str, torch.Tensor]]) -> None:
+        """Copy this rank's shard INTO the existing parameter tensors (their addresses are baked into captured graphs), then
+        re-derive the constants the layout transformers computed from them."""
+        sd = self._my_shard(sharded_checkpoint)
+        with torch.no_grad():
+            for own in self._named_state():
                 for k, v in sd.items():
                     if k in own and tuple(own[k].shape) == tuple(v.shape):
                         own[k].copy_(v)
+        self._run_layout_transformers()
         self._weights_set = True
 
     def replace_weights(self, sharded_checkpoint: Sequence[Dict[str, torch.Tensor]]) -> None:
@@ -316,6 +345,10 @@ class NxDModel(BaseNxDModel):
         for m in self._unique_modules():
             for p in m.parameters():
                 return p.dtype
+        for own in self._named_state():
+            for t in own.values():
+                if t.is_floating_point():
+                    return t.dtype
         return None
 
     @property
@@ -329,10 +362,9 @@ class NxDModel(BaseNxDModel):
         for st in self.states:
             if buffer_key in st:
                 return st[buffer_key]
-        for m in self._unique_modules():
-            for n, b in list(m.named_buffers()) + list(m.named_parameters()):
-                if n == buffer_key:
-                    return b
+        for own in self._named_state():
+            if buffer_key in own:
+                return own[buffer_key]
         raise KeyError(f"no state / weight buffer named {buffer_key!r}")
 
     def read_from_neuron_buffer(self, buffer_key: str, rank: int = 0) -> torch.Tensor:
@@ -346,9 +378,28 @@ class NxDModel(BaseNxDModel):
             dst.copy_(tensor.to(dst.dtype))
 
     # ---- persistence ---------------------------------------------------------------------
-    def save(self, path_to_save: str, save_weights: bool = False) -> None:
+    def _rank(self) -> int:
+        import torch.distributed as dist
+
+        return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+    def portable_plans(self) -> Dict[str, Any]:
+        """Bucket key → launch plan (recorded now for buckets that were compiled straight from the module), plus
+        ``__lt__<key>`` → layout transformer for WLO buckets."""
+        plans: Dict[str, Any] = {}
+        for key, (ta, ca) in self.units.items():
+            plans[key] = getattr(ca, "plan", None) or ta.record_plan()
+        for key, (transformer, _main) in self._layout_pairs.items():
+            plans[f"__lt__{key}"] = transformer
+        return plans
+
+    def save(self, path_to_save: str, save_weights: bool = False, portable: bool = False) -> None:
         """Directory with ``nxd_model_meta.pt`` (bucket keys, signatures, example input shapes; the module object itself when
-        it pickles, so ``load`` can re-capture without user code) and optionally ``weights_<i>_tp<rank>.safetensors``."""
+        it pickles, so ``load`` can re-capture without user code) and optionally ``weights_<i>_tp<rank>.safetensors``.
+
+        ``portable=True`` writes the model-code-free artefact instead: one launch plan per bucket
+        (``plans_rank<r>.json``) and the constants they bind (``constants_rank<r>.safetensors``: state buffers and
+        captured tables always, checkpoint weights when ``save_weights``)."""
         from ..parallel_layers import parallel_state as ps
         from ..utils.safetensors_utils import save_state_dict_safetensors
 
@@ -359,6 +410,16 @@ class NxDModel(BaseNxDModel):
             "units": {k: {"inputs": ta.input_signature(), "outputs": ta.output_spec, "flags": ca.compiler_args}
                       for k, (ta, ca) in self.units.items()},
         }
+        if portable:
+            if not self.units:
+                raise ValueError("portable save needs buckets registered with add(key, trace_artifacts, compilation_artifacts)")
+            from .launch_plan import save_plans
+
+            extra = {"world_size": self.world_size, "model_params": [list(p) for p in self.model_params],
+                     "units": {k: {"inputs": [list(i[:1]) + [list(i[1]), i[2]] for i in u["inputs"]], "flags": u["flags"],
+                                   "state": list(self.units[k][0].state_names)} for k, u in meta["units"].items()}}
+            save_plans(path_to_save, self.portable_plans(), self._rank(), extra, save_weights=save_weights)
+            return
         mods = self._unique_modules()
         if self.units and len(mods) == 1:
             try:
@@ -377,9 +438,57 @@ class NxDModel(BaseNxDModel):
                 save_state_dict_safetensors(m.state_dict(), os.path.join(path_to_save, f"weights_{i}_tp{r}.safetensors"))
 
     @classmethod
+    def _load_portable(cls, path_to_model: str, start_rank: Optional[int], local_ranks_size: Optional[int],
+                       device: Optional[torch.device]) -> "NxDModel":
+        from .functions import compile as _compile
+        from .launch_plan import load_plans
+        from .model_builder_utils import ModelParamInfo, ProvidedArgInfo, TraceArtifacts
+
+        import torch.distributed as dist
+
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        plans, _tensors, extra = load_plans(path_to_model, rank, device)
+        nxd = cls(world_size=extra.get("world_size", 1), start_rank=start_rank, local_ranks_size=local_ranks_size)
+        params = [ModelParamInfo(n, bool(p)) for n, p in extra.get("model_params", [])]
+        positional = {p.param_name: p.is_positional for p in params}
+        complete = True
+        for key, plan in plans.items():
+            if key.startswith("__lt__"):
+                continue
+            lt = plans.get(f"__lt__{key}")
+            missing = [c.name for i, c in plan.constants.items() if i not in plan.tensors and not c.name.startswith("_derived_")]
+            if lt is not None:
+                missing += [c.name for i, c in lt.constants.items() if i not in lt.tensors]
+            if missing:                                          # saved without weights: allocate, set_weights() fills them
+                complete = False
+                for p in (plan, lt):
+                    if p is None:
+                        continue
+                    for i, c in p.constants.items():
+                        if i not in p.tensors and not c.name.startswith("_derived_"):
+                            shared = next((q.named_constants()[c.name] for q in plans.values() if c.name in q.named_constants()), None)
+                            p.tensors[i] = shared if shared is not None else \
+                                torch.zeros(c.shape, dtype=getattr(torch, c.dtype), device=plan.device)
+            if lt is not None:
+                plan.apply_transformer(lt)
+            u = extra["units"][key]
+            provided = [ProvidedArgInfo(n, positional.get(n, True), torch.zeros(shape, dtype=getattr(torch, dt.replace("torch.", "")),
+                                                                              device=plan.device))
+                        for n, shape, dt in u["inputs"]]
+            ta = TraceArtifacts(model=plan, provided_args=provided, model_params=params, state_names=list(u.get("state", [])))
+            ta._plan = plan
+            ca = _compile(ta, None, None, u.get("flags"), key)
+            nxd.add(key, ta, ca)
+            if lt is not None:
+                nxd._layout_pairs[key] = (lt, plan)
+        nxd._weights_set = complete
+        return nxd
+
+    @classmethod
     def load(cls, path_to_model: str, start_rank: Optional[int] = None, local_ranks_size: Optional[int] = None,
              model: Optional[nn.Module] = None, device: Optional[torch.device] = None) -> "NxDModel":
-        """Rebuild a saved v2 model: re-trace and re-capture every bucket from the recorded input signatures.  ``model`` is
+        """Rebuild a saved v2 model.  A portable artefact (``save(portable=True)``) is re-captured from its launch plans —
+        no model code needed.  Otherwise every bucket is re-traced from the recorded input signatures; ``model`` is then
         needed when the module could not be pickled at save time."""
         import pickle
 
@@ -388,6 +497,8 @@ class NxDModel(BaseNxDModel):
         from .functions import compile as _compile
         from .functions import trace as _trace
 
+        if model is None and not os.path.exists(os.path.join(path_to_model, "nxd_model_meta.pt")):
+            return cls._load_portable(path_to_model, start_rank, local_ranks_size, device)
         meta = torch.load(os.path.join(path_to_model, "nxd_model_meta.pt"), weights_only=False)
         if model is None:
             if not meta.get("module_pickle"):
@@ -406,3 +517,36 @@ class NxDModel(BaseNxDModel):
             nxd.add(key, ta, _compile(ta, None, None, u.get("flags"), key))
         nxd._weights_set = os.path.exists(wpath)
         return nxd
+
+
+class TorchScriptNxDModel(NxDModel):
+    """An ``NxDModel`` whose buckets interpret launch plans: it carries no reference to the model's Python code, and
+    ``save`` / ``load`` default to the portable artefact (reference ``nxd_model.py:709-969``)."""
+
+    def save(self, path_to_save: str, save_weights: bool = True, portable: bool = True) -> None:  # noqa: D102
+        super().save(path_to_save, save_weights=save_weights, portable=portable)
+
+
+def convert_nxd_model_to_torchscript_model(nxd_model: NxDModel, save_weights: bool = False) -> TorchScriptNxDModel:
+    """Model-code-free copy of ``nxd_model`` (reference ``nxd_model.py:924-969``): every bucket is recorded into a launch
+    plan and re-compiled from it.  The copy SHARES weights and state tensors with ``nxd_model``.  ``save_weights`` is the
+    default of the copy's ``save``."""
+    from .functions import compile as _compile
+    from .model_builder_utils import TraceArtifacts
+
+    out = TorchScriptNxDModel(world_size=nxd_model.world_size, start_rank=nxd_model.start_rank if nxd_model.start_rank else None,
+                              local_ranks_size=nxd_model.local_ranks_size if nxd_model.start_rank else None)
+    if not nxd_model.units:
+        raise ValueError("only models built from trace → compile units can be converted")
+    for key, (ta, ca) in nxd_model.units.items():
+        plan = getattr(ca, "plan", None) or ta.record_plan()
+        pta = TraceArtifacts(model=plan, provided_args=ta.provided_args, model_params=ta.model_params, output_spec=ta.output_spec,
+                             weight_name_to_idx=dict(ta.weight_name_to_idx), weight_names_to_skip=set(ta.weight_names_to_skip),
+                             state_names=list(ta.state_names))
+        pta._plan = plan
+        out.add(key, pta, _compile(pta, None, None, ca.compiler_args, key))
+        if key in nxd_model._layout_pairs:
+            out._layout_pairs[key] = nxd_model._layout_pairs[key]
+    out.loaded_on_device = nxd_model.loaded_on_device
+    out._default_save_weights = save_weights
+    return out

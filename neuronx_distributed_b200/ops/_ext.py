@@ -22,6 +22,7 @@ BUILD_DIR = PKG_DIR / "_build"
 EXT_NAME = "nxd_b200_C"
 
 _C = None
+_PLAN_PROXY = None          # set by inference.launch_plan.record(): kernel calls are recorded through it
 _LOAD_ERROR: Optional[BaseException] = None
 _TRIED = False
 
@@ -50,6 +51,8 @@ def _load():
 
 def ext():
     """The extension module or ``None``."""
+    if _PLAN_PROXY is not None:
+        return _PLAN_PROXY
     return _load()
 
 

@@ -24,6 +24,7 @@ from typing import Dict, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from ..utils.plan_registry import plan_op, recording
 from . import _ext, symm
 
 BLOCK_M = 128
@@ -380,6 +381,8 @@ class _ColumnSP:
         self.saved_gathered: Optional[torch.Tensor] = None
 
     def forward(self, x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        if recording():                                    # launch-plan recording: one replayable node, no saved activations
+            return _column_sp_forward_op(x, weight, self.ws.group)
         x2 = _flat(x).contiguous()
         out, gathered = self.ws.ag_gemm(x2, weight, True)
         self.gathered = gathered.clone()   # keep AG(x) for wgrad (one D2D copy; no re-gather in backward)
@@ -413,6 +416,8 @@ class _RowSP:
         self.ws = ws
 
     def forward(self, x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        if recording():
+            return _row_sp_forward_op(x, weight, self.ws.group)
         x2 = _flat(x).contiguous()
         out = self.ws.gemm_rs(x2, weight, True)
         return out.view(x.shape[0] // self.ws.world, *x.shape[1:-1], weight.shape[0])
@@ -433,6 +438,21 @@ class _RowSP:
             else:
                 gw = _wgrad(g_full, _flat(x), weight)                     # AG(g)ᵀ @ x
         return gx, gw, gbias
+
+
+@plan_op("tp_fused.column_sp_forward", pure=True)
+def _column_sp_forward_op(x: torch.Tensor, weight: torch.Tensor, group) -> torch.Tensor:
+    """all-gather(x, dim 0) @ weightᵀ through the fused kernel of ``group``'s workspace (inference: nothing is kept)."""
+    ws = workspace(group)
+    out, _ = ws.ag_gemm(_flat(x).contiguous(), weight, True)
+    return out.view(x.shape[0] * ws.world, *x.shape[1:-1], weight.shape[0])
+
+
+@plan_op("tp_fused.row_sp_forward", pure=True)
+def _row_sp_forward_op(x: torch.Tensor, weight: torch.Tensor, group) -> torch.Tensor:
+    ws = workspace(group)
+    out = ws.gemm_rs(_flat(x).contiguous(), weight, True)
+    return out.view(x.shape[0] // ws.world, *x.shape[1:-1], weight.shape[0])
 
 
 def select(x: torch.Tensor, weight: torch.Tensor, in_mode: str, out_mode: str, seq_dim: int, group):

@@ -10,6 +10,7 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
+from ..utils.plan_registry import plan_op
 from . import _ext, symm
 
 _MAX_BYTES = int(os.environ.get("NXD_ONESHOT_AR_MAX_KB", "2048")) << 10
@@ -48,6 +49,7 @@ def eligible(x: torch.Tensor, group) -> bool:
     return 1 < world <= 8 and dist.get_backend(group) == "nccl"
 
 
+@plan_op("allreduce.all_reduce_sum", pure=True)
 def all_reduce_sum(x: torch.Tensor, group) -> Optional[torch.Tensor]:
     """Returns the reduced tensor (new storage) or ``None`` when the caller should use NCCL.  Every rank of ``group`` must
     make the same decision — it depends only on shape/dtype, which are identical across ranks for TP collectives."""

@@ -15,6 +15,7 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
+from ..utils.plan_registry import plan_op
 from . import _ext, symm
 
 _FLAG_BYTES = 4096                     # 1024 per-CTA barrier counters
@@ -64,6 +65,7 @@ def has_multicast(group) -> bool:
     return _coll(group, "ar", 0, int(os.environ.get("NXD_NVLS_AR_MAX_MB", "8"))).ws.has_multicast
 
 
+@plan_op("nvls.all_reduce_sum", pure=True)
 def all_reduce_sum(x: torch.Tensor, group, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``sum_over_ranks(x) (+ residual)`` as a new tensor.  bf16 / fp32, contiguous, bytes % 16 == 0."""
     nbytes = x.numel() * x.element_size()
@@ -72,6 +74,7 @@ def all_reduce_sum(x: torch.Tensor, group, residual: Optional[torch.Tensor] = No
     return _ext.ext().nvls_allreduce(x, residual, *c.args)
 
 
+@plan_op("nvls.gemv_all_reduce", pure=True)
 def gemv_all_reduce(x: torch.Tensor, weight: torch.Tensor, group, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``sum_over_ranks(x @ weightᵀ) (+ residual)`` for ``x`` [M<=8, K] bf16, ``weight`` [N, K] bf16 in ONE kernel (decode-time
     RowParallelLinear): the GEMV's fp32 partials are reduced in the switch, never rounded to bf16 in between."""
@@ -87,6 +90,7 @@ def gemv_all_reduce_eligible(x2d: torch.Tensor, weight: torch.Tensor) -> bool:
             and available() and os.environ.get("NXD_GEMV_AR", "1") == "1")
 
 
+@plan_op("nvls.all_gather", pure=True)
 def all_gather(x: torch.Tensor, group, ctas: int = 32) -> torch.Tensor:
     """Concatenation over ranks along dim 0 (the shard is multicast into every rank's symmetric buffer, then copied out)."""
     world = dist.get_world_size(group)
@@ -98,6 +102,7 @@ def all_gather(x: torch.Tensor, group, ctas: int = 32) -> torch.Tensor:
     return out
 
 
+@plan_op("nvls.reduce_scatter_sum", pure=True)
 def reduce_scatter_sum(x: torch.Tensor, group, ctas: int = 32) -> torch.Tensor:
     """``x`` = [world * n, ...] on every rank → this rank's [n, ...] chunk of the sum."""
     world = dist.get_world_size(group)

@@ -16,6 +16,7 @@ from typing import Optional, Sequence, Union
 import torch
 import torch.distributed as dist
 
+from ..utils.plan_registry import plan_op
 from . import parallel_state as ps
 
 _REDUCE_OPS = {
@@ -46,6 +47,7 @@ def group_rank(group=None) -> int:
     return dist.get_rank(_tp(group))
 
 
+@plan_op("comm.all_reduce")
 def all_reduce(
     tensors: Union[torch.Tensor, Sequence[torch.Tensor]],
     op: str = "sum",
@@ -89,6 +91,7 @@ def all_reduce(
     return tensors
 
 
+@plan_op("comm.all_gather", pure=True)
 def all_gather(x: torch.Tensor, dim: int = 0, group=None) -> torch.Tensor:
     """Concatenate every rank's ``x`` along ``dim``."""
     group = _tp(group)
@@ -110,6 +113,7 @@ def all_gather(x: torch.Tensor, dim: int = 0, group=None) -> torch.Tensor:
     return out.reshape(shape)
 
 
+@plan_op("comm.reduce_scatter", pure=True)
 def reduce_scatter(x: torch.Tensor, dim: int = 0, group=None, op: str = "sum") -> torch.Tensor:
     """Sum ``x`` over the group and return this rank's 1/n slice along ``dim``."""
     group = _tp(group)
@@ -135,6 +139,7 @@ def reduce_scatter(x: torch.Tensor, dim: int = 0, group=None, op: str = "sum") -
     return out
 
 
+@plan_op("comm.all_to_all", pure=True)
 def all_to_all(x: torch.Tensor, split_dim: int, concat_dim: int, group=None) -> torch.Tensor:
     """Split ``x`` into n pieces along ``split_dim``, exchange, concatenate along ``concat_dim``
     (semantics of ``xm.all_to_all`` used at reference mappings.py:160-172)."""
@@ -156,6 +161,7 @@ def all_to_all(x: torch.Tensor, split_dim: int, concat_dim: int, group=None) -> 
     return torch.cat(outs, dim=concat_dim)
 
 
+@plan_op("comm.broadcast")
 def broadcast(x: torch.Tensor, src: int, group=None) -> torch.Tensor:
     group = _tp(group)
     if dist.get_world_size(group) > 1:

@@ -375,6 +375,24 @@ def _group(name: str, as_list: bool) -> GroupOrMesh:
     return g.mesh if as_list else g.pg
 
 
+def group_name(pg: ProcessGroup) -> Optional[str]:
+    """Registry name of a process group ("tp", "dp", "world", …) or ``None`` — used to store groups symbolically (launch plans)."""
+    for name, g in _STATE.groups.items():
+        if g.pg is pg:
+            return name
+    if pg is None or (dist.is_initialized() and pg is dist.group.WORLD):
+        return "__default__"
+    return None
+
+
+def group_by_name(name: str) -> Optional[ProcessGroup]:
+    if name == "__default__":
+        return dist.group.WORLD
+    g = _STATE.groups.get(name)
+    assert g is not None, f"process group {name!r} is not initialized"
+    return g.pg
+
+
 def _my_ranks(name: str) -> List[int]:
     return _STATE.groups[name].my_ranks(_STATE.rank)
 

@@ -187,10 +187,10 @@ def test_trace_namespace_v1_pieces():
     assert torch.equal(got, e[[1, 3]][:, :, :3])
     f8 = torch.randn(4, 2, 6).to(torch.float8_e4m3fn)
     assert create_local_weight_with_expert_parallel(1, 2, f8, 2, 3, 1, [0]).dtype == torch.float8_e4m3fn
-    # identity behaviour of the layout-transformation hooks; HLO-only entry points explain themselves
+    # the layout-transformation hooks work on launch plans (tests/test_launch_plan_cpu.py); without a transformer they are identities
     wts = {"a": torch.ones(1)}
-    assert hlo_utils.transform_weight_layout_on_cpu(wts) is wts and hlo_utils.get_layout_transform_map() == {}
-    with pytest.raises(NotImplementedError):
+    assert hlo_utils.update_weight(wts) is wts
+    with pytest.raises(FileNotFoundError):
         hlo_utils.read_hlo("x.pb")
     with mock_distributed(8) as d:
         import torch.distributed as td
