@@ -37,9 +37,10 @@ class ModelBuilder:
 
     def compile(self, priority_model_key: Optional[str] = None, compiler_workdir=None,
                 compiler_args: Optional[Union[str, Dict[str, str]]] = None, max_workers: Optional[int] = None) -> NxDModel:
-        """Capture every traced bucket.  ``priority_model_key`` names the bucket captured first (in the reference: the one
-        whose weight layout wins; here it only fixes the capture order, e.g. the largest bucket first so the graph memory
-        pool is sized once).  Captures run sequentially — CUDA graph capture is a per-stream, per-process affair — so
+        """Capture every traced bucket.  ``priority_model_key`` names the bucket that is compiled first and with
+        weight-layout optimisation (``compile_wlo``: its weight-only launches are hoisted into a layout transformer that runs
+        once per weight load); a bucket whose launches cannot be recorded (``PlanError``) is captured as is, with a
+        warning.  Captures run sequentially — CUDA graph capture is a per-stream, per-process affair — so
         ``max_workers`` is accepted and ignored."""
         if not self.trace_artifacts_collection:
             raise ValueError("No traces available for compilation. Call trace() first.")
@@ -57,10 +58,18 @@ class ModelBuilder:
             order.remove(priority_model_key)
             order.insert(0, priority_model_key)
         try:
+            from .launch_plan import PlanError
+
             for key in order:
-                fn = compile_wlo if key == priority_model_key else _compile
-                results[key] = fn(self.trace_artifacts_collection[key], None, compiler_workdir,
-                                  compiler_args[key] if compiler_args else None, key)
+                ta, flags = self.trace_artifacts_collection[key], (compiler_args[key] if compiler_args else None)
+                if key == priority_model_key:
+                    try:
+                        results[key] = compile_wlo(ta, None, compiler_workdir, flags, key)
+                        continue
+                    except PlanError as e:
+                        logger.warning("bucket %s: launch plan not recordable (%s); compiled without the layout pass", key, e)
+                        ta._plan = None
+                results[key] = _compile(ta, None, compiler_workdir, flags, key)
             if priority_model_key:
                 results[ModelBuilderConstants.LAYOUT_TRANSFORMER_KEY] = compile_layout_transformer(results[priority_model_key])
         except Exception as e:  # noqa: BLE001

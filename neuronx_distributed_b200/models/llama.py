@@ -25,7 +25,7 @@ from ..modules.qkv_linear import GQAQKVColumnParallelLinear
 from ..modules.rms_norm import RMSNorm
 from ..parallel_layers import parallel_state as ps
 from ..parallel_layers.layers import ColumnParallelLinear, ParallelEmbedding, RowParallelLinear
-from ..parallel_layers.loss_functions import parallel_cross_entropy
+from ..parallel_layers.loss_functions import fused_linear_cross_entropy, parallel_cross_entropy
 
 
 @dataclass
@@ -155,6 +155,10 @@ class LlamaAttention(nn.Module):
 # tests/test_kernels_gpu.py::test_fused_add_rmsnorm_vs_fp32_reference, measured +0.8 % on the TP=1 step with the
 # post-attention norm alone).  NXD_FUSED_ADD_NORM=0 restores the separate add + norm kernels.
 _FUSED_ADD_NORM = os.environ.get("NXD_FUSED_ADD_NORM", "1") == "1"
+# lm_head + vocab-parallel CE in row chunks without materialising the logits (parallel_layers/loss_functions.py
+# ``fused_linear_cross_entropy``).  Opt-in: CPU-verified against the unfused path, not yet timed on hardware.
+_FUSED_LMHEAD_CE = os.environ.get("NXD_FUSED_LMHEAD_CE", "0") == "1"
+_LMHEAD_CE_CHUNK = int(os.environ.get("NXD_LMHEAD_CE_CHUNK", "2048"))
 
 
 class LlamaDecoderLayer(nn.Module):
@@ -265,13 +269,18 @@ class LlamaForCausalLM(nn.Module):
         """Returns ``(loss, logits)``; ``logits`` are vocab-parallel ``[S, B, V/tp]`` and are only
         returned when ``labels`` is None (so training never holds two copies)."""
         h = self.model(input_ids)
-        logits = self.lm_head(h)  # [S, B, V/tp]
         if labels is None:
-            return None, logits
+            return None, self.lm_head(h)  # [S, B, V/tp]
         # next-token objective: position s predicts labels[s+1]
         tgt = labels.transpose(0, 1)  # [S, B]
         if shift_labels:
             tgt = torch.cat([tgt[1:], torch.full_like(tgt[:1], -100)], dim=0)
+        if _FUSED_LMHEAD_CE:
+            # lm_head GEMM, CE statistics, CE gradient, dgrad and wgrad per row chunk: the [S·B, V/tp] logits never exist
+            loss = fused_linear_cross_entropy(h, self.lm_head.weight, tgt, sequence_parallel=self.config.sequence_parallel_enabled,
+                                              chunk_rows=_LMHEAD_CE_CHUNK)
+            return loss, None
+        logits = self.lm_head(h)  # [S, B, V/tp]
         mask = tgt != -100
         safe_tgt = torch.where(mask, tgt, torch.zeros_like(tgt))
         per_tok = parallel_cross_entropy(logits, safe_tgt)

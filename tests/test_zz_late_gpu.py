@@ -1,0 +1,52 @@
+"""GPU checks for code written AFTER the round's GPU budget was spent: none of these has run on hardware yet.  Each check runs
+in its own process with a timeout (a hang or a CUDA fault cannot take the rest of the suite down) and is marked
+``xfail(strict=False)``: the round-end run records XPASS (works on a B200) or XFAIL (does not) without hiding either.  The
+paths they exercise are opt-in (environment flags / explicit API calls), not defaults of the training or serving step."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="written after the GPU budget of the round was spent; "
+                                                 "first execution on hardware is this run")]
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(code: str, timeout: int = 300, env=None) -> None:
+    e = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    e.update(env or {})
+    p = subprocess.run([sys.executable, "-c", textwrap.dedent(code)], cwd=ROOT, env=e, timeout=timeout,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout[-4000:]
+
+
+def test_fused_lmhead_ce_on_device():
+    """bf16 chunked lm_head + CE on the tcgen05 GEMM / ce kernels vs an fp32 PyTorch reference of the same op."""
+    _run("""
+        import torch, torch.distributed as dist
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29631", rank=0, world_size=1)
+        torch.cuda.set_device(0)
+        from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+        from neuronx_distributed_b200.parallel_layers.loss_functions import fused_linear_cross_entropy
+        from neuronx_distributed_b200.ops import _ext
+        ps.initialize_model_parallel(1)
+        T, H, V = 4096, 1024, 8192
+        g = torch.Generator(device="cuda").manual_seed(0)
+        h = (torch.randn(T, 1, H, device="cuda", generator=g)).bfloat16().requires_grad_(True)
+        w = (torch.randn(V, H, device="cuda", generator=g) * 0.03).bfloat16().requires_grad_(True)
+        tgt = torch.randint(0, V, (T, 1), device="cuda", generator=g)
+        tgt[-7:] = -100
+        _ext.reset_launches()
+        loss = fused_linear_cross_entropy(h, w, tgt, chunk_rows=1024)
+        loss.backward()
+        assert _ext.launches() >= 4 * 5, _ext.launches()        # GEMM + stats + backward + dgrad + wgrad per chunk
+        hf, wf = h.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+        ref = torch.nn.functional.cross_entropy(hf.view(T, H) @ wf.t(), tgt.view(-1), ignore_index=-100)
+        ref.backward()
+        def rel(a, b): return ((a.float() - b).norm() / b.norm()).item()
+        print("loss", loss.item(), ref.item(), "dH", rel(h.grad, hf.grad), "dW", rel(w.grad, wf.grad))
+        assert abs(loss.item() - ref.item()) < 2e-2 and rel(h.grad, hf.grad) < 2e-2 and rel(w.grad, wf.grad) < 2e-2
+    """)
