@@ -259,6 +259,31 @@ static Tensor decode_attention(const Tensor& q, const Tensor& k, const Tensor& v
                         out.stride(0), out.stride(2), (float)scale, splits, stream());
   return out;
 }
+// This rank's contribution to distributed flash-decoding: un-normalised output (relative to the row maximum) [B,H,128] fp32 and
+// (row maximum in natural-log units, row sum) [B,H,2] fp32 over the local cache shard; ``positions`` are LOCAL (may be < 0 or
+// >= L: nothing / everything of this shard is visible).
+static std::vector<Tensor> decode_attention_partial(const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& positions,
+                                                    double scale) {
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && q.dim() == 4 && q.size(1) == 1 && q.size(3) == 128 && q.stride(3) == 1);
+  TORCH_CHECK(k.scalar_type() == at::kBFloat16 && k.dim() == 4 && k.size(3) == 128 && k.stride(3) == 1 && v.stride(3) == 1 &&
+              v.sizes() == k.sizes());
+  TORCH_CHECK(positions.scalar_type() == at::kLong && positions.is_cuda() && positions.is_contiguous() && positions.numel() == q.size(0));
+  const int B = q.size(0), H = q.size(2), L = k.size(1), Hkv = k.size(2);
+  TORCH_CHECK(H % Hkv == 0 && k.size(0) == B);
+  TORCH_CHECK(q.stride(2) % 8 == 0 && k.stride(1) % 8 == 0 && k.stride(2) % 8 == 0 && v.stride(1) % 8 == 0 && v.stride(2) % 8 == 0);
+  c10::cuda::CUDAGuard guard(q.device());
+  int splits = (6 * 148 + B * Hkv - 1) / (B * Hkv);
+  splits = std::max(1, std::min(std::min(splits, 64), (L + 63) / 64));
+  Tensor fin_o = at::empty({B, H, 128}, q.options().dtype(at::kFloat));
+  Tensor fin_ml = at::empty({B, H, 2}, q.options().dtype(at::kFloat));
+  Tensor part_o = at::empty({B * H * splits, 128}, q.options().dtype(at::kFloat));
+  Tensor part_ml = at::empty({B * H * splits, 2}, q.options().dtype(at::kFloat));
+  const long ks[3] = {k.stride(0), k.stride(1), k.stride(2)}, vs[3] = {v.stride(0), v.stride(1), v.stride(2)};
+  nxd::decode_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), positions.data_ptr<long>(), nullptr, part_o.data_ptr<float>(),
+                        part_ml.data_ptr<float>(), B, H, Hkv, L, ks, vs, q.stride(0), q.stride(2), 0, 0, (float)scale, splits,
+                        stream(), fin_o.data_ptr<float>(), fin_ml.data_ptr<float>());
+  return {fin_o, fin_ml};
+}
 static Tensor gemv(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& residual) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && x.dim() == 2 && w.dim() == 2);
   TORCH_CHECK(x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1) && x.size(0) >= 1 && x.size(0) <= 8 && x.size(1) % 8 == 0);
@@ -601,6 +626,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16_2cta", &gemm_bf16_2cta);
   m.def("oneshot_allreduce", &oneshot_allreduce);
   m.def("decode_attention", &decode_attention);
+  m.def("decode_attention_partial", &decode_attention_partial);
   m.def("decode_rope_kv", &decode_rope_kv);
   m.def("moe_block_metadata", &moe_block_metadata);
   m.def("row_argmax", &row_argmax);

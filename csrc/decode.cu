@@ -135,6 +135,25 @@ __global__ void __launch_bounds__(HD) decode_combine_kernel(const float* __restr
   out[b * o_sb + h * o_sh + d] = __float2bfloat16_rn(ls > 0.f ? acc / ls : 0.f);
 }
 
+// Same merge over the splits, but the result stays un-normalised: o (relative to the row maximum), the maximum (natural-log
+// units) and the row sum — what a rank contributes to distributed flash-decoding, where the final normalisation happens after
+// the cross-rank log-sum-exp merge (modules/attention/flash_decode.py).
+__global__ void __launch_bounds__(HD) decode_combine_partial_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
+                                                                    float* __restrict__ fin_o, float* __restrict__ fin_ml, int splits) {
+  const int bh = blockIdx.x, d = threadIdx.x;
+  float mn = -INFINITY;
+  for (int s = 0; s < splits; ++s) mn = fmaxf(mn, part_ml[((long)bh * splits + s) * 2]);
+  float acc = 0.f, ls = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const long idx = (long)bh * splits + s;
+    const float c = mn == -INFINITY ? 0.f : exp2f(part_ml[idx * 2] - mn);
+    acc += part_o[idx * HD + d] * c;
+    ls += part_ml[idx * 2 + 1] * c;
+  }
+  fin_o[(long)bh * HD + d] = acc;
+  if (d == 0) { fin_ml[bh * 2] = mn * 0.6931471805599453f; fin_ml[bh * 2 + 1] = ls; }
+}
+
 // y[m, n] = Σ_k x[m, k] · W[n, k]; one warp per output column n (8 columns per 256-thread CTA), M ≤ 8 rows of x kept hot in L1.
 template <int M>
 __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
@@ -230,7 +249,7 @@ void decode_rope_kv(const void* q, const void* k, const void* v, const long* pos
 
 void decode_attention(const void* q, const void* k, const void* v, const long* positions, void* out, float* part_o,
                       float* part_ml, int B, int H, int Hkv, int L, const long* ks, const long* vs, long q_sb, long q_sh,
-                      long o_sb, long o_sh, float scale, int splits, cudaStream_t st) {
+                      long o_sb, long o_sh, float scale, int splits, cudaStream_t st, float* fin_o, float* fin_ml) {
   const int G = H / Hkv;
   dim3 grid(Hkv, B, splits);
   const float sl2 = scale * 1.4426950408889634f;
@@ -246,7 +265,8 @@ void decode_attention(const void* q, const void* k, const void* v, const long* p
     default: nxd_throw("decode_attention: unsupported GQA group size", __FILE__, __LINE__);
   }
 #undef NXD_DEC
-  decode_combine_kernel<<<B * H, HD, 0, st>>>(part_o, part_ml, (__nv_bfloat16*)out, splits, o_sb, o_sh, H);
+  if (fin_o != nullptr) decode_combine_partial_kernel<<<B * H, HD, 0, st>>>(part_o, part_ml, fin_o, fin_ml, splits);
+  else decode_combine_kernel<<<B * H, HD, 0, st>>>(part_o, part_ml, (__nv_bfloat16*)out, splits, o_sb, o_sh, H);
   NXD_CUDA_CHECK(cudaGetLastError());
 }
 

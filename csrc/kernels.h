@@ -112,7 +112,8 @@ void moe_block_metadata(const void* expert_index, bool idx64, long n, int k, int
 // ---- decode (decode.cu)
 void decode_attention(const void* q, const void* k, const void* v, const long* positions, void* out, float* part_o,
                       float* part_ml, int B, int H, int Hkv, int L, const long* ks, const long* vs, long q_sb, long q_sh,
-                      long o_sb, long o_sh, float scale, int splits, cudaStream_t st);
+                      long o_sb, long o_sh, float scale, int splits, cudaStream_t st, float* fin_o = nullptr,
+                      float* fin_ml = nullptr);   // fin_o/fin_ml: un-normalised [B*H,128] + (max, sum) [B*H,2] instead of ``out``
 void decode_rope_kv(const void* q, const void* k, const void* v, const long* positions, const float* cos_t, const float* sin_t,
                     void* q_out, void* kc, void* vc, int B, int H, int Hkv, int D, int L, long q_sb, long q_sh, long k_sb, long k_sh,
                     long v_sb, long v_sh, long c_sb, long c_ss, long c_sh, cudaStream_t st);

@@ -36,53 +36,58 @@ def write_decode_sharded(k_cache: torch.Tensor, v_cache: torch.Tensor, k_new: to
     v_cache[b, off] = keep * v_new[:, 0] + (1 - keep) * v_cache[b, off]
 
 
-def flash_decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, positions: torch.Tensor,
-                           group, scale: Optional[float] = None) -> torch.Tensor:
-    """q ``[B, 1, H_local, D]`` (this rank's query heads), caches ``[B, L_local, Hkv, D]`` (this rank's sequence shard of the
-    shared KV heads), ``positions`` ``[B]`` = index of the newest token (attend to ≤ position).  Returns ``[B, 1, H_local, D]``."""
-    n = dist.get_world_size(group)
-    r = dist.get_rank(group)
-    B, _, Hl, D = q.shape
+def _local_partial(q_all: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, local_pos: torch.Tensor, scale: float):
+    """Partial attention of ``q_all [B, 1, H, D]`` over this rank's cache shard, cache index ≤ ``local_pos[b]`` visible
+    (``local_pos`` may be negative: nothing visible yet).  Returns un-normalised ``o [B, H, D]`` relative to the row maximum
+    ``m [B, H]`` (natural-log units, −inf when nothing is visible) and the row sum ``l [B, H]``, all fp32.
+
+    CUDA / bf16 / head_dim 128: the split-KV decode kernel (``csrc/decode.cu`` ``decode_attn_kernel`` + the partial combine):
+    K/V are read once per KV head for the whole GQA group.  Otherwise fp32 torch math."""
+    from ...ops import _ext
+
+    B, _, H, D = q_all.shape
     l_local, Hkv = k_cache.shape[1], k_cache.shape[2]
-    scale = scale if scale is not None else 1.0 / math.sqrt(D)
-    # 1. every rank needs the queries of the whole group
-    if n > 1:
-        parts = [torch.empty_like(q) for _ in range(n)]
-        dist.all_gather(parts, q.contiguous(), group=group)
-        q_all = torch.cat(parts, dim=2)                                  # [B, 1, n·Hl, D]
-    else:
-        q_all = q
-    H = q_all.shape[2]
-    # 2. partial attention over the local shard (fp32), masked to the positions this rank owns that are ≤ position
+    if (_ext.use_cuda(q_all, k_cache, v_cache) and q_all.dtype == torch.bfloat16 and k_cache.dtype == torch.bfloat16 and D == 128
+            and H % Hkv == 0 and (H // Hkv) in (1, 2, 4, 8) and hasattr(_ext.ext(), "decode_attention_partial")):
+        _ext.count_launch(2)
+        o, ml = _ext.ext().decode_attention_partial(q_all.contiguous(), k_cache, v_cache, local_pos.to(torch.long).contiguous(),
+                                                    float(scale))
+        return o, ml[..., 0], ml[..., 1]
     g = H // Hkv
     kf = k_cache.float().repeat_interleave(g, dim=2)                    # [B, L_local, H, D]
     vf = v_cache.float().repeat_interleave(g, dim=2)
     s = torch.einsum("bhd,blhd->bhl", q_all[:, 0].float(), kf) * scale  # [B, H, L_local]
-    gpos = r * l_local + torch.arange(l_local, device=q.device)
-    valid = gpos[None, :] <= positions[:, None]                         # [B, L_local]
+    valid = torch.arange(l_local, device=q_all.device)[None, :] <= local_pos[:, None]          # [B, L_local]
     s = s.masked_fill(~valid[:, None, :], float("-inf"))
     m = s.max(dim=-1).values                                            # [B, H]  (−inf if this shard has nothing yet)
     p = torch.exp(s - torch.where(torch.isinf(m), torch.zeros_like(m), m).unsqueeze(-1))
     p = torch.where(valid[:, None, :], p, torch.zeros_like(p))
-    l = p.sum(-1)                                                       # [B, H]
-    o = torch.einsum("bhl,blhd->bhd", p, vf)                            # un-normalised [B, H, D]
+    return torch.einsum("bhl,blhd->bhd", p, vf), m, p.sum(-1)
+
+
+def flash_decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, positions: torch.Tensor,
+                           group, scale: Optional[float] = None) -> torch.Tensor:
+    """q ``[B, 1, H_local, D]`` (this rank's query heads), caches ``[B, L_local, Hkv, D]`` (this rank's sequence shard of the
+    shared KV heads), ``positions`` ``[B]`` = index of the newest token (attend to ≤ position).  Returns ``[B, 1, H_local, D]``.
+    Collectives go through ``parallel_layers.comm`` (NCCL / gloo; recordable in launch plans)."""
+    from ...parallel_layers import comm
+
+    n = dist.get_world_size(group)
+    r = dist.get_rank(group)
+    B, _, Hl, D = q.shape
+    l_local = k_cache.shape[1]
+    scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    # 1. every rank needs the queries of the whole group
+    q_all = comm.all_gather(q.contiguous(), dim=2, group=group) if n > 1 else q          # [B, 1, n·Hl, D]
+    # 2. partial attention over the local shard: global position p is local index p − r·L_local
+    o, m, l = _local_partial(q_all, k_cache, v_cache, positions - r * l_local, scale)
     # 3. combine across the group
     if n > 1:
-        m_glob = m.clone()
-        dist.all_reduce(m_glob, op=dist.ReduceOp.MAX, group=group)
+        m_glob = comm.all_reduce(m.clone(), op="max", group=group)
         w = torch.where(torch.isinf(m), torch.zeros_like(m), torch.exp(m - m_glob))
-        o, l = o * w.unsqueeze(-1), l * w
-        o_parts = list(o.view(B, n, Hl, D).unbind(1))
-        l_parts = list(l.view(B, n, Hl).unbind(1))
-        o_mine, l_mine = torch.empty_like(o_parts[0]), torch.empty_like(l_parts[0])
-        if dist.get_backend(group) == "gloo":                           # gloo has no reduce_scatter
-            o_sum, l_sum = o.clone(), l.clone()
-            dist.all_reduce(o_sum, group=group)
-            dist.all_reduce(l_sum, group=group)
-            o_mine, l_mine = o_sum.view(B, n, Hl, D)[:, r], l_sum.view(B, n, Hl)[:, r]
-        else:
-            dist.reduce_scatter(o_mine, [t.contiguous() for t in o_parts], group=group)
-            dist.reduce_scatter(l_mine, [t.contiguous() for t in l_parts], group=group)
+        ol = torch.cat([o * w.unsqueeze(-1), (l * w).unsqueeze(-1)], dim=-1)             # [B, n·Hl, D+1]: ONE reduce-scatter
+        mine = comm.reduce_scatter(ol, dim=1, group=group)                               # [B, Hl, D+1]
+        o_mine, l_mine = mine[..., :D], mine[..., D]
     else:
         o_mine, l_mine = o, l
     return (o_mine / l_mine.clamp(min=1e-30).unsqueeze(-1)).to(q.dtype).unsqueeze(1)

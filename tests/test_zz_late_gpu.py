@@ -50,3 +50,33 @@ def test_fused_lmhead_ce_on_device():
         print("loss", loss.item(), ref.item(), "dH", rel(h.grad, hf.grad), "dW", rel(w.grad, wf.grad))
         assert abs(loss.item() - ref.item()) < 2e-2 and rel(h.grad, hf.grad) < 2e-2 and rel(w.grad, wf.grad) < 2e-2
     """)
+
+
+def test_decode_attention_partial_shards_merge_to_full_attention():
+    """``decode_attention_partial`` (per-rank piece of distributed flash-decoding) on two sequence shards of one cache, merged
+    with the log-sum-exp rule, vs fp32 attention over the whole cache — including a shard with nothing visible yet."""
+    _run("""
+        import math, torch
+        from neuronx_distributed_b200.modules.attention.flash_decode import _local_partial
+        torch.manual_seed(0)
+        B, H, Hkv, D, L = 3, 8, 2, 128, 512
+        q = torch.randn(B, 1, H, D, device="cuda").bfloat16()
+        k = torch.randn(B, L, Hkv, D, device="cuda").bfloat16()
+        v = torch.randn(B, L, Hkv, D, device="cuda").bfloat16()
+        pos = torch.tensor([40, 300, 511], device="cuda")            # row 0: the second shard has nothing visible
+        scale = 1 / math.sqrt(D)
+        parts = []
+        for r in range(2):
+            sl = slice(r * 256, (r + 1) * 256)
+            parts.append(_local_partial(q, k[:, sl], v[:, sl], pos - r * 256, scale))
+        m = torch.maximum(parts[0][1], parts[1][1])
+        w = [torch.where(torch.isinf(p[1]), torch.zeros_like(m), torch.exp(p[1] - m)) for p in parts]
+        o = sum(p[0] * wi.unsqueeze(-1) for p, wi in zip(parts, w)) / sum(p[2] * wi for p, wi in zip(parts, w)).unsqueeze(-1)
+        kf, vf = k.float().repeat_interleave(H // Hkv, 2), v.float().repeat_interleave(H // Hkv, 2)
+        s = torch.einsum("bhd,blhd->bhl", q[:, 0].float(), kf) * scale
+        s = s.masked_fill(torch.arange(L, device="cuda")[None, None, :] > pos[:, None, None], float("-inf"))
+        ref = torch.einsum("bhl,blhd->bhd", s.softmax(-1), vf)
+        err = ((o - ref).norm() / ref.norm()).item()
+        print("rel err", err, "m[0] shard1", parts[1][1][0, 0].item())
+        assert err < 5e-3 and torch.isinf(parts[1][1][0]).all() and (parts[1][2][0] == 0).all()
+    """)
