@@ -30,8 +30,10 @@ def __getattr__(name):
     if name in ckpt:
         mod = importlib.import_module(".trainer.checkpoint", __name__)
         return getattr(mod, name)
-    inf = {"ModelBuilder", "NxDModel", "BaseNxDModel", "shard_checkpoint", "NxDParallelState"}
+    # reference __init__.py:14-19: the v2 builder, the functional shard_checkpoint, the runtime model classes
+    inf = {"ModelBuilder": ".trace.model_builder_v2", "shard_checkpoint": ".trace.functions", "NxDModel": ".trace.nxd_model",
+           "BaseNxDModel": ".trace.nxd_model", "TorchScriptNxDModel": ".trace.nxd_model",
+           "convert_nxd_model_to_torchscript_model": ".trace.nxd_model", "NxDParallelState": ".trace.parallel_context"}
     if name in inf:
-        mod = importlib.import_module(".inference", __name__)
-        return getattr(mod, name)
+        return getattr(importlib.import_module(inf[name], __name__), name)
     raise AttributeError(name)

@@ -219,6 +219,7 @@ class ConstInfo:
     dtype: str
     named: bool                     # a module parameter / buffer (survives under its own name) vs an anonymous capture
     device_type: str = ""           # where the recorded tensor lived ("" = the plan's device type)
+    in_checkpoint: bool = True      # a key of the module's ``state_dict`` (non-persistent buffers and captures are not)
 
 
 def _resolve_op(target: str) -> Callable:
@@ -440,7 +441,7 @@ class LaunchPlan:
         m_consts = {i: c for i, c in self.constants.items() if i in needed}
         for v in derived:
             shp, dt = shapes.get(str(v), ((), "float32"))
-            m_consts[v] = ConstInfo(f"_derived_{v}", tuple(shp), dt, named=False)
+            m_consts[v] = ConstInfo(f"_derived_{v}", tuple(shp), dt, named=False, in_checkpoint=False)
         main = LaunchPlan(rest, list(self.inputs), self.outputs, m_consts, self.device_type,
                           dict(self.meta, derived_ids=derived))
         tmap: Dict[str, List[str]] = {}
@@ -485,14 +486,16 @@ class LaunchPlan:
     def to_json(self) -> Dict[str, Any]:
         return {"format": self.FORMAT, "device_type": self.device_type, "meta": self.meta,
                 "inputs": self.inputs, "outputs": self.outputs,
-                "constants": {str(i): [c.name, list(c.shape), c.dtype, c.named, c.device_type] for i, c in self.constants.items()},
+                "constants": {str(i): [c.name, list(c.shape), c.dtype, c.named, c.device_type, c.in_checkpoint]
+                              for i, c in self.constants.items()},
                 "nodes": [n.to_json() for n in self.nodes]}
 
     @staticmethod
     def from_json(d: Dict[str, Any]) -> "LaunchPlan":
         if d.get("format") != LaunchPlan.FORMAT:
             raise PlanError(f"launch plan format {d.get('format')} is not supported (expected {LaunchPlan.FORMAT})")
-        consts = {int(i): ConstInfo(v[0], tuple(v[1]), v[2], bool(v[3]), v[4] if len(v) > 4 else "") for i, v in d["constants"].items()}
+        consts = {int(i): ConstInfo(v[0], tuple(v[1]), v[2], bool(v[3]), v[4] if len(v) > 4 else "",
+                                   bool(v[5]) if len(v) > 5 else bool(v[3])) for i, v in d["constants"].items()}
         return LaunchPlan([Node.from_json(n) for n in d["nodes"]], d["inputs"], d["outputs"], consts, d["device_type"], d.get("meta"))
 
     def save(self, path: str) -> None:
@@ -532,9 +535,10 @@ class _ExtProxy:
 
 
 class _Recorder(TorchDispatchMode):
-    def __init__(self, names: Dict[int, str], by_mem: Dict[Tuple, str]):
+    def __init__(self, names: Dict[int, str], by_mem: Dict[Tuple, str], checkpoint_keys: Optional[Set[str]] = None):
         super().__init__()
         self.names, self.mem_names = names, by_mem
+        self.checkpoint_keys = checkpoint_keys
         self.nodes: List[Node] = []
         self.by_pyid: Dict[int, int] = {}
         self.by_mem: Dict[Tuple, int] = {}
@@ -579,7 +583,8 @@ class _Recorder(TorchDispatchMode):
         named = name is not None
         if name is None:
             name = f"_const_{vid}"
-        self.constants[vid] = (ConstInfo(name, tuple(t.shape), str(t.dtype).split(".", 1)[1], named, t.device.type), t)
+        in_ckpt = named and (self.checkpoint_keys is None or name in self.checkpoint_keys)
+        self.constants[vid] = (ConstInfo(name, tuple(t.shape), str(t.dtype).split(".", 1)[1], named, t.device.type, in_ckpt), t)
         if key[0]:
             self.by_mem[key] = vid
         return vid
@@ -702,7 +707,8 @@ def record(model: Callable, example_inputs: Sequence[torch.Tensor], input_names:
         raise PlanError("a recording is already active")
     names = list(input_names) if input_names is not None else [f"arg{i}" for i in range(len(example_inputs))]
     ids, mem, _ = _named_tensors(model)
-    rec = _Recorder(ids, mem)
+    ckpt_keys = set(model.state_dict().keys()) if isinstance(model, torch.nn.Module) else None
+    rec = _Recorder(ids, mem, ckpt_keys)
     inputs = [{"id": rec.bind_input(t), "name": n, "shape": list(t.shape), "dtype": str(t.dtype).split(".", 1)[1]}
               for n, t in zip(names, example_inputs)]
     real = _ext._load()
@@ -744,7 +750,8 @@ def save_plans(path: str, plans: Dict[str, LaunchPlan], rank: int = 0, extra: Op
     """``<path>/plans_rank<r>.json`` (all buckets) + ``<path>/constants_rank<r>.safetensors`` (one copy of every named
     constant — buckets share them — and each bucket's anonymous captures under ``<key>::<name>``).  Derived constants
     (outputs of a layout transformer) are not stored: they are recomputed at load.  ``save_weights=False`` leaves out the
-    named constants that no bucket writes to (the checkpoint weights: supply them with ``set_weights`` after loading)."""
+    ``state_dict`` entries that no bucket writes to (the checkpoint weights: supply them with ``set_weights`` after loading);
+    non-persistent buffers and captured tables are always stored."""
     from ..utils.safetensors_utils import save_state_dict_safetensors
 
     os.makedirs(path, exist_ok=True)
@@ -757,7 +764,7 @@ def save_plans(path: str, plans: Dict[str, LaunchPlan], rank: int = 0, extra: Op
         for vid, c in plan.constants.items():
             if vid in derived and c.name.startswith("_derived_"):
                 continue
-            if not save_weights and c.named and c.name not in state:
+            if not save_weights and c.named and c.in_checkpoint and c.name not in state:
                 continue
             if vid not in plan.tensors:
                 raise PlanError(f"bucket {key}: constant {c.name} has no tensor to save")

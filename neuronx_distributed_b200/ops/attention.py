@@ -117,3 +117,23 @@ def flash_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: b
     if _own_kernel_ok(q, k, v) and (not causal or q.shape[1] == k.shape[1]):
         return _FlashAttn.apply(q, k, v, causal, scale)
     return _sdpa(q, k, v, causal, scale)
+
+
+def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, positions: torch.Tensor,
+                     scale: Optional[float] = None) -> torch.Tensor:
+    """One new token per sequence against a KV cache: ``q [B,1,H,D]``, caches ``[B,L,Hkv,D]`` (any batch / sequence / head
+    strides), ``positions [B]`` = cache index of the newest token (keys ≤ position are visible).  CUDA bf16 with head_dim 128:
+    the split-KV flash-decoding kernel (``csrc/decode.cu``); otherwise SDPA with a length mask."""
+    B, _, H, D = q.shape
+    Hkv, L = k_cache.shape[2], k_cache.shape[1]
+    scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    e = _ext.ext() if q.is_cuda else None
+    if (e is not None and hasattr(e, "decode_attention") and D == 128 and q.dtype == torch.bfloat16 and k_cache.dtype == torch.bfloat16
+            and H // Hkv in (1, 2, 4, 8) and k_cache.stride(3) == 1 and v_cache.stride(3) == 1):
+        _ext.count_launch(2)
+        return e.decode_attention(q.contiguous(), k_cache, v_cache, positions.to(torch.long).contiguous(), float(scale))
+    qt, kt, vt = q.transpose(1, 2), k_cache.transpose(1, 2), v_cache.transpose(1, 2)
+    if H != Hkv:
+        kt, vt = kt.repeat_interleave(H // Hkv, 1), vt.repeat_interleave(H // Hkv, 1)
+    mask = (torch.arange(L, device=q.device)[None, :] <= positions[:, None])[:, None, None, :]
+    return torch.nn.functional.scaled_dot_product_attention(qt, kt, vt, attn_mask=mask, scale=scale).transpose(1, 2)

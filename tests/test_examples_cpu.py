@@ -1,0 +1,38 @@
+"""The standalone inference sample (``examples/inference/llama``) end to end on CPU: eager baseline, offline sharding, artefact
+build on 2 gloo ranks, and the three ways of serving it — all must print the same generations."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RUN = os.path.join(ROOT, "examples", "inference", "llama", "run.py")
+COMMON = ["--prompts", "Hello", "abc", "--max-new-tokens", "6"]
+
+
+def _py(args, port=None, nproc=1):
+    env = dict(os.environ, PYTHONPATH=ROOT, MASTER_PORT=str(port or 29700), NXD_LOG_LEVEL="WARNING")
+    if nproc > 1:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+               "--master-port", str(port), RUN] + args
+    else:
+        cmd = [sys.executable, RUN] + args
+    p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:]
+    return [ln for ln in p.stdout.splitlines() if ln.startswith(("'", '"'))]
+
+
+def test_llama_sample_all_flows_agree(tmp_path):
+    tiny = ["--tiny", "--seq-len", "32"]
+    want = _py(["generate_cpu"] + tiny + COMMON)
+    assert len(want) == 2 and want[0].startswith("'Hello")
+    sharded, art, art_nw = str(tmp_path / "sharded"), str(tmp_path / "art"), str(tmp_path / "art_nw")
+    _py(["shard"] + tiny + ["--tp-degree", "2", "--output-path", sharded])
+    assert sorted(os.listdir(sharded)) == ["tp0_sharded_checkpoint.safetensors", "tp1_sharded_checkpoint.safetensors"]
+    _py(["compile"] + tiny + ["--output-path", art], port=29711, nproc=2)
+    _py(["compile"] + tiny + ["--output-path", art_nw, "--no-save-weights"], port=29712, nproc=2)
+    assert {"plans_rank0.json", "plans_rank1.json", "constants_rank0.safetensors", "constants_rank1.safetensors"} <= set(os.listdir(art))
+    assert os.path.getsize(os.path.join(art_nw, "constants_rank0.safetensors")) < os.path.getsize(os.path.join(art, "constants_rank0.safetensors"))
+    assert _py(["generate", "--compiled-model-path", art] + COMMON, port=29713, nproc=2) == want
+    assert _py(["generate", "--compiled-model-path", art_nw, "--sharded-dir", sharded] + COMMON, port=29714, nproc=2) == want
+    assert _py(["generate", "--compiled-model-path", art_nw, "--shard-on-load"] + COMMON, port=29715, nproc=2) == want
+    _py(["test_attention"] + tiny, port=29716, nproc=2)
