@@ -284,6 +284,48 @@ static std::vector<Tensor> decode_attention_partial(const Tensor& q, const Tenso
                         stream(), fin_o.data_ptr<float>(), fin_ml.data_ptr<float>());
   return {fin_o, fin_ml};
 }
+// x [T,H] bf16; gamma [H] bf16 or none; router_w [E,H] bf16; router_bias [E] fp32 or none; w_gu [El,H,2I]; w_dn [El,I,H]
+// → (out [T,H] bf16 partial over this rank's experts / intermediate shard, router logits [T,E] fp32, top-k idx [T,K], top-k w [T,K])
+static std::vector<Tensor> moe_block_tkg(const Tensor& x, const c10::optional<Tensor>& gamma, const Tensor& router_w,
+                                         const c10::optional<Tensor>& router_bias, const Tensor& w_gu, const Tensor& w_dn,
+                                         int64_t e0, int64_t top_k, double eps, int64_t router_act, bool act_over_topk, bool normalize,
+                                         bool pre_scale, bool round_logits, int64_t act, double act_alpha, double act_beta,
+                                         double gate_lo, double gate_hi, double up_lo, double up_hi, bool cooperative) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.is_contiguous());
+  TORCH_CHECK(router_w.scalar_type() == at::kBFloat16 && router_w.dim() == 2 && router_w.is_contiguous() && router_w.size(1) == x.size(1));
+  TORCH_CHECK(w_gu.scalar_type() == at::kBFloat16 && w_gu.dim() == 3 && w_gu.is_contiguous() && w_gu.size(1) == x.size(1) &&
+              w_gu.size(2) % 2 == 0);
+  TORCH_CHECK(w_dn.scalar_type() == at::kBFloat16 && w_dn.dim() == 3 && w_dn.is_contiguous() && w_dn.size(0) == w_gu.size(0) &&
+              w_dn.size(1) * 2 == w_gu.size(2) && w_dn.size(2) == x.size(1));
+  const int T = x.size(0), H = x.size(1), E = router_w.size(0), El = w_gu.size(0), I = w_dn.size(1), K = top_k;
+  TORCH_CHECK(nxd::moe_block_tkg_supported(T, H, E, I, K), "moe_block_tkg: unsupported shape");
+  TORCH_CHECK(e0 >= 0 && e0 + El <= E);
+  const void* g = nullptr;
+  if (gamma.has_value()) {
+    TORCH_CHECK(gamma->scalar_type() == at::kBFloat16 && gamma->is_contiguous() && gamma->numel() == H);
+    g = gamma->data_ptr();
+  }
+  const float* rb = nullptr;
+  if (router_bias.has_value()) {
+    TORCH_CHECK(router_bias->scalar_type() == at::kFloat && router_bias->is_contiguous() && router_bias->numel() == E);
+    rb = router_bias->data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard guard(x.device());
+  auto f32 = x.options().dtype(at::kFloat);
+  Tensor out = at::empty({T, H}, x.options());
+  Tensor logits = at::empty({T, E}, f32);
+  Tensor idx = at::empty({T, K}, x.options().dtype(at::kLong));
+  Tensor w = at::empty({T, K}, f32);
+  Tensor gu = at::empty({(long)T * K, 2L * I}, f32);
+  Tensor yacc = at::empty({T, H}, f32);
+  Tensor bar = at::empty({1}, x.options().dtype(at::kInt));
+  nxd::moe_block_tkg(x.data_ptr(), g, router_w.data_ptr(), rb, w_gu.data_ptr(), w_dn.data_ptr(), logits.data_ptr<float>(),
+                     gu.data_ptr<float>(), yacc.data_ptr<float>(), out.data_ptr(), idx.data_ptr<long>(), w.data_ptr<float>(),
+                     (unsigned*)bar.data_ptr<int>(), T, H, E, El, (int)e0, I, K, (float)eps, (int)router_act, act_over_topk, normalize,
+                     pre_scale, round_logits, (int)act, (float)act_alpha, (float)act_beta, (float)gate_lo, (float)gate_hi, (float)up_lo,
+                     (float)up_hi, cooperative, stream());
+  return {out, logits, idx, w};
+}
 static Tensor gemv(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& residual) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && x.dim() == 2 && w.dim() == 2);
   TORCH_CHECK(x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1) && x.size(0) >= 1 && x.size(0) <= 8 && x.size(1) % 8 == 0);
@@ -627,6 +669,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("oneshot_allreduce", &oneshot_allreduce);
   m.def("decode_attention", &decode_attention);
   m.def("decode_attention_partial", &decode_attention_partial);
+  m.def("moe_block_tkg", &moe_block_tkg);
+  m.def("moe_block_tkg_supported", [](int64_t T, int64_t H, int64_t E, int64_t I, int64_t K) {
+    return nxd::moe_block_tkg_supported((int)T, (int)H, (int)E, (int)I, (int)K);
+  });
   m.def("decode_rope_kv", &decode_rope_kv);
   m.def("moe_block_metadata", &moe_block_metadata);
   m.def("row_argmax", &row_argmax);

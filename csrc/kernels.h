@@ -109,6 +109,14 @@ void row_topk(const void* x, float* vals, long* idxs, int rows, int V, int k, lo
 void moe_block_metadata(const void* expert_index, bool idx64, long n, int k, int E, int B, int nb, long* block_to_expert, long* tp2id,
                         long* counts, cudaStream_t st);
 
+// ---- decode-time MoE block in one cooperative launch (moe_tkg.cu)
+bool moe_block_tkg_supported(int T, int H, int E, int I, int K);
+void moe_block_tkg(const void* x, const void* gamma, const void* router_w, const float* router_bias, const void* w_gu,
+                   const void* w_dn, float* logits, float* gu, float* yacc, void* out, long* topk_idx, float* topk_w,
+                   unsigned* barrier, int T, int H, int E, int El, int e0, int I, int K, float eps, int router_act,
+                   int act_over_topk, int normalize, int pre_scale, int round_logits, int act, float act_alpha, float act_beta,
+                   float gate_lo, float gate_hi, float up_lo, float up_hi, bool cooperative, cudaStream_t st);
+
 // ---- decode (decode.cu)
 void decode_attention(const void* q, const void* k, const void* v, const long* positions, void* out, float* part_o,
                       float* part_ml, int B, int H, int Hkv, int L, const long* ks, const long* vs, long q_sb, long q_sh,

@@ -32,7 +32,10 @@ class MoE(nn.Module):
         if init_tkg_module:
             from .moe_fused_tkg import MoEFusedTKG
 
-            self.moe_fused_tkg = MoEFusedTKG(router, expert_mlps, shared_experts, rmsnorm, tkg_config)
+            self.moe_fused_tkg = MoEFusedTKG(router, expert_mlps, shared_experts, rmsnorm, tkg_config,
+                                             sequence_dimension=self.sequence_dimension,
+                                             tensor_model_parallel_group=tensor_model_parallel_group,
+                                             return_router_logits=return_router_logits, return_expert_index=return_expert_index)
 
     def _shared(self, full: torch.Tensor, seq_len: int) -> torch.Tensor:
         try:

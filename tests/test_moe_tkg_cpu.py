@@ -1,0 +1,86 @@
+"""Decode MoE block: the kernel's numerics oracle (``ops.moe_tkg.moe_block_tkg_reference``) against the composed module path
+for the routing / activation variants the one-launch kernel implements, and the ``MoEFusedTKG`` wrapper contract."""
+import itertools
+
+import pytest
+import torch
+
+from dist_utils import run_distributed
+
+
+def _build(hidden_act="silu", glu_type="glu", router_act="softmax", over_topk=False, normalize=True, pre_scale=False, clamps=False,
+           E=8, k=2, H=32, inter=48, dtype=torch.float32):
+    from neuronx_distributed_b200.modules.moe.expert_mlps_v2 import ExpertMLPsV2
+    from neuronx_distributed_b200.modules.moe.moe_configs import RoutedExpertsMLPOpsConfig
+    from neuronx_distributed_b200.modules.moe.routing import RouterTopK
+    from neuronx_distributed_b200.modules.rms_norm import RMSNorm
+
+    kw = {}
+    if clamps:
+        kw = dict(gate_clamp_upper_limit=0.8, gate_clamp_lower_limit=-0.7, up_clamp_upper_limit=0.9, up_clamp_lower_limit=-0.6)
+    cfg = RoutedExpertsMLPOpsConfig(num_experts=E, top_k=k, hidden_size=H, intermediate_size=inter, hidden_act=hidden_act,
+                                    glu_mlp=True, glu_type=glu_type, capacity_factor=None, normalize_top_k_affinities=normalize,
+                                    early_expert_affinity_modulation=pre_scale, hidden_act_scaling_factor=1.702 if glu_type == "swiglu" else 1.0,
+                                    hidden_act_bias=1.0 if glu_type == "swiglu" else 0.0, **kw)
+    torch.manual_seed(0)
+    router = RouterTopK(E, k, H, dtype=dtype, act_fn=router_act, apply_act_fn_over_topk=over_topk, bias=True)
+    with torch.no_grad():
+        router.linear_router.bias.normal_(std=0.1)
+    experts = ExpertMLPsV2(cfg, dtype=dtype)
+    norm = RMSNorm(H, eps=1e-5)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+    return cfg, router, experts, norm
+
+
+def _worker(rank, world):
+    from neuronx_distributed_b200.modules.moe.moe_configs import MoEFusedTKGConfig
+    from neuronx_distributed_b200.modules.moe.moe_fused_tkg import MoEFusedTKG
+    from neuronx_distributed_b200.ops import moe_tkg
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    variants = [dict(), dict(router_act="sigmoid"), dict(over_topk=True), dict(over_topk=True, router_act="sigmoid", normalize=False),
+                dict(pre_scale=True), dict(glu_type="swiglu", hidden_act="sigmoid", clamps=True), dict(hidden_act="gelu"),
+                dict(hidden_act="gelu_new", normalize=False), dict(k=4, E=16)]
+    for v in variants:
+        cfg, router, experts, norm = _build(**v)
+        fused = MoEFusedTKG(router, experts, None, norm, return_router_logits=True, return_expert_index=True).eval()
+        x = torch.randn(1, 5, cfg.hidden_size)                                   # [S=1, B=5, H]: five decode tokens
+        with torch.no_grad():
+            want, want_logits, want_idx = fused(x)                               # composed path (CPU) incl. the TP all-reduce
+            op = experts.mlp_op
+            c = [cfg.gate_clamp_lower_limit, cfg.gate_clamp_upper_limit, cfg.up_clamp_lower_limit, cfg.up_clamp_upper_limit]
+            c = [(-float("inf") if i % 2 == 0 else float("inf")) if val is None else val for i, val in enumerate(c)]
+            out, logits, idx, w = moe_tkg.moe_block_tkg(
+                x.reshape(-1, cfg.hidden_size), norm.weight, router.linear_router.weight, router.linear_router.bias,
+                op.gate_up_proj.weight, op.down_proj.weight, int(op.local_expert_ids[0]), cfg.top_k, norm.variance_epsilon,
+                0 if router.act_fn == "softmax" else 1, router.apply_act_fn_over_topk, cfg.normalize_top_k_affinities,
+                cfg.early_expert_affinity_modulation, True, moe_tkg.act_id(cfg.hidden_act, cfg.glu_type),
+                cfg.hidden_act_scaling_factor, cfg.hidden_act_bias, tuple(c))
+            if world > 1:                                                        # the op returns this rank's partial sum
+                torch.distributed.all_reduce(out)
+        torch.testing.assert_close(logits, want_logits.float(), rtol=1e-5, atol=1e-5, msg=lambda m: f"{v}: {m}")
+        assert torch.equal(idx.sort(-1).values, want_idx.sort(-1).values), v
+        torch.testing.assert_close(out.view_as(want), want, rtol=2e-4, atol=2e-5, msg=lambda m: f"{v}: {m}")
+        assert w.shape == (5, cfg.top_k) and (not cfg.normalize_top_k_affinities or torch.allclose(w.sum(-1), torch.ones(5), atol=1e-5))
+    # wrapper contract: reference constructor order, residual stream, CPU → flat path with the reason recorded
+    cfg, router, experts, norm = _build()
+    f2 = MoEFusedTKG(router, experts, MoEFusedTKGConfig(), 0, None, post_attention_layernorm=norm).eval()
+    assert f2.post_attention_layernorm is norm and f2.router is router and f2.expert_mlps is experts and f2.shared_experts is None
+    x, res = torch.randn(1, 3, cfg.hidden_size), torch.randn(1, 3, cfg.hidden_size)
+    with torch.no_grad():
+        y, stream = f2(x, res)
+        y0, = f2(x + res)
+    torch.testing.assert_close(y, y0) and torch.testing.assert_close(stream, x + res)
+    assert f2._why_not == "cannot run on cpu" and not list(f2.parameters())      # holds references, owns nothing
+    f2.config.moe_fused_kernel_enabled = False
+    assert not f2._can_use_kernel(x) and "disabled" in f2._why_not
+
+
+def test_moe_block_tkg_reference_matches_composed_path_tp1():
+    run_distributed(_worker, 1)
+
+
+def test_moe_block_tkg_reference_matches_composed_path_tp2():
+    run_distributed(_worker, 2)

@@ -80,3 +80,54 @@ def test_decode_attention_partial_shards_merge_to_full_attention():
         print("rel err", err, "m[0] shard1", parts[1][1][0, 0].item())
         assert err < 5e-3 and torch.isinf(parts[1][1][0]).all() and (parts[1][2][0] == 0).all()
     """)
+
+
+def test_moe_block_tkg_kernel_matches_reference():
+    """The one-launch decode MoE block (``csrc/moe_tkg.cu``) vs its fp32 oracle for the routing / activation variants, with an
+    expert-parallel slice of local experts, 1 and 5 tokens."""
+    _run("""
+        import torch
+        from neuronx_distributed_b200.ops import moe_tkg, _ext
+        torch.manual_seed(0)
+        dev = "cuda"
+        def case(T, H, E, I, K, e0, El, **kw):
+            x = torch.randn(T, H, device=dev).bfloat16()
+            gamma = (torch.rand(H, device=dev) + 0.5).bfloat16()
+            rw = (torch.randn(E, H, device=dev) * 0.2).bfloat16()
+            rb = torch.randn(E, device=dev) * 0.1
+            wgu = (torch.randn(El, H, 2 * I, device=dev) * H ** -0.5).bfloat16()
+            wdn = (torch.randn(El, I, H, device=dev) * I ** -0.5).bfloat16()
+            args = (x, gamma, rw, rb, wgu, wdn, e0, K)
+            assert moe_tkg.kernel_eligible(x, rw, wgu, wdn, K)
+            n0 = _ext.launches()
+            out, logits, idx, w = moe_tkg.moe_block_tkg(*args, eps=1e-5, **kw)
+            assert _ext.launches() == n0 + 1
+            ro, rl, ri, rwt = moe_tkg.moe_block_tkg_reference(*args, eps=1e-5, **kw)
+            torch.cuda.synchronize()
+            assert torch.equal(idx.sort(-1).values, ri.sort(-1).values), (kw, idx, ri)
+            torch.testing.assert_close(logits, rl, rtol=0, atol=2e-2)
+            torch.testing.assert_close(w.sort(-1).values, rwt.sort(-1).values, rtol=0, atol=1e-2)
+            err = ((out.float() - ro.float()).norm() / ro.float().norm().clamp(min=1e-6)).item()
+            print(T, H, E, I, K, e0, El, kw, "rel err", err)
+            assert err < 2e-2, err
+        case(1, 1024, 8, 512, 2, 0, 8)
+        case(5, 2048, 16, 768, 4, 4, 8, router_act=1, normalize=False)
+        case(8, 1024, 64, 256, 8, 0, 64, act_over_topk=True)
+        case(3, 1024, 8, 512, 2, 0, 8, pre_scale=True, act=3, act_alpha=1.702, act_beta=1.0, clamps=(-0.7, 0.8, -0.6, 0.9))
+        case(2, 4096, 8, 1792, 2, 0, 8, act=2)
+        # twice in a row + under a CUDA graph (the barrier counter is reset by a memset node)
+        x = torch.randn(2, 1024, device=dev).bfloat16(); rw = torch.randn(8, 1024, device=dev).bfloat16() * 0.2
+        wgu = (torch.randn(8, 1024, 1024, device=dev) * 0.03).bfloat16(); wdn = (torch.randn(8, 512, 1024, device=dev) * 0.04).bfloat16()
+        ref = moe_tkg.moe_block_tkg_reference(x, None, rw, None, wgu, wdn, 0, 2)[0]
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                eager = moe_tkg.moe_block_tkg(x, None, rw, None, wgu, wdn, 0, 2)[0]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cap = moe_tkg.moe_block_tkg(x, None, rw, None, wgu, wdn, 0, 2)[0]
+            g.replay(); g.replay()
+        torch.cuda.synchronize()
+        for got in (eager, cap):
+            assert ((got.float() - ref.float()).norm() / ref.float().norm()).item() < 2e-2
+    """, timeout=420, env={"NXD_MOE_TKG_KERNEL": "1"})
