@@ -131,3 +131,48 @@ def test_moe_block_tkg_kernel_matches_reference():
         for got in (eager, cap):
             assert ((got.float() - ref.float()).norm() / ref.float().norm()).item() < 2e-2
     """, timeout=420, env={"NXD_MOE_TKG_KERNEL": "1"})
+
+
+def test_launch_plan_replays_extension_kernels_and_captures():
+    """A bf16 Llama decode + prefill bucket recorded on the GPU (dispatcher ops + ``nxd_b200_C`` kernels as ``ext`` nodes), saved,
+    loaded without the model object, re-captured into CUDA graphs: tokens must equal the module's."""
+    _run("""
+        import torch, torch.distributed as dist, tempfile
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29633", rank=0, world_size=1)
+        torch.cuda.set_device(0)
+        from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+        ps.initialize_model_parallel(1)
+        from neuronx_distributed_b200.models.llama import LlamaConfig
+        from neuronx_distributed_b200.models.llama_inference import LlamaForInference
+        from neuronx_distributed_b200.inference.functions import trace, compile as ncompile, compile_wlo
+        from neuronx_distributed_b200.inference.nxd_model import NxDModel
+        from torch import nn
+        class Wrap(nn.Module):
+            def __init__(s, m, which): super().__init__(); s.m, s.which = m, which
+            def forward(s, input_ids, aux):
+                return s.m.context_encoding(input_ids, aux) if s.which == "cte" else s.m.token_generation(input_ids, aux)
+        cfg = LlamaConfig(vocab_size=4096, hidden_size=1024, intermediate_size=2816, num_hidden_layers=2, num_attention_heads=8,
+                          num_key_value_heads=2, dtype=torch.bfloat16, device=torch.device("cuda"), max_position_embeddings=256)
+        torch.manual_seed(0)
+        m = LlamaForInference(cfg, batch_size=2, max_seq_len=256).eval()
+        ids = torch.randint(0, 4096, (2, 128), device="cuda"); last = torch.tensor([127, 90], device="cuda")
+        want = m.generate(ids, 6, prompt_lens=last + 1)
+        ta_c = trace(Wrap(m, "cte"), (ids, last))
+        ta_t = trace(Wrap(m, "tkg"), (torch.zeros(2, 1, dtype=torch.long, device="cuda"), torch.tensor([128, 91], device="cuda")))
+        nxd = NxDModel(world_size=1)
+        wlo = compile_wlo(ta_t, None, None, None, "tkg")
+        nxd.add("cte", ta_c, ncompile(ta_c, None, None, "--plan", "cte")).add("tkg", ta_t, wlo)
+        nxd.to_neuron()
+        print("tkg plan", wlo.plan.summary()); assert wlo.plan.calls_extension() and wlo.captured
+        def gen(model, n):
+            tok = model(ids, last, model_name="cte"); out, pos = [tok.clone()], last + 1
+            for _ in range(n - 1):
+                tok = model(tok.view(2, 1), pos, model_name="tkg"); out.append(tok.clone()); pos = pos + 1
+            return torch.stack(out, 1)
+        assert torch.equal(gen(nxd, 6), want), (gen(nxd, 6), want)
+        d = tempfile.mkdtemp()
+        nxd.save(d, save_weights=True, portable=True)
+        del nxd, wlo, ta_c, ta_t
+        loaded = NxDModel.load(d); loaded.to_neuron()
+        assert torch.equal(gen(loaded, 6), want)
+    """, timeout=420)
