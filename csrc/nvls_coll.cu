@@ -9,6 +9,8 @@
 // All three are CUDA-graph capturable: the call counter (epoch) lives in device memory and is advanced by the last CTA.
 // Region layout is chosen by the caller (ops/nvls.py): `flag_off` = kNvlsCollMaxCtas u32 barrier counters, payload
 // double-buffered by epoch parity.  With `mc_base == nullptr` the kernels use unicast peer accesses (same protocol).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -303,6 +305,54 @@ __global__ void __launch_bounds__(256) gemv_allreduce_kernel(const __nv_bfloat16
   finish_call(state, epoch);
 }
 
+// ---- vocab-parallel embedding lookup for a sequence-parallel consumer (SURVEY §7.4 `embedding_rs`) -------------------------
+// The reference looks every token up in the local vocab shard (zero rows for foreign ids), producing the full [S, B, H]
+// partial, and reduce-scatters it (layers.py:334-378): S·B·H elements written, masked and pushed through a collective although
+// every output row has exactly ONE non-zero contributor.  With NVSwitch peer memory the lookup itself can be remote:
+//   1. nvls_publish_kernel      every rank copies its table shard into its symmetric slot (parity by call) and meets the same CTA
+//                               of every other rank; when the kernel has finished on a rank, all shards are visible to it;
+//   2. peer_row_gather_kernel   one warp per token of THIS rank's sequence shard loads the row from the owner's slot over
+//                               NVLink (16-byte loads) and stores it locally.  No reduction, S/tp·B·H elements moved once.
+__global__ void __launch_bounds__(512) nvls_publish_kernel(const uint8_t* __restrict__ x, NvlsRegion r, uint32_t* __restrict__ state,
+                                                           long bytes) {
+  const uint32_t epoch = ld_acquire_sys(state) + 1u;
+  const long base = r.data_off + (long)(epoch & 1u) * r.half_bytes;
+  const long nvec = bytes / 16;
+  const long per_cta = (nvec + gridDim.x - 1) / gridDim.x;
+  const long v0 = (long)blockIdx.x * per_cta, v1 = min(nvec, v0 + per_cta);
+  uint4* mine = (uint4*)(r.local_base + base);
+  for (long v = v0 + threadIdx.x; v < v1; v += blockDim.x) mine[v] = ((const uint4*)x)[v];
+  __threadfence_system();
+  __syncthreads();
+  cta_barrier_all_ranks(r, state);
+  finish_call(state, epoch);
+}
+
+__global__ void __launch_bounds__(256) peer_row_gather_kernel(const long* __restrict__ ids, uint8_t* __restrict__ out, NvlsRegion r,
+                                                              const uint32_t* __restrict__ state, long rows_per_rank, long row_bytes,
+                                                              long ntok) {
+  const uint32_t epoch = ld_acquire_sys(state);                    // the publish kernel of this call has advanced it
+  const long base = r.data_off + (long)(epoch & 1u) * r.half_bytes;
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long t = warp; t < ntok; t += nwarps) {
+    const long id = ids[t];
+    const long owner = id / rows_per_rank;
+    uint4* dst = (uint4*)(out + t * row_bytes);
+    if (id < 0 || owner >= r.world) {                              // not a vocabulary id: zero row (what the masked lookup gives)
+      for (long i = lane; i < row_bytes / 16; i += 32) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+    const uint4* src = (const uint4*)((const uint8_t*)r.peer_bases[owner] + base + (id - owner * rows_per_rank) * row_bytes);
+    for (long i = lane; i < row_bytes / 16; i += 32) {
+      uint4 v;
+      asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
+      dst[i] = v;
+    }
+  }
+}
+
 static NvlsRegion make_region(const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off, long data_off,
                               long half_bytes, int rank, int world) {
   NvlsRegion r;
@@ -377,6 +427,26 @@ void nvls_reduce_scatter(const void* x, void* out, const int64_t* peer_bases, in
   else
     nxd_throw("nvls_reduce_scatter: bf16 or fp32 only", __FILE__, __LINE__);
   NXD_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace nxd
+
+namespace nxd {
+
+void nvls_embedding_gather(const void* table, const long* ids, void* out, const int64_t* peer_bases, int64_t mc_base,
+                           int64_t local_base, long flag_off, long data_off, long half_bytes, uint32_t* state, int rank, int world,
+                           long rows_per_rank, long row_bytes, long ntok, int ctas, cudaStream_t st) {
+  if (ctas > kNvlsCollMaxCtas) ctas = kNvlsCollMaxCtas;
+  const long bytes = rows_per_rank * row_bytes;
+  if (row_bytes % 16 || bytes > half_bytes) nxd_throw("nvls_embedding_gather: rows of 16-byte multiples, shard must fit the slot", __FILE__, __LINE__);
+  const NvlsRegion r = make_region(peer_bases, mc_base, local_base, flag_off, data_off, half_bytes, rank, world);
+  nvls_publish_kernel<<<ctas, 512, 0, st>>>((const uint8_t*)table, r, state, bytes);
+  NXD_CUDA_CHECK(cudaGetLastError());
+  if (ntok > 0) {
+    const int grid = (int)std::min<long>((ntok + 7) / 8, 148L * 8);
+    peer_row_gather_kernel<<<grid, 256, 0, st>>>(ids, (uint8_t*)out, r, state, rows_per_rank, row_bytes, ntok);
+    NXD_CUDA_CHECK(cudaGetLastError());
+  }
 }
 
 }  // namespace nxd

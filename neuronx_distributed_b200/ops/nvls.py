@@ -111,3 +111,30 @@ def reduce_scatter_sum(x: torch.Tensor, group, ctas: int = 32) -> torch.Tensor:
     _ext.count_launch()
     out = _ext.ext().nvls_reduce_scatter(x.contiguous(), *c.args, int(ctas))
     return out.view((x.shape[0] // world,) + tuple(x.shape[1:]))
+
+
+@plan_op("nvls.embedding_gather", pure=True)
+def embedding_gather(ids: torch.Tensor, table: torch.Tensor, group, ctas: int = 64) -> torch.Tensor:
+    """Rows ``ids`` (GLOBAL vocabulary ids, any shape) of a vocabulary-sharded table (``table`` = this rank's equal-sized shard
+    ``[V/world, H]``) → ``[*ids.shape, H]``.  CUDA: every rank publishes its shard in its symmetric slot and pulls the rows it
+    needs straight from the owners over NVLink (``csrc/nvls_coll.cu`` ``nvls_publish_kernel`` + ``peer_row_gather_kernel``) — no
+    masked partial lookups, no reduction.  Ids outside the vocabulary give zero rows.  CPU: all-gather of the shards + index."""
+    world = dist.get_world_size(group)
+    flat = ids.reshape(-1).long().contiguous()
+    if table.is_cuda and _ext.use_cuda(table) and hasattr(_ext.ext(), "nvls_embedding_gather") and available():
+        nbytes = table.numel() * table.element_size()
+        c = _coll(group, "emb", nbytes, 64)
+        _ext.count_launch(2)
+        out = _ext.ext().nvls_embedding_gather(table.contiguous(), flat, *c.args, int(ctas))
+    else:
+        from ..parallel_layers import comm
+
+        full = comm.all_gather(table.contiguous(), dim=0, group=group) if world > 1 else table
+        ok = (flat >= 0) & (flat < full.shape[0])
+        out = full[torch.where(ok, flat, torch.zeros_like(flat))] * ok.unsqueeze(-1).to(full.dtype)
+    return out.view(*ids.shape, table.shape[1])
+
+
+def embedding_gather_eligible(table: torch.Tensor) -> bool:
+    return (table.is_cuda and table.dtype in (torch.bfloat16, torch.float32, torch.float16) and table.is_contiguous()
+            and (table.shape[1] * table.element_size()) % 16 == 0 and available())

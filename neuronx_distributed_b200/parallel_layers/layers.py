@@ -21,6 +21,7 @@ B200 design notes
 from __future__ import annotations
 
 import math
+import os
 import warnings
 from typing import Any, Callable, Dict, Optional, Sequence, Tuple
 
@@ -208,6 +209,40 @@ class SPMDRank(nn.Module):
 # --------------------------------------------------------------------------------------
 # Embedding
 # --------------------------------------------------------------------------------------
+class _EmbeddingRS(torch.autograd.Function):
+    """``embedding_rs``: ids ``[B, S]`` → this rank's sequence shard ``[S/tp, B, H]`` of the vocabulary-parallel lookup, by
+    pulling each row from the rank that owns it (``ops.nvls.embedding_gather``) instead of a masked local lookup of all S·B
+    rows + reduce-scatter (reference layers.py:334-378).  Backward = the transpose of the reference path: all-gather the
+    output gradient along the sequence, scatter-add the rows of the locally owned ids into the shard's gradient."""
+
+    @staticmethod
+    def forward(ctx, ids, weight, group, start):
+        from .. import ops
+
+        n, r = dist.get_world_size(group), dist.get_rank(group)
+        B, S = ids.shape
+        assert S % n == 0, f"sequence length {S} is not divisible by the tensor-parallel size {n}"
+        mine = ids[:, r * (S // n):(r + 1) * (S // n)].t().contiguous()            # [S/tp, B]
+        out = ops.nvls.embedding_gather(mine, weight, group)                      # [S/tp, B, H]
+        ctx.save_for_backward(ids)
+        ctx.group, ctx.start, ctx.shape, ctx.dtype = group, start, weight.shape, weight.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        (ids,) = ctx.saved_tensors
+        g_full = comm.all_gather(gy.contiguous(), dim=0, group=ctx.group)          # [S, B, H]
+        local = ids.t().reshape(-1) - ctx.start                                    # [S·B] in (s, b) order
+        ok = (local >= 0) & (local < ctx.shape[0])
+        gw = torch.zeros(ctx.shape, dtype=g_full.dtype, device=g_full.device)
+        gw.index_add_(0, torch.where(ok, local, torch.zeros_like(local)),
+                      g_full.reshape(-1, g_full.shape[-1]) * ok.unsqueeze(-1).to(g_full.dtype))
+        return None, gw.to(ctx.dtype), None, None
+
+
+_EMBEDDING_RS = os.environ.get("NXD_EMBEDDING_RS", "0") == "1"     # opt-in until the kernels have run on hardware
+
+
 class ParallelEmbedding(BaseParallelLayer):
     """Embedding sharded along the vocabulary (default) or the embedding dim.
 
@@ -302,6 +337,8 @@ class ParallelEmbedding(BaseParallelLayer):
                 out = out.narrow(-1, 0, self.embedding_dim - self.pad_size)
             return out
         tp = self.tensor_model_parallel_size
+        if self._use_embedding_rs(input_):
+            return _EmbeddingRS.apply(input_, self.weight, self.tensor_model_parallel_group, self.start_index)
         if tp > 1:
             if self.rank_util is not None:
                 start = self.num_embeddings_per_partition * self.rank_util.get_rank().to(input_.device).long()
@@ -327,6 +364,23 @@ class ParallelEmbedding(BaseParallelLayer):
                 out.transpose(0, 1).contiguous(), 0, self.tensor_model_parallel_group
             )
         return mappings.reduce_from_tensor_model_parallel_region(out, self.tensor_model_parallel_group)
+
+    def _use_embedding_rs(self, input_: torch.Tensor) -> bool:
+        """The remote-gather path covers the default training contract: vocab sharding with equal shards, sequence parallel,
+        ``[B, S]`` ids → ``[S/tp, B, H]``, no ``F.embedding`` extras.  CPU tensors take it too when forced (tests)."""
+        if not (_EMBEDDING_RS or getattr(self, "force_embedding_rs", False)):
+            return False
+        if (self.tensor_model_parallel_size == 1 or not self.sequence_parallel_enabled or self.sequence_dim is not None
+                or not self.collect_output or self.rank_util is not None or input_.dim() != 2
+                or input_.shape[1] % self.tensor_model_parallel_size
+                or self.padding_idx is not None or self.max_norm is not None or self.scale_grad_by_freq or self.sparse
+                or self.num_embeddings % self.tensor_model_parallel_size):
+            return False
+        if input_.is_cuda:
+            from .. import ops
+
+            return ops.nvls.embedding_gather_eligible(self.weight)
+        return True
 
     def preshard_hook(self, model_state_dict: Dict[str, Any], prefix: str) -> None:
         """Pad a full (unsharded) checkpoint weight so it divides by tp (reference :404-431)."""

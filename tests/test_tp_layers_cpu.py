@@ -123,3 +123,36 @@ def _mappings(rank, world):
 
 def test_mappings_tp2():
     run_distributed(_mappings, 2)
+
+
+def _embedding_rs(rank, world):
+    """``embedding_rs`` (remote gather of the owner's rows instead of masked lookup + reduce-scatter): same output and the same
+    weight gradient as the reference path, on the CPU fallback of ``ops.nvls.embedding_gather``."""
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.parallel_layers.layers import ParallelEmbedding
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    torch.manual_seed(0)
+    V, H, B, S = 32, 8, 3, 8
+    ids = torch.randint(0, V, (B, S), generator=torch.Generator().manual_seed(3))
+    ref = ParallelEmbedding(V, H, sequence_parallel_enabled=True)
+    new = ParallelEmbedding(V, H, sequence_parallel_enabled=True)
+    new.load_state_dict(ref.state_dict())
+    new.force_embedding_rs = True
+    assert new._use_embedding_rs(ids) and not ref._use_embedding_rs(ids)
+    a, b = ref(ids), new(ids)
+    assert a.shape == (S // world, B, H)
+    torch.testing.assert_close(b, a)
+    g = torch.randn(a.shape, generator=torch.Generator().manual_seed(5 + rank))
+    (a * g).sum().backward()
+    (b * g).sum().backward()
+    torch.testing.assert_close(new.weight.grad, ref.weight.grad)
+    # not covered → the reference path
+    odd = ParallelEmbedding(V, H, sequence_parallel_enabled=True, padding_idx=0)
+    odd.force_embedding_rs = True
+    assert not odd._use_embedding_rs(ids) and not new._use_embedding_rs(ids[:, :7])
+
+
+def test_embedding_rs_matches_masked_lookup_plus_reduce_scatter():
+    run_distributed(_embedding_rs, 2)
+    run_distributed(_embedding_rs, 4)

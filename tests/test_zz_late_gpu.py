@@ -176,3 +176,32 @@ def test_launch_plan_replays_extension_kernels_and_captures():
         loaded = NxDModel.load(d); loaded.to_neuron()
         assert torch.equal(gen(loaded, 6), want)
     """, timeout=420)
+
+
+def _embedding_gather_loopback(rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from neuronx_distributed_b200.ops import nvls
+
+    g = dist.group.WORLD
+    V, H = 4096, 1024
+    tables = [(torch.randn(V // world, H, device="cuda", generator=torch.Generator(device="cuda").manual_seed(50 + r))).bfloat16()
+              for r in range(world)]
+    full = torch.cat(tables)
+    for it in range(3):                                    # parity halves / call counter
+        ids = torch.randint(-2, V + 2, (257,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(60 + it * 7 + rank))
+        got = nvls.embedding_gather(ids, tables[rank], g)
+        ok = (ids >= 0) & (ids < V)
+        want = full[ids.clamp(0, V - 1)] * ok.unsqueeze(-1)
+        assert torch.equal(got, want), (it, (got.float() - want.float()).abs().max())
+
+
+def test_embedding_gather_over_peer_memory_loopback():
+    """``embedding_rs``: two processes on cuda:0 publish their vocabulary shards and pull rows from each other."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from dist_utils import run_distributed
+
+    run_distributed(_embedding_gather_loopback, 2, use_cuda="loopback", timeout=240)
