@@ -639,6 +639,16 @@ static void nvls_all_gather(const Tensor& x, const c10::optional<Tensor>& out, c
   nxd::nvls_all_gather(x.data_ptr(), out ? out->data_ptr() : nullptr, peer_bases.data_ptr<int64_t>(), mc_base, local_base, flag_off,
                        data_off, half_bytes, (uint32_t*)state.data_ptr(), (int)rank, (int)world, bytes, (int)ctas, stream());
 }
+// x = [world, chunk…] contiguous: chunk p goes to rank p; returns [world, chunk…] with chunk p received from rank p
+static Tensor nvls_all_to_all(const Tensor& x, const Tensor& peer_bases, int64_t mc_base, int64_t local_base, int64_t flag_off,
+                              int64_t data_off, int64_t half_bytes, Tensor state, int64_t rank, int64_t world, int64_t ctas) {
+  CHECK_IN(x);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = at::empty_like(x);
+  nxd::nvls_all_to_all(x.data_ptr(), out.data_ptr(), peer_bases.data_ptr<int64_t>(), mc_base, local_base, flag_off, data_off,
+                       half_bytes, (uint32_t*)state.data_ptr(), (int)rank, (int)world, x.numel() * x.element_size(), (int)ctas, stream());
+  return out;
+}
 // table [rows_per_rank, H] (this rank's vocab shard), ids [ntok] int64 GLOBAL vocabulary ids of this rank's tokens → [ntok, H]
 static Tensor nvls_embedding_gather(const Tensor& table, const Tensor& ids, const Tensor& peer_bases, int64_t mc_base,
                                     int64_t local_base, int64_t flag_off, int64_t data_off, int64_t half_bytes, Tensor state,
@@ -684,6 +694,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_attention", &decode_attention);
   m.def("decode_attention_partial", &decode_attention_partial);
   m.def("nvls_embedding_gather", &nvls_embedding_gather);
+  m.def("nvls_all_to_all", &nvls_all_to_all);
   m.def("moe_block_tkg", &moe_block_tkg);
   m.def("moe_block_tkg_supported", [](int64_t T, int64_t H, int64_t E, int64_t I, int64_t K) {
     return nxd::moe_block_tkg_supported((int)T, (int)H, (int)E, (int)I, (int)K);

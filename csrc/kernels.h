@@ -76,6 +76,8 @@ void gemv_allreduce(const void* x, const void* w, const void* residual, void* y,
                     int world, int max_ctas, cudaStream_t st);
 void nvls_all_gather(const void* x, void* out, const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off,
                      long data_off, long half_bytes, uint32_t* state, int rank, int world, long bytes, int ctas, cudaStream_t st);
+void nvls_all_to_all(const void* x, void* out, const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off,
+                     long data_off, long half_bytes, uint32_t* state, int rank, int world, long bytes, int ctas, cudaStream_t st);
 void nvls_embedding_gather(const void* table, const long* ids, void* out, const int64_t* peer_bases, int64_t mc_base,
                            int64_t local_base, long flag_off, long data_off, long half_bytes, uint32_t* state, int rank, int world,
                            long rows_per_rank, long row_bytes, long ntok, int ctas, cudaStream_t st);

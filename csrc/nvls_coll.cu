@@ -353,6 +353,25 @@ __global__ void __launch_bounds__(256) peer_row_gather_kernel(const long* __rest
   }
 }
 
+// ---- all-to-all with equal splits (EP dispatch / combine; reference mappings.py:160-172 `xm.all_to_all`) ----------------------
+// After `nvls_publish_kernel` every rank's whole send buffer [world][chunk] sits in its slot; rank r pulls chunk r of every peer
+// straight into its output (16-byte loads over NVLink, all peers in flight at once): out[p] = send_p[r].
+__global__ void __launch_bounds__(512) peer_chunk_pull_kernel(uint8_t* __restrict__ out, NvlsRegion r, const uint32_t* __restrict__ state,
+                                                              long chunk_bytes) {
+  const uint32_t epoch = ld_acquire_sys(state);
+  const long base = r.data_off + (long)(epoch & 1u) * r.half_bytes;
+  const long nvec = chunk_bytes / 16, total = nvec * r.world;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int p = (int)(i / nvec);
+    const long v = i - (long)p * nvec;
+    const uint4* src = (const uint4*)((const uint8_t*)r.peer_bases[p] + base + (long)r.rank * chunk_bytes) + v;
+    uint4 t;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(src) : "memory");
+    ((uint4*)(out + (long)p * chunk_bytes))[v] = t;
+  }
+}
+
 static NvlsRegion make_region(const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off, long data_off,
                               long half_bytes, int rank, int world) {
   NvlsRegion r;
@@ -432,6 +451,16 @@ void nvls_reduce_scatter(const void* x, void* out, const int64_t* peer_bases, in
 }  // namespace nxd
 
 namespace nxd {
+
+void nvls_all_to_all(const void* x, void* out, const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off,
+                     long data_off, long half_bytes, uint32_t* state, int rank, int world, long bytes, int ctas, cudaStream_t st) {
+  if (ctas > kNvlsCollMaxCtas) ctas = kNvlsCollMaxCtas;
+  if (bytes % (16L * world) || bytes > half_bytes) nxd_throw("nvls_all_to_all: per-peer chunks of 16-byte multiples, buffer must fit the slot", __FILE__, __LINE__);
+  const NvlsRegion r = make_region(peer_bases, mc_base, local_base, flag_off, data_off, half_bytes, rank, world);
+  nvls_publish_kernel<<<ctas, 512, 0, st>>>((const uint8_t*)x, r, state, bytes);
+  peer_chunk_pull_kernel<<<ctas, 512, 0, st>>>((uint8_t*)out, r, state, bytes / world);
+  NXD_CUDA_CHECK(cudaGetLastError());
+}
 
 void nvls_embedding_gather(const void* table, const long* ids, void* out, const int64_t* peer_bases, int64_t mc_base,
                            int64_t local_base, long flag_off, long data_off, long half_bytes, uint32_t* state, int rank, int world,

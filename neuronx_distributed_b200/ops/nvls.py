@@ -138,3 +138,21 @@ def embedding_gather(ids: torch.Tensor, table: torch.Tensor, group, ctas: int = 
 def embedding_gather_eligible(table: torch.Tensor) -> bool:
     return (table.is_cuda and table.dtype in (torch.bfloat16, torch.float32, torch.float16) and table.is_contiguous()
             and (table.shape[1] * table.element_size()) % 16 == 0 and available())
+
+
+@plan_op("nvls.all_to_all", pure=True)
+def all_to_all(x: torch.Tensor, group, ctas: int = 64) -> torch.Tensor:
+    """Equal-split all-to-all along dim 0 (``x`` = ``[world * n, …]``: rows ``[p*n, (p+1)*n)`` go to rank ``p``; the result holds
+    at the same place what rank ``p`` sent here) over peer memory: publish the send buffer in the symmetric slot, pull the own
+    chunk of every peer (``csrc/nvls_coll.cu``).  No NCCL, CUDA-graph capturable."""
+    nbytes = x.numel() * x.element_size()
+    c = _coll(group, "a2a", nbytes, 64)
+    _ext.count_launch(2)
+    return _ext.ext().nvls_all_to_all(x.contiguous(), *c.args, int(ctas))
+
+
+def all_to_all_eligible(x: torch.Tensor, group) -> bool:
+    world = dist.get_world_size(group)
+    return (x.is_cuda and x.dim() >= 1 and x.shape[0] % world == 0 and (x.numel() * x.element_size()) % (16 * world) == 0
+            and x.numel() > 0 and available() and hasattr(_ext.ext(), "nvls_all_to_all")
+            and os.environ.get("NXD_NVLS_A2A", "0") == "1")

@@ -147,6 +147,17 @@ def all_to_all(x: torch.Tensor, split_dim: int, concat_dim: int, group=None) -> 
     n = dist.get_world_size(group)
     if n == 1:
         return x
+    if x.is_cuda and x.shape[split_dim] % n == 0:
+        from ..ops import nvls as _nvls
+
+        # EP dispatch / combine over peer memory (opt-in NXD_NVLS_A2A=1): one publish + one pull kernel instead of NCCL
+        send = x.movedim(split_dim, 0).contiguous() if split_dim != 0 else x.contiguous()
+        if _nvls.all_to_all_eligible(send, group):
+            recv = _nvls.all_to_all(send, group)                       # [n * c, …rest] with the split dim in front
+            chunks = recv.chunk(n, dim=0)
+            if split_dim != 0:
+                chunks = [c.movedim(0, split_dim) for c in chunks]
+            return torch.cat(chunks, dim=concat_dim)
     pieces = [p.contiguous() for p in x.chunk(n, dim=split_dim)]
     outs = [torch.empty_like(pieces[0]) for _ in range(n)]
     if _is_gloo(group):

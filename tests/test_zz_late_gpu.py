@@ -205,3 +205,37 @@ def test_embedding_gather_over_peer_memory_loopback():
     from dist_utils import run_distributed
 
     run_distributed(_embedding_gather_loopback, 2, use_cuda="loopback", timeout=240)
+
+
+def _all_to_all_loopback(rank, world):
+    import os
+
+    os.environ["NXD_NVLS_A2A"] = "1"
+    import torch
+    import torch.distributed as dist
+
+    from neuronx_distributed_b200.ops import nvls
+    from neuronx_distributed_b200.parallel_layers import comm
+
+    g = dist.group.WORLD
+    for it in range(3):
+        xs = [torch.randn(world * 64, 4, 256, device="cuda", generator=torch.Generator(device="cuda").manual_seed(70 + it * 5 + r)).bfloat16()
+              for r in range(world)]
+        assert nvls.all_to_all_eligible(xs[rank], g)
+        got = nvls.all_to_all(xs[rank], g)
+        want = torch.cat([xs[p].chunk(world, 0)[rank] for p in range(world)], 0)
+        assert torch.equal(got, want), it
+        # through the comm wrapper with a split dim that is not the leading one (EP dispatch layout)
+        got2 = comm.all_to_all(xs[rank], split_dim=1, concat_dim=0, group=g)
+        want2 = torch.cat([xs[p].chunk(world, 1)[rank] for p in range(world)], 0)
+        assert torch.equal(got2, want2), it
+
+
+def test_all_to_all_over_peer_memory_loopback():
+    """EP dispatch / combine without NCCL: publish + pull kernels between two processes on cuda:0."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from dist_utils import run_distributed
+
+    run_distributed(_all_to_all_loopback, 2, use_cuda="loopback", timeout=240)
