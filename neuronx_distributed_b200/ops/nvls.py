@@ -152,7 +152,8 @@ def all_to_all(x: torch.Tensor, group, ctas: int = 64) -> torch.Tensor:
 
 
 def all_to_all_eligible(x: torch.Tensor, group) -> bool:
+    if os.environ.get("NXD_NVLS_A2A", "0") != "1":             # opt-in until the kernels have run on hardware
+        return False
     world = dist.get_world_size(group)
     return (x.is_cuda and x.dim() >= 1 and x.shape[0] % world == 0 and (x.numel() * x.element_size()) % (16 * world) == 0
-            and x.numel() > 0 and available() and hasattr(_ext.ext(), "nvls_all_to_all")
-            and os.environ.get("NXD_NVLS_A2A", "0") == "1")
+            and x.numel() > 0 and available() and hasattr(_ext.ext(), "nvls_all_to_all"))

@@ -11,6 +11,7 @@ GEMM+collective kernels in ``ops/tp_fused.py``.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Sequence, Union
 
 import torch
@@ -147,7 +148,7 @@ def all_to_all(x: torch.Tensor, split_dim: int, concat_dim: int, group=None) -> 
     n = dist.get_world_size(group)
     if n == 1:
         return x
-    if x.is_cuda and x.shape[split_dim] % n == 0:
+    if x.is_cuda and x.shape[split_dim] % n == 0 and os.environ.get("NXD_NVLS_A2A", "0") == "1":
         from ..ops import nvls as _nvls
 
         # EP dispatch / combine over peer memory (opt-in NXD_NVLS_A2A=1): one publish + one pull kernel instead of NCCL
