@@ -369,6 +369,9 @@ def _wgrad_on_side(ready_event, go2d: torch.Tensor, x2d: torch.Tensor, weight: t
     return done
 
 
+_KEEP_GATHERED = os.environ.get("NXD_TP_KEEP_GATHERED", "1") == "1"
+
+
 def _flat(x: torch.Tensor) -> torch.Tensor:
     return x.reshape(-1, x.shape[-1])
 
@@ -385,13 +388,25 @@ class _ColumnSP:
             return _column_sp_forward_op(x, weight, self.ws.group)
         x2 = _flat(x).contiguous()
         out, gathered = self.ws.ag_gemm(x2, weight, True)
-        self.gathered = gathered.clone()   # keep AG(x) for wgrad (one D2D copy; no re-gather in backward)
+        # Keep AG(x) for wgrad: one D2D copy now instead of a second all-gather in backward (faster, but the saved input is
+        # tp× the sharded one).  NXD_TP_KEEP_GATHERED=0 saves only the shard and re-gathers (the reference's memory behaviour).
+        self.gathered = gathered.clone() if _KEEP_GATHERED else None
         return out.view(x.shape[0] * self.ws.world, *x.shape[1:-1], weight.shape[0])
 
     def backward(self, x, weight, gy, has_bias, need_gx, need_gw, gathered, gy_dgrad=None):
         g2 = _flat(gy).contiguous()
         gbias = g2.float().sum(0).to(gy.dtype) if has_bias else None
         gx = gw = None
+        if gathered is None and need_gw:                                   # NXD_TP_KEEP_GATHERED=0: re-gather the saved shard
+            from . import nvls
+
+            x2 = _flat(x).contiguous()
+            if nvls.available(self.ws.group) and nvls.has_multicast(self.ws.group):
+                gathered = nvls.all_gather(x2, self.ws.group)
+            else:
+                full = torch.empty((self.ws.world * x2.shape[0], x2.shape[1]), dtype=x2.dtype, device=x2.device)
+                dist.all_gather_into_tensor(full, x2, group=self.ws.group)
+                gathered = full
         side = _side_wgrad_ok(self.ws, weight, need_gw and need_gx)
         ev = None
         if side:
