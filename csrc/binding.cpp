@@ -326,6 +326,26 @@ static std::vector<Tensor> moe_block_tkg(const Tensor& x, const c10::optional<Te
                      (float)up_hi, cooperative, stream());
   return {out, logits, idx, w};
 }
+// x [M<=8, K] bf16; w = MX byte stream of [N, K] (fp4: K/2 bytes per row, fp8: K), any integer dtype view; scale [N, K/32] uint8
+static Tensor gemv_mx(const Tensor& x, const Tensor& w, const Tensor& scale, int64_t fmt, const c10::optional<Tensor>& residual) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.is_contiguous() && x.size(0) >= 1 && x.size(0) <= 8);
+  TORCH_CHECK(w.is_cuda() && w.is_contiguous() && scale.is_cuda() && scale.is_contiguous() && scale.scalar_type() == at::kByte &&
+              scale.dim() == 2);
+  const int M = x.size(0), K = x.size(1), N = scale.size(0);
+  TORCH_CHECK(K % 32 == 0 && scale.size(1) == K / 32, "gemv_mx: scale must be [N, K/32]");
+  const long row_bytes = fmt == 0 ? K / 2 : K;
+  TORCH_CHECK((long)(w.numel() * w.element_size()) == (long)N * row_bytes, "gemv_mx: weight bytes do not match [N, K] in this format");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(w.data_ptr()) % 16 == 0);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor y = at::empty({M, N}, x.options());
+  const void* res = nullptr;
+  if (residual.has_value()) {
+    TORCH_CHECK(residual->is_contiguous() && residual->sizes() == y.sizes() && residual->scalar_type() == at::kBFloat16);
+    res = residual->data_ptr();
+  }
+  nxd::gemv_mx(x.data_ptr(), w.data_ptr(), scale.data_ptr(), res, y.data_ptr(), M, N, K, (int)fmt, stream());
+  return y;
+}
 static Tensor gemv(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& residual) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && x.dim() == 2 && w.dim() == 2);
   TORCH_CHECK(x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1) && x.size(0) >= 1 && x.size(0) <= 8 && x.size(1) % 8 == 0);
@@ -695,6 +715,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_attention_partial", &decode_attention_partial);
   m.def("nvls_embedding_gather", &nvls_embedding_gather);
   m.def("nvls_all_to_all", &nvls_all_to_all);
+  m.def("gemv_mx", &gemv_mx);
   m.def("moe_block_tkg", &moe_block_tkg);
   m.def("moe_block_tkg_supported", [](int64_t T, int64_t H, int64_t E, int64_t I, int64_t K) {
     return nxd::moe_block_tkg_supported((int)T, (int)H, (int)E, (int)I, (int)K);

@@ -122,6 +122,10 @@ void moe_block_tkg(const void* x, const void* gamma, const void* router_w, const
                    int act_over_topk, int normalize, int pre_scale, int round_logits, int act, float act_alpha, float act_beta,
                    float gate_lo, float gate_hi, float up_lo, float up_hi, bool cooperative, cudaStream_t st);
 
+// ---- decode GEMV on MX (block-scaled fp4 / fp8) weights (gemv_mx.cu)
+void gemv_mx(const void* x, const void* w, const void* scale, const void* residual, void* y, int M, int N, int K, int fmt,
+             cudaStream_t st);
+
 // ---- decode (decode.cu)
 void decode_attention(const void* q, const void* k, const void* v, const long* positions, void* out, float* part_o,
                       float* part_ml, int B, int H, int Hkv, int L, const long* ks, const long* vs, long q_sb, long q_sh,

@@ -5,7 +5,7 @@ reference used on CPU and as the numerics oracle in tests.  On a GPU box the CUD
 mandatory (see ``_ext.use_cuda``).
 """
 from . import _ext  # noqa: F401
-from . import act, attention, cross_entropy, gemm, moe_tkg, norm, nvls, optim, rope, select, symm, tp_fused, zero1_comm  # noqa: F401
+from . import act, attention, cross_entropy, gemm, gemm_mx, moe_tkg, norm, nvls, optim, rope, select, symm, tp_fused, zero1_comm  # noqa: F401
 
 
 def extension_available() -> bool:

@@ -363,6 +363,13 @@ class BaseQuantizeParallelLinear(ProcessGroupSafeDeepcopy, nn.Module, metaclass=
         if self._scale_is_output_only(0):
             y = torch.nn.functional.linear(x.to(out_dtype), direct_cast_dequantize(self.weight, out_dtype))
             return scale_dequantize(y, w_scale.reshape(1, -1) if w_scale.numel() > 1 else w_scale, out_dtype)
+        if self._is_mx() and x.is_cuda and self.weight.dim() == 2 and not self.mx_swizzle:
+            from ..ops import gemm_mx
+
+            x2 = x.reshape(-1, x.shape[-1])
+            if gemm_mx.gemv_eligible(x2.contiguous(), self.weight, self.scale):
+                # token generation on MX weights: decode the codes in registers, read 4.25 / 8.25 bits per weight
+                return gemm_mx.linear_mx(x, self.weight, self.scale).to(out_dtype)
         return torch.nn.functional.linear(x.to(out_dtype), self._dequantized_weight(self.weight, self.scale, out_dtype))
 
     def _linear_experts(self, x: torch.Tensor, expert_indices: Optional[torch.Tensor]) -> torch.Tensor:

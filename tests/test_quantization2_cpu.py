@@ -368,3 +368,22 @@ def _experts(rank, world):
 
 def test_quantized_expert_layers_tp2():
     run_distributed(_experts, 2, timeout=150)
+
+
+def test_linear_mx_matches_mx_matmul_oracle():
+    """``ops.gemm_mx.linear_mx`` (the de-quantise + GEMM path every non-decode call takes) equals the MX oracle for both packings,
+    leading dims and a residual; x4 words and raw bytes are the same stream."""
+    import torch
+
+    from neuronx_distributed_b200.ops import gemm_mx
+    from neuronx_distributed_b200.quantization.microscaling.mx_torch import mx_matmul, quantize_mx
+
+    torch.manual_seed(0)
+    w, x, r = torch.randn(24, 96), torch.randn(2, 3, 96), torch.randn(2, 3, 24)
+    for kind in ("mxfp4", "mxfp8"):
+        p, s = quantize_mx(w, kind)
+        assert gemm_mx.kind_of(p) == kind
+        want = mx_matmul(x.reshape(-1, 96), p, s, kind, torch.float32).view(2, 3, 24) + r
+        torch.testing.assert_close(gemm_mx.linear_mx(x, p, s, residual=r), want)
+        torch.testing.assert_close(gemm_mx.linear_mx(x, p.view(torch.uint8), s, kind=kind, residual=r), want)
+    assert not gemm_mx.gemv_eligible(x.reshape(-1, 96), p, s)            # CPU / opt-in flag unset
