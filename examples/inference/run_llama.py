@@ -4,6 +4,8 @@ reference's ``examples/inference/run_llama.py`` / ``runner.py`` (trace → load 
 
   torchrun --nproc-per-node 8 examples/inference/run_llama.py --model 13b --tp_degree 8 --batch_size 1 \
       --max_prompt_length 1024 --sequence_length 2048 --benchmark
+  # GQA with fewer KV heads than ranks: replicas of a KV head shard its cache along the sequence (flash decoding)
+  torchrun --nproc-per-node 8 examples/inference/run_llama.py --model 7b --num_kv_heads 4 --tp_degree 8 --flash_decoding
 """
 import argparse
 import json
@@ -37,6 +39,9 @@ def main():
     p.add_argument("--benchmark", action="store_true")
     p.add_argument("--num_runs", type=int, default=20)
     p.add_argument("--no_cuda_graphs", action="store_true")
+    p.add_argument("--flash_decoding", action="store_true",
+                   help="shard the KV cache along the sequence inside each KV-replica group (needs tp_degree > number of KV heads)")
+    p.add_argument("--num_kv_heads", type=int, default=0, help="override the number of KV heads (GQA experiments)")
     a = p.parse_args()
     dev = init_distributed()
     ps.initialize_model_parallel(tensor_model_parallel_size=a.tp_degree)
@@ -46,8 +51,11 @@ def main():
         vocab_size=4096, hidden_size=512, intermediate_size=1408, num_hidden_layers=4, num_attention_heads=8, **k))(**kw)
     if a.num_layers > 0:
         cfg.num_hidden_layers = a.num_layers
+    if a.num_kv_heads > 0:
+        cfg.num_key_value_heads = a.num_kv_heads
     torch.manual_seed(0)
-    model = LlamaForInference(cfg, batch_size=a.batch_size, max_seq_len=a.sequence_length).eval()
+    model = LlamaForInference(cfg, batch_size=a.batch_size, max_seq_len=a.sequence_length,
+                              flash_decoding=a.flash_decoding).eval()
     B, P = a.batch_size, a.max_prompt_length
     mb = ModelBuilder(tp_degree=a.tp_degree, use_cuda_graphs=(dev.type == "cuda" and not a.no_cuda_graphs))
     for bucket in generate_buckets(min(128, P), P):

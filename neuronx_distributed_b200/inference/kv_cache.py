@@ -45,6 +45,16 @@ class KVCacheManager:
             self.k[layer][seq_ids, :S] = self._q(k)
             self.v[layer][seq_ids, :S] = self._q(v)
 
+    def write_prefill_sharded(self, layer: int, k: torch.Tensor, v: torch.Tensor, shard_rank: int) -> None:
+        """Flash-decoding layout: this rank keeps prompt positions ``[shard_rank·L_local, (shard_rank+1)·L_local)`` of the
+        k/v ``[B, S, H, D]`` every member of the KV-replica group computed (reference ``kv_cache_manager.py:60-88``)."""
+        l_local = self.k[layer].shape[1]
+        lo = shard_rank * l_local
+        hi = min(k.shape[1], lo + l_local)
+        if hi > lo:
+            self.k[layer][: k.shape[0], : hi - lo].copy_(self._q(k[:, lo:hi]))
+            self.v[layer][: v.shape[0], : hi - lo].copy_(self._q(v[:, lo:hi]))
+
     def write_decode(self, layer: int, k: torch.Tensor, v: torch.Tensor, positions: torch.Tensor) -> None:
         """k/v ``[B, 1, H, D]``; ``positions`` ``[B]`` (device tensor; no host sync → graph capturable)."""
         b = torch.arange(k.shape[0], device=k.device)

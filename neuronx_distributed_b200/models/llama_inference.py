@@ -18,7 +18,7 @@ from .llama import LlamaConfig, LlamaForCausalLM
 
 class LlamaForInference(nn.Module):
     def __init__(self, cfg: LlamaConfig, batch_size: int = 1, max_seq_len: int = 2048, on_device_sampling: bool = True,
-                 sampler: Optional[Sampler] = None, lm_cls=None):
+                 sampler: Optional[Sampler] = None, lm_cls=None, flash_decoding: bool = False):
         """``lm_cls``: any decoder built from Llama attention blocks (``LlamaForCausalLM`` default; ``MixtralForCausalLM`` for
         the MoE families — its layers' ``mlp`` returns ``(y, router_logits)``, handled in ``_body``)."""
         super().__init__()
@@ -28,8 +28,19 @@ class LlamaForInference(nn.Module):
         self.lm = (lm_cls or LlamaForCausalLM)(cfg)
         self.batch_size, self.max_seq_len = batch_size, max_seq_len
         attn0 = self._core.layers[0].self_attn
+        # flash decoding (reference examples/inference ``flash_decoding_enabled``): TP ranks that hold replicas of the same KV
+        # heads shard the cache along the SEQUENCE inside that replica group instead of storing it ``m`` times
+        self.flash_decoding, self.kv_group, self.kv_rank, shards = bool(flash_decoding), None, 0, 1
+        if flash_decoding:
+            import torch.distributed as dist
+
+            self.kv_group = getattr(attn0.qkv_proj, "kv_group", None)
+            assert self.kv_group is not None and dist.get_world_size(self.kv_group) > 1, \
+                "flash decoding needs replicated KV heads (tensor-parallel size > number of KV heads)"
+            shards, self.kv_rank = dist.get_world_size(self.kv_group), dist.get_rank(self.kv_group)
+            assert max_seq_len % shards == 0, f"max_seq_len {max_seq_len} must divide by the KV replication factor {shards}"
         self.kv = KVCacheManager(cfg.num_hidden_layers, batch_size, max_seq_len, attn0.num_kv_heads_local, cfg.head_dim,
-                                 dtype=cfg.dtype, device=cfg.device)
+                                 dtype=cfg.dtype, device=cfg.device, num_cores_per_group=shards)
         self.sampler = sampler or Sampler(top_k=1, vocab_parallel=True)
         self.on_device_sampling = on_device_sampling
         cos, sin = ops.rope.rope_tables(max_seq_len, cfg.head_dim, cfg.rope_theta, cfg.device, 0, cfg.rope_scaling_factor)
@@ -57,7 +68,16 @@ class LlamaForInference(nn.Module):
         q = q.reshape(S, B, att.num_heads_local, D).transpose(0, 1)
         k = k.reshape(S, B, att.num_kv_heads_local, D).transpose(0, 1)
         v = v.reshape(S, B, att.num_kv_heads_local, D).transpose(0, 1).contiguous()
-        if not prefill and S > 1:
+        if self.flash_decoding and not prefill:
+            assert S == 1 and tree is None, "flash decoding serves plain token generation (no speculation window)"
+            from ..modules.attention.flash_decode import flash_decode_attention, write_decode_sharded
+
+            cos = self.rope_cos[positions].unsqueeze(1)
+            sin = self.rope_sin[positions].unsqueeze(1)
+            q, k = _rope_per_batch(q, cos, sin), _rope_per_batch(k, cos, sin)
+            write_decode_sharded(self.kv.k[layer_idx], self.kv.v[layer_idx], k, v, positions, self.kv_rank)   # owner-only write
+            o = flash_decode_attention(q, self.kv.k[layer_idx], self.kv.v[layer_idx], positions, self.kv_group)
+        elif not prefill and S > 1:
             # speculation window: W new tokens per sequence at positions p..p+W-1, causal among themselves, full cache before
             W = S
             # linear window: node w sits at sequence position p+w; Medusa tree: node w sits at p+depth[w] (its cache SLOT is
@@ -72,7 +92,10 @@ class LlamaForInference(nn.Module):
         elif prefill:
             cos, sin = self.rope_cos[:S], self.rope_sin[:S]
             q, k = ops.rope.apply_rotary(q, cos, sin), ops.rope.apply_rotary(k, cos, sin)
-            self.kv.write_prefill(layer_idx, k, v)
+            if self.flash_decoding:
+                self.kv.write_prefill_sharded(layer_idx, k, v, self.kv_rank)
+            else:
+                self.kv.write_prefill(layer_idx, k, v)
             o = ops.attention.flash_attention(q, k, v, causal=True)
         elif (q.is_cuda and q.dtype == torch.bfloat16 and self.kv.kv_quant is None and self.kv.seq_shards == 1
               and ops._ext.ext() is not None and hasattr(ops._ext.ext(), "decode_rope_kv")):

@@ -77,16 +77,21 @@ def flash_decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torc
     B, _, Hl, D = q.shape
     l_local = k_cache.shape[1]
     scale = scale if scale is not None else 1.0 / math.sqrt(D)
-    # 1. every rank needs the queries of the whole group
-    q_all = comm.all_gather(q.contiguous(), dim=2, group=group) if n > 1 else q          # [B, 1, n·Hl, D]
+    # 1. every rank needs the queries of the whole group.  Heads are ordered (local head, rank): the group members share the
+    #    same Hkv local KV heads and local query head j belongs to KV head j // (Hl / Hkv) on every member, so this order keeps
+    #    the GQA mapping "head i → KV head i // (n·Hl / Hkv)" valid for any number of local KV heads
+    if n > 1:
+        q_all = comm.all_gather(q.unsqueeze(3).contiguous(), dim=3, group=group).reshape(B, 1, Hl * n, D)
+    else:
+        q_all = q
     # 2. partial attention over the local shard: global position p is local index p − r·L_local
     o, m, l = _local_partial(q_all, k_cache, v_cache, positions - r * l_local, scale)
     # 3. combine across the group
     if n > 1:
         m_glob = comm.all_reduce(m.clone(), op="max", group=group)
         w = torch.where(torch.isinf(m), torch.zeros_like(m), torch.exp(m - m_glob))
-        ol = torch.cat([o * w.unsqueeze(-1), (l * w).unsqueeze(-1)], dim=-1)             # [B, n·Hl, D+1]: ONE reduce-scatter
-        mine = comm.reduce_scatter(ol, dim=1, group=group)                               # [B, Hl, D+1]
+        ol = torch.cat([o * w.unsqueeze(-1), (l * w).unsqueeze(-1)], dim=-1)             # [B, Hl·n, D+1]: ONE reduce-scatter
+        mine = comm.reduce_scatter(ol.view(B, Hl, n, D + 1), dim=2, group=group)[:, :, 0]  # this rank's column of (head, rank)
         o_mine, l_mine = mine[..., :D], mine[..., D]
     else:
         o_mine, l_mine = o, l

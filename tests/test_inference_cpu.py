@@ -178,3 +178,30 @@ def _medusa(rank, world):
 
 def test_medusa_tree_decoding_matches_greedy():
     run_distributed(_medusa, 1, timeout=120)
+
+
+def _flash_decode_model(rank, world):
+    """``LlamaForInference(flash_decoding=True)``: TP=4 over 2 KV heads → each KV head lives on 2 ranks, which shard its cache
+    along the sequence; generation equals the replicated-cache model token for token."""
+    from neuronx_distributed_b200.models.llama import LlamaConfig
+    from neuronx_distributed_b200.models.llama_inference import LlamaForInference
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    cfg = dict(vocab_size=64, hidden_size=64, intermediate_size=96, num_hidden_layers=2, num_attention_heads=8,
+               num_key_value_heads=2, dtype=torch.float32, max_position_embeddings=32)
+    torch.manual_seed(0)
+    plain = LlamaForInference(LlamaConfig(**cfg), batch_size=2, max_seq_len=32).eval()
+    torch.manual_seed(0)
+    fd = LlamaForInference(LlamaConfig(**cfg), batch_size=2, max_seq_len=32, flash_decoding=True).eval()
+    fd.load_state_dict(plain.state_dict())
+    assert fd.kv.k[0].shape[1] == 16 and plain.kv.k[0].shape[1] == 32          # half the cache per rank
+    ids = torch.randint(0, 64, (2, 20), generator=torch.Generator().manual_seed(1))   # prompt crosses the shard boundary (16)
+    lens = torch.tensor([20, 13])
+    want = plain.generate(ids, 8, prompt_lens=lens)
+    got = fd.generate(ids, 8, prompt_lens=lens)
+    assert torch.equal(got, want), (got, want)
+
+
+def test_llama_inference_flash_decoding_tp4():
+    run_distributed(_flash_decode_model, 4, timeout=240)
