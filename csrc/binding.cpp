@@ -326,6 +326,20 @@ static std::vector<Tensor> moe_block_tkg(const Tensor& x, const c10::optional<Te
                      (float)up_hi, cooperative, stream());
   return {out, logits, idx, w};
 }
+// a [M,K], b [N,K]: fp8 bytes; sfa [ceil(M/128), K/128, 512], sfb [ceil(N/128), K/128, 512]: tiled E8M0 scales → [M,N] bf16
+static Tensor gemm_mxfp8(const Tensor& a, const Tensor& b, const Tensor& sfa, const Tensor& sfb, int64_t a_fmt, int64_t b_fmt) {
+  CHECK_IN(a); CHECK_IN(b); CHECK_IN(sfa); CHECK_IN(sfb);
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.element_size() == 1 && b.element_size() == 1 && a.size(1) == b.size(1));
+  const int M = a.size(0), N = b.size(0), K = a.size(1);
+  TORCH_CHECK(K % 128 == 0 && N % 8 == 0, "gemm_mxfp8: K % 128 == 0 and N % 8 == 0");
+  TORCH_CHECK(sfa.scalar_type() == at::kByte && sfb.scalar_type() == at::kByte);
+  TORCH_CHECK(sfa.numel() == (long)((M + 127) / 128) * (K / 128) * 512 && sfb.numel() == (long)((N + 127) / 128) * (K / 128) * 512,
+              "gemm_mxfp8: scale tensors must be tiled [rows/128, K/128, 512]");
+  c10::cuda::CUDAGuard guard(a.device());
+  Tensor out = at::empty({M, N}, a.options().dtype(at::kBFloat16));
+  nxd::gemm_mxfp8(a.data_ptr(), b.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), out.data_ptr(), M, N, K, (int)a_fmt, (int)b_fmt, stream());
+  return out;
+}
 // x [M<=8, K] bf16; w = MX byte stream of [N, K] (fp4: K/2 bytes per row, fp8: K), any integer dtype view; scale [N, K/32] uint8
 static Tensor gemv_mx(const Tensor& x, const Tensor& w, const Tensor& scale, int64_t fmt, const c10::optional<Tensor>& residual) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.is_contiguous() && x.size(0) >= 1 && x.size(0) <= 8);
@@ -716,6 +730,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("nvls_embedding_gather", &nvls_embedding_gather);
   m.def("nvls_all_to_all", &nvls_all_to_all);
   m.def("gemv_mx", &gemv_mx);
+  m.def("gemm_mxfp8", &gemm_mxfp8);
   m.def("moe_block_tkg", &moe_block_tkg);
   m.def("moe_block_tkg_supported", [](int64_t T, int64_t H, int64_t E, int64_t I, int64_t K) {
     return nxd::moe_block_tkg_supported((int)T, (int)H, (int)E, (int)I, (int)K);

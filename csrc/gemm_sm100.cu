@@ -516,6 +516,10 @@ CUtensorMap make_tmap_bf16_strided(const void* ptr, uint64_t rows, uint64_t cols
   return m;
 }
 int device_sm_count() { return sm_count(); }
+// fp8 bytes, box = {128 k-bytes, box_rows} (used by gemm_mx_sm100.cu)
+CUtensorMap make_tmap_u8_box(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  return make_tmap_u8(ptr, rows, cols, box_rows);
+}
 
 template <bool AK, bool BK, int MODE, typename OutT>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, void* out, int M, int N, int K, bool accumulate,

@@ -122,6 +122,10 @@ void moe_block_tkg(const void* x, const void* gamma, const void* router_w, const
                    int act_over_topk, int normalize, int pre_scale, int round_logits, int act, float act_alpha, float act_beta,
                    float gate_lo, float gate_hi, float up_lo, float up_hi, bool cooperative, cudaStream_t st);
 
+// ---- block-scaled MXFP8 GEMM on tcgen05 (gemm_mx_sm100.cu); a_fmt / b_fmt: 0 = e4m3, 1 = e5m2
+void gemm_mxfp8(const void* a, const void* b, const void* sfa, const void* sfb, void* out, int M, int N, int K, int a_fmt,
+                int b_fmt, cudaStream_t st);
+
 // ---- decode GEMV on MX (block-scaled fp4 / fp8) weights (gemv_mx.cu)
 void gemv_mx(const void* x, const void* w, const void* scale, const void* residual, void* y, int M, int N, int K, int fmt,
              cudaStream_t st);

@@ -6,6 +6,9 @@ byte (low nibble first; ``uint16`` x4 words are a view of the same bytes), MXFP8
 
 * ``rows <= 8`` on CUDA (token generation): ``csrc/gemv_mx.cu`` — the codes are decoded in registers, nothing is expanded in
   memory, so a decode step reads 4.25 / 8.25 bits per weight instead of 16;
+* MXFP8 weights, more rows, opt-in ``NXD_GEMM_MX=1``: activations are quantised to MXFP8 online and both operands go through
+  the block-scaled tensor-core GEMM (``csrc/gemm_mx_sm100.cu``, ``tcgen05.mma.kind::mxf8f6f4.block_scale``: the E8M0 scales
+  are applied inside the tensor core, nothing is de-quantised) — W8A8-MX numerics, oracle :func:`matmul_mxfp8_reference`;
 * otherwise: de-quantise to the activation dtype and run the dense GEMM (tcgen05 bf16 kernel on CUDA) — numerically the
   oracle ``experimental…mx_torch.mx_matmul``."""
 from __future__ import annotations
@@ -40,6 +43,42 @@ def dequantize(weight: torch.Tensor, scale: torch.Tensor, kind: str, dtype: torc
     return torch.ldexp(vals.reshape(N, -1, 32), (scale.to(torch.int32) - 127).unsqueeze(-1)).reshape(N, -1).to(dtype)
 
 
+def tile_scales(scale: torch.Tensor) -> torch.Tensor:
+    """E8M0 scales ``[R, K/32]`` → the chunked layout the block-scaled GEMM streams: ``[ceil(R/128), K/128, 512]`` where the
+    512-byte chunk of (row tile, 128-wide K block) holds scale (r, j) at byte ``(r % 32) * 16 + (r // 32) * 4 + j`` — what
+    ``tcgen05.cp.32x128b.warpx4`` spreads over 4 TMEM columns.  Rows are padded with 2^0."""
+    R, KB = scale.shape
+    assert KB % 4 == 0, "K must be a multiple of 128"
+    T = (R + 127) // 128
+    if T * 128 != R:
+        scale = torch.cat([scale, torch.full((T * 128 - R, KB), 127, dtype=scale.dtype, device=scale.device)])
+    s = scale.reshape(T, 4, 32, KB // 4, 4)                       # [tile, r // 32, r % 32, k block of 128, j]
+    return s.permute(0, 3, 2, 1, 4).contiguous().reshape(T, KB // 4, 512)
+
+
+def matmul_mxfp8_reference(a_q: torch.Tensor, a_scale: torch.Tensor, b_q: torch.Tensor, b_scale: torch.Tensor,
+                           a_kind: str = "mxfp8", b_kind: str = "mxfp8") -> torch.Tensor:
+    """fp32 oracle of the block-scaled GEMM: ``dequant(a) @ dequant(b)ᵀ``."""
+    return dequantize(a_q, a_scale, a_kind) @ dequantize(b_q, b_scale, b_kind).t()
+
+
+def gemm_mx_eligible(x2d: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, kind: str) -> bool:
+    if os.environ.get("NXD_GEMM_MX", "0") != "1":                 # opt-in until the kernel has run on hardware
+        return False
+    return (x2d.is_cuda and _FMT.get(kind, 0) in (1, 2) and x2d.shape[1] % 128 == 0 and scale.shape[0] % 8 == 0
+            and weight.is_contiguous() and _ext.use_cuda(x2d, weight, scale) and hasattr(_ext.ext(), "gemm_mxfp8"))
+
+
+def matmul_mxfp8(a_q: torch.Tensor, a_scale: torch.Tensor, b_q: torch.Tensor, b_scale: torch.Tensor, a_kind: str = "mxfp8",
+                 b_kind: str = "mxfp8", b_scale_tiled: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``[M, K] · [N, K]ᵀ`` on MXFP8 operands (byte streams or x4 words) with E8M0 block scales → bf16 ``[M, N]``."""
+    a8 = a_q.contiguous().view(torch.uint8).reshape(a_scale.shape[0], -1)
+    b8 = b_q.contiguous().view(torch.uint8).reshape(b_scale.shape[0], -1)
+    _ext.count_launch()
+    return _ext.ext().gemm_mxfp8(a8, b8, tile_scales(a_scale), b_scale_tiled if b_scale_tiled is not None else tile_scales(b_scale),
+                                 _FMT[a_kind] - 1, _FMT[b_kind] - 1)
+
+
 def gemv_eligible(x2d: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor) -> bool:
     if os.environ.get("NXD_GEMV_MX", "0") != "1":                 # opt-in until the kernel has run on hardware
         return False
@@ -58,6 +97,14 @@ def linear_mx(x: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, kind: 
         r2 = None if residual is None else residual.reshape(-1, residual.shape[-1]).contiguous()
         y = _ext.ext().gemv_mx(x2.contiguous(), weight, scale, _FMT[kind], r2)
         return y.view(*x.shape[:-1], y.shape[-1])
+    if gemm_mx_eligible(x2, weight, scale, kind):
+        from ..quantization.microscaling.mx_torch import quantize_mxfp8
+
+        xq, xs = quantize_mxfp8(x2.contiguous())
+        y = matmul_mxfp8(xq, xs, weight, scale, "mxfp8", kind)
+        if residual is not None:
+            y = y + residual.reshape(-1, residual.shape[-1]).to(y.dtype)
+        return y.view(*x.shape[:-1], y.shape[-1]).to(x.dtype)
     w = dequantize(weight, scale, kind, x.dtype if x.dtype in (torch.bfloat16, torch.float16) else torch.float32)
     y = torch.nn.functional.linear(x.to(w.dtype), w)
     if residual is not None:

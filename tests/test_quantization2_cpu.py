@@ -387,3 +387,25 @@ def test_linear_mx_matches_mx_matmul_oracle():
         torch.testing.assert_close(gemm_mx.linear_mx(x, p, s, residual=r), want)
         torch.testing.assert_close(gemm_mx.linear_mx(x, p.view(torch.uint8), s, kind=kind, residual=r), want)
     assert not gemm_mx.gemv_eligible(x.reshape(-1, 96), p, s)            # CPU / opt-in flag unset
+
+
+def test_mx_scale_tiling_layout():
+    """``tile_scales``: byte (r % 32) * 16 + (r // 32) * 4 + j of chunk (row tile, K block of 128) = scale (r, j); padding = 2^0."""
+    import torch
+
+    from neuronx_distributed_b200.ops import gemm_mx
+
+    s = torch.arange(200 * 8, dtype=torch.int32).remainder(251).to(torch.uint8).reshape(200, 8)
+    t = gemm_mx.tile_scales(s)
+    assert t.shape == (2, 2, 512)
+    for r, kb in ((0, 0), (33, 5), (127, 7), (130, 2), (199, 4)):
+        rr = r % 128
+        assert t[r // 128, kb // 4, (rr % 32) * 16 + (rr // 32) * 4 + kb % 4] == s[r, kb]
+    assert (t[1, :, (100 % 32) * 16 + (100 // 32) * 4] == 127).all()      # row 228 does not exist: scale 1.0
+    # the oracle of the block-scaled GEMM is the plain product of the de-quantised operands
+    from neuronx_distributed_b200.quantization.microscaling.mx_torch import quantize_mxfp8
+
+    a, b = torch.randn(8, 64), torch.randn(5, 64)
+    (aq, asc), (bq, bsc) = quantize_mxfp8(a), quantize_mxfp8(b)
+    ref = gemm_mx.matmul_mxfp8_reference(aq, asc, bq, bsc)
+    assert ((ref - a @ b.t()).norm() / (a @ b.t()).norm()) < 0.08

@@ -265,3 +265,32 @@ def test_gemv_mx_matches_dequantised_reference():
                 print(kind, M, N, K, "rel err", err)
                 assert err < 1e-2, err
     """, env={"NXD_GEMV_MX": "1"})
+
+
+def test_block_scaled_mxfp8_gemm_matches_dequantised_reference():
+    """``tcgen05.mma.kind::mxf8f6f4.block_scale`` GEMM (scale chunks staged smem → TMEM with ``tcgen05.cp``) vs fp32 matmul on the
+    de-quantised operands; ragged M / N, several K, e4m3 and e5m2 weights."""
+    _run("""
+        import torch
+        from neuronx_distributed_b200.ops import gemm_mx
+        from neuronx_distributed_b200.quantization.microscaling.mx_torch import quantize_mxfp8
+        torch.manual_seed(0)
+        for M, N, K in ((128, 128, 128), (256, 384, 512), (1000, 264, 4096), (4096, 4096, 4096)):
+            for fp8 in (torch.float8_e4m3fn, torch.float8_e5m2):
+                a = torch.randn(M, K, device="cuda") * torch.rand(M, 1, device="cuda") * 4
+                b = torch.randn(N, K, device="cuda") * 0.1
+                aq, asc = quantize_mxfp8(a)
+                bq, bsc = quantize_mxfp8(b, fp8_dtype=fp8)
+                kind = "mxfp8" if fp8 == torch.float8_e4m3fn else "mxfp8_e5m2"
+                out = gemm_mx.matmul_mxfp8(aq, asc, bq, bsc, "mxfp8", kind)
+                ref = gemm_mx.matmul_mxfp8_reference(aq, asc, bq, bsc, "mxfp8", kind)
+                err = ((out.float() - ref).norm() / ref.norm()).item()
+                print(M, N, K, kind, "rel err", err)
+                assert err < 5e-3, err                      # products are exact in fp32; only the bf16 output rounds
+        # through the layer-level entry point (activations quantised online)
+        x = torch.randn(512, 1024, device="cuda").bfloat16(); w = torch.randn(768, 1024, device="cuda") * 0.05
+        wq, ws = quantize_mxfp8(w)
+        y = gemm_mx.linear_mx(x, wq, ws, kind="mxfp8")
+        ref = x.float() @ gemm_mx.dequantize(wq, ws, "mxfp8").t()
+        assert ((y.float() - ref).norm() / ref.norm()).item() < 5e-2          # + MXFP8 rounding of the activations
+    """, env={"NXD_GEMM_MX": "1"}, timeout=420)
