@@ -14,8 +14,26 @@ pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="written a
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
+# A kernel that has never run may hang: every check is bounded (subprocess timeout) and the whole file has a time budget, after
+# which the remaining checks are skipped — the validated part of the GPU suite (all files before this one) is never at risk.
+_BUDGET_S = float(os.environ.get("NXD_LATE_GPU_BUDGET_S", "600"))
+_PER_TEST_S = 150
+_spent = [0.0]
 
-def _run(code: str, timeout: int = 300, env=None) -> None:
+
+@pytest.fixture(autouse=True)
+def _time_budget():
+    import time
+
+    if _spent[0] > _BUDGET_S:
+        pytest.skip(f"time budget of the late GPU checks ({_BUDGET_S:.0f} s) is used up")
+    t0 = time.time()
+    yield
+    _spent[0] += time.time() - t0
+
+
+def _run(code: str, timeout: int = _PER_TEST_S, env=None) -> None:
+    timeout = min(timeout, _PER_TEST_S)
     e = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     e.update(env or {})
     p = subprocess.run([sys.executable, "-c", textwrap.dedent(code)], cwd=ROOT, env=e, timeout=timeout,
@@ -204,7 +222,7 @@ def test_embedding_gather_over_peer_memory_loopback():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from dist_utils import run_distributed
 
-    run_distributed(_embedding_gather_loopback, 2, use_cuda="loopback", timeout=240)
+    run_distributed(_embedding_gather_loopback, 2, use_cuda="loopback", timeout=_PER_TEST_S)
 
 
 def _all_to_all_loopback(rank, world):
@@ -238,7 +256,7 @@ def test_all_to_all_over_peer_memory_loopback():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from dist_utils import run_distributed
 
-    run_distributed(_all_to_all_loopback, 2, use_cuda="loopback", timeout=240)
+    run_distributed(_all_to_all_loopback, 2, use_cuda="loopback", timeout=_PER_TEST_S)
 
 
 def test_gemv_mx_matches_dequantised_reference():
