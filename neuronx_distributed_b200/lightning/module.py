@@ -24,6 +24,7 @@ class NeuronLTModule(LightningModule):
         self.scheduler_args, self.scheduler_kwargs = scheduler_args, scheduler_kwargs or {}
         self.grad_accum_steps, self.train_batch_size, self.logging_interval = grad_accum_steps, train_batch_size, logging_interval
         self.automatic_optimization = not manual_opt
+        self.log_rank0 = log_rank0
         self.model = None
         self.averaged_loss = torch.zeros(())
         self._micro = 0
@@ -67,6 +68,46 @@ class NeuronLTModule(LightningModule):
 
     def forward(self, *a, **k):
         return self.model(*a, **k)
+
+    # ---- logging (reference :141-313 overrides ``LightningModule.log`` for device tensors and rank filtering) -------------
+    @staticmethod
+    def _to_tensor(value, name: str) -> torch.Tensor:
+        if isinstance(value, torch.Tensor):
+            if value.numel() != 1:
+                raise ValueError(f"`self.log({name}, {value})` was called, but the tensor must have a single element.")
+            return value.detach().reshape(())
+        if isinstance(value, bool) or not isinstance(value, (int, float)):
+            raise ValueError(f"`self.log({name}, {value!r})` was called, but `{type(value).__name__}` values cannot be logged.")
+        return torch.tensor(float(value))
+
+    def log(self, name: str, value, prog_bar: bool = False, logger: Optional[bool] = None, on_step: Optional[bool] = None,
+            on_epoch: Optional[bool] = None, reduce_fx="mean", sync_dist: bool = False, rank_zero_only: bool = False,
+            batch_size: Optional[int] = None, **kwargs) -> None:
+        """Record a scalar metric.  ``log_rank0`` (constructor) / ``rank_zero_only`` keep non-zero ranks silent; ``sync_dist``
+        averages over the data-parallel replicas through the strategy; values stay on their device (no ``.item()`` in the
+        step — the trainer / logger reads them at its logging interval)."""
+        if not isinstance(name, str):
+            raise TypeError(f"metric names must be strings, got {type(name).__name__}")
+        if isinstance(value, dict):
+            raise ValueError(f"`self.log({name}, {value})` was called, but nested dictionaries cannot be logged; use log_dict")
+        v = self._to_tensor(value, name)
+        strategy = getattr(getattr(self, "trainer", None), "strategy", None)
+        if sync_dist and strategy is not None and hasattr(strategy, "reduce"):
+            v = strategy.reduce(v, reduce_op=reduce_fx if isinstance(reduce_fx, str) else "mean")      # collective: every rank
+        if (self.log_rank0 or rank_zero_only) and torch.distributed.is_initialized() and torch.distributed.get_rank() != 0:
+            return
+        from ._compat import HAVE_LIGHTNING
+
+        if HAVE_LIGHTNING and getattr(self, "_trainer", None) is not None:      # pragma: no cover - needs the lightning wheel
+            return super().log(name, v, prog_bar=prog_bar, logger=logger, on_step=on_step, on_epoch=on_epoch, reduce_fx=reduce_fx,
+                               sync_dist=False, rank_zero_only=rank_zero_only, batch_size=batch_size, **kwargs)
+        self._logged[name] = v
+        if prog_bar:
+            self.__dict__.setdefault("_progress_bar_metrics", {})[name] = v
+
+    def log_dict(self, dictionary: Dict[str, Any], **kwargs) -> None:
+        for k, v in dictionary.items():
+            self.log(k, v, **kwargs)
 
     # ---- hooks Lightning calls that the NxD wrappers already cover (reference :89-139) ---------------------------------
     def configure_gradient_clipping(self, *args, **kwargs) -> None:

@@ -44,11 +44,71 @@ class NxDStrategy(_BaseStrategy):
     def is_global_zero(self) -> bool:
         return (dist.get_rank() if dist.is_initialized() else 0) == 0
 
+    def _configure_launcher(self) -> None:
+        from .launcher import _NeuronXLALauncher
+
+        self._launcher = _NeuronXLALauncher(self)
+
+    @property
+    def root_device(self) -> torch.device:
+        from ..utils import get_device
+
+        return get_device()
+
+    def model_to_device(self) -> None:
+        """The NxD model is built on its device by ``initialize_parallel_model`` (meta-init + per-stage materialisation):
+        nothing to move, like the reference (:131-133)."""
+
+    def batch_to_device(self, batch: Any, device: Optional[torch.device] = None, dataloader_idx: int = 0) -> Any:
+        from ..utils.device_loader import _map
+
+        dev = device or self.root_device
+        return _map(batch, lambda t: t.to(dev, non_blocking=True))
+
+    def process_dataloader(self, dataloader):
+        """Wrap the host dataloader in the device prefetcher (reference :201-218 wraps it in ``MpDeviceLoader``)."""
+        from ..utils.device_loader import DevicePrefetchLoader
+
+        return dataloader if isinstance(dataloader, DevicePrefetchLoader) else DevicePrefetchLoader(dataloader, self.root_device)
+
     def broadcast(self, obj, src: int = 0):
         return obj          # all ranks construct identical objects from the same seed/config
 
-    def reduce(self, tensor, *a, **k):
-        return tensor       # losses are already averaged over DP by the model/optimizer wrappers
+    def reduce(self, tensor, group: Optional[Any] = None, reduce_op: Optional[Any] = "mean"):
+        """Metric reduction across DATA-parallel replicas (TP / PP ranks of one replica hold the same value): ``mean`` /
+        ``avg`` / ``sum``; non-tensors and single-replica runs pass through (reference :159-199)."""
+        if not isinstance(tensor, torch.Tensor) or not dist.is_initialized() or not ps.model_parallel_is_initialized():
+            return tensor
+        n = ps.get_data_parallel_size()
+        if n == 1:
+            return tensor
+        op = str(reduce_op).lower() if reduce_op is not None else "sum"
+        if op not in ("mean", "avg", "sum", "reduceop.sum", "reduceop.avg"):
+            raise ValueError(f"unsupported reduce_op {reduce_op!r}: use 'mean' / 'avg' / 'sum'")
+        out = tensor.detach().clone().float()
+        dist.all_reduce(out, group=group if group is not None else ps.get_data_parallel_group())
+        if op in ("mean", "avg", "reduceop.avg"):
+            out = out / n
+        return out.to(tensor.dtype)
+
+    # ---- checkpoints go through NeuronCheckpointIO (reference :220-238) ---------------------------------------------------
+    @property
+    def checkpoint_io(self):
+        if getattr(self, "_ckpt_io", None) is None:
+            from .checkpoint_io import NeuronCheckpointIO
+
+            self._ckpt_io = NeuronCheckpointIO(save_load_xser=self.save_load_xser)
+        return self._ckpt_io
+
+    @checkpoint_io.setter
+    def checkpoint_io(self, io) -> None:
+        self._ckpt_io = io
+
+    def save_checkpoint(self, checkpoint: Dict[str, Any], filepath: str, storage_options: Optional[Any] = None) -> None:
+        self.checkpoint_io.save_checkpoint(checkpoint, filepath, storage_options)
+
+    def load_checkpoint(self, checkpoint_path: str, **kwargs) -> Any:
+        return self.checkpoint_io.load_checkpoint(checkpoint_path, **kwargs)
 
     def barrier(self, name: Optional[str] = None) -> None:
         if dist.is_initialized():

@@ -81,6 +81,8 @@ class Trainer:
         self._call("setup", "fit")
         self._call("on_train_start")
         device = get_device()
+        if self.strategy is not None and hasattr(self.strategy, "process_dataloader"):
+            train_dataloaders = self.strategy.process_dataloader(train_dataloaders)      # pinned, prefetched H2D copies
         done = False
         while not done and self.current_epoch < self.max_epochs:
             for batch_idx, batch in enumerate(train_dataloaders):

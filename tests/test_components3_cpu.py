@@ -193,3 +193,65 @@ def _fused_block(rank, world):
 
 def test_llama_block_with_fused_add_norm():
     run_distributed(_fused_block, 2, timeout=120)
+
+
+def _lightning_strategy(rank, world, tmp):
+    """Strategy surface of the reference (``lightning/strategy.py:84-238``): DP-only metric reduction, batch / dataloader
+    placement, checkpoint routing; ``NeuronLTModule.log`` validation and rank filtering; the device prefetch loader."""
+    import pytest
+
+    from neuronx_distributed_b200.lightning import NeuronLTModule, NeuronXLAStrategy, NxDStrategy
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.trainer import neuronx_distributed_config
+    from neuronx_distributed_b200.utils.device_loader import DevicePrefetchLoader, MpDeviceLoader
+
+    assert NeuronXLAStrategy is NxDStrategy and MpDeviceLoader is DevicePrefetchLoader
+    cfg = neuronx_distributed_config(tensor_parallel_size=2)
+    st = NxDStrategy(nxd_config=cfg)
+    st.setup_distributed()                                            # world 4 = TP 2 × DP 2
+    assert ps.get_data_parallel_size() == 2 and st.distributed_sampler_kwargs == {"num_replicas": 2, "rank": ps.get_data_parallel_rank()}
+    v = torch.tensor(float(ps.get_data_parallel_rank() + 1))
+    torch.testing.assert_close(st.reduce(v, reduce_op="mean"), torch.tensor(1.5))       # over DP replicas only
+    torch.testing.assert_close(st.reduce(v, reduce_op="sum"), torch.tensor(3.0))
+    assert st.reduce("text") == "text"
+    with pytest.raises(ValueError):
+        st.reduce(v, reduce_op="max")
+    b = st.batch_to_device({"a": torch.ones(2), "b": [torch.zeros(1), 3]})
+    assert b["a"].device == st.root_device and b["b"][1] == 3
+    data = [{"x": torch.full((2,), float(i))} for i in range(5)]
+    dl = st.process_dataloader(data)
+    assert isinstance(dl, DevicePrefetchLoader) and st.process_dataloader(dl) is dl and len(dl) == 5
+    assert [float(d["x"][0]) for d in dl] == [0.0, 1.0, 2.0, 3.0, 4.0]                    # order kept, nothing dropped
+    st.model_to_device()
+    st._configure_launcher()
+    assert st._launcher.launch(lambda a: a + 1, 1) == 2
+    # checkpoint routing: strategy → NeuronCheckpointIO → nxd.save_checkpoint layout
+    lin = torch.nn.Linear(4, 4)
+    st.save_checkpoint({"state_dict": lin, "global_step": 7}, f"{tmp}/ck/step_7")
+    user = st.load_checkpoint(f"{tmp}/ck/step_7", model=lin)
+    assert int(user["global_step"]) == 7
+    # log(): scalar tensors / numbers only, rank filtering, DP sync through the strategy
+    mod = NeuronLTModule(cfg, lambda: lin, torch.optim.SGD, log_rank0=True)
+
+    class T:
+        strategy = st
+
+    mod.trainer = T()
+    mod.log("m", v, sync_dist=True, prog_bar=True)
+    if rank == 0:
+        torch.testing.assert_close(mod._logged["m"], torch.tensor(1.5))
+        assert "m" in mod._progress_bar_metrics
+    else:
+        assert "m" not in mod._logged                                  # log_rank0
+    for bad in (torch.ones(2), "s", True, None):
+        with pytest.raises(ValueError):
+            mod.log("bad", bad)
+    with pytest.raises(ValueError):
+        mod.log("nested", {"a": 1})
+    with pytest.raises(TypeError):
+        mod.log(3, 1.0)
+    st.teardown()
+
+
+def test_lightning_strategy_surface_and_logging(tmp_path):
+    run_distributed(_lightning_strategy, 4, str(tmp_path), timeout=180)
