@@ -46,9 +46,13 @@ from ..utils.plan_registry import active_recorder, plan_op, recording, set_recor
 
 # extension entry points that take raw peer pointers / epochs: only legal inside a plan_op
 _EXT_RESOURCE_PREFIXES = ("vmm_", "symm_", "tp_gemm", "nvls_", "gemv_allreduce", "zero1_", "oneshot_", "allreduce_")
-# extension entry points known to have no side effect besides their return values are all the others: kernels allocate
-# their outputs.  The exceptions write into a tensor argument:
-_EXT_MUTATING = ("decode_rope_kv", "kv_append", "adamw", "multi_tensor", "gemm_accumulate", "copy_into")
+# Extension entry points that allocate their results and write to none of their arguments.  Everything else (``gemm_bf16`` /
+# ``grouped_gemm`` with an ``out`` argument, ``decode_rope_kv`` appending to the cache, optimizer kernels …) is treated as
+# writing to EVERY tensor argument: conservative — such tensors count as state, are never hoisted or dropped — but safe.
+_EXT_PURE = frozenset({"rmsnorm_fwd", "rmsnorm_bwd", "add_rmsnorm_fwd", "add_rmsnorm_bwd", "swiglu_fwd", "swiglu_bwd", "rope_apply",
+                       "ce_stats", "ce_backward", "decode_attention", "decode_attention_partial", "gemv", "gemv_mx",
+                       "gemm_mxfp8", "moe_block_tkg", "moe_block_metadata", "row_argmax", "row_topk", "flash_attn_fwd",
+                       "flash_attn_bwd", "moe_block_tkg_supported", "row_topk_supported"})
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -674,7 +678,7 @@ class _Recorder(TorchDispatchMode):
             pure = _PY_OPS[name][1]
             self.py_modules.add(fn.__module__)
         else:
-            pure = not any(m in name for m in _EXT_MUTATING)
+            pure = name in _EXT_PURE
         # anything not declared pure may write into any tensor argument
         mutates = [] if pure else sorted({self.by_pyid[id(t)] for t in in_tensors})
         self.nodes.append(Node(kind, name, {"l": enc_a}, {"d": enc_k}, outs, mutates, pure, alias))
