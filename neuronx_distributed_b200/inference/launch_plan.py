@@ -52,7 +52,10 @@ _EXT_RESOURCE_PREFIXES = ("vmm_", "symm_", "tp_gemm", "nvls_", "gemv_allreduce",
 _EXT_PURE = frozenset({"rmsnorm_fwd", "rmsnorm_bwd", "add_rmsnorm_fwd", "add_rmsnorm_bwd", "swiglu_fwd", "swiglu_bwd", "rope_apply",
                        "ce_stats", "ce_backward", "decode_attention", "decode_attention_partial", "gemv", "gemv_mx",
                        "gemm_mxfp8", "moe_block_tkg", "moe_block_metadata", "row_argmax", "row_topk", "flash_attn_fwd",
-                       "flash_attn_bwd", "moe_block_tkg_supported", "row_topk_supported"})
+                       "flash_attn_bwd", "moe_block_tkg_supported", "row_topk_supported", "grouped_gemm"})
+# … and the ones that write exactly these positional arguments (everything else they take is read-only)
+_EXT_WRITES = {"gemm_bf16": (2,), "gemm_bf16_2cta": (2,), "gemm_fp8": (2,), "grouped_wgrad": (2,), "decode_rope_kv": (6, 7),
+               "multi_tensor_sq_norm": (1,)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -679,8 +682,13 @@ class _Recorder(TorchDispatchMode):
             self.py_modules.add(fn.__module__)
         else:
             pure = name in _EXT_PURE
-        # anything not declared pure may write into any tensor argument
-        mutates = [] if pure else sorted({self.by_pyid[id(t)] for t in in_tensors})
+        if kind == "ext" and name in _EXT_WRITES:
+            pure = True                                            # no effect besides the listed arguments and the results
+            mutates = sorted({self.by_pyid[id(t)] for i in _EXT_WRITES[name] if i < len(args)
+                              for t in _flat_tensors(args[i], []) if t is not None})
+        else:
+            # anything not declared pure may write into any tensor argument
+            mutates = [] if pure else sorted({self.by_pyid[id(t)] for t in in_tensors})
         self.nodes.append(Node(kind, name, {"l": enc_a}, {"d": enc_k}, outs, mutates, pure, alias))
         return out
 
