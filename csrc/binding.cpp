@@ -673,6 +673,19 @@ static void nvls_all_gather(const Tensor& x, const c10::optional<Tensor>& out, c
   nxd::nvls_all_gather(x.data_ptr(), out ? out->data_ptr() : nullptr, peer_bases.data_ptr<int64_t>(), mc_base, local_base, flag_off,
                        data_off, half_bytes, (uint32_t*)state.data_ptr(), (int)rank, (int)world, bytes, (int)ctas, stream());
 }
+static void nvls_publish(const Tensor& x, const Tensor& peer_bases, int64_t mc_base, int64_t local_base, int64_t flag_off,
+                         int64_t data_off, int64_t half_bytes, Tensor state, int64_t rank, int64_t world, int64_t parity, int64_t ctas) {
+  CHECK_IN(x);
+  c10::cuda::CUDAGuard guard(x.device());
+  nxd::nvls_publish(x.data_ptr(), peer_bases.data_ptr<int64_t>(), mc_base, local_base, flag_off, data_off, half_bytes,
+                    (uint32_t*)state.data_ptr(), (int)rank, (int)world, x.numel() * x.element_size(), (int)parity, (int)ctas, stream());
+}
+// A tensor over memory this process has mapped (a peer's symmetric slot): the caller guarantees the mapping outlives the view.
+static Tensor ptr_view(int64_t ptr, const std::vector<int64_t>& shape, py::object dtype) {
+  auto st = torch::python::detail::py_object_to_dtype(dtype);
+  int dev; cudaGetDevice(&dev);
+  return at::from_blob(reinterpret_cast<void*>(ptr), shape, at::TensorOptions().dtype(st).device(at::kCUDA, dev));
+}
 // x = [world, chunk…] contiguous: chunk p goes to rank p; returns [world, chunk…] with chunk p received from rank p
 static Tensor nvls_all_to_all(const Tensor& x, const Tensor& peer_bases, int64_t mc_base, int64_t local_base, int64_t flag_off,
                               int64_t data_off, int64_t half_bytes, Tensor state, int64_t rank, int64_t world, int64_t ctas) {
@@ -728,6 +741,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_attention", &decode_attention);
   m.def("decode_attention_partial", &decode_attention_partial);
   m.def("nvls_embedding_gather", &nvls_embedding_gather);
+  m.def("nvls_publish", &nvls_publish);
+  m.def("ptr_view", &ptr_view);
   m.def("nvls_all_to_all", &nvls_all_to_all);
   m.def("gemv_mx", &gemv_mx);
   m.def("gemm_mxfp8", &gemm_mxfp8);

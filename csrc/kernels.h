@@ -78,6 +78,8 @@ void nvls_all_gather(const void* x, void* out, const int64_t* peer_bases, int64_
                      long data_off, long half_bytes, uint32_t* state, int rank, int world, long bytes, int ctas, cudaStream_t st);
 void nvls_all_to_all(const void* x, void* out, const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off,
                      long data_off, long half_bytes, uint32_t* state, int rank, int world, long bytes, int ctas, cudaStream_t st);
+void nvls_publish(const void* x, const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off, long data_off,
+                  long half_bytes, uint32_t* state, int rank, int world, long bytes, int parity, int ctas, cudaStream_t st);
 void nvls_embedding_gather(const void* table, const long* ids, void* out, const int64_t* peer_bases, int64_t mc_base,
                            int64_t local_base, long flag_off, long data_off, long half_bytes, uint32_t* state, int rank, int world,
                            long rows_per_rank, long row_bytes, long ntok, int ctas, cudaStream_t st);

@@ -314,9 +314,11 @@ __global__ void __launch_bounds__(256) gemv_allreduce_kernel(const __nv_bfloat16
 //   2. peer_row_gather_kernel   one warp per token of THIS rank's sequence shard loads the row from the owner's slot over
 //                               NVLink (16-byte loads) and stores it locally.  No reduction, S/tp·B·H elements moved once.
 __global__ void __launch_bounds__(512) nvls_publish_kernel(const uint8_t* __restrict__ x, NvlsRegion r, uint32_t* __restrict__ state,
-                                                           long bytes) {
+                                                           long bytes, int forced_parity) {
+  // forced_parity >= 0: the host chose the half (it needs the address to build views / TMA maps of the peers' copies);
+  // otherwise the half follows the device-side call counter (CUDA-graph capturable)
   const uint32_t epoch = ld_acquire_sys(state) + 1u;
-  const long base = r.data_off + (long)(epoch & 1u) * r.half_bytes;
+  const long base = r.data_off + (long)(forced_parity >= 0 ? (uint32_t)forced_parity : (epoch & 1u)) * r.half_bytes;
   const long nvec = bytes / 16;
   const long per_cta = (nvec + gridDim.x - 1) / gridDim.x;
   const long v0 = (long)blockIdx.x * per_cta, v1 = min(nvec, v0 + per_cta);
@@ -457,8 +459,19 @@ void nvls_all_to_all(const void* x, void* out, const int64_t* peer_bases, int64_
   if (ctas > kNvlsCollMaxCtas) ctas = kNvlsCollMaxCtas;
   if (bytes % (16L * world) || bytes > half_bytes) nxd_throw("nvls_all_to_all: per-peer chunks of 16-byte multiples, buffer must fit the slot", __FILE__, __LINE__);
   const NvlsRegion r = make_region(peer_bases, mc_base, local_base, flag_off, data_off, half_bytes, rank, world);
-  nvls_publish_kernel<<<ctas, 512, 0, st>>>((const uint8_t*)x, r, state, bytes);
+  nvls_publish_kernel<<<ctas, 512, 0, st>>>((const uint8_t*)x, r, state, bytes, -1);
   peer_chunk_pull_kernel<<<ctas, 512, 0, st>>>((uint8_t*)out, r, state, bytes / world);
+  NXD_CUDA_CHECK(cudaGetLastError());
+}
+
+// Copy `x` into this rank's half `parity` of the slot and meet every rank: after the kernel, every peer's copy can be read at
+// peer_base + data_off + parity * half_bytes (e.g. by the attention kernel's TMA loads: context-parallel attention without a ring).
+void nvls_publish(const void* x, const int64_t* peer_bases, int64_t mc_base, int64_t local_base, long flag_off, long data_off,
+                  long half_bytes, uint32_t* state, int rank, int world, long bytes, int parity, int ctas, cudaStream_t st) {
+  if (ctas > kNvlsCollMaxCtas) ctas = kNvlsCollMaxCtas;
+  if (bytes % 16 || bytes > half_bytes) nxd_throw("nvls_publish: multiple of 16 bytes that fits the slot", __FILE__, __LINE__);
+  const NvlsRegion r = make_region(peer_bases, mc_base, local_base, flag_off, data_off, half_bytes, rank, world);
+  nvls_publish_kernel<<<ctas, 512, 0, st>>>((const uint8_t*)x, r, state, bytes, parity);
   NXD_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -469,7 +482,7 @@ void nvls_embedding_gather(const void* table, const long* ids, void* out, const 
   const long bytes = rows_per_rank * row_bytes;
   if (row_bytes % 16 || bytes > half_bytes) nxd_throw("nvls_embedding_gather: rows of 16-byte multiples, shard must fit the slot", __FILE__, __LINE__);
   const NvlsRegion r = make_region(peer_bases, mc_base, local_base, flag_off, data_off, half_bytes, rank, world);
-  nvls_publish_kernel<<<ctas, 512, 0, st>>>((const uint8_t*)table, r, state, bytes);
+  nvls_publish_kernel<<<ctas, 512, 0, st>>>((const uint8_t*)table, r, state, bytes, -1);
   NXD_CUDA_CHECK(cudaGetLastError());
   if (ntok > 0) {
     const int grid = (int)std::min<long>((ntok + 7) / 8, 148L * 8);

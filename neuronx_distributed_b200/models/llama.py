@@ -142,9 +142,9 @@ class LlamaAttention(nn.Module):
         q = ops.rope.apply_rotary(q, cos, sin)
         k = ops.rope.apply_rotary(k, cos, sin)
         if self.cfg.context_parallel and ps.get_context_model_parallel_size() > 1:
-            from ..modules.attention.ring import ring_attention
+            from ..modules.attention.ring import pull_attention, ring_attention
 
-            o = ring_attention(q, k, v, causal=True)
+            o = (pull_attention if _CP_PULL else ring_attention)(q, k, v, causal=True)
         else:
             o = ops.attention.flash_attention(q, k, v, causal=True)
         o = o.transpose(0, 1).reshape(S, B, self.num_heads_local * self.head_dim)
@@ -159,6 +159,9 @@ _FUSED_ADD_NORM = os.environ.get("NXD_FUSED_ADD_NORM", "1") == "1"
 # ``fused_linear_cross_entropy``).  Opt-in: CPU-verified against the unfused path, not yet timed on hardware.
 _FUSED_LMHEAD_CE = os.environ.get("NXD_FUSED_LMHEAD_CE", "0") == "1"
 _LMHEAD_CE_CHUNK = int(os.environ.get("NXD_LMHEAD_CE_CHUNK", "2048"))
+# context parallelism without a ring: K/V published in symmetric memory, peers' slices read inside the attention kernel
+# (modules/attention/ring.py ``pull_attention``).  Opt-in: CPU-verified against the ring and dense attention only.
+_CP_PULL = os.environ.get("NXD_CP_PULL", "0") == "1"
 
 
 class LlamaDecoderLayer(nn.Module):

@@ -105,3 +105,110 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
     # every ring-shift backward, otherwise its neighbours would wait forever for the matching exchange
     out = out + 0.0 * last_kv.float().sum()
     return out.to(q.dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Context-parallel attention WITHOUT a ring: every rank publishes its K/V slice in NVSwitch-visible symmetric memory and
+# the attention kernels read the other ranks' slices where they are (TMA loads over NVLink inside the kernel) — the
+# K/V "rotation" of the reference's ring kernels (K3/K4, kernels/ring_attention_kernel.py:118-167) happens inside the
+# attention kernel, and there are no ring steps to serialise on.  Backward re-publishes K/V, computes every block's
+# (dQ, dK, dV) from the GLOBAL softmax statistics (so no per-block LSE gradients are needed) and returns the dK/dV
+# contributions to their owners with ONE reduce-scatter (in-switch sum on NVLS).
+# ---------------------------------------------------------------------------------------------------------------------
+def _block_backward(q, k, v, out, lse, dout, causal: bool, scale: float):
+    """Gradients of one K/V block given the GLOBAL output ``out`` / log-normaliser ``lse`` of the rows:
+    P = exp(S − lse), dV = Pᵀ dO, dS = P ∘ (dO Vᵀ − rowsum(dO ∘ out)), dQ = dS K · scale, dK = dSᵀ Q · scale."""
+    if q.is_cuda:
+        from ... import ops
+
+        e = ops._ext.ext()
+        if (e is not None and hasattr(e, "flash_attn_bwd") and q.dtype == torch.bfloat16 and q.shape[-1] == 128
+                and (not causal or q.shape[1] == k.shape[1])):
+            ops._ext.count_launch(4)
+            tv = ops.attention._tma_view
+            dq, dk, dv = e.flash_attn_bwd(tv(dout.to(out.dtype)), tv(q), tv(k), tv(v), tv(out), lse.contiguous(), bool(causal),
+                                          float(scale), False, None)
+            return dq, dk, dv
+    hq, hkv = q.shape[2], k.shape[2]
+    g = hq // hkv
+    qt, dot, ot = q.transpose(1, 2).float(), dout.transpose(1, 2).float(), out.transpose(1, 2).float()     # [B,H,S,D]
+    kt, vt = k.transpose(1, 2).float().repeat_interleave(g, 1), v.transpose(1, 2).float().repeat_interleave(g, 1)
+    s = torch.matmul(qt, kt.transpose(-1, -2)) * scale
+    if causal:
+        sq, sk = s.shape[-2], s.shape[-1]
+        s = s.masked_fill(~torch.ones(sq, sk, dtype=torch.bool, device=s.device).tril(diagonal=sk - sq), float("-inf"))
+    p = torch.exp(s - lse.unsqueeze(-1))
+    dv = torch.matmul(p.transpose(-1, -2), dot)
+    ds = p * (torch.matmul(dot, vt.transpose(-1, -2)) - (dot * ot).sum(-1, keepdim=True))
+    dq = torch.matmul(ds, kt) * scale
+    dk = torch.matmul(ds.transpose(-1, -2), qt) * scale
+    B, _, Sk, D = dk.shape
+    dk, dv = dk.view(B, hkv, g, Sk, D).sum(2), dv.view(B, hkv, g, Sk, D).sum(2)
+    return dq.transpose(1, 2).to(q.dtype), dk.transpose(1, 2).to(k.dtype), dv.transpose(1, 2).to(v.dtype)
+
+
+class _PullAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, causal, scale, group):
+        from ... import ops
+
+        cp, r = dist.get_world_size(group), dist.get_rank(group)
+        kv = torch.stack([k, v]).contiguous()                        # one slot per rank: [2, B, S/cp, Hkv, D]
+        views = ops.nvls.publish(kv, group)
+        out = lse = None
+        with torch.no_grad():
+            for step in range(cp):
+                src = (r - step) % cp                                # own block first, then the nearest earlier ranks
+                if causal and src > r:
+                    continue
+                o_b, lse_b = block_attention(q, views[src][0], views[src][1], causal and src == r, scale)
+                if out is None:
+                    out, lse = o_b.float(), lse_b.float()
+                else:
+                    new = torch.logaddexp(lse, lse_b)
+                    out = out * torch.exp(lse - new).transpose(1, 2).unsqueeze(-1) + \
+                        o_b.float() * torch.exp(lse_b - new).transpose(1, 2).unsqueeze(-1)
+                    lse = new
+        out = out.to(q.dtype)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.causal, ctx.scale, ctx.group = causal, scale, group
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from ... import ops
+        from ...parallel_layers import comm
+
+        q, k, v, out, lse = ctx.saved_tensors
+        group, causal, scale = ctx.group, ctx.causal, ctx.scale
+        cp, r = dist.get_world_size(group), dist.get_rank(group)
+        views = ops.nvls.publish(torch.stack([k, v]).contiguous(), group)          # peers' K/V again (the slot was reused since)
+        dq = torch.zeros_like(q, dtype=torch.float32)
+        dkv = torch.zeros((cp,) + tuple(views[r].shape), dtype=torch.float32, device=q.device)      # [cp, 2, B, S/cp, Hkv, D]
+        dout = dout.contiguous()
+        for step in range(cp):
+            src = (r - step) % cp
+            if causal and src > r:
+                continue
+            dq_b, dk_b, dv_b = _block_backward(q, views[src][0], views[src][1], out, lse, dout, causal and src == r, scale)
+            dq += dq_b.float()
+            dkv[src, 0], dkv[src, 1] = dk_b.float(), dv_b.float()
+        # every rank holds its contributions to ALL blocks; each owner needs the sum over ranks of its own block
+        flat = dkv.reshape(cp * dkv[0].numel() // dkv.shape[-1], dkv.shape[-1])
+        if flat.is_cuda and ops.nvls.available(group) and ops.nvls.has_multicast(group):
+            mine = ops.nvls.reduce_scatter_sum(flat, group)
+        else:
+            mine = comm.reduce_scatter(flat, dim=0, group=group)
+        mine = mine.view(dkv.shape[1:])
+        return dq.to(q.dtype), mine[0].to(k.dtype), mine[1].to(v.dtype), None, None, None
+
+
+def pull_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True, scale: Optional[float] = None,
+                   group=None) -> torch.Tensor:
+    """Same contract as :func:`ring_attention` (``[B, S/cp, H, D]`` slices in, local output out), no ring: see the section
+    comment above.  Opt-in from the models with ``NXD_CP_PULL=1`` until the symmetric-memory path has run on hardware."""
+    group = group if group is not None else ps.get_context_model_parallel_group()
+    scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
+    if dist.get_world_size(group) == 1:
+        return block_attention(q, k, v, causal, scale)[0]
+    return _PullAttention.apply(q, k, v, causal, scale, group)

@@ -157,3 +157,26 @@ def all_to_all_eligible(x: torch.Tensor, group) -> bool:
     world = dist.get_world_size(group)
     return (x.is_cuda and x.dim() >= 1 and x.shape[0] % world == 0 and (x.numel() * x.element_size()) % (16 * world) == 0
             and x.numel() > 0 and available() and hasattr(_ext.ext(), "nvls_all_to_all"))
+
+
+def publish(x: torch.Tensor, group, ctas: int = 64):
+    """Make ``x`` readable by every rank of ``group``: returns one tensor per rank, entry ``p`` viewing rank ``p``'s ``x``.
+    CUDA: ``x`` is copied into this rank's symmetric slot (halves alternate per call), all ranks meet, and the returned
+    tensors are VIEWS of the peers' slots — a kernel that takes them (e.g. flash attention, through TMA) loads straight over
+    NVLink.  They stay valid until the second next ``publish`` on the same group.  The half is chosen on the host (the
+    addresses are needed to build the views), so a call is not CUDA-graph capturable.  CPU: an all-gather."""
+    world = dist.get_world_size(group)
+    if not (x.is_cuda and _ext.use_cuda(x) and hasattr(_ext.ext(), "nvls_publish") and available()):
+        from ..parallel_layers import comm
+
+        full = comm.all_gather(x.contiguous().unsqueeze(0), dim=0, group=group) if world > 1 else x.unsqueeze(0)
+        return list(full.unbind(0))
+    nbytes = x.numel() * x.element_size()
+    c = _coll(group, "publish", nbytes, 64)
+    calls = getattr(c, "calls", 0)
+    c.calls = calls + 1
+    parity = calls & 1
+    _ext.count_launch()
+    _ext.ext().nvls_publish(x.contiguous(), *c.args, parity, int(ctas))
+    off = _FLAG_BYTES + parity * c.half_bytes
+    return [_ext.ext().ptr_view(int(p) + off, list(x.shape), x.dtype) for p in c.ws.ptr_list]

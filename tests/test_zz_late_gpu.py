@@ -312,3 +312,48 @@ def test_block_scaled_mxfp8_gemm_matches_dequantised_reference():
         ref = x.float() @ gemm_mx.dequantize(wq, ws, "mxfp8").t()
         assert ((y.float() - ref).norm() / ref.norm()).item() < 5e-2          # + MXFP8 rounding of the activations
     """, env={"NXD_GEMM_MX": "1"}, timeout=420)
+
+
+def _pull_attention_loopback(rank, world):
+    import math
+
+    import torch
+    import torch.distributed as dist
+
+    from neuronx_distributed_b200.modules.attention.ring import pull_attention
+    from neuronx_distributed_b200.ops import _ext
+
+    g = dist.group.WORLD
+    B, S, H, Hkv, D = 1, 512, 4, 2, 128
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    q, k, v = (torch.randn(B, S, h, D, device="cuda", generator=gen).bfloat16() for h in (H, Hkv, Hkv))
+    go = torch.randn(B, S, H, D, device="cuda", generator=gen).bfloat16()
+    sl = slice(rank * S // world, (rank + 1) * S // world)
+    for it in range(2):                                     # both halves of the publish slot
+        ql, kl, vl = (t[:, sl].clone().requires_grad_(True) for t in (q, k, v))
+        n0 = _ext.launches()
+        out = pull_attention(ql, kl, vl, causal=True, group=g)
+        assert _ext.launches() > n0                         # publish + tcgen05 attention kernels, not the SDPA fallback
+        out.backward(go[:, sl])
+        qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+        s = torch.einsum("bqhd,bkhd->bhqk", qf, kf.repeat_interleave(H // Hkv, 2)) / math.sqrt(D)
+        s = s.masked_fill(~torch.ones(S, S, dtype=torch.bool, device="cuda").tril(), float("-inf"))
+        ref = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), vf.repeat_interleave(H // Hkv, 2))
+        ref.backward(go.float())
+
+        def rel(a, b):
+            return float((a.float() - b).norm() / b.norm())
+
+        errs = (rel(out, ref[:, sl]), rel(ql.grad, qf.grad[:, sl]), rel(kl.grad, kf.grad[:, sl]), rel(vl.grad, vf.grad[:, sl]))
+        assert max(errs) < 2e-2, errs
+
+
+def test_pull_attention_reads_peer_kv_inside_the_kernel_loopback():
+    """Context parallelism without a ring: K/V published in symmetric memory, the flash-attention kernels' TMA loads read the
+    other process's slice in place; dK/dV return through one reduce-scatter."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from dist_utils import run_distributed
+
+    run_distributed(_pull_attention_loopback, 2, use_cuda="loopback", timeout=_PER_TEST_S)
