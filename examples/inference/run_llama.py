@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "examples", "training"))
 
 from neuronx_distributed_b200.inference.autobucketing import generate_buckets  # noqa: E402
 from neuronx_distributed_b200.inference.benchmark import Benchmark, generate_report  # noqa: E402
-from neuronx_distributed_b200.inference.model_builder import ModelBuilder  # noqa: E402
+from neuronx_distributed_b200.trace.model_builder import ModelBuilder  # noqa: E402
 from neuronx_distributed_b200.models.llama import LlamaConfig, llama2_7b_config, llama2_13b_config  # noqa: E402
 from neuronx_distributed_b200.models.llama_inference import LlamaForInference  # noqa: E402
 from neuronx_distributed_b200.parallel_layers import parallel_state as ps  # noqa: E402

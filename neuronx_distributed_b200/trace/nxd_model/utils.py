@@ -27,7 +27,7 @@ def retrieve_artifact_from_model(nxd_model, key: str, artifact: str):
 
 def generate_route_key_from_provided_args(provided_args: Sequence[Any]) -> str:
     """Routing key of a traced bucket: parameter names + shapes + dtypes of its example inputs."""
-    from ...inference.nxd_model import NxDModel
+    from .nxd_model import NxDModel
 
     return NxDModel._route_key([a.param_name for a in provided_args], [a.tensor for a in provided_args])
 

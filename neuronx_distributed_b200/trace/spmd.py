@@ -7,8 +7,8 @@ from typing import Dict, List, Sequence, Tuple
 import torch
 from torch import nn
 
-from ..inference.nxd_model import BucketProgram, NxDModel  # noqa: F401
-from ..inference.nxd_model import StateInitializer as _StateInitializer
+from .nxd_model import BucketProgram, NxDModel  # noqa: F401
+from .nxd_model import StateInitializer as _StateInitializer
 
 
 def default_bucket_kernel(inputs: List[torch.Tensor]):

@@ -13,7 +13,6 @@ import torch
 from torch import nn
 
 from ..inference.sharding import shard_tensor
-from ..inference.trace import parallel_model_load, parallel_model_save, parallel_model_trace  # noqa: F401
 from ..parallel_layers.utils import create_local_weight as _create_local_weight
 from ..parallel_layers.utils import divide
 from ..utils.safetensors_utils import check_for_duplicate_tensors
@@ -168,3 +167,21 @@ def get_sharded_checkpoint(checkpoint: Dict[str, Any], model: nn.Module, rank: i
         preprocess_checkpoint(model, checkpoint)
     dtype = getattr(getattr(model, "config", None), "torch_dtype", None)
     shard_children(model, checkpoint, "", dtype, rank, tp_degree)
+
+
+# ---- v0 entry points (reference :242-371).  A "traced parallel model" is the per-rank module plus its captured bucket programs;
+# every rank is its own process (torchrun) instead of being spawned by the library. ---------------------------------------------
+def parallel_model_trace(func: Callable[[], Any], example_inputs: Any, tp_degree: int = 1, **kwargs):
+    from .model_builder import ModelBuilder
+
+    module, _aliases = func()
+    ex = example_inputs if isinstance(example_inputs, (tuple, list)) else (example_inputs,)
+    return ModelBuilder(tp_degree=tp_degree).add("main", module, [tuple(ex)]).trace()
+
+
+def parallel_model_save(model, save_dir: str) -> None:
+    model.save(save_dir, save_weights=True)
+
+
+def parallel_model_load(load_dir: str) -> Any:
+    return torch.load(os.path.join(load_dir, "nxd_model_meta.pt"), weights_only=False)

@@ -97,7 +97,7 @@ def test_spmd_rank_hooks_pad_cumsum_lora_gqa(tmp_path):
 
 def test_parallel_state_context_builds_any_rank_in_one_process():
     """NxDParallelState: construct rank 1's shard of a TP=2 layer in a single process (no process group of size 2)."""
-    from neuronx_distributed_b200.inference.parallel_context import NxDParallelState
+    from neuronx_distributed_b200.trace.parallel_context import NxDParallelState
     from neuronx_distributed_b200.parallel_layers.layers import ColumnParallelLinear
 
     shards = {}
@@ -111,7 +111,7 @@ def test_parallel_state_context_builds_any_rank_in_one_process():
 
 
 def _trace_v0(rank, world, tmp):
-    from neuronx_distributed_b200.inference.trace import parallel_model_load, parallel_model_save, parallel_model_trace
+    from neuronx_distributed_b200.trace.trace import parallel_model_load, parallel_model_save, parallel_model_trace
     from neuronx_distributed_b200.parallel_layers import parallel_state as ps
     from neuronx_distributed_b200.parallel_layers.layers import ColumnParallelLinear, RowParallelLinear
 

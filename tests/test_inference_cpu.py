@@ -6,7 +6,7 @@ from dist_utils import run_distributed
 
 
 def _infer(rank, world, tmp):
-    from neuronx_distributed_b200.inference.model_builder import ModelBuilder, shard_checkpoint
+    from neuronx_distributed_b200.trace.model_builder import ModelBuilder, shard_checkpoint
     from neuronx_distributed_b200.models.llama import LlamaConfig
     from neuronx_distributed_b200.models.llama_inference import LlamaForInference
     from neuronx_distributed_b200.operators import argmax

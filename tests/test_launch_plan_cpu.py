@@ -95,7 +95,7 @@ def test_record_replay_passes_and_persistence(tmp_path):
 
 def test_hlo_utils_roles_on_plans(tmp_path):
     """``trace/hlo_utils.py`` entry points: marking, extraction, per-weight transforms, checkpoint transformation on disk."""
-    from neuronx_distributed_b200.inference.functions import trace
+    from neuronx_distributed_b200.trace.functions import trace
     from neuronx_distributed_b200.trace import hlo_utils as hu
     from neuronx_distributed_b200.utils.safetensors_utils import load_state_dict_safetensors, save_state_dict_safetensors
 
@@ -208,9 +208,9 @@ class _Wrap(nn.Module):
 
 
 def _portable_llama(rank, world, tmp):
-    from neuronx_distributed_b200.inference.functions import compile as ncompile
-    from neuronx_distributed_b200.inference.functions import compile_layout_transformer, compile_wlo, trace
-    from neuronx_distributed_b200.inference.nxd_model import NxDModel, TorchScriptNxDModel, convert_nxd_model_to_torchscript_model
+    from neuronx_distributed_b200.trace.functions import compile as ncompile
+    from neuronx_distributed_b200.trace.functions import compile_layout_transformer, compile_wlo, trace
+    from neuronx_distributed_b200.trace.nxd_model import NxDModel, TorchScriptNxDModel, convert_nxd_model_to_torchscript_model
     from neuronx_distributed_b200.models.llama import LlamaConfig
     from neuronx_distributed_b200.models.llama_inference import LlamaForInference
     from neuronx_distributed_b200.parallel_layers import parallel_state as ps

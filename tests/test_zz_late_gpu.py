@@ -162,8 +162,8 @@ def test_launch_plan_replays_extension_kernels_and_captures():
         ps.initialize_model_parallel(1)
         from neuronx_distributed_b200.models.llama import LlamaConfig
         from neuronx_distributed_b200.models.llama_inference import LlamaForInference
-        from neuronx_distributed_b200.inference.functions import trace, compile as ncompile, compile_wlo
-        from neuronx_distributed_b200.inference.nxd_model import NxDModel
+        from neuronx_distributed_b200.trace.functions import trace, compile as ncompile, compile_wlo
+        from neuronx_distributed_b200.trace.nxd_model import NxDModel
         from torch import nn
         class Wrap(nn.Module):
             def __init__(s, m, which): super().__init__(); s.m, s.which = m, which

@@ -45,7 +45,7 @@ def main(args) -> int:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29535")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     from neuronx_distributed_b200 import ops
-    from neuronx_distributed_b200.inference.model_builder import ModelBuilder
+    from neuronx_distributed_b200.trace.model_builder import ModelBuilder
     from neuronx_distributed_b200.models.llama import llama2_13b_config
     from neuronx_distributed_b200.models.llama_inference import LlamaForInference
     from neuronx_distributed_b200.parallel_layers import parallel_state as ps
