@@ -12,8 +12,6 @@ What to look at:
   attention over the prompt, cache slots 0..S-1 written) or ``[B, 1]`` (decode: one slot written at ``last_pos``, attention over
   the cache with the split-KV kernel).  The builder captures each shape as its own CUDA graph.
 """
-import math
-
 import torch
 from torch import nn
 

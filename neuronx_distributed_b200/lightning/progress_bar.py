@@ -1,10 +1,7 @@
 """Progress bar that only prints on the ranks that log (reference ``lightning/progress_bar.py:1-22``)."""
 from __future__ import annotations
 
-import os
-from typing import Any, List, Optional
-
-import torch
+from typing import Optional
 
 from ._compat import Callback
 

@@ -21,7 +21,7 @@ def _dense(h_full, w_full, tgt, smoothing):
 
 
 def _worker(rank, world, sp):
-    from neuronx_distributed_b200.parallel_layers import comm, parallel_state as ps
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
     from neuronx_distributed_b200.parallel_layers.loss_functions import fused_linear_cross_entropy, parallel_cross_entropy
 
     ps.initialize_model_parallel(tensor_model_parallel_size=world)

@@ -1,8 +1,5 @@
 """Decode MoE block: the kernel's numerics oracle (``ops.moe_tkg.moe_block_tkg_reference``) against the composed module path
 for the routing / activation variants the one-launch kernel implements, and the ``MoEFusedTKG`` wrapper contract."""
-import itertools
-
-import pytest
 import torch
 
 from dist_utils import run_distributed
