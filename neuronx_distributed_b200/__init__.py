@@ -12,7 +12,7 @@ from .trainer.trainer import (  # noqa: F401
     neuronx_distributed_config,
 )
 
-__version__ = "0.1.0"
+from ._version import __version__  # noqa: E402,F401
 
 
 def __getattr__(name):

@@ -1,4 +1,5 @@
-from .expert_mlps_v2 import ExpertMLPs, ExpertMLPsV2  # noqa: F401
+from .expert_mlps import ExpertMLPs  # noqa: F401
+from .expert_mlps_v2 import ExpertMLPsV2  # noqa: F401
 from .experts import ACT2FN, Experts  # noqa: F401
 from .loss_function import load_balancing_loss_func  # noqa: F401
 from .model import MoE  # noqa: F401

@@ -400,7 +400,6 @@ class ExpertMLPsV2(ProcessGroupSafeDeepcopy, nn.Module):
         return out.view(hidden_states.shape)
 
 
-ExpertMLPs = ExpertMLPsV2
 
 
 def create_spmd_ranks(model_state_dict, prefix: str, world_size: int, n_routed_experts: Optional[int] = None,

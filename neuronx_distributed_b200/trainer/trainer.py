@@ -13,7 +13,7 @@ from ..optimizer.zero_redundancy_optimizer import NeuronEPZero1Optimizer, Neuron
 from ..parallel_layers import parallel_state as ps
 from ..utils import get_device
 from ..utils.logger import get_logger
-from .hooks import hooks
+from .post_partition_hooks import hooks
 from .model import NxDModel
 from .optimizer import NxDOptimizer
 

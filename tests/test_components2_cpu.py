@@ -14,7 +14,7 @@ def _spmd_pad_lora(rank, world, tmp):
     from neuronx_distributed_b200.parallel_layers import parallel_state as ps
     from neuronx_distributed_b200.parallel_layers.layers import ColumnParallelLinear, RowParallelLinear, SPMDRank
     from neuronx_distributed_b200.parallel_layers.pad import pad_model
-    from neuronx_distributed_b200.trainer import hooks as pph
+    from neuronx_distributed_b200.trainer import post_partition_hooks as pph
     from neuronx_distributed_b200.utils.tensor_utils import cumsum
 
     ps.initialize_model_parallel(tensor_model_parallel_size=world)

@@ -257,3 +257,35 @@ def test_moe_config_validator(tmp_path):
         get_dict_from_json(tmp_path / "bad.json")
     assert hardware("trn2") is hardware.B200 and HloMetadataLevel(False) is HloMetadataLevel.INFO
     assert to_torch_dtype("bfloat16") == torch.bfloat16 and to_torch_dtype(torch.float16) == torch.float16
+
+
+def _legacy_expert_mlps(rank, world):
+    """``ExpertMLPs`` (first-generation flat-keyword constructor, reference ``modules/moe/expert_mlps.py``) builds the same module
+    as ``ExpertMLPsV2`` with the two config objects."""
+    import pytest
+
+    from neuronx_distributed_b200.modules.moe import ExpertMLPs, ExpertMLPsV2
+    from neuronx_distributed_b200.modules.moe.model_utils import GLUType
+    from neuronx_distributed_b200.modules.moe.moe_configs import BlockwiseMatmulConfig, RoutedExpertsMLPOpsConfig
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    old = ExpertMLPs(4, 2, 16, 32, "silu", True, None, block_size=None, normalize_top_k_affinities=True, glu_type=GLUType.GLU,
+                     init_method=torch.nn.init.kaiming_uniform_, use_torch_block_wise=True, blockwise_nki_autograd_cls=None,
+                     early_expert_affinity_modulation=False, use_shard_on_block_dynamic_while=False, dtype=torch.float32)
+    new = ExpertMLPsV2(RoutedExpertsMLPOpsConfig(num_experts=4, top_k=2, hidden_size=16, intermediate_size=32, hidden_act="silu",
+                                                 glu_mlp=True, capacity_factor=None, normalize_top_k_affinities=True),
+                       BlockwiseMatmulConfig(use_torch_block_wise=True), dtype=torch.float32)
+    assert isinstance(old, ExpertMLPsV2) and old.cfg.input_layer_init_method is torch.nn.init.kaiming_uniform_
+    assert old.bw == new.bw and old.cfg.top_k == 2 and old.bw.block_size == 512
+    new.load_state_dict(old.state_dict())
+    x = torch.randn(6, 16)
+    aff = torch.softmax(torch.randn(6, 4), -1)
+    idx = aff.topk(2, -1).indices
+    torch.testing.assert_close(old(x, aff, idx, seq_len=6), new(x, aff, idx, seq_len=6))
+    with pytest.raises(TypeError):
+        ExpertMLPs(4, 2, 16, 32, "silu", True, None, not_an_option=1)
+
+
+def test_legacy_expert_mlps_constructor():
+    run_distributed(_legacy_expert_mlps, 2, timeout=120)
