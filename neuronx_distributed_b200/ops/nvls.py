@@ -163,7 +163,8 @@ def publish(x: torch.Tensor, group, ctas: int = 64):
     """Make ``x`` readable by every rank of ``group``: returns one tensor per rank, entry ``p`` viewing rank ``p``'s ``x``.
     CUDA: ``x`` is copied into this rank's symmetric slot (halves alternate per call), all ranks meet, and the returned
     tensors are VIEWS of the peers' slots — a kernel that takes them (e.g. flash attention, through TMA) loads straight over
-    NVLink.  They stay valid until the second next ``publish`` on the same group.  The half is chosen on the host (the
+    NVLink.  They stay valid until this rank's NEXT ``publish`` on the same group (once a rank has arrived there its peers may
+    run one call further and rewrite this half — `tools/sim_nvls_protocol.py::simulate_publish` shows the interleaving).  The half is chosen on the host (the
     addresses are needed to build the views), so a call is not CUDA-graph capturable.  CPU: an all-gather."""
     world = dist.get_world_size(group)
     if not (x.is_cuda and _ext.use_cuda(x) and hasattr(_ext.ext(), "nvls_publish") and available()):

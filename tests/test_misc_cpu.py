@@ -341,3 +341,25 @@ def test_nvls_protocol_model_catches_epoch_reset_and_passes_monotonic():
     with pytest.raises(sim.StaleRead):
         for seed in range(10):
             sim.simulate(3, calls, 2, 4, True, True, seed)
+
+
+def test_publish_pull_protocol_model():
+    """Model of ``nvls_publish_kernel`` + pull readers (embedding gather, all-to-all, ``publish`` views): alternating halves are
+    sufficient for reads that finish before the rank's next publish; a single buffer is not; views read after the rank has arrived
+    at its next publish are not safe either (hence ``pull_attention`` re-publishes K/V in backward)."""
+    import importlib.util
+    import os
+
+    import pytest
+
+    spec = importlib.util.spec_from_file_location("sim_nvls_protocol", os.path.join(os.path.dirname(__file__), "..", "tools", "sim_nvls_protocol.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    for seed in range(40):
+        sim.simulate_publish(2 + seed % 3, 2 + seed % 5, 1 + seed % 3, seed)
+    with pytest.raises(sim.StaleRead):
+        for seed in range(10):
+            sim.simulate_publish(3, 5, 2, seed, single_buffer=True)
+    with pytest.raises(sim.StaleRead):
+        for seed in range(40):
+            sim.simulate_publish(3, 6, 2, seed, reads_outlive=1)

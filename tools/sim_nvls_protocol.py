@@ -12,6 +12,8 @@ read); a seeded scheduler picks which rank moves next, so slow / fast rank skews
 ``reset_epochs=True`` models the round-2 bug (epoch counters restarted at 1 while the reused region still held old epochs): the
 model FAILS for it with a stale read, and passes with monotonic epochs — `tests/test_misc_cpu.py` runs both.
 
+``simulate_publish`` models the publish + pull kernels of ``csrc/nvls_coll.cu`` (embedding gather, all-to-all, ``publish`` views).
+
     python tools/sim_nvls_protocol.py            # 200 random schedules each of the good configurations
 """
 from __future__ import annotations
@@ -118,6 +120,70 @@ def simulate(world: int, calls: List[str], blocks: int, relayout_at: int, reuse_
     return steps
 
 
+def simulate_publish(world: int, calls: int, ctas: int, seed: int, single_buffer: bool = False, reads_outlive: int = 0,
+                     max_steps: int = 2_000_000) -> int:
+    """Model of ``nvls_publish_kernel`` + readers (csrc/nvls_coll.cu; ops.nvls.publish / embedding_gather / all_to_all /
+    pull_attention): per call every rank's CTA ``c`` copies slice ``c`` of its buffer into half ``call & 1`` of its OWN slot,
+    bumps counter ``c`` on every rank, waits until counter ``c`` shows ``world`` arrivals of this call; after its LAST CTA
+    passed, the rank reads every peer's slot (any slice) and only then starts the next call.
+
+    Checked: a reader only ever sees the version of its own call.  ``single_buffer=True`` (no parity halves) must FAIL — a
+    fast rank overwrites its slot while a slow peer still reads the previous call.  ``reads_outlive=k`` models views that are
+    still read after the rank has passed the barrier of call ``n + k``: already k = 1 FAILS (once a rank has arrived at call
+    n+1 its peers may run ahead into call n+2 and rewrite half ``n & 1``) — which is why ``ops.nvls.publish`` promises its views
+    only until the caller's NEXT publish and ``pull_attention`` re-publishes K/V in its backward."""
+    rnd = random.Random(seed)
+    slot = [[[-1] * ctas for _ in range(2)] for _ in range(world)]      # slot[rank][half][slice] = call id that wrote it
+    counter = [[0] * ctas for _ in range(world)]                         # counter[rank][cta]: arrivals seen by that rank
+    pending: List[List] = [[] for _ in range(world)]                     # (due_call, src, half, slice, expected version)
+
+    def check(r, src, half, sl, want, when):
+        got = slot[src][half][sl]
+        if got != want:
+            raise StaleRead(f"rank {r} at call {when} read version {got} of rank {src} half {half} slice {sl}, expected {want}")
+
+    def rank_prog(r: int):
+        for ci in range(calls):
+            half = 0 if single_buffer else ci & 1
+            order = list(range(ctas))
+            rnd.shuffle(order)                                           # CTAs of one rank run in any order
+            for c in order:
+                slot[r][half][c] = ci                                    # copy my slice
+                yield
+                for p in range(world):                                   # arrive on every rank's counter c
+                    counter[p][c] += 1
+                    yield
+            for c in order:                                              # ... and wait for this call's arrivals (kernel end = all CTAs)
+                while counter[r][c] < (ci + 1) * world:
+                    yield
+            # late readers of earlier calls' views
+            for item in [x for x in pending[r] if x[0] == ci]:
+                check(r, item[1], item[2], item[3], item[4], ci)
+                yield
+            pending[r][:] = [x for x in pending[r] if x[0] != ci]
+            reads = [(s, c) for s in range(world) for c in range(ctas)]
+            rnd.shuffle(reads)
+            for s, c in reads:                                           # pull kernels read any slice of any peer
+                check(r, s, half, c, ci, ci)
+                if reads_outlive and ci + reads_outlive < calls:
+                    pending[r].append((ci + reads_outlive, s, half, c, ci))
+                yield
+
+    progs = [rank_prog(r) for r in range(world)]
+    alive = list(range(world))
+    steps = 0
+    while alive:
+        r = rnd.choice(alive)
+        try:
+            next(progs[r])
+        except StopIteration:
+            alive.remove(r)
+        steps += 1
+        if steps > max_steps:
+            raise RuntimeError("publish protocol model did not terminate (deadlock?)")
+    return steps
+
+
 def main() -> None:
     rnd = random.Random(0)
     n = 0
@@ -129,6 +195,11 @@ def main() -> None:
             simulate(world, calls, rnd.choice([1, 2]), at, reuse, reset, seed)
             n += 1
     print(f"nvls protocol model: {n} schedules ok")
+    m = 0
+    for seed in range(200):
+        simulate_publish(rnd.choice([2, 3, 4]), rnd.randint(2, 7), rnd.choice([1, 2, 3]), seed)
+        m += 1
+    print(f"publish / pull protocol model: {m} schedules ok")
 
 
 if __name__ == "__main__":
