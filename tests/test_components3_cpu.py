@@ -255,3 +255,34 @@ def _lightning_strategy(rank, world, tmp):
 
 def test_lightning_strategy_surface_and_logging(tmp_path):
     run_distributed(_lightning_strategy, 4, str(tmp_path), timeout=180)
+
+
+def _launched(x):
+    import os
+
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+    t = torch.tensor(float(int(os.environ["RANK"]) + x))
+    dist.all_reduce(t)
+    dist.destroy_process_group()
+    if x < 0:
+        raise ValueError("boom")
+    return float(t)
+
+
+def test_lightning_launcher_spawns_ranks_and_returns_rank0_value(monkeypatch):
+    """``_NeuronXLALauncher`` (reference ``lightning/launcher.py``): outside torchrun it spawns the workers itself, sets their rank
+    environment, joins them and hands back worker 0's result; worker failures surface in the parent; under torchrun it runs
+    in-process."""
+    import pytest
+
+    from neuronx_distributed_b200.lightning.launcher import _NeuronXLALauncher
+
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    assert _NeuronXLALauncher(num_processes=3).launch(_launched, 10) == 33.0          # (0+10) + (1+10) + (2+10)
+    with pytest.raises(RuntimeError, match="boom"):
+        _NeuronXLALauncher(num_processes=2).launch(_launched, -1)
+    monkeypatch.setenv("RANK", "0")
+    assert _NeuronXLALauncher(num_processes=4).launch(lambda a: a + 1, 1) == 2         # torchrun: this process is the rank
