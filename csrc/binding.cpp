@@ -329,8 +329,10 @@ static std::vector<Tensor> moe_block_tkg(const Tensor& x, const c10::optional<Te
 // a [M,K], b [N,K]: fp8 bytes; sfa [ceil(M/128), K/128, 512], sfb [ceil(N/128), K/128, 512]: tiled E8M0 scales → [M,N] bf16
 static Tensor gemm_mxfp8(const Tensor& a, const Tensor& b, const Tensor& sfa, const Tensor& sfb, int64_t a_fmt, int64_t b_fmt) {
   CHECK_IN(a); CHECK_IN(b); CHECK_IN(sfa); CHECK_IN(sfb);
-  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.element_size() == 1 && b.element_size() == 1 && a.size(1) == b.size(1));
-  const int M = a.size(0), N = b.size(0), K = a.size(1);
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.element_size() == 1 && b.element_size() == 1);
+  // byte tensors: K bytes per row for fp8 formats, K/2 for packed e2m1 (format 5)
+  const int M = a.size(0), N = b.size(0), K = a_fmt == 5 ? 2 * a.size(1) : a.size(1);
+  TORCH_CHECK((b_fmt == 5 ? 2 * b.size(1) : b.size(1)) == K, "gemm_mxfp8: K of a and b differ");
   TORCH_CHECK(K % 128 == 0 && N % 8 == 0, "gemm_mxfp8: K % 128 == 0 and N % 8 == 0");
   TORCH_CHECK(sfa.scalar_type() == at::kByte && sfb.scalar_type() == at::kByte);
   TORCH_CHECK(sfa.numel() == (long)((M + 127) / 128) * (K / 128) * 512 && sfb.numel() == (long)((N + 127) / 128) * (K / 128) * 512,

@@ -194,15 +194,19 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
 // declared in gemm_sm100.cu
 CUtensorMap make_tmap_u8_box(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+CUtensorMap make_tmap_u4_unpacked_box(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 int device_sm_count();
 
-// a [M,K], b [N,K] fp8 bytes; sfa / sfb: scale chunks tiled [rows/128][K/128][512]; out [M,N] bf16.  N % 8 == 0, K % 128 == 0;
-// the scale arrays are padded to whole 128-row tiles by the caller.
+// a [M,K], b [N,K]: fp8 bytes (format 0 = e4m3, 1 = e5m2) or packed e2m1 (format 5: K/2 bytes per row, unpacked into 8-bit
+// containers by the TMA engine — W4A8: MXFP4 weights against MXFP8 activations); sfa / sfb: scale chunks tiled
+// [rows/128][K/128][512]; out [M,N] bf16.  N % 8 == 0, K % 128 == 0; scale arrays padded to whole 128-row tiles by the caller.
 void gemm_mxfp8(const void* a, const void* b, const void* sfa, const void* sfb, void* out, int M, int N, int K, int a_fmt,
                 int b_fmt, cudaStream_t st) {
   if (K % mx::BK || N % 8) nxd_throw("gemm_mxfp8: K % 128 == 0 and N % 8 == 0", __FILE__, __LINE__);
-  const CUtensorMap ta = make_tmap_u8_box(a, M, K, mx::BM);
-  const CUtensorMap tb = make_tmap_u8_box(b, N, K, mx::BN);
+  auto fmt_ok = [](int f) { return f == 0 || f == 1 || f == 5; };
+  if (!fmt_ok(a_fmt) || !fmt_ok(b_fmt)) nxd_throw("gemm_mxfp8: formats 0 (e4m3), 1 (e5m2), 5 (e2m1)", __FILE__, __LINE__);
+  const CUtensorMap ta = a_fmt == 5 ? make_tmap_u4_unpacked_box(a, M, K, mx::BM) : make_tmap_u8_box(a, M, K, mx::BM);
+  const CUtensorMap tb = b_fmt == 5 ? make_tmap_u4_unpacked_box(b, N, K, mx::BN) : make_tmap_u8_box(b, N, K, mx::BN);
   const int tiles = ((M + mx::BM - 1) / mx::BM) * ((N + mx::BN - 1) / mx::BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   static bool configured = false;

@@ -516,6 +516,23 @@ CUtensorMap make_tmap_bf16_strided(const void* ptr, uint64_t rows, uint64_t cols
   return m;
 }
 int device_sm_count() { return sm_count(); }
+// packed e2m1 [rows, cols] (two elements per byte, low nibble first), loaded UNPACKED: every 16 elements (8 bytes) land in a
+// 16-byte smem chunk — the operand layout kind::f8f6f4 / mxf8f6f4 expects for 4-bit types; box = {128 elements, box_rows}, so a
+// k-block occupies the same 128-byte swizzle row as an fp8 one (used by gemm_mx_sm100.cu for MXFP4 weights)
+CUtensorMap make_tmap_u4_unpacked_box(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  ensure_driver_context();
+  if (cols % 128 || ((uintptr_t)ptr % 32)) nxd_throw("4-bit tensor map: K % 128 == 0 and a 32-byte aligned base", __FILE__, __LINE__);
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols / 2};
+  cuuint32_t box[2] = {128, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) nxd_throw("cuTensorMapEncodeTiled (u4 unpacked) failed: " + std::to_string((int)r), __FILE__, __LINE__);
+  return m;
+}
 // fp8 bytes, box = {128 k-bytes, box_rows} (used by gemm_mx_sm100.cu)
 CUtensorMap make_tmap_u8_box(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   return make_tmap_u8(ptr, rows, cols, box_rows);

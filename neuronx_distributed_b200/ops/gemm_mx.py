@@ -6,7 +6,7 @@ byte (low nibble first; ``uint16`` x4 words are a view of the same bytes), MXFP8
 
 * ``rows <= 8`` on CUDA (token generation): ``csrc/gemv_mx.cu`` — the codes are decoded in registers, nothing is expanded in
   memory, so a decode step reads 4.25 / 8.25 bits per weight instead of 16;
-* MXFP8 weights, more rows, opt-in ``NXD_GEMM_MX=1``: activations are quantised to MXFP8 online and both operands go through
+* MXFP8 or MXFP4 weights, more rows, opt-in ``NXD_GEMM_MX=1``: activations are quantised to MXFP8 online and both operands go through
   the block-scaled tensor-core GEMM (``csrc/gemm_mx_sm100.cu``, ``tcgen05.mma.kind::mxf8f6f4.block_scale``: the E8M0 scales
   are applied inside the tensor core, nothing is de-quantised) — W8A8-MX numerics, oracle :func:`matmul_mxfp8_reference`;
 * otherwise: de-quantise to the activation dtype and run the dense GEMM (tcgen05 bf16 kernel on CUDA) — numerically the
@@ -20,7 +20,8 @@ import torch
 
 from . import _ext
 
-_FMT = {"mxfp4": 0, "mxfp8": 1, "mxfp8_e4m3": 1, "mxfp8_e5m2": 2}
+_FMT = {"mxfp4": 0, "mxfp8": 1, "mxfp8_e4m3": 1, "mxfp8_e5m2": 2}                    # gemv_mx format codes
+_MMA_FMT = {"mxfp4": 5, "mxfp8": 0, "mxfp8_e4m3": 0, "mxfp8_e5m2": 1}               # kind::mxf8f6f4 operand formats
 
 
 def kind_of(weight: torch.Tensor, fp8_dtype: torch.dtype = torch.float8_e4m3fn) -> str:
@@ -65,18 +66,19 @@ def matmul_mxfp8_reference(a_q: torch.Tensor, a_scale: torch.Tensor, b_q: torch.
 def gemm_mx_eligible(x2d: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, kind: str) -> bool:
     if os.environ.get("NXD_GEMM_MX", "0") != "1":                 # opt-in until the kernel has run on hardware
         return False
-    return (x2d.is_cuda and _FMT.get(kind, 0) in (1, 2) and x2d.shape[1] % 128 == 0 and scale.shape[0] % 8 == 0
+    return (x2d.is_cuda and kind in _MMA_FMT and x2d.shape[1] % 128 == 0 and scale.shape[0] % 8 == 0
             and weight.is_contiguous() and _ext.use_cuda(x2d, weight, scale) and hasattr(_ext.ext(), "gemm_mxfp8"))
 
 
 def matmul_mxfp8(a_q: torch.Tensor, a_scale: torch.Tensor, b_q: torch.Tensor, b_scale: torch.Tensor, a_kind: str = "mxfp8",
                  b_kind: str = "mxfp8", b_scale_tiled: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``[M, K] · [N, K]ᵀ`` on MXFP8 operands (byte streams or x4 words) with E8M0 block scales → bf16 ``[M, N]``."""
+    """``[M, K] · [N, K]ᵀ`` on MX operands (byte streams or x4 words; MXFP8 or MXFP4 — the TMA engine unpacks e2m1 pairs into the
+    8-bit containers the tensor core reads) with E8M0 block scales → bf16 ``[M, N]``."""
     a8 = a_q.contiguous().view(torch.uint8).reshape(a_scale.shape[0], -1)
     b8 = b_q.contiguous().view(torch.uint8).reshape(b_scale.shape[0], -1)
     _ext.count_launch()
     return _ext.ext().gemm_mxfp8(a8, b8, tile_scales(a_scale), b_scale_tiled if b_scale_tiled is not None else tile_scales(b_scale),
-                                 _FMT[a_kind] - 1, _FMT[b_kind] - 1)
+                                 _MMA_FMT[a_kind], _MMA_FMT[b_kind])
 
 
 def gemv_eligible(x2d: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor) -> bool:

@@ -305,6 +305,18 @@ def test_block_scaled_mxfp8_gemm_matches_dequantised_reference():
                 err = ((out.float() - ref).norm() / ref.norm()).item()
                 print(M, N, K, kind, "rel err", err)
                 assert err < 5e-3, err                      # products are exact in fp32; only the bf16 output rounds
+        # W4A8: MXFP4 weights (packed e2m1, unpacked to 8-bit containers by the TMA engine) against MXFP8 activations
+        from neuronx_distributed_b200.quantization.microscaling.mx_torch import quantize_mx
+        for M, N, K in ((256, 256, 256), (1000, 512, 2048)):
+            a = torch.randn(M, K, device="cuda"); b = torch.randn(N, K) * 0.1
+            aq, asc = quantize_mxfp8(a)
+            bq, bsc = quantize_mx(b, "mxfp4")
+            bq, bsc = bq.cuda(), bsc.cuda()
+            out = gemm_mx.matmul_mxfp8(aq, asc, bq, bsc, "mxfp8", "mxfp4")
+            ref = gemm_mx.matmul_mxfp8_reference(aq, asc, bq, bsc, "mxfp8", "mxfp4")
+            err = ((out.float() - ref).norm() / ref.norm()).item()
+            print(M, N, K, "w4a8 rel err", err)
+            assert err < 5e-3, err
         # through the layer-level entry point (activations quantised online)
         x = torch.randn(512, 1024, device="cuda").bfloat16(); w = torch.randn(768, 1024, device="cuda") * 0.05
         wq, ws = quantize_mxfp8(w)
