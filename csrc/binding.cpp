@@ -362,6 +362,21 @@ static Tensor gemv_mx(const Tensor& x, const Tensor& w, const Tensor& scale, int
   nxd::gemv_mx(x.data_ptr(), w.data_ptr(), scale.data_ptr(), res, y.data_ptr(), M, N, K, (int)fmt, stream());
   return y;
 }
+// x [S, K] bf16 (one row per (token, slot)); w = MX byte stream of [E, N, K]; scale [E, N, K/32]; expert [S] int64 → [S, N] bf16
+static Tensor gemv_mx_grouped(const Tensor& x, const Tensor& w, const Tensor& scale, const Tensor& expert, int64_t fmt) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.is_contiguous());
+  TORCH_CHECK(w.is_cuda() && w.is_contiguous() && scale.is_cuda() && scale.is_contiguous() && scale.scalar_type() == at::kByte &&
+              scale.dim() == 3);
+  TORCH_CHECK(expert.is_cuda() && expert.scalar_type() == at::kLong && expert.is_contiguous() && expert.numel() == x.size(0));
+  const int S = x.size(0), K = x.size(1), E = scale.size(0), N = scale.size(1);
+  TORCH_CHECK(K % 32 == 0 && scale.size(2) == K / 32, "gemv_mx_grouped: scale must be [E, N, K/32]");
+  const long row_bytes = fmt == 0 ? K / 2 : K;
+  TORCH_CHECK((long)(w.numel() * w.element_size()) == (long)E * N * row_bytes, "gemv_mx_grouped: weight bytes do not match [E, N, K]");
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor y = at::empty({S, N}, x.options());
+  nxd::gemv_mx_grouped(x.data_ptr(), w.data_ptr(), scale.data_ptr(), expert.data_ptr<long>(), y.data_ptr(), S, N, K, E, (int)fmt, stream());
+  return y;
+}
 static Tensor gemv(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& residual) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && x.dim() == 2 && w.dim() == 2);
   TORCH_CHECK(x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1) && x.size(0) >= 1 && x.size(0) <= 8 && x.size(1) % 8 == 0);
@@ -747,6 +762,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ptr_view", &ptr_view);
   m.def("nvls_all_to_all", &nvls_all_to_all);
   m.def("gemv_mx", &gemv_mx);
+  m.def("gemv_mx_grouped", &gemv_mx_grouped);
   m.def("gemm_mxfp8", &gemm_mxfp8);
   m.def("moe_block_tkg", &moe_block_tkg);
   m.def("moe_block_tkg_supported", [](int64_t T, int64_t H, int64_t E, int64_t I, int64_t K) {

@@ -132,6 +132,9 @@ void gemm_mxfp8(const void* a, const void* b, const void* sfa, const void* sfb, 
 void gemv_mx(const void* x, const void* w, const void* scale, const void* residual, void* y, int M, int N, int K, int fmt,
              cudaStream_t st);
 
+void gemv_mx_grouped(const void* x, const void* w, const void* scale, const long* expert, void* y, int S, int N, int K, int E, int fmt,
+                     cudaStream_t st);
+
 // ---- decode (decode.cu)
 void decode_attention(const void* q, const void* k, const void* v, const long* positions, void* out, float* part_o,
                       float* part_ml, int B, int H, int Hkv, int L, const long* ks, const long* vs, long q_sb, long q_sh,

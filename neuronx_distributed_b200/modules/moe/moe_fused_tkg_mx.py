@@ -87,14 +87,16 @@ def mxfp4_moe_block_tkg_wrapper(inp: torch.Tensor, gamma: Optional[torch.Tensor]
         dense = torch.zeros(T, E, dtype=torch.float32, device=x.device).scatter_(1, top_i, top_w)
         out = torch.einsum("eth,te->th", y, dense)
     else:                                                            # touch only the T·k selected experts' bytes
+        from ...ops import gemm_mx
+
         fe = top_i.reshape(-1)
-        w1 = _dequant(expert_gate_up_weights[fe], expert_gate_up_weights_scale[fe])          # [T·k, 2I, H]
-        w2 = _dequant(expert_down_weights[fe], expert_down_weights_scale[fe])                # [T·k, H, I]
         hk = h.repeat_interleave(top_k, 0)
-        gu = torch.einsum("sh,snh->sn", hk, w1)
+        # one (token, slot) row per chosen expert: the MX codes of only those experts are read (decoded in registers by
+        # ``gemv_mx_grouped`` on CUDA, gathered + de-quantised otherwise); expert ids never leave the device
+        gu = gemm_mx.grouped_linear_mx(hk.to(inp.dtype), expert_gate_up_weights, expert_gate_up_weights_scale, fe, "mxfp4").float()
         if expert_gate_up_bias is not None:
             gu = gu + expert_gate_up_bias.float()[fe]
-        y = torch.einsum("si,shi->sh", glu(gu), w2)
+        y = gemm_mx.grouped_linear_mx(glu(gu).to(inp.dtype), expert_down_weights, expert_down_weights_scale, fe, "mxfp4").float()
         if expert_down_bias is not None:
             y = y + expert_down_bias.float()[fe]
         out = (y * top_w.reshape(-1, 1)).reshape(T, top_k, -1).sum(1)

@@ -89,6 +89,22 @@ def gemv_eligible(x2d: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor) 
             and scale.dim() == 2 and _ext.use_cuda(x2d, weight, scale) and hasattr(_ext.ext(), "gemv_mx"))
 
 
+def grouped_linear_mx(x: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, expert: torch.Tensor, kind: Optional[str] = None
+                      ) -> torch.Tensor:
+    """Row ``s`` of ``x [S, K]`` against expert ``expert[s]`` of the stacked MX weights ``[E, N, K]`` (x4 words or bytes) with scales
+    ``[E, N, K/32]`` → ``[S, N]``: the selective-loading step of a decode-time MoE block.  CUDA (opt-in ``NXD_GEMV_MX=1``): one
+    launch that reads only the chosen experts' codes, ids stay on the device; otherwise gather + de-quantise + batched matmul."""
+    kind = kind or kind_of(weight)
+    E, N = scale.shape[0], scale.shape[1]
+    if (os.environ.get("NXD_GEMV_MX", "0") == "1" and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2 and x.shape[1] % 32 == 0
+            and _ext.use_cuda(x, weight, scale) and hasattr(_ext.ext(), "gemv_mx_grouped")):
+        _ext.count_launch()
+        return _ext.ext().gemv_mx_grouped(x.contiguous(), weight.contiguous(), scale.contiguous(), expert.long().contiguous(), _FMT[kind])
+    wb = weight.contiguous().view(torch.uint8).reshape(E, N, -1)[expert.long()]                      # [S, N, bytes]
+    w = dequantize(wb.reshape(-1, wb.shape[-1]), scale[expert.long()].reshape(-1, scale.shape[-1]), kind).view(x.shape[0], N, -1)
+    return torch.einsum("sk,snk->sn", x.float(), w).to(x.dtype)
+
+
 def linear_mx(x: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, kind: Optional[str] = None,
               residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``x [..., K] @ dequant(weight)[N, K]ᵀ (+ residual)`` → ``[..., N]`` in ``x.dtype``."""

@@ -409,3 +409,19 @@ def test_mx_scale_tiling_layout():
     (aq, asc), (bq, bsc) = quantize_mxfp8(a), quantize_mxfp8(b)
     ref = gemm_mx.matmul_mxfp8_reference(aq, asc, bq, bsc)
     assert ((ref - a @ b.t()).norm() / (a @ b.t()).norm()) < 0.08
+
+
+def test_grouped_linear_mx_selects_experts_per_row():
+    """``grouped_linear_mx`` (selective loading of a decode MoE block on MX weights): row s uses expert ``expert[s]``."""
+    import torch
+
+    from neuronx_distributed_b200.ops import gemm_mx
+    from neuronx_distributed_b200.quantization.microscaling.mx_torch import quantize_mx
+
+    torch.manual_seed(0)
+    E, N, K, S = 4, 6, 64, 5
+    w, x, ex = torch.randn(E, N, K), torch.randn(S, K), torch.tensor([3, 0, 0, 2, 1])
+    for kind in ("mxfp4", "mxfp8"):
+        p, sc = quantize_mx(w, kind)
+        want = torch.stack([x[i] @ gemm_mx.dequantize(p[ex[i]], sc[ex[i]], kind).t() for i in range(S)])
+        torch.testing.assert_close(gemm_mx.grouped_linear_mx(x, p, sc, ex), want, rtol=1e-5, atol=1e-5)

@@ -282,6 +282,18 @@ def test_gemv_mx_matches_dequantised_reference():
                 err = ((y.float() - ref).norm() / ref.norm()).item()
                 print(kind, M, N, K, "rel err", err)
                 assert err < 1e-2, err
+            # per-slot expert selection (MoE decode): only the chosen experts' codes are read
+            E, N, K, S = 8, 1024, 2048, 6
+            w = torch.randn(E, N, K) * 0.05
+            p, s = quantize_mx(w, kind)
+            p, s = p.cuda(), s.cuda()
+            x = torch.randn(S, K, device="cuda").bfloat16()
+            ex = torch.tensor([7, 0, 3, 3, 5, 1], device="cuda")
+            y = gemm_mx.grouped_linear_mx(x, p, s, ex)
+            ref = torch.stack([x[i].float() @ gemm_mx.dequantize(p[ex[i]], s[ex[i]], kind).t() for i in range(S)])
+            err = ((y.float() - ref).norm() / ref.norm()).item()
+            print(kind, "grouped rel err", err)
+            assert err < 1e-2, err
     """, env={"NXD_GEMV_MX": "1"})
 
 
