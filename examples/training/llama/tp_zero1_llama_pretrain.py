@@ -28,8 +28,11 @@ from training_utils import (Throughput, TrainingMetrics, init_distributed, linea
 def get_args():
     p = argparse.ArgumentParser()
     p.add_argument("--model", default="7b", choices=["tiny", "7b", "13b", "70b"])
-    p.add_argument("--pretrained_hf", default=None, help="HF Llama directory (config.json + safetensors): continue pre-training / fine-tune from it")
-    p.add_argument("--num_layers", type=int, default=-1)
+    p.add_argument("--pretrained_hf", "--pretrained_weight", dest="pretrained_hf", default=None,
+                   help="HF Llama directory (config.json + safetensors): continue pre-training / fine-tune from it")
+    p.add_argument("--num_layers", "--num_layer", dest="num_layers", type=int, default=-1)
+    p.add_argument("--hidden_size", type=int, default=-1, help="override the hidden size of the chosen model (shape experiments)")
+    p.add_argument("--fuse_qkv", type=int, default=1, help="one fused QKV weight per layer (1) or separate q / k / v weights (0)")
     p.add_argument("--tensor_parallel_size", type=int, default=8)
     p.add_argument("--context_parallel_size", type=int, default=1)
     p.add_argument("--use_sequence_parallel", type=int, default=1)
@@ -81,6 +84,9 @@ def main():
         mcfg = hf_compat.config_from_hf(a.pretrained_hf, **kw)
     if a.num_layers > 0:
         mcfg.num_hidden_layers = a.num_layers
+    if a.hidden_size > 0:
+        mcfg.hidden_size = a.hidden_size
+    mcfg.fuse_qkv = bool(a.fuse_qkv)
 
     def model_fn():
         torch.manual_seed(a.seed)
