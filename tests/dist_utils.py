@@ -55,6 +55,9 @@ def _worker(rank, world, port, fn, args, use_cuda, errq):
 
 
 def run_distributed(fn, world: int, *args, use_cuda: bool = False, timeout: float = 300.0):
+    if not use_cuda:
+        # CPU workers re-import torch in every spawned process (slow on a cold or busy box): callers' tighter limits are floors
+        timeout = max(float(timeout), 300.0)
     ctx = mp.get_context("spawn")
     errq = ctx.SimpleQueue()
     port = _free_port()
