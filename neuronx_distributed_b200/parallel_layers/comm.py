@@ -125,9 +125,9 @@ def reduce_scatter(x: torch.Tensor, dim: int = 0, group=None, op: str = "sum") -
     assert x.shape[dim] % n == 0, f"dim {dim} of {tuple(x.shape)} not divisible by group size {n}"
     r = dist.get_rank(group)
     if _is_gloo(group):
-        full = x.contiguous().clone()
+        full = x.contiguous().clone() if not x.is_cuda else x.detach().cpu()    # gloo control plane next to CUDA data (loopback)
         dist.all_reduce(full, op=_REDUCE_OPS[op], group=group)
-        out = full.chunk(n, dim=dim)[r].contiguous()
+        out = full.chunk(n, dim=dim)[r].contiguous().to(x.device)
     else:
         xin = x if dim == 0 else x.movedim(dim, 0)
         xin = xin.contiguous()
