@@ -124,6 +124,9 @@ class NxDPPModel(nn.Module):
         self.manual_pp_partition = manual_pp_partition
         self.manual_pp_stage_partition_fn, self.manual_pp_loss_fn = manual_pp_stage_partition_fn, manual_pp_loss_fn
         self._debug_mode = _debug_mode
+        # delayed tracing (reference model.py:210-232): with no ``input_names`` the traced inputs are taken from the keyword
+        # arguments of the FIRST run_train / run_eval call — partitioning waits for that batch
+        self._delay_tracing = bool(_delay_tracing) and input_names is None and not manual_pp_partition
         self.pp_size = _debug_pp_size if _debug_mode else ps.get_pipeline_model_parallel_size()
         self.pp_rank = _debug_pp_rank if _debug_mode else ps.get_pipeline_model_parallel_rank()
         self.num_stages = self.pp_size * virtual_pipeline_size
@@ -143,6 +146,8 @@ class NxDPPModel(nn.Module):
             raise ValueError("auto_partition needs transformer_layer_cls (the block class whose instances are distributed over the stages)")
         if manual_pp_partition:
             self._manual_partition()
+        elif self._delay_tracing:
+            pass                                                    # first batch decides the input names
         elif transformer_layer_cls is not None or self.pipeline_cuts:
             self.trace_and_partition()
 
@@ -358,6 +363,9 @@ class NxDPPModel(nn.Module):
         return mbs
 
     def _run(self, kwargs: Dict[str, Any], train: bool):
+        if not self.partitioned and self._delay_tracing:
+            self.perform_delayed_tracing_and_partition(**kwargs)
+            self.move_model_to_device()
         assert self.partitioned, "model is not partitioned"
         self.move_model_to_device()
         self._mbs = self._split_microbatches(kwargs)
@@ -704,8 +712,13 @@ class NxDPPModel(nn.Module):
         self.trace_and_partition()
 
     def perform_delayed_tracing_and_partition(self, *args, **kwargs) -> None:
-        """Delayed tracing (trace on the first batch) is never needed here — FX tracing does not depend on tensor shapes —
-        so this just partitions if the constructor did not."""
+        """Trace and partition now.  With delayed tracing the input names come from this call's keyword arguments (the first
+        batch): FX does not need tensor shapes, only which ``forward`` parameters are tensors and which stay at their defaults."""
+        if self.partitioned:
+            return
+        if self._delay_tracing and self.input_names is None and kwargs:
+            self.input_names = [k for k, v in kwargs.items() if v is not None]
+        self._delay_tracing = False
         self.partition()
 
     def maybe_materialize_local_module(self) -> None:

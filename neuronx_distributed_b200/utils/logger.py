@@ -55,7 +55,10 @@ _CACHE: dict[tuple[str, bool], logging.Logger] = {}
 
 
 def get_log_level() -> int:
-    return _LEVELS.get(os.environ.get("NXD_LOG_LEVEL", "info").lower(), logging.INFO)
+    name = os.environ.get("NXD_LOG_LEVEL", "info").lower()
+    if name not in _LEVELS:
+        raise ValueError(f"NXD_LOG_LEVEL={name!r} is not supported; use one of {sorted(_LEVELS)}")
+    return _LEVELS[name]
 
 
 def get_logger(name: str = "nxd_b200", rank0_only: bool = True) -> logging.Logger:
@@ -63,7 +66,11 @@ def get_logger(name: str = "nxd_b200", rank0_only: bool = True) -> logging.Logge
     if key in _CACHE:
         return _CACHE[key]
     logger = logging.getLogger(f"{name}{'.r0' if rank0_only else '.all'}")
-    logger.setLevel(get_log_level())
+    level = get_log_level()
+    if level > logging.CRITICAL:                         # "off": nothing is emitted, whatever the record's level
+        logger.disabled = True
+    else:
+        logger.setLevel(level)
     logger.propagate = False
     if not logger.handlers:
         handler = logging.StreamHandler(sys.stdout)

@@ -168,12 +168,21 @@ def maybe_materalize_model(model: nn.Module) -> None:
             module.to_empty(device=get_device(), recurse=False)
 
 
-def get_delay_tracing(nxd_config) -> bool:
-    return False
+def get_delay_tracing(arg):
+    """The delayed-tracing flag of a pipeline model (``_delay_tracing``) or of an nxd_config (``pipeline_config._delay_tracing``);
+    ``None`` when the argument carries none (reference model_utils.py:285-296)."""
+    if type(arg).__name__ == "NxDPPModel" or hasattr(arg, "original_torch_module"):
+        return bool(getattr(arg, "_delay_tracing", False))
+    if isinstance(arg, dict):
+        return (arg.get("pipeline_config") or {}).get("_delay_tracing")
+    return None
 
 
 def check_delay_tracing(nxd_config) -> bool:
-    return False
+    """Delayed tracing applies when the pipeline model is built by the model wrapper and the user gave no ``input_names``: the
+    first batch then names the traced inputs (reference model_utils.py:299-309)."""
+    pc = (nxd_config or {}).get("pipeline_config") or {}
+    return bool(pc.get("use_model_wrapper", False)) and not pc.get("input_names")
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -200,3 +200,55 @@ def _ring_worker(rank, world):
 
 def test_ring_attention_context_parallel():
     run_distributed(_ring_worker, 4, timeout=90)
+
+
+def _delayed(rank, world):
+    """Delayed tracing: no ``input_names`` → partitioning waits for the first batch, whose keyword arguments name the traced
+    inputs; the result equals the eagerly traced model.  Helpers ``get_delay_tracing`` / ``check_delay_tracing`` and the
+    signature analysis of ``get_concrete_args`` follow the reference's rules."""
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.pipeline import NxDPPModel
+    from neuronx_distributed_b200.pipeline.trace import get_concrete_args
+    from neuronx_distributed_b200.utils.model_utils import check_delay_tracing, get_delay_tracing
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=1, pipeline_model_parallel_size=world)
+    ids = torch.randint(0, 32, (8, 6), generator=torch.Generator().manual_seed(1))
+    torch.manual_seed(0)
+    eager = NxDPPModel(Toy(tie=False), transformer_layer_cls=Block, num_microbatches=4, output_loss_value_spec=True,
+                       input_names=["input_ids", "labels"], broadcast_and_average_loss=True)
+    torch.manual_seed(0)
+    lazy = NxDPPModel(Toy(tie=False), transformer_layer_cls=Block, num_microbatches=4, output_loss_value_spec=True,
+                      broadcast_and_average_loss=True, _delay_tracing=True)
+    assert eager.partitioned and not lazy.partitioned and get_delay_tracing(lazy) is True and get_delay_tracing(eager) is False
+    a = eager.run_train(input_ids=ids, labels=ids)
+    b = lazy.run_train(input_ids=ids, labels=ids)                     # traces here: input names = this call's keywords
+    assert lazy.partitioned and lazy.input_names == ["input_ids", "labels"] and get_delay_tracing(lazy) is False
+    torch.testing.assert_close(a, b)
+    for (n1, p1), (n2, p2) in zip(eager.local_named_parameters(), lazy.local_named_parameters()):
+        assert n1 == n2
+        if p1.grad is not None:
+            torch.testing.assert_close(p1.grad, p2.grad)
+    # the helper functions
+    assert get_delay_tracing({"pipeline_config": {"_delay_tracing": True}}) is True
+    assert get_delay_tracing({"pipeline_config": {"other": 1}}) is None and get_delay_tracing("text") is None
+    assert check_delay_tracing({"pipeline_config": {"use_model_wrapper": True}})
+    assert not check_delay_tracing({"pipeline_config": {"use_model_wrapper": True, "input_names": ["x"]}})
+    assert not check_delay_tracing({"pipeline_config": {"use_model_wrapper": False}}) and not check_delay_tracing({"pipeline_config": {}})
+
+    # signature analysis: everything the call does not supply stays a constant (in signature order)
+    class Sig(nn.Module):
+        def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                    labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
+                    cache_position=None):
+            return None
+
+    concrete = get_concrete_args(Sig(), None, (1, 2, "a"), dict(use_cache=True, output_hidden_states=True, return_dict=True))
+    assert list(concrete) == ["past_key_values", "inputs_embeds", "labels", "output_attentions", "cache_position"]
+    import pytest
+
+    with pytest.raises(ValueError, match="does not have input"):
+        get_concrete_args(Sig(), ["nope"])
+
+
+def test_delayed_tracing_and_signature_analysis_pp2():
+    run_distributed(_delayed, 2, timeout=180)
