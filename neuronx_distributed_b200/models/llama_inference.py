@@ -116,6 +116,19 @@ class LlamaForInference(nn.Module):
         o = o.transpose(0, 1).reshape(S, B, att.num_heads_local * D)
         return _row_linear_plus_residual(att.o_proj, o, x)
 
+    def _tkg_block(self, layer_idx: int, layer):
+        """Decode-time fused view of a MoE layer (shares its router / experts / norm; owns no parameters).  Kept outside the
+        module tree so that state dicts and ``named_modules`` of the served model do not change."""
+        blocks = self.__dict__.setdefault("_tkg_blocks", {})
+        if layer_idx not in blocks:
+            from ..modules.moe.moe_fused_tkg import MoEFusedTKG
+
+            mlp = layer.mlp
+            blocks[layer_idx] = MoEFusedTKG(mlp.router, mlp.expert_mlps, getattr(mlp, "shared_experts", None),
+                                            layer.post_attention_layernorm, sequence_dimension=0,
+                                            tensor_model_parallel_group=getattr(mlp, "tensor_parallel_group", None)).eval()
+        return blocks[layer_idx]
+
     def _body(self, input_ids: torch.Tensor, positions: Optional[torch.Tensor], prefill: bool, kv_len: Optional[int], tree=None):
         core = self._core
         x = core.embed_tokens(input_ids).transpose(0, 1).contiguous()               # [S, B, H]
@@ -127,6 +140,13 @@ class LlamaForInference(nn.Module):
                 hmid = ops.act.swiglu(mlp.gate_up_proj(layer.post_attention_layernorm(x)))
                 x = _row_linear_plus_residual(mlp.down_proj, hmid, x)
                 continue
+            if not prefill and x.shape[0] * x.shape[1] <= 8 and hasattr(mlp, "expert_mlps") and hasattr(mlp, "router"):
+                # MoE decode: norm → router → top-k → chosen experts → weighted sum as ONE launch when the kernel applies
+                # (modules/moe/moe_fused_tkg.py, csrc/moe_tkg.cu); otherwise the MoE layer's own dispatch below
+                fused = self._tkg_block(i, layer)
+                if fused._can_use_kernel(x):
+                    x = x + fused(x)[0]
+                    continue
             y = mlp(layer.post_attention_layernorm(x))
             x = x + (y[0] if isinstance(y, tuple) else y)                           # MoE blocks also return router logits
         return core.norm(x)

@@ -81,3 +81,39 @@ def test_moe_block_tkg_reference_matches_composed_path_tp1():
 
 def test_moe_block_tkg_reference_matches_composed_path_tp2():
     run_distributed(_worker, 2)
+
+
+def _serving(rank, world):
+    """Mixtral behind the serving wrapper: token generation through the fused decode block (forced on; on CPU it runs the
+    kernel's fp32 oracle) gives the same tokens as the MoE layer's own dispatch, TP=2."""
+    from neuronx_distributed_b200.models.llama_inference import LlamaForInference
+    from neuronx_distributed_b200.models.mixtral import MixtralConfig, MixtralForCausalLM
+    from neuronx_distributed_b200.modules.moe.moe_fused_tkg import MoEFusedTKG
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    cfg = MixtralConfig(vocab_size=64, hidden_size=32, intermediate_size=48, num_hidden_layers=2, num_attention_heads=4,
+                        num_key_value_heads=2, num_local_experts=4, num_experts_per_tok=2, dtype=torch.float32,
+                        max_position_embeddings=32)
+    torch.manual_seed(0)
+    m = LlamaForInference(cfg, batch_size=2, max_seq_len=32, lm_cls=MixtralForCausalLM).eval()
+    ids = torch.randint(0, 64, (2, 8), generator=torch.Generator().manual_seed(1))
+    want = m.generate(ids, 6)
+    assert "_tkg_blocks" in m.__dict__ and not any("tkg" in n for n, _ in m.named_modules())      # consulted, not in the module tree
+    calls = []
+    orig = MoEFusedTKG._moe_fused_tkg_kernel
+
+    def counted(self, x):
+        calls.append(tuple(x.shape))
+        return orig(self, x)
+
+    MoEFusedTKG._can_use_kernel = lambda self, x: True
+    MoEFusedTKG._moe_fused_tkg_kernel = counted
+    m.kv.reset()
+    got = m.generate(ids, 6)
+    assert torch.equal(got, want), (got, want)
+    assert len(calls) == 2 * 5 and all(c == (1, 2, 32) for c in calls)                          # 2 MoE layers × 5 decode steps
+
+
+def test_serving_uses_the_fused_moe_decode_block():
+    run_distributed(_serving, 2, timeout=240)
