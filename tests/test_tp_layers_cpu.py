@@ -128,9 +128,11 @@ def test_mappings_tp2():
 def _embedding_rs(rank, world):
     """``embedding_rs`` (remote gather of the owner's rows instead of masked lookup + reduce-scatter): same output and the same
     weight gradient as the reference path, on the CPU fallback of ``ops.nvls.embedding_gather``."""
+    from neuronx_distributed_b200.parallel_layers import layers as _layers
     from neuronx_distributed_b200.parallel_layers import parallel_state as ps
     from neuronx_distributed_b200.parallel_layers.layers import ParallelEmbedding
 
+    _layers._EMBEDDING_RS = False                                  # the comparison needs the reference path for ``ref``
     ps.initialize_model_parallel(tensor_model_parallel_size=world)
     torch.manual_seed(0)
     V, H, B, S = 32, 8, 3, 8
