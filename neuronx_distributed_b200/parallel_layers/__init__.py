@@ -7,7 +7,7 @@ from . import parallel_state  # noqa: F401
 from . import comm, grads, layer_norm, layers, loss_functions, mappings, random, utils  # noqa: F401
 from .grads import clip_grad_norm  # noqa: F401
 from .layers import ColumnParallelLinear, ParallelEmbedding, RowParallelLinear  # noqa: F401
-from .loss_functions import parallel_cross_entropy  # noqa: F401
+from .loss_functions import fused_linear_cross_entropy, parallel_cross_entropy  # noqa: F401
 from .mappings import (  # noqa: F401
     copy_to_tensor_model_parallel_region,
     gather_from_tensor_model_parallel_region,
@@ -41,6 +41,7 @@ def __getattr__(name):
 PARALLEL_MODULES: List[Type[torch.nn.Module]] = [ColumnParallelLinear, RowParallelLinear, ParallelEmbedding]
 PARALLEL_FUNCTIONS: List[Callable] = [
     parallel_cross_entropy,
+    fused_linear_cross_entropy,
     copy_to_tensor_model_parallel_region,
     gather_from_tensor_model_parallel_region,
     reduce_from_tensor_model_parallel_region,
