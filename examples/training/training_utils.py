@@ -79,9 +79,16 @@ def synthetic_batches(vocab: int, batch: int, seq: int, seed: int, device) -> It
         yield {"input_ids": ids, "labels": ids}
 
 
-def memmap_batches(path: str, batch: int, seq: int, dp_rank: int, dp_size: int, device, dtype=np.uint16) -> Iterator[Dict[str, torch.Tensor]]:
-    """Flat token file → [batch, seq] windows, strided over data-parallel ranks."""
+def memmap_batches(path: str, batch: int, seq: int, dp_rank: int, dp_size: int, device, dtype=None) -> Iterator[Dict[str, torch.Tensor]]:
+    """Flat token file → [batch, seq] windows, strided over data-parallel ranks.  The element type comes from the ``<path>.json``
+    side file written by ``llama/get_dataset.py`` (``uint16`` without one)."""
+    if dtype is None:
+        dtype = np.uint16
+        if os.path.exists(path + ".json"):
+            with open(path + ".json") as f:
+                dtype = np.dtype(json.load(f).get("dtype", "uint16"))
     data = np.memmap(path, dtype=dtype, mode="r")
+    assert len(data) > seq, f"{path} holds {len(data)} tokens, fewer than one sequence of {seq}"
     n = (len(data) - 1) // seq
     i = dp_rank
     while True:

@@ -36,3 +36,27 @@ def test_llama_sample_all_flows_agree(tmp_path):
     assert _py(["generate", "--compiled-model-path", art_nw, "--sharded-dir", sharded] + COMMON, port=29714, nproc=2) == want
     assert _py(["generate", "--compiled-model-path", art_nw, "--shard-on-load"] + COMMON, port=29715, nproc=2) == want
     _py(["test_attention"] + tiny, port=29716, nproc=2)
+
+
+def test_tokenise_corpus_then_pretrain_from_it(tmp_path):
+    """``get_dataset.py`` (local corpus → flat token file + metadata) feeds ``tp_zero1_llama_pretrain.py --data_path`` on 2 ranks."""
+    import json
+
+    corpus = tmp_path / "c.txt"
+    corpus.write_text("Hello world.\nSecond line.\n\nAnother document with more text to tokenise.\n" * 60)
+    (tmp_path / "d.jsonl").write_text("\n".join(json.dumps({"text": f"json doc {i} " * 5}) for i in range(20)))
+    tokens = str(tmp_path / "tokens.bin")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "training", "llama", "get_dataset.py"), "--input", str(corpus),
+                          str(tmp_path / "d.jsonl"), "--output", tokens, "--min_tokens", "512"], env=env, text=True,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    assert out.returncode == 0, out.stdout
+    meta = json.loads(out.stdout.strip().splitlines()[-1])
+    assert meta["documents"] == 81 and meta["dtype"] == "uint16" and os.path.getsize(tokens) == 2 * meta["tokens"]
+    train = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                            "--master-port", "29721", os.path.join(ROOT, "examples", "training", "llama", "tp_zero1_llama_pretrain.py"),
+                            "--model", "tiny", "--tensor_parallel_size", "2", "--max_steps", "2", "--grad_accum_usteps", "1",
+                            "--seq_len", "64", "--data_path", tokens, "--output_dir", str(tmp_path / "out")], env=env, text=True,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert train.returncode == 0, train.stdout[-3000:]
+    assert "step 2 loss" in train.stdout
