@@ -35,6 +35,8 @@ def get_args():
     p.add_argument("--fuse_qkv", type=int, default=1, help="one fused QKV weight per layer (1) or separate q / k / v weights (0)")
     p.add_argument("--tensor_parallel_size", type=int, default=8)
     p.add_argument("--context_parallel_size", type=int, default=1)
+    p.add_argument("--cp_layout", default="contiguous", choices=["contiguous", "zigzag"],
+                   help="zigzag: rank r holds sequence chunks (r, 2cp-1-r) so causal attention work is balanced (pull attention path)")
     p.add_argument("--use_sequence_parallel", type=int, default=1)
     p.add_argument("--use_zero_1", type=int, default=1)
     p.add_argument("--use_mix_precision", type=int, default=1)
@@ -75,7 +77,7 @@ def main():
     )
     dtype = torch.bfloat16 if dev.type == "cuda" else torch.float32
     kw = dict(sequence_parallel_enabled=sp, dtype=dtype, device=dev, max_position_embeddings=a.seq_len,
-              context_parallel=a.context_parallel_size > 1)
+              context_parallel=a.context_parallel_size > 1, cp_layout=a.cp_layout)
     mcfg = {"7b": llama2_7b_config, "13b": llama2_13b_config, "70b": llama2_70b_config}.get(a.model, lambda **k: LlamaConfig(
         vocab_size=4096, hidden_size=512, intermediate_size=1408, num_hidden_layers=4, num_attention_heads=8, **k))(**kw)
     if a.pretrained_hf:                                          # architecture from the HF config, weights loaded after sharding
@@ -121,7 +123,7 @@ def main():
             if a.context_parallel_size > 1:
                 from neuronx_distributed_b200.utils.batch_utils import get_batch_on_this_context_parallel_rank
 
-                batch = get_batch_on_this_context_parallel_rank(batch)
+                batch = get_batch_on_this_context_parallel_rank(batch, layout=a.cp_layout)
             loss = model.run_train(**batch)
             total = total + loss.detach() / a.grad_accum_usteps
         opt.step()

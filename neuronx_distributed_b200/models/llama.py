@@ -50,6 +50,7 @@ class LlamaConfig:
     pad_token_id: Optional[int] = None
     # context parallel: each CP rank holds a contiguous S/cp slice; positions are offset
     context_parallel: bool = False
+    cp_layout: str = "contiguous"           # "zigzag": rank r holds sequence chunks (r, 2·cp−1−r); needs the pull attention path
     device: Optional[torch.device] = None       # construct parameters directly here (e.g. cuda)
 
     def __post_init__(self):
@@ -144,7 +145,10 @@ class LlamaAttention(nn.Module):
         if self.cfg.context_parallel and ps.get_context_model_parallel_size() > 1:
             from ..modules.attention.ring import pull_attention, ring_attention
 
-            o = (pull_attention if _CP_PULL else ring_attention)(q, k, v, causal=True)
+            if self.cfg.cp_layout != "contiguous":
+                o = pull_attention(q, k, v, causal=True, layout=self.cfg.cp_layout)      # the ring keeps the contiguous split
+            else:
+                o = (pull_attention if _CP_PULL else ring_attention)(q, k, v, causal=True)
         else:
             o = ops.attention.flash_attention(q, k, v, causal=True)
         o = o.transpose(0, 1).reshape(S, B, self.num_heads_local * self.head_dim)
@@ -233,9 +237,21 @@ class LlamaModel(nn.Module):
         if not self.cfg.sequence_parallel_enabled:
             x = x.transpose(0, 1).contiguous()
         offset = 0
-        if self.cfg.context_parallel and ps.get_context_model_parallel_size() > 1:
-            offset = ps.get_context_model_parallel_rank() * S
-        cos, sin = self.rope(S, input_ids.device, offset)
+        cp = ps.get_context_model_parallel_size() if self.cfg.context_parallel else 1
+        if cp > 1 and self.cfg.cp_layout == "zigzag":
+            # local tokens = sequence chunks (r, 2·cp−1−r): two position ranges
+            r, c = ps.get_context_model_parallel_rank(), S // 2
+            zz = self.__dict__.get("_rope_cache_zz")
+            if zz is None or zz[0] != (S, r, cp, input_ids.device):
+                tabs = [ops.rope.rope_tables(c, self.cfg.head_dim, self.cfg.rope_theta, input_ids.device, off,
+                                             self.cfg.rope_scaling_factor) for off in (r * c, (2 * cp - 1 - r) * c)]
+                zz = ((S, r, cp, input_ids.device), torch.cat([tabs[0][0], tabs[1][0]]), torch.cat([tabs[0][1], tabs[1][1]]))
+                self.__dict__["_rope_cache_zz"] = zz
+            cos, sin = zz[1], zz[2]
+        else:
+            if cp > 1:
+                offset = ps.get_context_model_parallel_rank() * S
+            cos, sin = self.rope(S, input_ids.device, offset)
         ckpt = self.cfg.activation_checkpointing == "full" and self.training
         if _FUSED_ADD_NORM and not ckpt and type(self.layers[0]).forward is LlamaDecoderLayer.forward \
                 and not torch.jit.is_tracing() and not isinstance(x, torch.fx.Proxy):

@@ -147,31 +147,59 @@ def _block_backward(q, k, v, out, lse, dout, causal: bool, scale: float):
     return dq.transpose(1, 2).to(q.dtype), dk.transpose(1, 2).to(k.dtype), dv.transpose(1, 2).to(v.dtype)
 
 
+def _chunk_ids(rank: int, cp: int, layout: str):
+    """Global sequence-chunk ids held by ``rank``, in local order.  ``contiguous``: one chunk per rank.  ``zigzag``: the sequence
+    is cut into 2·cp chunks and rank r holds chunks r and 2·cp−1−r — with a causal mask every rank then owns the same number of
+    visible (query chunk, key chunk) pairs (2·cp + 1), instead of r + 1 for the contiguous split."""
+    if layout == "contiguous":
+        return [rank]
+    if layout == "zigzag":
+        return [rank, 2 * cp - 1 - rank]
+    raise ValueError(f"unknown context-parallel layout {layout!r}")
+
+
+def _visible_pairs(rank: int, cp: int, layout: str, causal: bool):
+    """(local query chunk index, source rank, source chunk index, is_diagonal) for every block this rank computes; own rank first."""
+    mine = _chunk_ids(rank, cp, layout)
+    pairs = []
+    for step in range(cp):
+        src = (rank - step) % cp
+        theirs = _chunk_ids(src, cp, layout)
+        for qi, gq in enumerate(mine):
+            for kj, gk in enumerate(theirs):
+                if not causal or gk <= gq:
+                    pairs.append((qi, src, kj, causal and gk == gq))
+    return pairs
+
+
 class _PullAttention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, causal, scale, group):
+    def forward(ctx, q, k, v, causal, scale, group, layout):
         from ... import ops
 
         cp, r = dist.get_world_size(group), dist.get_rank(group)
+        nq = len(_chunk_ids(r, cp, layout))
+        assert q.shape[1] % nq == 0 and k.shape[1] % nq == 0, "the local sequence must split into the layout's chunks"
         kv = torch.stack([k, v]).contiguous()                        # one slot per rank: [2, B, S/cp, Hkv, D]
         views = ops.nvls.publish(kv, group)
-        out = lse = None
+        qs = q.chunk(nq, dim=1)
+        outs = [None] * nq
+        lses = [None] * nq
         with torch.no_grad():
-            for step in range(cp):
-                src = (r - step) % cp                                # own block first, then the nearest earlier ranks
-                if causal and src > r:
-                    continue
-                o_b, lse_b = block_attention(q, views[src][0], views[src][1], causal and src == r, scale)
-                if out is None:
-                    out, lse = o_b.float(), lse_b.float()
+            for qi, src, kj, diag in _visible_pairs(r, cp, layout, causal):
+                kb, vb = views[src][0].chunk(nq, dim=1)[kj], views[src][1].chunk(nq, dim=1)[kj]
+                o_b, lse_b = block_attention(qs[qi], kb, vb, diag, scale)
+                if outs[qi] is None:
+                    outs[qi], lses[qi] = o_b.float(), lse_b.float()
                 else:
-                    new = torch.logaddexp(lse, lse_b)
-                    out = out * torch.exp(lse - new).transpose(1, 2).unsqueeze(-1) + \
+                    new = torch.logaddexp(lses[qi], lse_b)
+                    outs[qi] = outs[qi] * torch.exp(lses[qi] - new).transpose(1, 2).unsqueeze(-1) + \
                         o_b.float() * torch.exp(lse_b - new).transpose(1, 2).unsqueeze(-1)
-                    lse = new
-        out = out.to(q.dtype)
+                    lses[qi] = new
+        out = torch.cat(outs, dim=1).to(q.dtype)
+        lse = torch.cat(lses, dim=2)                                 # [B, H, S/cp]
         ctx.save_for_backward(q, k, v, out, lse)
-        ctx.causal, ctx.scale, ctx.group = causal, scale, group
+        ctx.causal, ctx.scale, ctx.group, ctx.layout = causal, scale, group, layout
         return out
 
     @staticmethod
@@ -180,19 +208,22 @@ class _PullAttention(torch.autograd.Function):
         from ...parallel_layers import comm
 
         q, k, v, out, lse = ctx.saved_tensors
-        group, causal, scale = ctx.group, ctx.causal, ctx.scale
+        group, causal, scale, layout = ctx.group, ctx.causal, ctx.scale, ctx.layout
         cp, r = dist.get_world_size(group), dist.get_rank(group)
+        nq = len(_chunk_ids(r, cp, layout))
         views = ops.nvls.publish(torch.stack([k, v]).contiguous(), group)          # peers' K/V again (the slot was reused since)
-        dq = torch.zeros_like(q, dtype=torch.float32)
+        dqs = [torch.zeros_like(c, dtype=torch.float32) for c in q.chunk(nq, dim=1)]
         dkv = torch.zeros((cp,) + tuple(views[r].shape), dtype=torch.float32, device=q.device)      # [cp, 2, B, S/cp, Hkv, D]
-        dout = dout.contiguous()
-        for step in range(cp):
-            src = (r - step) % cp
-            if causal and src > r:
-                continue
-            dq_b, dk_b, dv_b = _block_backward(q, views[src][0], views[src][1], out, lse, dout, causal and src == r, scale)
-            dq += dq_b.float()
-            dkv[src, 0], dkv[src, 1] = dk_b.float(), dv_b.float()
+        qs, os_, ds = q.chunk(nq, dim=1), out.chunk(nq, dim=1), dout.contiguous().chunk(nq, dim=1)
+        ls = lse.chunk(nq, dim=2)
+        c = k.shape[1] // nq
+        for qi, src, kj, diag in _visible_pairs(r, cp, layout, causal):
+            kb, vb = views[src][0].chunk(nq, dim=1)[kj], views[src][1].chunk(nq, dim=1)[kj]
+            dq_b, dk_b, dv_b = _block_backward(qs[qi].contiguous(), kb.contiguous(), vb.contiguous(), os_[qi].contiguous(),
+                                               ls[qi].contiguous(), ds[qi].contiguous(), diag, scale)
+            dqs[qi] += dq_b.float()
+            dkv[src, 0, :, kj * c:(kj + 1) * c] += dk_b.float()
+            dkv[src, 1, :, kj * c:(kj + 1) * c] += dv_b.float()
         # every rank holds its contributions to ALL blocks; each owner needs the sum over ranks of its own block
         flat = dkv.reshape(cp * dkv[0].numel() // dkv.shape[-1], dkv.shape[-1])
         if flat.is_cuda and ops.nvls.available(group) and ops.nvls.has_multicast(group):
@@ -200,15 +231,17 @@ class _PullAttention(torch.autograd.Function):
         else:
             mine = comm.reduce_scatter(flat, dim=0, group=group)
         mine = mine.view(dkv.shape[1:])
-        return dq.to(q.dtype), mine[0].to(k.dtype), mine[1].to(v.dtype), None, None, None
+        return torch.cat(dqs, dim=1).to(q.dtype), mine[0].to(k.dtype), mine[1].to(v.dtype), None, None, None, None
 
 
 def pull_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True, scale: Optional[float] = None,
-                   group=None) -> torch.Tensor:
+                   group=None, layout: str = "contiguous") -> torch.Tensor:
     """Same contract as :func:`ring_attention` (``[B, S/cp, H, D]`` slices in, local output out), no ring: see the section
-    comment above.  Opt-in from the models with ``NXD_CP_PULL=1`` until the symmetric-memory path has run on hardware."""
+    comment above.  ``layout="zigzag"``: the local slice is chunks (r, 2·cp−1−r) of the sequence (``utils.batch_utils`` cuts
+    batches that way) — causal work is then balanced over the ranks.  Opt-in from the models with ``NXD_CP_PULL=1`` until the
+    symmetric-memory path has run on hardware."""
     group = group if group is not None else ps.get_context_model_parallel_group()
     scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
     if dist.get_world_size(group) == 1:
         return block_attention(q, k, v, causal, scale)[0]
-    return _PullAttention.apply(q, k, v, causal, scale, group)
+    return _PullAttention.apply(q, k, v, causal, scale, group, layout)

@@ -10,8 +10,19 @@ import torch
 from ..parallel_layers import parallel_state as ps
 
 
+def context_parallel_slice(t: torch.Tensor, rank: int, cp: int, seq_dim: int = 1, layout: str = "contiguous") -> torch.Tensor:
+    """This rank's part of a full-sequence tensor.  ``contiguous``: chunk ``rank`` of ``cp``.  ``zigzag``: chunks ``rank`` and
+    ``2·cp − 1 − rank`` of ``2·cp`` (balanced causal attention, see ``modules/attention/ring.py``)."""
+    if layout == "contiguous":
+        return t.chunk(cp, dim=seq_dim)[rank].contiguous()
+    if layout == "zigzag":
+        parts = t.chunk(2 * cp, dim=seq_dim)
+        return torch.cat([parts[rank], parts[2 * cp - 1 - rank]], dim=seq_dim).contiguous()
+    raise ValueError(f"unknown context-parallel layout {layout!r}")
+
+
 def get_batch_on_this_context_parallel_rank(batch: Dict[str, Any], seq_dim: int = 1, shift_labels: bool = True,
-                                            ignore_index: int = -100) -> Dict[str, Any]:
+                                            ignore_index: int = -100, layout: str = "contiguous") -> Dict[str, Any]:
     cp = ps.get_context_model_parallel_size()
     out = dict(batch)
     if shift_labels and "labels" in out and out["labels"] is not None:
@@ -25,9 +36,10 @@ def get_batch_on_this_context_parallel_rank(batch: Dict[str, Any], seq_dim: int 
     if cp == 1:
         return out
     r = ps.get_context_model_parallel_rank()
+    div = cp if layout == "contiguous" else 2 * cp
     for k, v in list(out.items()):
-        if isinstance(v, torch.Tensor) and v.dim() > seq_dim and v.shape[seq_dim] % cp == 0:
-            out[k] = v.chunk(cp, dim=seq_dim)[r].contiguous()
+        if isinstance(v, torch.Tensor) and v.dim() > seq_dim and v.shape[seq_dim] % div == 0:
+            out[k] = context_parallel_slice(v, r, cp, seq_dim, layout)
     return out
 
 
