@@ -352,13 +352,17 @@ def _pull_attention_loopback(rank, world):
     gen = torch.Generator(device="cuda").manual_seed(0)
     q, k, v = (torch.randn(B, S, h, D, device="cuda", generator=gen).bfloat16() for h in (H, Hkv, Hkv))
     go = torch.randn(B, S, H, D, device="cuda", generator=gen).bfloat16()
-    sl = slice(rank * S // world, (rank + 1) * S // world)
-    for it in range(2):                                     # both halves of the publish slot
-        ql, kl, vl = (t[:, sl].clone().requires_grad_(True) for t in (q, k, v))
+    from neuronx_distributed_b200.utils.batch_utils import context_parallel_slice
+
+    for it, layout in enumerate(("contiguous", "zigzag")):  # two calls = both halves of the publish slot
+        def cut(t, layout=layout):
+            return context_parallel_slice(t, rank, world, 1, layout)
+
+        ql, kl, vl = (cut(t).clone().requires_grad_(True) for t in (q, k, v))
         n0 = _ext.launches()
-        out = pull_attention(ql, kl, vl, causal=True, group=g)
+        out = pull_attention(ql, kl, vl, causal=True, group=g, layout=layout)
         assert _ext.launches() > n0                         # publish + tcgen05 attention kernels, not the SDPA fallback
-        out.backward(go[:, sl])
+        out.backward(cut(go))
         qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
         s = torch.einsum("bqhd,bkhd->bhqk", qf, kf.repeat_interleave(H // Hkv, 2)) / math.sqrt(D)
         s = s.masked_fill(~torch.ones(S, S, dtype=torch.bool, device="cuda").tril(), float("-inf"))
@@ -368,8 +372,8 @@ def _pull_attention_loopback(rank, world):
         def rel(a, b):
             return float((a.float() - b).norm() / b.norm())
 
-        errs = (rel(out, ref[:, sl]), rel(ql.grad, qf.grad[:, sl]), rel(kl.grad, kf.grad[:, sl]), rel(vl.grad, vf.grad[:, sl]))
-        assert max(errs) < 2e-2, errs
+        errs = (rel(out, cut(ref)), rel(ql.grad, cut(qf.grad)), rel(kl.grad, cut(kf.grad)), rel(vl.grad, cut(vf.grad)))
+        assert max(errs) < 2e-2, (layout, errs)
 
 
 def test_pull_attention_reads_peer_kv_inside_the_kernel_loopback():
