@@ -117,3 +117,28 @@ def _serving(rank, world):
 
 def test_serving_uses_the_fused_moe_decode_block():
     run_distributed(_serving, 2, timeout=240)
+
+
+def test_kernel_index_arithmetic_emulation():
+    """``tools/emulate_moe_tkg.py`` replays the kernel's work decomposition and pointer arithmetic on the host (ragged sizes, an
+    expert-parallel slice, both affinity modes): every weight element of an active expert is read exactly once and the result
+    equals the oracle."""
+    import importlib.util
+    import os
+
+    import numpy as np
+
+    from neuronx_distributed_b200.ops import moe_tkg
+
+    spec = importlib.util.spec_from_file_location("emulate_moe_tkg", os.path.join(os.path.dirname(__file__), "..", "tools", "emulate_moe_tkg.py"))
+    em = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(em)
+    torch.manual_seed(0)
+    for T, H, E, I, K, e0, El, pre in ((5, 264, 8, 136, 3, 0, 8, True), (4, 136, 12, 72, 2, 4, 4, False)):
+        x, rw = torch.randn(T, H), torch.randn(E, H) * 0.3
+        wgu, wdn = torch.randn(El, H, 2 * I) * 0.2, torch.randn(El, I, H) * 0.2
+        out, _, idx, w = moe_tkg.moe_block_tkg_reference(x, None, rw, None, wgu, wdn, e0, K, round_logits=False, pre_scale=pre)
+        assert int(((idx >= e0) & (idx < e0 + El)).sum()) > 0
+        y = em.run(x.numpy(), idx.numpy(), w.numpy(), wgu.numpy(), wdn.numpy(), e0, pre, lambda g, u: g / (1 + np.exp(-g)) * u,
+                   grid_warps=7)
+        np.testing.assert_allclose(y, out.numpy(), rtol=1e-4, atol=1e-4)
