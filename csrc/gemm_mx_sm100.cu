@@ -104,7 +104,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_wait_bounded(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t full = bar_full + 8 * stage;
           mbar_expect_tx(full, kTileBytes + 2 * kSfBytes);
           const uint32_t sa = smem_base + stage * kTileBytes, sb = sa + kABytes;
@@ -124,11 +124,11 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const uint32_t idesc0 = make_idesc_mx(a_fmt, b_fmt);
       int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+        mbar_wait_bounded(bar_tempty + 8 * as, aphase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
+          mbar_wait_bounded(bar_full + 8 * stage, phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * kTileBytes, sb = sa + kABytes;
           const uint32_t ssf = smem_base + kSfOffset + stage * 2 * kSfBytes;
@@ -156,7 +156,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
-      mbar_wait(bar_tfull + 8 * as, aphase);
+      mbar_wait_bounded(bar_tfull + 8 * as, aphase);
       tcgen05_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
       __nv_bfloat16* orow = out + (size_t)row * N;

@@ -80,7 +80,17 @@ NXD_DEVICE void grid_barrier(unsigned* ctr, unsigned target) {
   if (threadIdx.x == 0) {
     __threadfence();
     red_release_gpu_add(ctr, 1u);
-    while (ld_acquire_gpu_u32(ctr) < target) { __nanosleep(32); }
+    uint32_t it = 0;
+    uint64_t t0 = 0;
+    while (ld_acquire_gpu_u32(ctr) < target) {
+      __nanosleep(32);
+      if ((++it & 0x3fffu) == 0) {                       // a grid that is not co-resident would wait forever: trap after ~4 s
+        uint64_t t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 4000000000ull) __trap();
+      }
+    }
     __threadfence();
   }
   __syncthreads();

@@ -31,6 +31,27 @@ NXD_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// Same wait with a wall-clock bound: a kernel whose producer never arrives (wrong expected-byte count, rejected tensor map)
+// traps after ~4 s instead of spinning until the host gives up.  Used by kernels that have not had a hardware run yet.
+NXD_DEVICE void mbar_wait_bounded(uint32_t bar, uint32_t parity) {
+  uint32_t done, it = 0;
+  uint64_t t0 = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && (++it & 0x3ffu) == 0) {
+      uint64_t t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) __trap();
+    }
+  } while (!done);
+}
 NXD_DEVICE void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 NXD_DEVICE void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {

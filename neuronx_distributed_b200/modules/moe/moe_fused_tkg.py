@@ -23,6 +23,10 @@ from .moe_configs import MoEFusedTKGConfig
 logger = get_logger()
 
 
+def _on_cuda(t: torch.Tensor) -> bool:                 # separate so host tests can walk the eligibility rules
+    return t.device.type == "cuda"
+
+
 class MoEFusedTKG(nn.Module):
     def __init__(self, router: nn.Module, expert_mlps: nn.Module, shared_experts: Any = None, rmsnorm: Any = None,
                  config: Optional[MoEFusedTKGConfig] = None, sequence_dimension: int = 0,
@@ -94,7 +98,7 @@ class MoEFusedTKG(nn.Module):
             return no("disabled by config.moe_fused_kernel_enabled")
         if self.training or torch.is_grad_enabled() and hidden_states.requires_grad:
             return no("training / autograd")
-        if hidden_states.device.type != "cuda":
+        if not _on_cuda(hidden_states):
             return no("cannot run on cpu")
         if self.config.quantized or self.config.is_mxfp4_compute:
             return no("quantized experts")

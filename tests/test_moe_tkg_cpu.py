@@ -75,6 +75,40 @@ def _worker(rank, world):
     assert not f2._can_use_kernel(x) and "disabled" in f2._why_not
 
 
+def _eligibility(rank, world):
+    """Every rule of ``_can_use_kernel`` after the device check, walked on the host (device predicate and the op-level shape /
+    dtype check patched): a supported block says yes, each unsupported variant names its reason."""
+    from neuronx_distributed_b200 import ops
+    from neuronx_distributed_b200.modules.moe import moe_fused_tkg as mod
+    from neuronx_distributed_b200.modules.moe.moe_configs import MoEFusedTKGConfig
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    mod._on_cuda = lambda t: True
+    seen = []
+    ops.moe_tkg.kernel_eligible = lambda x, rw, wgu, wdn, k: (seen.append((tuple(x.shape), tuple(rw.shape), tuple(wgu.shape),
+                                                                             tuple(wdn.shape), k)) or True)
+    cfg, router, experts, norm = _build()
+    f = mod.MoEFusedTKG(router, experts, MoEFusedTKGConfig(), 0, None, post_attention_layernorm=norm).eval()
+    x = torch.randn(1, 3, cfg.hidden_size)
+    with torch.no_grad():
+        assert not f._can_use_kernel(x) and f._why_not == "norm weight dtype"                      # fp32 norm weight on this host build
+        norm.weight.data = norm.weight.data.bfloat16()
+        assert f._can_use_kernel(x), f._why_not
+    (xs, rws, gus, dns, k), = seen[-1:]
+    assert xs == (3, cfg.hidden_size) and rws == (cfg.num_experts, cfg.hidden_size) and k == cfg.top_k
+    assert gus == (cfg.num_experts, cfg.hidden_size, 2 * dns[1]) and dns == (cfg.num_experts, cfg.intermediate_size, cfg.hidden_size)
+    router.act_fn = "tanh"
+    assert not f._can_use_kernel(x) and "router" in f._why_not
+    router.act_fn = "softmax"
+    f.train()
+    assert not f._can_use_kernel(x) and "training" in f._why_not
+
+
+def test_kernel_eligibility_rules_walked_on_host():
+    run_distributed(_eligibility, 1)
+
+
 def test_moe_block_tkg_reference_matches_composed_path_tp1():
     run_distributed(_worker, 1)
 
