@@ -342,6 +342,24 @@ static Tensor gemm_mxfp8(const Tensor& a, const Tensor& b, const Tensor& sfa, co
   nxd::gemm_mxfp8(a.data_ptr(), b.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), out.data_ptr(), M, N, K, (int)a_fmt, (int)b_fmt, stream());
   return out;
 }
+// a [M,K/2], b [N,K/2]: packed e2m1 bytes; sfa [ceil(M/128), K/(4·vs), 512], sfb likewise: tiled scales (E8M0 for vs 32, UE4M3 for
+// vs 16) → alpha · product, [M,N] bf16
+static Tensor gemm_f4(const Tensor& a, const Tensor& b, const Tensor& sfa, const Tensor& sfb, int64_t vec_size, double alpha) {
+  CHECK_IN(a); CHECK_IN(b); CHECK_IN(sfa); CHECK_IN(sfb);
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.element_size() == 1 && b.element_size() == 1);
+  const int M = a.size(0), N = b.size(0), K = 2 * a.size(1);
+  TORCH_CHECK(2 * b.size(1) == K, "gemm_f4: K of a and b differ");
+  TORCH_CHECK(K % 256 == 0 && N % 8 == 0, "gemm_f4: K % 256 == 0 and N % 8 == 0");
+  TORCH_CHECK(vec_size == 32 || vec_size == 16, "gemm_f4: vec_size 32 (MXFP4) or 16 (NVFP4)");
+  TORCH_CHECK(sfa.scalar_type() == at::kByte && sfb.scalar_type() == at::kByte);
+  const long kc = K / (4 * vec_size);
+  TORCH_CHECK(sfa.numel() == (long)((M + 127) / 128) * kc * 512 && sfb.numel() == (long)((N + 127) / 128) * kc * 512,
+              "gemm_f4: scale tensors must be tiled [rows/128, K/(4*vec_size), 512]");
+  c10::cuda::CUDAGuard guard(a.device());
+  Tensor out = at::empty({M, N}, a.options().dtype(at::kBFloat16));
+  nxd::gemm_f4(a.data_ptr(), b.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), out.data_ptr(), M, N, K, (int)vec_size, (float)alpha, stream());
+  return out;
+}
 // x [M<=8, K] bf16; w = MX byte stream of [N, K] (fp4: K/2 bytes per row, fp8: K), any integer dtype view; scale [N, K/32] uint8
 static Tensor gemv_mx(const Tensor& x, const Tensor& w, const Tensor& scale, int64_t fmt, const c10::optional<Tensor>& residual) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.is_contiguous() && x.size(0) >= 1 && x.size(0) <= 8);
@@ -764,6 +782,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemv_mx", &gemv_mx);
   m.def("gemv_mx_grouped", &gemv_mx_grouped);
   m.def("gemm_mxfp8", &gemm_mxfp8);
+  m.def("gemm_f4", &gemm_f4);
   m.def("moe_block_tkg", &moe_block_tkg);
   m.def("moe_block_tkg_supported", [](int64_t T, int64_t H, int64_t E, int64_t I, int64_t K) {
     return nxd::moe_block_tkg_supported((int)T, (int)H, (int)E, (int)I, (int)K);

@@ -533,6 +533,22 @@ CUtensorMap make_tmap_u4_unpacked_box(const void* ptr, uint64_t rows, uint64_t c
   if (r != CUDA_SUCCESS) nxd_throw("cuTensorMapEncodeTiled (u4 unpacked) failed: " + std::to_string((int)r), __FILE__, __LINE__);
   return m;
 }
+// packed e2m1 [rows, cols] read PACKED (two elements per byte in smem as in global memory): the operand layout of
+// kind::mxf4 / kind::mxf4nvf4; box = {256 elements = 128 bytes, box_rows} (used by gemm_mxf4_sm100.cu)
+CUtensorMap make_tmap_u4_packed_box(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  ensure_driver_context();
+  if (cols % 256 || ((uintptr_t)ptr % 16)) nxd_throw("packed 4-bit tensor map: K % 256 == 0 and a 16-byte aligned base", __FILE__, __LINE__);
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols / 2};
+  cuuint32_t box[2] = {256, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN8B, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) nxd_throw("cuTensorMapEncodeTiled (u4 packed) failed: " + std::to_string((int)r), __FILE__, __LINE__);
+  return m;
+}
 // fp8 bytes, box = {128 k-bytes, box_rows} (used by gemm_mx_sm100.cu)
 CUtensorMap make_tmap_u8_box(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   return make_tmap_u8(ptr, rows, cols, box_rows);

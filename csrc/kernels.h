@@ -128,6 +128,11 @@ void moe_block_tkg(const void* x, const void* gamma, const void* router_w, const
 void gemm_mxfp8(const void* a, const void* b, const void* sfa, const void* sfb, void* out, int M, int N, int K, int a_fmt,
                 int b_fmt, cudaStream_t st);
 
+// ---- 4-bit block-scaled GEMM at the FP4 rate (gemm_mxf4_sm100.cu): packed e2m1 operands; vec_size 32 = MXFP4 (E8M0 scales),
+// 16 = NVFP4 (UE4M3 scales, alpha = product of the per-tensor factors)
+void gemm_f4(const void* a, const void* b, const void* sfa, const void* sfb, void* out, int M, int N, int K, int vec_size, float alpha,
+             cudaStream_t st);
+
 // ---- decode GEMV on MX (block-scaled fp4 / fp8) weights (gemv_mx.cu)
 void gemv_mx(const void* x, const void* w, const void* scale, const void* residual, void* y, int M, int N, int K, int fmt,
              cudaStream_t st);

@@ -8,7 +8,7 @@ import os as _os
 # NXD_EXPERIMENTAL=1 switches on every opt-in path that has not been timed on hardware yet (docs/ROUND2.md): one flag to
 # validate them together.  Individual flags set by the user win.
 _EXPERIMENTAL_FLAGS = ("NXD_FUSED_LMHEAD_CE", "NXD_MOE_TKG_KERNEL", "NXD_EMBEDDING_RS", "NXD_NVLS_A2A", "NXD_CP_PULL", "NXD_GEMM_MX",
-                       "NXD_GEMV_MX")
+                       "NXD_GEMV_MX")          # NXD_GEMM_F4 (W4A4) changes numerics and stays a separate, explicit choice
 if _os.environ.get("NXD_EXPERIMENTAL", "0") == "1":
     for _f in _EXPERIMENTAL_FLAGS:
         _os.environ.setdefault(_f, "1")

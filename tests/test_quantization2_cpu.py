@@ -411,6 +411,52 @@ def test_mx_scale_tiling_layout():
     assert ((ref - a @ b.t()).norm() / (a @ b.t()).norm()) < 0.08
 
 
+def test_fp4_gemm_quantisers_oracle_and_scale_addressing():
+    """4-bit × 4-bit GEMM (``csrc/gemm_mxf4_sm100.cu``): the MXFP4 / NVFP4 quantisers (round-to-nearest-even on the e2m1 grid),
+    the oracle, and a replay of the kernel's scale addressing — which chunk column and which scale bytes each K=64 MMA reads —
+    against the un-tiled scale matrix."""
+    import torch
+
+    from neuronx_distributed_b200.ops import gemm_mx
+
+    torch.manual_seed(0)
+    assert gemm_mx._e2m1_codes(torch.tensor([0.25, 0.75, 1.25, 1.75, 2.5, 3.5, 5.0, -0.75, 7.0])).tolist() == [0, 2, 2, 4, 4, 6, 6, 10, 7]
+    a, b = torch.randn(40, 512) * torch.rand(40, 1) * 3, torch.randn(24, 512)
+    want = a @ b.t()
+    aq, asc = gemm_mx.quantize_mxfp4(a)
+    bq, bsc = gemm_mx.quantize_mxfp4(b)
+    assert aq.shape == (40, 256) and asc.shape == (40, 16) and asc.dtype == torch.uint8
+    assert torch.equal(gemm_mx.dequantize_f4(aq, asc, 32), gemm_mx.dequantize(aq, asc, "mxfp4"))        # same decode as the MX layers
+    assert ((gemm_mx.matmul_f4_reference(aq, asc, bq, bsc, 32) - want).norm() / want.norm()) < 0.2
+    aq, asc, ag = gemm_mx.quantize_nvfp4(a)
+    bq, bsc, bg = gemm_mx.quantize_nvfp4(b)
+    assert asc.shape == (40, 32) and float(ag) > 0
+    e_mx = ((gemm_mx.dequantize_f4(*gemm_mx.quantize_mxfp4(a), 32) - a).norm() / a.norm()).item()
+    e_nv = ((gemm_mx.dequantize_f4(aq, asc, 16, ag) - a).norm() / a.norm()).item()
+    assert e_nv < e_mx < 0.15                                           # finer blocks + e4m3 scales round better than 2^k per 32
+    assert ((gemm_mx.matmul_f4_reference(aq, asc, bq, bsc, 16, ag, bg) - want).norm() / want.norm()) < 0.15
+    # kernel-side addressing: a k-block is 256 elements; chunk = 128 rows x 4 consecutive scales at byte (r%32)*16 + (r//32)*4 + j;
+    # MXFP4: 2 chunks per k-block, MMA k reads bytes {sf_id, sf_id+1} (sf_id = 2·(k&1)) of chunk k>>1;
+    # NVFP4: 4 chunks per k-block, MMA k reads bytes 0..3 of chunk k
+    R, K = 200, 1024
+    for vs, pad in ((32, 127), (16, 0x38)):
+        sc = torch.randint(1, 250, (R, K // vs), dtype=torch.uint8)
+        t = gemm_mx.tile_scales(sc, pad)
+        ch = 256 // (4 * vs)
+        assert t.shape == (2, K // 256 * ch, 512)
+        for r in (0, 31, 32, 127, 128, 199):
+            tile, rr = r // 128, r % 128
+            base = (rr % 32) * 16 + (rr // 32) * 4
+            for kb in range(K // 256):
+                for k in range(4):                                         # the four K=64 MMAs of the k-block
+                    chunk, sf_id, nsf = (kb * ch + (k >> 1), 2 * (k & 1), 2) if vs == 32 else (kb * ch + k, 0, 4)
+                    got = t[tile, chunk, base + sf_id: base + sf_id + nsf]
+                    first = (kb * 256 + k * 64) // vs
+                    assert torch.equal(got, sc[r, first: first + nsf]), (vs, r, kb, k)
+        assert t[1, 0, (100 % 32) * 16 + (100 // 32) * 4] == pad           # row 228 does not exist
+    assert not gemm_mx.gemm_f4_eligible(128, 128, 256, a)                  # CPU / opt-in flag unset
+
+
 def test_grouped_linear_mx_selects_experts_per_row():
     """``grouped_linear_mx`` (selective loading of a decode MoE block on MX weights): row s uses expert ``expert[s]``."""
     import torch

@@ -338,6 +338,36 @@ def test_block_scaled_mxfp8_gemm_matches_dequantised_reference():
     """, env={"NXD_GEMM_MX": "1"}, timeout=420)
 
 
+def test_fp4_block_scaled_gemm_matches_dequantised_reference():
+    """``kind::mxf4`` (MXFP4: E8M0 per 32) and ``kind::mxf4nvf4`` (NVFP4: UE4M3 per 16 + per-tensor factor) with both operands
+    packed e2m1, vs fp32 matmul on the de-quantised operands; ragged M / N, several K; and the W4A4 layer entry point."""
+    _run("""
+        import torch
+        from neuronx_distributed_b200.ops import gemm_mx
+        torch.manual_seed(0)
+        for M, N, K in ((128, 128, 256), (256, 384, 512), (1000, 264, 4096), (4096, 4096, 4096)):
+            a = torch.randn(M, K, device="cuda") * torch.rand(M, 1, device="cuda") * 4
+            b = torch.randn(N, K, device="cuda") * 0.1
+            aq, asc = gemm_mx.quantize_mxfp4(a); bq, bsc = gemm_mx.quantize_mxfp4(b)
+            out = gemm_mx.matmul_f4(aq, asc, bq, bsc, 32)
+            ref = gemm_mx.matmul_f4_reference(aq, asc, bq, bsc, 32)
+            err = ((out.float() - ref).norm() / ref.norm()).item()
+            print(M, N, K, "mxfp4 rel err", err)
+            assert err < 5e-3, err                          # products are exact in fp32; only the bf16 output rounds
+            aq, asc, ag = gemm_mx.quantize_nvfp4(a); bq, bsc, bg = gemm_mx.quantize_nvfp4(b)
+            out = gemm_mx.matmul_f4(aq, asc, bq, bsc, 16, ag, bg)
+            ref = gemm_mx.matmul_f4_reference(aq, asc, bq, bsc, 16, ag, bg)
+            err = ((out.float() - ref).norm() / ref.norm()).item()
+            print(M, N, K, "nvfp4 rel err", err)
+            assert err < 5e-3, err
+        x = torch.randn(512, 1024, device="cuda").bfloat16(); w = torch.randn(768, 1024, device="cuda") * 0.05
+        wq, ws = gemm_mx.quantize_mxfp4(w)
+        y = gemm_mx.linear_mx(x, wq.view(torch.uint16), ws, kind="mxfp4")
+        ref = x.float() @ gemm_mx.dequantize(wq, ws, "mxfp4").t()
+        assert ((y.float() - ref).norm() / ref.norm()).item() < 0.2            # + MXFP4 rounding of the activations
+    """, env={"NXD_GEMM_F4": "1"}, timeout=420)
+
+
 def _pull_attention_loopback(rank, world):
     import math
 

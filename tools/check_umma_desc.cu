@@ -16,8 +16,27 @@ uint64_t make_smem_desc_noswizzle(uint32_t saddr, uint32_t lbo_bytes, uint32_t s
 uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return make_smem_desc_noswizzle(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)2 << 61);
 }
+// csrc/gemm_mxf4_sm100.cu
+template <int VS>
+constexpr uint32_t make_idesc_f4() {
+  return (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((VS == 32 ? 1u : 0u) << 23) | ((uint32_t)(BM >> 4) << 24);
+}
 int main() {
   int bad = 0;
+  {
+    using namespace cute;
+    // the factory CUTLASS uses for its own kind::mxf4 / kind::mxf4nvf4 atoms (packed float_e2m1_t operands, K-major)
+    auto mx = UMMA::make_instr_desc_block_scaled<float_e2m1_t, float_e2m1_t, float, float_ue8m0_t, BM, BN, UMMA::Major::K, UMMA::Major::K>();
+    auto nv = UMMA::make_instr_desc_block_scaled<float_e2m1_t, float_e2m1_t, float, float_ue4m3_t, BM, BN, UMMA::Major::K, UMMA::Major::K>();
+    for (uint32_t id : {0u, 2u}) {
+      mx.a_sf_id_ = id; mx.b_sf_id_ = id;
+      const uint32_t mine = make_idesc_f4<32>() | (id << 4) | (id << 29);
+      if ((uint32_t)mx != mine) { printf("mxf4 idesc mismatch id=%u: %08x vs %08x\n", id, (uint32_t)mx, mine); ++bad; }
+    }
+    if ((uint32_t)nv != make_idesc_f4<16>()) { printf("nvf4 idesc mismatch: %08x vs %08x\n", (uint32_t)nv, make_idesc_f4<16>()); ++bad; }
+    printf("kind::mxf4 idesc %08x, kind::mxf4nvf4 idesc %08x (MXF4Format::E2M1 = %d, UE4M3 scale = %d)\n", make_idesc_f4<32>(),
+           make_idesc_f4<16>(), (int)UMMA::MXF4Format::E2M1, (int)UMMA::ScaleFormat::UE4M3);
+  }
   for (int af : {0, 1, 5}) for (int bf : {0, 1, 5}) for (int k = 0; k < 4; ++k) {
     cute::UMMA::InstrDescriptorBlockScaled d{};
     d.desc_ = 0;
