@@ -19,6 +19,29 @@ from .tp_layer import LoraGQAQKVParallelLinear, LoraParallelLinear
 _DEFAULT_TARGETS = ["q_proj", "k_proj", "v_proj", "o_proj", "qkv_proj", "gate_up_proj", "down_proj", "up_proj", "gate_proj"]
 
 
+def _by_targets(groups):
+    return {arch: list(t) for t, archs in groups for arch in archs}
+
+
+# Default adapter placement per Hugging Face ``config.model_type`` when ``LoraConfig.target_modules`` is not given (the table
+# of reference lora/model.py:35-67, which follows peft): attention query / value projections, or the fused QKV where the
+# architecture has one.
+MODELS_TO_LORA_TARGET_MODULES_MAPPING = _by_targets([
+    (("q_proj", "v_proj"), ("llama", "mistral", "mixtral", "gemma", "stablelm", "opt", "gptj", "gpt_neo", "bart")),
+    (("query_key_value",), ("gpt_neox", "bloom", "falcon", "chatglm", "RefinedWeb", "RefinedWebModel")),
+    (("query", "value"), ("bert", "roberta", "xlm-roberta", "electra", "layoutlm")),
+    (("q", "v"), ("t5", "mt5")),
+    (("c_attn",), ("gpt2", "gpt_bigcode")),
+    (("q", "v", "q_proj", "v_proj"), ("blip-2",)),
+    (("query_proj", "value_proj"), ("deberta-v2",)),
+    (("in_proj",), ("deberta",)),
+    (("Wqkv",), ("mpt",)),
+    (("c_proj", "c_attn"), ("btlm",)),
+    (("qkv_proj",), ("codegen",)),
+    (("q_proj", "v_proj", "fc1", "fc2"), ("phi",)),
+])
+
+
 def _wrap(module: nn.Module, cfg: LoraConfig) -> Optional[nn.Module]:
     if isinstance(module, GQAQKVColumnParallelLinear):
         return LoraGQAQKVParallelLinear(module, cfg)
@@ -72,10 +95,27 @@ class LoraModel(nn.Module):
     def _is_target(self, name: str) -> bool:
         t = self.lora_config.target_modules
         if t is None:
-            t = _DEFAULT_TARGETS
+            t = self._default_targets()
         if isinstance(t, str):
             return re.fullmatch(t, name) is not None
         return any(name == x or name.endswith("." + x) for x in t)
+
+    def _default_targets(self):
+        """No ``target_modules``: the per-architecture default when the base model says what it is (``config.model_type``) and
+        that default matches modules of this model (a fused-QKV build of a "q_proj / v_proj" architecture has ``qkv_proj``
+        instead); otherwise every projection of the attention and MLP blocks."""
+        cached = self.__dict__.get("_auto_targets")
+        if cached is None:
+            cfg = getattr(self.module, "config", None)
+            mt = (cfg.get("model_type") if isinstance(cfg, dict) else getattr(cfg, "model_type", None)) or "unknown"
+            want = MODELS_TO_LORA_TARGET_MODULES_MAPPING.get(mt) or MODELS_TO_LORA_TARGET_MODULES_MAPPING.get(str(mt).lower())
+            names = [n for n, _ in self.module.named_modules()]
+            if want and any(n == x or n.endswith("." + x) for n in names for x in want):
+                cached = list(want)
+            else:
+                cached = _DEFAULT_TARGETS
+            self.__dict__["_auto_targets"] = cached
+        return cached
 
     def inject_adapter(self) -> None:
         replaced = 0

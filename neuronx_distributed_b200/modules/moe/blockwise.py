@@ -20,6 +20,14 @@ from typing import Any, Optional, Tuple
 
 import torch
 
+from .moe_configs import (  # noqa: F401  (re-exported here as in the reference, blockwise.py:83-87)
+    ActFnType,
+    ActivationFunction,
+    BlockShardStrategy,
+    ExpertAffinityScaleMode,
+    SkipMode,
+)
+
 
 def get_num_blocks(total_tokens: int, top_k: int, num_experts: int, block_size: int) -> int:
     return max(1, math.ceil(max(total_tokens * top_k - (num_experts - 1), 0) / block_size) + (num_experts - 1))
@@ -116,6 +124,68 @@ def blockwise_expert_mlp(hidden: torch.Tensor, expert_affinities: torch.Tensor, 
 DEFAULT_PADDING_VALUE = -1
 
 
+_TORCH_TO_KERNEL_DTYPE = {torch.bfloat16: "bf16", torch.float16: "f16", torch.float32: "f32", torch.float8_e4m3fn: "e4m3",
+                          torch.float8_e5m2: "e5m2", torch.uint8: "u8", torch.int8: "s8", torch.int32: "s32", torch.int64: "s64"}
+
+
+def torch_to_nki_dtype(dtype: torch.dtype) -> str:
+    """torch dtype → the element-type name the kernels' tensor maps / epilogues are specialised on (reference
+    ``blockwise.py:33-40`` maps to ``nki.language`` dtypes)."""
+    name = _TORCH_TO_KERNEL_DTYPE.get(dtype)
+    if name is None:
+        raise ValueError(f"Unsupported torch dtype for kernel conversion: {dtype}")
+    return name
+
+
+def _resolve(imports) -> dict:
+    import warnings
+
+    from .nki_import import import_kernel
+
+    out = {}
+    for key, cfg in imports.items():
+        obj, err = import_kernel(cfg)
+        if err:
+            warnings.warn(f"Warning: {err}")
+        out[key] = obj
+    return out
+
+
+def initialize_nki_components() -> dict:
+    """Inference-side building blocks by the reference's component names (``blockwise.py:43-87``): the grouped tcgen05 GEMM that
+    every blockwise variant runs on, the device-side block-metadata build, the fused decode block, and the enums."""
+    from .nki_import import KernelImport as K
+
+    return _resolve({
+        "bwmm_shard_on_block": K("blockwise_mlp_from_metadata", module_name="modules.moe.blockwise"),
+        "bwmm_shard_on_block_mx": K("BlockwiseMatmulMXNKIFunc", module_name="modules.moe.blockwise"),
+        "blockwise_mm_baseline_shard_intermediate": K("blockwise_mlp_from_metadata", module_name="modules.moe.blockwise"),
+        "blockwise_mm_baseline_shard_intermediate_hybrid": K("blockwise_mlp_from_metadata", module_name="modules.moe.blockwise"),
+        "blockwise_mm_shard_intermediate_dropping": K("blockwise_mlp_from_metadata", module_name="modules.moe.blockwise"),
+        "moe_cte": K("blockwise_expert_mlp", module_name="modules.moe.blockwise"),
+        "grouped_gemm": K("grouped_gemm", is_kernel=True),
+        "moe_block_metadata": K("moe_block_metadata", is_kernel=True),
+        "moe_block_tkg": K("moe_block_tkg", is_kernel=True),
+        "block_shard_strategy": K("BlockShardStrategy", module_name="modules.moe.moe_configs"),
+        "skip_mode": K("SkipMode", module_name="modules.moe.moe_configs"),
+        "affinity_scale_mode": K("ExpertAffinityScaleMode", module_name="modules.moe.moe_configs"),
+        "act_fn_type": K("ActFnType", module_name="modules.moe.moe_configs"),
+    })
+
+
+def initialize_training_kernels() -> dict:
+    """Training-side kernels by the reference's names (``blockwise.py:90-104``): forward = grouped GEMMs over the block list,
+    backward = the grouped dgrad (same kernel, transposed weights) + ``grouped_wgrad``."""
+    from .nki_import import KernelImport as K
+
+    return _resolve({
+        "blockwise_mm_training": K("TorchBlockwiseTraining", module_name="modules.moe.blockwise"),
+        "blockwise_mm_baseline_shard_hidden": K("TorchBlockwiseTraining", module_name="modules.moe.blockwise"),
+        "blockwise_mm_bwd": K("grouped_wgrad", is_kernel=True),
+        "blockwise_mm_bwd_baseline_shard_hidden": K("grouped_wgrad", is_kernel=True),
+    })
+
+
 class KernelAvailabilityError(RuntimeError):
     """Raised when the grouped-GEMM kernel cannot serve a configuration (reference :88)."""
 
@@ -143,7 +213,9 @@ class BlockwiseMatmulArgs:
     down_proj_scale: Optional[torch.Tensor] = None
     output: Optional[torch.Tensor] = None
     dtype: torch.dtype = torch.bfloat16
-    expert_affinities_scaling_mode: str = "post_scale"
+    expert_affinities_scaling_mode: Any = ExpertAffinityScaleMode.POST_SCALE      # enum, its int, or "post_scale" / "pre_scale"
+    skip_dma: Any = SkipMode(False, False)
+    block_sharding_strategy: Any = BlockShardStrategy.HI_LO
     gate_clamp_upper_limit: Optional[float] = None
     gate_clamp_lower_limit: Optional[float] = None
     up_clamp_upper_limit: Optional[float] = None
@@ -197,7 +269,11 @@ def augment_inputs_for_padded_blockwise_matmul(output: torch.Tensor, hidden_stat
 def _glu_act(args: BlockwiseMatmulArgs):
     import torch.nn.functional as F
 
-    act = args.kernel_act_fn if callable(args.kernel_act_fn) else F.silu
+    act = args.kernel_act_fn
+    if isinstance(act, ActFnType):
+        act = act.fn()
+    elif not callable(act):
+        act = F.silu
 
     def f(h):
         g, u = h.chunk(2, -1)
@@ -211,10 +287,14 @@ def _glu_act(args: BlockwiseMatmulArgs):
 
 def blockwise_matmul(args: BlockwiseMatmulArgs) -> torch.Tensor:
     """Run one blockwise MLP described by ``args`` (autograd-enabled: the grouped GEMM op has its own backward)."""
-    out = blockwise_mlp_from_metadata(args.hidden_states, args.expert_affinities_masked, args.gate_up_proj_weight,
+    mode = ExpertAffinityScaleMode.coerce(args.expert_affinities_scaling_mode)
+    aff = args.expert_affinities_masked
+    if mode is ExpertAffinityScaleMode.NO_SCALE:                    # plain sum of the chosen experts: weight 1 wherever routed
+        aff = (aff != 0).to(aff.dtype)
+    out = blockwise_mlp_from_metadata(args.hidden_states, aff, args.gate_up_proj_weight,
                                       args.down_proj_weight, args.token_position_to_id, args.block_to_expert, args.block_size,
                                       _glu_act(args), args.gate_up_proj_bias, args.down_proj_bias,
-                                      pre_scale=args.expert_affinities_scaling_mode == "pre_scale")
+                                      pre_scale=mode is ExpertAffinityScaleMode.PRE_SCALE)
     if args.output is not None and args.is_tensor_update_accumulating:
         out = out + args.output
     return out

@@ -1,8 +1,9 @@
 """MoE configuration objects (reference ``modules/moe/moe_configs.py:22-273``)."""
 from __future__ import annotations
 
+import enum
 from dataclasses import dataclass
-from typing import Optional
+from typing import NamedTuple, Optional
 
 import torch
 
@@ -47,6 +48,61 @@ class RouterConfig:
         if "router_dtype" in kwargs:
             kwargs.setdefault("dtype", kwargs.pop("router_dtype"))
         return _from_kwargs(cls, kwargs)
+
+
+# ---- kernel-side enums (reference: imported from the closed kernel library at blockwise.py:57-87 and re-exported there) ----
+class ExpertAffinityScaleMode(enum.IntEnum):
+    """Where the routing weight multiplies an expert's contribution (ints as documented at reference blockwise.py:906-909)."""
+    NO_SCALE = 0
+    POST_SCALE = 1          # after the down projection (default)
+    PRE_SCALE = 2           # on the expert's input ("early affinity modulation")
+
+    @classmethod
+    def coerce(cls, v) -> "ExpertAffinityScaleMode":
+        if isinstance(v, cls):
+            return v
+        if isinstance(v, str):
+            return cls[v.upper()]
+        return cls(int(v))
+
+
+class BlockShardStrategy(enum.Enum):
+    """How a 2-core kernel split the block list on the reference hardware.  The grouped GEMM here is one persistent launch
+    over all blocks (tile scheduler), so both values run the same code; kept so configs round-trip."""
+    HI_LO = "HI_LO"
+    PING_PONG = "PING_PONG"
+
+
+class SkipMode(NamedTuple):
+    """Skip the loads of padded token rows / of weights for empty blocks.  The grouped GEMM never loads either (padding slots
+    are masked in the gather, empty blocks are not in the block list), so the flags are accepted and ignored."""
+    skip_token: bool = False
+    skip_weight: bool = False
+
+
+class ActFnType(enum.Enum):
+    SiLU = "silu"
+    GELU = "gelu"
+    GELU_Tanh_Approx = "gelu_new"
+    Swish = "sigmoid"        # x·σ(αx) with the configured scaling factor (the "swiglu" GLU type)
+
+    def fn(self):
+        import torch.nn.functional as F
+
+        return {"silu": F.silu, "gelu": F.gelu, "gelu_new": lambda x: F.gelu(x, approximate="tanh"),
+                "sigmoid": lambda x: x * torch.sigmoid(x)}[self.value]
+
+
+ActivationFunction = ActFnType
+
+
+class RouterActFnType(enum.IntEnum):
+    """Router activation as the decode kernel numbers it (``csrc/moe_tkg.cu`` ``router_act``)."""
+    SOFTMAX = 0
+    SIGMOID = 1
+
+
+ROUTER_ACT_FN_MAPPING = {"softmax": RouterActFnType.SOFTMAX, "sigmoid": RouterActFnType.SIGMOID}
 
 
 @dataclass

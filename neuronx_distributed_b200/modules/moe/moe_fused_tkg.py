@@ -18,7 +18,13 @@ from torch import nn
 from ...parallel_layers import mappings
 from ...parallel_layers import parallel_state as ps
 from ...utils.logger import get_logger
-from .moe_configs import MoEFusedTKGConfig
+from .moe_configs import (  # noqa: F401  (enums re-exported as in the reference module)
+    ROUTER_ACT_FN_MAPPING,
+    ActFnType,
+    ExpertAffinityScaleMode,
+    MoEFusedTKGConfig,
+    RouterActFnType,
+)
 
 logger = get_logger()
 
@@ -107,7 +113,7 @@ class MoEFusedTKG(nn.Module):
             return no("non-GLU experts")
         if cfg.bias:
             return no("expert biases")
-        if type(r).__name__ != "RouterTopK" or r.act_fn not in ("softmax", "sigmoid") or r.sequence_parallel_enabled:
+        if type(r).__name__ != "RouterTopK" or r.act_fn not in ROUTER_ACT_FN_MAPPING or r.sequence_parallel_enabled:
             return no(f"router {type(r).__name__} / {getattr(r, 'act_fn', None)}")
         act = ops.moe_tkg.act_id(cfg.hidden_act, cfg.glu_type)
         if act is None:
@@ -141,7 +147,7 @@ class MoEFusedTKG(nn.Module):
 
         out, logits, idx, _w = ops.moe_tkg.moe_block_tkg(
             x2, None if n is None else n.weight, r.linear_router.weight, r.linear_router.bias, op.gate_up_proj.weight,
-            op.down_proj.weight, int(op.local_expert_ids[0]), cfg.top_k, eps, 0 if r.act_fn == "softmax" else 1,
+            op.down_proj.weight, int(op.local_expert_ids[0]), cfg.top_k, eps, int(ROUTER_ACT_FN_MAPPING[r.act_fn]),
             bool(r.apply_act_fn_over_topk), bool(cfg.normalize_top_k_affinities), bool(cfg.early_expert_affinity_modulation),
             True, ops.moe_tkg.act_id(cfg.hidden_act, cfg.glu_type), float(cfg.hidden_act_scaling_factor), float(cfg.hidden_act_bias),
             (lim(cfg.gate_clamp_lower_limit, -inf), lim(cfg.gate_clamp_upper_limit, inf), lim(cfg.up_clamp_lower_limit, -inf),

@@ -20,7 +20,13 @@ from torch import nn
 from ...parallel_layers import mappings
 from ...quantization.microscaling.transform_weights import get_mxfp4_tensor, pack_fp4_x4_uint16, quantize_to_mxfp4
 from .model_utils import ACT2FN
-from .moe_configs import MoEFusedTKGConfig
+from .moe_configs import (  # noqa: F401  (enums re-exported as in the reference module)
+    ROUTER_ACT_FN_MAPPING,
+    ActFnType,
+    ExpertAffinityScaleMode,
+    MoEFusedTKGConfig,
+    RouterActFnType,
+)
 from .moe_fused_tkg import MoEFusedTKG
 
 

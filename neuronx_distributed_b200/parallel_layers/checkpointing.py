@@ -9,7 +9,7 @@ every module's ``preshard_hook`` first (padding, KV replication, QKV fusion).
 from __future__ import annotations
 
 import os
-from typing import Any, Dict, Optional
+from typing import Any, Callable, Dict, Optional
 
 import torch
 import torch.distributed as dist
@@ -17,6 +17,10 @@ from torch import nn
 
 from . import parallel_state as ps
 from .utils import cast_all
+
+
+NXD_SKIP_RENDEZVOUS = "NXD_SKIP_RENDEZVOUS"          # =1: no barriers around the filesystem operations (single-process tools)
+PreShardHookFn = Callable[[nn.Module, dict, str], bool]   # module.preshard_hook(model_state_dict, prefix)
 
 
 def _chkpt_dir(base: str, with_dp: bool = False) -> str:
@@ -27,7 +31,7 @@ def _chkpt_dir(base: str, with_dp: bool = False) -> str:
 
 
 def _barrier():
-    if dist.is_initialized() and os.environ.get("NXD_SKIP_RENDEZVOUS", "0") != "1":
+    if dist.is_initialized() and os.environ.get(NXD_SKIP_RENDEZVOUS, "0") != "1":
         dist.barrier()
 
 

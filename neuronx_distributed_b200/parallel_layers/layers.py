@@ -984,6 +984,10 @@ class BaseParallelConv(BaseParallelLayer):
             self.arg_init_method(w)
 
 
+CONV_KERNEL_OUTPUT_CHANNEL_DIMENSION = 0             # Conv2d weight is [out, in / groups, kh, kw]
+CONV_KERNEL_INPUT_CHANNEL_DIMENSION = 1
+
+
 class OutputChannelParallelConv2d(BaseParallelConv):
     """Conv2d sharded along output channels; optional all-gather on the channel dim
     (reference layers.py:1309-1430)."""
@@ -992,8 +996,8 @@ class OutputChannelParallelConv2d(BaseParallelConv):
                  bias=True, padding_mode="zeros", gather_output=True, dtype=torch.float32, device=None,
                  init_method=None, keep_master_weight=False, partition_pad=False, tensor_model_parallel_group=None):
         super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
-                         padding_mode, 0, dtype, device, init_method, keep_master_weight, tensor_model_parallel_group,
-                         partition_pad)
+                         padding_mode, CONV_KERNEL_OUTPUT_CHANNEL_DIMENSION, dtype, device, init_method, keep_master_weight,
+                         tensor_model_parallel_group, partition_pad)
         self.gather_output = gather_output
 
     def preshard_hook(self, model_state_dict: Dict[str, Any], prefix: str) -> None:
@@ -1025,8 +1029,8 @@ class InputChannelParallelConv2d(BaseParallelConv):
                  bias=True, padding_mode="zeros", input_is_parallel=False, dtype=torch.float32, device=None,
                  init_method=None, keep_master_weight=False, partition_pad=False, tensor_model_parallel_group=None):
         super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
-                         padding_mode, 1, dtype, device, init_method, keep_master_weight, tensor_model_parallel_group,
-                         partition_pad)
+                         padding_mode, CONV_KERNEL_INPUT_CHANNEL_DIMENSION, dtype, device, init_method, keep_master_weight,
+                         tensor_model_parallel_group, partition_pad)
         self.input_is_parallel = input_is_parallel
 
     def preshard_hook(self, model_state_dict: Dict[str, Any], prefix: str) -> None:

@@ -9,6 +9,9 @@ from torch import nn
 from .partition import create_partitions
 
 
+WEIGHT_SHARING_ATTR_NAME = "weight_sharing"          # parameter attribute carrying the tie-group index
+
+
 class _LocalStage(nn.Module):
     def __init__(self, layers: Sequence[nn.Module], names: Sequence[str]):
         super().__init__()
@@ -51,8 +54,14 @@ class PipelineStageModule(nn.Module):
         return _LocalStage(list(self.all_layers[lo:hi]), self.layer_names[lo:hi])
 
     def mark_weight_sharing(self, names: Sequence[str]) -> None:
-        """Declare parameters (qualified names inside ``all_layers``) that are tied across stages."""
+        """Declare parameters (qualified names inside ``all_layers``) that are tied across stages.  The parameters are also
+        tagged with ``WEIGHT_SHARING_ATTR_NAME`` = index of their tie group (how the reference marks them)."""
+        group = len(self._tied)
         self._tied.append(list(names))
+        params = dict(self.all_layers.named_parameters(remove_duplicate=False))
+        for n in names:
+            if n in params:
+                setattr(params[n], WEIGHT_SHARING_ATTR_NAME, group)
 
     def forward(self, *args, **kwargs):
         x = None

@@ -64,6 +64,12 @@ def mark_timeline(timeline, msg: str):
         timeline.mark_event_end(msg)
 
 
+# keyword names of the two batch entries a manually partitioned model is driven with (reference model.py:70-71; the
+# misspelling is the reference's public name)
+INPUTS_ARG_NAME = "inputs"
+LABLES_ARG_NAME = "labels"
+
+
 class NxDPPModel(nn.Module):
     def __init__(
         self,
@@ -492,7 +498,7 @@ class NxDPPModel(nn.Module):
                 out = st.module(leaves["hidden"])
             named = {"hidden": out}
             if st.index == self.num_stages - 1 and self.manual_pp_loss_fn is not None:
-                labels = mb.get("labels")
+                labels = mb.get(LABLES_ARG_NAME)
                 named = {"hidden": self.manual_pp_loss_fn(out, labels)}
         else:
             args = [leaves[a] if a in leaves else

@@ -81,6 +81,7 @@ def mx_matmul(a: torch.Tensor, b_packed: torch.Tensor, b_scale: torch.Tensor, ki
 # ---------------------------------------------------------------------------------------------------------------------
 VALID_MX_TYPES = (torch.uint16, torch.uint32)
 VALID_QMX_INPUT_TYPE = (torch.bfloat16, torch.float16, torch.float32)
+VALID_QMX_OUTPUT_TYPE = torch.uint32                     # online quantisation produces fp8_x4 words
 
 
 def quantize_mxfp8(in_tensor: torch.Tensor, out_x4_dtype: torch.dtype = torch.uint32,
@@ -91,7 +92,7 @@ def quantize_mxfp8(in_tensor: torch.Tensor, out_x4_dtype: torch.dtype = torch.ui
     Scale = 2^(floor(log2(amax)) − emax) with emax = 8 for e4m3 (15 for e5m2); ``use_unbiased_scale`` lowers emax by one
     (no element saturates, one bit less precision) like the reference's flag."""
     assert in_tensor.dtype in VALID_QMX_INPUT_TYPE, f"expected one of {VALID_QMX_INPUT_TYPE}, got {in_tensor.dtype}"
-    assert out_x4_dtype == torch.uint32, "online quantisation produces fp8_x4 (uint32) only"
+    assert out_x4_dtype == VALID_QMX_OUTPUT_TYPE, "online quantisation produces fp8_x4 (uint32) only"
     assert in_tensor.shape[-1] % BLOCK == 0
     emax = (8 if fp8_dtype == torch.float8_e4m3fn else 15) - (1 if use_unbiased_scale else 0)
     fmax = torch.finfo(fp8_dtype).max

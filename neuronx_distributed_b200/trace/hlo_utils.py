@@ -30,6 +30,11 @@ import torch
 from ..inference.launch_plan import LaunchPlan, PlanError
 
 TRANSPOSABLE_WEIGHT_IDX = "transposable_weight_idx"          # meta key (the reference's HLO frontend attribute)
+# Where the layout transformer of a WLO build runs when its results are serialised ahead of time instead of being recomputed
+# at every load (reference hlo_utils.py:36-38, read by ``ModelBuilder.transform_weight_layout_with_overriden_option``)
+NXD_LAYOUT_TRANSFORMATION_OPTIONS = "NXD_LAYOUT_TRANSFORMATION_OPTIONS"           # environment variable
+NXD_LAYOUT_ON_CPU_AND_SERIALIZE = "NXD_LAYOUT_ON_CPU_AND_SERIALIZE"
+NXD_LAYOUT_ON_DEVICE_AND_SERIALIZE = "NXD_LAYOUT_ON_DEVICE_AND_SERIALIZE"
 
 
 # ---- plans on disk ---------------------------------------------------------------------------------------------------------
@@ -199,7 +204,8 @@ def update_weight(weights: Dict[str, torch.Tensor], transformer: Optional[Launch
 
 
 def transform_weight_layout_on_cpu(hlo_filename: Any, metaneff_filename: Any = None, start_rank_id: int = 0, local_ranks_size: int = 1,
-                                   sharded_checkpoint_dir: Optional[str] = None) -> Dict[int, Dict[str, torch.Tensor]]:
+                                   sharded_checkpoint_dir: Optional[str] = None, device: Optional[torch.device] = None
+                                   ) -> Dict[int, Dict[str, torch.Tensor]]:
     """Run a transformer plan (path or object) over ``tp<r>_sharded_checkpoint.safetensors`` of the given ranks and write the
     derived tensors next to the weights (``tp<r>_derived.safetensors``), so that loading does not have to recompute them."""
     from ..utils.safetensors_utils import load_state_dict_safetensors, save_state_dict_safetensors
@@ -208,8 +214,10 @@ def transform_weight_layout_on_cpu(hlo_filename: Any, metaneff_filename: Any = N
     done: Dict[int, Dict[str, torch.Tensor]] = {}
     for rank in range(start_rank_id, start_rank_id + local_ranks_size):
         ckpt = load_state_dict_safetensors(os.path.join(sharded_checkpoint_dir, f"tp{rank}_sharded_checkpoint.safetensors"))
+        if device is not None:
+            ckpt = {k: v.to(device) for k, v in ckpt.items()}
         full = update_weight(ckpt, transformer)
-        derived = {k: v.contiguous() for k, v in full.items() if k.startswith("_derived_")}
+        derived = {k: v.cpu().contiguous() for k, v in full.items() if k.startswith("_derived_")}
         save_state_dict_safetensors(derived, os.path.join(sharded_checkpoint_dir, f"tp{rank}_derived.safetensors"))
         done[rank] = derived
     return done
@@ -217,8 +225,10 @@ def transform_weight_layout_on_cpu(hlo_filename: Any, metaneff_filename: Any = N
 
 def transform_weight_layout_on_device_and_save_to_disk(metaneff_filename: Any, start_rank_id: int, local_ranks_size: int,
                                                        wlt_neff_path: Any, sharded_checkpoint_dir: str) -> None:
-    """Same transformation; tensors are moved to this process's GPU for the run when one is present."""
-    transform_weight_layout_on_cpu(wlt_neff_path, metaneff_filename, start_rank_id, local_ranks_size, sharded_checkpoint_dir)
+    """Same transformation with the shard moved to this process's GPU for the run (de-quantisation / casts of a large shard are
+    bandwidth-bound: HBM instead of host memory); results are brought back and written next to the shard."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    transform_weight_layout_on_cpu(wlt_neff_path, metaneff_filename, start_rank_id, local_ranks_size, sharded_checkpoint_dir, device=dev)
 
 
 def convert_inputs_to_optimal_shape(inputs, *args, **kwargs):

@@ -44,6 +44,7 @@ class ModelBuilder:
                  model: Optional[nn.Module] = None, use_cuda_graphs: Optional[bool] = None):
         self.router, self.tp_degree, self.checkpoint_loader = router, tp_degree, checkpoint_loader
         self.world_size = world_size or tp_degree * pp_degree
+        self.start_rank_id, self.local_ranks_size = start_rank_id, local_ranks_size
         self.model = model
         self.entries: Dict[str, Dict[str, Any]] = {}
         self.use_cuda_graphs = torch.cuda.is_available() if use_cuda_graphs is None else use_cuda_graphs
@@ -143,8 +144,27 @@ class ModelBuilder:
                 for p in progs:
                     f.write(f"{k}: shapes={p.shapes} dtypes={p.dtypes} cuda_graph={p.graph is not None}\n")
 
-    def transform_weight_layout_with_overriden_option(self, *args, **kwargs) -> None:
-        """No weight-layout transformation exists (see ``trace/hlo_utils.py``)."""
+    def transform_weight_layout_with_overriden_option(self, sharded_checkpoint_dir: str, transformer: Any = None,
+                                                      option: Optional[str] = None) -> Optional[Dict[int, Dict[str, torch.Tensor]]]:
+        """Run the layout transformer of a WLO build (``compile_wlo`` → ``WLOArtifacts.transformer``, a plan object or its path)
+        over the rank shards in ``sharded_checkpoint_dir`` AHEAD of time and serialise the derived tensors
+        (``tp<r>_derived.safetensors``) so that loading does not recompute them (reference model_builder.py:1330-1369).
+        ``option`` / ``$NXD_LAYOUT_TRANSFORMATION_OPTIONS``: ``NXD_LAYOUT_ON_CPU_AND_SERIALIZE`` or
+        ``NXD_LAYOUT_ON_DEVICE_AND_SERIALIZE``; unset → nothing is done (transform at load, the default flow)."""
+        from . import hlo_utils
+
+        option = option or os.environ.get(hlo_utils.NXD_LAYOUT_TRANSFORMATION_OPTIONS)
+        if option is None:
+            return None
+        if transformer is None:
+            raise ValueError("a layout transformer (WLOArtifacts.transformer or its file) is required")
+        start, n = getattr(self, "start_rank_id", 0), getattr(self, "local_ranks_size", None) or self.tp_degree
+        if option == hlo_utils.NXD_LAYOUT_ON_CPU_AND_SERIALIZE:
+            return hlo_utils.transform_weight_layout_on_cpu(transformer, None, start, n, sharded_checkpoint_dir)
+        if option == hlo_utils.NXD_LAYOUT_ON_DEVICE_AND_SERIALIZE:
+            hlo_utils.transform_weight_layout_on_device_and_save_to_disk(None, start, n, transformer, sharded_checkpoint_dir)
+            return None
+        raise ValueError(f"Unknown layout option: {option}")
 
     def shard_checkpoint(self, serialize_path: Optional[str] = None) -> List[Dict[str, torch.Tensor]]:
         assert self.model is not None and self.checkpoint_loader is not None

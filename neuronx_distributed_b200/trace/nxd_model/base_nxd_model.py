@@ -25,7 +25,38 @@ class StateInitializer(nn.Module):
 class BaseNxDModel(nn.Module):
     """Interface of the runtime model (reference ``base_nxd_model.py:36-182``)."""
 
+    def add(self, key: str, trace_artifacts, compilation_artifacts):
+        """Register a compiled bucket under ``key`` (reference: ``add(key, hlo, neff)``)."""
+        raise NotImplementedError
+
     def get_available_keys(self):
+        raise NotImplementedError
+
+    def get_hlo(self, key: str):
+        """The program of a bucket — here its launch plan (reference: the HLO module)."""
+        raise NotImplementedError
+
+    def get_neff(self, key: str) -> bytes:
+        """The serialised executable of a bucket (reference: NEFF bytes)."""
+        raise NotImplementedError
+
+    def get_metaneff(self, key: str):
+        """Input / output / state description of a bucket (reference: MetaNeff)."""
+        raise NotImplementedError
+
+    def read_from_neuron_buffer(self, state_buffer_key: str) -> torch.Tensor:
+        """Copy of a state buffer (KV cache …) on the host."""
+        raise NotImplementedError
+
+    def write_to_neuron_buffer(self, tensor: torch.Tensor, state_buffer_key: str):
+        """Overwrite a state buffer in place from a host tensor."""
+        raise NotImplementedError
+
+    def save(self, path_to_save: str, save_weights: bool = False):
+        raise NotImplementedError
+
+    @classmethod
+    def load(cls, path_to_model: str, start_rank: int = 0):
         raise NotImplementedError
 
     def set_weights(self, sharded_checkpoint):

@@ -25,6 +25,18 @@ from torch import nn
 from .base_nxd_model import BaseNxDModel, StateInitializer  # noqa: F401
 
 
+class JITWrapper(nn.Module):
+    """A Python callable (the input flattener / output packer of a bucket) as a module, so it sits in the model's module tree
+    and is scripted / saved with it (reference ``nxd_model.py:29-39``)."""
+
+    def __init__(self, func):
+        super().__init__()
+        self.func = func
+
+    def forward(self, inputs):
+        return self.func(inputs)
+
+
 class BucketProgram:
     def __init__(self, key: str, module: nn.Module, fn: Callable, example: Tuple[torch.Tensor, ...],
                  use_cuda_graph: bool = True, warmup: int = 2):

@@ -9,6 +9,9 @@ _DTYPES = [torch.float32, torch.float16, torch.bfloat16, torch.float64, torch.in
            torch.int64, torch.bool, torch.float8_e4m3fn, torch.float8_e5m2, torch.uint16, torch.uint32]
 
 
+TORCH_DTYPES = [getattr(torch, a) for a in dir(torch) if isinstance(getattr(torch, a), torch.dtype)]   # every dtype of this build
+
+
 def get_dtype_enum(dtype: torch.dtype) -> int:
     """Stable integer code of a dtype (for metadata that must not pickle torch objects)."""
     return _DTYPES.index(dtype)

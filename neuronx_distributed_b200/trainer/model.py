@@ -73,6 +73,25 @@ class NxDModel(nn.Module):
     def load_state_dict(self, state_dict, strict: bool = True):
         return self.module.load_state_dict(state_dict, strict=strict)
 
+    # ---- Hugging Face conveniences, always answered by the user's module (also under pipeline parallelism; reference
+    # trainer/model.py:106-116) ------------------------------------------------------------------------------------------
+    @property
+    def dtype(self):
+        m = self.original_module()
+        d = getattr(m, "dtype", None)
+        if d is None:
+            p = next(iter(m.parameters()), None)
+            d = None if p is None else p.dtype
+        return d
+
+    @property
+    def config(self):
+        return self.original_module().config
+
+    @property
+    def name_or_path(self):
+        return self.original_module().name_or_path
+
     def __getattr__(self, name: str) -> Any:
         try:
             return super().__getattr__(name)

@@ -3,10 +3,20 @@
 Built on ``torch.utils._pytree`` instead of a hand-written recursive walker."""
 from __future__ import annotations
 
-from typing import Any, List, Tuple
+from typing import Any, List, NamedTuple, Tuple
 
 import torch
 from torch.utils import _pytree as pytree
+
+
+class TensorMeta(NamedTuple):
+    """What a receiver needs to allocate a tensor before its payload arrives (reference :73-83; the pipeline's p2p metadata,
+    ``pipeline/comm.py``, carries these)."""
+    tensor_index: int
+    dtype: torch.dtype
+    shape: torch.Size
+    requires_grad: bool
+    device: torch.device
 
 
 class TensorStub:
@@ -31,6 +41,10 @@ class SerializationManager:
             else:
                 stubs.append(leaf)
         return (stubs, spec), tensors
+
+    def tensor_metas(self, tensors: List[torch.Tensor]) -> List[TensorMeta]:
+        """The third element of the reference's ``serialize`` result: one :class:`TensorMeta` per extracted tensor."""
+        return [TensorMeta(i, t.dtype, t.shape, t.requires_grad, t.device) for i, t in enumerate(tensors)]
 
     def extract_stubs(self, skeleton: Any) -> List[TensorStub]:
         """The tensor placeholders of a serialised skeleton, in tensor order (what a receiver must allocate)."""

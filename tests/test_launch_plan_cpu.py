@@ -1,5 +1,7 @@
 """Launch plans (``inference/launch_plan.py``): the model-code-free inference artefact and the plan passes that take the role
 of the reference's HLO surgery (``trace/hlo_utils.py``) and TorchScript export (``trace/nxd_model/nxd_model.py:709-969``)."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -135,6 +137,25 @@ def test_hlo_utils_roles_on_plans(tmp_path):
     done = hu.transform_weight_layout_on_cpu(transformer, None, 0, 1, str(tmp_path))
     on_disk = load_state_dict_safetensors(str(tmp_path / "tp0_derived.safetensors"))
     assert set(on_disk) == set(done[0]) and all(k.startswith("_derived_") for k in on_disk)
+    # the builder-level switch (reference $NXD_LAYOUT_TRANSFORMATION_OPTIONS): unset → transform at load; CPU / device → serialise now
+    from neuronx_distributed_b200.trace.model_builder import ModelBuilder as BuilderV1
+
+    b1 = BuilderV1(tp_degree=1)
+    assert b1.transform_weight_layout_with_overriden_option(str(tmp_path), transformer) is None
+    os.remove(str(tmp_path / "tp0_derived.safetensors"))
+    again = b1.transform_weight_layout_with_overriden_option(str(tmp_path), transformer, option=hu.NXD_LAYOUT_ON_CPU_AND_SERIALIZE)
+    assert set(again[0]) == set(done[0]) and os.path.exists(str(tmp_path / "tp0_derived.safetensors"))
+    os.environ[hu.NXD_LAYOUT_TRANSFORMATION_OPTIONS] = hu.NXD_LAYOUT_ON_DEVICE_AND_SERIALIZE
+    try:
+        os.remove(str(tmp_path / "tp0_derived.safetensors"))
+        b1.transform_weight_layout_with_overriden_option(str(tmp_path), transformer)              # no GPU here: runs on the host
+        redo = load_state_dict_safetensors(str(tmp_path / "tp0_derived.safetensors"))
+        assert all(torch.equal(redo[k], on_disk[k]) for k in on_disk)
+        os.environ[hu.NXD_LAYOUT_TRANSFORMATION_OPTIONS] = "SOMETHING_ELSE"
+        with pytest.raises(ValueError):
+            b1.transform_weight_layout_with_overriden_option(str(tmp_path), transformer)
+    finally:
+        del os.environ[hu.NXD_LAYOUT_TRANSFORMATION_OPTIONS]
     full = hu.update_weight(sd, transformer)
     want = m.master.detach().float()                               # what the per-call plan consumes is the transposed cast
     assert any(v.shape == want.shape and (torch.equal(v, want) or torch.equal(v, want.t()))

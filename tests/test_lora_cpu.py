@@ -66,6 +66,23 @@ def test_lora_linear_merge_roundtrip():
     assert any(k.endswith("2.weight") for k in lm3.state_dict())
     with pytest.raises(ValueError):
         LoraModel(nn.Sequential(nn.Linear(2, 2)), LoraConfig(lora_rank=0, target_modules=["0"]))
+    # no target_modules: the architecture's default placement (config.model_type), or every projection when that does not apply
+    from neuronx_distributed_b200.modules.lora.model import MODELS_TO_LORA_TARGET_MODULES_MAPPING as table
+
+    assert table["llama"] == ["q_proj", "v_proj"] and table["gpt_neox"] == ["query_key_value"] and len(table) >= 30
+
+    class Attn(nn.Module):
+        def __init__(self, model_type):
+            super().__init__()
+            self.q_proj, self.k_proj, self.v_proj, self.o_proj = (nn.Linear(8, 8) for _ in range(4))
+            self.config = {"model_type": model_type}
+
+    def wrapped(m):
+        return sorted(n for n, c in m.module.named_children() if hasattr(c, "base_layer"))
+
+    assert wrapped(LoraModel(Attn("llama"), LoraConfig(lora_rank=2))) == ["q_proj", "v_proj"]
+    assert wrapped(LoraModel(Attn("gpt_neox"), LoraConfig(lora_rank=2))) == ["k_proj", "o_proj", "q_proj", "v_proj"]   # no fused QKV here
+    assert wrapped(LoraModel(Attn(None), LoraConfig(lora_rank=2))) == ["k_proj", "o_proj", "q_proj", "v_proj"]
 
 
 def _tp_lora(rank, world, tmp):

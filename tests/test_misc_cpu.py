@@ -260,6 +260,19 @@ def test_small_utils(tmp_path):
 
     P = namedtuple("P", "a b")
     assert uncompress_from_string(compress_to_string({"x": (1, [2]), "t": torch.ones(2)}))["x"] == (1, [2])
+    from neuronx_distributed_b200.utils.serialization import SerializationManager, TensorMeta
+
+    sm = SerializationManager()
+    skel, tens = sm.serialize({"a": torch.ones(2, 3, requires_grad=True), "b": [torch.zeros(4, dtype=torch.int64), 5]})
+    metas = sm.tensor_metas(tens)
+    assert metas == [TensorMeta(0, torch.float32, torch.Size([2, 3]), True, torch.device("cpu")),
+                     TensorMeta(1, torch.int64, torch.Size([4]), False, torch.device("cpu"))]
+    back = sm.deserialize(skel, [torch.empty(m.shape, dtype=m.dtype, device=m.device) for m in metas])   # receiver side
+    assert back["a"].shape == (2, 3) and back["b"][1] == 5
+    from neuronx_distributed_b200.trace.nxd_model.nxd_model import JITWrapper
+
+    jw = JITWrapper(lambda xs: [x * 2 for x in xs])
+    assert isinstance(jw, torch.nn.Module) and jw([torch.ones(1)])[0].item() == 2
     assert is_instance_namedtuple(P(1, 2)) and not is_instance_namedtuple((1, 2))
     sb = shift_labels({"input_ids": torch.arange(6).view(2, 3), "labels": torch.arange(6).view(2, 3)})
     assert sb["labels"].tolist() == [[1, 2, -100], [4, 5, -100]] and sb["input_ids"].tolist() == [[0, 1, 2], [3, 4, 5]]

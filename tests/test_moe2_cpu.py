@@ -108,6 +108,34 @@ def _modes(rank, world):
         torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(BlockwiseMatmulNKIFunc.apply(x, am, w1, w2, tp2id, b2e, B), y_or, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(em.torch_blockwise_matmul_inference(x, am, idx), y_or, rtol=1e-4, atol=1e-4)
+    # kernel-side enums of the reference's entry points (re-exported by blockwise as there) and the kernel resolver
+    from neuronx_distributed_b200.modules.moe import blockwise as bw
+    from neuronx_distributed_b200.modules.moe.nki_import import NKIImport, import_nki, import_nki_beta2
+
+    post = blockwise_matmul(BlockwiseMatmulArgs(x, am, w1, w2, tp2id, b2e, B, expert_affinities_scaling_mode=bw.ExpertAffinityScaleMode.POST_SCALE,
+                                                skip_dma=bw.SkipMode(True, False), block_sharding_strategy=bw.BlockShardStrategy.PING_PONG,
+                                                kernel_act_fn=bw.ActFnType.SiLU))
+    torch.testing.assert_close(post, y_or, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(blockwise_matmul(BlockwiseMatmulArgs(x, am, w1, w2, tp2id, b2e, B, expert_affinities_scaling_mode=1)), post)
+    none = blockwise_matmul(BlockwiseMatmulArgs(x, am, w1, w2, tp2id, b2e, B, expert_affinities_scaling_mode=bw.ExpertAffinityScaleMode.NO_SCALE))
+    ones = blockwise_matmul(BlockwiseMatmulArgs(x, (am != 0).to(am.dtype), w1, w2, tp2id, b2e, B))
+    torch.testing.assert_close(none, ones)                                  # NO_SCALE = plain sum over the chosen experts
+    pre = blockwise_matmul(BlockwiseMatmulArgs(x, am, w1, w2, tp2id, b2e, B, expert_affinities_scaling_mode="pre_scale"))
+    assert not torch.allclose(pre, post) and bw.ExpertAffinityScaleMode.coerce(2) is bw.ExpertAffinityScaleMode.PRE_SCALE
+    assert bw.ActivationFunction is bw.ActFnType and bw.torch_to_nki_dtype(torch.bfloat16) == "bf16"
+    with pytest.raises(ValueError):
+        bw.torch_to_nki_dtype(torch.complex64)
+    fn, err = import_nki(NKIImport("blockwise_mlp_from_metadata", module_name="modules.moe.blockwise"))
+    assert fn is bw.blockwise_mlp_from_metadata and err is None
+    fn, err = import_nki_beta2(NKIImport("no_such_kernel", module_name="moe.moe_cte.bwmm_shard_on_block", is_kernel=False))
+    assert fn is None and "no_such_kernel" in err
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                                     # device entry points warn when the extension is not built
+        comps, train = bw.initialize_nki_components(), bw.initialize_training_kernels()
+    assert comps["moe_cte"] is bw.blockwise_expert_mlp and comps["affinity_scale_mode"] is bw.ExpertAffinityScaleMode
+    assert train["blockwise_mm_training"] is TorchBlockwiseTraining and set(train) >= {"blockwise_mm_bwd"}
     o, h, ids, a = augment_inputs_for_padded_blockwise_matmul(torch.zeros(T, H), x, tp2id, am)
     assert o.shape == (T + 1, H) and h[-1].abs().sum() == 0 and ids.min() >= 0 and (ids == T).sum() == (tp2id < 0).sum() and a.shape == (T + 1, E)
     assert not can_use_blockwise_matmul_nki(H, I, 128, device=torch.device("cpu"))

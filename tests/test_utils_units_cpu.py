@@ -70,3 +70,33 @@ def test_rope_polar_compatible_equals_complex_rotation():
     plain = precompute_freqs_cis(D, S, theta=500000.0)
     assert torch.equal(scaled[:, 0], plain[:, 0]) and not torch.equal(scaled[:, -1], plain[:, -1])
     assert math.isclose(float(table[0, 0, 0]), 1.0) and float(table[0, 0, 1]) == 0.0
+    # Hugging Face ``rope_scaling`` keys are accepted as keywords; the defaults are the Llama-3.1 values
+    from neuronx_distributed_b200.modules.attention.utils import ROPE_DEFAULTS, apply_scaling
+
+    f = 1.0 / (500000.0 ** (torch.arange(0, D, 2).float() / D))
+    assert torch.equal(apply_scaling(f), apply_scaling(f, **ROPE_DEFAULTS)) and torch.equal(apply_scaling(f), apply_scaling(f, 8.0, 1.0, 4.0, 8192))
+    assert not torch.equal(apply_scaling(f, factor=32.0), apply_scaling(f))
+    assert torch.equal(precompute_freqs_cis(D, S, theta=500000.0, use_scaled=True, factor=32.0, rope_type="llama3")[:, 0], plain[:, 0])
+
+
+def test_reference_named_constants_are_wired():
+    """Module-level names of the reference that code may import: present, and the behaviour behind them uses them."""
+    from torch import nn
+
+    from neuronx_distributed_b200.modules.moe.moe_fused_tkg import ROUTER_ACT_FN_MAPPING, RouterActFnType
+    from neuronx_distributed_b200.parallel_layers import checkpointing, layers
+    from neuronx_distributed_b200.pipeline import manual_pipe_stage as mps
+    from neuronx_distributed_b200.pipeline import model as ppm
+    from neuronx_distributed_b200.trace.nxd_model.utils import TORCH_DTYPES, get_dtype_enum, get_dtype_from_enum
+
+    assert (ppm.INPUTS_ARG_NAME, ppm.LABLES_ARG_NAME) == ("inputs", "labels")
+    assert (layers.CONV_KERNEL_OUTPUT_CHANNEL_DIMENSION, layers.CONV_KERNEL_INPUT_CHANNEL_DIMENSION) == (0, 1)
+    assert checkpointing.NXD_SKIP_RENDEZVOUS == "NXD_SKIP_RENDEZVOUS" and checkpointing.PreShardHookFn is not None
+    assert torch.bfloat16 in TORCH_DTYPES and get_dtype_from_enum(get_dtype_enum(torch.bfloat16)) is torch.bfloat16
+    assert ROUTER_ACT_FN_MAPPING["sigmoid"] is RouterActFnType.SIGMOID and int(RouterActFnType.SOFTMAX) == 0
+    emb, head = nn.Embedding(8, 4), nn.Linear(4, 8, bias=False)
+    head.weight = emb.weight
+    stage = mps.PipelineStageModule([emb, head], num_stages=1, stage_index=0)
+    stage.mark_weight_sharing(["0.weight", "1.weight"])
+    assert getattr(emb.weight, mps.WEIGHT_SHARING_ATTR_NAME) == 0 and getattr(head.weight, mps.WEIGHT_SHARING_ATTR_NAME) == 0
+
