@@ -403,9 +403,22 @@ class ExpertMLPsV2(ProcessGroupSafeDeepcopy, nn.Module):
 
 
 def create_spmd_ranks(model_state_dict, prefix: str, world_size: int, n_routed_experts: Optional[int] = None,
-                      expert_model_parallel_group=None, spmd_rank_name: str = "spmd_rank") -> None:
-    """Reference :1501-1530 — add ``{prefix}{spmd_rank_name}.rank = arange(world)`` to a full checkpoint."""
+                      expert_model_parallel_group=None, spmd_rank_name: str = "spmd_rank", expert_distribution=None) -> None:
+    """Reference :1501-1530 — add ``{prefix}{spmd_rank_name}.rank = arange(world)`` to a full checkpoint and, with expert
+    parallelism, ``….local_expert_indices`` ``[world, experts per EP rank]``: the logical experts every global rank hosts
+    (contiguous blocks, or ``expert_distribution[ep_rank]`` when experts are placed explicitly / redundantly)."""
     model_state_dict[f"{prefix}{spmd_rank_name}.rank"] = torch.arange(0, world_size, dtype=torch.int32)
+    ep = 1 if expert_model_parallel_group is None else (
+        expert_model_parallel_group.size() if hasattr(expert_model_parallel_group, "size") else int(expert_model_parallel_group))
+    if ep > 1:
+        assert n_routed_experts is not None, "n_routed_experts is required with expert parallelism"
+        rows = []
+        for rank in range(world_size):
+            ep_rank = ps.get_expert_parallel_rank_from_global_rank(rank, expert_model_parallel_group)
+            rows.append(ps.get_experts_for_expert_parallel_rank(ep_rank, total_number_of_experts=n_routed_experts,
+                                                                expert_model_parallel_size=ep,
+                                                                expert_distribution=expert_distribution))
+        model_state_dict[f"{prefix}{spmd_rank_name}.local_expert_indices"] = torch.tensor(rows, dtype=torch.int32)
 
 
 def duplicate_and_replace_prefixes(old_prefix: str, new_prefix: str, model_state_dict) -> None:

@@ -54,9 +54,21 @@ class MoE(nn.Module):
             y = mappings.reduce_from_tensor_model_parallel_region(y, ps.get_expert_model_parallel_group())
         return y
 
-    def forward(self, hidden_states: torch.Tensor, padding_mask: Optional[torch.Tensor] = None):
-        if self.moe_fused_tkg is not None and not self.training and hidden_states.shape[self.sequence_dimension] == 1:
-            return self.moe_fused_tkg(hidden_states)
+    def forward(self, hidden_states: torch.Tensor, padding_mask: Optional[torch.Tensor] = None,
+                is_speculative_decoding: bool = False, residual: Optional[torch.Tensor] = None):
+        """Returns ``(output, [router_logits], [expert_index], [residual])``.  ``residual`` (same layout as ``hidden_states``):
+        the layer computes on ``hidden_states + residual`` and also returns that sum, the residual stream after the attention
+        block (fused into the decode kernel on the token-generation path).  ``is_speculative_decoding``: a short verification
+        window is served by the decode block as well (reference model.py:260-303)."""
+        decode = hidden_states.shape[self.sequence_dimension] == 1 or is_speculative_decoding
+        if self.moe_fused_tkg is not None and not self.training and decode:
+            return self.moe_fused_tkg(hidden_states) if residual is None else self.moe_fused_tkg(hidden_states, residual=residual)
+        if residual is not None:
+            hidden_states = hidden_states + residual
+            return self._forward_compute_bound(hidden_states, padding_mask) + (hidden_states,)
+        return self._forward_compute_bound(hidden_states, padding_mask)
+
+    def _forward_compute_bound(self, hidden_states: torch.Tensor, padding_mask: Optional[torch.Tensor] = None) -> Tuple:
         x = self.rmsnorm(hidden_states) if self.rmsnorm is not None else hidden_states
         perm = None
         if self.token_shuffle_group_size > 1:

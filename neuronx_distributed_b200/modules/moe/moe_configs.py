@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import enum
 from dataclasses import dataclass
-from typing import NamedTuple, Optional
+from typing import Any, NamedTuple, Optional
 
 import torch
 
@@ -107,16 +107,25 @@ ROUTER_ACT_FN_MAPPING = {"softmax": RouterActFnType.SOFTMAX, "sigmoid": RouterAc
 
 @dataclass
 class BlockwiseMatmulConfig:
+    """Field order of reference moe_configs.py:22-99 (all required there; defaults = its ``default()`` values).  The flags that
+    picked between the reference's kernel variants (2-core sharding, dynamic-while block loops, static block counts, padding
+    the block count to even, the autograd class) have no effect: every variant is the one persistent grouped GEMM whose block
+    list is data, not a compile-time count."""
     block_size: int = 512
     use_block_parallel: bool = False
-    use_torch_block_wise: bool = False      # force the PyTorch reference instead of the CUDA grouped GEMM
+    block_sharding_strategy: Any = "HI_LO"               # BlockShardStrategy or its name
     skip_dma_token: bool = False
     skip_dma_weight: bool = False
     logical_nc_config: int = 1
+    blockwise_nki_autograd_cls: Any = None
+    use_torch_block_wise: bool = False      # force the PyTorch reference instead of the CUDA grouped GEMM
     parallelize_token_to_block_mapping: bool = True
     optimized_block_to_token_mapping: bool = True
     always_augment_inputs_for_blockwise_matmul: bool = False
-    block_sharding_strategy: str = "HI_LO"
+    use_shard_on_intermediate_dynamic_while: bool = False
+    use_shard_on_block_dynamic_while: bool = False
+    num_static_blocks: Optional[int] = None
+    pad_num_blocks_to_even: bool = False
 
     @classmethod
     def default(cls) -> "BlockwiseMatmulConfig":
@@ -124,35 +133,40 @@ class BlockwiseMatmulConfig:
 
     @classmethod
     def from_kwargs(cls, **kwargs) -> "BlockwiseMatmulConfig":
-        kwargs = dict(kwargs)
-        kwargs.pop("blockwise_nki_autograd_cls", None)       # kernel-class selection has no counterpart (one grouped GEMM)
-        return _from_kwargs(cls, kwargs)
+        return _from_kwargs(cls, dict(kwargs))
 
 
 @dataclass
 class RoutedExpertsMLPOpsConfig:
+    """Field order and defaults of reference moe_configs.py:102-160 (the first six are required there; the defaults here only
+    add convenience).  ``*_actual`` / ``is_*_dim_shuffled`` describe a checkpoint whose hidden / intermediate dims were padded
+    or permuted offline for the reference's kernels — recorded, not needed by the grouped GEMM."""
     num_experts: int = 8
-    top_k: int = 2
     hidden_size: int = 1024
     intermediate_size: int = 4096
+    top_k: int = 2
     hidden_act: str = "silu"
     glu_mlp: bool = True
-    glu_type: str = "glu"                    # "glu" | "swiglu"
     bias: bool = False
-    capacity_factor: Optional[float] = None  # None → dropless
-    normalize_top_k_affinities: bool = True
-    early_expert_affinity_modulation: bool = False
+    glu_type: str = "glu"                    # "glu" | "swiglu" (or the GLUType enum)
     hidden_act_scaling_factor: float = 1.0
     hidden_act_bias: float = 0.0
+    hidden_size_actual: Optional[int] = None
+    intermediate_size_actual: Optional[int] = None
+    is_hidden_dim_shuffled: Optional[bool] = None
+    is_intermediate_dim_shuffled: Optional[bool] = None
+    use_index_calc_kernel: bool = True
     gate_clamp_upper_limit: Optional[float] = None
     gate_clamp_lower_limit: Optional[float] = None
     up_clamp_upper_limit: Optional[float] = None
     up_clamp_lower_limit: Optional[float] = None
-    enable_spmd_rank: bool = False
+    normalize_top_k_affinities: bool = False
+    early_expert_affinity_modulation: bool = False
     input_layer_init_method: Optional[object] = None
     output_layer_init_method: Optional[object] = None
-    use_index_calc_kernel: bool = True
-    is_prefill: bool = True
+    capacity_factor: Optional[float] = None  # None → dropless
+    enable_spmd_rank: bool = False
+    is_prefill: Optional[bool] = None
     expert_distribution: Optional[list] = None       # [ep_rank][slot] → logical expert id (redundant experts allowed)
 
     def __post_init__(self):
@@ -173,11 +187,13 @@ class RoutedExpertsMLPOpsConfig:
 
 @dataclass
 class MoEFusedTKGConfig:
-    """Decode-time fused path (RMSNorm → router → experts → shared experts, reference K8)."""
+    """Decode-time fused path (RMSNorm → router → experts → shared experts, reference K8; fields / defaults of reference
+    moe_configs.py:236-273).  The ``*_kernel_enabled`` switches are tri-state: ``None`` = use the kernel whenever it applies."""
     quantized: bool = False
-    moe_fused_kernel_enabled: bool = True
-    router_topk_kernel_enabled: bool = True
-    expert_mlp_kernel_enabled: bool = True
-    shared_mlp_kernel_enabled: bool = True
-    norm_topk_prob: bool = True
-    is_mxfp4_compute: bool = False
+    moe_fused_kernel_enabled: Optional[bool] = None
+    router_topk_kernel_enabled: Optional[bool] = None
+    expert_mlp_kernel_enabled: Optional[bool] = None
+    shared_mlp_kernel_enabled: Optional[bool] = None
+    norm_topk_prob: bool = False
+    is_mxfp4_compute: Optional[bool] = None
+    router_mm_dtype: torch.dtype = torch.float32      # accumulation / output dtype of the router GEMV (the kernel keeps fp32)

@@ -118,9 +118,14 @@ def mxfp4_moe_block_tkg_wrapper(inp: torch.Tensor, gamma: Optional[torch.Tensor]
 class MoEFusedTKGMX(MoEFusedTKG):
     """``MoEFusedTKG`` whose routed experts run from MXFP4 copies of the weights (``config.is_mxfp4_compute``)."""
 
-    def __init__(self, router: nn.Module, expert_mlps: nn.Module, shared_experts: Optional[nn.Module] = None,
-                 rmsnorm: Optional[nn.Module] = None, config: Optional[MoEFusedTKGConfig] = None):
-        super().__init__(router, expert_mlps, shared_experts, rmsnorm, config)
+    def __init__(self, router: nn.Module, expert_mlps: nn.Module, shared_experts=None, rmsnorm=None,
+                 config: Optional[MoEFusedTKGConfig] = None, sequence_dimension: int = 0,
+                 post_attention_layernorm: Optional[nn.Module] = None, tensor_model_parallel_group=None,
+                 logical_nc_config: int = 1, return_router_logits: bool = False, return_expert_index: bool = False):
+        """Same two constructor orders as :class:`MoEFusedTKG` (this package's and the reference's
+        ``(router, expert_mlps, config, sequence_dimension, shared_experts, post_attention_layernorm, …)``)."""
+        super().__init__(router, expert_mlps, shared_experts, rmsnorm, config, sequence_dimension, post_attention_layernorm,
+                         tensor_model_parallel_group, logical_nc_config, return_router_logits, return_expert_index)
         self.config.is_mxfp4_compute = True
         self.prepare_mx_weights()
 
@@ -136,7 +141,7 @@ class MoEFusedTKGMX(MoEFusedTKG):
     def forward(self, hidden_states: torch.Tensor, residual: Optional[torch.Tensor] = None):
         x = hidden_states if residual is None else hidden_states + residual
         h = self._norm(x) if self._norm is not None else x
-        _, aff, idx = self._router(h)
+        logits, aff, idx = self._router(h)
         em, ops = self._experts, self._experts.mlp_op
         flat = h.reshape(-1, h.shape[-1])
         a = em._topk_affinities(aff, idx)                                           # [T, E]
@@ -152,5 +157,10 @@ class MoEFusedTKGMX(MoEFusedTKG):
         y = torch.einsum("eth,te->th", y, a[:, local].float()).to(h.dtype).view(h.shape)
         if self._shared is not None:
             y = y + self._shared(h)
-        y = mappings.reduce_from_tensor_model_parallel_region(y)
-        return (y,) if residual is None else (y, x)
+        y = self._reduce(y)
+        out = (y,)
+        if self.return_router_logits:
+            out += (logits,)
+        if self.return_expert_index:
+            out += (idx,)
+        return out if residual is None else out + (x,)

@@ -16,11 +16,13 @@ from ..parallel_layers import parallel_state as ps
 
 
 def argmax(tensor: torch.Tensor, dim: int, gather_dim: Optional[int] = None, keepdim: bool = False,
-           process_group=None, rank_id: Optional[torch.Tensor] = None) -> torch.Tensor:
+           process_group=None, disable_argmax_kernel: bool = False, rank_id: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Positional order of the reference (argmax.py:106-113); ``disable_argmax_kernel`` forces ``torch.max`` for the local
+    reduction instead of the one-pass row arg-max kernel."""
     group = process_group if process_group is not None else ps.get_tensor_model_parallel_group()
     n = dist.get_world_size(group)
     dim = dim % tensor.dim()
-    if dim == tensor.dim() - 1 and tensor.is_cuda:
+    if dim == tensor.dim() - 1 and tensor.is_cuda and not disable_argmax_kernel:
         from ..ops import select as _select           # one-pass row arg-max kernel (csrc/select.cu, role of NKI cascaded_max)
 
         val, idx = _select.row_max(tensor)

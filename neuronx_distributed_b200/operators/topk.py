@@ -11,8 +11,11 @@ from ..parallel_layers import comm
 from ..parallel_layers import parallel_state as ps
 
 
-def topk(tensor: torch.Tensor, k: int, dim: int, gather_dim: Optional[int] = None, process_group=None,
-         rank_id: Optional[torch.Tensor] = None, stages: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+def topk(tensor: torch.Tensor, k: int, dim: int, gather_dim: Optional[int] = None, process_group=None, stages: int = 1,
+         rank_id: Optional[torch.Tensor] = None, use_topk_rotated_kernel: bool = False, lnc: int = 2
+         ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Positional order of the reference (topk.py:31-42).  ``use_topk_rotated_kernel`` / ``lnc`` select between two device
+    kernels there; here one selection kernel serves every case, so they are accepted and ignored."""
     group = process_group if process_group is not None else ps.get_tensor_model_parallel_group()
     n = dist.get_world_size(group)
     dim = dim % tensor.dim()

@@ -81,12 +81,14 @@ def get_sharded_model_dict(model: nn.Module, model_state_dict: Dict[str, Any]) -
 
 
 def load(chkpt_path: str, model: Optional[nn.Module] = None, model_or_optimizer: Any = None, model_key: Optional[str] = "model",
-         load_xser: bool = False, sharded: bool = True, strict: bool = True, weights_only: bool = False) -> Dict[str, Any]:
-    """Load a legacy checkpoint.  ``sharded=True``: read this rank's ``tp_rank_XX_pp_rank_XX`` file;
+         load_xser: bool = False, sharded: bool = True, strict: bool = True, master_dp_only: bool = True,
+         weights_only: bool = False) -> Dict[str, Any]:
+    """Load a legacy checkpoint.  ``sharded=True``: read this rank's ``tp_rank_XX_pp_rank_XX`` file (``master_dp_only=False``:
+    the per-DP-rank file ``…_dp_rank_XX`` written by ``save(master_dp_only=False)`` — ZeRO-sharded optimizer state);
     ``sharded=False``: ``chkpt_path`` is one full checkpoint file that is sharded on the fly."""
     target = model if model is not None else model_or_optimizer
     if sharded:
-        d = _chkpt_dir(chkpt_path)
+        d = _chkpt_dir(chkpt_path, with_dp=not master_dp_only)
         f = os.path.join(d, "checkpoint.pt")
         from ..trainer.checkpoint import _torch_xla_pickle_names
 

@@ -17,6 +17,7 @@ coincides with this for tp=1.
 """
 from __future__ import annotations
 
+from typing import Optional
 
 import torch
 import torch.distributed as dist
@@ -109,6 +110,7 @@ class DistributedLogprob(torch.autograd.Function):
         else:
             gmax, sumexp, pred = stats[:, 0], stats[:, 1], stats[:, 2]
         lse = gmax + torch.log(sumexp)
+        ctx.inference_only = bool(inference_only)
         if not inference_only:
             ctx.save_for_backward(logits2d, tgt, lse)
             ctx.start, ctx.shape, ctx.vocab = start, vocab_parallel_logits.shape, vp * n
@@ -118,6 +120,8 @@ class DistributedLogprob(torch.autograd.Function):
     def backward(ctx, grad_output):
         from .. import ops
 
+        if ctx.inference_only:
+            raise RuntimeError("log-probs computed with inference=True keep no state for backward; pass inference=False")
         logits2d, tgt, lse = ctx.saved_tensors
         # d(logp)/dlogits = onehot - softmax = -(softmax - onehot)
         g = ops.cross_entropy.ce_backward(
@@ -126,11 +130,16 @@ class DistributedLogprob(torch.autograd.Function):
         return g.view(ctx.shape), None, None, None
 
 
-def from_parallel_logits_to_logprobs(vocab_parallel_logits, target, inference_only: bool = False, process_group=None):
-    """Log-probabilities of ``target[:, 1:]`` under ``logits[:, :-1]`` (next-token shift as in the
-    reference :206-215)."""
+def from_parallel_logits_to_logprobs(vocab_parallel_logits, target, inference: bool = True, process_group=None,
+                                     inference_only: Optional[bool] = None):
+    """Log-probabilities of ``target[:, 1:]`` under ``logits[:, :-1]`` (next-token shift as in the reference :206-215;
+    pass the UNSHIFTED targets).  ``inference=True`` (the reference's default) keeps nothing for a backward pass; pass
+    ``inference=False`` when the log-probs feed a training objective (DPO / ORPO).  ``inference_only`` is this package's
+    earlier name of the same flag."""
+    if inference_only is not None:
+        inference = inference_only
     target = target.roll(shifts=-1, dims=-1)
-    probs = DistributedLogprob.apply(vocab_parallel_logits, target, inference_only, process_group)
+    probs = DistributedLogprob.apply(vocab_parallel_logits, target, inference, process_group)
     return probs[:, :-1].contiguous()
 
 

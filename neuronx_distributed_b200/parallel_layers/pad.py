@@ -16,21 +16,48 @@ from .layers import ColumnParallelLinear, RowParallelLinear
 from .utils import divide
 
 
-def get_number_of_extra_heads(num_heads: int, tp_degree: int) -> int:
-    return (-num_heads) % tp_degree
+def get_number_of_extra_heads(n_head: int, tp_degree: int) -> int:
+    """Heads to add so that ``n_head`` divides ``tp_degree`` (reference :14-27)."""
+    return (-n_head) % tp_degree
 
 
-def generate_padding_mask(num_heads: int, num_heads_with_pad: int, num_kv_heads: int, num_kv_heads_with_pad: int,
-                          tp_degree: int, kv_layout: str = "tile"):
-    """Boolean masks (True = real head) over the padded Q and KV head slots as laid out on this TP group.
-    With ``kv_layout='tile'`` KV heads repeat K0..Kn,K0..Kn…; with ``'adjacent'`` each head repeats
-    consecutively (the two replication layouts of :mod:`modules.qkv_linear`)."""
+def generate_padding_mask(num_heads: int, num_heads_with_pad: int, num_kv_heads: int, tp_degree: int, tp_rank: int,
+                          hardware_type=None, kv_layout: Optional[str] = None) -> torch.Tensor:
+    """1-D mask over the query heads held by ``tp_rank`` (length ``num_heads_with_pad / tp_degree``): True for heads of the
+    original model, False for heads that exist only because the query heads were padded (reference :114-185).
+
+    With GQA and ``tp_degree > num_kv_heads`` the KV heads are replicated and the query heads of one KV head are spread over the
+    ranks holding its replicas, so WHICH local heads are padding depends on the replication layout (``modules.qkv_linear``):
+    ``"tile"`` (K0..Kn, K0..Kn, … — replica index = ``tp_rank // num_kv_heads``; the reference's first-generation layout) or
+    ``"adjacent"`` (K0,K0,…,K1,K1,… — replica index = ``tp_rank % replicas``).  ``hardware_type`` is accepted for source
+    compatibility: the strings ``"trn1"`` / ``"trn2"`` select ``"tile"`` / ``"adjacent"``; otherwise ``kv_layout`` (default
+    ``"tile"``, the default of ``GQAQKVColumnParallelLinear``) decides."""
+    if kv_layout is None:
+        name = str(getattr(hardware_type, "value", hardware_type)).lower() if isinstance(hardware_type, str) else ""
+        kv_layout = "adjacent" if name == "trn2" else "tile"
+    per_rank = num_heads_with_pad // tp_degree
+    per_kv = num_heads // num_kv_heads
+    if kv_layout == "tile":
+        replica = tp_rank // num_kv_heads
+        limit = per_kv
+    elif kv_layout == "adjacent":
+        replicas = max(tp_degree // num_kv_heads, 1)
+        replica = tp_rank % replicas
+        limit = per_kv * ((num_kv_heads * replicas) // tp_degree)         # local KV heads × query heads per KV head
+    else:
+        raise RuntimeError(f"Unexpected KV replication layout {kv_layout!r} in padding mask generation.")
+    mask = torch.arange(per_rank * replica, per_rank * (replica + 1)) < limit
+    mask.requires_grad = False
+    return mask
+
+
+def generate_global_padding_masks(num_heads: int, num_heads_with_pad: int, num_kv_heads: int, num_kv_heads_with_pad: int,
+                                  tp_degree: int):
+    """Masks over ALL padded query / KV head slots of the unsharded model (True = real head; replicated KV heads are real)."""
     q_mask = torch.arange(num_heads_with_pad) < num_heads
     kv_mask = torch.arange(num_kv_heads_with_pad) < num_kv_heads
     if num_kv_heads_with_pad > num_kv_heads and num_kv_heads_with_pad % num_kv_heads == 0 and num_kv_heads < tp_degree:
-        rep = num_kv_heads_with_pad // num_kv_heads
-        kv_mask = torch.ones(num_kv_heads_with_pad, dtype=torch.bool)  # replicated real heads, none padded
-        del rep
+        kv_mask = torch.ones(num_kv_heads_with_pad, dtype=torch.bool)
     return q_mask, kv_mask
 
 

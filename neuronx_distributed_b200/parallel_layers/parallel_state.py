@@ -179,14 +179,18 @@ def arrange_kv_groups(
     tensor_model_parallel_size: int = 1,
     kv_shared_group_size: int = 1,
     sequential_ranks_in_group: bool = False,
+    hardware_type: Any = None,
     adjacent_replication: bool = False,
 ) -> List[List[int]]:
     """Ranks that hold replicas of the same KV head (GQA with kv_heads < tp).
 
     ``sequential_ranks_in_group``/``adjacent_replication`` → [[0,1],[2,3]]; default is the
-    interleaved layout [[0,2],[1,3]] (reference parallel_state.py:1605-1645; the hardware
-    enum there collapses to the ``adjacent_replication`` flag here).
+    interleaved layout [[0,2],[1,3]] (reference parallel_state.py:1605-1645).  The reference
+    picks the adjacent layout by hardware generation; ``hardware_type="trn2"`` is accepted
+    and means ``adjacent_replication=True``, anything else leaves the flags in charge.
     """
+    if isinstance(hardware_type, str) and hardware_type.lower() == "trn2":
+        adjacent_replication = True
     tp, k = tensor_model_parallel_size, kv_shared_group_size
     groups: List[List[int]] = []
     if sequential_ranks_in_group or adjacent_replication:

@@ -94,6 +94,11 @@ def _legacy(rank, world, root):
         m[0].weight.zero_(); m[1].weight.zero_()
     checkpointing.load(os.path.join(root, "full.pt"), model=m, sharded=False)
     torch.testing.assert_close(m[0].weight, w0)
+    # per-DP-rank files (state that differs across data-parallel ranks): written and read back with master_dp_only=False
+    per_dp = os.path.join(root, "per_dp")
+    checkpointing.save({"step": torch.tensor(7 + rank)}, per_dp, master_dp_only=False)
+    assert os.path.isfile(os.path.join(per_dp, f"tp_rank_{rank:02d}_pp_rank_00_dp_rank_00", "checkpoint.pt"))
+    assert int(checkpointing.load(per_dp, master_dp_only=False)["step"]) == 7 + rank
 
 
 def test_legacy_checkpoint(tmp_path):

@@ -185,7 +185,7 @@ def _zero_dcp_and_ep(rank, world, tmp):
     ps.initialize_model_parallel(tensor_model_parallel_size=1, expert_model_parallel_size=world)
     torch.manual_seed(0)
     E, k, H, I = 4, 2, 8, 16
-    layer = MoE(RouterTopK(E, k, H), ExpertMLPsV2(RoutedExpertsMLPOpsConfig(num_experts=E, top_k=k, hidden_size=H,
+    layer = MoE(RouterTopK(E, k, H), ExpertMLPsV2(RoutedExpertsMLPOpsConfig(normalize_top_k_affinities=True, num_experts=E, top_k=k, hidden_size=H,
                                                                               intermediate_size=I, capacity_factor=4.0)))
     opt = NeuronEPZero1Optimizer(layer.parameters(), torch.optim.AdamW, lr=1e-2, grad_clipping=True, max_norm=1.0)
     before = [p_.detach().clone() for p_ in layer.parameters()]

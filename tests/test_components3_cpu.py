@@ -18,7 +18,7 @@ def _quant_moe(rank, world):
     ps.initialize_model_parallel(tensor_model_parallel_size=world)
     torch.manual_seed(0)
     E, k, H, I, T = 4, 2, 32, 64, 6
-    cfg = RoutedExpertsMLPOpsConfig(num_experts=E, top_k=k, hidden_size=H, intermediate_size=I)
+    cfg = RoutedExpertsMLPOpsConfig(normalize_top_k_affinities=True, num_experts=E, top_k=k, hidden_size=H, intermediate_size=I)
     router, experts = RouterTopK(E, k, H), ExpertMLPsV2(cfg)
     shared = SharedExperts(H, 16, fused_gate_up_projection=True)
     norm = RMSNorm(H)

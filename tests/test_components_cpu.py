@@ -2,6 +2,7 @@
 input-channel parallel conv, pad_model, RNG tracker, grad norm / clip, DistributedLogprob, the extra routers, shared experts,
 token shuffling."""
 
+import pytest
 import torch
 from torch import nn
 
@@ -62,8 +63,21 @@ def _conv_pad_rng(rank, world):
     torch.testing.assert_close(y, ref, rtol=1e-4, atol=1e-4)
     # head padding helpers
     assert get_number_of_extra_heads(6, 4) == 2 and get_number_of_extra_heads(8, 4) == 0
-    q_mask, kv_mask = generate_padding_mask(6, 8, 2, 2, 4)
+    from neuronx_distributed_b200.parallel_layers.pad import generate_global_padding_masks
+
+    q_mask, kv_mask = generate_global_padding_masks(6, 8, 2, 2, 4)
     assert q_mask.tolist() == [True] * 6 + [False] * 2 and kv_mask.tolist() == [True, True]
+    # per-rank mask (the reference's docstring example): 48 query heads padded to 64, 8 KV heads replicated 4x, TP=32 →
+    # 2 local heads; the 6 query heads of a KV head fill replicas 0..2, replica 3 holds only padding
+    for layout, rank_of in (("tile", lambda kv, rep: rep * 8 + kv), ("adjacent", lambda kv, rep: kv * 4 + rep)):
+        real = 0
+        for kv in range(8):
+            got = [generate_padding_mask(48, 64, 8, 32, rank_of(kv, rep), kv_layout=layout).tolist() for rep in range(4)]
+            assert got == [[True, True]] * 3 + [[False, False]], (layout, kv, got)
+            real += sum(sum(g) for g in got)
+        assert real == 48
+    assert generate_padding_mask(48, 64, 8, 32, 31, hardware_type="trn2").tolist() == [False, False]
+    assert generate_padding_mask(48, 64, 8, 32, 7, hardware_type="trn1").tolist() == [True, True]
     # RNG tracker: default generator identical inside the TP group, the model-parallel stream differs per tp rank
     prandom.model_parallel_manual_seed(123)
     a = torch.rand(4)
@@ -111,7 +125,9 @@ def _grads_logprob(rank, world):
     logits_full = torch.randn(4, 3, 16, generator=torch.Generator().manual_seed(5))
     tgt = torch.randint(0, 16, (4, 3), generator=torch.Generator().manual_seed(6))
     local = logits_full.chunk(world, -1)[rank].clone().requires_grad_(True)
-    lp = from_parallel_logits_to_logprobs(local, tgt)
+    with pytest.raises(RuntimeError, match="inference=False"):            # the reference's default: scoring only
+        from_parallel_logits_to_logprobs(local, tgt).sum().backward()
+    lp = from_parallel_logits_to_logprobs(local, tgt, inference=False)
     ref = torch.log_softmax(logits_full, -1)[:, :-1].gather(-1, tgt[:, 1:].unsqueeze(-1)).squeeze(-1)
     torch.testing.assert_close(lp, ref, rtol=1e-5, atol=1e-5)
     lp.sum().backward()

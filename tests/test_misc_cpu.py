@@ -204,7 +204,7 @@ def _ep(rank, world):
     assert ps.get_expert_model_parallel_size() == 2 and ps.get_data_parallel_size() == world
     torch.manual_seed(0)
     E, k, H, I = 4, 2, 16, 32
-    cfg = RoutedExpertsMLPOpsConfig(num_experts=E, top_k=k, hidden_size=H, intermediate_size=I, capacity_factor=4.0)
+    cfg = RoutedExpertsMLPOpsConfig(normalize_top_k_affinities=True, num_experts=E, top_k=k, hidden_size=H, intermediate_size=I, capacity_factor=4.0)
     layer = MoE(RouterTopK(E, k, H), ExpertMLPsV2(cfg))
     w = layer.expert_mlps.mlp_op.down_proj.weight
     assert w.shape[0] == E // 2 and getattr(w, "expert_model_parallel", False)
@@ -214,6 +214,22 @@ def _ep(rank, world):
     assert y.shape == x.shape
     y.pow(2).mean().backward()
     assert x.grad is not None and w.grad is not None and torch.isfinite(w.grad).all()
+    # checkpoint-side rank tables (reference expert_mlps_v2.py:1501-1530): which logical experts every global rank hosts
+    from neuronx_distributed_b200.modules.moe.expert_mlps_v2 import create_spmd_ranks
+
+    sd = {}
+    create_spmd_ranks(sd, "m.", world, E, ps.get_expert_model_parallel_group(), "spmd_rank")
+    assert sd["m.spmd_rank.rank"].tolist() == [0, 1] and sd["m.spmd_rank.local_expert_indices"].tolist() == [[0, 1], [2, 3]]
+    create_spmd_ranks(sd, "m.", world, E, ps.get_expert_model_parallel_group(), "spmd_rank", expert_distribution=[[0, 3], [1, 2]])
+    assert sd["m.spmd_rank.local_expert_indices"].tolist() == [[0, 3], [1, 2]]
+    # a residual passed to the layer is added first and handed back (the stream the next block adds to)
+    layer.eval()
+    with torch.no_grad():
+        res = torch.randn_like(x)
+        y2, stream = layer(x.detach(), residual=res)
+        (y3,) = layer(x.detach() + res)
+    torch.testing.assert_close(y2, y3)
+    torch.testing.assert_close(stream, x.detach() + res)
 
 
 def test_expert_parallel_all_to_all_training():

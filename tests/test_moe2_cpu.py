@@ -45,7 +45,7 @@ def _modes(rank, world):
     for kw in (dict(), dict(bias=True), dict(early_expert_affinity_modulation=True),
                dict(glu_type="swiglu", hidden_act="sigmoid", hidden_act_scaling_factor=1.702, hidden_act_bias=1.0,
                     gate_clamp_upper_limit=7.0, up_clamp_upper_limit=7.0, up_clamp_lower_limit=-7.0)):
-        cfg = RoutedExpertsMLPOpsConfig(num_experts=E, top_k=k, hidden_size=H, intermediate_size=I, **kw)
+        cfg = RoutedExpertsMLPOpsConfig(normalize_top_k_affinities=True, num_experts=E, top_k=k, hidden_size=H, intermediate_size=I, **kw)
         em = ExpertMLPsV2(cfg).eval()
         if cfg.bias:
             with torch.no_grad():
@@ -73,20 +73,20 @@ def _modes(rank, world):
             assert m2[::3].sum() == 0 and a2[::3].sum() == 0 and em.mask_padding_tokens(mask, am, None)[0] is mask
 
     # capacity factor: dropping really drops (tokens beyond capacity get no contribution from that expert)
-    cfg = RoutedExpertsMLPOpsConfig(num_experts=E, top_k=k, hidden_size=H, intermediate_size=I, capacity_factor=0.5)
+    cfg = RoutedExpertsMLPOpsConfig(normalize_top_k_affinities=True, num_experts=E, top_k=k, hidden_size=H, intermediate_size=I, capacity_factor=0.5)
     em = ExpertMLPsV2(cfg).eval()
     y = em(x, aff, idx, seq_len=T)
     assert (y.abs().sum(-1) == 0).any() or not torch.allclose(y, _dense_ref(x, em._topk_affinities(aff, idx), em.mlp_op), atol=1e-4)
-    cfg_full = RoutedExpertsMLPOpsConfig(num_experts=E, top_k=k, hidden_size=H, intermediate_size=I, capacity_factor=100.0)
+    cfg_full = RoutedExpertsMLPOpsConfig(normalize_top_k_affinities=True, num_experts=E, top_k=k, hidden_size=H, intermediate_size=I, capacity_factor=100.0)
     ExpertMLPsV2.validate_routed_experts_configs(cfg_full)
     assert cfg_full.capacity_factor is None                                  # ≥ E/k cannot drop → full capacity
     with pytest.raises(ValueError):
-        ExpertMLPsV2.validate_routed_experts_configs(RoutedExpertsMLPOpsConfig(num_experts=4, top_k=5))
+        ExpertMLPsV2.validate_routed_experts_configs(RoutedExpertsMLPOpsConfig(normalize_top_k_affinities=True, num_experts=4, top_k=5))
     with pytest.raises(ValueError):
         ExpertMLPsV2.validate_routed_experts_configs(RoutedExpertsMLPOpsConfig(hidden_act="nope"))
 
     # explicit-metadata entry points and the PyTorch training oracle (forward AND hand-written backward vs autograd)
-    cfg = RoutedExpertsMLPOpsConfig(num_experts=E, top_k=k, hidden_size=H, intermediate_size=I)
+    cfg = RoutedExpertsMLPOpsConfig(normalize_top_k_affinities=True, num_experts=E, top_k=k, hidden_size=H, intermediate_size=I)
     em = ExpertMLPsV2(cfg)
     B = 8
     b2e, tp2id, counts = build_block_metadata(idx, E, B)
@@ -175,7 +175,7 @@ def _mx_and_groups(rank, world):
     ps.initialize_model_parallel(tensor_model_parallel_size=world)
     torch.manual_seed(0)
     E, k, H, I, T = 4, 2, 64, 128, 3
-    cfg = RoutedExpertsMLPOpsConfig(num_experts=E, top_k=k, hidden_size=H, intermediate_size=I)
+    cfg = RoutedExpertsMLPOpsConfig(normalize_top_k_affinities=True, num_experts=E, top_k=k, hidden_size=H, intermediate_size=I)
     router, experts, shared, norm = RouterTopK(E, k, H), ExpertMLPsV2(cfg), SharedExperts(H, 32), RMSNorm(H)
     x = torch.randn(T, 1, H, generator=torch.Generator().manual_seed(1))
     with torch.no_grad():

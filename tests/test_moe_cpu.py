@@ -34,7 +34,7 @@ def _moe_worker(rank, world):
     logits, aff, idx = router(x)
     assert idx.shape == (T, k) and aff.shape == (T, E)
     if world == 1:
-        cfg = RoutedExpertsMLPOpsConfig(num_experts=E, top_k=k, hidden_size=H, intermediate_size=I)
+        cfg = RoutedExpertsMLPOpsConfig(normalize_top_k_affinities=True, num_experts=E, top_k=k, hidden_size=H, intermediate_size=I)
         em = ExpertMLPsV2(cfg)
         ref = _ref_moe(x, aff.detach(), idx, em.mlp_op)
         torch.testing.assert_close(em.forward_all_experts(x, aff, idx), ref, rtol=1e-4, atol=1e-5)
@@ -46,7 +46,7 @@ def _moe_worker(rank, world):
         assert (tp2id >= 0).sum() == T * k
     # full layer with TP (+SP): output must equal the tp=1 computation
     torch.manual_seed(1)
-    cfg = RoutedExpertsMLPOpsConfig(num_experts=E, top_k=k, hidden_size=H, intermediate_size=I)
+    cfg = RoutedExpertsMLPOpsConfig(normalize_top_k_affinities=True, num_experts=E, top_k=k, hidden_size=H, intermediate_size=I)
     torch.manual_seed(2)
     layer = MoE(RouterTopK(E, k, H, sequence_parallel_enabled=world > 1), ExpertMLPsV2(cfg),
                 sequence_parallel_enabled=world > 1, return_router_logits=True)
