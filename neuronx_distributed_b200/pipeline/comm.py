@@ -61,11 +61,24 @@ class P2PBatch:
         return (works, []) if "recv" in kinds else ([], works)
 
 
-def send_python_object(obj: Any, dst: int) -> None:
+MAX_LENGTH = 2 ** 20          # largest pickled object the reference's fixed-size exchange accepts; objects here have no bound
+MAX_RETRY = 3                 # attempts of the reference's store-based receive; the gloo exchange below blocks instead
+
+
+def send_python_object(obj: Any, dst: Any = True, method: str = "gloo") -> None:
+    """Send a picklable object over the pipeline's CPU (gloo) group.  ``dst``: a global rank, or the reference's
+    ``send_next`` flag (``True`` → next pipeline rank, ``False`` → previous; comm.py:114-123).  ``method`` is accepted for
+    source compatibility — there is one transport."""
+    if isinstance(dst, bool):
+        dst = ps.get_pipeline_model_parallel_next_rank() if dst else ps.get_pipeline_model_parallel_prev_rank()
     dist.send_object_list([obj], dst=dst, group=ps.get_pp_gloo_group())
 
 
-def recv_python_object(src: int) -> Any:
+def recv_python_object(src: Any = True, method: str = "gloo") -> Any:
+    """Counterpart of :func:`send_python_object`.  ``src``: a global rank, or the reference's ``recv_prev`` flag (``True`` →
+    from the previous pipeline rank; comm.py:160-169)."""
+    if isinstance(src, bool):
+        src = ps.get_pipeline_model_parallel_prev_rank() if src else ps.get_pipeline_model_parallel_next_rank()
     box: List[Any] = [None]
     dist.recv_object_list(box, src=src, group=ps.get_pp_gloo_group())
     return box[0]
@@ -78,7 +91,9 @@ def send(tensor: torch.Tensor, send_next: bool = True, all_reduce_send_recv: boo
     return tensor
 
 
-def recv_from(tensor_meta: TensorMeta, recv_prev: bool = True, all_reduce_send_recv: bool = False) -> torch.Tensor:
+def recv_from(tensor_meta: TensorMeta, recv_prev: bool = True, tracing: bool = False,
+              all_reduce_send_recv: bool = False) -> torch.Tensor:
+    """``tracing`` (reference: record the receive in a lazy graph instead of executing it) has no meaning with eager NCCL."""
     src = ps.get_pipeline_model_parallel_prev_rank() if recv_prev else ps.get_pipeline_model_parallel_next_rank()
     buf = torch.empty(tensor_meta.shape, dtype=tensor_meta.dtype, device=get_device())
     dist.recv(buf, src=src, group=ps.get_pipeline_model_parallel_group())

@@ -227,7 +227,9 @@ class NxDPPModel(nn.Module):
         self.final_output_names = ["hidden"]
         self._output_spec = "hidden"
         self._manual = True
-        self._register_stages(stage_modules, ios, [])
+        shared = model.shared_across_stages(self.num_stages) if isinstance(model, PipelineStageModule) \
+            and not self.manual_pp_stage_partition_fn else []
+        self._register_stages(stage_modules, ios, shared)
 
     def _register_stages(self, stage_modules: List[Optional[nn.Module]], ios: List[part.StageIO], shared) -> None:
         self.stage_ios = ios

@@ -16,9 +16,15 @@ from torch import nn
 from torch.fx.passes.split_module import split_module
 
 
-def create_partitions(num_layers: int, num_stages: int) -> List[int]:
-    """Even split of ``num_layers`` transformer layers into ``num_stages`` stages, remainder to the
-    *later* stages; returns the layer indices after which to cut (reference partition.py:268-303)."""
+def create_partitions(num_layers, num_stages):
+    """Even split of the transformer layers into stages, remainder to the *later* stages (reference partition.py:268-303).
+    Two calling conventions: ``create_partitions(num_layers, num_stages)`` → the layer INDICES after which to cut;
+    the reference's ``create_partitions(pipeline_parallel_size, model_layer_names)`` → the layer NAMES after which to cut
+    (what ``pipeline_cuts`` takes)."""
+    names = None
+    if not isinstance(num_stages, int):                                  # (pipeline_parallel_size, model_layer_names)
+        names = list(num_stages)
+        num_layers, num_stages = len(names), int(num_layers)
     if num_stages > num_layers:
         raise ValueError(f"cannot split {num_layers} layers into {num_stages} stages")
     base, rem = divmod(num_layers, num_stages)
@@ -27,7 +33,7 @@ def create_partitions(num_layers: int, num_stages: int) -> List[int]:
     for s in sizes[:-1]:
         acc += s
         cuts.append(acc - 1)
-    return cuts
+    return cuts if names is None else [names[c] for c in cuts]
 
 
 def stage_to_pipeline_parallel_rank(stage: int, pp_size: int) -> int:

@@ -15,7 +15,7 @@ import torch.fx as fx
 from torch import nn
 
 from ..utils.model_utils import is_hf_pretrained_model, is_hf_transformers_available
-from .partition import trace_model  # noqa: F401
+from .partition import trace_model as _trace_with_leaf_classes
 
 try:
     from torch.fx._symbolic_trace import _create_wrapped_func
@@ -116,3 +116,35 @@ def patch_obj_method(autowrap_obj_methods: Optional[Dict[Any, List[str]]]):
                         delattr(obj, name)
                     except AttributeError:
                         setattr(obj, name, original)
+
+
+def trace_model(model: nn.Module, args: Optional[List[Any]] = None, kwargs: Optional[Dict[Any, Any]] = None,
+                input_names: Optional[List[str]] = None, tracer_cls: Any = None, leaf_modules: Optional[List[Any]] = None,
+                autowrap_functions: Optional[List[Any]] = None, autowrap_modules: Optional[List[Any]] = None,
+                autowrap_obj_methods: Optional[Dict[Any, List[str]]] = None, leaf_module_cls=None) -> fx.GraphModule:
+    """FX-trace ``model`` for pipeline partitioning with the reference's calling convention (``pipeline/trace.py:153-203``):
+    the traced inputs come from ``input_names`` or from example ``args`` / ``kwargs`` (only their NAMES matter — nothing is
+    executed); ``leaf_modules`` are classes or class names kept as single call nodes (the parallel layers and norms always
+    are); ``autowrap_obj_methods`` = ``{obj: [method names]}`` recorded as opaque calls.  This package's earlier positional
+    form ``trace_model(model, input_names, leaf_classes)`` is still accepted."""
+    if isinstance(args, (list, tuple)) and args and all(isinstance(a, str) for a in args) and input_names is None:
+        input_names, args = list(args), None                                  # (model, input_names, leaf classes, …)
+        if isinstance(kwargs, (list, tuple)):
+            leaf_modules, kwargs = list(kwargs), None
+    if input_names is None and (args is not None or kwargs is not None):
+        sig = list(inspect.signature(model.forward).parameters)
+        input_names = sig[: len(args or [])] + [k for k in (kwargs or {}) if kwargs[k] is not None]
+    wanted = list(leaf_modules or []) + list(leaf_module_cls or [])
+    by_name = {type(m).__name__: type(m) for m in model.modules()}
+    leaf_classes = []
+    for item in wanted:
+        cls = by_name.get(item) if isinstance(item, str) else item
+        if cls is None:
+            raise ValueError(f"leaf module {item!r} does not name the class of any submodule")
+        leaf_classes.append(cls)
+    if tracer_cls is not None and not (isinstance(tracer_cls, type) and issubclass(tracer_cls, fx.Tracer)):
+        tracer_cls = None if tracer_cls in ("torch", "hf") else tracer_cls    # both names select the built-in leaf-aware tracer
+    with patch_obj_method(autowrap_obj_methods):
+        return _trace_with_leaf_classes(model, input_names, leaf_classes, tuple(autowrap_functions or ()),
+                                        tuple(autowrap_modules or ()), None)
+

@@ -86,6 +86,41 @@ def test_create_partitions():
     assert create_partitions(10, 4) == [1, 3, 6]      # remainder goes to later stages: sizes 2,2,3,3
     with pytest.raises(ValueError):
         create_partitions(2, 4)
+    # the reference's convention: (pipeline_parallel_size, layer names) → names to cut after (what ``pipeline_cuts`` takes)
+    names = [f"model.layers.{i}" for i in range(10)]
+    assert create_partitions(4, names) == ["model.layers.1", "model.layers.3", "model.layers.6"]
+    assert create_partitions(1, names) == []
+
+
+def test_trace_model_reference_calling_convention():
+    """``pipeline.trace.trace_model(model, args=…, kwargs=…, leaf_modules=[class names], autowrap_obj_methods=…)``."""
+    from neuronx_distributed_b200.pipeline.trace import trace_model
+
+    class Helper:
+        def scale(self, x):
+            return x * 2 if x.sum() > 0 else x                        # data-dependent: cannot be traced through
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.blk, self.out, self.h = Block(8), nn.Linear(8, 4), Helper()
+
+        def forward(self, x, mask=None, scale=1.0):
+            y = self.blk(x) * scale
+            return self.out(self.h.scale(y))
+
+    m = M()
+    gm = trace_model(m, args=[torch.zeros(1, 8)], leaf_modules=["Block"], autowrap_obj_methods={m.h: ["scale"]})
+    targets = [(n.op, str(n.target)) for n in gm.graph.nodes]
+    assert ("call_module", "blk") in targets and not any("fc1" in t for _, t in targets)          # Block kept as one node
+    assert [t for op, t in targets if op == "placeholder"] == ["x"]                              # mask / scale are constants
+    assert any(op == "call_function" and "scale" in t for op, t in targets)                      # the wrapped method is opaque
+    x = torch.randn(3, 8)
+    torch.testing.assert_close(gm(x), m(x))
+    gm2 = trace_model(m, kwargs={"x": torch.zeros(1, 8), "mask": None}, leaf_modules=[Block], autowrap_obj_methods={m.h: ["scale"]})
+    assert [n.target for n in gm2.graph.nodes if n.op == "placeholder"] == ["x"]
+    with pytest.raises(ValueError, match="does not name the class"):
+        trace_model(m, args=[x], leaf_modules=["NoSuchBlock"])
 
 
 class Block(nn.Module):
@@ -252,3 +287,107 @@ def _delayed(rank, world):
 
 def test_delayed_tracing_and_signature_analysis_pp2():
     run_distributed(_delayed, 2, timeout=180)
+
+
+class _Emb(nn.Module):
+    def __init__(self, v, h):
+        super().__init__()
+        self.emb = nn.Embedding(v, h)
+
+    def forward(self, input_ids):
+        return self.emb(input_ids)
+
+
+class _Head(nn.Module):
+    def __init__(self, v, h):
+        super().__init__()
+        self.proj = nn.Linear(h, v, bias=False)
+
+    def forward(self, x):
+        return self.proj(x)
+
+
+def _manual_pp(rank, world, tie_mode):
+    """Manually partitioned pipeline (ordered layer list, loss function on the last stage): equals the unpartitioned model, and
+    an embedding / head weight shared across the first and the last stage stays shared — by being the same Parameter
+    (``"identity"``) or by ``PipelineStageModule.mark_weight_sharing`` on two separate tensors (``"marked"``)."""
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.pipeline import NxDPPModel
+    from neuronx_distributed_b200.pipeline.manual_pipe_stage import WEIGHT_SHARING_ATTR_NAME, PipelineStageModule
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=1, pipeline_model_parallel_size=world)
+    V, H = 32, 16
+
+    def build():
+        torch.manual_seed(0)
+        layers = [_Emb(V, H), Block(H), Block(H), _Head(V, H)]
+        if tie_mode == "identity":
+            layers[-1].proj.weight = layers[0].emb.weight
+        elif tie_mode == "marked":
+            with torch.no_grad():
+                layers[-1].proj.weight.copy_(layers[0].emb.weight)          # separate tensors, equal values
+            PipelineStageModule.mark_weight_sharing([(layers[0], "emb.weight"), (layers[-1], "proj.weight")], "embeddings")
+        return layers
+
+    def loss_fn(logits, labels):
+        return torch.nn.functional.cross_entropy(logits.view(-1, V), labels.view(-1))
+
+    ids = torch.randint(0, V, (8, 6), generator=torch.Generator().manual_seed(1))
+    ref_layers = build()
+    ref = nn.Sequential(*ref_layers)
+    ref_loss = loss_fn(ref(ids), ids)
+    ref_loss.backward()
+    if tie_mode == "marked":                                               # what sharing means for separate tensors: summed gradients
+        g = ref_layers[0].emb.weight.grad + ref_layers[-1].proj.weight.grad
+        ref_layers[0].emb.weight.grad, ref_layers[-1].proj.weight.grad = g, g.clone()
+    stage = PipelineStageModule(build(), layer_names=["emb", "b0", "b1", "head"])
+    if tie_mode != "none":
+        assert stage.weight_sharing_groups() == [["0.emb.weight", "3.proj.weight"]]
+        assert stage.shared_across_stages(2) == [[(0, "layers.emb.emb.weight"), (1, "layers.head.proj.weight")]]
+        if tie_mode == "marked":
+            assert getattr(stage.all_layers[0], WEIGHT_SHARING_ATTR_NAME) == {"embeddings": "emb.weight"}
+            with pytest.raises(RuntimeError, match="already exists"):
+                PipelineStageModule.mark_weight_sharing([(stage.all_layers[0], "emb.weight")], "embeddings")
+    else:
+        assert stage.weight_sharing_groups() == []
+    ppm = NxDPPModel(stage, manual_pp_partition=True, manual_pp_loss_fn=loss_fn, num_microbatches=4, input_names=["input_ids"],
+                     broadcast_and_average_loss=True)
+    assert len(ppm.shared_weight_groups) == (0 if tie_mode == "none" else 1)
+    loss = ppm.run_train(input_ids=ids, labels=ids)
+    torch.testing.assert_close(loss.float(), ref_loss.detach().float(), rtol=1e-4, atol=1e-5)
+    refp = {n: p for n, p in ref.named_parameters(remove_duplicate=False)}
+    checked = 0
+    for name, p in ppm.local_named_parameters():                           # names of the user's module: all_layers.<i>.<path>
+        for ref_name in ("0.emb.weight", "3.proj.weight"):
+            if name.endswith(ref_name):
+                torch.testing.assert_close(p.grad, refp[ref_name].grad, rtol=1e-3, atol=1e-5)
+                checked += 1
+    assert checked == 1                                                    # each rank holds one end of the pipeline
+
+
+@pytest.mark.parametrize("tie_mode", ["none", "identity", "marked"])
+def test_manual_partition_with_shared_weights_pp2(tie_mode):
+    run_distributed(_manual_pp, 2, tie_mode, timeout=180)
+
+
+def _pyobj(rank, world):
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.pipeline import comm
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=1, pipeline_model_parallel_size=world)
+    meta = {"from": rank, "shape": (2, 3), "dtype": torch.bfloat16}
+    if rank == 0:
+        comm.send_python_object(meta, True)                                   # reference flags: send_next=True
+        assert comm.recv_python_object(False, method="gloo") == {"from": 1, "shape": (2, 3), "dtype": torch.bfloat16}
+    else:
+        assert comm.recv_python_object(True)["from"] == 0                     # recv_prev=True
+        comm.send_python_object(meta, send_next := False)                     # back to the previous rank
+    if rank == 0:
+        comm.send_python_object("by rank", 1)                                 # explicit global rank still works
+    else:
+        assert comm.recv_python_object(0) == "by rank"
+    assert comm.MAX_RETRY == 3 and comm.MAX_LENGTH == 2 ** 20
+
+
+def test_python_object_exchange_between_stages():
+    run_distributed(_pyobj, 2, timeout=120)

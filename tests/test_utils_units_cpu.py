@@ -97,6 +97,11 @@ def test_reference_named_constants_are_wired():
     emb, head = nn.Embedding(8, 4), nn.Linear(4, 8, bias=False)
     head.weight = emb.weight
     stage = mps.PipelineStageModule([emb, head], num_stages=1, stage_index=0)
-    stage.mark_weight_sharing(["0.weight", "1.weight"])
-    assert getattr(emb.weight, mps.WEIGHT_SHARING_ATTR_NAME) == 0 and getattr(head.weight, mps.WEIGHT_SHARING_ATTR_NAME) == 0
+    assert stage.weight_sharing_groups() == [["0.weight", "1.weight"]]                 # same Parameter object
+    emb2, head2 = nn.Embedding(8, 4), nn.Linear(4, 8, bias=False)
+    mps.PipelineStageModule.mark_weight_sharing([(emb2, "weight"), (head2, "weight")], "tied")   # before the stage module exists
+    assert getattr(emb2, mps.WEIGHT_SHARING_ATTR_NAME) == {"tied": "weight"}
+    stage2 = mps.PipelineStageModule([emb2, nn.Linear(4, 4), head2])
+    stage2.mark_weight_sharing(["0.weight", "2.weight"])                               # by qualified names: same group, listed once
+    assert stage2.weight_sharing_groups() == [["0.weight", "2.weight"]]
 
