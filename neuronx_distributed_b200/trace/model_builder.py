@@ -38,10 +38,19 @@ class BaseModelInstance:
 
 class ModelBuilder:
     def __init__(self, router: Any = None, tp_degree: int = 1, checkpoint_loader: Optional[Callable[[], Dict[str, torch.Tensor]]] = None,
-                 pp_degree: int = 1, ep_degree: int = 1, world_size: Optional[int] = None, start_rank_id: int = 0,
-                 local_ranks_size: Optional[int] = None, compiler_workdir: Optional[str] = None, debug: bool = False,
-                 num_cores_per_group: int = 1, logical_nc_config: int = 1, weights_to_skip_layout_optimization=None,
+                 start_rank_id: int = 0, pp_degree: int = 1, ep_degree: int = 1, local_ranks_size: Optional[int] = None,
+                 world_size: Optional[int] = None, compiler_workdir: Optional[str] = None, master_proc_env_vars: Optional[Dict] = None,
+                 debug: bool = False, num_cores_per_group: int = 1, init_custom_process_group_fn: Optional[Callable] = None,
+                 logical_nc_config: int = 1, weights_to_skip_layout_optimization=None, compiler_flag_hook: Optional[Callable] = None,
                  model: Optional[nn.Module] = None, use_cuda_graphs: Optional[bool] = None):
+        """Positional order of reference model_builder.py:230-249.  ``master_proc_env_vars`` (environment of the reference's
+        per-rank compile workers), ``init_custom_process_group_fn`` (called once here, right away: this process IS the rank) and
+        ``compiler_flag_hook`` (there is no compiler command line) are accepted for source compatibility."""
+        if master_proc_env_vars:
+            os.environ.update({str(k): str(v) for k, v in master_proc_env_vars.items()})
+        if init_custom_process_group_fn is not None:
+            init_custom_process_group_fn()
+        self.compiler_flag_hook = compiler_flag_hook
         self.router, self.tp_degree, self.checkpoint_loader = router, tp_degree, checkpoint_loader
         self.world_size = world_size or tp_degree * pp_degree
         self.start_rank_id, self.local_ranks_size = start_rank_id, local_ranks_size
@@ -58,7 +67,15 @@ class ModelBuilder:
                              "priority": priority_model_idx}
         return self
 
-    def trace(self, tag: Optional[str] = None, initialize_model_weights: bool = True) -> NxDModel:
+    def trace(self, initialize_model_weights: bool = True, dry_run: bool = False, disable_fail_fast: bool = False,
+              tag: Optional[str] = None) -> NxDModel:
+        """Positional order of reference model_builder.py:394.  ``dry_run``: build every bucket program (validates that the
+        entries are callable on their example shapes' metadata) but load no weights; ``disable_fail_fast`` concerned the
+        reference's parallel compile workers."""
+        if isinstance(initialize_model_weights, str):                       # earlier form of this package: trace(tag)
+            initialize_model_weights, tag = True, initialize_model_weights
+        if dry_run:
+            initialize_model_weights = False
         nxd = NxDModel(world_size=self.world_size, router=self.router)
         for key, e in self.entries.items():
             inst = e["instance"]

@@ -5,6 +5,8 @@ from __future__ import annotations
 
 import contextlib
 
+from typing import Optional
+
 import torch.distributed as dist
 
 from ..parallel_layers import parallel_state as ps
@@ -12,7 +14,10 @@ from ..parallel_layers import parallel_state as ps
 
 class NxDParallelState(contextlib.AbstractContextManager):
     def __init__(self, world_size: int = 1, rank: int = 0, tensor_model_parallel_size: int = 1,
-                 pipeline_model_parallel_size: int = 1, context_parallel_size: int = 1, expert_model_parallel_size: int = 1):
+                 pipeline_model_parallel_size: int = 1, context_parallel_size: int = 1, expert_model_parallel_size: int = 1,
+                 lnc_size: Optional[int] = None):
+        """``lnc_size`` (logical cores fused into one rank on the reference hardware) is recorded only: a rank is one GPU."""
+        self.lnc_size = lnc_size
         self.world_size, self.rank = world_size, rank
         self.tp, self.pp, self.cp, self.ep = (tensor_model_parallel_size, pipeline_model_parallel_size,
                                               context_parallel_size, expert_model_parallel_size)

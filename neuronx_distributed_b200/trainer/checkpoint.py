@@ -133,7 +133,8 @@ class CheckpointIOState:
         self.lock = threading.Lock()
 
     # -- lifecycle -----------------------------------------------------------------------
-    def begin(self, storage: BaseCheckpointStorage, tag: str) -> None:
+    def begin(self, checkpoint_dir: BaseCheckpointStorage, tag: str) -> None:
+        storage = checkpoint_dir              # reference argument name; it is the storage object of the checkpoint directory
         self.wait_all()                       # at most one save in flight
         self.storage, self.tag, self.items = storage, tag, []
         if _rank() == 0:
@@ -219,7 +220,10 @@ class CheckpointIOState:
         # the "done" marker needs *all* ranks' writes → it is written at the next synchronisation point
         self._pending_done = (storage, tag, num_kept)
 
-    def wait_save(self) -> None:
+    def wait_save(self, async_remove: bool = False) -> None:
+        """``async_remove`` (reference :198): also wait for a pending asynchronous removal of old checkpoints."""
+        if async_remove and hasattr(self, "wait_remove"):
+            self.wait_remove()
         if self.save_future is not None:
             self.save_future.result()
             self.save_future = None

@@ -60,7 +60,8 @@ class BaseCheckpointStorage(ABC):
     def list_completed_checkpoint_tags(self) -> List[str]:
         return [t for t in self.list_checkpoint_tags() if self.is_checkpoint_tag_completed(t)]
 
-    def find_files(self, dirname: str, pattern: str) -> List[str]:
+    def find_files(self, dirname=None, pattern=None, search_root: Optional[str] = None, max_count: Optional[int] = None,
+                   sort_by_mdate: bool = False, search_depth: Optional[int] = None) -> List[str]:
         return []
 
     def find_subdirs_contain_path(self, pattern: str, search_depth: int, search_root: Optional[str] = None,
@@ -108,13 +109,15 @@ class FilesysCheckpointStorage(BaseCheckpointStorage):
             return []
         return [x for x in os.listdir(d) if os.path.isdir(os.path.join(d, x))]
 
-    def find_files(self, dirname, pattern=None, search_root: Optional[str] = None, max_count: Optional[int] = None,
-                   sort_by_mdate: bool = False) -> List[str]:
+    def find_files(self, dirname=None, pattern=None, search_root: Optional[str] = None, max_count: Optional[int] = None,
+                   sort_by_mdate: bool = False, search_depth: Optional[int] = None) -> List[str]:
         """Two call forms: ``find_files(dirname, pattern)`` (everything below ``dirname``) and the reference's
         ``find_files(pattern, search_depth, search_root=None, max_count=None, sort_by_mdate=False)`` (:176-205), which bounds
         the walk depth, optionally sorts newest first and truncates."""
         import fnmatch
 
+        if search_depth is not None:                                   # keyword form of the reference's signature
+            dirname, pattern = (pattern if dirname is None else dirname), search_depth
         if isinstance(pattern, int):
             pat, depth, root_rel = dirname, pattern, search_root or ""
         else:
@@ -363,13 +366,15 @@ class S3CheckpointStorage(BaseCheckpointStorage):
         _, prefixes = self._list(pfx, delimiter="/")
         return [p[len(pfx):].rstrip("/") for p in prefixes]
 
-    def find_files(self, dirname, pattern=None, search_root: Optional[str] = None, max_count: Optional[int] = None,
-                   sort_by_mdate: bool = False) -> List[str]:
+    def find_files(self, dirname=None, pattern=None, search_root: Optional[str] = None, max_count: Optional[int] = None,
+                   sort_by_mdate: bool = False, search_depth: Optional[int] = None) -> List[str]:
         """Two call forms, like the file-system back-end: ``find_files(dirname, pattern)`` — files under ``dirname`` whose
         base name matches the glob; ``find_files(pattern, search_depth, search_root, max_count, sort_by_mdate)`` — the
         reference's depth-limited search (paths relative to the storage root)."""
         import fnmatch
 
+        if search_depth is not None:
+            dirname, pattern = (pattern if dirname is None else dirname), search_depth
         if isinstance(pattern, int):
             glob_pat, depth, root = dirname, pattern, search_root or ""
         else:
@@ -407,7 +412,7 @@ class S3CheckpointStorage(BaseCheckpointStorage):
     def remove_file(self, filename: str) -> None:
         self._retry(self.s3.delete_object, Bucket=self._bucket, Key=self.convert_path_to_key(filename))
 
-    def save_text(self, text: str, filename: str) -> None:
+    def save_text(self, text: str, filename: str, use_threads: bool = True) -> None:   # one PUT: nothing to thread
         self._retry(self.s3.put_object, Bucket=self._bucket, Key=self.convert_path_to_key(filename), Body=text.encode())
 
     def upload_stream_to_file(self, stream_creator, filename: str, chunk_size_MB: int = 64, max_concurrency: int = 10,

@@ -46,9 +46,11 @@ def is_nxd_pipeline_model(model) -> bool:
 
 
 @contextlib.contextmanager
-def init_on_device(device: torch.device, include_buffers: bool = False):
+def init_on_device(device: torch.device, include_buffers: bool = False, force_custom_init_on_device: bool = False):
     """Create parameters (and optionally buffers) directly on ``device`` (typically ``meta``) while
-    keeping the parallel attributes set by the TP layers (reference :147-213)."""
+    keeping the parallel attributes set by the TP layers (reference :147-213).  This is always the "custom" implementation of
+    the reference (it keeps ``requires_grad=False`` and the parallel attributes, which the accelerate one loses), so
+    ``force_custom_init_on_device`` changes nothing."""
     old_register_parameter = nn.Module.register_parameter
     old_register_buffer = nn.Module.register_buffer
 
@@ -138,27 +140,49 @@ def reinit_model(model: nn.Module, device: torch.device, param_init_fn: Optional
         setattr(mods[pb], nb, getattr(mods[pa], na))
 
 
-def get_model_sequential(model_fn: Callable[[], nn.Module], sequential_move_factor: int = 11,
+def get_model_sequential(model, device=None, sequential_move_factor: int = 11, param_init_fn: Optional[Callable] = None,
                          move_to_device: bool = True) -> nn.Module:
-    """Build (and optionally move) the model ``sequential_move_factor`` local ranks at a time so host
-    memory holds at most that many full CPU copies at once (reference :335-356)."""
+    """Bring a model onto the device ``sequential_move_factor`` local ranks at a time, so host memory holds at most that many
+    full CPU copies at once (reference :335-356).  Two forms:
+
+    * ``get_model_sequential(model, device, sequential_move_factor=11, param_init_fn=None)`` — the reference's: ``model`` exists
+      (possibly on the meta device): materialise it, re-initialise with ``param_init_fn(module, device)`` if given, move it
+      (a pipeline model moves its local stages);
+    * ``get_model_sequential(model_fn, sequential_move_factor, move_to_device=…)`` — build it inside the wave as well."""
+    build = None
+    if not isinstance(model, nn.Module):
+        build, model = model, None
+        if isinstance(device, int):                                       # (model_fn, sequential_move_factor)
+            sequential_move_factor, device = device, None
+    device = device if device is not None else get_device()
+
+    def bring_up():
+        m = build() if build is not None else model
+        if build is None or move_to_device:
+            if hasattr(m, "maybe_materialize_local_module") and hasattr(m, "move_model_to_device"):   # NxDPPModel
+                m.maybe_materialize_local_module()
+                m.move_model_to_device()
+            elif build is None:
+                maybe_materalize_model(m)
+                if param_init_fn is not None:
+                    reinit_model(m, torch.device("cpu"), param_init_fn)
+                m.to(device)
+            else:
+                m.to(device)
+        return m
+
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        model = model_fn()
-        if move_to_device:
-            model.to(get_device())
-        return model
-    local_rank = dist.get_rank() % max(1, torch.cuda.device_count() if not cpu_mode() else dist.get_world_size())
+        return bring_up()
     local_world = torch.cuda.device_count() if not cpu_mode() else dist.get_world_size()
+    local_rank = dist.get_rank() % max(1, local_world)
     waves = max(1, math.ceil(local_world / max(1, sequential_move_factor)))
-    model = None
+    out = None
     for w in range(waves):
         if local_rank % waves == w:
-            model = model_fn()
-            if move_to_device:
-                model.to(get_device())
+            out = bring_up()
         if waves > 1:
             dist.barrier()
-    return model
+    return out
 
 
 def maybe_materalize_model(model: nn.Module) -> None:

@@ -12,15 +12,33 @@ from ..operators import topk as dist_topk
 
 
 class Sampler:
-    def __init__(self, top_k: int = 1, top_p: float = 1.0, temperature: float = 1.0, do_sample: bool = False,
+    def __init__(self, top_k=1, top_p: float = 1.0, temperature: float = 1.0, do_sample: bool = False,
                  dynamic: bool = False, deterministic: bool = False, on_device: bool = True, vocab_parallel: bool = False):
+        """Explicit settings, or — the reference's constructor (sampling.py:12-22) — one ``neuron_config`` object carrying
+        ``on_device_sampling`` and ``hf_config.{do_sample, num_beams, top_k[, top_p, temperature]}``; as there, anything but
+        single-beam sampling is refused and ``sample`` is the inverse-CDF multinomial (greedy for ``top_k == 1``)."""
+        self._reference_style = False
+        if not isinstance(top_k, int):
+            nc = top_k
+            hf = getattr(nc, "hf_config", nc)
+            if not (getattr(hf, "do_sample", False) and getattr(hf, "num_beams", 1) == 1):
+                raise Exception("Selected sampling method is not supported.")
+            on_device = bool(getattr(nc, "on_device_sampling", True))
+            self.is_medusa = bool(getattr(nc, "is_medusa", False))
+            top_k, do_sample = int(hf.top_k), True
+            top_p, temperature = float(getattr(hf, "top_p", 1.0) or 1.0), float(getattr(hf, "temperature", 1.0) or 1.0)
+            self._reference_style = True
+        self.on_device_sampling = on_device
         self.top_k, self.top_p, self.temperature = top_k, top_p, temperature
         self.do_sample, self.dynamic, self.deterministic = do_sample, dynamic, deterministic
         self.vocab_parallel = vocab_parallel
 
-    def sample(self, logits: torch.Tensor, rank_id: Optional[torch.Tensor] = None,
+    def sample(self, token_logits: torch.Tensor, rank_id: Optional[torch.Tensor] = None,
                generator: Optional[torch.Generator] = None) -> torch.Tensor:
         """``logits`` [B, V] (or [B, V/tp] when ``vocab_parallel``) → token ids [B]."""
+        logits = token_logits
+        if self._reference_style and not self.vocab_parallel and self.top_p >= 1.0:
+            return self.multinomial(logits, generator)
         if self.top_k == 1 or not self.do_sample:
             if self.vocab_parallel:
                 return dist_argmax(logits, dim=-1, rank_id=rank_id)

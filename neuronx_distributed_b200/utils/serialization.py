@@ -30,7 +30,13 @@ class TensorStub:
 
 
 class SerializationManager:
-    def serialize(self, obj: Any) -> Tuple[Any, List[torch.Tensor]]:
+    def serialize(self, obj: Any, return_stub_list: bool = False):
+        """``(skeleton, tensors)``; with ``return_stub_list=True`` also the :class:`TensorMeta` of every tensor — the
+        reference's three-tuple (:103-129; it defaults to returning it, the two-tuple is this package's default because the
+        pipeline engine keeps the metadata in its own cache)."""
+        if return_stub_list:
+            skeleton, tensors = self.serialize(obj)
+            return skeleton, tensors, self.tensor_metas(tensors)
         leaves, spec = pytree.tree_flatten(obj)
         tensors: List[torch.Tensor] = []
         stubs = []
@@ -46,9 +52,9 @@ class SerializationManager:
         """The third element of the reference's ``serialize`` result: one :class:`TensorMeta` per extracted tensor."""
         return [TensorMeta(i, t.dtype, t.shape, t.requires_grad, t.device) for i, t in enumerate(tensors)]
 
-    def extract_stubs(self, skeleton: Any) -> List[TensorStub]:
+    def extract_stubs(self, stubbed_obj: Any) -> List[TensorStub]:
         """The tensor placeholders of a serialised skeleton, in tensor order (what a receiver must allocate)."""
-        stubs, _ = skeleton
+        stubs, _ = stubbed_obj
         return [s for s in stubs if isinstance(s, TensorStub)]
 
     @staticmethod
@@ -66,16 +72,17 @@ class SerializationManager:
 
         return ctx()
 
-    def deserialize(self, skeleton: Any, tensors: List[torch.Tensor]) -> Any:
-        stubs, spec = skeleton
+    def deserialize(self, stubbed_obj: Any, tensors: List[torch.Tensor]) -> Any:
+        stubs, spec = stubbed_obj
         leaves = [tensors[s.index] if isinstance(s, TensorStub) else s for s in stubs]
         return pytree.tree_unflatten(leaves, spec)
 
 
-def find_loss_from_output_and_spec(output: Any, spec: Any) -> torch.Tensor:
+def find_loss_from_output_and_spec(output_val: Any, spec_val: Any) -> torch.Tensor:
     """Pick the loss out of a model output using a spec of the same structure whose leaves are
     booleans (exactly one True), e.g. ``(True, False)`` or ``{"loss": True}``; ``True`` alone means
     the output itself (reference :212-254)."""
+    output, spec = output_val, spec_val
     if spec is True or spec is None:
         if isinstance(output, torch.Tensor):
             return output

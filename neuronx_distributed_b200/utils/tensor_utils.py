@@ -4,7 +4,9 @@ signature)."""
 import torch
 
 
-def cumsum(tensor: torch.Tensor, dim: int = 0) -> torch.Tensor:
+def cumsum(tensor: torch.Tensor, dim: int = 0, tril_size: int = 2048) -> torch.Tensor:
+    """``tril_size``: tile size of the triangular-matmul formulation the reference uses on its hardware (tensor_utils.py);
+    a prefix sum is a library call here, the argument is accepted and unused."""
     if tensor.is_floating_point():
         return torch.cumsum(tensor.float(), dim=dim).to(tensor.dtype)
     return torch.cumsum(tensor, dim=dim)

@@ -137,6 +137,7 @@ def _optimizer_views_and_shard_files(rank, world, root):
     dist.barrier()
     assert sorted(st.find_subdirs_contain_path("done", 1)) == ["t1", "t2", "t3"]
     assert st.find_files("w.pt", 1) == [] and len(st.find_files("w.pt", 2)) == 3 and len(st.find_files("w.pt", 2, max_count=2)) == 2
+    assert st.find_files(pattern="w.pt", search_depth=2) == st.find_files("w.pt", 2) == st.find_files("w.pt", search_depth=2)
     io = CheckpointIOState(async_save=True)
     io.storage = st
     io.submit_remove(num_kept=1, async_remove=True)

@@ -287,6 +287,35 @@ def test_small_utils(tmp_path):
     assert back["a"].shape == (2, 3) and back["b"][1] == 5
     from neuronx_distributed_b200.trace.nxd_model.nxd_model import JITWrapper
 
+    skel3, tens3, metas3 = sm.serialize({"t": torch.ones(2)}, return_stub_list=True)                   # the reference's 3-tuple
+    assert len(tens3) == 1 and metas3[0].shape == (2,) and sm.deserialize(stubbed_obj=skel3, tensors=tens3)["t"].shape == (2,)
+    # sampler built from a config object (reference constructor): inverse-CDF top-k sampling, greedy for top_k == 1
+    from types import SimpleNamespace as NS
+
+    from neuronx_distributed_b200.utils.sampling import Sampler
+
+    logits = torch.tensor([[0.0, 5.0, 1.0, 4.9], [3.0, 0.0, 0.0, 0.0]])
+    greedy = Sampler(NS(on_device_sampling=True, hf_config=NS(do_sample=True, num_beams=1, top_k=1)))
+    assert greedy.sample(token_logits=logits).tolist() == [1, 0] and greedy.on_device_sampling
+    top2 = Sampler(NS(on_device_sampling=False, hf_config=NS(do_sample=True, num_beams=1, top_k=2)))
+    draws = {int(top2.sample(logits, generator=torch.Generator().manual_seed(i))[0]) for i in range(40)}
+    assert draws == {1, 3}                                                      # only the two best candidates are ever drawn
+    with pytest.raises(Exception, match="not supported"):
+        Sampler(NS(on_device_sampling=True, hf_config=NS(do_sample=False, num_beams=1, top_k=1)))
+    # hook registry with the reference's argument names and return values
+    from neuronx_distributed_b200.trainer.post_partition_hooks import PostPartitionHooks
+
+    hk = PostPartitionHooks()
+
+    def filter_to_local_parameter_group(groups, model=None):
+        return (groups, type(model).__name__)
+
+    hk.register_post_partition_hook(callable_function=lambda a, b=0: a + b, func_args=(1,), func_kwargs={"b": 2})
+    hk.register_post_partition_hook(filter_to_local_parameter_group, (["g"],))
+    assert [h["name"] for h in hk.hooks] == ["<lambda>", "filter_to_local_parameter_group"]
+    assert hk.execute_all_hooks(model=torch.nn.Linear(1, 1)) == [3, (["g"], "Linear")] and hk.hooks == []
+    with pytest.raises(ValueError):
+        hk.register_post_partition_hook("not callable")
     jw = JITWrapper(lambda xs: [x * 2 for x in xs])
     assert isinstance(jw, torch.nn.Module) and jw([torch.ones(1)])[0].item() == 2
     assert is_instance_namedtuple(P(1, 2)) and not is_instance_namedtuple((1, 2))
