@@ -3,6 +3,8 @@ from __future__ import annotations
 
 import math
 
+from typing import Optional
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -16,7 +18,9 @@ class LoraLayer(nn.Module):
     adapter_layer_names = ("lora_A", "lora_B", "lora_embedding_A", "lora_embedding_B")
     other_param_names = ("lora_rank", "lora_alpha", "scaling", "lora_dropout")
 
-    def __init__(self, base_layer: nn.Module, config: LoraConfig):
+    def __init__(self, base_layer: nn.Module, config: Optional[LoraConfig] = None, lora_config: Optional[LoraConfig] = None, **_compat):
+        config = config if config is not None else lora_config          # ``lora_config=`` is the reference's keyword
+        assert config is not None, "a LoraConfig is required"
         if config.lora_rank <= 0:
             raise ValueError(f"`lora_rank` should be a positive integer value but the value passed is {config.lora_rank}")
         super().__init__()
@@ -29,7 +33,20 @@ class LoraLayer(nn.Module):
         for p in base_layer.parameters():
             p.requires_grad_(False)
 
-    def init_lora_parameters(self, a: torch.Tensor, b: torch.Tensor) -> None:
+    def init_lora_parameters(self, a=None, b: Optional[torch.Tensor] = None) -> None:
+        """``init_lora_parameters(A, B)`` initialises the two given tensors; the reference's form
+        ``init_lora_parameters("default" | "gaussian")`` (layer.py:133-151) re-initialises this layer's own adapter."""
+        if a is None or isinstance(a, str):
+            mode = (a or self.lora_config.init_lora_weights or "default").lower()
+            assert mode in ("default", "gaussian"), f"Unknown LoRA parameters initialization with {mode}"
+            saved, self.lora_config.init_lora_weights = self.lora_config.init_lora_weights, mode
+            try:
+                la, lb = getattr(self, "lora_A", None), getattr(self, "lora_B", None)
+                if la is not None and lb is not None:
+                    self.init_lora_parameters(getattr(la, "weight", la), getattr(lb, "weight", lb))
+            finally:
+                self.lora_config.init_lora_weights = saved
+            return
         if self.lora_config.init_lora_weights == "gaussian":
             nn.init.normal_(a, std=1.0 / self.r)
         else:
@@ -88,7 +105,9 @@ class LoraLayer(nn.Module):
 
 
 class LoraLinear(LoraLayer):
-    def __init__(self, base_layer: nn.Linear, config: LoraConfig):
+    def __init__(self, base_layer: nn.Linear, config: Optional[LoraConfig] = None, lora_config: Optional[LoraConfig] = None, **_compat):
+        config = config if config is not None else lora_config          # ``lora_config=`` is the reference's keyword
+        assert config is not None, "a LoraConfig is required"
         super().__init__(base_layer, config)
         dt, dev = base_layer.weight.dtype, base_layer.weight.device
         self.lora_A = nn.Linear(base_layer.in_features, self.r, bias=False, dtype=dt, device=dev)
@@ -106,7 +125,9 @@ class LoraLinear(LoraLayer):
 
 
 class LoraEmbedding(LoraLayer):
-    def __init__(self, base_layer: nn.Embedding, config: LoraConfig):
+    def __init__(self, base_layer: nn.Embedding, config: Optional[LoraConfig] = None, lora_config: Optional[LoraConfig] = None, **_compat):
+        config = config if config is not None else lora_config          # ``lora_config=`` is the reference's keyword
+        assert config is not None, "a LoraConfig is required"
         super().__init__(base_layer, config)
         dt, dev = base_layer.weight.dtype, base_layer.weight.device
         self.lora_embedding_A = nn.Parameter(torch.empty(self.r, base_layer.num_embeddings, dtype=dt, device=dev))
@@ -126,7 +147,9 @@ class LoraEmbedding(LoraLayer):
 
 
 class LoraConv2d(LoraLayer):
-    def __init__(self, base_layer: nn.Conv2d, config: LoraConfig):
+    def __init__(self, base_layer: nn.Conv2d, config: Optional[LoraConfig] = None, lora_config: Optional[LoraConfig] = None, **_compat):
+        config = config if config is not None else lora_config          # ``lora_config=`` is the reference's keyword
+        assert config is not None, "a LoraConfig is required"
         super().__init__(base_layer, config)
         dt, dev = base_layer.weight.dtype, base_layer.weight.device
         self.lora_A = nn.Conv2d(base_layer.in_channels, self.r, base_layer.kernel_size, base_layer.stride,

@@ -183,11 +183,16 @@ class LoraModel(nn.Module):
     def base_state_dict(self) -> Dict[str, torch.Tensor]:
         return {k.replace(".base_layer", ""): v for k, v in self.module.state_dict().items() if "lora_" not in k}
 
-    def save_lora(self, path: Optional[str] = None, tag: Optional[str] = None) -> str:
+    def save_lora(self, save_dir: Optional[str] = None, adapter_tag: Optional[str] = None, path: Optional[str] = None,
+                  tag: Optional[str] = None) -> str:
+        """Write this rank's adapter file under ``save_dir[/adapter_tag]`` (argument names of reference lora/model.py:461;
+        ``path`` / ``tag`` are this package's earlier names).  Unlike the reference — which refuses here once model parallelism
+        is initialised and sends the user to ``nxd.save_checkpoint`` — every (tp, pp) rank writes its own shard file."""
         from ...parallel_layers import parallel_state as ps
 
-        path = path or self.lora_config.lora_save_path
-        assert path is not None
+        path = save_dir or path or getattr(self.lora_config, "lora_save_dir", None) or getattr(self.lora_config, "lora_save_path", None)
+        tag = adapter_tag or tag
+        assert path is not None, "no save_dir given and lora_config.lora_save_dir is not set"
         d = os.path.join(path, tag) if tag else path
         os.makedirs(d, exist_ok=True)
         tp = ps.get_tensor_model_parallel_rank() if ps.model_parallel_is_initialized() else 0
@@ -196,9 +201,23 @@ class LoraModel(nn.Module):
         torch.save({"lora_config": self.lora_config.to_dict(), "state_dict": {k: v.cpu() for k, v in self.lora_state_dict().items()}}, f)
         return f
 
-    def load_lora(self, path: str, tag: Optional[str] = None) -> None:
+    def load_lora(self, save_dir: Optional[str] = None, adapter_tag: Optional[str] = None, ckpt_path: Optional[str] = None,
+                  adapter_only: bool = True, path: Optional[str] = None, tag: Optional[str] = None) -> None:
+        """Load this rank's adapter file from ``save_dir[/adapter_tag]`` (reference lora/model.py:555-595).  With
+        ``adapter_only=False`` the base model's weights are loaded first from ``ckpt_path`` (a plain ``state_dict`` file;
+        default ``<save_dir>[/<tag>]/adapter_model.pt``) unless the adapter checkpoint itself carries the base
+        (``save_lora_base``)."""
         from ...parallel_layers import parallel_state as ps
 
+        path = save_dir or path or getattr(self.lora_config, "lora_save_dir", None)
+        tag = adapter_tag or tag
+        assert path is not None, "no save_dir given and lora_config.lora_save_dir is not set"
+        if not adapter_only and not self.lora_config.save_lora_base:
+            base = ckpt_path or os.path.join(os.path.join(path, tag) if tag else path, WEIGHTS_NAME)
+            if not os.path.exists(base):
+                raise FileNotFoundError(f"The checkpoint file {base} is not found.")
+            self.load_state_dict(torch.load(base, map_location="cpu", weights_only=False), strict=False)
+        self.is_base_model_loaded = True
         d = os.path.join(path, tag) if tag else path
         tp = ps.get_tensor_model_parallel_rank() if ps.model_parallel_is_initialized() else 0
         pp = ps.get_pipeline_model_parallel_rank() if ps.model_parallel_is_initialized() else 0
@@ -347,9 +366,20 @@ class LoraModel(nn.Module):
             get_logger().info("LoRA configuration: %s", self.lora_config)
             self.print_trainable_parameters()
 
-    def load_state_dict(self, sd, strict: bool = True):
-        sd = {(k[len("base_model.model."):] if k.startswith("base_model.model.") else k): v for k, v in sd.items()}
-        return self.module.load_state_dict(sd, strict=False)
+    def load_state_dict(self, state_dict=None, strict: bool = False, assign: bool = False):
+        """Adapter and / or base tensors into the wrapped module.  Keys of a base-model checkpoint written before the adapters
+        were injected (``….weight`` where the module now holds ``….base_layer.weight``) are redirected, as the reference's
+        ``update_state_dict_keys`` does; missing adapter or base entries are tolerated (``strict`` only reports them in the
+        returned result)."""
+        sd = {(k[len("base_model.model."):] if k.startswith("base_model.model.") else k): v for k, v in (state_dict or {}).items()}
+        have = set(self.module.state_dict().keys())
+        for key in list(sd):
+            if key not in have:
+                head, _, leaf = key.rpartition(".")
+                moved = f"{head}.base_layer.{leaf}" if head else key
+                if moved in have:
+                    sd[moved] = sd.pop(key)
+        return self.module.load_state_dict(sd, strict=False, assign=assign)
 
 
 def get_lora_model(model: nn.Module, lora_config: LoraConfig) -> LoraModel:

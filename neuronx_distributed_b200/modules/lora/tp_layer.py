@@ -8,6 +8,8 @@
 """
 from __future__ import annotations
 
+from typing import Optional
+
 import torch
 from torch import nn
 
@@ -18,7 +20,9 @@ from .layer import LoraLayer
 
 
 class LoraParallelLinear(LoraLayer):
-    def __init__(self, base_layer: nn.Module, config: LoraConfig):
+    def __init__(self, base_layer: nn.Module, config: Optional[LoraConfig] = None, lora_config: Optional[LoraConfig] = None, **_compat):
+        config = config if config is not None else lora_config          # ``lora_config=`` is the reference's keyword
+        assert config is not None, "a LoraConfig is required"
         super().__init__(base_layer, config)
         dt, dev = base_layer.weight.dtype, base_layer.weight.device
         self.is_row = isinstance(base_layer, RowParallelLinear)
@@ -63,7 +67,9 @@ class LoraParallelLinear(LoraLayer):
 
 
 class LoraGQAQKVParallelLinear(LoraLayer):
-    def __init__(self, base_layer: GQAQKVColumnParallelLinear, config: LoraConfig):
+    def __init__(self, base_layer: GQAQKVColumnParallelLinear, config: Optional[LoraConfig] = None, lora_config: Optional[LoraConfig] = None, **_compat):
+        config = config if config is not None else lora_config          # ``lora_config=`` is the reference's keyword
+        assert config is not None, "a LoraConfig is required"
         nn.Module.__init__(self)
         self.base_layer, self.lora_config = base_layer, config
         self.r, self.scaling, self.merged = config.lora_rank, config.scaling, False

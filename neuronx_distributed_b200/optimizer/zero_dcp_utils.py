@@ -5,7 +5,7 @@ data-parallel degree re-slices the saved shards on the fly (``_reshard``), witho
 from __future__ import annotations
 
 import os
-from typing import Any, Dict
+from typing import Any, Dict, Optional
 
 import torch
 import torch.distributed as dist
@@ -23,10 +23,26 @@ def _to_dtensor_dict(inner) -> Dict[str, Any]:
     return out
 
 
-def save_optim_state_dict(path: str, state_dict: Dict[str, Any], inner) -> None:
+MAX_RETRY = 100               # the reference polls for other ranks' files this often; loads here open files after a barrier
+
+
+def _inner_of(optim_or_aux):
+    """The ZeRO-1 optimizer from either the optimizer itself (possibly wrapped) or an ``aux_infos`` dict of
+    :func:`get_dcp_aux_infos`."""
+    if isinstance(optim_or_aux, dict):
+        assert "optimizer" in optim_or_aux, "aux_infos must come from get_dcp_aux_infos(model, optimizer)"
+        optim_or_aux = optim_or_aux["optimizer"]
+    return optim_or_aux if hasattr(optim_or_aux, "pg") else getattr(optim_or_aux, "optimizer", optim_or_aux)
+
+
+def save_optim_state_dict(path: str, state_dict: Dict[str, Any], aux_infos, dedup: bool = False) -> None:
     """Each rank writes its shard file set under ``path`` via DCP (one sub-directory per zero1 rank so that shards of
-    differently-sized worlds never collide) plus a small layout file."""
+    differently-sized worlds never collide) plus a small layout file.  Third argument: the optimizer, or — the reference's
+    signature (zero_dcp_utils.py:383-388) — the ``aux_infos`` of :func:`get_dcp_aux_infos`.  ``dedup`` (skip tensor-parallel
+    duplicates) is moot: a rank's directory holds only the state it owns."""
     import torch.distributed.checkpoint as dcp
+
+    inner = _inner_of(aux_infos)
 
     r = dist.get_rank(inner.pg)
     d = os.path.join(path, f"zero1_rank_{r:02d}_of_{dist.get_world_size(inner.pg):02d}")
@@ -92,9 +108,10 @@ def _reshard(path: str, saved_world: int, inner) -> Dict[str, torch.Tensor]:
     return out
 
 
-def load_optim_state_dict(path: str, inner) -> Dict[str, Any]:
+def load_optim_state_dict(path: str, optimizer, aux_infos: Optional[Dict[str, Any]] = None, dedup: bool = False) -> Dict[str, Any]:
     """Load this rank's ZeRO-1 state.  Same data-parallel degree as at save time: read the rank's own directory; a different
     degree: re-slice the saved shards on the fly (reference: DCP load plans over ShardedTensors, ``zero_dcp_utils.py:329-370``)."""
+    inner = _inner_of(optimizer)
     r, world = dist.get_rank(inner.pg), dist.get_world_size(inner.pg)
     d = os.path.join(path, f"zero1_rank_{r:02d}_of_{world:02d}")
     if os.path.isdir(d):
@@ -131,4 +148,5 @@ def get_dcp_aux_infos(model: torch.nn.Module, optim) -> Dict[str, Any]:
             pid_to_names[pid] = names.get(id(p))
             pid += 1
     sd = inner.state_dict() if hasattr(inner, "state_dict") else {}
-    return {"optim_pid_to_params": pid_to_params, "optim_pid_to_pnames": pid_to_names, "shape_info": sd.get("shape_info")}
+    return {"optim_pid_to_params": pid_to_params, "optim_pid_to_pnames": pid_to_names, "shape_info": sd.get("shape_info"),
+            "optimizer": inner}

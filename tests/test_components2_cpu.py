@@ -180,6 +180,18 @@ def _zero_dcp_and_ep(rank, world, tmp):
     step(m1, o1, 2); step(m2, o2, 2)
     for p1, p2 in zip(m1.parameters(), m2.parameters()):
         torch.testing.assert_close(p1, p2, rtol=1e-6, atol=1e-7)
+    # the reference's signatures: save(path, state_dict, aux_infos, dedup) / load(path, optimizer, aux_infos, dedup)
+    aux = dcp.get_dcp_aux_infos(m1, o1)
+    dcp.save_optim_state_dict(os.path.join(tmp, "optim_ref"), o1.state_dict(), aux, dedup=True)
+    dist.barrier()
+    m3, o3 = make()
+    m3.load_state_dict(m1.state_dict())
+    for fg1, fg3 in zip(o1.flat_groups, o3.flat_groups):
+        fg3.param_flat.copy_(fg1.param_flat)
+    o3.load_state_dict(dcp.load_optim_state_dict(os.path.join(tmp, "optim_ref"), o3, dcp.get_dcp_aux_infos(m3, o3), dedup=True))
+    step(m1, o1, 3); step(m3, o3, 3)
+    for p1, p3 in zip(m1.parameters(), m3.parameters()):
+        torch.testing.assert_close(p1, p3, rtol=1e-6, atol=1e-7)
     # ---- EP-aware ZeRO-1
     ps.destroy_model_parallel()
     ps.initialize_model_parallel(tensor_model_parallel_size=1, expert_model_parallel_size=world)

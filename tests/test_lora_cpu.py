@@ -120,6 +120,17 @@ def _tp_lora(rank, world, tmp):
     lm2 = LoraModel(Net(), LoraConfig(lora_rank=2, lora_alpha=4, target_modules=["up_proj", "down_proj"]))
     lm2.load_lora(tmp, "t0")
     torch.testing.assert_close(lm2(x), y)
+    # the reference's keyword names; a base checkpoint written BEFORE adapters were injected loads through the wrapped layers
+    lm.save_lora(save_dir=tmp, adapter_tag="t1")
+    torch.manual_seed(0)
+    plain = Net()
+    base_file = f"{tmp}/base_rank{rank}.pt"
+    torch.save({k: v + 0.25 for k, v in plain.state_dict().items()}, base_file)
+    lm3 = LoraModel(plain, LoraConfig(lora_rank=2, lora_alpha=4, target_modules=["up_proj", "down_proj"]))
+    lm3.load_lora(save_dir=tmp, adapter_tag="t1", ckpt_path=base_file, adapter_only=False)
+    assert lm3.is_base_model_loaded
+    torch.testing.assert_close(lm3.module.up_proj.base_layer.weight, net.up_proj.base_layer.weight + 0.25)
+    torch.testing.assert_close(lm3.module.up_proj.lora_B.weight, lm.module.up_proj.lora_B.weight)
     # merged (un-sharded) adapter: B of the column layer / A of the row layer gathered over TP → same on every rank
     import torch.distributed as dist
 
