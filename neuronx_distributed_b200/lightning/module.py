@@ -30,8 +30,10 @@ class NeuronLTModule(LightningModule):
         self._micro = 0
         self._t_last = None
 
-    def setup(self, stage: Optional[str] = None) -> None:
-        self.model = initialize_parallel_model(self.nxd_config, self.model_fn, False, *self.model_args, **self.model_kwargs)
+    def setup(self, stage: Optional[str] = None, include_buffers: bool = False) -> None:
+        """``include_buffers``: with meta-device initialisation also create the buffers on the meta device (reference
+        module.py ``setup(stage, include_buffers)``)."""
+        self.model = initialize_parallel_model(self.nxd_config, self.model_fn, include_buffers, *self.model_args, **self.model_kwargs)
         self.averaged_loss = torch.zeros((), device=next(self.model.parameters()).device)
 
     def configure_optimizers(self):

@@ -16,8 +16,11 @@ class NeuronHooksCallback(Callback):
     ``cfg.dump_only_norms``, ``cfg.dump_only_master_rank``, ``cfg.master_print_model_layers``), which records
     (input, output) pairs per target layer every ``hooks_interval`` global steps and writes them on batch end."""
 
-    def __init__(self, cfg_or_dump_dir: Any = "hooks_dump", steps: Optional[List[int]] = None, module_filter: Optional[str] = None,
-                 dump_grads: bool = True, dump_dir: Optional[str] = None):
+    def __init__(self, cfg: Any = "hooks_dump", steps: Optional[List[int]] = None, module_filter: Optional[str] = None,
+                 dump_grads: bool = True, dump_dir: Optional[str] = None, cfg_or_dump_dir: Any = None):
+        """``cfg``: the reference's config object (attributes ``hooks``, ``hooks_dump_base_directory``, ``target_layers``, …;
+        neuron_hooks_callback.py:9-40) or simply a dump directory."""
+        cfg_or_dump_dir = cfg if cfg_or_dump_dir is None else cfg_or_dump_dir
         self._handles: List[Any] = []
         self._step = 0
         cfg = None if isinstance(cfg_or_dump_dir, str) else cfg_or_dump_dir

@@ -198,9 +198,11 @@ def test_llama_block_with_fused_add_norm():
 def _lightning_strategy(rank, world, tmp):
     """Strategy surface of the reference (``lightning/strategy.py:84-238``): DP-only metric reduction, batch / dataloader
     placement, checkpoint routing; ``NeuronLTModule.log`` validation and rank filtering; the device prefetch loader."""
+    import os
+
     import pytest
 
-    from neuronx_distributed_b200.lightning import NeuronLTModule, NeuronXLAStrategy, NxDStrategy
+    from neuronx_distributed_b200.lightning import NeuronCheckpointIO, NeuronLTModule, NeuronXLAStrategy, NxDStrategy
     from neuronx_distributed_b200.parallel_layers import parallel_state as ps
     from neuronx_distributed_b200.trainer import neuronx_distributed_config
     from neuronx_distributed_b200.utils.device_loader import DevicePrefetchLoader, MpDeviceLoader
@@ -230,6 +232,15 @@ def _lightning_strategy(rank, world, tmp):
     st.save_checkpoint({"state_dict": lin, "global_step": 7}, f"{tmp}/ck/step_7")
     user = st.load_checkpoint(f"{tmp}/ck/step_7", model=lin)
     assert int(user["global_step"]) == 7
+    # the reference plugin's layout: the whole Lightning dict through the legacy per-rank files, per-DP-rank on request
+    legacy = NeuronCheckpointIO(save_load_xser=False, weights_only=False, layout="legacy")
+    legacy.save_checkpoint({"state_dict": lin.state_dict(), "global_step": 9}, f"{tmp}/legacy/step_9")
+    assert os.path.isfile(f"{tmp}/legacy/step_9/tp_rank_00_pp_rank_00/checkpoint.pt")
+    assert int(legacy.load_checkpoint(checkpoint_path=f"{tmp}/legacy/step_9")["global_step"]) == 9
+    legacy.save_checkpoint({"r": rank}, f"{tmp}/legacy/per_dp", master_dp_only=False)
+    assert legacy.load_checkpoint(f"{tmp}/legacy/per_dp", master_dp_only=False)["r"] == rank
+    with pytest.raises(TypeError):
+        legacy.save_checkpoint({}, f"{tmp}/legacy/x", storage_options={"a": 1})
     # log(): scalar tensors / numbers only, rank filtering, DP sync through the strategy
     mod = NeuronLTModule(cfg, lambda: lin, torch.optim.SGD, log_rank0=True)
 
