@@ -18,10 +18,20 @@ class Experts(nn.Module):
                  dtype=torch.float32, device=None, input_layer_init_method=None, output_layer_init_method=None,
                  tensor_model_parallel_group=None, hidden_act_scaling_factor: float = 1.0, hidden_act_bias: float = 0.0,
                  gate_clamp_upper_limit=None, gate_clamp_lower_limit=None, up_clamp_upper_limit=None,
-                 up_clamp_lower_limit=None, bias: bool = False, expert_model_parallel_group=None, is_prefill: bool = True):
+                 up_clamp_lower_limit=None, bias: bool = False, expert_model_parallel_group=None, is_prefill: bool = True,
+                 glu: Optional[bool] = None, activation_fn=None, expert_distribution=None):
+        """``glu`` / ``activation_fn`` (a callable) are the reference's names for ``glu_mlp`` / the activation (experts.py:24-50);
+        ``hidden_act`` may itself be a callable.  ``expert_distribution`` is forwarded to the expert-fused linears' placement."""
         super().__init__()
+        if glu is not None:
+            glu_mlp = bool(glu)
+        if activation_fn is None and callable(hidden_act):
+            activation_fn, hidden_act = hidden_act, getattr(hidden_act, "__name__", "custom")
+        glu_type = getattr(glu_type, "value", glu_type)
+        glu_type = glu_type.lower() if isinstance(glu_type, str) else glu_type
         self.glu_mlp, self.glu_type = glu_mlp, glu_type
-        self.act = ACT2FN[hidden_act]
+        self.act = activation_fn if activation_fn is not None else ACT2FN[hidden_act]
+        self.expert_distribution = expert_distribution
         self.scale, self.act_bias = hidden_act_scaling_factor, hidden_act_bias
         self.gc_hi, self.gc_lo, self.uc_hi, self.uc_lo = (gate_clamp_upper_limit, gate_clamp_lower_limit,
                                                           up_clamp_upper_limit, up_clamp_lower_limit)
