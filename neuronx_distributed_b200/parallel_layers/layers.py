@@ -603,11 +603,21 @@ def linear_with_async_allreduce(
     async_grad_allreduce: bool,
     sequence_parallel_enabled: bool,
     sequence_dimension: Optional[int] = 0,
-    autocast: bool = False,
+    autograd_func_class: Any = None,
     save_for_backward: bool = True,
     process_group=None,
     reduce_dtype: torch.dtype = torch.float32,
+    autocast: bool = False,
 ) -> torch.Tensor:
+    """Seventh positional argument as in the reference (layers.py:507-532): an autograd class whose ``apply`` takes
+    ``(input, weight, bias, async_grad_allreduce, sequence_parallel_enabled, sequence_dimension, save_for_backward,
+    process_group, reduce_dtype)`` — a custom class is called as is, the default / ``None`` runs the fused TP linear.  A bool in
+    that position is this package's earlier ``autocast`` flag."""
+    if isinstance(autograd_func_class, bool):
+        autocast, autograd_func_class = autograd_func_class, None
+    if autograd_func_class is not None and autograd_func_class is not LinearWithAsyncCommunication:
+        return autograd_func_class.apply(input, weight, bias, async_grad_allreduce, sequence_parallel_enabled, sequence_dimension,
+                                         save_for_backward, process_group, reduce_dtype)
     if sequence_parallel_enabled:
         in_mode = "gather"
     else:

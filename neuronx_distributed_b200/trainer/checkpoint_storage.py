@@ -17,6 +17,10 @@ from typing import Optional, Any, Callable, List
 import torch
 
 
+MB = 1024 ** 2
+SHM_PATH = "/dev/shm"          # scratch for objects staged before an upload (reference checkpoint_storage.py:42-44)
+
+
 class BaseCheckpointStorage(ABC):
     def __init__(self, dirname: str):
         self._dirname = dirname
