@@ -70,21 +70,43 @@ def _pad_dim(t: torch.Tensor, dim: int, new_size: int) -> torch.Tensor:
 
 
 def pad_model(model: nn.Module, tp_degree: int, n_heads: int, wrapped_classes: Sequence[type] = (),
-              pad_hook_fn: Optional[Callable[[nn.Module, int, int], None]] = None) -> nn.Module:
+              pad_hook_fn: Optional[Callable[..., None]] = None) -> nn.Module:
     """Pad every head-sized TP projection from ``n_heads`` to the next multiple of ``tp_degree``.
 
     A Column layer whose *output* size is a multiple of ``n_heads`` (q/k/v/fused-qkv) grows along the
     output dim; a Row layer whose *input* size is a multiple of ``n_heads`` (o_proj) grows along the
     input dim.  Module attributes holding the head count (``num_heads``, ``num_attention_heads``…) on
-    the parent are updated.  ``pad_hook_fn(module, tp_degree, n_heads)`` can customise further."""
+    the parent are updated.
+
+    ``wrapped_classes``: restrict the padding to instances of these classes AND everything below them (reference :79-83).
+    ``pad_hook_fn(module, tgt_src_ratio)`` is called for every module in that scope with ``padded heads / heads`` (reference
+    :59-63, e.g. to rescale a ``split_size`` attribute); a three-parameter hook receives ``(module, tp_degree, n_heads)``."""
+    import inspect
+
     extra = get_number_of_extra_heads(n_heads, tp_degree)
     if extra == 0:
         return model
     tgt_heads = n_heads + extra
+    tgt_src_ratio = tgt_heads / n_heads
     tp_rank, tp = ps.get_tensor_model_parallel_rank(), ps.get_tensor_model_parallel_size()
+    wrapped = tuple(wrapped_classes)
+    in_scope = set()
+
+    def mark(mod, inside):
+        inside = inside or not wrapped or isinstance(mod, wrapped)
+        if inside:
+            in_scope.add(id(mod))
+        for child in mod.children():
+            mark(child, inside)
+
+    mark(model, False)
+    hook_arity = None if pad_hook_fn is None else len([p for p in inspect.signature(pad_hook_fn).parameters.values()
+                                                       if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)])
     for parent in model.modules():
-        if wrapped_classes and not isinstance(parent, tuple(wrapped_classes)):
+        if id(parent) not in in_scope:
             continue
+        if pad_hook_fn is not None and hook_arity == 2:
+            pad_hook_fn(parent, tgt_src_ratio)
         touched = False
         for name, child in list(parent.named_children()):
             if isinstance(child, ColumnParallelLinear) and child.output_size % n_heads == 0 and not child.gather_output:
@@ -128,7 +150,7 @@ def pad_model(model: nn.Module, tp_degree: int, n_heads: int, wrapped_classes: S
             for attr in ("num_heads_local",):
                 if hasattr(parent, attr):
                     setattr(parent, attr, tgt_heads // tp)
-            if pad_hook_fn is not None:
+            if pad_hook_fn is not None and hook_arity != 2:
                 pad_hook_fn(parent, tp_degree, n_heads)
     return model
 

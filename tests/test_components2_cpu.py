@@ -47,6 +47,28 @@ def _spmd_pad_lora(rank, world, tmp):
     pad_model(a, tp_degree=2, n_heads=3)
     assert a.num_heads == 4 and a.q.weight.shape == (16, 8) and a.o.weight.shape == (8, 16)
     torch.testing.assert_close(a.o(a.q(x)), want)
+    # scope and hook of the reference: only instances of ``wrapped_classes`` (and what is below them) are padded, and the hook
+    # sees every module in that scope together with padded_heads / heads
+    class Two(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.attn, self.other = Attn(), Attn()
+            self.attn.split_size = 12
+
+    two, seen = Two(), []
+
+    def hook(mod, ratio):
+        seen.append((type(mod).__name__, ratio))
+        if hasattr(mod, "split_size"):
+            mod.split_size = int(mod.split_size * ratio)
+
+    class Marker(Attn):
+        pass
+
+    two.attn.__class__ = Marker
+    pad_model(two, tp_degree=2, n_heads=3, wrapped_classes=[Marker], pad_hook_fn=hook)
+    assert two.attn.q.weight.shape == (16, 8) and two.other.q.weight.shape == (12, 8) and two.attn.split_size == 16
+    assert sorted(n for n, _ in seen) == ["ColumnParallelLinear", "Marker", "RowParallelLinear"] and all(abs(r - 4 / 3) < 1e-9 for _, r in seen)
     ps.destroy_model_parallel(); ps.initialize_model_parallel(tensor_model_parallel_size=world)
     # cumsum helper keeps dtype semantics
     t = torch.arange(10, dtype=torch.float32).view(2, 5)
