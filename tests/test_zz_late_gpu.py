@@ -36,9 +36,27 @@ def _run(code: str, timeout: int = _PER_TEST_S, env=None) -> None:
     timeout = min(timeout, _PER_TEST_S)
     e = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     e.update(env or {})
-    p = subprocess.run([sys.executable, "-c", textwrap.dedent(code)], cwd=ROOT, env=e, timeout=timeout,
-                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    assert p.returncode == 0, p.stdout[-4000:]
+    # own session = own process group: on a timeout the whole group is killed, so worker processes spawned by the check (the
+    # two-rank loopback checks) cannot stay behind with a spinning kernel and occupy the GPU for whatever runs after this file
+    import signal
+
+    proc = subprocess.Popen([sys.executable, "-c", textwrap.dedent(code)], cwd=ROOT, env=e, stdout=subprocess.PIPE,
+                            stderr=subprocess.STDOUT, text=True, start_new_session=True)
+    try:
+        out, _ = proc.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(proc.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
+        out, _ = proc.communicate()
+        raise AssertionError(f"timed out after {timeout} s\n{(out or '')[-4000:]}")
+    finally:
+        try:                                            # stragglers of a check that returned (failed or not)
+            os.killpg(proc.pid, signal.SIGKILL)
+        except (ProcessLookupError, PermissionError):
+            pass
+    assert proc.returncode == 0, (out or "")[-4000:]
 
 
 def test_fused_lmhead_ce_on_device():
