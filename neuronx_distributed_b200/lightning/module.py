@@ -16,7 +16,7 @@ class NeuronLTModule(LightningModule):
     def __init__(self, nxd_config: Dict[str, Any], model_fn: Callable, opt_cls: Callable, scheduler_cls: Optional[Callable] = None,
                  model_args: Tuple = (), model_kwargs: Optional[Dict] = None, opt_args: Tuple = (), opt_kwargs: Optional[Dict] = None,
                  scheduler_args: Tuple = (), scheduler_kwargs: Optional[Dict] = None, grad_accum_steps: int = 1,
-                 log_rank0: bool = False, manual_opt: bool = True, train_batch_size: int = 1, logging_interval: int = 1):
+                 log_rank0: bool = False, manual_opt: bool = True, train_batch_size: int = 16, logging_interval: int = 1):
         super().__init__()
         self.nxd_config, self.model_fn, self.opt_cls, self.scheduler_cls = nxd_config, model_fn, opt_cls, scheduler_cls
         self.model_args, self.model_kwargs = model_args, model_kwargs or {}

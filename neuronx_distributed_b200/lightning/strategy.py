@@ -74,7 +74,7 @@ class NxDStrategy(_BaseStrategy):
     def broadcast(self, obj, src: int = 0):
         return obj          # all ranks construct identical objects from the same seed/config
 
-    def reduce(self, output=None, group: Optional[Any] = None, reduce_op: Optional[Any] = "mean", tensor=None):
+    def reduce(self, output=None, group: Optional[Any] = None, reduce_op: Optional[Any] = None, tensor=None):
         """Metric reduction across DATA-parallel replicas (TP / PP ranks of one replica hold the same value): ``mean`` /
         ``avg`` / ``sum``; non-tensors and single-replica runs pass through (reference :159-199)."""
         tensor = output if tensor is None else tensor            # ``output`` is the reference's / Lightning's argument name

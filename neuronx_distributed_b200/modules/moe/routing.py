@@ -89,12 +89,15 @@ class RouterSinkhorn(RouterBase):
 
     """Top-1 routing balanced with Sinkhorn iterations during training (Megatron-style)."""
 
-    def __init__(self, *a, sinkhorn_iterations: int = 30, sinkhorn_tol: Optional[float] = None, **k):
+    DEFAULT_SINKHORN_ITERS = 30
+
+    def __init__(self, *a, sinkhorn_iterations: Optional[int] = None, sinkhorn_tol: Optional[float] = None, **k):
         k.setdefault("act_fn", "sigmoid")
         super().__init__(*a, **k)
         if self.top_k != 1:
             raise NotImplementedError("RouterSinkhorn supports top_k=1 only")
-        self.sinkhorn_iterations, self.sinkhorn_tol = sinkhorn_iterations, sinkhorn_tol
+        self.sinkhorn_iterations = sinkhorn_iterations if sinkhorn_iterations is not None else self.DEFAULT_SINKHORN_ITERS
+        self.sinkhorn_tol = sinkhorn_tol
 
     @staticmethod
     def _sinkhorn(cost: torch.Tensor, iters: int, tol: Optional[float]) -> torch.Tensor:

@@ -692,7 +692,7 @@ class QuantizedExpertFusedColumnParallel(QuantizedColumnParallel, _QuantizedExpe
 class QuantizedExpertFusedRowParallel(QuantizedRowParallel, _QuantizedExpertMixin):
     """Quantised ``[E_local, in/tp, out]`` expert weights (reference :1215-1414)."""
 
-    def __init__(self, num_experts: int, input_size: int, output_size: int, reduce_output: bool = True, bias: bool = False,
+    def __init__(self, num_experts: int, input_size: int, output_size: int, reduce_output: bool = False, bias: bool = False,
                  quantization_type: Union[QuantizationType, str] = "per_tensor_symmetric", dtype: torch.dtype = torch.float32,
                  quantized_dtype: Union[QuantizedDtype, torch.dtype] = QuantizedDtype.INT8,
                  device: Optional[torch.device] = None, stride: int = 1, keep_master_weight: bool = False,

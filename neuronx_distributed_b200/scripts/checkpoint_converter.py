@@ -138,7 +138,7 @@ class CheckpointConverterBase:
                  ("self_attn", "self_attention"), ("mlp.gate_up_proj", "mlp.dense_h_to_4h"), ("mlp.down_proj", "mlp.dense_4h_to_h"),
                  ("model.norm", "language_model.encoder.final_layernorm"), ("lm_head", "language_model.output_layer")]
 
-    def rename_keys_for_megatron(self, key: str, model_style: str, hf_to_nxdt: bool = True) -> str:
+    def rename_keys_for_megatron(self, key: str, model_style: str, hf_to_nxdt: bool = False) -> str:
         if model_style != "megatron":
             return key
         for hf, mg in self._MEGATRON:

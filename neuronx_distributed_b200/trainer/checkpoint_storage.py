@@ -371,7 +371,7 @@ class S3CheckpointStorage(BaseCheckpointStorage):
         return [p[len(pfx):].rstrip("/") for p in prefixes]
 
     def find_files(self, dirname=None, pattern=None, search_root: Optional[str] = None, max_count: Optional[int] = None,
-                   sort_by_mdate: bool = False, search_depth: Optional[int] = None) -> List[str]:
+                   sort_by_mdate: bool = True, search_depth: Optional[int] = None) -> List[str]:
         """Two call forms, like the file-system back-end: ``find_files(dirname, pattern)`` — files under ``dirname`` whose
         base name matches the glob; ``find_files(pattern, search_depth, search_root, max_count, sort_by_mdate)`` — the
         reference's depth-limited search (paths relative to the storage root)."""
