@@ -268,8 +268,9 @@ class ExpertMLPsV2(ProcessGroupSafeDeepcopy, nn.Module):
             expert_mask, a = expert_mask[:, chosen_expert_indices], a[:, chosen_expert_indices]
         return num_experts, expert_mask, a, hidden_states
 
-    def forward_all_experts(self, x: torch.Tensor, aff: torch.Tensor, idx: torch.Tensor, chosen_expert_indices=None,
+    def forward_all_experts(self, hidden_states: torch.Tensor, expert_affinities: torch.Tensor, expert_index: torch.Tensor, chosen_expert_indices=None,
                             padding_mask=None) -> torch.Tensor:
+        x, aff, idx = hidden_states, expert_affinities, expert_index      # reference parameter names in the signature
         mlp_op = self.get_mlp_op()
         a = self._topk_affinities(aff, idx, padding_mask)                     # [T, E]
         local = torch.as_tensor(mlp_op.local_expert_ids, device=x.device)
@@ -283,13 +284,16 @@ class ExpertMLPsV2(ProcessGroupSafeDeepcopy, nn.Module):
         y = mlp_op(xe, chosen_expert_indices)                                 # [E_l, T, H]
         return (y * w.to(y.dtype)).sum(0)
 
-    def forward_all_experts_EP(self, x: torch.Tensor, aff: torch.Tensor, idx: torch.Tensor, padding_mask=None) -> torch.Tensor:
+    def forward_all_experts_EP(self, hidden_states: torch.Tensor, expert_affinities: torch.Tensor, expert_index: torch.Tensor,
+                               chosen_expert_indices=None, padding_mask=None) -> torch.Tensor:
         """Inference EP: every rank runs its local experts on all tokens; the MoE layer sums over the EP group."""
+        x, aff, idx = hidden_states, expert_affinities, expert_index      # reference parameter names in the signature
         return self.forward_all_experts(x, aff, idx, padding_mask=padding_mask)
 
-    def forward_selective_loading(self, x: torch.Tensor, aff: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    def forward_selective_loading(self, hidden_states: torch.Tensor, expert_affinities: torch.Tensor, expert_index: torch.Tensor) -> torch.Tensor:
         """Touch only the ``T·k`` chosen experts (decode / short speculation windows, reference :595-625).  Vectorised
         over tokens: the (token, slot) pairs become ``T·k`` single-token "experts" of one batched contraction."""
+        x, aff, idx = hidden_states, expert_affinities, expert_index      # reference parameter names in the signature
         if self.ep > 1:
             raise NotImplementedError("Selective Loading with Expert parallelism is not supported in token generation.")
         mlp_op = self.get_mlp_op()
@@ -307,7 +311,8 @@ class ExpertMLPsV2(ProcessGroupSafeDeepcopy, nn.Module):
             y = y * w.to(y.dtype)
         return y.reshape(T, k, -1).sum(1)
 
-    def forward_capacity_factor(self, x: torch.Tensor, aff: torch.Tensor, idx: torch.Tensor, padding_mask=None) -> torch.Tensor:
+    def forward_capacity_factor(self, hidden_states: torch.Tensor, expert_affinities: torch.Tensor, expert_index: torch.Tensor, padding_mask=None) -> torch.Tensor:
+        x, aff, idx = hidden_states, expert_affinities, expert_index      # reference parameter names in the signature
         T, H = x.shape
         E, k = self.num_experts, self.top_k
         cf = self.capacity_factor if self.capacity_factor is not None else E / k
@@ -347,8 +352,9 @@ class ExpertMLPsV2(ProcessGroupSafeDeepcopy, nn.Module):
         out.index_add_(0, t_idx, picked if early else picked * a[t_idx, e_idx].unsqueeze(-1).to(y.dtype))
         return out
 
-    def forward_blockwise(self, x: torch.Tensor, aff: torch.Tensor, idx: torch.Tensor, expert_affinities_masked_full=None,
+    def forward_blockwise(self, hidden_states: torch.Tensor, expert_affinities: torch.Tensor, expert_index: torch.Tensor, expert_affinities_masked_full=None,
                           padding_mask=None) -> torch.Tensor:
+        x, aff, idx = hidden_states, expert_affinities, expert_index      # reference parameter names in the signature
         a = expert_affinities_masked_full if expert_affinities_masked_full is not None else \
             self._topk_affinities(aff, idx, padding_mask)
         if self.ep > 1:

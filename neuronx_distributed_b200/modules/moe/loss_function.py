@@ -9,8 +9,9 @@ import torch
 import torch.nn.functional as F
 
 
-def load_balancing_loss_func(concatenated_gate_logits: Union[torch.Tensor, Sequence[torch.Tensor]], num_experts: int,
+def load_balancing_loss_func(router_logits: Union[torch.Tensor, Sequence[torch.Tensor]], num_experts: int,
                              top_k: int) -> torch.Tensor:
+    concatenated_gate_logits = router_logits      # reference parameter names in the signature
     if not isinstance(concatenated_gate_logits, torch.Tensor):
         concatenated_gate_logits = torch.cat([g.reshape(-1, num_experts) for g in concatenated_gate_logits], dim=0)
     logits = concatenated_gate_logits.reshape(-1, num_experts).float()
