@@ -425,6 +425,14 @@ def get_tensor_model_parallel_replica_groups() -> List[List[int]]:
     return _group("tp", True)
 
 
+def _set_override(key: str, value) -> None:
+    """Manual override of a size / rank (offline tools that play every rank in one process); ``None`` removes it."""
+    if value is None:
+        _STATE.overrides.pop(key, None)
+    else:
+        _STATE.overrides[key] = value
+
+
 def get_tensor_model_parallel_size() -> int:
     if "tp_size" in _STATE.overrides:
         return _STATE.overrides["tp_size"]
@@ -432,7 +440,7 @@ def get_tensor_model_parallel_size() -> int:
 
 
 def set_tensor_model_parallel_size(world_size: int) -> None:
-    _STATE.overrides["tp_size"] = world_size
+    _set_override("tp_size", world_size)
 
 
 def get_tensor_model_parallel_rank() -> int:
@@ -442,7 +450,7 @@ def get_tensor_model_parallel_rank() -> int:
 
 
 def set_tensor_model_parallel_rank(rank: int) -> None:
-    _STATE.overrides["tp_rank"] = rank
+    _set_override("tp_rank", rank)
 
 
 def get_tensor_model_parallel_src_rank() -> int:
@@ -495,7 +503,7 @@ def get_expert_model_parallel_size() -> int:
 
 
 def set_expert_model_parallel_size(world_size: int) -> None:
-    _STATE.overrides["ep_size"] = world_size
+    _set_override("ep_size", world_size)
 
 
 def get_expert_model_parallel_rank() -> int:
@@ -505,7 +513,7 @@ def get_expert_model_parallel_rank() -> int:
 
 
 def set_expert_model_parallel_rank(rank: int) -> None:
-    _STATE.overrides["ep_rank"] = rank
+    _set_override("ep_rank", rank)
 
 
 def get_expert_data_parallel_group(as_list: bool = False) -> GroupOrMesh:
@@ -646,7 +654,7 @@ def get_context_model_parallel_size() -> int:
 
 
 def set_context_model_parallel_size(world_size: int) -> None:
-    _STATE.overrides["cp_size"] = world_size
+    _set_override("cp_size", world_size)
 
 
 def get_context_model_parallel_rank() -> int:
