@@ -16,18 +16,25 @@ class MockDistributed(MagicMock):
     def __init__(self, *args, world_size: int = 1, **kwargs):
         super().__init__(*args, **kwargs)
         self.__dict__["_world_size"] = world_size
+        self.__dict__["_rank"] = 0
+        self.__dict__["_alive"] = True
 
     def is_initialized(self) -> bool:
-        return True
+        return self.__dict__["_alive"]
 
     def is_available(self) -> bool:
         return True
 
     def init_process_group(self, backend=None, rank: int = 0, world_size: int = 1, **_):
-        self.__dict__["_world_size"] = world_size
+        """Which rank this process pretends to be (reference :22-25: the rank whose shard is being built)."""
+        self.__dict__["_world_size"], self.__dict__["_rank"], self.__dict__["_alive"] = world_size, rank, True
 
     def get_rank(self, group=None) -> int:
-        return 0
+        ranks = getattr(group, "ranks", None)
+        me = self.__dict__["_rank"]
+        if ranks:
+            return ranks.index(me) if me in ranks else -1
+        return me
 
     def get_backend(self, group=None) -> str:
         return "gloo"
@@ -40,13 +47,15 @@ class MockDistributed(MagicMock):
         return list(getattr(group, "ranks", range(self.__dict__["_world_size"])))
 
     def destroy_process_group(self, group=None) -> None:
-        return None
+        if group is None:
+            self.__dict__["_alive"] = False
 
     def new_group(self, ranks=None, *args, **kwargs):
         g = MagicMock(spec=torch.distributed.ProcessGroup)
         g.ranks = list(ranks) if ranks is not None else list(range(self.__dict__["_world_size"]))
         g.size.return_value = len(g.ranks)
-        g.rank.return_value = 0
+        me = self.__dict__["_rank"]
+        g.rank.return_value = g.ranks.index(me) if me in g.ranks else -1
         return g
 
     def barrier(self, *a, **k) -> None:

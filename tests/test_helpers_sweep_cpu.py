@@ -217,3 +217,55 @@ def _opt_from_class(rank, world):
 
 def test_initialize_optimizer_from_class():
     run_distributed(_opt_from_class, 1, timeout=120)
+
+
+def test_mock_distributed_schedule_bases_and_state_dict_adaptor():
+    from neuronx_distributed_b200.pipeline import scheduler as S
+    from neuronx_distributed_b200.quantization.quantization_config import MyEnumMeta, QuantizationType
+    from neuronx_distributed_b200.quantization.quantization_layers import QuantizedParallelLinearLayerStateDictAdaptor as Ad
+    from neuronx_distributed_b200.trace.mock_torchdist import MockDistributed
+    from neuronx_distributed_b200.trace.trace import ParallelModel
+    from neuronx_distributed_b200.utils.serialization import TensorStub
+    from neuronx_distributed_b200.utils.tensor_replacement import TensorReplacementRegistry, enable_tensor_replacement
+
+    # stand-in for torch.distributed while sharding checkpoints for N ranks in one process
+    md = MockDistributed(world_size=8)
+    md.init_process_group("nccl", rank=3, world_size=8)
+    assert md.is_available() and md.is_initialized() and md.get_world_size() == 8 and md.get_rank() == 3
+    g = md.new_group(ranks=[2, 3])
+    assert md.get_world_size(g) == 2 and md.get_process_group_ranks(g) == [2, 3] and md.get_rank(g) == 1
+    md.barrier(); md.destroy_process_group()
+    assert not md.is_initialized()
+    # schedule base classes: the deprecated lock-step name computes in 1F1B order; task records carry (mb, chunk)
+    assert issubclass(S.Train1F1BSchedule, S.PipeSchedule) and issubclass(S.TrainSchedule, S.Train1F1BSchedule)
+    assert S.TrainSchedule(4, 2, 0).compute_order() == S.Train1F1BSchedule(4, 2, 0).compute_order()
+    t = S.ForwardStepTask(1, 0)
+    assert isinstance(t, S.PipelineTask) and (t.mb, t.model_chunk) == (1, 0) and isinstance(S.ReduceGradsTask(), S.PostProcessTask)
+    with pytest.raises(TypeError):
+        S.PipeSchedule(4, 2, 0)                                                     # abstract
+    # wrapper base of the traced models is a plain module container
+    pm = ParallelModel()
+    assert isinstance(pm, nn.Module) and list(pm.parameters()) == []
+    # state-dict adaptor: plain layout and torch's packed qint8 layout answer the same questions
+    w, b = torch.randint(-8, 8, (4, 3), dtype=torch.int8), torch.ones(4)
+    sd = {"l.weight": w, "l.scale": torch.tensor([0.5]), "l.bias": b}
+    assert torch.equal(Ad.get_weight_from_state_dict("l.", sd), w) and float(Ad.get_scale_from_state_dict("l.", sd)) == 0.5
+    assert torch.equal(Ad.get_bias_from_state_dict("l.", sd), b)
+    Ad.set_weight_to_state_dict("l.", w + 1, sd); Ad.set_bias_to_state_dict("l.", b * 2, sd)
+    assert torch.equal(Ad.get_weight_from_state_dict("l.", sd), w + 1) and torch.equal(Ad.get_bias_from_state_dict("l.", sd), b * 2)
+    qlin = torch.ao.nn.quantized.Linear(3, 4)
+    qsd = {"q." + k: v for k, v in qlin.state_dict().items()}
+    assert Ad.get_weight_from_state_dict("q.", qsd).shape == (4, 3) and Ad.get_scale_from_state_dict("q.", qsd).numel() >= 1
+    # enum membership by raw value
+    assert isinstance(QuantizationType, MyEnumMeta) and "per_tensor_symmetric" in QuantizationType and "nope" not in QuantizationType
+    # replacement registry is a process-wide singleton that the hooks read
+    lin = nn.Linear(2, 2)
+    m = nn.Sequential(lin)
+    reg = TensorReplacementRegistry.get()
+    assert reg is TensorReplacementRegistry.get()
+    enable_tensor_replacement(m, {"0": torch.full((1, 2), 7.0)})
+    assert torch.equal(m(torch.zeros(1, 2)), torch.full((1, 2), 7.0)) and "0" in reg.replacements
+    for h in reg.handles:
+        h.remove()
+    reg.handles.clear(); reg.replacements.clear(); reg.masks.clear()
+    assert repr(TensorStub(3)) == "TensorStub(3)"
