@@ -269,3 +269,95 @@ def test_mock_distributed_schedule_bases_and_state_dict_adaptor():
         h.remove()
     reg.handles.clear(); reg.replacements.clear(); reg.masks.clear()
     assert repr(TensorStub(3)) == "TensorStub(3)"
+
+
+def _moe_helpers(rank, world):
+    """Building blocks of ``ExpertMLPsV2`` that the reference exposes and callers reach directly."""
+    from neuronx_distributed_b200.modules.moe import ExpertMLPsV2, RoutedExpertsMLPOpsConfig
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.parallel_layers.layers import SPMDRank
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    torch.manual_seed(0)
+    E, k, H, I, T = 4, 2, 8, 16, 6
+    em = ExpertMLPsV2(RoutedExpertsMLPOpsConfig(normalize_top_k_affinities=True, num_experts=E, top_k=k, hidden_size=H, intermediate_size=I))
+    aff = torch.rand(T, E).softmax(-1)
+    idx = aff.topk(k, -1).indices
+    x = torch.randn(T, H)
+    # all-experts set-up: (count, k-hot mask, affinities of the chosen experts only, tokens), optionally a subset of experts
+    n, mask, a, xs = em.setup_all_experts(x, aff, idx)
+    assert n == E and mask.shape == (T, E) and mask.sum(-1).tolist() == [k] * T and xs is x
+    assert torch.allclose(a.sum(-1), torch.ones(T)) and ((a > 0) == (mask > 0)).all()
+    n2, mask2, a2, _ = em.setup_all_experts(x, aff, idx, chosen_expert_indices=[0, 2])
+    assert n2 == 2 and torch.equal(mask2, mask[:, [0, 2]]) and torch.equal(a2, a[:, [0, 2]])
+    # masked affinities: computed from the router outputs unless the caller already has the full tensor
+    assert torch.equal(em.maybe_get_expert_affinities_masked(idx, aff), a)
+    marker = torch.zeros(1)
+    assert em.maybe_get_expert_affinities_masked(idx, aff, expert_affinities_masked_full=marker) is marker
+    # sequence-parallel router outputs are gathered over the TP group (rank r holds its own token shard)
+    full = em.get_full_expert_affinities_masked(aff, idx)
+    assert full.shape == (T * world, E) and torch.equal(full[rank * T:(rank + 1) * T], a)
+    ga, gm, gi = em.get_sp_expert_masks_index(a, idx)
+    assert ga.shape == (T * world, E) and gi.shape == (T * world, k) and torch.equal((ga > 0).to(torch.float64), gm)
+    # block bookkeeping: which blocks hold at least one real token; the kernel-named mapping equals the default one
+    from neuronx_distributed_b200.modules.moe.blockwise import build_block_metadata
+
+    b2e, tp2id, _ = build_block_metadata(idx, E, 4)
+    cond = em.get_block_conditions(4, b2e.numel(), tp2id)
+    assert cond.dtype == torch.int32 and cond.tolist() == [int((tp2id.view(-1, 4)[b] != -1).any()) for b in range(b2e.numel())]
+    m1 = em.get_blockwise_expert_and_token_mapping(T, b2e.numel(), None, idx, block_size=4)
+    m2 = em.get_blockwise_expert_and_token_mapping_kernel(T, b2e.numel(), None, idx, block_size=4)
+    assert all(torch.equal(u, v) for u, v in zip(m1, m2))
+    # redundant experts: this rank hosts logical experts [1, 1, 3]; expert 1's token range is split between its two replicas,
+    # and the second local copy of the same expert is switched off
+    deg = torch.tensor([[0, 2, 0, 1]])                                            # one EP rank, replicas per expert
+    start, end = em.allocate_token_blocks(deg, [8, 8, 8, 8])
+    lm = torch.ones(8, 3)
+    out = em.generate_local_expert_mask_with_redundancy(lm, torch.tensor([1, 1, 3]), start, end, E, 0)
+    assert out[:, 0].sum() == 8 and out[:, 1].sum() == 0 and out[:, 2].sum() == 8
+    # expert weights can be rebuilt for other groups (hybrid prefill / decode sharding)
+    old = em.mlp_op
+    new = em.initialize_mlp_op(ps.get_tensor_model_parallel_group(), None, is_prefill=False)
+    assert new is em.mlp_op and new is not old and new.down_proj.weight.shape == old.down_proj.weight.shape
+    assert em.get_spmd_rank() is None
+    # the SPMD rank module carries this rank's expert ids as a (sharded) weight
+    sr = SPMDRank(world_size=world)
+    p = sr.initialize_expert_indices(E)
+    assert p.shape == (1, E) and sr.get_local_expert_indices() is p and p.tolist() == [[0, 1, 2, 3]] and p.tensor_model_parallel
+
+
+def test_expert_mlp_building_blocks_tp2():
+    run_distributed(_moe_helpers, 2, timeout=180)
+
+
+def test_schedule_ids_rng_states_observer_and_dtypes():
+    from neuronx_distributed_b200.parallel_layers import random as prandom
+    from neuronx_distributed_b200.pipeline import scheduler as S
+    from neuronx_distributed_b200.quantization.observer import PerChannelAbsMaxObserver
+    from neuronx_distributed_b200.quantization.quantization_config import QuantizedDtype
+
+    sch = S.TrainInterleavedSchedule(4, 2, 2, 0)                                    # 4 micro-batches, 2 chunks, pp = 2, stage 0
+    order = sch.compute_order()
+    fwd = [(mb, c) for is_f, mb, c in order if is_f]
+    assert [(sch.get_microbatch_id(i), sch.get_model_chunk_id(i)) for i in range(len(fwd))] == fwd
+    assert sorted(fwd) == sorted((m, c) for m in range(4) for c in range(2))
+    # RNG tracker state can be exported / restored (activation recompute replays the same dropout masks)
+    tr = prandom.RNGStatesTracker()
+    tr.add("mp", 7)
+    snap = {k: v.clone() for k, v in tr.get_states().items()}
+    with tr.fork("mp"):
+        a = torch.rand(4)
+    tr.set_states(snap)
+    with tr.fork("mp"):
+        b = torch.rand(4)
+    assert torch.equal(a, b)
+    # per-channel abs-max observer accumulates over calls and can be reset
+    ob = PerChannelAbsMaxObserver(ch_axis=0)
+    ob(torch.tensor([[1.0, -3.0], [0.5, 0.2]])); ob(torch.tensor([[2.0, 1.0], [-4.0, 0.1]]))
+    assert ob.abs_max.flatten().tolist() == [3.0, 4.0]
+    ob.reset_min_max_vals()
+    ob(torch.tensor([[1.0, 0.0], [0.0, 0.5]]))
+    assert ob.abs_max.flatten().tolist() == [1.0, 0.5]
+    scale, zero = ob.calculate_qparams()
+    assert scale.shape == (2,) and torch.allclose(scale, torch.tensor([1.0, 0.5]) / ob.quant_max) and not zero.any()
+    assert QuantizedDtype.INT8.storage_dtype() is torch.int8 and QuantizedDtype.F8E4M3FN_X4.storage_dtype() is torch.uint32
