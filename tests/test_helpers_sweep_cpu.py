@@ -361,3 +361,85 @@ def test_schedule_ids_rng_states_observer_and_dtypes():
     scale, zero = ob.calculate_qparams()
     assert scale.shape == (2,) and torch.allclose(scale, torch.tensor([1.0, 0.5]) / ob.quant_max) and not zero.any()
     assert QuantizedDtype.INT8.storage_dtype() is torch.int8 and QuantizedDtype.F8E4M3FN_X4.storage_dtype() is torch.uint32
+
+
+def _builder_pieces(rank, world, tmp):
+    """The separately callable steps of the first-generation builder and the runtime model's initialisation variants."""
+    import neuronx_distributed_b200  # noqa: F401
+    from neuronx_distributed_b200.parallel_layers import ColumnParallelLinear, RowParallelLinear
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.trace.model_builder import ModelBuilder
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.up = ColumnParallelLinear(8, 16, bias=False, gather_output=False)
+            self.down = RowParallelLinear(16, 8, bias=False, input_is_parallel=True)
+            self.register_buffer("cache", torch.zeros(2, 8))
+
+        def forward(self, x):
+            return self.down(torch.relu(self.up(x)))
+
+    torch.manual_seed(0)
+    net = Net()
+    torch.manual_seed(1)
+    full = {"up.weight": torch.randn(16, 8), "down.weight": torch.randn(8, 16)}
+    mb = ModelBuilder(None, world, lambda: dict(full), model=net, use_cuda_graphs=False)       # reference positional order
+    mb.add("main", net, [(torch.randn(2, 8),)])
+    shard = mb.shard_weights(rank)
+    assert shard["up.weight"].shape == (16 // world, 8) and torch.equal(shard["up.weight"], full["up.weight"].chunk(world, 0)[rank])
+    assert torch.equal(mb.shard_weights_with_cache(rank)["down.weight"], full["down.weight"].chunk(world, 1)[rank])
+    assert torch.equal(mb.shard_weights_with_cache(rank)["up.weight"], shard["up.weight"])      # second call: cached full checkpoint
+    cast = ModelBuilder.cast_weights({"up.weight": torch.ones(16 // world, 8, dtype=torch.float64)}, net)
+    assert cast["up.weight"].dtype == torch.float32
+    init = mb.build_state_initializer()
+    states = init()
+    assert list(states[0]) == ["cache"] and states[0]["cache"].shape == (2, 8) and not states[0]["cache"].any()
+    fl, pk = mb.build_flattener_map(), mb.build_packer()
+    assert list(fl) == ["main_0"] and fl["main_0"]((1, 2)) == [1, 2] and pk("y") == "y"
+    nxd_model = mb.build_nxd_model()
+    # weights: `initialize` = set_weights + to_neuron in one call; `initialize_with_saved_weights` trusts the modules
+    nxd_model.initialize_spmd_models(None, [mb.shard_weights(r) for r in range(world)], 0)
+    x = torch.randn(2, 8, generator=torch.Generator().manual_seed(3))
+    want = torch.relu(x @ full["up.weight"].t()) @ full["down.weight"].t()
+    torch.testing.assert_close(nxd_model(x), want, rtol=1e-4, atol=1e-5)
+    nxd2 = mb.build_nxd_model()
+    nxd2.mock_initialization(True)
+    assert nxd2.loaded_on_device
+    nxd2.initialize_with_saved_weights(0)
+    torch.testing.assert_close(nxd2(x), want, rtol=1e-4, atol=1e-5)
+    mb.write_neff_to_file(nxd_model, os.path.join(tmp, f"r{rank}"))
+    assert "main" in open(os.path.join(tmp, f"r{rank}", "programs.txt")).read()
+
+
+def test_v1_builder_steps_and_runtime_initialisation_tp2(tmp_path):
+    run_distributed(_builder_pieces, 2, str(tmp_path), timeout=180)
+
+
+def test_lora_serving_config_files_and_lightning_bits(tmp_path):
+    from neuronx_distributed_b200.lightning.accelerator import NeuronXLAAccelerator
+    from neuronx_distributed_b200.lightning.logger import NeuronTensorBoardLogger
+    from neuronx_distributed_b200.modules.lora.serving import LoraServingConfig
+
+    cfg = LoraServingConfig(max_loras=3, max_lora_rank=8, target_modules=["q_proj"], lora_dtype=torch.bfloat16)
+    f = str(tmp_path / "serving.json")
+    cfg.to_json_file(f)
+    back = LoraServingConfig.from_json_file(f)
+    assert (back.max_loras, back.max_lora_rank, back.target_modules, back.lora_dtype) == (3, 8, ["q_proj"], torch.bfloat16)
+    assert LoraServingConfig.from_json_file(str(tmp_path / "missing.json")) is None
+    assert LoraServingConfig.from_json_file(f, max_loras=5).max_loras == 5                     # keyword overrides win
+
+    class Registry(dict):
+        def register(self, name, cls, description=""):
+            self[name] = (cls, description)
+
+    reg = Registry()
+    NeuronXLAAccelerator.register_accelerators(reg)
+    assert reg["b200"][0] is NeuronXLAAccelerator
+    assert NeuronXLAAccelerator().get_device_stats(torch.device("cpu")) == {}                 # no CUDA here: nothing to report
+    lg = NeuronTensorBoardLogger(str(tmp_path), name="run", version="v0")
+    lg.log_metrics({"loss": 1.5}, step=1)
+    assert lg.experiment is not None and lg.print_step() in (True, False)
+    lg.log_graph(nn.Linear(2, 2))                                                             # accepted, nothing to draw
