@@ -443,3 +443,84 @@ def test_lora_serving_config_files_and_lightning_bits(tmp_path):
     lg.log_metrics({"loss": 1.5}, step=1)
     assert lg.experiment is not None and lg.print_step() in (True, False)
     lg.log_graph(nn.Linear(2, 2))                                                             # accepted, nothing to draw
+
+
+def _last_batch(rank, world, tmp):
+    import neuronx_distributed_b200 as nxd
+    from neuronx_distributed_b200.inference.gqa import GQA, BaseGroupQueryAttention
+    from neuronx_distributed_b200.lightning import NeuronCheckpointIO, NeuronLTModule
+    from neuronx_distributed_b200.models.llama import LlamaConfig, LlamaForCausalLM
+    from neuronx_distributed_b200.modules.lora import LoraConfig, LoraModel
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.pipeline import NxDPPModel
+    from neuronx_distributed_b200.scripts.checkpoint_converter import CheckpointConverterBase
+    from neuronx_distributed_b200.utils.serialization import SerializationManager, TensorStub
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=1, pipeline_model_parallel_size=world)
+    # head layout of a GQA block under a TP degree that exceeds the KV heads: KV heads are replicated up to the degree
+    g = BaseGroupQueryAttention(64, 8, num_attention_heads=8, num_key_value_heads=2, tp_degree=1,
+                                desired_sharding_strategy=GQA.REPLICATE_TO_TP_DEGREE)
+    assert g.get_sharding_strategy() in tuple(GQA) and g.get_num_attention_heads() == 8 and g.get_num_key_value_heads() >= 2
+    # analytic parameter count of the flagship model == what it actually holds when nothing is sharded
+    cfg = LlamaConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, dtype=torch.float32, max_position_embeddings=16)
+    if world == 1:
+        lm = LlamaForCausalLM(cfg)
+        assert lm.num_parameters_global() == sum(p.numel() for p in lm.parameters())
+    # pipeline model: names of the layers it cuts at, children of the local partition
+    from test_pipeline_cpu import Block, Toy
+
+    torch.manual_seed(0)
+    ppm = NxDPPModel(Toy(tie=False), transformer_layer_cls=Block, num_microbatches=2, output_loss_value_spec=True,
+                     input_names=["input_ids", "labels"])
+    assert ppm.get_model_layers() == [f"layers.{i}" for i in range(4)] and len(list(ppm.local_children())) == 1
+    # LoRA: the base weights under their original names (what a plain checkpoint of the base model contains)
+    net = nn.Sequential(nn.Linear(4, 4), nn.ReLU(), nn.Linear(4, 2))
+    lora = LoraModel(net, LoraConfig(lora_rank=2, target_modules=["0"]))
+    base = lora.base_state_dict()
+    assert set(base) == {"0.weight", "0.bias", "2.weight", "2.bias"} and torch.equal(base["0.weight"], lora.module[0].base_layer.weight)
+    # Lightning module: decayed / un-decayed optimizer groups
+    ncfg = nxd.neuronx_distributed_config(pipeline_parallel_size=world) if world == 1 else None
+    if ncfg is not None:
+        mod = NeuronLTModule(ncfg, lambda: nn.Sequential(nn.Linear(4, 4), nn.LayerNorm(4)), torch.optim.AdamW)
+        mod.setup()
+        groups = mod.get_param_groups_by_weight_decay(0.1, no_decay=("bias", "1.weight"))
+        assert [g["weight_decay"] for g in groups] == [0.1, 0.0] and len(groups[0]["params"]) == 1 and len(groups[1]["params"]) == 3
+    # checkpoint plugin removes what it wrote
+    io = NeuronCheckpointIO(save_load_xser=False)
+    lin = nn.Linear(2, 2)
+    io.save_checkpoint({"state_dict": lin, "global_step": 1}, f"{tmp}/ck/step_1")
+    assert os.path.isdir(f"{tmp}/ck/step_1")
+    import torch.distributed as dist
+
+    dist.barrier()
+    if rank == 0:
+        io.remove_checkpoint(f"{tmp}/ck/step_1")
+        assert not os.path.exists(f"{tmp}/ck/step_1")
+    # converter: which tensors of a Megatron-style checkpoint are query / output projections
+    conv = CheckpointConverterBase()
+    from types import SimpleNamespace as NS
+
+    assert conv.is_q_or_o_for_megatron(NS(model_style="megatron"), "layers.0.self_attn.o_proj.weight")
+    assert not conv.is_q_or_o_for_megatron(NS(model_style="hf"), "layers.0.self_attn.o_proj.weight")
+    assert not conv.is_q_or_o_for_megatron(NS(model_style="megatron"), "layers.0.mlp.down_proj.weight")
+    # serializer: placeholders of a skeleton in tensor order; very deep objects fail with the object's class name
+    sm = SerializationManager()
+    skel, tens = sm.serialize((torch.ones(1), {"k": torch.zeros(2)}, 3))
+    stubs = sm.extract_stubs(skel)
+    assert [type(s) for s in stubs] == [TensorStub, TensorStub] and [s.index for s in stubs] == [0, 1] and len(tens) == 2
+
+    class Deep:
+        pass
+
+    with pytest.raises(RuntimeError, match="Deep"):
+        with sm.catch_and_raise_for_large_object(Deep()):
+            raise RecursionError()
+
+
+def test_remaining_public_methods_single_rank(tmp_path):
+    run_distributed(_last_batch, 1, str(tmp_path), timeout=180)
+
+
+def test_remaining_public_methods_pp2(tmp_path):
+    run_distributed(_last_batch, 2, str(tmp_path), timeout=180)
