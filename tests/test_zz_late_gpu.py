@@ -88,6 +88,45 @@ def test_fused_lmhead_ce_on_device():
     """)
 
 
+def test_llama_step_with_fused_lmhead_ce_follows_the_default_path():
+    """Model level: three optimizer steps of a small bf16 Llama with the chunked lm_head + CE switched on give the loss curve of
+    the default (materialised-logits) path within bf16 tolerance."""
+    code = """
+        import os, json, torch, torch.distributed as dist
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d", rank=0, world_size=1)
+        torch.cuda.set_device(0)
+        import neuronx_distributed_b200 as nxd
+        from neuronx_distributed_b200.models.llama import LlamaConfig, LlamaForCausalLM
+        from neuronx_distributed_b200.utils.adamw_fp32_optim_params import AdamW_FP32OptimParams
+        dev = torch.device("cuda", 0)
+        cfg = nxd.neuronx_distributed_config(tensor_parallel_size=1, optimizer_config={"zero_one_enabled": True, "grad_clipping": True,
+                                                                                    "max_grad_norm": 1.0})
+        mcfg = LlamaConfig(vocab_size=8192, hidden_size=1024, intermediate_size=2816, num_hidden_layers=2, num_attention_heads=8,
+                           num_key_value_heads=8, dtype=torch.bfloat16, device=dev, max_position_embeddings=1024)
+        torch.manual_seed(0)
+        model = nxd.initialize_parallel_model(cfg, lambda: LlamaForCausalLM(mcfg))
+        opt = nxd.initialize_parallel_optimizer(cfg, AdamW_FP32OptimParams, model.parameters(), lr=1e-3)
+        ids = torch.randint(0, 8192, (2, 1024), device=dev, generator=torch.Generator(device="cuda").manual_seed(1))
+        out = []
+        for _ in range(3):
+            opt.zero_grad(); loss = model.run_train(input_ids=ids, labels=ids); opt.step(); out.append(float(loss))
+        print("LOSSES", json.dumps(out))
+    """
+    import json
+    import re
+
+    def losses(flag, port):
+        e = dict(os.environ, PYTHONPATH=ROOT, NXD_FUSED_LMHEAD_CE=flag, NXD_LMHEAD_CE_CHUNK="512")
+        p = subprocess.run([sys.executable, "-c", textwrap.dedent(code % port)], cwd=ROOT, env=e, timeout=_PER_TEST_S,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, start_new_session=True)
+        assert p.returncode == 0, p.stdout[-3000:]
+        return json.loads(re.search(r"LOSSES (.*)", p.stdout).group(1))
+
+    a, b = losses("0", 29641), losses("1", 29642)
+    print(a, b)
+    assert all(abs(x - y) < 3e-2 * max(1.0, abs(x)) for x, y in zip(a, b)) and b[-1] < b[0], (a, b)
+
+
 def test_decode_attention_partial_shards_merge_to_full_attention():
     """``decode_attention_partial`` (per-rank piece of distributed flash-decoding) on two sequence shards of one cache, merged
     with the log-sum-exp rule, vs fp32 attention over the whole cache — including a shard with nothing visible yet."""
