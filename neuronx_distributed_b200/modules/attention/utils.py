@@ -42,10 +42,11 @@ def precompute_freqs_cis(dim: int, end: int, theta: float = 10000.0, use_scaled:
     return torch.stack([f.cos(), f.sin()], dim=-1)
 
 
-def apply_rotary_polar_compatible(xq: torch.Tensor, xk: torch.Tensor, freqs_cis: torch.Tensor
+def apply_rotary_polar_compatible(query: torch.Tensor, key: torch.Tensor, freqs_cis: torch.Tensor
                                   ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Interleaved-pair rotation (Meta checkpoint convention): x[..., 2i], x[..., 2i+1] rotate together.
     ``xq/xk``: [B, S, H, D]; ``freqs_cis``: [S, D/2, 2]."""
+    xq, xk = query, key      # reference parameter names in the signature
     def rot(x):
         xf = x.float().reshape(*x.shape[:-1], -1, 2)
         c = freqs_cis[None, : x.shape[1], None, :, 0]

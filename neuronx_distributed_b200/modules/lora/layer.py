@@ -138,7 +138,8 @@ class LoraEmbedding(LoraLayer):
     def delta_weight(self) -> torch.Tensor:
         return (self.lora_embedding_B @ self.lora_embedding_A).t() * self.scaling
 
-    def forward(self, ids: torch.Tensor):
+    def forward(self, x: torch.Tensor):
+        ids = x      # reference parameter names in the signature
         y = self.base_layer(ids)
         if self.merged:
             return y

@@ -118,7 +118,8 @@ class ExpertMLPsV2(ProcessGroupSafeDeepcopy, nn.Module):
 
     # ------------------------------------------------------------------ helpers
     @staticmethod
-    def validate_routed_experts_configs(c: RoutedExpertsMLPOpsConfig) -> None:
+    def validate_routed_experts_configs(routed_experts_mlp_config: RoutedExpertsMLPOpsConfig) -> None:
+        c = routed_experts_mlp_config      # reference parameter names in the signature
         if not (0 < c.top_k <= c.num_experts):
             raise ValueError(f"Invalid top_k={c.top_k} for num_experts={c.num_experts}")
         if c.hidden_act not in ACT2FN:

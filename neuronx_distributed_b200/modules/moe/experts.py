@@ -64,7 +64,8 @@ class Experts(nn.Module):
             return gate * torch.sigmoid(self.scale * gate) * (up + self.act_bias)
         return self.act(gate) * up
 
-    def forward(self, x: torch.Tensor, expert_indices: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, hidden_states: torch.Tensor, expert_indices: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x ``[E_local, C, H]`` → ``[E_local, C, H]`` (partial over TP unless ``reduce_output``)."""
+        x = hidden_states      # reference parameter names in the signature
         proj = self.gate_up_proj if self.glu_mlp else self.up_proj
         return self.down_proj(self.activation(proj(x, expert_indices)), expert_indices)

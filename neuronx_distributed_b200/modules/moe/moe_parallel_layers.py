@@ -205,8 +205,9 @@ class ExpertFusedColumnParallelLinear(_ExpertFusedBase):
         self._mark_expert_parallel_weights(expert_parallel_group_size=self.ep, is_prefill=is_prefill,
                                            expert_distribution=expert_distribution)
 
-    def forward(self, x: torch.Tensor, expert_indices: Optional[torch.Tensor] = None, *_: Any) -> torch.Tensor:
+    def forward(self, input_: torch.Tensor, expert_indices: Optional[torch.Tensor] = None, *_: Any) -> torch.Tensor:
         """x ``[E_local, …, H]`` → ``[E_local, …, out/tp]`` (dgrad all-reduce over TP in backward)."""
+        x = input_      # reference parameter names in the signature
         w = self.weight if expert_indices is None else self.weight[expert_indices]
         out = self.autograd_func_class.apply(x, w, None, self.async_tensor_model_parallel_allreduce, False, 0, True,
                                              self.tensor_parallel_group)
@@ -237,7 +238,8 @@ class ExpertFusedRowParallelLinear(_ExpertFusedBase):
         self._mark_expert_parallel_weights(expert_parallel_group_size=self.ep, is_prefill=is_prefill,
                                            expert_distribution=expert_distribution)
 
-    def forward(self, x: torch.Tensor, expert_indices: Optional[torch.Tensor] = None, *_: Any) -> torch.Tensor:
+    def forward(self, input_: torch.Tensor, expert_indices: Optional[torch.Tensor] = None, *_: Any) -> torch.Tensor:
+        x = input_      # reference parameter names in the signature
         w = self.weight if expert_indices is None else self.weight[expert_indices]
         out = self.autograd_func_class.apply(x, w, None, False, False, 0, True, self.tensor_parallel_group)
         if self.reduce_output:

@@ -61,7 +61,8 @@ class RouterBase(nn.Module):
         w = self.linear_router.weight
         return F.linear(x.to(w.dtype), w, self.linear_router.bias).float()
 
-    def apply_activation_fn(self, logits: torch.Tensor) -> torch.Tensor:
+    def apply_activation_fn(self, weights: torch.Tensor) -> torch.Tensor:
+        logits = weights      # reference parameter names in the signature
         if self.act_fn == "softmax":
             return torch.softmax(logits, dim=-1, dtype=torch.float32)
         if self.act_fn == "sigmoid":

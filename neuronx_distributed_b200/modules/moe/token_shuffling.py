@@ -35,7 +35,8 @@ def token_shuffle(hidden_states: torch.Tensor, seed: Optional[int] = None, dim: 
     return x, perm
 
 
-def token_unshuffle(hidden_states: torch.Tensor, permutation: torch.Tensor, dim: int = 0) -> torch.Tensor:
+def token_unshuffle(permuted_states: torch.Tensor, permutation: torch.Tensor, dim: int = 0) -> torch.Tensor:
+    hidden_states = permuted_states      # reference parameter names in the signature
     x = mappings.all_to_all_in_expert_parallel_region(hidden_states, dim, dim, ps.get_token_shuffle_group())
     inv = torch.empty_like(permutation)
     inv[permutation] = torch.arange(permutation.numel(), device=permutation.device)

@@ -52,7 +52,8 @@ class RMSNorm(nn.Module):
             self.weight.fill_(1.0)
         setattr(self.weight, "sequence_parallel_enabled", self.sequence_parallel_enabled)
 
-    def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        hidden_states = input      # reference parameter names in the signature
         return rms_norm(hidden_states, self.weight, self.variance_epsilon)
 
     def extra_repr(self) -> str:

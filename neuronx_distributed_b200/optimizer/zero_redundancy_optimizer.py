@@ -638,7 +638,8 @@ class NeuronEPZero1Optimizer(torch.optim.Optimizer):
         return {"non_ep": self.non_ep.state_dict() if self.non_ep else None,
                 "ep": self.ep.state_dict() if self.ep else None}
 
-    def load_state_dict(self, sd):
+    def load_state_dict(self, state_dict):
+        sd = state_dict      # reference parameter names in the signature
         if self.non_ep and sd.get("non_ep") is not None:
             self.non_ep.load_state_dict(sd["non_ep"])
         if self.ep and sd.get("ep") is not None:

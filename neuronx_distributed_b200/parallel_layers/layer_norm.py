@@ -22,9 +22,10 @@ class LayerNorm(nn.LayerNorm):
             if self.bias is not None:
                 _set_sequence_parallel_enabled(self.bias, sequence_parallel_enabled)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
         # compute in fp32, return in the caller's dtype (the reference forgets to assign the
         # cast result, layer_norm.py:47; the intent is implemented here)
+        x = input      # reference parameter names in the signature
         dt = x.dtype
         w = self.weight.float() if self.weight is not None else None
         b = self.bias.float() if self.bias is not None else None

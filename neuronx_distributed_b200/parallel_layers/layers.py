@@ -1020,7 +1020,8 @@ class OutputChannelParallelConv2d(BaseParallelConv):
                                f"{self.out_channels - self.partition_pad_size}")
         model_state_dict[prefix] = F.pad(w, (0, 0) * (w.dim() - 1) + (0, self.partition_pad_size))
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, in_tensor: torch.Tensor) -> torch.Tensor:
+        x = in_tensor      # reference parameter names in the signature
         tp = self.tensor_model_parallel_size
         out = _ConvWithAsyncAllReduce.apply(x, self.weight, self.bias, self.stride, self.padding, self.dilation,
                                             self.groups, tp > 1, self.tensor_parallel_group)
@@ -1051,7 +1052,8 @@ class InputChannelParallelConv2d(BaseParallelConv):
             raise RuntimeError(f"State dict {prefix} is of an unexpected size {w.shape[1]}")
         model_state_dict[prefix] = F.pad(w, (0, 0, 0, 0, 0, self.partition_pad_size))
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, in_tensor: torch.Tensor) -> torch.Tensor:
+        x = in_tensor      # reference parameter names in the signature
         if not self.input_is_parallel:
             if self.partition_pad and self.partition_pad_size > 0:
                 x = F.pad(x, (0, 0, 0, 0, 0, self.partition_pad_size))

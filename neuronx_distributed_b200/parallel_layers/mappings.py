@@ -203,9 +203,10 @@ def exit_expert_parallel_region(x: torch.Tensor, scatter_gather: bool) -> torch.
 # inference-only scatter with the rank supplied as a tensor (so one captured CUDA graph /
 # traced program serves all ranks) — reference :558-678
 # --------------------------------------------------------------------------------------
-def scatter_to_process_group_spmd(x: torch.Tensor, partition_dim: int, rank: torch.Tensor, process_group=None):
+def scatter_to_process_group_spmd(input_: torch.Tensor, partition_dim: int, rank: torch.Tensor, process_group=None):
     """Return the ``rank``-th of n contiguous slices of ``x`` along ``partition_dim`` where
     ``rank`` is a 0-d/1-elem integer *tensor* (e.g. :class:`SPMDRank`'s weight)."""
+    x = input_      # reference parameter names in the signature
     group = _tp_group(process_group)
     n = _size(group)
     if n == 1:
@@ -216,9 +217,10 @@ def scatter_to_process_group_spmd(x: torch.Tensor, partition_dim: int, rank: tor
 
 
 def round_robin_scatter_to_process_group_spmd(
-    x: torch.Tensor, partition_dim: int, rank: torch.Tensor, process_group=None
+    input_: torch.Tensor, partition_dim: int, rank: torch.Tensor, process_group=None
 ):
     """Like :func:`scatter_to_process_group_spmd` but rank r takes elements r, r+n, r+2n, …"""
+    x = input_      # reference parameter names in the signature
     group = _tp_group(process_group)
     n = _size(group)
     if n == 1:

@@ -165,7 +165,8 @@ def is_torch_version_greater_than_2() -> bool:
     return int(torch.__version__.split(".")[0]) >= 2
 
 
-def cast_tensor(t, from_dtype=torch.float32, to_dtype=torch.bfloat16):
+def cast_tensor(tensor, from_dtype=torch.float32, to_dtype=torch.bfloat16):
+    t = tensor      # reference parameter names in the signature
     return t.to(to_dtype) if isinstance(t, torch.Tensor) and t.dtype == from_dtype else t
 
 

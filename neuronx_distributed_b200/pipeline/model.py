@@ -775,18 +775,20 @@ class NxDPPModel(nn.Module):
         return iter(self._split_microbatches(batch))
 
     @staticmethod
-    def custom_backward(output: torch.Tensor, grad_output: Optional[torch.Tensor]) -> None:
+    def custom_backward(outputs: torch.Tensor, grad_outputs: Optional[torch.Tensor]) -> None:
         """Backward through ``output`` even after its storage was released by :meth:`maybe_deallocate_output_tensor` — the
         autograd engine only needs the graph, not the values (reference :890-925, after Megatron-LM)."""
+        output, grad_output = outputs, grad_outputs      # reference parameter names in the signature
         assert output.numel() == 1 or grad_output is not None or output.numel() > 0
         if grad_output is None:
             assert output.numel() == 1, "implicit grad requires scalar output."
             grad_output = torch.ones_like(output, memory_format=torch.preserve_format)
         torch.autograd.backward((output,), (grad_output,))
 
-    def maybe_deallocate_output_tensor(self, model_chunk_id: int = 0) -> None:
+    def maybe_deallocate_output_tensor(self, model_chunk: int = 0) -> None:
         """After a stage's outputs were sent downstream, free their storage (only the autograd graph is needed for the
         backward of this stage): enabled by ``deallocate_pipeline_outputs``."""
+        model_chunk_id = model_chunk      # reference parameter names in the signature
         if not self.deallocate_pipeline_outputs:
             return
         for (mb, chunk), outs in list(getattr(self, "_out", {}).items()):
@@ -824,8 +826,9 @@ class NxDPPModel(nn.Module):
     def translate_local_state_dict_to_origin_state_dict(self, local_state_dict: Dict[str, Any]) -> Dict[str, Any]:
         return {self.local_name_to_original_name.get(k, k): v for k, v in local_state_dict.items()}
 
-    def construct_state_dict_per_model_chunk(self, state_dict: Dict[str, Any], strict: bool = True) -> List[Dict[str, Any]]:
+    def construct_state_dict_per_model_chunk(self, origin_state_dict_all_model_chunks: Dict[str, Any], strict: bool = True) -> List[Dict[str, Any]]:
         """Split an original-key state dict into one dict per local model chunk (keys relative to the chunk's module)."""
+        state_dict = origin_state_dict_all_model_chunks      # reference parameter names in the signature
         per_chunk: List[Dict[str, Any]] = [dict() for _ in self.stages]
         local = self.translate_origin_state_dict_to_local_state_dict(state_dict)
         for k, v in local.items():

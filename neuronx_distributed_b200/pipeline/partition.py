@@ -118,8 +118,9 @@ def partition_traced_model(traced: fx.GraphModule, cut_after: Sequence[str], num
     return split
 
 
-def analyze_pipeline_module(split: fx.GraphModule) -> Tuple[List[StageIO], List[str]]:
+def analyze_pipeline_module(top_mod: fx.GraphModule) -> Tuple[List[StageIO], List[str]]:
     """Per-stage IO of a ``split_module`` result.  Returns (stage_ios, names of the final outputs)."""
+    split = top_mod      # reference parameter names in the signature
     placeholders: Set[str] = set()
     produced_by: Dict[str, int] = {}
     stage_nodes: List[fx.Node] = []
@@ -187,8 +188,9 @@ def analyze_pipeline_module(split: fx.GraphModule) -> Tuple[List[StageIO], List[
     return ios, final_outputs
 
 
-def analyze_shared_weights_across_stages(split: fx.GraphModule, stage_modules: List[nn.Module]) -> List[List[Tuple[int, str]]]:
+def analyze_shared_weights_across_stages(top_module: fx.GraphModule, partitions: List[nn.Module]) -> List[List[Tuple[int, str]]]:
     """Groups of (stage, local parameter name) that are the same Parameter object in several stages."""
+    split, stage_modules = top_module, partitions      # reference parameter names in the signature
     seen: Dict[int, List[Tuple[int, str]]] = {}
     for s, m in enumerate(stage_modules):
         for name, p in m.named_parameters(remove_duplicate=False):

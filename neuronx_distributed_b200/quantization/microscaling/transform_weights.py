@@ -104,8 +104,9 @@ def get_mxfp8_tensor_from_uint32(blocks: torch.Tensor, scales: torch.Tensor, *, 
     return _quad(vals.to(dtype), prefix, G, B, output_quad_row)
 
 
-def pack_fp4_x4_uint16(x: Union[torch.Tensor, np.ndarray]):
+def pack_fp4_x4_uint16(X: Union[torch.Tensor, np.ndarray]):
     """Re-view ``fp4_x2`` bytes as ``fp4_x4`` 16-bit words (last dim halves)."""
+    x = X      # reference parameter names in the signature
     if isinstance(x, torch.Tensor):
         assert x.dtype == torch.uint8, f"expected uint8, got {x.dtype}"
         return x.contiguous().view(QuantizedDtype.F4E2M1FN_X4.value)
@@ -130,9 +131,10 @@ def quantize_to_mxfp4(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return pack_byte_4bit_tensor(codes), (exp + E8M0_BIAS).clamp(0, 254).to(torch.uint8)
 
 
-def split_gate_up(w_gate_up, scale_gate_up, bias_gate_up):
+def split_gate_up(W_gate_up, scale_gate_up, bias_gate_up):
     """De-interleave fused gate/up tensors whose ``2I`` axis (dim 1) alternates gate, up rows
     (``W [E, 2I, H/32, 16]``, ``scale [E, 2I, H/32]``, ``bias [E, 2I]``)."""
+    w_gate_up = W_gate_up      # reference parameter names in the signature
     parts = (w_gate_up[:, 0::2], scale_gate_up[:, 0::2], bias_gate_up[:, 0::2],
              w_gate_up[:, 1::2], scale_gate_up[:, 1::2], bias_gate_up[:, 1::2])
     if isinstance(w_gate_up, torch.Tensor):
@@ -153,13 +155,14 @@ def _pad_tensor(x, pad_to, pad_value=0):
     raise ValueError("Invalid input type!")
 
 
-def reshape_pad_proj(w, scale, bias, pad_multiple: int = 512):
+def reshape_pad_proj(W, scale, bias, pad_multiple: int = 512):
     """Flatten ``W [E, R, C/32, 8]`` (x4-packed) to ``[E, R, C/4]`` and right-pad rows / columns up to a multiple of
     ``pad_multiple`` elements (scales padded with the E8M0 bias, i.e. 2⁰; weights / bias with zero).
 
     The reference hard-codes the gpt-oss-120b geometry (128 experts, 2880 → 3072); here the target is derived from the
     tensor so that any expert geometry can be aligned for the 128-row UMMA tiles.
     """
+    w = W      # reference parameter names in the signature
     E, R = w.shape[0], w.shape[1]
     C = w.shape[2] * w.shape[3] * 4
     up = lambda n: -(-n // pad_multiple) * pad_multiple  # noqa: E731

@@ -199,10 +199,11 @@ class CheckpointConverterBase:
         return partial_state
 
     # ---- hooks -------------------------------------------------------------------------------------------------------
-    def pre_process_full_state_before_tp_conversion(self, state: Dict[str, torch.Tensor], args) -> Dict[str, torch.Tensor]:
+    def pre_process_full_state_before_tp_conversion(self, full_state: Dict[str, torch.Tensor], args) -> Dict[str, torch.Tensor]:
         """Bring an HF-style full state into the parameter naming of the target model: gate/up → fused ``gate_up_proj``
         (``--fuse_gate_up``), q/k/v → ``qkv_proj.weight_{q,k,v}`` with KV replication and Q / o_proj head permutation
         (``--qkv_linear``).  Subclasses may override or extend."""
+        state = full_state      # reference parameter names in the signature
         out = dict(state)
         if getattr(args, "fuse_gate_up", False):
             for k in [k for k in state if k.endswith("gate_proj.weight")]:
@@ -232,8 +233,9 @@ class CheckpointConverterBase:
                 out[base + "qkv_proj.weight_q"], out[base + "qkv_proj.weight_k"], out[base + "qkv_proj.weight_v"] = q, kk, v
         return out
 
-    def post_process_full_state_after_tp_conversion(self, state: Dict[str, torch.Tensor], args) -> Dict[str, torch.Tensor]:
+    def post_process_full_state_after_tp_conversion(self, full_state: Dict[str, torch.Tensor], args) -> Dict[str, torch.Tensor]:
         """Inverse of the pre-processing for the sharded → full direction (un-permute, de-replicate, HF names)."""
+        state = full_state      # reference parameter names in the signature
         if not getattr(args, "qkv_linear", False):
             return state
         out = dict(state)

@@ -23,8 +23,9 @@ def get_dtype_from_enum(dtype_enum: int) -> torch.dtype:
     return _DTYPES[dtype_enum]
 
 
-def retrieve_artifact_from_model(nxd_model, key: str, artifact: str):
+def retrieve_artifact_from_model(model, key: str, artifact: str):
     """``artifact`` ∈ {"hlo", "metaneff", "neff"} of bucket ``key``."""
+    nxd_model = model      # reference parameter names in the signature
     return {"hlo": nxd_model.get_hlo, "metaneff": nxd_model.get_metaneff, "neff": nxd_model.get_neff}[artifact](key)
 
 

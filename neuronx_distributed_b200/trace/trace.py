@@ -183,5 +183,6 @@ def parallel_model_save(model, save_dir: str) -> None:
     model.save(save_dir, save_weights=True)
 
 
-def parallel_model_load(load_dir: str) -> Any:
+def parallel_model_load(model_dir: str) -> Any:
+    load_dir = model_dir      # reference parameter names in the signature
     return torch.load(os.path.join(load_dir, "nxd_model_meta.pt"), weights_only=False)

@@ -101,7 +101,8 @@ class FilesysCheckpointStorage(BaseCheckpointStorage):
     def file_exists(self, filename: str) -> bool:
         return os.path.isfile(self._p(filename))
 
-    def is_checkpoint_xser(self, dirname: str) -> bool:
+    def is_checkpoint_xser(self, ckpt_path: str) -> bool:
+        dirname = ckpt_path      # reference parameter names in the signature
         d = self._p(dirname)
         if not os.path.isdir(d):
             return False

@@ -91,7 +91,8 @@ class NxDOptimizer(torch.optim.Optimizer):
     def state_dict(self) -> Any:
         return self.optimizer.state_dict()
 
-    def load_state_dict(self, sd: Any) -> None:
+    def load_state_dict(self, state_dict: Any) -> None:
+        sd = state_dict      # reference parameter names in the signature
         self.optimizer.load_state_dict(sd)
 
     def step(self, closure=None):
