@@ -414,6 +414,7 @@ struct BwdParams {
   long stats_stride;
   float* dq_acc;               // [B, H, S_pad, 128] fp32
   int debug;                   // NXD_FA_DEBUG bits (perf triage only): 1 no bulk reduce, 2 no dQ staging, 4 no softmax math
+  unsigned* turnstile;         // DET only: [B, H, ceil(S_q / BQ)] contributions already added to each dQ tile
 };
 
 NXD_DEVICE void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
@@ -496,6 +497,12 @@ NXD_DEVICE void bwd_ds_math(uint32_t (&dpv)[2][32], const float (&pf)[2][32], ui
   }
 }
 
+// DET = deterministic dQ: the contributions of the K/V tiles to one dQ tile are added in K/V-tile order through a turnstile
+// counter per (batch, head, query tile) — CTA n of a (batch, KV head) column waits until n earlier tiles have landed, adds its
+// own with the same bulk reduce, waits for that reduce to COMPLETE and releases the next.  CTAs are dispatched in increasing
+// blockIdx.x, so the CTA being waited for is always resident or done.  Slower (the drain of a tile is serialised across the
+// column), bit-reproducible.  DET = false compiles to exactly the kernel without the option.
+template <bool DET>
 __global__ void __launch_bounds__(kThreadsBwd, 1)
 fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
               const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tg,
@@ -749,8 +756,32 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         fence_async_smem();
         named_bar(1, 128);
         if (tid == 0 && !(p.debug & 1)) {
+          if constexpr (DET) {
+            if (h == 0) {                           // my turn: the n earlier K/V tiles of this column have been added
+              const unsigned* turn = p.turnstile + ((long)b * p.H + head) * nq + t;
+              unsigned seen, spins = 0;
+              unsigned long long t_start = 0;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(turn) : "memory");
+                if (seen < (unsigned)n && (++spins & 0x3ffu) == 0) {
+                  unsigned long long now;
+                  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                  if (t_start == 0) t_start = now;
+                  else if (now - t_start > 10000000000ull) __trap();          // an earlier tile never arrived
+                }
+              } while (seen < (unsigned)n);
+            }
+          }
           bulk_reduce_add_f32(gdst + (long)h * 32 * HD, sdQ, 16384);
           bulk_commit();
+          if constexpr (DET) {
+            if (h == 1) {                           // both halves of the tile are in memory before the next CTA may add
+              bulk_wait0();
+              __threadfence();
+              unsigned* turn = p.turnstile + ((long)b * p.H + head) * nq + t;
+              asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(turn), "r"(1u) : "memory");
+            }
+          }
         }
       }
     }
@@ -872,6 +903,25 @@ void flash_attn_bwd(const void* go, const void* q, const void* k, const void* v,
   p.stats = stats; p.stats_stride = (long)B * H * S_pad + 64;
   p.dq_acc = dq_acc;
   { const char* e = getenv("NXD_FA_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  // NXD_FA_DETERMINISTIC=1: ordered dQ accumulation (see fa_bwd_kernel<true>); the turnstile counters live in a per-device
+  // buffer that only grows (debug mode: allocation is synchronous, not meant for graph capture)
+  bool det = false;
+  { const char* e = getenv("NXD_FA_DETERMINISTIC"); det = e && atoi(e) != 0; }
+  p.turnstile = nullptr;
+  if (det) {
+    static unsigned* turn[64] = {nullptr};
+    static size_t cap[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t need = (size_t)B * H * ((S_q + BQ - 1) / BQ) * sizeof(unsigned);
+    if (cap[dev & 63] < need) {
+      if (turn[dev & 63]) { NXD_CUDA_CHECK(cudaDeviceSynchronize()); cudaFree(turn[dev & 63]); }
+      NXD_CUDA_CHECK(cudaMalloc(&turn[dev & 63], need));
+      cap[dev & 63] = need;
+    }
+    p.turnstile = turn[dev & 63];
+    NXD_CUDA_CHECK(cudaMemsetAsync(p.turnstile, 0, need, st));
+  }
   NXD_CUDA_CHECK(cudaMemsetAsync(dq_acc, 0, (size_t)B * H * S_pad * HD * sizeof(float), st));
   {
     const long warps = (long)B * H * S_q;
@@ -883,11 +933,13 @@ void flash_attn_bwd(const void* go, const void* q, const void* k, const void* v,
   }
   static bool configured = false;
   if (!configured) {
-    NXD_CUDA_CHECK(cudaFuncSetAttribute(fa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd));
+    NXD_CUDA_CHECK(cudaFuncSetAttribute(fa_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd));
+    NXD_CUDA_CHECK(cudaFuncSetAttribute(fa_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd));
     configured = true;
   }
   dim3 grid((S_kv + BN - 1) / BN, Hkv, B);
-  fa_bwd_kernel<<<grid, kThreadsBwd, kSmemBwd, st>>>(tq, tk, tv, tg, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, p);
+  if (det) fa_bwd_kernel<true><<<grid, kThreadsBwd, kSmemBwd, st>>>(tq, tk, tv, tg, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, p);
+  else fa_bwd_kernel<false><<<grid, kThreadsBwd, kSmemBwd, st>>>(tq, tk, tv, tg, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, p);
   {
     const long n = (long)B * H * S_q * 16;
     fa_bwd_dq_out_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dq, B, S_q, H, S_pad, dqs[0],

@@ -127,6 +127,34 @@ def test_llama_step_with_fused_lmhead_ce_follows_the_default_path():
     assert all(abs(x - y) < 3e-2 * max(1.0, abs(x)) for x, y in zip(a, b)) and b[-1] < b[0], (a, b)
 
 
+def test_deterministic_attention_backward_is_bit_reproducible():
+    """``NXD_FA_DETERMINISTIC=1``: the dQ contributions of the K/V tiles are added in tile order (turnstile per query tile) — two
+    backward passes give bit-identical dQ / dK / dV, equal to the default kernel within its own run-to-run tolerance; causal and
+    not, MHA and GQA."""
+    _run("""
+        import os, torch
+        from neuronx_distributed_b200.ops import attention
+        torch.manual_seed(0)
+        for (B, S, H, Hkv, causal) in ((2, 1024, 8, 8, True), (1, 2048, 8, 2, True), (2, 512, 4, 4, False)):
+            q, k, v = (torch.randn(B, S, h, 128, device="cuda", dtype=torch.bfloat16).requires_grad_(True) for h in (H, Hkv, Hkv))
+            go = torch.randn(B, S, H, 128, device="cuda", dtype=torch.bfloat16)
+            def grads():
+                for t in (q, k, v): t.grad = None
+                attention.flash_attention(q, k, v, causal=causal).backward(go)
+                torch.cuda.synchronize()
+                return [t.grad.clone() for t in (q, k, v)]
+            os.environ["NXD_FA_DETERMINISTIC"] = "1"
+            a, b = grads(), grads()
+            assert all(torch.equal(x, y) for x, y in zip(a, b)), "deterministic mode is not reproducible"
+            os.environ["NXD_FA_DETERMINISTIC"] = "0"
+            c = grads()
+            for x, y in zip(a, c):
+                err = ((x.float() - y.float()).norm() / y.float().norm()).item()
+                assert err < 1e-2, err
+            print(B, S, H, Hkv, causal, "ok")
+    """, timeout=150)
+
+
 def test_decode_attention_partial_shards_merge_to_full_attention():
     """``decode_attention_partial`` (per-rank piece of distributed flash-decoding) on two sequence shards of one cache, merged
     with the log-sum-exp rule, vs fp32 attention over the whole cache — including a shard with nothing visible yet."""
