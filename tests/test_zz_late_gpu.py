@@ -127,6 +127,60 @@ def test_llama_step_with_fused_lmhead_ce_follows_the_default_path():
     assert all(abs(x - y) < 3e-2 * max(1.0, abs(x)) for x, y in zip(a, b)) and b[-1] < b[0], (a, b)
 
 
+def test_quantized_layers_and_moe_training_on_device():
+    """Subsystems that so far only ran on the host, now on the GPU against their own CPU results: quantised Column / Row
+    parallel layers (int8 per-channel, blockwise, fp8 with dynamic activation scaling) and a Mixtral-style MoE layer trained
+    for three steps through the grouped tcgen05 GEMMs and the device-side block-metadata build."""
+    _run("""
+        import copy, torch, torch.distributed as dist
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29651", rank=0, world_size=1)
+        torch.cuda.set_device(0)
+        from neuronx_distributed_b200.parallel_layers import ColumnParallelLinear, RowParallelLinear, parallel_state as ps
+        from neuronx_distributed_b200.quantization import ActivationQuantizationType, QuantizedDtype, convert
+        from neuronx_distributed_b200.quantization.quantization_config import (get_default_blockwise_custom_qconfig_dict,
+                                                                            get_default_per_channel_custom_qconfig_dict)
+        ps.initialize_model_parallel(1)
+        torch.manual_seed(0)
+        m = torch.nn.Sequential(ColumnParallelLinear(256, 512, bias=False, gather_output=False),
+                                RowParallelLinear(512, 256, bias=False, input_is_parallel=True)).eval()
+        x = torch.randn(64, 256)
+        for cfg in (get_default_per_channel_custom_qconfig_dict(), get_default_blockwise_custom_qconfig_dict(),
+                    {**get_default_per_channel_custom_qconfig_dict(), "quantized_dtype": QuantizedDtype.F8E4M3,
+                     "activation_quantization_type": ActivationQuantizationType.DYNAMIC}):
+            q = convert(copy.deepcopy(m), cfg)
+            want = q(x)
+            got = q.cuda()(x.cuda()).cpu()
+            err = ((got - want).norm() / want.norm()).item()
+            print(str(cfg["quantization_type"]), str(cfg.get("quantized_dtype")), "device vs host rel err", err)
+            assert err < 2e-2, err
+        # MoE layer: same initial weights and data on host (fp32) and device (bf16); loss curves agree, loss falls
+        from neuronx_distributed_b200.modules.moe import ExpertMLPsV2, MoE, RoutedExpertsMLPOpsConfig, RouterTopK
+        from neuronx_distributed_b200.ops import _ext
+        def build():
+            torch.manual_seed(1)
+            cfg = RoutedExpertsMLPOpsConfig(num_experts=8, top_k=2, hidden_size=256, intermediate_size=512, hidden_act="silu",
+                                            glu_mlp=True, normalize_top_k_affinities=True)
+            return MoE(RouterTopK(8, 2, 256), ExpertMLPsV2(cfg), return_router_logits=True)
+        data = [torch.randn(512, 1, 256, generator=torch.Generator().manual_seed(10))] * 3          # same batch: the loss must fall
+        def run(layer, dev, dtype):
+            layer = layer.to(dev).to(dtype)
+            opt = torch.optim.SGD(layer.parameters(), lr=1.0)
+            out = []
+            for xb in data:
+                xb = xb.to(dev, dtype)
+                y, logits = layer(xb)
+                loss = (y.float() - torch.tanh(xb.float())).pow(2).mean()
+                opt.zero_grad(); loss.backward(); opt.step(); out.append(float(loss))
+            return out
+        host = run(build(), "cpu", torch.float32)
+        _ext.reset_launches()
+        dev = run(build(), "cuda", torch.bfloat16)
+        print("host", host, "device", dev, "own-kernel launches", _ext.launches())
+        assert _ext.launches() > 0, "the MoE layer did not reach the extension kernels"
+        assert all(abs(a - b) < 0.05 * max(1.0, abs(a)) for a, b in zip(host, dev)) and dev[-1] < dev[0]
+    """, timeout=150)
+
+
 def test_deterministic_attention_backward_is_bit_reproducible():
     """``NXD_FA_DETERMINISTIC=1``: the dQ contributions of the K/V tiles are added in tile order (turnstile per query tile) — two
     backward passes give bit-identical dQ / dK / dV, equal to the default kernel within its own run-to-run tolerance; causal and
