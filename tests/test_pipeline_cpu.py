@@ -391,3 +391,80 @@ def _pyobj(rank, world):
 
 def test_python_object_exchange_between_stages():
     run_distributed(_pyobj, 2, timeout=120)
+
+
+def _manual_tp_pp(rank, world):
+    """Manual partition with tensor-parallel layers inside the stages (TP=2 x PP=2): loss and the shared embedding / head
+    gradient equal the unpartitioned, unsharded model."""
+    from neuronx_distributed_b200.parallel_layers import ColumnParallelLinear, ParallelEmbedding, RowParallelLinear
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+    from neuronx_distributed_b200.pipeline import NxDPPModel
+    from neuronx_distributed_b200.pipeline.manual_pipe_stage import PipelineStageModule
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=2, pipeline_model_parallel_size=2)
+    tp_rank = ps.get_tensor_model_parallel_rank()
+    V, H = 32, 16
+
+    class TPEmb(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = ParallelEmbedding(V, H)
+
+        def forward(self, input_ids):
+            return self.emb(input_ids)
+
+    class TPBlock(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.up = ColumnParallelLinear(H, 2 * H, bias=False, gather_output=False, keep_master_weight=True)
+            self.down = RowParallelLinear(2 * H, H, bias=False, input_is_parallel=True, keep_master_weight=True)
+
+        def forward(self, x):
+            return x + self.down(torch.tanh(self.up(x)))
+
+    class TPHead(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.proj = ColumnParallelLinear(H, V, bias=False, gather_output=True, keep_master_weight=True)
+
+        def forward(self, x):
+            return self.proj(x)
+
+    torch.manual_seed(0)
+    layers = [TPEmb(), TPBlock(), TPBlock(), TPHead()]
+
+    def loss_fn(logits, labels):
+        return torch.nn.functional.cross_entropy(logits.view(-1, V), labels.view(-1))
+
+    ids = torch.randint(0, V, (8, 6), generator=torch.Generator().manual_seed(1))
+    # dense reference from the master weights
+    full_emb = torch.randn(V, H, generator=torch.Generator().manual_seed(5)) * 0.5          # same full table on every rank
+    with torch.no_grad():
+        layers[0].emb.weight.copy_(full_emb.chunk(2, 0)[tp_rank])
+    emb_w, head_w = full_emb.clone().requires_grad_(True), layers[3].proj.master_weight.clone().requires_grad_(True)
+    blocks = [(l.up.master_weight.clone().requires_grad_(True), l.down.master_weight.clone().requires_grad_(True)) for l in layers[1:3]]
+    x = emb_w[ids]
+    for up, down in blocks:
+        x = x + torch.tanh(x @ up.t()) @ down.t()
+    ref_loss = loss_fn(x @ head_w.t(), ids)
+    ref_loss.backward()
+    stage = PipelineStageModule(layers, layer_names=["emb", "b0", "b1", "head"])
+    ppm = NxDPPModel(stage, manual_pp_partition=True, manual_pp_loss_fn=loss_fn, num_microbatches=4, input_names=["input_ids"],
+                     broadcast_and_average_loss=True)
+    loss = ppm.run_train(input_ids=ids, labels=ids)
+    torch.testing.assert_close(loss.float(), ref_loss.detach().float(), rtol=1e-4, atol=1e-5)
+    checked = 0
+    for name, p in ppm.local_named_parameters():
+        if name.endswith("1.up.weight"):
+            torch.testing.assert_close(p.grad, blocks[0][0].grad.chunk(2, 0)[tp_rank], rtol=1e-3, atol=1e-5); checked += 1
+        if name.endswith("2.down.weight"):
+            torch.testing.assert_close(p.grad, blocks[1][1].grad.chunk(2, 1)[tp_rank], rtol=1e-3, atol=1e-5); checked += 1
+        if name.endswith("3.proj.weight"):
+            torch.testing.assert_close(p.grad, head_w.grad.chunk(2, 0)[tp_rank], rtol=1e-3, atol=1e-5); checked += 1
+        if name.endswith("0.emb.weight"):
+            torch.testing.assert_close(p.grad, emb_w.grad.chunk(2, 0)[tp_rank], rtol=1e-3, atol=1e-5); checked += 1
+    assert checked == 2, checked                                       # two of the four layers live on every pipeline rank
+
+
+def test_manual_partition_with_tensor_parallel_stages_tp2_pp2():
+    run_distributed(_manual_tp_pp, 4, timeout=240)
