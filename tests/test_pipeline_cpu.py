@@ -387,6 +387,27 @@ def _pyobj(rank, world):
     else:
         assert comm.recv_python_object(0) == "by rank"
     assert comm.MAX_RETRY == 3 and comm.MAX_LENGTH == 2 ** 20
+    # blocking tensor helpers of the reference: the receiver allocates from the metadata it was sent first
+    t = torch.arange(6, dtype=torch.float32).view(2, 3) + rank
+    if rank == 0:
+        comm.send_python_object(comm.TensorMeta(0, t.dtype, t.shape, True), True)
+        assert comm.send(t, send_next=True) is t
+        back = comm.recv_from(comm.TensorMeta(0, torch.float32, torch.Size([2, 3]), False), recv_prev=False)
+        assert torch.equal(back, t * 2) and not back.requires_grad
+    else:
+        meta = comm.recv_python_object(True)
+        got = comm.recv_from(meta, recv_prev=True, tracing=False)
+        assert torch.equal(got, torch.arange(6, dtype=torch.float32).view(2, 3)) and got.requires_grad
+        comm.send(got.detach() * 2, send_next=False)
+    # one batched group of isend / irecv per schedule step
+    b = comm.P2PBatch(ps.get_pipeline_model_parallel_group())
+    peer = 1 - rank
+    b.send(torch.full((4,), float(rank)), peer)
+    buf = b.recv(comm.TensorMeta(0, torch.float32, torch.Size([4]), False), peer)
+    recv_works, send_works = b.launch()
+    for w in recv_works + send_works:
+        w.wait()
+    assert buf.tolist() == [float(peer)] * 4 and b.launch() == ([], [])
 
 
 def test_python_object_exchange_between_stages():
