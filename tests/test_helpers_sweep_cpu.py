@@ -524,3 +524,65 @@ def test_remaining_public_methods_single_rank(tmp_path):
 
 def test_remaining_public_methods_pp2(tmp_path):
     run_distributed(_last_batch, 2, str(tmp_path), timeout=180)
+
+
+def test_hooks_callback_progress_bar_and_ring_alias(tmp_path):
+    from types import SimpleNamespace as NS
+
+    from neuronx_distributed_b200.kernels import nki_ring_attn_func
+    from neuronx_distributed_b200.lightning import NeuronHooksCallback
+    from neuronx_distributed_b200.lightning.progress_bar import NeuronTQDMProgressBar
+
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(4, 8), nn.Tanh(), nn.Linear(8, 2))
+    pl = NS(model=model, global_step=0)
+    x = torch.randn(3, 4)
+    # keyword style: dump outputs / output gradients of the matching leaf modules at the listed steps
+    cb = NeuronHooksCallback(str(tmp_path / "dump"), steps=[0], module_filter="2", dump_grads=True)
+    cb.on_train_start(None, pl)
+    model(x).sum().backward()
+    cb.on_train_batch_end(None, pl)
+    model(x).sum().backward()                                           # step 1: not listed, nothing written
+    cb.detach()
+    files = sorted(os.listdir(tmp_path / "dump"))
+    assert files == ["step0_2_bwd.pt", "step0_2_fwd.pt"], files
+    assert torch.equal(torch.load(tmp_path / "dump" / "step0_2_fwd.pt"), model(x).detach())
+    # the reference's config object: (input, output) of the target layers every `hooks_interval` steps, norms only
+    cfg = NS(hooks=True, hooks_dump_base_directory=str(tmp_path / "ref"), target_layers="0, 2", hooks_interval=1,
+             enable_activation_dumps=True, enable_grad_dumps=True, dump_only_norms=True, dump_only_master_rank=True,
+             master_print_model_layers=False)
+    cb2 = NeuronHooksCallback(cfg)
+    cb2.on_train_start(None, pl)
+    model(x).sum().backward()
+    assert set(cb2.activations_map) == {"0", "2"} and set(cb2.gradients_map) == {"0", "2"}
+    cb2.on_train_batch_end(None, pl)
+    cb2.detach()
+    d = tmp_path / "ref" / "0" / "global_step_0"
+    names = sorted(os.listdir(d))
+    assert [n.split("_rank")[0] for n in names] == ["grad_output", "input", "output"] or len(names) >= 3, names
+    got = torch.load(d / [n for n in names if n.startswith("input")][0])
+    assert got.dim() == 0 and torch.allclose(got, x.norm())             # dump_only_norms
+    assert not cb2.activations_map and not cb2.gradients_map            # flushed
+    # progress bar: created at train start on the printing rank, advances per batch
+    bar = NeuronTQDMProgressBar()
+    bar.setup()
+    bar.on_train_start(None, pl)
+    bar.on_train_batch_end(None, pl)
+    assert bar._bar is None or bar._bar.n == 1
+    if bar._bar is not None:
+        bar._bar.close()
+    # ring-attention entry point under the reference's kernel name: [B, H, S_local, D] in and out (one rank = plain causal attention)
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29673")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    from neuronx_distributed_b200.parallel_layers import parallel_state as ps
+
+    if not ps.model_parallel_is_initialized():
+        ps.initialize_model_parallel(tensor_model_parallel_size=1)
+    q, k, v = (torch.randn(1, 2, 8, 4) for _ in range(3))
+    out = nki_ring_attn_func(q, k, v, causal=True)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    ps.destroy_model_parallel(); dist.destroy_process_group()
