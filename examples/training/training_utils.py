@@ -100,13 +100,16 @@ def memmap_batches(path: str, batch: int, seq: int, dp_rank: int, dp_size: int, 
         yield {"input_ids": ids, "labels": ids}
 
 
-def linear_warmup_cosine(optimizer, warmup: int, total: int, min_ratio: float = 0.1):
+def linear_warmup_cosine(optimizer, warmup: int, total: int, min_ratio: float = 0.1, constant: int = 0):
+    """Linear warm-up, `constant` steps at the peak, cosine decay to `min_ratio` x peak at `total`."""
     import math
 
     def f(step):
         if step < warmup:
             return (step + 1) / max(1, warmup)
-        p = min(1.0, (step - warmup) / max(1, total - warmup))
+        if step < warmup + constant:
+            return 1.0
+        p = min(1.0, (step - warmup - constant) / max(1, total - warmup - constant))
         return min_ratio + (1 - min_ratio) * 0.5 * (1 + math.cos(math.pi * p))
 
     return torch.optim.lr_scheduler.LambdaLR(optimizer, f)

@@ -393,6 +393,7 @@ class NxDPPModel(nn.Module):
             self._flush(batch)
         self._wait_all()
         self._drain_sends()
+        self.timeline.mark_step_end()               # one trace dump per run_train / run_eval call (no-op without trace_file_path)
         return self._process_loss()
 
     # ------------------------------------------------------------------ task dispatch

@@ -60,3 +60,34 @@ def test_tokenise_corpus_then_pretrain_from_it(tmp_path):
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     assert train.returncode == 0, train.stdout[-3000:]
     assert "step 2 loss" in train.stdout
+
+
+def test_tp_pp_pretrain_script_with_reference_flags_checkpoints_and_resumes(tmp_path):
+    """``tp_pp_llama_pretrain.py`` (same driver as the TP + ZeRO-1 script) on 4 ranks = TP 2 x PP 2 with the reference script's flag
+    names: trains from a token directory, checkpoints, stops after ``--steps_this_run``, resumes and finishes."""
+    import json
+
+    import numpy as np
+
+    data_dir = tmp_path / "data"
+    data_dir.mkdir()
+    np.random.default_rng(0).integers(0, 4096, 64 * 400, dtype=np.uint16).tofile(data_dir / "tokens.bin")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    base = [sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
+            "--master-port", "29733", os.path.join(ROOT, "examples", "training", "llama", "tp_pp_llama_pretrain.py"),
+            "--training_dir", str(data_dir), "--seq_len", "64", "--num_microbatches", "2", "--max_steps", "4",
+            "--sequence_parallel_enabled", "--use_zero1_optimizer", "1", "--use_selective_checkpoint", "0", "--kv_replicator", "1",
+            "--constant_steps", "1", "--min_lr", "1e-5", "--print_grad_norm", "--use_flash_attention", "1",
+            "--checkpoint_freq", "2", "--checkpoint_dir", str(tmp_path / "ckpt"), "--save_load_xser", "0",
+            "--tb_dir", str(tmp_path / "tb"), "--output_dir", str(tmp_path / "out"), "--trace_file_path", str(tmp_path / "trace.json")]
+    first = subprocess.run(base + ["--steps_this_run", "2"], env=env, text=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           timeout=900)
+    assert first.returncode == 0, first.stdout[-3000:]
+    assert "step 2 loss" in first.stdout and "step 3 loss" not in first.stdout
+    assert os.path.isdir(tmp_path / "ckpt" / "step_2")
+    second = subprocess.run(base, env=env, text=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    assert second.returncode == 0, second.stdout[-3000:]
+    assert "step 3 loss" in second.stdout and "step 4 loss" in second.stdout and "step 1 loss" not in second.stdout      # resumed
+    res = json.load(open(tmp_path / "out" / "results.json"))
+    assert res["steps"] == 4 if "steps" in res else True
+    assert os.path.exists(str(tmp_path / "trace.json") + ".pp0.json") and os.listdir(tmp_path / "tb")     # one trace per pipeline rank
