@@ -19,7 +19,7 @@ import neuronx_distributed_b200 as nxd  # noqa: E402
 from neuronx_distributed_b200.models.bert import BertConfig, BertForPreTraining  # noqa: E402
 from neuronx_distributed_b200.parallel_layers import parallel_state as ps  # noqa: E402
 from neuronx_distributed_b200.utils.adamw_fp32_optim_params import AdamW_FP32OptimParams  # noqa: E402
-from training_utils import Throughput, init_distributed  # noqa: E402
+from training_utils import Throughput, add_checkpoint_args, init_distributed, maybe_resume, maybe_save  # noqa: E402
 
 
 def main():
@@ -30,6 +30,11 @@ def main():
     p.add_argument("--seq_len", type=int, default=128)
     p.add_argument("--max_steps", type=int, default=10)
     p.add_argument("--mask_prob", type=float, default=0.15)
+    p.add_argument("--max_pred_len", type=int, default=0, help="at most this many masked positions per sequence (0 = no limit)")
+    p.add_argument("--optimizer", default="AdamW", choices=["AdamW", "LAMB"],
+                   help="LAMB is accepted and runs AdamW (layer-wise trust ratios are not implemented)")
+    p.add_argument("--lr", type=float, default=1e-4)
+    add_checkpoint_args(p)
     a = p.parse_args()
     dev = init_distributed()
     cfg = nxd.neuronx_distributed_config(tensor_parallel_size=a.tensor_parallel_size,
@@ -45,12 +50,19 @@ def main():
         return BertForPreTraining(mcfg)
 
     model = nxd.initialize_parallel_model(cfg, model_fn)
-    opt = nxd.initialize_parallel_optimizer(cfg, AdamW_FP32OptimParams, model.parameters(), lr=1e-4, weight_decay=0.01)
+    opt = nxd.initialize_parallel_optimizer(cfg, AdamW_FP32OptimParams, model.parameters(), lr=a.lr, weight_decay=0.01)
+    start = maybe_resume(a, nxd, model, opt)
     gen = torch.Generator().manual_seed(17 + ps.get_data_parallel_rank())
     thr = Throughput(a.batch_size, ps.get_data_parallel_size(), 1)
-    for step in range(a.max_steps):
+    for step in range(start, a.max_steps):
+        if a.steps_this_run >= 0 and step - start >= a.steps_this_run:
+            break
         ids = torch.randint(4, mcfg.vocab_size, (a.batch_size, a.seq_len), generator=gen)
         masked = torch.rand(ids.shape, generator=gen) < a.mask_prob
+        if a.max_pred_len > 0:                                                       # keep the first max_pred_len masked positions
+            masked = masked & (masked.cumsum(-1) <= a.max_pred_len)
+        if a.debug and step == start and dist.get_rank() == 0:
+            print("batch", tuple(ids.shape), "masked per row", masked.sum(-1).tolist()[:4], flush=True)
         labels = torch.where(masked, ids, torch.full_like(ids, -100))
         ids = torch.where(masked, torch.full_like(ids, 3), ids)                      # [MASK] id 3
         batch = dict(input_ids=ids.to(dev), labels=labels.to(dev), attention_mask=torch.ones_like(ids).to(dev),
@@ -62,6 +74,8 @@ def main():
         tp = thr.get_throughput()
         if dist.get_rank() == 0:
             print(f"step {step + 1} loss {float(loss):.4f} throughput {tp:.2f} seq/s", flush=True)
+        maybe_save(a, nxd, model, opt, step + 1)
+    nxd.finalize_checkpoint()
     dist.barrier()
     dist.destroy_process_group()
 

@@ -20,7 +20,8 @@ import neuronx_distributed_b200 as nxd  # noqa: E402
 from neuronx_distributed_b200.models.gpt_neox import GPTNeoXConfig, GPTNeoXForCausalLM, GPTNeoXLayer  # noqa: E402
 from neuronx_distributed_b200.parallel_layers import parallel_state as ps  # noqa: E402
 from neuronx_distributed_b200.utils.adamw_fp32_optim_params import AdamW_FP32OptimParams  # noqa: E402
-from training_utils import Throughput, init_distributed, synthetic_batches  # noqa: E402
+from training_utils import (Throughput, add_checkpoint_args, init_distributed, maybe_resume, maybe_save,  # noqa: E402
+                            synthetic_batches)
 
 
 def main():
@@ -32,6 +33,8 @@ def main():
     p.add_argument("--seq_len", type=int, default=2048)
     p.add_argument("--max_steps", type=int, default=10)
     p.add_argument("--num_layers", type=int, default=-1)
+    p.add_argument("--lr", type=float, default=1e-4)
+    add_checkpoint_args(p)
     a = p.parse_args()
     dev = init_distributed()
     sp = a.tensor_parallel_size > 1
@@ -54,16 +57,21 @@ def main():
         return GPTNeoXForCausalLM(mcfg)
 
     model = nxd.initialize_parallel_model(cfg, model_fn)
-    opt = nxd.initialize_parallel_optimizer(cfg, AdamW_FP32OptimParams, model.parameters(), lr=1e-4)
+    opt = nxd.initialize_parallel_optimizer(cfg, AdamW_FP32OptimParams, model.parameters(), lr=a.lr)
+    start = maybe_resume(a, nxd, model, opt)
     data = synthetic_batches(mcfg.vocab_size, a.num_microbatches, a.seq_len, 1 + ps.get_data_parallel_rank(), dev)
     thr = Throughput(a.num_microbatches, ps.get_data_parallel_size(), 1)
-    for step in range(a.max_steps):
+    for step in range(start, a.max_steps):
+        if a.steps_this_run >= 0 and step - start >= a.steps_this_run:
+            break
         opt.zero_grad()
         loss = model.run_train(**next(data))
         opt.step()
         tp = thr.get_throughput()
         if dist.get_rank() == 0:
             print(f"step {step + 1} loss {float(loss):.4f} throughput {tp:.2f} seq/s ({tp * a.seq_len:.0f} tok/s)", flush=True)
+        maybe_save(a, nxd, model, opt, step + 1)
+    nxd.finalize_checkpoint()
     dist.barrier()
     dist.destroy_process_group()
 

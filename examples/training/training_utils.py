@@ -113,3 +113,55 @@ def linear_warmup_cosine(optimizer, warmup: int, total: int, min_ratio: float = 
         return min_ratio + (1 - min_ratio) * 0.5 * (1 + math.cos(math.pi * p))
 
     return torch.optim.lr_scheduler.LambdaLR(optimizer, f)
+
+
+# ---- checkpoint / resume flags shared by the smaller example scripts (BERT, GPT-NeoX, MoE) ---------------------------------
+def add_checkpoint_args(p) -> None:
+    """Flags of the reference's BERT / GPT-NeoX scripts (``--resume_ckpt``, ``--resume_step``, ``--resume_ckpt_path``,
+    ``--minimal_ckpt``, ``--shards_per_ckpt``, ``--test_checkpointing``) over ``nxd.save_checkpoint`` tags ``step_<n>``."""
+    p.add_argument("--output_dir", default="./output")
+    p.add_argument("--checkpoint_freq", "--shards_per_ckpt", dest="checkpoint_freq", type=int, default=0,
+                   help="save every N steps (the reference counts data shards; a step is the unit here); 0 = never")
+    p.add_argument("--resume_ckpt", action="store_true", help="resume from --resume_step, or from the newest complete checkpoint")
+    p.add_argument("--resume_step", type=int, default=-1)
+    p.add_argument("--resume_ckpt_path", default=None, help="checkpoint directory to resume from instead of <output_dir>/checkpoints")
+    p.add_argument("--minimal_ckpt", action="store_true", help="model weights only (no optimizer / scheduler state)")
+    p.add_argument("--test_checkpointing", action="store_true",
+                   help="after the first save, load it back into the live model and check that nothing changed")
+    p.add_argument("--steps_this_run", type=int, default=-1)
+    p.add_argument("--debug", action="store_true", help="print the batch shapes and the checkpoint actions")
+    p.add_argument("--enable_pt_autocast", action="store_true", help="accepted: bf16 parameters, fp32 statistics is the only mode")
+
+
+def maybe_resume(a, nxd, model, opt, sched=None) -> int:
+    """Returns the step to continue from (0 without ``--resume_ckpt`` or without a checkpoint)."""
+    d = a.resume_ckpt_path or os.path.join(a.output_dir, "checkpoints")
+    if not a.resume_ckpt or not nxd.has_checkpoint(d):
+        return 0
+    tag = f"step_{a.resume_step}" if a.resume_step >= 0 else None
+    uc = nxd.load_checkpoint(d, tag=tag, model=model, optimizer=None if a.minimal_ckpt else opt,
+                             scheduler=None if a.minimal_ckpt else sched)
+    step = int((uc or {}).get("total_steps", max(a.resume_step, 0)))
+    if a.debug and dist.get_rank() == 0:
+        print(f"resumed from {d} ({tag or 'newest'}) at step {step}", flush=True)
+    return step
+
+
+def maybe_save(a, nxd, model, opt, step: int, sched=None) -> None:
+    if a.checkpoint_freq <= 0 or step % a.checkpoint_freq:
+        return
+    d = os.path.join(a.output_dir, "checkpoints")
+    nxd.save_checkpoint(d, f"step_{step}", model=model, optimizer=None if a.minimal_ckpt else opt,
+                        scheduler=None if a.minimal_ckpt else sched, user_content={"total_steps": step}, use_xser=False,
+                        num_kept_ckpts=2)
+    if a.debug and dist.get_rank() == 0:
+        print(f"saved {d}/step_{step}", flush=True)
+    if a.test_checkpointing and not getattr(a, "_ckpt_tested", False):
+        a._ckpt_tested = True
+        before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        nxd.load_checkpoint(d, tag=f"step_{step}", model=model, optimizer=None if a.minimal_ckpt else opt)
+        for k, v in model.state_dict().items():
+            assert torch.equal(v, before[k]), f"checkpoint round trip changed {k}"
+        if dist.get_rank() == 0:
+            print("checkpoint round trip ok", flush=True)
+

@@ -91,3 +91,29 @@ def test_tp_pp_pretrain_script_with_reference_flags_checkpoints_and_resumes(tmp_
     res = json.load(open(tmp_path / "out" / "results.json"))
     assert res["steps"] == 4 if "steps" in res else True
     assert os.path.exists(str(tmp_path / "trace.json") + ".pp0.json") and os.listdir(tmp_path / "tb")     # one trace per pipeline rank
+
+
+def test_bert_and_gpt_neox_scripts_checkpoint_and_resume(tmp_path):
+    """The smaller pre-training scripts take the reference's checkpoint flags: save every N steps, verify the round trip, stop,
+    resume from the newest checkpoint (BERT, TP=2) or from a named step with weights only (GPT-NeoX, TP 2 x PP 2)."""
+    env = dict(os.environ, PYTHONPATH=ROOT)
+
+    def run(script, nproc, port, *flags):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+                            "--master-port", str(port), os.path.join(ROOT, "examples", "training", script), *flags], env=env, text=True,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:]
+        return r.stdout
+
+    bert = ["--model", "tiny", "--tensor_parallel_size", "2", "--batch_size", "4", "--seq_len", "32", "--max_steps", "4",
+            "--max_pred_len", "3", "--optimizer", "LAMB", "--output_dir", str(tmp_path / "bert"), "--shards_per_ckpt", "2", "--debug"]
+    out = run("bert/tp_dp_bert_pretrain.py", 2, 29741, *bert, "--steps_this_run", "2", "--test_checkpointing")
+    assert "step 2 loss" in out and "step 3 loss" not in out and "checkpoint round trip ok" in out and "masked per row" in out
+    out = run("bert/tp_dp_bert_pretrain.py", 2, 29742, *bert, "--resume_ckpt")
+    assert "resumed from" in out and "at step 2" in out and "step 3 loss" in out and "step 1 loss" not in out
+    neox = ["--model", "tiny", "--tensor_parallel_size", "2", "--pipeline_parallel_size", "2", "--num_microbatches", "2", "--seq_len", "32",
+            "--max_steps", "3", "--output_dir", str(tmp_path / "neox"), "--checkpoint_freq", "1", "--minimal_ckpt", "--debug"]
+    out = run("gpt_neox/tp_pp_gpt_neox_pretrain.py", 4, 29743, *neox, "--steps_this_run", "2")
+    assert "step 2 loss" in out and os.path.isdir(tmp_path / "neox" / "checkpoints" / "step_2")
+    out = run("gpt_neox/tp_pp_gpt_neox_pretrain.py", 4, 29744, *neox, "--resume_ckpt", "--resume_step", "1")
+    assert "at step 1" in out and "step 2 loss" in out and "step 3 loss" in out
