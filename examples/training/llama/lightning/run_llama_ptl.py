@@ -25,8 +25,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "examples", "training"))
 
 import neuronx_distributed_b200 as nxd  # noqa: E402
-from neuronx_distributed_b200.lightning import (NeuronCheckpointIO, NeuronLTModule, NeuronTensorBoardLogger,  # noqa: E402
-                                                NeuronTQDMProgressBar, NxDStrategy)
+from neuronx_distributed_b200.lightning import (NeuronCheckpointIO, NeuronHooksCallback, NeuronLTModule,  # noqa: E402
+                                                NeuronTensorBoardLogger, NeuronTQDMProgressBar, NxDStrategy)
 from neuronx_distributed_b200.lightning._compat import HAVE_LIGHTNING  # noqa: E402
 from neuronx_distributed_b200.models.llama import (LlamaConfig, LlamaForCausalLM, llama2_7b_config, llama2_13b_config,  # noqa: E402
                                                   llama2_70b_config)
@@ -83,7 +83,28 @@ def main():
     p.add_argument("--checkpoint_freq", type=int, default=0)
     p.add_argument("--resume_from", default=None)
     p.add_argument("--log_dir", default="/tmp/nxd_ptl_logs")
+    # flags of the reference script (run_llama_nxd_ptl.py): checkpoint switches and the activation / gradient dump hooks
+    p.add_argument("--save_checkpoint", action="store_true", help="same as --checkpoint_freq > 0 (every --checkpoint_freq or 1 steps)")
+    p.add_argument("--load_step", type=int, default=-1, help="resume from <checkpoint_dir>/step_<n> (-1: --resume_from decides)")
+    p.add_argument("--load_epoch", type=int, default=-1, help="accepted: checkpoints are tagged by optimizer step")
+    p.add_argument("--log_rank0", action="store_true", help="log from global rank 0 instead of the last pipeline stage")
+    p.add_argument("--hooks", action="store_true", help="record (input, output) of --target_layers during training")
+    p.add_argument("--target_layers", default="", help="comma-separated module names (see --master_print_model_layers)")
+    p.add_argument("--hooks_interval", type=int, default=1)
+    p.add_argument("--hooks_dump_base_directory", default="./hooks_outputs/local/hooks_dumps")
+    p.add_argument("--enable_activation_dumps", action="store_true")
+    p.add_argument("--enable_grad_dumps", action="store_true")
+    p.add_argument("--dump_only_norms", action="store_true")
+    p.add_argument("--dump_only_master_rank", action="store_true")
+    p.add_argument("--master_print_model_layers", action="store_true")
+    p.add_argument("--enable_tb_logging_master_rank_activation_norms", action="store_true",
+                   help="accepted: dumped norms are files under --hooks_dump_base_directory")
+    p.add_argument("--enable_tb_logging_master_rank_grad_norms", action="store_true", help="accepted, as above")
     a = p.parse_args()
+    if a.save_checkpoint and a.checkpoint_freq <= 0:
+        a.checkpoint_freq = 1
+    if a.load_step >= 0 and a.checkpoint_dir and not a.resume_from:
+        a.resume_from = os.path.join(a.checkpoint_dir, f"step_{a.load_step}")
 
     def warmup_cosine(step):
         if step < a.warmup_steps:
@@ -110,10 +131,13 @@ def main():
     module = NeuronLTModule(nxd_config, model_fn, torch.optim.AdamW, scheduler_cls=torch.optim.lr_scheduler.LambdaLR,
                             opt_kwargs={"lr": a.lr, "betas": (0.9, 0.95), "weight_decay": 0.1},
                             scheduler_args=(warmup_cosine,),
-                            grad_accum_steps=a.grad_accum_usteps, train_batch_size=a.micro_batch)
+                            grad_accum_steps=a.grad_accum_usteps, train_batch_size=a.micro_batch, log_rank0=a.log_rank0)
     dm = LlamaDataModule(VOCAB_TINY if a.model == "tiny" else 32000, a.seq_len, a.micro_batch)
     strategy = NxDStrategy(nxd_config=nxd_config)
-    kwargs = dict(strategy=strategy, callbacks=[NeuronTQDMProgressBar()], logger=NeuronTensorBoardLogger(a.log_dir, "llama_ptl"),
+    callbacks = [NeuronTQDMProgressBar()]
+    if a.hooks:
+        callbacks.append(NeuronHooksCallback(a))                        # the argument namespace carries the hook settings
+    kwargs = dict(strategy=strategy, callbacks=callbacks, logger=NeuronTensorBoardLogger(a.log_dir, "llama_ptl", log_rank0=a.log_rank0),
                   max_steps=a.max_steps, log_every_n_steps=1, plugins=[NeuronCheckpointIO(async_save=False, num_kept_ckpts=2)])
     if HAVE_LIGHTNING:                                                   # pragma: no cover - not in the offline image
         import lightning.pytorch as pl

@@ -120,11 +120,14 @@ class NeuronHooksCallback(Callback):
         if self.master_print_model_layers and (not torch.distributed.is_initialized() or torch.distributed.get_rank() == 0):
             print("Printing Model Layers:\n" + "\n".join(n for n, _ in model.named_modules()))
         for name, layer in model.named_modules():
-            if name.strip() in self.target_layers:
+            # a target names a module of the USER's model; the trainer's wrappers (``module.`` / pipeline stage prefixes) may sit
+            # in front of it, so a dotted-suffix match counts and the dump directory carries the name the user gave
+            target = next((t for t in self.target_layers if name.strip() == t or name.endswith("." + t)), None)
+            if target is not None:
                 if self.enable_activation_dumps:
-                    self.register_forward_hook_wrapper(name, layer, pl_module)
+                    self.register_forward_hook_wrapper(target, layer, pl_module)
                 if self.enable_grad_dumps:
-                    self.register_backward_hook_wrapper(name, layer, pl_module)
+                    self.register_backward_hook_wrapper(target, layer, pl_module)
 
     def on_train_batch_end(self, trainer=None, pl_module=None, *a, **k) -> None:
         self._step += 1

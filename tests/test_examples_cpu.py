@@ -117,3 +117,29 @@ def test_bert_and_gpt_neox_scripts_checkpoint_and_resume(tmp_path):
     assert "step 2 loss" in out and os.path.isdir(tmp_path / "neox" / "checkpoints" / "step_2")
     out = run("gpt_neox/tp_pp_gpt_neox_pretrain.py", 4, 29744, *neox, "--resume_ckpt", "--resume_step", "1")
     assert "at step 1" in out and "step 2 loss" in out and "step 3 loss" in out
+
+
+def test_lightning_example_with_hook_dumps_and_checkpoint_flags(tmp_path):
+    """``run_llama_ptl.py`` with the reference script's switches: activation / gradient dumps of a target layer, checkpoint
+    every step, resume from a named step."""
+    env = dict(os.environ, PYTHONPATH=ROOT, NXD_CPU_MODE="1")
+    script = os.path.join(ROOT, "examples", "training", "llama", "lightning", "run_llama_ptl.py")
+    common = ["--tensor_parallel_size", "2", "--model", "tiny", "--seq_len", "32", "--micro_batch", "2", "--grad_accum_usteps", "1",
+              "--checkpoint_dir", str(tmp_path / "ck"), "--log_dir", str(tmp_path / "logs"), "--log_rank0"]
+
+    def run(port, *flags):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                            "--master-port", str(port), script, *common, *flags], env=env, text=True, stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:]
+        return r.stdout
+
+    out = run(29751, "--max_steps", "2", "--save_checkpoint", "--hooks", "--target_layers", "model.layers.0.mlp.down_proj",
+              "--enable_activation_dumps", "--enable_grad_dumps", "--dump_only_norms", "--dump_only_master_rank",
+              "--hooks_dump_base_directory", str(tmp_path / "hooks"), "--master_print_model_layers")
+    assert "finished 2 optimizer steps" in out and "Printing Model Layers" in out
+    assert os.path.isdir(tmp_path / "ck" / "step_2")
+    layer_dir = tmp_path / "hooks" / "model.layers.0.mlp.down_proj"
+    assert os.path.isdir(layer_dir) and any(f.startswith("output") for d in os.listdir(layer_dir) for f in os.listdir(layer_dir / d))
+    out = run(29752, "--max_steps", "3", "--load_step", "2")
+    assert "finished 3 optimizer steps" in out
